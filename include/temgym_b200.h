@@ -1,0 +1,204 @@
+/*
+ * temgym_b200.h -- C ABI of the B200-native TemGymCore hot path.
+ *
+ * The reference (TemGym/TemGymCore, pure Python on JAX) has no plugin / FFI layer;
+ * its hot path is reached through Python calls.  Each entry point below states the
+ * reference call it replaces (file:line relative to the reference repository).
+ * The Python package `temgymcore_b200` binds these symbols with ctypes; a JAX user
+ * would bind the same symbols through jax.ffi.
+ *
+ * Conventions
+ *  - plain C types only; no torch / XLA types.
+ *  - `*_f64` / `tg_field_*` entry points take DEVICE pointers owned by the caller and
+ *    enqueue work on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *    stream).  They are asynchronous and retain no pointer after return.
+ *  - `*_host` entry points take HOST pointers (pinned or pageable), do the H2D copy,
+ *    the kernels and the D2H copy themselves, and return after the result is in the
+ *    host buffers.
+ *  - return value 0 = ok, negative = error (TG_E*); tg_last_error() gives a
+ *    thread-local message.  No CPU fallback exists: without a CUDA device every
+ *    compute entry point returns TG_ECUDA.
+ *  - state vector order everywhere: [x, y, dx, dy, z, pathlength, _one]
+ *    (reference src/temgym_core/ray.py:39-45).
+ */
+#ifndef TEMGYM_B200_H
+#define TEMGYM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_ABI_VERSION 1
+
+/* error codes */
+#define TG_OK 0
+#define TG_EINVAL (-1)        /* bad argument */
+#define TG_ECUDA (-2)         /* CUDA runtime error (message in tg_last_error) */
+#define TG_ENOTSEPARABLE (-3) /* tg_field_sum_separable: a beamlet has an xy cross term */
+#define TG_EUNSUPPORTED (-4)
+
+/* ---- model descriptor --------------------------------------------------- */
+
+#define TG_MAX_COMPS 24
+#define TG_NPARAM 26
+
+/* opcodes: one per reference component class on the path */
+enum tg_op {
+  TG_OP_PLANE = 0,     /* Plane / Detector / ScanGrid / Source: identity
+                          (components.py:133-134, 248-249, 405-406; source.py:21-34) */
+  TG_OP_LENS = 1,      /* Lens                (components.py:161-174)  p[0]=focal_length */
+  TG_OP_DEFLECTOR = 2, /* Deflector           (components.py:476-482)  p[0]=def_x p[1]=def_y */
+  TG_OP_BIPRISM = 3,   /* Biprism             (components.py:553-559)  p[0]=def_x */
+  TG_OP_KRIVANEK = 4,  /* AberratedLensKrivanek (components.py:192-215; aberrations.py:42-108)
+                          p[0]=focal_length, p[1..25]=KrivanekCoeffs in field order */
+  TG_OP_OFFSET = 5,    /* Scanner / Descanner (components.py:279-285, 343-372)
+                          p[0..3] = offsets added to x, y, dx, dy times _one */
+  TG_OP_THICKLENS = 6, /* ThickLens           (components.py:431-452)  p[0]=focal_length,
+                          p[1]=z_po - z_pi ; z = z_po */
+  TG_OP_ROTATOR = 7    /* Rotator             (components.py:503-523)  p[0]=cos p[1]=sin */
+};
+
+/* flags */
+#define TG_F_NOPROP 1 /* do not insert the free-space step before this component
+                         (used to expose run_iter's individual steps, run.py:75-82) */
+#define TG_F_DIST 2   /* `z` holds a fixed propagation DISTANCE instead of a plane position:
+                         Propagator(distance, FreeSpaceParaxial) (propagator.py:22-40) */
+
+typedef struct {
+  int32_t op;
+  int32_t flags;
+  double z; /* component.z : free space of (z - ray.z) is inserted first, also when 0
+               (run.py:76-80; propagator.py:52-72) */
+  double p[TG_NPARAM];
+} tg_comp;
+
+typedef struct {
+  int32_t n_comp;
+  int32_t reserved;
+  tg_comp comp[TG_MAX_COMPS];
+} tg_model;
+
+/* Ray input: SoA.  ptr[i] == NULL means "field i is the scalar value[i] for every ray"
+ * (a reference Ray may mix Python floats and arrays, ray.py:58-77; source.py:73-79). */
+typedef struct {
+  const double *ptr[7];
+  double value[7];
+} tg_ray_in;
+
+/* Jacobian layouts for tg_trace_f64 */
+#define TG_JAC_NONE 0   /* rays only                    == run_to_end (run.py:85-116) */
+#define TG_JAC_ABCD5 1  /* jac = n*25 doubles, (n,5,5) row-major over [x,y,dx,dy,_one]
+                           == vmap(jacobian(run_to_end)) + custom_jacobian_matrix
+                           (gaussian.py:234-239; utils.py:7-43) */
+#define TG_JAC_FULL7 2  /* jac = n*49 doubles, (n,7,7): d out_i / d in_j over all seven
+                           Ray leaves == the full Ray-of-Ray pytree of jax.jacobian
+                           (README.md:227-234) */
+
+const char *tg_last_error(void);
+int tg_abi_version(void);
+/* number of visible CUDA devices, or TG_ECUDA */
+int tg_device_count(void);
+
+/* ---- K1: batched ray propagation + Jacobian ------------------------------ */
+/* replaces run_to_end / run_iter steps / jax.jacobian(run_to_end) / solve_model steps
+ * (run.py:47-116, 150-179).  out[i] may be NULL to skip field i. */
+int tg_trace_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in,
+                 double *const out[7], double *jac, int jac_layout, void *stream);
+
+/* host-buffer variant: pointers in `in`, `out`, `jac` are HOST memory. */
+int tg_trace_f64_host(const tg_model *model_host, int64_t n, const tg_ray_in *in,
+                      double *const out[7], double *jac, int jac_layout, int device);
+
+/* ---- K5: metres -> pixels ------------------------------------------------ */
+/* replaces Grid.metres_to_pixels(cast=True) (grid.py:120-153) given the inverse 3x3
+ * m2px (row-major, acting on [y_m, x_m, 1], grid.py:50-63).  Evaluation order
+ * (m[0]*y + m[1]*x) + m[2] without FMA contraction; round half to even; saturating;
+ * NaN -> 0.  With as_float != 0 writes doubles (cast=False) into py/px instead. */
+int tg_metres_to_pixels(int64_t n, const double *x, const double *y, const double m2px[9],
+                        void *py, void *px, int as_float, void *stream);
+int tg_metres_to_pixels_host(int64_t n, const double *x, const double *y,
+                             const double m2px[9], void *py, void *px, int as_float,
+                             int device);
+
+/* Grid.into_image (grid.py:231-280; utils.py:83-114): bounds-checked scatter-add of
+ * 1 per ray into an int64 image of shape (H, W). */
+int tg_into_image_i64(int64_t n, const int32_t *py, const int32_t *px, int H, int W,
+                      long long *image, void *stream);
+
+/* ---- K2: per-beamlet coefficient builder --------------------------------- */
+/* Collapses _beam_field (gaussian.py:276-316) + Qinv_ABCD (gaussian.py:92-96) to a
+ * complex quadratic in the observation point (x, y) [metres]:
+ *   field_n(x,y) = exp(i * P_n),  P_n = c0 + c1 x + c2 y + c3 x^2 + c4 x y + c5 y^2
+ * poly[n*12 + 2*j + {0,1}] = Re/Im c_j.  All arrays are DEVICE fp64; complex inputs
+ * are interleaved (re,im).  Shapes as propagate_misaligned_gaussian_jax_scan
+ * (gaussian.py:319-337): amp,phase_offset,k (nb,); Q1_inv (nb,2,2) complex;
+ * A,B,C,D (nb,2,2); e,f,r1m,theta1m (nb,2). */
+int tg_beamlet_coeffs_f64(int64_t nb, const double *amp, const double *phase_offset,
+                          const double *Q1_inv, const double *A, const double *B,
+                          const double *C, const double *D, const double *e,
+                          const double *f, const double *r1m, const double *theta1m,
+                          const double *k, double *poly, void *stream);
+
+/* Same, but reads A,B,C,D,e,f from the (nb,5,5) ABCD array K1 wrote (gaussian.py:244-249). */
+int tg_beamlet_coeffs_abcd_f64(int64_t nb, const double *amp, const double *phase_offset,
+                               const double *Q1_inv, const double *abcd, const double *r1m_x,
+                               const double *r1m_y, const double *th_x, const double *th_y,
+                               const double *k, double *poly, void *stream);
+
+/* _input_beam_field (gaussian.py:402-407) in the same 6-coefficient format. */
+int tg_input_coeffs_f64(int64_t nb, const double *amp, const double *phase_offset,
+                        const double *Q1_inv, const double *r1m, const double *theta1m,
+                        const double *k, double *poly, void *stream);
+
+/* GaussianRay.Q_inv (gaussian.py:138-177): (nb,2,2) complex from waists, radii, theta. */
+int tg_gaussian_qinv_f64(int64_t nb, const double *waist_xy, const double *radii_xy,
+                         const double *wavelength, const double *theta, double *Q_inv,
+                         void *stream);
+
+/* k = 2 pi / wavelength and phase_offset = k * pathlength (gaussian.py:253-255). */
+int tg_wave_numbers_f64(int64_t nb, const double *wavelength, const double *pathlength,
+                        double *k, double *phase_offset, void *stream);
+
+/* ---- K3: field sum -------------------------------------------------------- */
+/* replaces map_reduce(_beam_field_outer, add) (gaussian.py:325-332, 340-369).
+ * Grid form: observation points are the pixel centres of an (H, W) grid with
+ *   x_m = px2m[0] + px2m[1]*col + px2m[2]*row,  y_m = px2m[3] + px2m[4]*col + px2m[5]*row
+ * (Grid.coords, grid.py:82-100).  Computes rows [row0, row0+nrows) and writes them to
+ * out[(row-row0)*W + col] as complex64 (out_is_c128 == 0) or complex128.
+ * cull_bits > 0 enables tile-level culling of beamlets whose envelope over the whole
+ * tile is below 2^-cull_bits of the brightest beamlet peak; 0 = dense (every beamlet
+ * evaluated on every pixel).  n_evals_out (host pointer, may be NULL) receives the
+ * number of executed beamlet*pixel evaluations (synchronises the stream if non-NULL). */
+int tg_field_sum_grid(int64_t nb, const double *poly, const double px2m[6], int H, int W,
+                      int row0, int nrows, void *out, int out_is_c128, int cull_bits,
+                      long long *n_evals_out, void *stream);
+
+/* Arbitrary observation points r (npts,2) (x,y) [metres], device fp64: the r2 argument
+ * of propagate_misaligned_gaussian_jax_scan (gaussian.py:319-337). */
+int tg_field_sum_points(int64_t nb, const double *poly, int64_t npts, const double *r_xy,
+                        void *out, int out_is_c128, void *stream);
+
+/* Tensor-core path for separable beamlets (cross term c4 == 0 for every beamlet and an
+ * axis-aligned grid).  Returns TG_ENOTSEPARABLE otherwise. */
+int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6], int H,
+                           int W, int row0, int nrows, void *out, int out_is_c128,
+                           void *stream);
+
+/* ---- host-buffer field sum (make_gaussian_image end to end, gaussian.py:225-273) -- */
+/* All pointers HOST.  rays[7] are the central rays (length nb each), waist_xy /
+ * radii_xy (nb,2), wavelength / theta / amplitude (nb,).  Traces the rays through
+ * `model`, builds Q_inv, the coefficients, sums the field on the (H,W) grid given by
+ * px2m and writes complex128 (H,W) to out. */
+int tg_make_gaussian_image_host(const tg_model *model_host, int64_t nb,
+                                const double *const rays[7], const double *amplitude,
+                                const double *waist_xy, const double *radii_xy,
+                                const double *wavelength, const double *theta,
+                                const double px2m[6], int H, int W, void *out,
+                                int out_is_c128, int cull_bits, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEMGYM_B200_H */

@@ -1,0 +1,206 @@
+"""Optical components (reference ``src/temgym_core/components.py``).
+
+Plain frozen dataclasses with the reference's field names, order and defaults.  A component
+carries parameters only; its ray arithmetic lives in the CUDA ray kernel
+(``csrc/trace.cu``), selected through the opcode returned by ``_tg_spec``.  Calling a
+component on a ray launches that kernel for the single step (no free-space insertion),
+like the reference's ``component(ray)``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, NamedTuple
+
+import numpy as np
+
+from . import Degrees
+from . import _lib as L
+from .aberrations import KrivanekCoeffs
+from .grid import Grid
+from .tree_utils import HasParamsMixin
+
+
+def _f(v) -> float:
+    """Component parameters are scalars (the model descriptor lives in kernel-parameter
+    constant memory); arrays of per-ray parameters are not part of this path."""
+    try:
+        return float(v)
+    except Exception as exc:  # noqa: BLE001
+        raise TypeError(f"component parameter must be a scalar, got {type(v).__name__}") from exc
+
+
+class Component(HasParamsMixin):
+    """Base component (components.py:12-24)."""
+
+    def _tg_spec(self):
+        """-> (opcode, z, params tuple) for the model descriptor."""
+        raise NotImplementedError(
+            f"{type(self).__name__} has no CUDA implementation; only the components of the "
+            "accelerated path can be used in a model (no Python fallback)")
+
+    def __call__(self, ray):
+        from .run import _apply_component_only
+        return _apply_component_only(ray, self)
+
+
+class DescanError(NamedTuple):  # components.py:27-115
+    pxo_pxi: float = 0.0
+    pxo_pyi: float = 0.0
+    pyo_pxi: float = 0.0
+    pyo_pyi: float = 0.0
+    sxo_pxi: float = 0.0
+    sxo_pyi: float = 0.0
+    syo_pxi: float = 0.0
+    syo_pyi: float = 0.0
+    offpxi: float = 0.0
+    offpyi: float = 0.0
+    offsxi: float = 0.0
+    offsyi: float = 0.0
+
+    def as_array(self) -> np.ndarray:
+        return np.array(self)
+
+    def as_matrix(self) -> np.ndarray:
+        # components.py:105-115, including the reference's offsyi-twice quirk (row 3)
+        return np.array([
+            [self.pxo_pxi, self.pxo_pyi, 0.0, 0.0, self.offpxi],
+            [self.pyo_pxi, self.pyo_pyi, 0.0, 0.0, self.offpyi],
+            [self.sxo_pxi, self.sxo_pyi, 0.0, 0.0, self.offsyi],
+            [self.syo_pxi, self.syo_pyi, 0.0, 0.0, self.offsyi],
+            [0.0, 0.0, 0.0, 0.0, 1.0],
+        ])
+
+
+@dataclass(frozen=True)
+class Plane(Component):  # components.py:118-134
+    z: float
+
+    def _tg_spec(self):
+        return L.TG_OP_PLANE, _f(self.z), ()
+
+
+@dataclass(frozen=True)
+class Lens(Component):  # components.py:137-174
+    z: float
+    focal_length: float
+
+    def _tg_spec(self):
+        return L.TG_OP_LENS, _f(self.z), (_f(self.focal_length),)
+
+
+@dataclass(frozen=True)
+class AberratedLensKrivanek(Lens):  # components.py:177-215
+    coeffs: Any = field(default_factory=KrivanekCoeffs)
+
+    def _tg_spec(self):
+        c = self.coeffs
+        if isinstance(c, dict):
+            c = KrivanekCoeffs(**c)
+        return L.TG_OP_KRIVANEK, _f(self.z), (_f(self.focal_length),) + tuple(_f(v) for v in c.as_tuple())
+
+
+@dataclass(frozen=True)
+class ScanGrid(Component, Grid):  # components.py:218-249
+    z: float
+    pixel_size: Any
+    shape: Any
+    rotation: Degrees = 0.
+    centre: Any = (0., 0)
+    flip_y: bool = False
+
+    def _tg_spec(self):
+        return L.TG_OP_PLANE, _f(self.z), ()
+
+
+@dataclass(frozen=True)
+class Scanner(Component):  # components.py:252-285
+    z: float
+    scan_pos_x: float
+    scan_pos_y: float
+    scan_tilt_x: float = 0.
+    scan_tilt_y: float = 0.
+
+    def _tg_spec(self):
+        return L.TG_OP_OFFSET, _f(self.z), (_f(self.scan_pos_x), _f(self.scan_pos_y),
+                                            _f(self.scan_tilt_x), _f(self.scan_tilt_y))
+
+
+@dataclass(frozen=True)
+class Descanner(Component):  # components.py:288-372
+    z: float
+    scan_pos_x: float
+    scan_pos_y: float
+    scan_tilt_x: float = 0.
+    scan_tilt_y: float = 0.
+    descan_error: DescanError = DescanError()
+
+    def _tg_spec(self):
+        de = self.descan_error
+        sp_x, sp_y = _f(self.scan_pos_x), _f(self.scan_pos_y)
+        st_x, st_y = _f(self.scan_tilt_x), _f(self.scan_tilt_y)
+        # the four 5th-column offsets, same operation order as components.py:343-372
+        return L.TG_OP_OFFSET, _f(self.z), (
+            sp_x * _f(de.pxo_pxi) + sp_y * _f(de.pxo_pyi) + _f(de.offpxi) - sp_x,
+            sp_x * _f(de.pyo_pxi) + sp_y * _f(de.pyo_pyi) + _f(de.offpyi) - sp_y,
+            sp_x * _f(de.sxo_pxi) + sp_y * _f(de.sxo_pyi) + _f(de.offsxi) - st_x,
+            sp_x * _f(de.syo_pxi) + sp_y * _f(de.syo_pyi) + _f(de.offsyi) - st_y,
+        )
+
+
+@dataclass(frozen=True)
+class Detector(Component, Grid):  # components.py:375-406
+    z: float
+    pixel_size: Any
+    shape: Any
+    rotation: Degrees = 0.
+    centre: Any = (0., 0)
+    flip_y: bool = False
+
+    def _tg_spec(self):
+        return L.TG_OP_PLANE, _f(self.z), ()
+
+
+@dataclass(frozen=True)
+class ThickLens(Component):  # components.py:409-452
+    z_po: float
+    z_pi: float
+    focal_length: float
+
+    @property
+    def z(self):
+        return self.z_po
+
+    def _tg_spec(self):
+        return L.TG_OP_THICKLENS, _f(self.z_po), (_f(self.focal_length), _f(self.z_po) - _f(self.z_pi))
+
+
+@dataclass(frozen=True)
+class Deflector(Component):  # components.py:455-482
+    z: float
+    def_x: float
+    def_y: float
+
+    def _tg_spec(self):
+        return L.TG_OP_DEFLECTOR, _f(self.z), (_f(self.def_x), _f(self.def_y))
+
+
+@dataclass(frozen=True)
+class Rotator(Component):  # components.py:485-523
+    z: float
+    angle: Degrees
+
+    def _tg_spec(self):
+        a = np.deg2rad(_f(self.angle))
+        return L.TG_OP_ROTATOR, _f(self.z), (float(np.cos(a)), float(np.sin(a)))
+
+
+@dataclass(frozen=True)
+class Biprism(Component):  # components.py:526-559 (offset, rotation, side are unused there too)
+    z: float
+    offset: float = 0.0
+    rotation: Degrees = 0.0
+    def_x: float = 0.0
+    side: int = 1
+
+    def _tg_spec(self):
+        return L.TG_OP_BIPRISM, _f(self.z), (_f(self.def_x),)

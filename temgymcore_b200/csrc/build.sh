@@ -1,0 +1,21 @@
+#!/usr/bin/env bash
+# Builds libtemgym_b200.so (sm_100a only) next to the Python package.
+# trace.cu / coeffs.cu: -fmad=false (bit-faithful fp64, see the file headers); field.cu: FMA on.
+set -euo pipefail
+here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+root="$(cd "$here/../.." && pwd)"
+out="$here/../libtemgym_b200.so"
+obj="$here/_obj"
+mkdir -p "$obj"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$root/include -I$here $ARCH"
+VERBOSE="${TG_PTXAS_V:+-Xptxas -v}"
+pids=()
+$NVCC $COMMON $VERBOSE -fmad=false -c "$here/trace.cu"    -o "$obj/trace.o" & pids+=($!)
+$NVCC $COMMON $VERBOSE -fmad=false -c "$here/coeffs.cu"   -o "$obj/coeffs.o" & pids+=($!)
+$NVCC $COMMON $VERBOSE             -c "$here/field.cu"    -o "$obj/field.o" & pids+=($!)
+$NVCC $COMMON $VERBOSE             -c "$here/host_api.cu" -o "$obj/host_api.o" & pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+$NVCC $ARCH -shared -o "$out" "$obj/trace.o" "$obj/coeffs.o" "$obj/field.o" "$obj/host_api.o" -cudart static
+echo "built $out"

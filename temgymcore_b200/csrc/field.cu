@@ -1,0 +1,518 @@
+// K3: the Gaussian-beamlet field sum  F[p] = sum_n exp(i P_n(p))  on sm_100a.
+//
+// Replaces map_reduce(_beam_field_outer, jnp.add, ...) of the reference
+// (src/temgym_core/gaussian.py:319-369) -- every complex Gaussian on every pixel.
+//
+// Design (SFU-bound; 3 MUFU per beamlet*pixel: sin, cos, ex2):
+//  * prep kernel: metre-space complex quadratic (K2 output) -> pixel-space table, phase in
+//    TURNS (Re P / 2pi) and envelope in BITS (-Im P * log2 e), fp64, 96 B per beamlet.
+//  * main kernel: a CTA owns a TR x TC pixel tile and streams the beamlet table through
+//    shared memory in chunks, double-buffered with 1-D bulk async copies issued to the TMA
+//    unit (cp.async.bulk ... mbarrier::complete_tx).  One thread per beamlet re-centres the
+//    chunk's polynomials on the tile origin in fp64, reduces the phase coefficients mod 1
+//    (they only ever multiply integers), optionally culls beamlets whose envelope over the
+//    whole tile is negligible, and writes compact tile-local records.
+//  * every thread owns a strip of L consecutive pixels of one row.  Per (thread, beamlet) it
+//    evaluates the strip-start phase and first difference in fp64 and converts them to
+//    32-bit FIXED-POINT turns; along the strip the phase advances by exact integer second
+//    differences (wrap-around mod 1 turn is free), the top 23 bits become an fp32 angle in
+//    [-pi, pi) for MUFU.SIN/COS, the envelope is a 2-FFMA Horner in fp32 for MUFU.EX2.
+//  * fp32 partial sums over one chunk (<= 128 terms) are flushed into fp64 accumulators held
+//    in shared memory, so accumulation error does not grow with the number of beamlets.
+//  * grid = tiles x beamlet-splits, split count chosen so the CTA count fills whole waves
+//    of 148 SMs x 2 resident CTAs; split partials are reduced by a second tiny kernel in a
+//    fixed order (deterministic, no atomics on the data path).
+#include <math.h>
+#include "tg_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kChunk = 128;          // beamlets per staged chunk
+constexpr int kRecDoubles = 14;      // tile-local record: 6 phase + 6 envelope + {dd,g2} + pad
+constexpr double kMagic = 1572864.0; // 1.5 * 2^20: ulp = 2^-32 -> low mantissa word = frac * 2^32
+constexpr double kInv2Pi = 0.15915494309189533577;
+constexpr double kLog2e = 1.4426950408889634074;
+
+struct FieldGeom {
+  int H, W;          // full detector
+  int row0, nrows;   // rows computed by this call
+  int tiles_x, tiles_y;
+  int nsplit;
+  long long nb;
+  int cull_bits;
+};
+
+// ---- ordered-uint encoding of doubles for atomicMin ---------------------------------
+__device__ __forceinline__ unsigned long long enc_ordered(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double dec_ordered(unsigned long long k) {
+  unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+// minimum of a convex quadratic g(u,v) = G0 + G1 v + G2 u + G3 v^2 + G4 u v + G5 u^2 over the
+// rectangle v in [0,V], u in [0,U].  Returns -inf when g is not convex (never cull then).
+__device__ __forceinline__ double min1d(double a, double b, double c, double S) {
+  // min over s in [0,S] of a + b s + c s^2
+  double s = 0.0;
+  if (c > 0.0) {
+    s = fmin(fmax(-b / (2.0 * c), 0.0), S);
+  } else {
+    s = (b * S + c * S * S < 0.0) ? S : 0.0;
+  }
+  return a + s * (b + c * s);
+}
+__device__ __forceinline__ double quad_min_rect(const double *G, double U, double V) {
+  const double G0 = G[0], G1 = G[1], G2 = G[2], G3 = G[3], G4 = G[4], G5 = G[5];
+  const double det = 4.0 * G3 * G5 - G4 * G4;
+  if (!(G3 >= 0.0 && G5 >= 0.0 && det >= 0.0)) return -INFINITY;
+  if (det > 0.0) {
+    const double vs = (-2.0 * G5 * G1 + G4 * G2) / det;
+    const double us = (-2.0 * G3 * G2 + G4 * G1) / det;
+    if (vs >= 0.0 && vs <= V && us >= 0.0 && us <= U) return G0 + 0.5 * (G1 * vs + G2 * us);
+  }
+  double m = min1d(G0, G2, G5, U);                                   // v = 0
+  m = fmin(m, min1d(G0 + V * (G1 + G3 * V), G2 + G4 * V, G5, U));    // v = V
+  m = fmin(m, min1d(G0, G1, G3, V));                                 // u = 0
+  m = fmin(m, min1d(G0 + U * (G2 + G5 * U), G1 + G4 * U, G3, V));    // u = U
+  return m;
+}
+
+// ---- prep: metre-space poly -> pixel-space table ------------------------------------
+// poly: c0..c5 complex (radians) in (x,y) metres.  x = X0 + Xc col + Xr row, y likewise.
+// table[n] = {T0..T5 (turns), E0..E5 (bits, = -Im * log2e)} over (col,row):
+//   a0 + a1 col + a2 row + a3 col^2 + a4 col row + a5 row^2
+__global__ void __launch_bounds__(128)
+    prep_kernel(long long nb, const double *__restrict__ poly, double X0, double Xc, double Xr,
+                double Y0, double Yc, double Yr, int H, int W, double *__restrict__ table,
+                unsigned long long *__restrict__ gref_key) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const double *c = poly + i * 12;
+  double a[2][6];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const double c0 = c[0 + p], c1 = c[2 + p], c2 = c[4 + p], c3 = c[6 + p], c4 = c[8 + p],
+                 c5 = c[10 + p];
+    a[p][3] = c3 * Xc * Xc + c4 * Xc * Yc + c5 * Yc * Yc;
+    a[p][5] = c3 * Xr * Xr + c4 * Xr * Yr + c5 * Yr * Yr;
+    a[p][4] = 2.0 * c3 * Xc * Xr + c4 * (Xc * Yr + Xr * Yc) + 2.0 * c5 * Yc * Yr;
+    a[p][1] = c1 * Xc + c2 * Yc + 2.0 * c3 * X0 * Xc + c4 * (X0 * Yc + Y0 * Xc) + 2.0 * c5 * Y0 * Yc;
+    a[p][2] = c1 * Xr + c2 * Yr + 2.0 * c3 * X0 * Xr + c4 * (X0 * Yr + Y0 * Xr) + 2.0 * c5 * Y0 * Yr;
+    a[p][0] = c0 + c1 * X0 + c2 * Y0 + c3 * X0 * X0 + c4 * X0 * Y0 + c5 * Y0 * Y0;
+  }
+  double *t = table + i * 12;
+  double G[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    t[j] = a[0][j] * kInv2Pi;
+    G[j] = a[1][j] * kLog2e;   // envelope exponent in bits: |field| = 2^-g
+    t[6 + j] = -G[j];
+  }
+  if (gref_key) {
+    const double gmin = quad_min_rect(G, (double)(H - 1), (double)(W - 1));
+    if (isfinite(gmin)) atomicMin(gref_key, enc_ordered(gmin));
+  }
+}
+
+// ---- main tiled kernel ----------------------------------------------------------------
+struct __align__(16) Rec {
+  double th[6];   // tile-local phase coefficients, turns, reduced to [-0.5, 0.5]
+  double en[6];   // tile-local envelope coefficients (bits, amplitude = 2^en(u,v))
+  uint32_t dd;    // second difference of the phase along a row, fixed point 2^-32 turn
+  float e2;       // en[3] as fp32
+  double pad;
+};
+static_assert(sizeof(Rec) == kRecDoubles * 8, "record size");
+
+template <int L, int SPR>
+struct FieldSmem {
+  static constexpr int TC = L * SPR;
+  static constexpr int TR = kThreads / SPR;
+  alignas(128) double raw[2][kChunk * 12];
+  alignas(16) Rec rec[kChunk];
+  alignas(16) double acc[2 * L * kThreads];  // [component][j][thread]
+  alignas(8) uint64_t full[2];
+  int warp_cnt[kChunk / 32];
+  int n_active;
+};
+
+template <int L, int SPR>
+__global__ void __launch_bounds__(kThreads, 2)
+    field_grid_kernel(const double *__restrict__ table, const FieldGeom g,
+                      const unsigned long long *__restrict__ gref_key, void *__restrict__ out,
+                      int out_is_c128, double2 *__restrict__ partial,
+                      unsigned long long *__restrict__ evals) {
+  using S = FieldSmem<L, SPR>;
+  constexpr int TC = S::TC, TR = S::TR;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  S &sm = *reinterpret_cast<S *>(smem_raw);
+
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int split = blockIdx.y;
+  const int ty = tile / g.tiles_x, tx = tile % g.tiles_x;
+  const int r0 = g.row0 + ty * TR;   // tile origin in full-detector pixel coordinates
+  const int c0 = tx * TC;
+  const int u = tid / SPR;           // row inside tile
+  const int v0 = (tid % SPR) * L;    // first column of this thread's strip inside the tile
+
+  // beamlet range of this split
+  const long long per = (g.nb + g.nsplit - 1) / g.nsplit;
+  const long long b_begin = (long long)split * per;
+  const long long b_end = b_begin + per < g.nb ? b_begin + per : g.nb;
+  const int nchunks = b_end > b_begin ? (int)((b_end - b_begin + kChunk - 1) / kChunk) : 0;
+
+  if (tid == 0) {
+    tg_mbar_init(&sm.full[0], 1);
+    tg_mbar_init(&sm.full[1], 1);
+    tg_fence_mbar_init();
+  }
+#pragma unroll
+  for (int j = 0; j < 2 * L; ++j) sm.acc[j * kThreads + tid] = 0.0;
+  __syncthreads();
+
+  auto issue = [&](int c) {
+    const long long b = b_begin + (long long)c * kChunk;
+    const int cnt = (int)((b_end - b) < kChunk ? (b_end - b) : kChunk);
+    const uint32_t bytes = (uint32_t)cnt * 96u;
+    tg_mbar_expect_tx(&sm.full[c & 1], bytes);
+    tg_bulk_g2s(sm.raw[c & 1], table + b * 12, bytes, &sm.full[c & 1]);
+  };
+  if (tid == 0 && nchunks > 0) issue(0);
+
+  // per-thread strip constants (exact small integers in fp64)
+  const double ud = (double)u, vd = (double)v0;
+  const double uu = ud * ud, uv = ud * vd, vv = vd * vd, tv1 = 2.0 * vd + 1.0, tv = 2.0 * vd;
+
+  double thr_bits = INFINITY;  // cull when min envelope exponent g over tile > thr_bits
+  if (g.cull_bits > 0 && gref_key) {
+    const unsigned long long key = *gref_key;
+    if (key != ~0ULL) thr_bits = dec_ordered(key) + (double)g.cull_bits;
+  }
+
+  float pr[L], pi[L];
+#pragma unroll
+  for (int j = 0; j < L; ++j) { pr[j] = 0.f; pi[j] = 0.f; }
+  unsigned long long my_active = 0;
+
+  for (int c = 0; c < nchunks; ++c) {
+    if (tid == 0 && c + 1 < nchunks) issue(c + 1);
+    tg_mbar_wait(&sm.full[c & 1], (uint32_t)((c >> 1) & 1));
+
+    // ---- stage: one thread per beamlet re-centres on the tile origin, culls, compacts
+    const long long b = b_begin + (long long)c * kChunk;
+    const int cnt = (int)((b_end - b) < kChunk ? (b_end - b) : kChunk);
+    bool keep = false;
+    Rec rec;
+    if (tid < cnt) {
+      const double *a = sm.raw[c & 1] + tid * 12;
+      const double cc = (double)c0, rr = (double)r0;
+      // phase, turns
+      double t0 = a[0] + cc * (a[1] + a[3] * cc + a[4] * rr) + rr * (a[2] + a[5] * rr);
+      double t1 = a[1] + 2.0 * a[3] * cc + a[4] * rr;
+      double t2 = a[2] + 2.0 * a[5] * rr + a[4] * cc;
+      double t3 = a[3], t4 = a[4], t5 = a[5];
+      rec.th[0] = t0 - rint(t0);
+      rec.th[1] = t1 - rint(t1);
+      rec.th[2] = t2 - rint(t2);
+      rec.th[3] = t3 - rint(t3);
+      rec.th[4] = t4 - rint(t4);
+      rec.th[5] = t5 - rint(t5);
+      const double dd = 2.0 * rec.th[3];
+      rec.dd = (uint32_t)__double2loint(dd + kMagic);
+      // envelope, bits (amplitude = 2^e)
+      const double *e = a + 6;
+      rec.en[0] = e[0] + cc * (e[1] + e[3] * cc + e[4] * rr) + rr * (e[2] + e[5] * rr);
+      rec.en[1] = e[1] + 2.0 * e[3] * cc + e[4] * rr;
+      rec.en[2] = e[2] + 2.0 * e[5] * rr + e[4] * cc;
+      rec.en[3] = e[3];
+      rec.en[4] = e[4];
+      rec.en[5] = e[5];
+      rec.e2 = (float)e[3];
+      rec.pad = 0.0;
+      keep = true;
+      if (thr_bits < INFINITY) {
+        double G[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) G[j] = -rec.en[j];
+        const double gmin = quad_min_rect(G, (double)(TR - 1), (double)(TC - 1));
+        keep = !(gmin > thr_bits);  // NaN keeps
+      }
+    }
+    int n_active;
+    if (thr_bits < INFINITY) {
+      // order-preserving compaction (determinism: beamlets stay in natural order)
+      const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+      const int warp = tid >> 5, lane = tid & 31;
+      if (warp < kChunk / 32 && lane == 0) sm.warp_cnt[warp] = __popc(ballot);
+      __syncthreads();
+      if (warp < kChunk / 32) {
+        int base = 0;
+#pragma unroll
+        for (int w = 0; w < kChunk / 32; ++w) base += (w < warp) ? sm.warp_cnt[w] : 0;
+        if (keep) sm.rec[base + __popc(ballot & ((1u << lane) - 1u))] = rec;
+      }
+      if (tid == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kChunk / 32; ++w) tot += sm.warp_cnt[w];
+        sm.n_active = tot;
+      }
+      __syncthreads();
+      n_active = sm.n_active;
+    } else {
+      if (keep) sm.rec[tid] = rec;
+      __syncthreads();
+      n_active = cnt;
+    }
+    my_active += (unsigned long long)n_active;
+
+    // ---- evaluate: every thread, its strip of L pixels, all active beamlets of the chunk
+    for (int n = 0; n < n_active; ++n) {
+      const Rec &q = sm.rec[n];
+      // strip-start phase and first difference (turns), fp64 -> 2^-32 fixed point
+      const double th0 = q.th[0] + q.th[1] * vd + q.th[2] * ud + q.th[3] * vv + q.th[4] * uv + q.th[5] * uu;
+      const double dl0 = q.th[1] + q.th[3] * tv1 + q.th[4] * ud;
+      const uint32_t t0 = (uint32_t)__double2loint(th0 + kMagic) + 0x100u;  // +0.5 ulp of the 23-bit angle
+      const uint32_t d0 = (uint32_t)__double2loint(dl0 + kMagic);
+      const uint32_t dd = q.dd;
+      // strip-local envelope Horner (bits): e(j) = e0 + j (e1 + j e2)
+      const float e0 = (float)(q.en[0] + q.en[1] * vd + q.en[2] * ud + q.en[3] * vv + q.en[4] * uv + q.en[5] * uu);
+      const float e1 = (float)(q.en[1] + q.en[3] * tv + q.en[4] * ud);
+      const float e2 = q.e2;
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        const uint32_t tj = t0 + (uint32_t)j * d0 + (uint32_t)(j * (j - 1) / 2) * dd;
+        const float ft = __uint_as_float((tj >> 9) | 0x3f800000u);       // 1 + frac(turns)
+        const float ang = fmaf(ft, 6.28318530717958648f, -9.42477796076937972f);  // 2pi frac - pi
+        const float ej = fmaf((float)j, fmaf((float)j, e2, e1), e0);
+        float amp, sn, cs;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(amp) : "f"(ej));
+        sn = __sinf(ang);
+        cs = __cosf(ang);
+        // exp(i 2pi frac) = -(cos ang + i sin ang)
+        pr[j] = fmaf(-amp, cs, pr[j]);
+        pi[j] = fmaf(-amp, sn, pi[j]);
+      }
+    }
+
+    // ---- flush fp32 chunk partials into the fp64 accumulators
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      sm.acc[j * kThreads + tid] += (double)pr[j];
+      sm.acc[(L + j) * kThreads + tid] += (double)pi[j];
+      pr[j] = 0.f;
+      pi[j] = 0.f;
+    }
+    __syncthreads();  // records and raw[c&1] are free for the next stage / TMA
+  }
+
+  // ---- write the tile
+  const int row = r0 + u;
+  const bool row_ok = row < g.row0 + g.nrows && row < g.H;
+  if (row_ok) {
+    const size_t base = (size_t)(row - g.row0) * g.W + c0 + v0;
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      if (c0 + v0 + j < g.W) {
+        const double re = sm.acc[j * kThreads + tid], im = sm.acc[(L + j) * kThreads + tid];
+        if (g.nsplit > 1) {
+          partial[(size_t)split * ((size_t)g.nrows * g.W) + base + j] = make_double2(re, im);
+        } else if (out_is_c128) {
+          static_cast<double2 *>(out)[base + j] = make_double2(re, im);
+        } else {
+          static_cast<float2 *>(out)[base + j] = make_float2((float)re, (float)im);
+        }
+      }
+    }
+  }
+  if (evals && tid == 0) {
+    const int rows_valid = min(TR, g.row0 + g.nrows - r0);
+    const int cols_valid = min(TC, g.W - c0);
+    atomicAdd(evals, my_active * (unsigned long long)(rows_valid > 0 ? rows_valid : 0) *
+                         (unsigned long long)(cols_valid > 0 ? cols_valid : 0));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    split_reduce_kernel(const double2 *__restrict__ partial, int nsplit, size_t npix,
+                        void *__restrict__ out, int out_is_c128) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  double re = 0.0, im = 0.0;
+  for (int s = 0; s < nsplit; ++s) {
+    const double2 v = partial[(size_t)s * npix + i];
+    re += v.x;
+    im += v.y;
+  }
+  if (out_is_c128) static_cast<double2 *>(out)[i] = make_double2(re, im);
+  else static_cast<float2 *>(out)[i] = make_float2((float)re, (float)im);
+}
+
+// ---- arbitrary observation points ------------------------------------------------------
+// One thread per point; beamlet polynomials (metre space, radians) streamed through smem.
+constexpr int kPtChunk = 128;
+__global__ void __launch_bounds__(128)
+    field_points_kernel(long long nb, const double *__restrict__ poly, long long npts,
+                        const double *__restrict__ r_xy, void *__restrict__ out, int out_is_c128) {
+  __shared__ double s_poly[kPtChunk * 12];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = i < npts;
+  const double x = ok ? r_xy[i * 2] : 0.0, y = ok ? r_xy[i * 2 + 1] : 0.0;
+  double are = 0.0, aim = 0.0;
+  for (long long b = 0; b < nb; b += kPtChunk) {
+    const int cnt = (int)((nb - b) < kPtChunk ? (nb - b) : kPtChunk);
+    __syncthreads();
+    for (int k = threadIdx.x; k < cnt * 12; k += blockDim.x) s_poly[k] = poly[b * 12 + k];
+    __syncthreads();
+    float pr = 0.f, pi = 0.f;
+    for (int n = 0; n < cnt; ++n) {
+      const double *c = s_poly + n * 12;
+      const double re = c[0] + x * (c[2] + c[6] * x + c[8] * y) + y * (c[4] + c[10] * y);
+      const double im = c[1] + x * (c[3] + c[7] * x + c[9] * y) + y * (c[5] + c[11] * y);
+      const double t = re * kInv2Pi;
+      const float fr = (float)(t - rint(t));              // turns in [-0.5, 0.5]
+      const float ang = fr * 6.28318530717958648f;
+      float amp;
+      const float ex = (float)(-im * kLog2e);
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(amp) : "f"(ex));
+      pr = fmaf(amp, __cosf(ang), pr);
+      pi = fmaf(amp, __sinf(ang), pi);
+    }
+    are += (double)pr;
+    aim += (double)pi;
+  }
+  if (ok) {
+    if (out_is_c128) static_cast<double2 *>(out)[i] = make_double2(are, aim);
+    else static_cast<float2 *>(out)[i] = make_float2((float)are, (float)aim);
+  }
+}
+
+// choose the beamlet-split count so tiles*S fills whole waves of resident CTAs
+int choose_split(long long tiles, long long nb, int slots, bool culling, size_t npix) {
+  if (tiles <= 0) return 1;
+  const long long max_by_chunks = nb / kChunk > 0 ? nb / kChunk : 1;
+  long long max_s = 32 < max_by_chunks ? 32 : max_by_chunks;
+  const size_t ws_cap = (size_t)1 << 30;  // <= 1 GiB of split partials
+  while (max_s > 1 && (size_t)max_s * npix * 16 > ws_cap) --max_s;
+  if (culling) {
+    long long s = tiles >= slots ? 1 : (slots + tiles - 1) / tiles;
+    return (int)(s < max_s ? s : max_s);
+  }
+  double best_eff = -1.0;
+  int best = 1;
+  for (long long s = 1; s <= max_s; ++s) {
+    const double waves = (double)(tiles * s) / slots;
+    const double eff = waves / ceil(waves);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = (int)s;
+    }
+  }
+  return best;
+}
+
+}  // namespace
+
+extern "C" int tg_field_sum_grid(int64_t nb, const double *poly, const double px2m[6], int H, int W,
+                                 int row0, int nrows, void *out, int out_is_c128, int cull_bits,
+                                 long long *n_evals_out, void *stream) {
+  TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad shape");
+  TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
+  TG_REQUIRE(px2m && out, "null pointer");
+  TG_REQUIRE(cull_bits >= 0 && cull_bits < 1000, "bad cull_bits");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_evals_out) *n_evals_out = 0;
+  if (nrows == 0) return TG_OK;
+  const size_t npix = (size_t)nrows * W;
+  const size_t elt = out_is_c128 ? 16 : 8;
+  if (nb == 0) {
+    TG_CUDA(cudaMemsetAsync(out, 0, npix * elt, st));
+    return TG_OK;
+  }
+  TG_REQUIRE(poly, "null poly");
+
+  constexpr int L = 16, SPR = 8;
+  using S = FieldSmem<L, SPR>;
+  FieldGeom g;
+  g.H = H; g.W = W; g.row0 = row0; g.nrows = nrows;
+  g.tiles_x = (W + S::TC - 1) / S::TC;
+  g.tiles_y = (nrows + S::TR - 1) / S::TR;
+  g.nb = nb;
+  g.cull_bits = cull_bits;
+  const long long tiles = (long long)g.tiles_x * g.tiles_y;
+  int dev = 0, sms = 148;
+  TG_CUDA(cudaGetDevice(&dev));
+  TG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  g.nsplit = choose_split(tiles, nb, 2 * sms, cull_bits > 0, npix);
+
+  // workspace: table (nb*96 B) | gref key (8) | evals (8) | split partials
+  const size_t table_bytes = (size_t)nb * 96;
+  const size_t part_bytes = g.nsplit > 1 ? (size_t)g.nsplit * npix * 16 : 0;
+  unsigned char *ws = nullptr;
+  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), table_bytes + 256 + part_bytes, st));
+  double *table = reinterpret_cast<double *>(ws);
+  unsigned long long *gref = reinterpret_cast<unsigned long long *>(ws + table_bytes);
+  unsigned long long *evals = gref + 1;
+  double2 *partial = part_bytes ? reinterpret_cast<double2 *>(ws + table_bytes + 256) : nullptr;
+  TG_CUDA(cudaMemsetAsync(gref, 0xFF, 8, st));
+  TG_CUDA(cudaMemsetAsync(evals, 0, 8, st));
+
+  prep_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(
+      nb, poly, px2m[0], px2m[1], px2m[2], px2m[3], px2m[4], px2m[5], H, W, table,
+      cull_bits > 0 ? gref : nullptr);
+  int rc = tg_launch_check("prep_kernel");
+  if (rc == TG_OK) {
+    const size_t smem = sizeof(S);
+    cudaError_t e = cudaFuncSetAttribute(field_grid_kernel<L, SPR>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      tg_set_error("cudaFuncSetAttribute(field_grid_kernel): %s", cudaGetErrorString(e));
+      rc = TG_ECUDA;
+    } else {
+      dim3 grid((unsigned)tiles, (unsigned)g.nsplit);
+      field_grid_kernel<L, SPR><<<grid, kThreads, smem, st>>>(
+          table, g, cull_bits > 0 ? gref : nullptr, out, out_is_c128, partial,
+          n_evals_out ? evals : nullptr);
+      rc = tg_launch_check("field_grid_kernel");
+      if (rc == TG_OK && g.nsplit > 1) {
+        split_reduce_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(partial, g.nsplit, npix,
+                                                                           out, out_is_c128);
+        rc = tg_launch_check("split_reduce_kernel");
+      }
+    }
+  }
+  if (rc == TG_OK && n_evals_out) {
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, evals, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      tg_set_error("n_evals readback: %s", cudaGetErrorString(e));
+      rc = TG_ECUDA;
+    } else {
+      *n_evals_out = (long long)h;
+    }
+  }
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
+extern "C" int tg_field_sum_points(int64_t nb, const double *poly, int64_t npts, const double *r_xy,
+                                   void *out, int out_is_c128, void *stream) {
+  TG_REQUIRE(nb >= 0 && npts >= 0, "bad sizes");
+  if (npts == 0) return TG_OK;
+  TG_REQUIRE(out && r_xy && (poly || nb == 0), "null pointer");
+  field_points_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      nb, poly, npts, r_xy, out, out_is_c128);
+  return tg_launch_check("field_points_kernel");
+}
+
+extern "C" int tg_field_sum_separable(int64_t, const double *, const double *, int, int, int, int,
+                                      void *, int, void *) {
+  tg_set_error("tg_field_sum_separable: tensor-core path not built in this round");
+  return TG_EUNSUPPORTED;
+}

@@ -1,0 +1,266 @@
+// Error plumbing and the HOST-buffer entry points of the C ABI (include/temgym_b200.h).
+// These are what a non-CUDA host program (the reference's Python with numpy buffers, or a
+// jax.ffi CPU-side shim) binds: pointers are host memory, the H2D copy, kernels and the D2H
+// copy run inside the call, chunked over several streams so PCIe up/down and the kernels
+// overlap.  No CPU compute fallback exists.
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+#include "tg_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void tg_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *tg_last_error(void) { return g_err; }
+extern "C" int tg_abi_version(void) { return TG_ABI_VERSION; }
+extern "C" int tg_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    tg_set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return TG_ECUDA;
+  }
+  return n;
+}
+
+namespace {
+
+constexpr int kSlots = 3;
+constexpr int64_t kChunkRays = 1 << 18;
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+struct Streams {
+  cudaStream_t s[kSlots] = {nullptr, nullptr, nullptr};
+  int n = 0;
+  int init(int count) {
+    for (int i = 0; i < count; ++i) {
+      TG_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+      n = i + 1;
+    }
+    return TG_OK;
+  }
+  ~Streams() {
+    for (int i = 0; i < n; ++i) cudaStreamDestroy(s[i]);
+  }
+};
+
+}  // namespace
+
+extern "C" int tg_trace_f64_host(const tg_model *model_host, int64_t n, const tg_ray_in *in,
+                                 double *const out[7], double *jac, int jac_layout, int device) {
+  TG_REQUIRE(model_host && in, "null model or input");
+  TG_REQUIRE(n >= 0, "negative n");
+  if (n == 0) return TG_OK;
+  DeviceGuard guard(device);
+  if (!guard.ok) {
+    tg_set_error("cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(cudaGetLastError()));
+    return TG_ECUDA;
+  }
+  const int jw = jac_layout == TG_JAC_ABCD5 ? 25 : (jac_layout == TG_JAC_FULL7 ? 49 : 0);
+  TG_REQUIRE(jw == 0 || jac, "jac requested but pointer is null");
+  const int64_t chunk = std::min<int64_t>(n, kChunkRays);
+  const int nslots = (int)std::min<int64_t>(kSlots, (n + chunk - 1) / chunk);
+  Streams st;
+  int rc = st.init(nslots);
+  if (rc != TG_OK) return rc;
+
+  int n_in = 0, n_out = 0;
+  for (int f = 0; f < 7; ++f) {
+    n_in += in->ptr[f] ? 1 : 0;
+    n_out += (out && out[f]) ? 1 : 0;
+  }
+  const size_t per_slot = (size_t)chunk * 8 * (size_t)(n_in + n_out + jw);
+  unsigned char *dbuf[kSlots] = {nullptr, nullptr, nullptr};
+  for (int s = 0; s < nslots; ++s) {
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&dbuf[s]), per_slot ? per_slot : 8, st.s[s]);
+    if (e != cudaSuccess) {
+      tg_set_error("cudaMallocAsync(%zu): %s", per_slot, cudaGetErrorString(e));
+      for (int k = 0; k < s; ++k) cudaFreeAsync(dbuf[k], st.s[k]);
+      return TG_ECUDA;
+    }
+  }
+  rc = TG_OK;
+  int slot = 0;
+  for (int64_t b = 0; b < n && rc == TG_OK; b += chunk, slot = (slot + 1) % nslots) {
+    const int64_t cnt = std::min<int64_t>(chunk, n - b);
+    cudaStream_t s = st.s[slot];
+    double *base = reinterpret_cast<double *>(dbuf[slot]);
+    tg_ray_in din = *in;
+    double *dout[7];
+    double *p = base;
+    cudaError_t e = cudaSuccess;
+    for (int f = 0; f < 7 && e == cudaSuccess; ++f) {
+      if (in->ptr[f]) {
+        e = cudaMemcpyAsync(p, in->ptr[f] + b, (size_t)cnt * 8, cudaMemcpyHostToDevice, s);
+        din.ptr[f] = p;
+        p += chunk;
+      }
+    }
+    for (int f = 0; f < 7; ++f) {
+      dout[f] = nullptr;
+      if (out && out[f]) {
+        dout[f] = p;
+        p += chunk;
+      }
+    }
+    double *djac = jw ? p : nullptr;
+    if (e != cudaSuccess) {
+      tg_set_error("H2D copy: %s", cudaGetErrorString(e));
+      rc = TG_ECUDA;
+      break;
+    }
+    rc = tg_trace_f64(model_host, cnt, &din, dout, djac, jac_layout, s);
+    if (rc != TG_OK) break;
+    for (int f = 0; f < 7 && e == cudaSuccess; ++f)
+      if (dout[f]) e = cudaMemcpyAsync(out[f] + b, dout[f], (size_t)cnt * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && jw)
+      e = cudaMemcpyAsync(jac + b * jw, djac, (size_t)cnt * jw * 8, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) {
+      tg_set_error("D2H copy: %s", cudaGetErrorString(e));
+      rc = TG_ECUDA;
+    }
+  }
+  for (int s = 0; s < nslots; ++s) {
+    cudaFreeAsync(dbuf[s], st.s[s]);
+    cudaError_t e = cudaStreamSynchronize(st.s[s]);
+    if (e != cudaSuccess && rc == TG_OK) {
+      tg_set_error("stream sync: %s", cudaGetErrorString(e));
+      rc = TG_ECUDA;
+    }
+  }
+  return rc;
+}
+
+extern "C" int tg_metres_to_pixels_host(int64_t n, const double *x, const double *y,
+                                        const double m2px[9], void *py, void *px, int as_float,
+                                        int device) {
+  TG_REQUIRE(n >= 0 && m2px, "bad arguments");
+  if (n == 0) return TG_OK;
+  TG_REQUIRE(x && y && py && px, "null pointer");
+  DeviceGuard guard(device);
+  if (!guard.ok) {
+    tg_set_error("cudaSetDevice(%d) failed", device);
+    return TG_ECUDA;
+  }
+  Streams st;
+  int rc = st.init(1);
+  if (rc != TG_OK) return rc;
+  cudaStream_t s = st.s[0];
+  const size_t osz = as_float ? 8 : 4;
+  unsigned char *d = nullptr;
+  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d), (size_t)n * (16 + 2 * osz), s));
+  double *dx = reinterpret_cast<double *>(d), *dy = dx + n;
+  unsigned char *dpy = d + (size_t)n * 16, *dpx = dpy + (size_t)n * osz;
+  cudaError_t e = cudaMemcpyAsync(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dy, y, (size_t)n * 8, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    rc = tg_metres_to_pixels(n, dx, dy, m2px, dpy, dpx, as_float, s);
+    if (rc == TG_OK) {
+      e = cudaMemcpyAsync(py, dpy, (size_t)n * osz, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(px, dpx, (size_t)n * osz, cudaMemcpyDeviceToHost, s);
+    }
+  }
+  cudaFreeAsync(d, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  if (rc == TG_OK && (e != cudaSuccess || e2 != cudaSuccess)) {
+    tg_set_error("metres_to_pixels_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    rc = TG_ECUDA;
+  }
+  return rc;
+}
+
+extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t nb,
+                                           const double *const rays[7], const double *amplitude,
+                                           const double *waist_xy, const double *radii_xy,
+                                           const double *wavelength, const double *theta,
+                                           const double px2m[6], int H, int W, void *out,
+                                           int out_is_c128, int cull_bits, int device) {
+  TG_REQUIRE(model_host && rays && amplitude && waist_xy && radii_xy && wavelength && theta && px2m && out,
+             "null pointer");
+  TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad sizes");
+  DeviceGuard guard(device);
+  if (!guard.ok) {
+    tg_set_error("cudaSetDevice(%d) failed", device);
+    return TG_ECUDA;
+  }
+  Streams st;
+  int rc = st.init(1);
+  if (rc != TG_OK) return rc;
+  cudaStream_t s = st.s[0];
+  const size_t npix = (size_t)H * W, elt = out_is_c128 ? 16 : 8;
+  // device layout (doubles): rays 7n | amp n | waist 2n | radii 2n | wl n | theta n | k n | p0 n |
+  //                          abcd 25n | qinv 8n | poly 12n | field
+  const size_t nd = (size_t)nb * (7 + 1 + 2 + 2 + 1 + 1 + 1 + 1 + 25 + 8 + 12);
+  unsigned char *d = nullptr;
+  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d), nd * 8 + 256 + npix * elt, s));
+  double *p = reinterpret_cast<double *>(d);
+  double *dr[7];
+  for (int f = 0; f < 7; ++f) { dr[f] = p; p += nb; }
+  double *damp = p; p += nb;
+  double *dw = p; p += 2 * nb;
+  double *drad = p; p += 2 * nb;
+  double *dwl = p; p += nb;
+  double *dth = p; p += nb;
+  double *dk = p; p += nb;
+  double *dp0 = p; p += nb;
+  double *dabcd = p; p += 25 * nb;
+  double *dq = p; p += 8 * nb;
+  double *dpoly = p; p += 12 * nb;
+  void *dout = d + ((nd * 8 + 255) / 256) * 256;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](double *dst, const double *src, size_t cnt) {
+    if (e == cudaSuccess && cnt) e = cudaMemcpyAsync(dst, src, cnt * 8, cudaMemcpyHostToDevice, s);
+  };
+  for (int f = 0; f < 7; ++f) up(dr[f], rays[f], nb);
+  up(damp, amplitude, nb);
+  up(dw, waist_xy, 2 * nb);
+  up(drad, radii_xy, 2 * nb);
+  up(dwl, wavelength, nb);
+  up(dth, theta, nb);
+  if (e != cudaSuccess) {
+    tg_set_error("H2D copy: %s", cudaGetErrorString(e));
+    rc = TG_ECUDA;
+  }
+  if (rc == TG_OK && nb > 0) {
+    tg_ray_in in;
+    for (int f = 0; f < 7; ++f) { in.ptr[f] = dr[f]; in.value[f] = 0.0; }
+    double *no_out[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    rc = tg_trace_f64(model_host, nb, &in, no_out, dabcd, TG_JAC_ABCD5, s);
+    if (rc == TG_OK) rc = tg_gaussian_qinv_f64(nb, dw, drad, dwl, dth, dq, s);
+    if (rc == TG_OK) rc = tg_wave_numbers(nb, dwl, dr[5], dk, dp0, s);
+    if (rc == TG_OK)
+      rc = tg_beamlet_coeffs_abcd_f64(nb, damp, dp0, dq, dabcd, dr[0], dr[1], dr[2], dr[3], dk, dpoly, s);
+  }
+  if (rc == TG_OK) rc = tg_field_sum_grid(nb, dpoly, px2m, H, W, 0, H, dout, out_is_c128, cull_bits, nullptr, s);
+  if (rc == TG_OK) {
+    e = cudaMemcpyAsync(out, dout, npix * elt, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) {
+      tg_set_error("D2H copy: %s", cudaGetErrorString(e));
+      rc = TG_ECUDA;
+    }
+  }
+  cudaFreeAsync(d, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  if (rc == TG_OK && e2 != cudaSuccess) {
+    tg_set_error("stream sync: %s", cudaGetErrorString(e2));
+    rc = TG_ECUDA;
+  }
+  return rc;
+}

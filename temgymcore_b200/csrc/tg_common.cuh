@@ -1,0 +1,93 @@
+// Shared helpers for the temgym_b200 translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "temgym_b200.h"
+
+void tg_set_error(const char *fmt, ...);
+// k = 2 pi / wavelength, p0 = k * pathlength (reference gaussian.py:253-255); internal helper
+int tg_wave_numbers(int64_t nb, const double *wavelength, const double *pathlength, double *k,
+                    double *p0, cudaStream_t st);
+
+#define TG_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t err__ = (call);                                                         \
+    if (err__ != cudaSuccess) {                                                         \
+      tg_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__)); \
+      return TG_ECUDA;                                                                  \
+    }                                                                                   \
+  } while (0)
+
+#define TG_REQUIRE(cond, msg)                                   \
+  do {                                                          \
+    if (!(cond)) {                                              \
+      tg_set_error("%s:%d: %s", __FILE__, __LINE__, msg);       \
+      return TG_EINVAL;                                         \
+    }                                                           \
+  } while (0)
+
+static inline int tg_launch_check(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    tg_set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+    return TG_ECUDA;
+  }
+  return TG_OK;
+}
+
+// ---- small PTX wrappers (Blackwell: bulk async copies through the TMA unit) ----------
+__device__ __forceinline__ uint32_t tg_smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void tg_mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tg_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tg_fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tg_fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tg_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tg_smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool tg_mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(tg_smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tg_mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!tg_mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared bulk copy (1D, TMA unit), completion on an mbarrier. 16 B aligned, size % 16 == 0
+__device__ __forceinline__ void tg_bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(tg_smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(tg_smem_u32(bar))
+      : "memory");
+}
+// shared -> global bulk copy (1D, TMA unit)
+__device__ __forceinline__ void tg_bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(tg_smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tg_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tg_bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tg_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

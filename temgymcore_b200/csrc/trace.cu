@@ -1,0 +1,575 @@
+// K1: batched paraxial ray propagation through a model with in-register forward-mode
+// duals (the 5x5 ABCD block or the full 7x7 Jacobian), K5: metres->pixels, into_image.
+//
+// Replaces, for whole batches in one launch:
+//   run_to_end / run_iter            reference src/temgym_core/run.py:47-116
+//   FreeSpaceParaxial.propagate      reference src/temgym_core/propagator.py:52-72
+//   component __call__s              reference src/temgym_core/components.py
+//   vmap(jacobian(run_to_end)) + custom_jacobian_matrix
+//                                    reference gaussian.py:234-239, utils.py:7-43
+//
+// Compiled with -fmad=false: every + - * / is a separate IEEE fp64 operation in the
+// order the reference writes it, so non-transcendental models reproduce the numpy
+// oracle bit for bit.  The kernel is HBM-bound (312 B/ray algorithmic), so the lost
+// FMA contraction costs nothing.
+//
+// Data layout: rays are SoA (seven fp64 arrays); one ray per thread, coalesced 8 B
+// loads/stores per field.  The (n,5,5)/(n,7,7) Jacobian is AoS in global memory as the
+// API returns it; a block stages its rows in shared memory (odd row pitch -> no bank
+// conflicts) and emits them as ONE contiguous bulk async copy through the TMA unit
+// (cp.async.bulk.global.shared::cta), so HBM sees full lines only.
+#include <math.h>
+#include "tg_common.cuh"
+
+namespace {
+
+constexpr int kTraceThreads = 128;
+
+// ------------------------------------------------------------------ dual numbers
+template <int N>
+struct Dual {
+  double v;
+  double t[N > 0 ? N : 1];
+};
+template <int N, int M>
+struct DMax {
+  static_assert(N == M || N == 0 || M == 0, "mixed tangent widths");
+  static constexpr int value = N > M ? N : M;
+};
+template <int N, int M>
+using DR = Dual<DMax<N, M>::value>;
+
+template <int N>
+__device__ __forceinline__ Dual<N> dconst(double v) {
+  Dual<N> r;
+  r.v = v;
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = 0.0;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> dseed(double v, int col) {
+  Dual<N> r = dconst<N>(v);
+  if (N > 0 && col >= 0) {
+#pragma unroll
+    for (int k = 0; k < (N > 0 ? N : 1); ++k)
+      if (k == col) r.t[k] = 1.0;
+  }
+  return r;
+}
+template <int N, int M>
+__device__ __forceinline__ DR<N, M> operator+(const Dual<N> &a, const Dual<M> &b) {
+  DR<N, M> r;
+  r.v = a.v + b.v;
+#pragma unroll
+  for (int k = 0; k < DMax<N, M>::value; ++k) {
+    if constexpr (N > 0 && M > 0) r.t[k] = a.t[k] + b.t[k];
+    else if constexpr (N > 0) r.t[k] = a.t[k];
+    else r.t[k] = b.t[k];
+  }
+  return r;
+}
+template <int N, int M>
+__device__ __forceinline__ DR<N, M> operator-(const Dual<N> &a, const Dual<M> &b) {
+  DR<N, M> r;
+  r.v = a.v - b.v;
+#pragma unroll
+  for (int k = 0; k < DMax<N, M>::value; ++k) {
+    if constexpr (N > 0 && M > 0) r.t[k] = a.t[k] - b.t[k];
+    else if constexpr (N > 0) r.t[k] = a.t[k];
+    else r.t[k] = -b.t[k];
+  }
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator-(const Dual<N> &a) {
+  Dual<N> r;
+  r.v = -a.v;
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = -a.t[k];
+  return r;
+}
+template <int N, int M>
+__device__ __forceinline__ DR<N, M> operator*(const Dual<N> &a, const Dual<M> &b) {
+  DR<N, M> r;
+  r.v = a.v * b.v;
+#pragma unroll
+  for (int k = 0; k < DMax<N, M>::value; ++k) {
+    if constexpr (N > 0 && M > 0) r.t[k] = a.t[k] * b.v + b.t[k] * a.v;
+    else if constexpr (N > 0) r.t[k] = a.t[k] * b.v;
+    else r.t[k] = b.t[k] * a.v;
+  }
+  return r;
+}
+template <int N, int M>
+__device__ __forceinline__ DR<N, M> operator/(const Dual<N> &a, const Dual<M> &b) {
+  DR<N, M> r;
+  const double q = a.v / b.v;
+  r.v = q;
+#pragma unroll
+  for (int k = 0; k < DMax<N, M>::value; ++k) {
+    if constexpr (N > 0 && M > 0) r.t[k] = (a.t[k] - b.t[k] * q) / b.v;
+    else if constexpr (N > 0) r.t[k] = a.t[k] / b.v;
+    else r.t[k] = (0.0 - b.t[k] * q) / b.v;
+  }
+  return r;
+}
+// scalar mixes
+template <int N>
+__device__ __forceinline__ Dual<N> operator+(const Dual<N> &a, double b) {
+  Dual<N> r = a;
+  r.v = a.v + b;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator+(double b, const Dual<N> &a) {
+  return a + b;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator-(const Dual<N> &a, double b) {
+  Dual<N> r = a;
+  r.v = a.v - b;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator-(double b, const Dual<N> &a) {
+  Dual<N> r;
+  r.v = b - a.v;
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = -a.t[k];
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator*(const Dual<N> &a, double b) {
+  Dual<N> r;
+  r.v = a.v * b;
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = a.t[k] * b;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator*(double b, const Dual<N> &a) {
+  return a * b;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator/(const Dual<N> &a, double b) {
+  Dual<N> r;
+  r.v = a.v / b;
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = a.t[k] / b;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator/(double b, const Dual<N> &a) {
+  Dual<N> r;
+  const double q = b / a.v;
+  r.v = q;
+  const double s = q / a.v;
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = -a.t[k] * s;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> dsign(const Dual<N> &a) {
+  // jnp.sign: sign(0) = 0, zero derivative (components.py:556)
+  return dconst<N>(a.v > 0.0 ? 1.0 : (a.v < 0.0 ? -1.0 : (a.v == 0.0 ? 0.0 : a.v)));
+}
+template <int N>
+__device__ __forceinline__ void dsincos(const Dual<N> &a, Dual<N> &s, Dual<N> &c) {
+  double sv, cv;
+  sincos(a.v, &sv, &cv);
+  s.v = sv;
+  c.v = cv;
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) {
+    s.t[k] = cv * a.t[k];
+    c.t[k] = (-sv) * a.t[k];
+  }
+}
+template <int N>
+__device__ __forceinline__ Dual<N> dhypot(const Dual<N> &a, const Dual<N> &b) {
+  Dual<N> r;
+  const double h = hypot(a.v, b.v);
+  r.v = h;
+  const double ca = a.v / h, cb = b.v / h;  // NaN at (0,0) like jnp.hypot's gradient
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = ca * a.t[k] + cb * b.t[k];
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> datan2(const Dual<N> &y, const Dual<N> &x) {
+  Dual<N> r;
+  r.v = atan2(y.v, x.v);
+  const double r2 = x.v * x.v + y.v * y.v;
+  const double cy = x.v / r2, cx = y.v / r2;
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = cy * y.t[k] - cx * x.t[k];
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> dwhere_zero(const Dual<N> &a, double eps) {
+  return a.v == 0.0 ? dconst<N>(eps) : a;
+}
+template <int M, int N>
+__device__ __forceinline__ Dual<M> dnarrow(const Dual<N> &a) {
+  // keep the value; keep tangents only if the destination tracks them
+  if constexpr (M == N) {
+    return a;
+  } else {
+    static_assert(M == 0, "narrowing only to value-only");
+    Dual<M> r;
+    r.v = a.v;
+    r.t[0] = 0.0;
+    return r;
+  }
+}
+
+// ------------------------------------------------------------------ Krivanek aberrations
+// aberrations.py:42-108; p = comp.p + 1 (25 coefficients in KrivanekCoeffs field order).
+enum {
+  K_C10 = 0, K_C12, K_PHI12, K_C21, K_PHI21, K_C23, K_PHI23, K_C30, K_C32, K_PHI32, K_C34,
+  K_PHI34, K_C41, K_PHI41, K_C43, K_PHI43, K_C45, K_PHI45, K_C50, K_C52, K_PHI52, K_C54,
+  K_PHI54, K_C56, K_PHI56
+};
+
+// One harmonic term: B += C cos(m (phi - phi0)),  T += (-m C) sin(m (phi - phi0)).
+// Terms with C == 0 contribute exactly zero in the reference as well and are skipped
+// (uniform branch on kernel-parameter constants).
+template <int N>
+__device__ __forceinline__ void kriv_term(double C, double m, const Dual<N> &phi, double phi0,
+                                          Dual<N> &B, Dual<N> &T) {
+  if (C == 0.0) return;
+  Dual<N> sk, ck;
+  dsincos(m * (phi - phi0), sk, ck);
+  B = B + C * ck;
+  T = T + (-m * C) * sk;
+}
+
+// (dW/dax, dW/day, W) of the Krivanek aberration function; N is the tangent width of the
+// arguments (2 inside the ray kernel: tangents w.r.t. (ax, ay), chained to the ray tangents
+// by the caller, which keeps the live register set small).
+template <int N>
+__device__ __forceinline__ void krivanek(const double *p, const Dual<N> &ax, const Dual<N> &ay,
+                                         Dual<N> &dWx, Dual<N> &dWy, Dual<N> &W) {
+  const Dual<N> a = dhypot(ax, ay);
+  const Dual<N> phi = datan2(ay, ax);
+  // brackets (aberrations.py:42-48) and the matching sin sums of dW/dphi (aberrations.py:78-98)
+  Dual<N> B2 = dconst<N>(p[K_C10]), T2 = dconst<N>(0.0);
+  kriv_term(p[K_C12], 2.0, phi, p[K_PHI12], B2, T2);
+  Dual<N> B3 = dconst<N>(0.0), T3 = dconst<N>(0.0);
+  kriv_term(p[K_C21], 1.0, phi, p[K_PHI21], B3, T3);
+  kriv_term(p[K_C23], 3.0, phi, p[K_PHI23], B3, T3);
+  Dual<N> B4 = dconst<N>(p[K_C30]), T4 = dconst<N>(0.0);
+  kriv_term(p[K_C32], 2.0, phi, p[K_PHI32], B4, T4);
+  kriv_term(p[K_C34], 4.0, phi, p[K_PHI34], B4, T4);
+  Dual<N> B5 = dconst<N>(0.0), T5 = dconst<N>(0.0);
+  kriv_term(p[K_C41], 1.0, phi, p[K_PHI41], B5, T5);
+  kriv_term(p[K_C43], 3.0, phi, p[K_PHI43], B5, T5);
+  kriv_term(p[K_C45], 5.0, phi, p[K_PHI45], B5, T5);
+  Dual<N> B6 = dconst<N>(p[K_C50]), T6 = dconst<N>(0.0);
+  kriv_term(p[K_C52], 2.0, phi, p[K_PHI52], B6, T6);
+  kriv_term(p[K_C54], 4.0, phi, p[K_PHI54], B6, T6);
+  kriv_term(p[K_C56], 6.0, phi, p[K_PHI56], B6, T6);
+  const Dual<N> a2 = a * a;
+  const Dual<N> a3 = a2 * a;
+  const Dual<N> a4 = a2 * a2;
+  const Dual<N> a5 = a4 * a;
+  const Dual<N> a6 = a3 * a3;
+  // W (aberrations.py:51-60)
+  W = 0.5 * a2 * B2 + (a3 / 3.0) * B3 + 0.25 * a4 * B4 + 0.2 * a4 * a * B5 + (a6 / 6.0) * B6;
+  // grad (aberrations.py:63-108)
+  const Dual<N> dW_dalpha = a * B2 + a2 * B3 + a3 * B4 + a4 * B5 + a5 * B6;
+  Dual<N> dW_dphi = (0.5 * a2) * T2;
+  dW_dphi = dW_dphi + (a3 / 3.0) * T3;
+  dW_dphi = dW_dphi + (0.25 * a4) * T4;
+  dW_dphi = dW_dphi + (0.2 * a4 * a) * T5;
+  dW_dphi = dW_dphi + (a6 / 6.0) * T6;
+  const Dual<N> a_safe = dwhere_zero(a, 1e-30);
+  const Dual<N> inv_a = 1.0 / a_safe;
+  const Dual<N> inv_a2 = inv_a * inv_a;
+  dWx = dW_dalpha * (ax * inv_a) + dW_dphi * ((-ay) * inv_a2);
+  dWy = dW_dalpha * (ay * inv_a) + dW_dphi * (ax * inv_a2);
+}
+
+// chain rule: r = f(ax, ay) given as Dual<2> (tangents w.r.t. ax, ay) -> tangents of width N
+template <int N>
+__device__ __forceinline__ Dual<N> dchain(const Dual<2> &r, const Dual<N> &ax, const Dual<N> &ay) {
+  Dual<N> o;
+  o.v = r.v;
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) o.t[k] = N > 0 ? r.t[0] * ax.t[k] + r.t[1] * ay.t[k] : 0.0;
+  return o;
+}
+
+// ------------------------------------------------------------------ the kernel
+struct TraceOut {
+  double *ptr[7];
+};
+
+// NC = number of tangent columns (0 none, 5 = [x,y,dx,dy,_one], 7 = all Ray leaves).
+// In the 5-column mode z and pathlength carry no tangents: d z_out / d {x,y,dx,dy,_one}
+// is identically zero for every component on the path (z only ever receives component
+// constants), and pathlength never feeds back into x,y,dx,dy.
+template <int NC, bool KRIV>
+__global__ void __launch_bounds__(kTraceThreads)
+    trace_kernel(const __grid_constant__ tg_model model, const tg_ray_in in, const long long n,
+                 const TraceOut out, double *__restrict__ jac) {
+  constexpr bool FULL = (NC == 7);
+  constexpr int NZ = FULL ? 7 : 0;  // tangent width of z and pathlength
+  constexpr int ROWS = (NC == 7) ? 7 : 5;
+  constexpr int JW = ROWS * (NC > 0 ? NC : 1);  // doubles per ray in the Jacobian
+  extern __shared__ __align__(16) double s_jac[];
+
+  const long long block_first = (long long)blockIdx.x * kTraceThreads;
+  const long long i = block_first + threadIdx.x;
+  const bool active = i < n;
+
+  if (active) {
+    // column ids: NC==5 -> x0 y1 dx2 dy3 one4 ; NC==7 -> x0 y1 dx2 dy3 z4 pl5 one6
+    constexpr int COL_ONE = FULL ? 6 : 4;
+    auto ld = [&](int f) -> double { return in.ptr[f] ? __ldg(in.ptr[f] + i) : in.value[f]; };
+    Dual<NC> x = dseed<NC>(ld(0), 0);
+    Dual<NC> y = dseed<NC>(ld(1), 1);
+    Dual<NC> dx = dseed<NC>(ld(2), 2);
+    Dual<NC> dy = dseed<NC>(ld(3), 3);
+    Dual<NZ> z = dseed<NZ>(ld(4), FULL ? 4 : -1);
+    Dual<NZ> pl = dseed<NZ>(ld(5), FULL ? 5 : -1);
+    Dual<NC> one = dseed<NC>(ld(6), NC > 0 ? COL_ONE : -1);
+
+    const int nc = model.n_comp;
+    for (int c = 0; c < nc; ++c) {
+      const tg_comp &cm = model.comp[c];
+      if (!(cm.flags & TG_F_NOPROP)) {
+        // distance = component.z - ray.z (run.py:77); FreeSpaceParaxial (propagator.py:67-72)
+        const Dual<NZ> d = (cm.flags & TG_F_DIST) ? dconst<NZ>(cm.z) : cm.z - z;
+        x = x + dx * d;
+        y = y + dy * d;
+        z = z + d;
+        pl = pl + d;
+      }
+      switch (cm.op) {
+        case TG_OP_PLANE:
+          break;
+        case TG_OP_LENS:
+        case TG_OP_THICKLENS: {  // components.py:161-174, 431-447
+          const double f = cm.p[0];
+          const Dual<NC> ndx = (-x) / f + dx;
+          const Dual<NC> ndy = (-y) / f + dy;
+          pl = pl - dnarrow<NZ>((x * x + y * y) / (2.0 * f));
+          one = one * 1.0;
+          dx = ndx;
+          dy = ndy;
+          if (cm.op == TG_OP_THICKLENS) z = z - cm.p[1];
+        } break;
+        case TG_OP_DEFLECTOR: {  // components.py:476-482
+          pl = pl + dnarrow<NZ>(dx * x) + dnarrow<NZ>(dy * y);
+          dx = dx + cm.p[0] * one;
+          dy = dy + cm.p[1] * one;
+        } break;
+        case TG_OP_BIPRISM: {  // components.py:553-559
+          pl = pl + dnarrow<NZ>(dx * x) + dnarrow<NZ>(dy * y);
+          dx = dx + cm.p[0] * one * dsign(x);
+        } break;
+        case TG_OP_OFFSET: {  // Scanner / Descanner, components.py:279-285, 343-372
+          x = x + cm.p[0] * one;
+          y = y + cm.p[1] * one;
+          dx = dx + cm.p[2] * one;
+          dy = dy + cm.p[3] * one;
+        } break;
+        case TG_OP_ROTATOR: {  // components.py:503-523
+          const double cs = cm.p[0], sn = cm.p[1];
+          const Dual<NC> nx = x * cs - y * sn;
+          const Dual<NC> ny = x * sn + y * cs;
+          const Dual<NC> ndx = dx * cs - dy * sn;
+          const Dual<NC> ndy = dx * sn + dy * cs;
+          x = nx;
+          y = ny;
+          dx = ndx;
+          dy = ndy;
+        } break;
+        case TG_OP_KRIVANEK: {  // components.py:192-215
+          if constexpr (KRIV) {
+            const double f = cm.p[0];
+            const Dual<NC> idx = (-x) / f + dx;
+            const Dual<NC> idy = (-y) / f + dy;
+            Dual<NC> dWx, dWy, W;
+            if constexpr (NC == 0) {
+              krivanek<0>(cm.p + 1, idx, idy, dWx, dWy, W);
+            } else {
+              Dual<2> gx, gy, w2;
+              krivanek<2>(cm.p + 1, dseed<2>(idx.v, 0), dseed<2>(idy.v, 1), gx, gy, w2);
+              dWx = dchain<NC>(gx, idx, idy);
+              dWy = dchain<NC>(gy, idx, idy);
+              W = dchain<NC>(w2, idx, idy);
+            }
+            const Dual<NC> dux = (-dWx) / f, duy = (-dWy) / f;
+            dx = idx + dux;
+            dy = idy + duy;
+            pl = pl - dnarrow<NZ>((x * x + y * y) / (2.0 * f)) + dnarrow<NZ>(W / f);
+            one = one * 1.0;
+          }
+        } break;
+        default:
+          break;
+      }
+    }
+
+    if (out.ptr[0]) out.ptr[0][i] = x.v;
+    if (out.ptr[1]) out.ptr[1][i] = y.v;
+    if (out.ptr[2]) out.ptr[2][i] = dx.v;
+    if (out.ptr[3]) out.ptr[3][i] = dy.v;
+    if (out.ptr[4]) out.ptr[4][i] = z.v;
+    if (out.ptr[5]) out.ptr[5][i] = pl.v;
+    if (out.ptr[6]) out.ptr[6][i] = one.v;
+
+    if constexpr (NC > 0) {
+      double *row = s_jac + (size_t)threadIdx.x * JW;
+      if constexpr (!FULL) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          row[0 * 5 + k] = x.t[k];
+          row[1 * 5 + k] = y.t[k];
+          row[2 * 5 + k] = dx.t[k];
+          row[3 * 5 + k] = dy.t[k];
+          row[4 * 5 + k] = one.t[k];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          row[0 * 7 + k] = x.t[k];
+          row[1 * 7 + k] = y.t[k];
+          row[2 * 7 + k] = dx.t[k];
+          row[3 * 7 + k] = dy.t[k];
+          row[4 * 7 + k] = z.t[k];
+          row[5 * 7 + k] = pl.t[k];
+          row[6 * 7 + k] = one.t[k];
+        }
+      }
+    }
+  }
+
+  if constexpr (NC > 0) {
+    // Emit the block's Jacobian rows: contiguous in global memory.
+    const long long rem = n - block_first;
+    const int nvalid = rem >= kTraceThreads ? kTraceThreads : (int)rem;
+    double *gdst = jac + block_first * JW;
+    const uint32_t bytes = (uint32_t)nvalid * JW * 8u;
+    const bool bulk_ok = ((bytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(gdst) & 15u) == 0);
+    if (bulk_ok) {
+      tg_fence_proxy_async();  // make the generic-proxy smem writes visible to the async proxy
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        tg_bulk_s2g(gdst, s_jac, bytes);
+        tg_bulk_commit();
+        tg_bulk_wait_read0();  // smem must stay valid until the TMA unit has read it
+      }
+    } else {
+      __syncthreads();
+      const int total = nvalid * JW;
+      for (int k = threadIdx.x; k < total; k += kTraceThreads) gdst[k] = s_jac[k];
+    }
+  }
+}
+
+template <int NC, bool KRIV>
+int launch_trace_k(const tg_model *m, int64_t n, const tg_ray_in *in, double *const out[7],
+                 double *jac, cudaStream_t st) {
+  TraceOut o;
+  for (int f = 0; f < 7; ++f) o.ptr[f] = out ? out[f] : nullptr;
+  constexpr int ROWS = (NC == 7) ? 7 : 5;
+  const size_t smem = NC > 0 ? (size_t)kTraceThreads * ROWS * NC * sizeof(double) : 0;
+  if (smem > 48 * 1024) {
+    TG_CUDA(cudaFuncSetAttribute(trace_kernel<NC, KRIV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  }
+  const long long blocks = (n + kTraceThreads - 1) / kTraceThreads;
+  TG_REQUIRE(blocks <= 0x7fffffffLL, "too many rays for one launch");
+  trace_kernel<NC, KRIV><<<(unsigned)blocks, kTraceThreads, smem, st>>>(*m, *in, (long long)n, o, jac);
+  return tg_launch_check("trace_kernel");
+}
+
+template <int NC>
+int launch_trace(const tg_model *m, int64_t n, const tg_ray_in *in, double *const out[7],
+                 double *jac, cudaStream_t st) {
+  bool kriv = false;
+  for (int c = 0; c < m->n_comp; ++c) kriv |= (m->comp[c].op == TG_OP_KRIVANEK);
+  return kriv ? launch_trace_k<NC, true>(m, n, in, out, jac, st)
+              : launch_trace_k<NC, false>(m, n, in, out, jac, st);
+}
+
+// ------------------------------------------------------------------ K5
+__global__ void __launch_bounds__(256)
+    m2p_kernel(long long n, const double *__restrict__ x, const double *__restrict__ y,
+               double m00, double m01, double m02, double m10, double m11, double m12,
+               void *__restrict__ py, void *__restrict__ px, int as_float) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double xv = x[i], yv = y[i];
+  // apply_transformation (coordinate_transforms.py:137-140): T @ [y, x, 1], left to right,
+  // no FMA contraction (this TU is built with -fmad=false; the intrinsics make it explicit)
+  const double ty = __dadd_rn(__dadd_rn(__dmul_rn(m00, yv), __dmul_rn(m01, xv)), m02);
+  const double tx = __dadd_rn(__dadd_rn(__dmul_rn(m10, yv), __dmul_rn(m11, xv)), m12);
+  if (as_float) {
+    static_cast<double *>(py)[i] = ty;
+    static_cast<double *>(px)[i] = tx;
+  } else {
+    // jnp.round(...).astype(int32) (grid.py:147-149): half-to-even, saturating, NaN -> 0
+    static_cast<int32_t *>(py)[i] = __double2int_rn(ty);
+    static_cast<int32_t *>(px)[i] = __double2int_rn(tx);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    into_image_kernel(long long n, const int32_t *__restrict__ py, const int32_t *__restrict__ px,
+                      int H, int W, unsigned long long *__restrict__ image) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = py[i], c = px[i];
+  if (r >= 0 && r < H && c >= 0 && c < W) atomicAdd(image + (size_t)r * W + c, 1ULL);
+}
+
+}  // namespace
+
+extern "C" int tg_trace_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in,
+                            double *const out[7], double *jac, int jac_layout, void *stream) {
+  TG_REQUIRE(model_host && in, "null model or input");
+  TG_REQUIRE(model_host->n_comp >= 0 && model_host->n_comp <= TG_MAX_COMPS, "bad n_comp");
+  TG_REQUIRE(n >= 0, "negative n");
+  TG_REQUIRE(jac_layout == TG_JAC_NONE || jac != nullptr, "jac requested but pointer is null");
+  if (n == 0) return TG_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (jac_layout) {
+    case TG_JAC_NONE:
+      return launch_trace<0>(model_host, n, in, out, nullptr, st);
+    case TG_JAC_ABCD5:
+      return launch_trace<5>(model_host, n, in, out, jac, st);
+    case TG_JAC_FULL7:
+      return launch_trace<7>(model_host, n, in, out, jac, st);
+    default:
+      tg_set_error("tg_trace_f64: unknown jac_layout %d", jac_layout);
+      return TG_EINVAL;
+  }
+}
+
+extern "C" int tg_metres_to_pixels(int64_t n, const double *x, const double *y,
+                                   const double m2px[9], void *py, void *px, int as_float,
+                                   void *stream) {
+  TG_REQUIRE(n >= 0 && m2px, "bad arguments");
+  if (n == 0) return TG_OK;
+  TG_REQUIRE(x && y && py && px, "null pointer");
+  const long long blocks = (n + 255) / 256;
+  m2p_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      n, x, y, m2px[0], m2px[1], m2px[2], m2px[3], m2px[4], m2px[5], py, px, as_float);
+  return tg_launch_check("m2p_kernel");
+}
+
+extern "C" int tg_into_image_i64(int64_t n, const int32_t *py, const int32_t *px, int H, int W,
+                                 long long *image, void *stream) {
+  TG_REQUIRE(n >= 0 && H > 0 && W > 0, "bad arguments");
+  if (n == 0) return TG_OK;
+  TG_REQUIRE(py && px && image, "null pointer");
+  const long long blocks = (n + 255) / 256;
+  into_image_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      n, py, px, H, W, reinterpret_cast<unsigned long long *>(image));
+  return tg_launch_check("into_image_kernel");
+}

@@ -1,0 +1,265 @@
+"""Runners (reference ``src/temgym_core/run.py``): ``run_iter``, ``run_to_end``,
+``solve_model`` -- and the fused ray + ABCD call that replaces
+``jax.vmap(jax.jacobian(run_to_end), in_axes=(0, None))`` + ``custom_jacobian_matrix``
+(reference gaussian.py:234-239, utils.py:7-43).
+
+A model (any sequence of components / sources) is compiled to a flat descriptor
+(opcode, z, parameters per element) that travels to the CUDA ray kernel as a kernel
+parameter; one launch propagates every ray through the whole model, carrying the
+Jacobian with forward-mode duals in registers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Generator, Sequence
+
+import numpy as np
+
+from . import _arrays as A
+from . import _lib as L
+from .components import Component
+from .propagator import BasePropagator, FreeSpaceParaxial, Propagator
+from .ray import RAY_FIELDS, Ray
+from .source import Source
+
+
+# ----------------------------------------------------------------------------- model compile
+def compile_model(components: Sequence[Any], noprop: bool = False) -> L.tg_model:
+    """Flatten a model into the ``tg_model`` descriptor of ``include/temgym_b200.h``."""
+    comps = list(components)
+    if len(comps) > L.TG_MAX_COMPS:
+        raise ValueError(f"model has {len(comps)} elements; the kernel descriptor holds "
+                         f"{L.TG_MAX_COMPS}")
+    m = L.tg_model()
+    m.n_comp = len(comps)
+    for i, c in enumerate(comps):
+        if isinstance(c, Source):
+            op, z, params = L.TG_OP_PLANE, float(c.z), ()
+        elif isinstance(c, Component):
+            op, z, params = c._tg_spec()
+        else:
+            raise TypeError(f"model element {i} ({type(c).__name__}) is neither a Component nor a "
+                            "Source")
+        m.comp[i].op = op
+        m.comp[i].flags = L.TG_F_NOPROP if noprop else 0
+        m.comp[i].z = z
+        for j, v in enumerate(params):
+            m.comp[i].p[j] = v
+    return m
+
+
+def _host_z(z, model: L.tg_model) -> float:
+    """z after the model for a ray-independent (scalar) input z: the same fp64 arithmetic
+    the kernel performs (run.py:77 + propagator.py:70; ThickLens components.py:442)."""
+    for i in range(model.n_comp):
+        c = model.comp[i]
+        if not (c.flags & L.TG_F_NOPROP):
+            z = z + (c.z if (c.flags & L.TG_F_DIST) else (c.z - z))
+        if c.op == L.TG_OP_THICKLENS:
+            z = z - c.p[1]
+    return z
+
+
+# ----------------------------------------------------------------------------- kernel call
+def _trace(ray, model: L.tg_model, jac_layout: int = L.TG_JAC_NONE, want_rays: bool = True):
+    """Run the ray kernel.  Returns (Ray | None, jac | None)."""
+    lib = L.load()
+    vals = [getattr(ray, f) for f in RAY_FIELDS]
+    kinds = [A.kind_of(v) for v in vals]
+    kind = max(kinds)
+    sizes = [A.numel(v) for v in vals]
+    n = max(sizes)
+    for f, k, s in zip(RAY_FIELDS, kinds, sizes):
+        if k != A.KIND_SCALAR and s != n:
+            raise ValueError(f"Ray field {f!r} has {s} elements, expected {n}")
+    shape = next((A.shape_of(v) for v, k in zip(vals, kinds) if k != A.KIND_SCALAR), ())
+    jw = {L.TG_JAC_NONE: 0, L.TG_JAC_ABCD5: 25, L.TG_JAC_FULL7: 49}[jac_layout]
+    jdim = 5 if jw == 25 else 7
+    # z and _one stay ray-independent scalars when they came in as scalars
+    scalar_out = {4: kinds[4] == A.KIND_SCALAR and kind != A.KIND_SCALAR,
+                  6: kinds[6] == A.KIND_SCALAR and kind != A.KIND_SCALAR}
+    rin = L.tg_ray_in()
+    out_ptrs = [None] * 7
+    outs = [None] * 7
+    keep = []
+
+    if kind == A.KIND_CUDA:
+        import torch
+        dev = A.cuda_device_of(vals)
+        for i, (v, k) in enumerate(zip(vals, kinds)):
+            if k == A.KIND_SCALAR:
+                rin.ptr[i] = None
+                rin.value[i] = A.to_float(v)
+            else:
+                t = A.to_device_f64(v, dev)
+                keep.append(t)
+                rin.ptr[i] = t.data_ptr()
+        if want_rays:
+            for i in range(7):
+                if scalar_out.get(i, False):
+                    continue
+                outs[i] = torch.empty(n, dtype=torch.float64, device=dev)
+                out_ptrs[i] = outs[i].data_ptr()
+        jac = torch.empty((n, jdim, jdim), dtype=torch.float64, device=dev) if jw else None
+        with torch.cuda.device(dev):
+            L.check(lib.tg_trace_f64(C.byref(model), n, C.byref(rin), L.ptr_array(out_ptrs),
+                                     jac.data_ptr() if jw else None, jac_layout,
+                                     A.current_stream_ptr(dev)), "tg_trace_f64")
+        conv = lambda t: t.reshape(shape)  # noqa: E731
+        if jw:
+            jac = jac.reshape(shape + (jdim, jdim))
+    else:
+        for i, (v, k) in enumerate(zip(vals, kinds)):
+            if k == A.KIND_SCALAR:
+                rin.ptr[i] = None
+                rin.value[i] = A.to_float(v)
+            else:
+                h = A.to_host_f64(v)
+                keep.append(h)
+                rin.ptr[i] = h.ctypes.data
+        if want_rays:
+            for i in range(7):
+                if scalar_out.get(i, False):
+                    continue
+                outs[i] = np.empty(n, dtype=np.float64)
+                out_ptrs[i] = outs[i].ctypes.data
+        jac = np.empty((n, jdim, jdim), dtype=np.float64) if jw else None
+        L.check(lib.tg_trace_f64_host(C.byref(model), n, C.byref(rin), L.ptr_array(out_ptrs),
+                                      jac.ctypes.data if jw else None, jac_layout,
+                                      A.current_device_index()), "tg_trace_f64_host")
+        if kind == A.KIND_SCALAR:
+            conv = lambda a: float(a[0])  # noqa: E731
+            if jw:
+                jac = jac[0]
+        else:
+            conv = lambda a: A.from_host(a, kind, shape)  # noqa: E731
+            if jw:
+                jac = A.from_host(jac, kind, shape + (jdim, jdim))
+
+    out_ray = None
+    if want_rays:
+        res = []
+        for i in range(7):
+            if outs[i] is not None:
+                res.append(conv(outs[i]))
+            elif i == 4:
+                res.append(_host_z(A.to_float(vals[4]), model))
+            else:  # _one: `one * 1.0`
+                res.append(A.to_float(vals[6]) * 1.0)
+        out_ray = Ray(*res)
+    return out_ray, jac
+
+
+def _check_propagator(propagator):
+    if not isinstance(propagator, FreeSpaceParaxial):
+        raise NotImplementedError(
+            "only FreeSpaceParaxial is implemented by the CUDA ray kernel "
+            f"(got {type(propagator).__name__}); there is no Python fallback")
+
+
+def _distance_model(distance) -> L.tg_model:
+    if A.numel(distance) != 1:
+        raise NotImplementedError("per-ray propagation distances: use run_to_end with a model")
+    m = L.tg_model()
+    m.n_comp = 1
+    m.comp[0].op = L.TG_OP_PLANE
+    m.comp[0].flags = L.TG_F_DIST
+    m.comp[0].z = A.to_float(distance)
+    return m
+
+
+def _propagate_only(ray, distance):
+    """FreeSpaceParaxial.propagate(ray, distance) (propagator.py:52-72) on the GPU."""
+    out, _ = _trace(ray, _distance_model(distance))
+    return out
+
+
+def _apply_component_only(ray, component):
+    """``component(ray)`` with no free-space step (components.py ``__call__``)."""
+    out, _ = _trace(ray, compile_model([component], noprop=True))
+    return out
+
+
+# ----------------------------------------------------------------------------- public API
+def passthrough_transform(component):  # run.py:26-32
+    def inner(ray):
+        out = component(ray)
+        return out, out
+    return inner
+
+
+def jacobian_transform(component):  # run.py:35-41
+    def inner(ray):
+        from .utils import RayJacobian
+        if isinstance(component, Propagator):
+            m = _distance_model(component.distance)
+        else:
+            m = compile_model([component], noprop=True)
+        out, jac = _trace(ray, m, L.TG_JAC_FULL7)
+        return out, RayJacobian(jac)
+    return inner
+
+
+def run_iter(ray, components: Sequence[Any], transform=passthrough_transform,
+             propagator: BasePropagator = FreeSpaceParaxial()) -> Generator:
+    """Step a ray through the model, yielding ``(Propagator, ray)`` then
+    ``(component, ray)`` for every element; free space over ``component.z - ray.z`` is
+    inserted before every element, also when that distance is 0 (run.py:47-82)."""
+    _check_propagator(propagator)
+    for component in components:
+        if isinstance(component, (Source, Component)):
+            distance = component.z - ray.z
+            propagator_d = propagator.with_distance(distance)
+            if transform is passthrough_transform:
+                m = L.tg_model()
+                m.n_comp = 1
+                m.comp[0].op = L.TG_OP_PLANE
+                m.comp[0].z = float(component.z)
+                ray, _ = _trace(ray, m)
+                out = ray
+            else:
+                ray, out = transform(propagator_d)(ray)
+            yield propagator_d, out
+        ray, out = transform(component)(ray)
+        yield component, out
+
+
+def run_to_end(ray, components: Sequence[Any],
+               propagator: BasePropagator = FreeSpaceParaxial()) -> Ray:
+    """Propagate ray(s) through all components in ONE kernel launch (run.py:85-116)."""
+    _check_propagator(propagator)
+    out, _ = _trace(ray, compile_model(components))
+    return out
+
+
+def run_to_end_abcd(ray, components: Sequence[Any],
+                    propagator: BasePropagator = FreeSpaceParaxial(), want_rays: bool = True):
+    """Fused ``run_to_end`` + per-ray 5x5 ABCD matrix, one launch.
+
+    Replaces ``custom_jacobian_matrix(jax.vmap(jax.jacobian(run_to_end), in_axes=(0, None))
+    (rays, model))`` (gaussian.py:234-239).  Returns ``(Ray, abcd)`` with ``abcd`` of shape
+    ``(N, 5, 5)`` (``(5, 5)`` for a scalar ray)."""
+    _check_propagator(propagator)
+    return _trace(ray, compile_model(components), L.TG_JAC_ABCD5, want_rays=want_rays)
+
+
+def ray_jacobian(ray, components: Sequence[Any], propagator: BasePropagator = FreeSpaceParaxial()):
+    """``jax.jacobian(run_to_end)(ray, model)`` (README.md:227-234): the full Ray-of-Ray
+    Jacobian as a :class:`~temgymcore_b200.utils.RayJacobian` (attribute access
+    ``jac.dy.x`` == d out.dy / d in.x)."""
+    from .utils import RayJacobian
+    _check_propagator(propagator)
+    _, jac = _trace(ray, compile_model(components), L.TG_JAC_FULL7, want_rays=False)
+    return RayJacobian(jac)
+
+
+def solve_model(ray, model: Sequence[Any], propagator: BasePropagator = FreeSpaceParaxial()):
+    """Per-step 5x5 ABCD matrices, shape ``(2 * n_components, 5, 5)`` (run.py:150-179)."""
+    from .utils import custom_jacobian_matrix
+    mats = []
+    for _, jac in run_iter(ray, model, transform=jacobian_transform, propagator=propagator):
+        mats.append(custom_jacobian_matrix(jac))
+    if A.kind_of(mats[0]) == A.KIND_CUDA:
+        import torch
+        return torch.stack(mats)
+    return np.array(mats)

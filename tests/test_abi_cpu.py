@@ -1,0 +1,128 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/temgym_b200.h declares, its structs match the ctypes mirror, and the host-side
+model compiler fills the descriptor as documented.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "temgym_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from temgymcore_b200 import _lib as L
+    if not os.path.exists(L.LIB_PATH):
+        subprocess.check_call([os.path.join(ROOT, "temgymcore_b200", "csrc", "build.sh")])
+    return L.load()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    from temgymcore_b200 import _lib as L
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+        assert s in L.SIGNATURES, f"{s} has no ctypes signature"
+    assert sorted(L.SIGNATURES) == syms
+    assert lib.tg_abi_version() == 1
+
+
+def test_struct_layout_matches_header(lib):
+    from temgymcore_b200 import _lib as L
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "temgym_b200.h"
+int main(void){
+  printf("%zu %zu %zu %zu %zu %zu %zu %d %d\n", sizeof(tg_comp), offsetof(tg_comp, z), offsetof(tg_comp, p),
+         sizeof(tg_model), offsetof(tg_model, comp), sizeof(tg_ray_in), offsetof(tg_ray_in, value),
+         TG_MAX_COMPS, TG_NPARAM);
+  return 0; }
+'''
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "probe.c")
+        open(src, "w").write(prog)
+        exe = os.path.join(d, "probe")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        vals = [int(v) for v in subprocess.check_output([exe]).split()]
+    assert vals == [C.sizeof(L.tg_comp), L.tg_comp.z.offset, L.tg_comp.p.offset, C.sizeof(L.tg_model),
+                    L.tg_model.comp.offset, C.sizeof(L.tg_ray_in), L.tg_ray_in.value.offset,
+                    L.TG_MAX_COMPS, L.TG_NPARAM]
+
+
+def test_error_reporting_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    n = lib.tg_device_count()
+    assert n <= 0  # 0 devices or TG_ECUDA, never a crash
+    from temgymcore_b200 import _lib as L
+    from temgymcore_b200.ray import Ray
+    from temgymcore_b200.run import run_to_end
+    from temgymcore_b200.components import Lens
+    # the product path fails loudly instead of falling back to the CPU
+    with pytest.raises(L.TemGymError):
+        run_to_end(Ray(0.1, 0.2, 0.3, 0.4, 0.0, 0.0), [Lens(z=0.5, focal_length=1.0)])
+
+
+def test_invalid_arguments(lib):
+    from temgymcore_b200 import _lib as L
+    m = L.tg_model()
+    m.n_comp = L.TG_MAX_COMPS + 1
+    rin = L.tg_ray_in()
+    rc = lib.tg_trace_f64(C.byref(m), 4, C.byref(rin), L.ptr_array([None] * 7), None, 0, None)
+    assert rc == L.TG_EINVAL and b"n_comp" in lib.tg_last_error()
+    m.n_comp = 0
+    assert lib.tg_trace_f64(C.byref(m), 0, C.byref(rin), L.ptr_array([None] * 7), None, 0, None) == 0
+    assert lib.tg_trace_f64(C.byref(m), 4, C.byref(rin), L.ptr_array([None] * 7), None, L.TG_JAC_ABCD5, None) == L.TG_EINVAL
+    assert lib.tg_field_sum_grid(0, None, L.dbl_array([0] * 6), 8, 8, 4, 8, None, 1, 0, None, None) == L.TG_EINVAL
+
+
+def test_compile_model():
+    from temgymcore_b200 import _lib as L
+    from temgymcore_b200.run import compile_model, _host_z
+    from tests.models import kitchen_sink_model, six_component_column
+    m = compile_model(kitchen_sink_model())
+    ops = [m.comp[i].op for i in range(m.n_comp)]
+    assert ops == [L.TG_OP_PLANE, L.TG_OP_OFFSET, L.TG_OP_LENS, L.TG_OP_PLANE, L.TG_OP_DEFLECTOR,
+                   L.TG_OP_ROTATOR, L.TG_OP_THICKLENS, L.TG_OP_BIPRISM, L.TG_OP_OFFSET, L.TG_OP_PLANE,
+                   L.TG_OP_PLANE]
+    assert m.comp[6].z == 0.4 and abs(m.comp[6].p[1] - (0.4 - 0.47)) < 1e-18
+    assert m.comp[2].p[0] == 0.35
+    # scalar z tracking equals the oracle's z
+    from oracle import temgym_oracle as O
+    from temgymcore_b200.ray import Ray
+    out = O.run_to_end(Ray(0.0, 0.0, 0.0, 0.0, -0.3, 0.0), kitchen_sink_model())
+    assert _host_z(-0.3, m) == float(out.z)
+    mk = compile_model(six_component_column())
+    assert mk.comp[1].op == L.TG_OP_KRIVANEK and mk.comp[1].p[0] == 2.5e-4
+    assert mk.comp[1].p[1 + 7] == 1e8 and mk.comp[1].p[1 + 1] == 1e-1  # C30, C12 slots
+    with pytest.raises(TypeError):
+        compile_model([object()])
+    with pytest.raises(ValueError):
+        compile_model(kitchen_sink_model() * 3)
+
+
+def test_grid_host_matrices_match_oracle():
+    from oracle import temgym_oracle as O
+    from temgymcore_b200.components import Detector
+    for rot, flip, centre in [(0.0, False, (0.0, 0.0)), (17.0, True, (1e-3, -2e-3)), (90.0, False, (0.5, 0.25))]:
+        det = Detector(z=0.0, pixel_size=(0.01, 0.02), shape=(33, 65), rotation=rot, centre=centre, flip_y=flip)
+        np.testing.assert_array_equal(det.pixels_to_metres_mat, O.grid_pixels_to_metres_mat(det))
+        np.testing.assert_array_equal(det.metres_to_pixels_mat, O.grid_metres_to_pixels_mat(det))
+        T = det.pixels_to_metres_mat
+        X0, Xc, Xr, Y0, Yc, Yr = det.px2m_affine
+        assert (X0, Xc, Xr, Y0, Yc, Yr) == (T[1, 2], T[1, 1], T[1, 0], T[0, 2], T[0, 1], T[0, 0])
