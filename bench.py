@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the TemGymCore hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm)
+  python bench.py --impl reference --gpus N --steps K ...   (CPU arm: the numpy oracle port of
+                                                             the reference, all host cores)
+
+One "step" = one pass of the hot path over BASELINE config C2 (aperture_diffraction):
+10^4 Gaussian beamlets traced through ParallelBeam -> Lens -> Detector (ray kernel + ABCD),
+their 6 complex coefficients built, and the field of every beamlet summed on every pixel
+of a 1024 x 1024 detector.  `value` = beamlet*pixel evaluations per second, whole job.
+At N > 1 the detector rows are sharded over the ranks (strong scaling of the one image):
+coefficient table broadcast (NCCL), local row block, all-gather of the blocks.
+A second section times the ray half of the path on its own (rays/s with the 5x5 ABCD,
+rays sharded over ranks with no communication) and is reported under "rays".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2_NB, C2_SHAPE = 10_000, (1024, 1024)
+MUFU_PER_EVAL = 3          # sin, cos, ex2
+MUFU_PER_CLK_SM = 16
+RAY_BYTES_ABCD = 312       # 56 in + 56 out + 200 ABCD, fp64
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            m = json.load(fh)
+        p.update(hbm_gbs=float(m["hbm_gbs"]), sm_max_mhz=float(m.get("sm_max_mhz", 1965.0)),
+                 source="MEASURED_PEAKS.json")
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        top = sorted(sm)[len(sm) // 2:]  # samples under load = upper half
+        return {"sm_mhz": float(np.median(top)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def _oracle_rows(args):
+    r0, r1, nb = args
+    from oracle import temgym_oracle as O
+    from tests import models as M
+    g, model = M.aperture_diffraction_case(C2_NB, C2_SHAPE)
+    gd = O._gr_arrays(g)
+    sl = slice(0, nb)
+    central = O.Ray(*(gd[f][sl] for f in O.RAY_FIELDS))
+    _, J = O.jacobian_run_to_end(central, model)
+    ab = O.custom_jacobian_matrix(J)
+    Q1 = O.gaussian_Q_inv(gd["waist_xy"][sl], gd["radii_of_curv"][sl], gd["wavelength"][sl], gd["theta"][sl])
+    k = 2 * np.pi / gd["wavelength"][sl]
+    W = C2_SHAPE[1]
+    yy, xx = np.meshgrid(np.arange(r0, r1), np.arange(W), indexing="ij")   # grid.py:76-100
+    cx, cy = O.grid_pixels_to_metres(model[-1], (yy.ravel(), xx.ravel()))
+    r2 = np.stack((cx, cy), axis=-1)
+    out = O.propagate_misaligned_gaussian(gd["amplitude"][sl], k * gd["pathlength"][sl], Q1, ab[:, 0:2, 0:2],
+                                          ab[:, 0:2, 2:4], ab[:, 2:4, 0:2], ab[:, 2:4, 2:4], ab[:, 0:2, 4],
+                                          ab[:, 2:4, 4], np.stack([gd["x"][sl], gd["y"][sl]], -1),
+                                          np.stack([gd["dx"][sl], gd["dy"][sl]], -1), k, r2)
+    return float(np.abs(out).sum())
+
+
+def cpu_field_rate(nb, rows_per_worker, workers):
+    """evals/s of the oracle on a bounded sample: `nb` beamlets of C2 on `workers` blocks of
+    `rows_per_worker` detector rows (one block per process)."""
+    import multiprocessing as mp
+    jobs = [(i * rows_per_worker, (i + 1) * rows_per_worker, nb) for i in range(workers)]
+    t0 = time.perf_counter()
+    if workers == 1:
+        _oracle_rows(jobs[0])
+    else:
+        with mp.get_context("fork").Pool(workers) as pool:
+            pool.map(_oracle_rows, jobs)
+    dt = time.perf_counter() - t0
+    evals = nb * rows_per_worker * workers * C2_SHAPE[1]
+    return evals / dt, dt, evals
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path.  jax is not installable here, so
+    this is the numpy oracle port (cpu_baseline.kind = "port"), on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nb, rows = 1024, 16
+    _oracle_rows((0, 2, 16))  # import / warm caches
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_field_rate(64, 2, cores)
+    rates, times = [], []
+    for _ in range(args.steps):
+        r, dt, evals = cpu_field_rate(nb, rows, cores)
+        rates.append(r)
+        times.append(dt)
+    value = float(np.mean(rates))
+    sample = (f"{nb} of {C2_NB} beamlets x {rows * cores} of {C2_SHAPE[0]} detector rows of C2 per step, "
+              f"{cores} processes (one row block each), numpy oracle port of gaussian.py:225-369")
+    line = {
+        "impl": "reference", "metric": "beamlet_pixel_evals_per_s", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 aperture_diffraction: 1e4 Gaussian beamlets -> 1024x1024 detector "
+                               "(bounded sample, rate extrapolates linearly)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tests import models as M
+    from temgymcore_b200 import _lib as L
+    from temgymcore_b200 import distributed as D
+    from temgymcore_b200.gaussian import (_field_sum_grid, beamlet_polynomials, make_gaussian_image_host)
+    from temgymcore_b200.ray import RAY_FIELDS, Ray
+    from temgymcore_b200.run import run_to_end_abcd
+
+    L.load()  # fail loudly if the CUDA library is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    H, W = C2_SHAPE
+    g_host, model = M.aperture_diffraction_case(C2_NB, C2_SHAPE)
+    grid = model[-1]
+    from dataclasses import fields, replace
+    g_dev = replace(g_host, **{f.name: torch.as_tensor(getattr(g_host, f.name), device=dev)
+                               for f in fields(g_host)})
+    g_pin = replace(g_host, **{f.name: torch.as_tensor(getattr(g_host, f.name)).pin_memory()
+                               for f in fields(g_host)})
+    r0, nr = D.row_shards(H, world)[rank]
+    launches = {"n": 0}
+
+    def step_device():
+        """inputs resident in HBM: trace+ABCD, Q_inv, k/p0, coefficients (4 launches + torch glue),
+        broadcast, prep + field (+ split reduce), all-gather."""
+        img = D.make_gaussian_image_sharded(g_dev, model, cull_bits=0)
+        launches["n"] += 7
+        return img
+
+    def timed(fn, steps, warmup, flush=True):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        times = []
+        for _ in range(steps):
+            if flush:
+                flush_l2()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        return times
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    times = timed(step_device, args.steps, args.warmup)
+    total_ms = max_over_ranks(float(np.sum(times)))
+    n_launch = launches["n"] - 7 * args.warmup
+    evals_per_step = C2_NB * H * W
+    ms_per_step = total_ms / args.steps
+    value = evals_per_step / (ms_per_step * 1e-3)
+
+    # dominant kernel alone (prep + tiled field kernel + split reduce of this rank's rows)
+    poly, nb, _ = beamlet_polynomials(g_dev, model)
+    kt = timed(lambda: _field_sum_grid(poly, nb, grid, dev, row0=r0, nrows=nr, cull_bits=0),
+               args.steps, args.warmup)
+    k_ms = float(np.mean(kt))
+    clocks = sampler.stop() if rank == 0 else None
+    k_evals = nb * nr * W
+    mufu_rate = k_evals * MUFU_PER_EVAL / (k_ms * 1e-3)
+    peak_mufu = sms * MUFU_PER_CLK_SM * pk["sm_max_mhz"] * 1e6
+    roofline = {"bound": "sfu", "kernel": "field_grid_kernel<16,8>", "achieved": mufu_rate / 1e9,
+                "peak": peak_mufu / 1e9, "unit": "GMUFU/s", "frac": mufu_rate / peak_mufu,
+                "traffic": None, "evals_per_s": k_evals / (k_ms * 1e-3), "kernel_ms": k_ms,
+                "peak_basis": f"{sms} SMs x 16 MUFU/clk x {pk['sm_max_mhz']:.0f} MHz (clocks.max.sm, "
+                              f"{pk['source']}); 3 MUFU per beamlet*pixel"}
+    if clocks and clocks.get("sm_mhz"):
+        roofline["frac_at_observed_clock"] = mufu_rate / (sms * MUFU_PER_CLK_SM * clocks["sm_mhz"] * 1e6)
+
+    # ---- end to end through the host-buffer C ABI (pinned inputs, D2H of the result)
+    def step_e2e():
+        return make_gaussian_image_host(g_pin, model, cull_bits=0, row0=r0, nrows=nr, device=local)
+    et = timed(step_e2e, args.steps, args.warmup, flush=False)
+    # host call is synchronous: wall time == device-bracketed time; use the events' span
+    e2e_ms = max_over_ranks(float(np.sum(et))) / args.steps
+    h2d = C2_NB * 8 * (7 + 1 + 2 + 2 + 1 + 1)
+    d2h = nr * W * 16
+    e2e = {"value": evals_per_step / (e2e_ms * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+           "api": "tg_make_gaussian_image_host (make_gaussian_image with host buffers)"}
+
+    # ---- ray half of the path: rays/s with the 5x5 ABCD, sharded, no communication
+    rays_section = {}
+    for label, n_rays in (("c1_1e6", 1_000_000), ("steady_1e7", 10_000_000)):
+        per = n_rays  # weak: every rank traces its own n_rays (C1 shape per GPU)
+        rng = np.random.default_rng(M.SEED + rank)
+        rr = M.random_rays(per, rng)
+        rd = Ray(*(torch.as_tensor(getattr(rr, f), device=dev) for f in RAY_FIELDS))
+        rmodel = M.readme_model()
+        keep = {}
+
+        def ray_step():
+            keep["o"] = run_to_end_abcd(rd, rmodel)
+        rt = timed(ray_step, args.steps, args.warmup, flush=(per * RAY_BYTES_ABCD < (200 << 20)))
+        r_ms = max_over_ranks(float(np.sum(rt))) / args.steps
+        rate = per * world / (r_ms * 1e-3)
+        gbs = per * RAY_BYTES_ABCD / (r_ms * 1e-3) / 1e9
+        rays_section[label] = {
+            "rays_per_s": rate, "ms_per_launch": r_ms, "rays_per_gpu": per, "scaling": "weak",
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / pk["hbm_gbs"], "traffic": None,
+                         "bytes_per_ray": RAY_BYTES_ABCD, "peak_source": pk["source"]}}
+        del rd, keep
+        torch.cuda.empty_cache()
+    # ray e2e through the host C ABI (pinned numpy in/out), 1e6 rays per rank
+    rr = M.random_rays(1_000_000, np.random.default_rng(M.SEED + rank))
+    rp = Ray(*(torch.as_tensor(getattr(rr, f)).pin_memory() for f in RAY_FIELDS))
+    ret = timed(lambda: run_to_end_abcd(rp, M.readme_model()), max(3, args.steps // 2), 2, flush=False)
+    re_ms = max_over_ranks(float(np.mean(ret)))
+    rays_section["e2e_c1_1e6"] = {"rays_per_s": 1_000_000 * world / (re_ms * 1e-3), "ms_per_call": re_ms,
+                                  "h2d_bytes_per_step": 56_000_000, "d2h_bytes_per_step": 256_000_000,
+                                  "api": "tg_trace_f64_host (run_to_end_abcd with host buffers)"}
+
+    # ---- CPU baseline (rank 0, N = 1): the numpy oracle port on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, dt, ev = cpu_field_rate(256, 32, 1)
+        cpu = {"value": rate, "unit": "evals/s", "cores": 1, "kind": "port",
+               "sample": f"256 of {C2_NB} beamlets x 32 of {H} rows of C2 ({ev:.3g} evals, {dt:.1f} s), "
+                         "single-process numpy oracle (jax not installable; see DESIGN.md)"}
+
+    if rank == 0:
+        line = {
+            "metric": "beamlet_pixel_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "C2 aperture_diffraction: 1e4 Gaussian beamlets (fibonacci disc r=1e-7 m, "
+                                   "lambda=2 pm, w0=1 nm) through ParallelBeam->Lens(f=1e-2)->Detector, summed "
+                                   "on 1024x1024 px (dense, cull_bits=0)",
+                       "parallelism": f"detector rows sharded over {world} GPU(s); table broadcast + row "
+                                      "all-gather" if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (256 MiB write); inputs (0.96 MB table) are "
+                             "L2-resident by design",
+                       "phase": "fp64 setup -> 32-bit fixed-point turns; fp32 MUFU sin/cos/ex2; fp64 "
+                                "accumulation across 128-beamlet chunks"},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": n_launch,
+            "rays": rays_section, "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -190,13 +190,14 @@ int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6],
 /* All pointers HOST.  rays[7] are the central rays (length nb each), waist_xy /
  * radii_xy (nb,2), wavelength / theta / amplitude (nb,).  Traces the rays through
  * `model`, builds Q_inv, the coefficients, sums the field on the (H,W) grid given by
- * px2m and writes complex128 (H,W) to out. */
+ * px2m and writes rows [row0, row0+nrows) as (nrows,W) complex to out (the row range is what a
+ * rank of a row-sharded multi-GPU job computes; row0=0,nrows=H gives the whole image). */
 int tg_make_gaussian_image_host(const tg_model *model_host, int64_t nb,
                                 const double *const rays[7], const double *amplitude,
                                 const double *waist_xy, const double *radii_xy,
                                 const double *wavelength, const double *theta,
-                                const double px2m[6], int H, int W, void *out,
-                                int out_is_c128, int cull_bits, int device);
+                                const double px2m[6], int H, int W, int row0, int nrows,
+                                void *out, int out_is_c128, int cull_bits, int device);
 
 #ifdef __cplusplus
 }

@@ -63,7 +63,7 @@ SIGNATURES = {
     "tg_field_sum_points": (_i32, [_i64, _vp, _i64, _vp, _vp, _i32, _vp]),
     "tg_field_sum_separable": (_i32, [_i64, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "tg_make_gaussian_image_host": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(_vp), _vp, _vp, _vp,
-                                           _vp, _vp, _dp, _i32, _i32, _vp, _i32, _i32, _i32]),
+                                           _vp, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32]),
 }
 
 _lib = None

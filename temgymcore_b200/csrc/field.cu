@@ -447,6 +447,7 @@ extern "C" int tg_field_sum_grid(int64_t nb, const double *poly, const double px
   const long long tiles = (long long)g.tiles_x * g.tiles_y;
   int dev = 0, sms = 148;
   TG_CUDA(cudaGetDevice(&dev));
+  tg_tune_mempool(dev);
   TG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   g.nsplit = choose_split(tiles, nb, 2 * sms, cull_bits > 0, npix);
 

@@ -29,10 +29,29 @@ extern "C" int tg_device_count(void) {
   return n;
 }
 
+void tg_tune_mempool(int dev);
+
 namespace {
 
 constexpr int kSlots = 3;
 constexpr int64_t kChunkRays = 1 << 18;
+
+}  // namespace
+
+// Keep freed stream-ordered allocations cached in the device's default pool instead of
+// returning them to the driver at every synchronisation (the default threshold is 0).
+void tg_tune_mempool(int dev) {
+  static bool done[64] = {false};
+  if (dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ULL;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done[dev] = true;
+}
+
+namespace {
 
 struct DeviceGuard {
   int prev = -1;
@@ -40,6 +59,7 @@ struct DeviceGuard {
   explicit DeviceGuard(int dev) {
     if (cudaGetDevice(&prev) != cudaSuccess) return;
     ok = cudaSetDevice(dev) == cudaSuccess;
+    if (ok) tg_tune_mempool(dev);
   }
   ~DeviceGuard() {
     if (prev >= 0) cudaSetDevice(prev);
@@ -190,11 +210,13 @@ extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t n
                                            const double *const rays[7], const double *amplitude,
                                            const double *waist_xy, const double *radii_xy,
                                            const double *wavelength, const double *theta,
-                                           const double px2m[6], int H, int W, void *out,
-                                           int out_is_c128, int cull_bits, int device) {
+                                           const double px2m[6], int H, int W, int row0, int nrows,
+                                           void *out, int out_is_c128, int cull_bits, int device) {
   TG_REQUIRE(model_host && rays && amplitude && waist_xy && radii_xy && wavelength && theta && px2m && out,
              "null pointer");
   TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad sizes");
+  TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
+  if (nrows == 0) return TG_OK;
   DeviceGuard guard(device);
   if (!guard.ok) {
     tg_set_error("cudaSetDevice(%d) failed", device);
@@ -204,7 +226,7 @@ extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t n
   int rc = st.init(1);
   if (rc != TG_OK) return rc;
   cudaStream_t s = st.s[0];
-  const size_t npix = (size_t)H * W, elt = out_is_c128 ? 16 : 8;
+  const size_t npix = (size_t)nrows * W, elt = out_is_c128 ? 16 : 8;
   // device layout (doubles): rays 7n | amp n | waist 2n | radii 2n | wl n | theta n | k n | p0 n |
   //                          abcd 25n | qinv 8n | poly 12n | field
   const size_t nd = (size_t)nb * (7 + 1 + 2 + 2 + 1 + 1 + 1 + 1 + 25 + 8 + 12);
@@ -248,7 +270,7 @@ extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t n
     if (rc == TG_OK)
       rc = tg_beamlet_coeffs_abcd_f64(nb, damp, dp0, dq, dabcd, dr[0], dr[1], dr[2], dr[3], dk, dpoly, s);
   }
-  if (rc == TG_OK) rc = tg_field_sum_grid(nb, dpoly, px2m, H, W, 0, H, dout, out_is_c128, cull_bits, nullptr, s);
+  if (rc == TG_OK) rc = tg_field_sum_grid(nb, dpoly, px2m, H, W, row0, nrows, dout, out_is_c128, cull_bits, nullptr, s);
   if (rc == TG_OK) {
     e = cudaMemcpyAsync(out, dout, npix * elt, cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) {

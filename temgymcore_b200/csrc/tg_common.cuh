@@ -6,6 +6,7 @@
 #include "temgym_b200.h"
 
 void tg_set_error(const char *fmt, ...);
+void tg_tune_mempool(int dev);
 // k = 2 pi / wavelength, p0 = k * pathlength (reference gaussian.py:253-255); internal helper
 int tg_wave_numbers(int64_t nb, const double *wavelength, const double *pathlength, double *k,
                     double *p0, cudaStream_t st);

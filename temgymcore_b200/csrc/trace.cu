@@ -514,8 +514,8 @@ __global__ void __launch_bounds__(256)
     static_cast<double *>(px)[i] = tx;
   } else {
     // jnp.round(...).astype(int32) (grid.py:147-149): half-to-even, saturating, NaN -> 0
-    static_cast<int32_t *>(py)[i] = __double2int_rn(ty);
-    static_cast<int32_t *>(px)[i] = __double2int_rn(tx);
+    static_cast<int32_t *>(py)[i] = isnan(ty) ? 0 : __double2int_rn(ty);
+    static_cast<int32_t *>(px)[i] = isnan(tx) ? 0 : __double2int_rn(tx);
   }
 }
 

@@ -182,12 +182,59 @@ def _result_kind(obj) -> int:
     return max(A.kind_of(v) for v in vals)
 
 
+def _pinned_empty(shape, dtype):
+    """Pinned host buffer from torch's caching host allocator (D2H at full PCIe rate)."""
+    import torch
+    return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
 def _finish(out, kind):
     if kind == A.KIND_CUDA:
         return out
-    if kind == A.KIND_TORCH_CPU:
-        return out.cpu()
-    return out.cpu().numpy()
+    import torch
+    host = _pinned_empty(tuple(out.shape), out.dtype)
+    host.copy_(out, non_blocking=True)
+    torch.cuda.current_stream(out.device).synchronize()
+    return host if kind == A.KIND_TORCH_CPU else host.numpy()
+
+
+def make_gaussian_image_host(gaussian_rays, model, *, cull_bits=None, out_dtype=None, row0=0,
+                             nrows=None, device=None):
+    """``make_gaussian_image`` for HOST inputs through the single host-buffer C-ABI call
+    ``tg_make_gaussian_image_host`` (H2D copies, all kernels, D2H copy inside the call)."""
+    import torch
+    lib = L.load()
+    g = gaussian_rays
+    grid = model[-1]
+    H, W = int(grid.shape[0]), int(grid.shape[1])
+    nrows = H - row0 if nrows is None else nrows
+    n = 1
+    for f in RAY_FIELDS + ("amplitude", "wavelength", "theta"):
+        n = max(n, A.numel(getattr(g, f)))
+    n = max(n, A.numel(g.waist_xy) // 2, A.numel(g.radii_of_curv) // 2)
+
+    def vec(v, width=1):
+        h = A.to_host_f64(v)
+        if h.size == width and n > 1:
+            h = np.ascontiguousarray(np.broadcast_to(h.reshape(1, width), (n, width)).reshape(-1))
+        if h.size != n * width:
+            raise ValueError("GaussianRay fields have mismatched sizes")
+        return h
+
+    rays = [vec(getattr(g, f)) for f in RAY_FIELDS]
+    amp, wl, th = vec(g.amplitude), vec(g.wavelength), vec(g.theta)
+    waist, radii = vec(g.waist_xy, 2), vec(g.radii_of_curv, 2)
+    out_dtype = torch.complex128 if out_dtype is None else out_dtype
+    out = _pinned_empty((nrows, W), out_dtype)
+    cull = DEFAULT_CULL_BITS if cull_bits is None else int(cull_bits)
+    cm = compile_model(model)
+    dev = A.current_device_index() if device is None else int(device)
+    L.check(lib.tg_make_gaussian_image_host(
+        C.byref(cm), n, L.ptr_array([r.ctypes.data for r in rays]), amp.ctypes.data,
+        waist.ctypes.data, radii.ctypes.data, wl.ctypes.data, th.ctypes.data,
+        L.dbl_array(grid.px2m_affine), H, W, row0, nrows, out.data_ptr(),
+        int(out_dtype == torch.complex128), cull, dev), "tg_make_gaussian_image_host")
+    return out
 
 
 def beamlet_polynomials(gaussian_rays: GaussianRay, model):
@@ -241,6 +288,9 @@ def make_gaussian_image(gaussian_rays, model, batch_size=128, *, cull_bits=None,
     grid = model[-1]
     assert isinstance(grid, Grid)
     kind = _result_kind(rays)
+    if kind != A.KIND_CUDA:
+        out = make_gaussian_image_host(rays, model, cull_bits=cull_bits, out_dtype=out_dtype)
+        return out if kind == A.KIND_TORCH_CPU else out.numpy()
     poly, n, dev = beamlet_polynomials(rays, model)
     out = _field_sum_grid(poly, n, grid, dev, out_dtype=out_dtype, cull_bits=cull_bits)
     return _finish(out, kind)

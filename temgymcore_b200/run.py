@@ -60,6 +60,19 @@ def _host_z(z, model: L.tg_model) -> float:
     return z
 
 
+def _host_empty(shape) -> np.ndarray:
+    """fp64 host result buffer; page-locked (torch's caching host allocator) for large
+    results so the D2H copy inside tg_*_host runs at PCIe rate."""
+    n = int(np.prod(shape))
+    if n >= (1 << 15):
+        try:
+            import torch
+            return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+        except Exception:  # noqa: BLE001 - no CUDA runtime: the call below fails loudly anyway
+            pass
+    return np.empty(shape, dtype=np.float64)
+
+
 # ----------------------------------------------------------------------------- kernel call
 def _trace(ray, model: L.tg_model, jac_layout: int = L.TG_JAC_NONE, want_rays: bool = True):
     """Run the ray kernel.  Returns (Ray | None, jac | None)."""
@@ -121,9 +134,9 @@ def _trace(ray, model: L.tg_model, jac_layout: int = L.TG_JAC_NONE, want_rays: b
             for i in range(7):
                 if scalar_out.get(i, False):
                     continue
-                outs[i] = np.empty(n, dtype=np.float64)
+                outs[i] = _host_empty((n,))
                 out_ptrs[i] = outs[i].ctypes.data
-        jac = np.empty((n, jdim, jdim), dtype=np.float64) if jw else None
+        jac = _host_empty((n, jdim, jdim)) if jw else None
         L.check(lib.tg_trace_f64_host(C.byref(model), n, C.byref(rin), L.ptr_array(out_ptrs),
                                       jac.ctypes.data if jw else None, jac_layout,
                                       A.current_device_index()), "tg_trace_f64_host")

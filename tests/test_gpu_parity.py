@@ -1,0 +1,444 @@
+"""GPU parity tests: the CUDA path (through the Python surface -> C ABI -> kernels) against
+the CPU oracle on the same seeded inputs, against the reference goldens, and -- at the
+BASELINE sizes -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star):
+  rays / ABCD / Jacobians : 1e-12 relative, fp64
+  detector complex field  : 1e-5 relative L2 (fp32 evaluation vs fp64 oracle)
+  pixel indices           : bit-exact
+"""
+import numpy as np
+import pytest
+
+from oracle import temgym_oracle as O
+from tests import models as M
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+FIELD_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from temgymcore_b200 import _lib as L
+    L.load()  # fails loudly if the native library is missing
+    return torch
+
+
+def close(got, ref, rtol=RTOL):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    scale = np.max(np.abs(ref)) if ref.size else 1.0
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=rtol * max(scale, 1e-300))
+
+
+def rel_l2(got, ref):
+    got, ref = np.asarray(got), np.asarray(ref)
+    return float(np.linalg.norm((got - ref).ravel()) / np.linalg.norm(ref.ravel()))
+
+
+def to_np(v):
+    return v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+
+
+def ray_to_cuda(torch, ray):
+    from temgymcore_b200.ray import RAY_FIELDS, Ray
+    return Ray(*(torch.as_tensor(np.asarray(getattr(ray, f), dtype=np.float64), device="cuda")
+                 for f in RAY_FIELDS))
+
+
+MODELS = {
+    "readme": M.readme_model,
+    "kitchen_sink": M.kitchen_sink_model,
+    "six_component_krivanek": M.six_component_column,
+    "biprism_column": lambda: M.biprism_model(dict(M1=-200, F1=0.0025, M2=-1500, F2=0.02, defocus=1e-9,
+                                                   def_x=-2e-5, aperture_radius=50e-9)),
+}
+
+
+def rays_for(name, n):
+    rng = np.random.default_rng(M.SEED)
+    if name == "six_component_krivanek":
+        return M.random_rays(n, rng, scale=0.2e-9, slope=1e-6)
+    if name == "biprism_column":
+        return M.random_rays(n, rng, scale=50e-9, slope=1e-7, z=1e-9)
+    return M.random_rays(n, rng)
+
+
+# ------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("name", sorted(MODELS))
+@pytest.mark.parametrize("path", ["device", "host"])
+def test_trace_parity(torch_cuda, name, path):
+    from temgymcore_b200.ray import RAY_FIELDS
+    from temgymcore_b200.run import ray_jacobian, run_to_end, run_to_end_abcd
+    n = 10007  # ragged: not a multiple of the block size
+    model = MODELS[name]()
+    rays = rays_for(name, n)
+    ref_out, ref_J = O.jacobian_run_to_end(rays, model)
+    ref_abcd = O.custom_jacobian_matrix(ref_J)
+    arg = ray_to_cuda(torch_cuda, rays) if path == "device" else rays
+    out = run_to_end(arg, model)
+    out2, abcd = run_to_end_abcd(arg, model)
+    J = ray_jacobian(arg, model).matrix
+    if path == "device":
+        assert out.x.is_cuda and abcd.is_cuda and tuple(abcd.shape) == (n, 5, 5)
+    else:
+        assert isinstance(out.x, np.ndarray) and isinstance(abcd, np.ndarray)
+    for f in RAY_FIELDS:
+        close(to_np(getattr(out, f)), getattr(ref_out, f))
+        np.testing.assert_array_equal(to_np(getattr(out, f)), to_np(getattr(out2, f)))
+    for i in range(5):
+        for j in range(5):  # entry-wise scale: the 5x5 spans 10+ orders of magnitude
+            close(to_np(abcd)[:, i, j], ref_abcd[:, i, j])
+    for i in range(7):
+        for j in range(7):
+            close(to_np(J)[:, i, j], ref_J[:, i, j])
+
+
+def test_trace_bit_exact_for_rational_models(torch_cuda):
+    """-fmad=false + reference operation order: models without transcendentals reproduce
+    the numpy oracle bit for bit."""
+    from temgymcore_b200.ray import RAY_FIELDS
+    from temgymcore_b200.run import run_to_end_abcd
+    for name in ("readme", "biprism_column"):
+        model, rays = MODELS[name](), rays_for(name, 4096)
+        ref_out, ref_abcd = O.abcd_run_to_end(rays, model)
+        out, abcd = run_to_end_abcd(ray_to_cuda(torch_cuda, rays), model)
+        for f in RAY_FIELDS:
+            np.testing.assert_array_equal(to_np(getattr(out, f)), getattr(ref_out, f))
+        np.testing.assert_array_equal(to_np(abcd), ref_abcd + 0.0)
+
+
+def test_scalar_and_mixed_rays(torch_cuda, goldens):
+    from temgymcore_b200.ray import Ray
+    from temgymcore_b200.run import ray_jacobian, run_to_end, run_to_end_abcd, solve_model
+    from temgymcore_b200.utils import custom_jacobian_matrix
+    g = goldens["readme_ray"]
+    model = M.build(g["model"])
+    out = run_to_end(Ray(**g["ray_in"]), model)  # README.md:35-52
+    assert isinstance(out.x, float)
+    assert (out.x, out.y, out.z) == (0.275, 0.4, 1.0) and abs(out.dx - 0.05) < 1e-15 and out.dy == 0.0
+    assert abs(out.pathlength - 0.88875) < 1e-15
+    # README.md:227-235
+    jac = ray_jacobian(Ray(**g["ray_in"]), model)
+    abcd = custom_jacobian_matrix(jac)
+    np.testing.assert_array_equal(abcd, np.array(goldens["readme_abcd"]["abcd"]))
+    assert jac.dy.x == 0.0 and jac.dx.x == -1.0  # README.md:147-160
+    _, abcd2 = run_to_end_abcd(Ray(**g["ray_in"]), model)
+    np.testing.assert_array_equal(abcd2, abcd)
+    # README.md:240-268
+    steps = solve_model(Ray(**g["ray_in"]), model)
+    np.testing.assert_array_equal(steps, np.array(goldens["readme_solve_model"]["per_step"]))
+    # Source.make_rays style: vector x..dy, scalar z / pathlength / _one (source.py:73-79)
+    rng = np.random.default_rng(5)
+    x, y, dx, dy = (rng.uniform(-0.1, 0.1, 301) for _ in range(4))
+    mixed = Ray(x=x, y=y, dx=dx, dy=dy, z=0.0, pathlength=0.0)
+    outm = run_to_end(mixed, model)
+    ref = O.run_to_end(mixed, model)
+    assert isinstance(outm.z, float) and outm.z == float(ref.z) and outm._one == 1.0
+    for f in ("x", "y", "dx", "dy", "pathlength"):
+        np.testing.assert_array_equal(getattr(outm, f), getattr(ref, f))
+
+
+def test_notebook_abcd_goldens(torch_cuda, goldens):
+    from temgymcore_b200.ray import Ray
+    from temgymcore_b200.run import run_to_end_abcd
+    g = goldens["aperture_diffraction_abcd"]
+    _, abcd = run_to_end_abcd(Ray(**g["ray_in"]), M.build(g["model"]))
+    np.testing.assert_allclose(abcd, np.array(g["abcd"]), rtol=g["rtol"], atol=g["atol"])
+    g = goldens["two_beam_abcd"]
+    model = M.two_beam_model(g["params"])
+    _, abcd = run_to_end_abcd(Ray(z=model[0].z, **g["ray_in"]), model)
+    np.testing.assert_allclose(abcd, np.array(g["abcd"]), rtol=g["rtol"], atol=1e-8)
+    g = goldens["biprism_abcd"]
+    model = M.biprism_model(g["params"])
+    _, abcd = run_to_end_abcd(Ray(z=model[0].z, **g["ray_in"]), model)
+    np.testing.assert_allclose(abcd, np.array(g["abcd"]), rtol=g["rtol"], atol=1e-14)
+
+
+def test_run_iter_matches_reference_contract(torch_cuda):
+    # reference tests/test_run.py:10-92
+    from temgymcore_b200.components import Descanner, Plane, Scanner
+    from temgymcore_b200.propagator import FreeSpaceParaxial, Propagator
+    from temgymcore_b200.ray import Ray
+    from temgymcore_b200.run import run_iter
+    from temgymcore_b200.source import PointSource
+    z = 1.2
+    comps = (PointSource(z=z, semi_conv=0.023), Scanner(z=z, scan_pos_x=23., scan_pos_y=42.), Plane(z=z),
+             Descanner(z=z, scan_pos_x=13., scan_pos_y=11.), Plane(z=3.1))
+    ray = Ray(x=0.12, y=0.23, dx=0.34, dy=0.45, z=z, pathlength=0.34)
+    res = list(run_iter(ray=ray, components=comps))
+    assert len(res) == 2 * len(comps)
+    prev = ray
+    for i, comp in enumerate(comps):
+        prop, prop_r = res[2 * i]
+        c, comp_r = res[2 * i + 1]
+        assert isinstance(prop, Propagator) and isinstance(prop.propagator, FreeSpaceParaxial)
+        assert prop.distance == comp.z - prev.z
+        np.testing.assert_allclose(prop_r.z, comp.z)
+        np.testing.assert_allclose(prop_r.x, prev.x + prev.dx * prop.distance)
+        assert c is comp
+        prev = comp_r
+    ref = O.run_to_end(ray, comps)
+    for f in ("x", "y", "dx", "dy", "z", "pathlength", "_one"):
+        np.testing.assert_allclose(getattr(res[-1][1], f), float(getattr(ref, f)), rtol=1e-15)
+    # component(ray) and FreeSpaceParaxial()(ray, d) single steps
+    out = Scanner(z=0.0, scan_pos_x=1.0, scan_pos_y=2.0)(ray)
+    assert (out.x, out.y, out.z) == (ray.x + 1.0, ray.y + 2.0, ray.z)
+    out = FreeSpaceParaxial()(ray, 0.5)
+    assert out.x == ray.x + ray.dx * 0.5 and out.z == ray.z + 0.5 and out.pathlength == ray.pathlength + 0.5
+
+
+def test_krivanek_on_axis_nan_like_jax(torch_cuda):
+    # jnp.hypot / arctan2 gradients at (0,0) are NaN (examples/aberrated_probe.ipynb skips it)
+    from temgymcore_b200.ray import Ray
+    from temgymcore_b200.run import run_to_end_abcd
+    model = M.six_component_column()
+    ray = Ray(x=np.zeros(3), y=np.zeros(3), dx=np.zeros(3), dy=np.zeros(3), z=np.zeros(3),
+              pathlength=np.zeros(3), _one=np.ones(3))
+    _, ref = O.abcd_run_to_end(ray, model)
+    _, got = run_to_end_abcd(ray, model)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+    assert np.isnan(got).any()
+
+
+# ------------------------------------------------------------------------------ K5
+@pytest.mark.parametrize("rot,flip,centre", [(0.0, False, (0.0, 0.0)), (17.0, True, (1e-3, -2e-3)),
+                                             (90.0, False, (0.0, 0.0)), (-133.7, True, (0.2, 0.1))])
+def test_metres_to_pixels_bit_exact(torch_cuda, rot, flip, centre):
+    from temgymcore_b200.components import Detector
+    det = Detector(z=0.0, pixel_size=(0.01, 0.013), shape=(128, 96), rotation=rot, centre=centre, flip_y=flip)
+    rng = np.random.default_rng(M.SEED)
+    n = 200003
+    x = rng.uniform(-1.0, 1.0, n)
+    y = rng.uniform(-1.0, 1.0, n)
+    x[:5] = [np.nan, np.inf, -np.inf, 1e300, -1e300]
+    ref_y, ref_x = O.grid_metres_to_pixels(det, (x, y))
+    py, px = det.metres_to_pixels((x, y))
+    assert py.dtype == np.int32
+    np.testing.assert_array_equal(py, ref_y)
+    np.testing.assert_array_equal(px, ref_x)
+    tpy, tpx = det.metres_to_pixels((torch_cuda.as_tensor(x, device="cuda"), torch_cuda.as_tensor(y, device="cuda")))
+    np.testing.assert_array_equal(to_np(tpy), ref_y)
+    np.testing.assert_array_equal(to_np(tpx), ref_x)
+    fy, fx = det.metres_to_pixels((x[5:], y[5:]), cast=False)
+    ry, rx = O.grid_metres_to_pixels(det, (x[5:], y[5:]), cast=False)
+    np.testing.assert_array_equal(fy, ry)
+    np.testing.assert_array_equal(fx, rx)
+    # half-way cases round to even (jnp.round): craft exact .5 pixel coordinates at rotation 0
+    if rot == 0.0 and not flip:
+        d2 = Detector(z=0.0, pixel_size=(0.25, 0.25), shape=(9, 9))
+        xs = np.array([-0.875, -0.625, -0.375, 0.125, 0.375])  # px = 0.5, 1.5, 2.5, 4.5, 5.5
+        py2, px2 = d2.metres_to_pixels((xs, np.zeros_like(xs)))
+        r2y, r2x = O.grid_metres_to_pixels(d2, (xs, np.zeros_like(xs)))
+        np.testing.assert_array_equal(px2, r2x)
+        np.testing.assert_array_equal(px2, [0, 2, 2, 4, 6])
+
+
+def test_grid_tables_and_coords(torch_cuda, goldens):
+    from temgymcore_b200.components import Detector, ScanGrid
+    g = goldens["grid_tables"]
+    for xy, rot, exp in g["m2p"]:
+        grid = ScanGrid(z=0.0, rotation=rot, pixel_size=tuple(g["pixel_size"]), shape=tuple(g["shape"]))
+        py, px = grid.metres_to_pixels((xy[0], xy[1]))
+        assert (int(py), int(px)) == tuple(exp)
+    for pix, rot, exp in g["p2m"]:
+        grid = ScanGrid(z=0.0, rotation=rot, pixel_size=tuple(g["pixel_size"]), shape=tuple(g["shape"]))
+        mx, my = grid.pixels_to_metres((pix[0], pix[1]))
+        np.testing.assert_allclose([mx, my], exp, atol=g["atol"])
+    det = Detector(z=0.0, pixel_size=(0.01, 0.02), shape=(37, 53), rotation=17.0, centre=(0.1, -0.2), flip_y=True)
+    np.testing.assert_array_equal(det.coords, O.grid_coords(det))
+    x1, y1 = det.coords_1d
+    assert x1.shape == (53,) and y1.shape == (37,)
+
+
+def test_into_image(torch_cuda):
+    from temgymcore_b200.components import Detector
+    det = Detector(z=1.0, pixel_size=(0.01, 0.01), shape=(128, 128))
+    rays = M.random_rays(50000, scale=0.8)  # some rays fall off the detector
+    img = det.into_image(rays)
+    ref = O.grid_into_image(det, O.Ray.from_obj(rays))
+    assert img.shape == (128, 128) and img.sum() == ref.sum() < 50000
+    np.testing.assert_array_equal(img, ref)
+
+
+# ------------------------------------------------------------------------------ K2 + K3
+def test_free_space_field_kat(torch_cuda, goldens):
+    """reference tests/test_gaussians.py:229-273 (its rtol 1e-9 is for the fp64 reference;
+    the fp32-evaluated CUDA sum is held to the north-star 1e-5)."""
+    from temgymcore_b200.gaussian import propagate_misaligned_gaussian_jax_scan
+    from tests.test_oracle_goldens import free_space_kat_inputs
+    a, expected = free_space_kat_inputs(goldens["free_space_field_kat"])
+    field = propagate_misaligned_gaussian_jax_scan(a["amp"], a["phase_offset"], a["Q1_inv"], a["A"], a["B"],
+                                                   a["C"], a["D"], a["e"], a["f"], a["r1m"], a["theta1m"],
+                                                   a["k"], a["r2"])
+    assert field.shape == expected.shape and field.dtype == np.complex128
+    assert rel_l2(field, expected) < FIELD_TOL
+    np.testing.assert_allclose(field, expected, rtol=1e-5, atol=1e-7)
+
+
+def field_cases():
+    rng = np.random.default_rng(M.SEED)
+    cases = {}
+    cases["c2_aperture"] = M.aperture_diffraction_case(400, (96, 160))
+    cases["c3_biprism_separable"] = M.biprism_case(600, (256, 256))
+    cases["c3_biprism_general"] = M.biprism_case(500, (200, 136), general=True, rng=rng)
+    # tilted, curved, astigmatic, rotated beamlets through lens + deflector onto a rotated,
+    # offset, flipped detector (the case no reference test pins tightly: oracle restatement only)
+    nb = 300
+    from temgymcore_b200.components import Deflector, Detector, Lens
+    from temgymcore_b200.source import ParallelBeam
+    x, y = rng.uniform(-2e-4, 2e-4, (2, nb))
+    g = M.gaussian_rays(x, y, dx=rng.uniform(-2e-4, 2e-4, nb), dy=rng.uniform(-2e-4, 2e-4, nb),
+                        wavelength=500e-9, amplitude=rng.uniform(0.5, 1.5, nb),
+                        waist_xy=rng.uniform(0.5e-4, 2e-4, (nb, 2)), radii=rng.uniform(0.5, 3.0, (nb, 2)),
+                        theta=rng.uniform(-np.pi, np.pi, nb), pathlength=rng.uniform(0, 1e-6, nb))
+    model = [ParallelBeam(z=0.0, radius=1e-3), Lens(z=0.1, focal_length=0.3),
+             Deflector(z=0.15, def_x=3e-4, def_y=-2e-4),
+             Detector(z=0.4, pixel_size=(8e-6, 6e-6), shape=(150, 170), rotation=-23.0, centre=(2e-5, -5e-5),
+                      flip_y=True)]
+    cases["misaligned_astigmatic"] = (g, model)
+    return cases
+
+
+@pytest.mark.parametrize("name", ["c2_aperture", "c3_biprism_separable", "c3_biprism_general",
+                                  "misaligned_astigmatic"])
+@pytest.mark.parametrize("cull_bits", [0, 40])
+def test_make_gaussian_image_parity(torch_cuda, name, cull_bits):
+    from temgymcore_b200.gaussian import make_gaussian_image
+    g, model = field_cases()[name]
+    ref = O.make_gaussian_image(g, model)
+    got = make_gaussian_image(g, model, cull_bits=cull_bits)
+    assert isinstance(got, np.ndarray) and got.dtype == np.complex128 and got.shape == tuple(model[-1].shape)
+    err = rel_l2(got, ref)
+    assert err < FIELD_TOL, f"{name}: rel L2 {err:.3e}"
+
+
+def test_make_gaussian_image_device_and_c64(torch_cuda):
+    from dataclasses import fields, replace
+    from temgymcore_b200.gaussian import make_gaussian_image
+    g, model = field_cases()["c2_aperture"]
+    ref = O.make_gaussian_image(g, model)
+    gd = replace(g, **{f.name: torch_cuda.as_tensor(getattr(g, f.name), device="cuda") for f in fields(g)})
+    got = make_gaussian_image(gd, model, cull_bits=0)
+    assert got.is_cuda and got.dtype == torch_cuda.complex128
+    assert rel_l2(to_np(got), ref) < FIELD_TOL
+    got32 = make_gaussian_image(gd, model, cull_bits=0, out_dtype=torch_cuda.complex64)
+    assert got32.dtype == torch_cuda.complex64 and rel_l2(to_np(got32), ref) < FIELD_TOL
+
+
+def test_input_image_parity(torch_cuda):
+    from temgymcore_b200.components import Detector
+    from temgymcore_b200.gaussian import evaluate_gaussian_input_image
+    g, _ = M.aperture_diffraction_case(500, (64, 64))
+    det = Detector(pixel_size=(1e-6 / 128, 1e-6 / 128), shape=(128, 128), z=0.0)
+    ref = O.evaluate_gaussian_input_image(g, det)
+    got = evaluate_gaussian_input_image(g, det, batch_size=10)
+    assert rel_l2(got, ref) < FIELD_TOL
+    # scalar wavelength is broadcast on the input plane (gaussian.py:385)
+    from dataclasses import replace
+    got2 = evaluate_gaussian_input_image(replace(g, wavelength=2e-12), det)
+    assert rel_l2(got2, ref) < FIELD_TOL
+
+
+def test_field_edge_cases(torch_cuda):
+    from temgymcore_b200.components import Detector
+    from temgymcore_b200.gaussian import make_gaussian_image
+    from temgymcore_b200.source import ParallelBeam
+    # single scalar GaussianRay (examples/two_beam_interference.ipynb cell 1)
+    from temgymcore_b200.gaussian import GaussianRay
+    det = Detector(z=1, pixel_size=(1e-4, 1e-4), shape=(64, 200))
+    one = GaussianRay(x=0.0, y=0.0, dx=1e-2, dy=0.0, wavelength=1e-5, waist_xy=(1e-4, 1e-4),
+                      radii_of_curv=(0.01, 0.01), z=0.0, pathlength=0.0, amplitude=1.0, theta=0.0)
+    got = make_gaussian_image(one, [det], batch_size=1)
+    ref = O.make_gaussian_image(one, [det])
+    assert got.shape == (64, 200) and rel_l2(got, ref) < FIELD_TOL
+    # detector at the rays' own z: B == 0 -> the reference yields NaN everywhere (gaussian.py:305)
+    g, _ = M.aperture_diffraction_case(7, (64, 64))
+    det0 = Detector(z=0.0, pixel_size=(1e-9, 1e-9), shape=(16, 16))
+    ref = O.make_gaussian_image(g, [ParallelBeam(z=0.0, radius=1e-7), det0])
+    got = make_gaussian_image(g, [ParallelBeam(z=0.0, radius=1e-7), det0])
+    assert np.isnan(ref).all() and np.isnan(got).all()
+
+
+def test_row_shard_and_linearity_small(torch_cuda):
+    from dataclasses import fields, replace
+    from temgymcore_b200.gaussian import _field_sum_grid, beamlet_polynomials
+    g, model = field_cases()["c3_biprism_general"]
+    poly, n, dev = beamlet_polynomials(g, model)
+    grid = model[-1]
+    full = to_np(_field_sum_grid(poly, n, grid, dev, cull_bits=0))
+    H = grid.shape[0]
+    parts = [to_np(_field_sum_grid(poly, n, grid, dev, row0=r0, nrows=nr, cull_bits=0))
+             for r0, nr in ((0, 67), (67, 1), (68, H - 68))]
+    np.testing.assert_array_equal(np.concatenate(parts, axis=0), full)  # row shards are bit-identical
+    a = to_np(_field_sum_grid(poly[: n // 2].contiguous(), n // 2, grid, dev, cull_bits=0))
+    b = to_np(_field_sum_grid(poly[n // 2:].contiguous(), n - n // 2, grid, dev, cull_bits=0))
+    assert rel_l2(a + b, full) < 1e-6
+
+
+# ------------------------------------------------------------------------------ BASELINE sizes
+def test_c1_full_size_rays(torch_cuda):
+    """Config C1: 1e6 rays through Lens(f=1, z=0.5) + Detector(128x128) with ABCD; checked
+    against the analytic 5x5 (README.md:227-235) and sampled rows against the oracle."""
+    from temgymcore_b200.run import run_to_end_abcd
+    n = 1_000_000
+    rays = M.random_rays(n)
+    out, abcd = run_to_end_abcd(ray_to_cuda(torch_cuda, rays), M.readme_model())
+    ref5 = torch_cuda.tensor([[.5, 0, .75, 0, 0], [0, .5, 0, .75, 0], [-1, 0, .5, 0, 0], [0, -1, 0, .5, 0],
+                              [0, 0, 0, 0, 1]], dtype=torch_cuda.float64, device="cuda")
+    assert bool((abcd == ref5).all())
+    idx = np.random.default_rng(1).integers(0, n, 5000)
+    sub = type(rays)(*(np.asarray(getattr(rays, f))[idx] for f in ("x", "y", "dx", "dy", "z", "pathlength", "_one")))
+    ref = O.run_to_end(sub, M.readme_model())
+    for f in ("x", "y", "dx", "dy", "z", "pathlength", "_one"):
+        np.testing.assert_array_equal(to_np(getattr(out, f))[idx], getattr(ref, f))
+
+
+def test_c2_full_size_field(torch_cuda):
+    """Config C2 at full size (1e4 beamlets x 1024^2): sampled pixels against the oracle,
+    linearity over beamlet halves, and culled == dense."""
+    from temgymcore_b200.gaussian import _field_sum_grid, beamlet_polynomials
+    g, model = M.aperture_diffraction_case(10_000, (1024, 1024))
+    grid = model[-1]
+    poly, n, dev = beamlet_polynomials(g, model)
+    full = to_np(_field_sum_grid(poly, n, grid, dev, cull_bits=0))
+    # oracle on 2048 sampled pixels
+    rng = np.random.default_rng(M.SEED)
+    pix = rng.integers(0, 1024 * 1024, 2048)
+    r2 = O.grid_coords(grid)[pix]
+    gd = O._gr_arrays(g)
+    central = O.Ray(*(gd[f] for f in O.RAY_FIELDS))
+    _, J = O.jacobian_run_to_end(central, model)
+    ab = O.custom_jacobian_matrix(J)
+    Q1 = O.gaussian_Q_inv(gd["waist_xy"], gd["radii_of_curv"], gd["wavelength"], gd["theta"])
+    k = 2 * np.pi / gd["wavelength"]
+    ref = O.propagate_misaligned_gaussian(gd["amplitude"], k * gd["pathlength"], Q1, ab[:, 0:2, 0:2],
+                                          ab[:, 0:2, 2:4], ab[:, 2:4, 0:2], ab[:, 2:4, 2:4], ab[:, 0:2, 4],
+                                          ab[:, 2:4, 4], np.stack([gd["x"], gd["y"]], -1),
+                                          np.stack([gd["dx"], gd["dy"]], -1), k, r2)
+    assert rel_l2(full.reshape(-1)[pix], ref) < FIELD_TOL
+    half = n // 2
+    a = to_np(_field_sum_grid(poly[:half].contiguous(), half, grid, dev, cull_bits=0))
+    b = to_np(_field_sum_grid(poly[half:].contiguous(), n - half, grid, dev, cull_bits=0))
+    assert rel_l2(a + b, full) < 1e-6
+    culled = to_np(_field_sum_grid(poly, n, grid, dev, cull_bits=40))
+    assert rel_l2(culled, full) < 1e-7
+
+
+def test_c3_culling_consistency(torch_cuda):
+    """Config C3 geometry (narrow envelopes): the tile-culled sum equals the dense sum and
+    executes far fewer evaluations."""
+    from temgymcore_b200.gaussian import _field_sum_grid, beamlet_polynomials
+    g, model = M.biprism_case(4000, (1024, 1024))
+    grid = model[-1]
+    poly, n, dev = beamlet_polynomials(g, model)
+    dense, ev_d = _field_sum_grid(poly, n, grid, dev, cull_bits=0, count_evals=True)
+    cull, ev_c = _field_sum_grid(poly, n, grid, dev, cull_bits=40, count_evals=True)
+    assert ev_d == n * 1024 * 1024
+    assert ev_c < ev_d / 4
+    assert rel_l2(to_np(cull), to_np(dense)) < 1e-7
