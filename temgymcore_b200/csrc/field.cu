@@ -29,7 +29,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kChunk = 128;          // beamlets per staged chunk
-constexpr int kRecDoubles = 14;      // tile-local record: 6 phase + 6 envelope + {dd,g2} + pad
+constexpr int kRecDoubles = 16;      // tile-local record: 6 phase + 6 envelope + vertex(2) + {dd,e2} + pad
 constexpr double kMagic = 1572864.0; // 1.5 * 2^20: ulp = 2^-32 -> low mantissa word = frac * 2^32
 constexpr double kInv2Pi = 0.15915494309189533577;
 constexpr double kLog2e = 1.4426950408889634074;
@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(128)
 struct __align__(16) Rec {
   double th[6];   // tile-local phase coefficients, turns, reduced to [-0.5, 0.5]
   double en[6];   // tile-local envelope coefficients (bits, amplitude = 2^en(u,v))
+  double vs0, vs1; // column of the envelope's vertex along row u: vs0 + vs1 * u (0,0 if none)
   uint32_t dd;    // second difference of the phase along a row, fixed point 2^-32 turn
   float e2;       // en[3] as fp32
   double pad;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 
   // per-thread strip constants (exact small integers in fp64)
   const double ud = (double)u, vd = (double)v0;
-  const double uu = ud * ud, uv = ud * vd, vv = vd * vd, tv1 = 2.0 * vd + 1.0, tv = 2.0 * vd;
+
 
   double thr_bits = INFINITY;  // cull when min envelope exponent g over tile > thr_bits
   if (g.cull_bits > 0 && gref_key) {
@@ -234,6 +235,14 @@ __global__ void __launch_bounds__(kThreads, 2)
       rec.en[5] = e[5];
       rec.e2 = (float)e[3];
       rec.pad = 0.0;
+      // vertex of the (concave) envelope exponent along a row: d/dv = 0
+      rec.vs0 = 0.0;
+      rec.vs1 = 0.0;
+      if (rec.en[3] < -1e-12) {
+        const double inv = -0.5 / rec.en[3];
+        const double a0 = rec.en[1] * inv, a1 = rec.en[4] * inv;
+        if (isfinite(a0) && isfinite(a1)) { rec.vs0 = a0; rec.vs1 = a1; }
+      }
       keep = true;
       if (thr_bits < INFINITY) {
         double G[6];
@@ -275,21 +284,35 @@ __global__ void __launch_bounds__(kThreads, 2)
     for (int n = 0; n < n_active; ++n) {
       const Rec &q = sm.rec[n];
       // strip-start phase and first difference (turns), fp64 -> 2^-32 fixed point
-      const double th0 = q.th[0] + q.th[1] * vd + q.th[2] * ud + q.th[3] * vv + q.th[4] * uv + q.th[5] * uu;
-      const double dl0 = q.th[1] + q.th[3] * tv1 + q.th[4] * ud;
+      // (Horner in v then u: only the two per-thread constants ud, vd stay live in registers)
+      const double rt = fma(q.th[4], ud, q.th[1]);                  // T1 + T4 u
+      const double wt = fma(q.th[3], vd, rt);                       // T1 + T4 u + T3 v0
+      const double th0 = fma(vd, wt, fma(ud, fma(q.th[5], ud, q.th[2]), q.th[0]));
+      const double dl0 = fma(q.th[3], vd, wt + q.th[3]);            // T1 + T4 u + T3 (2 v0 + 1)
       const uint32_t t0 = (uint32_t)__double2loint(th0 + kMagic) + 0x100u;  // +0.5 ulp of the 23-bit angle
       const uint32_t d0 = (uint32_t)__double2loint(dl0 + kMagic);
       const uint32_t dd = q.dd;
-      // strip-local envelope Horner (bits): e(j) = e0 + j (e1 + j e2)
-      const float e0 = (float)(q.en[0] + q.en[1] * vd + q.en[2] * ud + q.en[3] * vv + q.en[4] * uv + q.en[5] * uu);
-      const float e1 = (float)(q.en[1] + q.en[3] * tv + q.en[4] * ud);
+      // envelope exponent (bits) expanded about an integer PIVOT pixel jp of the strip, the one
+      // nearest the envelope's vertex: e(j) = ep + (j-jp) (e1p + (j-jp) e2).  Near a narrow
+      // (even sub-pixel) peak the two terms are small, away from it they have equal signs, so
+      // fp32 never cancels where the amplitude matters; broad envelopes are insensitive to jp.
+      // pivot = clamp(round(vertex column - strip start), 0, L-1), all without the XU pipe:
+      // round via the 1.5*2^52 mantissa trick, clamp as integer, rebuild float/double by bits
+      const double jsd = fma(q.vs1, ud, q.vs0 - vd) + 6755399441055744.0;
+      const int ji = min(max(__double2loint(jsd), 0), L - 1);
+      const float jp = __uint_as_float(0x4b000000u | (uint32_t)ji) - 8388608.0f;
+      const double vp = __hiloint2double(0x43300000, ji) + (vd - 4503599627370496.0);
+      const double r1 = q.en[1] + q.en[4] * ud;
+      const float ep = (float)(q.en[0] + ud * (q.en[2] + q.en[5] * ud) + vp * (r1 + q.en[3] * vp));
+      const float e1p = (float)(r1 + 2.0 * q.en[3] * vp);
       const float e2 = q.e2;
 #pragma unroll
       for (int j = 0; j < L; ++j) {
         const uint32_t tj = t0 + (uint32_t)j * d0 + (uint32_t)(j * (j - 1) / 2) * dd;
         const float ft = __uint_as_float((tj >> 9) | 0x3f800000u);       // 1 + frac(turns)
         const float ang = fmaf(ft, 6.28318530717958648f, -9.42477796076937972f);  // 2pi frac - pi
-        const float ej = fmaf((float)j, fmaf((float)j, e2, e1), e0);
+        const float dj = (float)j - jp;
+        const float ej = fmaf(dj, fmaf(dj, e2, e1p), ep);
         float amp, sn, cs;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(amp) : "f"(ej));
         sn = __sinf(ang);
@@ -399,10 +422,7 @@ int choose_split(long long tiles, long long nb, int slots, bool culling, size_t 
   long long max_s = 32 < max_by_chunks ? 32 : max_by_chunks;
   const size_t ws_cap = (size_t)1 << 30;  // <= 1 GiB of split partials
   while (max_s > 1 && (size_t)max_s * npix * 16 > ws_cap) --max_s;
-  if (culling) {
-    long long s = tiles >= slots ? 1 : (slots + tiles - 1) / tiles;
-    return (int)(s < max_s ? s : max_s);
-  }
+  (void)culling;  // culled work is irregular; finer granularity only helps balance
   double best_eff = -1.0;
   int best = 1;
   for (long long s = 1; s <= max_s; ++s) {

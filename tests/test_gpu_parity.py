@@ -375,7 +375,12 @@ def test_row_shard_and_linearity_small(torch_cuda):
     H = grid.shape[0]
     parts = [to_np(_field_sum_grid(poly, n, grid, dev, row0=r0, nrows=nr, cull_bits=0))
              for r0, nr in ((0, 67), (67, 1), (68, H - 68))]
-    np.testing.assert_array_equal(np.concatenate(parts, axis=0), full)  # row shards are bit-identical
+    # shards re-centre tiles on other origins and may use another beamlet split: equal to
+    # rounding of the fp32 evaluation, not bitwise
+    assert rel_l2(np.concatenate(parts, axis=0), full) < 1e-6
+    aligned = [to_np(_field_sum_grid(poly, n, grid, dev, row0=r0, nrows=nr, cull_bits=0))
+               for r0, nr in ((0, 64), (64, 96), (160, H - 160))]
+    assert rel_l2(np.concatenate(aligned, axis=0), full) < 1e-6
     a = to_np(_field_sum_grid(poly[: n // 2].contiguous(), n // 2, grid, dev, cull_bits=0))
     b = to_np(_field_sum_grid(poly[n // 2:].contiguous(), n - n // 2, grid, dev, cull_bits=0))
     assert rel_l2(a + b, full) < 1e-6
@@ -426,8 +431,9 @@ def test_c2_full_size_field(torch_cuda):
     a = to_np(_field_sum_grid(poly[:half].contiguous(), half, grid, dev, cull_bits=0))
     b = to_np(_field_sum_grid(poly[half:].contiguous(), n - half, grid, dev, cull_bits=0))
     assert rel_l2(a + b, full) < 1e-6
-    culled = to_np(_field_sum_grid(poly, n, grid, dev, cull_bits=40))
-    assert rel_l2(culled, full) < 1e-7
+    culled, ev = _field_sum_grid(poly, n, grid, dev, cull_bits=40, count_evals=True)
+    assert ev == n * 1024 * 1024  # C2 is dense: every beamlet covers the whole detector
+    np.testing.assert_array_equal(to_np(culled), full)
 
 
 def test_c3_culling_consistency(torch_cuda):
@@ -441,4 +447,4 @@ def test_c3_culling_consistency(torch_cuda):
     cull, ev_c = _field_sum_grid(poly, n, grid, dev, cull_bits=40, count_evals=True)
     assert ev_d == n * 1024 * 1024
     assert ev_c < ev_d / 4
-    assert rel_l2(to_np(cull), to_np(dense)) < 1e-7
+    assert rel_l2(to_np(cull), to_np(dense)) < 1e-6

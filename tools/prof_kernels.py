@@ -1,0 +1,34 @@
+"""Launches exactly the kernels we profile, a few times each, so `ncu -k regex:... -s N -c 1`
+hits a warm, full-size launch.  Usage: python tools/prof_kernels.py [field|trace|trace_c4|all]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests import models as M  # noqa: E402
+from temgymcore_b200.gaussian import _field_sum_grid, beamlet_polynomials  # noqa: E402
+from temgymcore_b200.ray import RAY_FIELDS, Ray  # noqa: E402
+from temgymcore_b200.run import run_to_end_abcd  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+dev = torch.device("cuda", 0)
+if what in ("field", "all"):
+    g, model = M.aperture_diffraction_case(10_000, (1024, 1024))
+    poly, n, _ = beamlet_polynomials(g, model)
+    for _ in range(3):
+        _field_sum_grid(poly, n, model[-1], dev, cull_bits=0)
+    torch.cuda.synchronize()
+if what in ("trace", "all"):
+    rr = M.random_rays(10_000_000)
+    rd = Ray(*(torch.as_tensor(getattr(rr, f), device=dev) for f in RAY_FIELDS))
+    for _ in range(3):
+        o = run_to_end_abcd(rd, M.readme_model())
+    torch.cuda.synchronize()
+if what in ("trace_c4", "all"):
+    rr = M.random_rays(10_000_000, scale=0.2e-9, slope=1e-6)
+    rd = Ray(*(torch.as_tensor(getattr(rr, f), device=dev) for f in RAY_FIELDS))
+    for _ in range(3):
+        o = run_to_end_abcd(rd, M.six_component_column())
+    torch.cuda.synchronize()
