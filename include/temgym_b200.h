@@ -180,11 +180,21 @@ int tg_field_sum_grid(int64_t nb, const double *poly, const double px2m[6], int 
 int tg_field_sum_points(int64_t nb, const double *poly, int64_t npts, const double *r_xy,
                         void *out, int out_is_c128, void *stream);
 
-/* Tensor-core path for separable beamlets (cross term c4 == 0 for every beamlet and an
- * axis-aligned grid).  Returns TG_ENOTSEPARABLE otherwise. */
+/* Tensor-core path (tcgen05, 3xTF32) for separable beamlets: when no beamlet has a col*row
+ * term on this pixel grid, exp(iP) = U(row) V(col) and the sum is the complex GEMM
+ * F = U^T V with K = nb.  Returns TG_ENOTSEPARABLE otherwise (then use tg_field_sum_grid).
+ * Synchronises `stream` once (separability verdict). */
 int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6], int H,
                            int W, int row0, int nrows, void *out, int out_is_c128,
                            void *stream);
+
+/* D[M x N] = (A_hi + A_lo)[M x K] * (B_hi + B_lo)[N x K]^T, products hi*hi + hi*lo + lo*hi on the
+ * tensor cores (kind::tf32, fp32 TMEM accumulation drained every 128 k), fp64 output with row pitch
+ * ldd.  Operands: device fp32, row pitch ldk elements (multiple of 4), 16-byte aligned; hi parts
+ * must be TF32-representable.  The GEMM engine of tg_field_sum_separable, exposed for testing. */
+int tg_gemm_tf32x3(int M, int N, int K, const float *A_hi, const float *A_lo, const float *B_hi,
+                   const float *B_lo, long long ldk, double *D, long long ldd, int accumulate,
+                   void *stream);
 
 /* ---- host-buffer field sum (make_gaussian_image end to end, gaussian.py:225-273) -- */
 /* All pointers HOST.  rays[7] are the central rays (length nb each), waist_xy /
@@ -197,7 +207,13 @@ int tg_make_gaussian_image_host(const tg_model *model_host, int64_t nb,
                                 const double *waist_xy, const double *radii_xy,
                                 const double *wavelength, const double *theta,
                                 const double px2m[6], int H, int W, int row0, int nrows,
-                                void *out, int out_is_c128, int cull_bits, int device);
+                                void *out, int out_is_c128, int cull_bits, int method,
+                                int device);
+
+/* `method` of tg_make_gaussian_image_host */
+#define TG_METHOD_AUTO 0   /* tensor-core path when the beamlets are separable, else SFU kernel */
+#define TG_METHOD_SFU 1    /* tg_field_sum_grid */
+#define TG_METHOD_TENSOR 2 /* tg_field_sum_separable (TG_ENOTSEPARABLE if it does not apply) */
 
 #ifdef __cplusplus
 }

@@ -438,6 +438,14 @@ int choose_split(long long tiles, long long nb, int slots, bool culling, size_t 
 
 }  // namespace
 
+// shared with separable.cu: metre-space polynomials -> pixel-space {turns, bits} table
+int tg_launch_prep(int64_t nb, const double *poly, const double px2m[6], int H, int W, double *table,
+                   unsigned long long *gref_key, cudaStream_t st) {
+  prep_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(nb, poly, px2m[0], px2m[1], px2m[2], px2m[3],
+                                                            px2m[4], px2m[5], H, W, table, gref_key);
+  return tg_launch_check("prep_kernel");
+}
+
 extern "C" int tg_field_sum_grid(int64_t nb, const double *poly, const double px2m[6], int H, int W,
                                  int row0, int nrows, void *out, int out_is_c128, int cull_bits,
                                  long long *n_evals_out, void *stream) {
@@ -483,10 +491,7 @@ extern "C" int tg_field_sum_grid(int64_t nb, const double *poly, const double px
   TG_CUDA(cudaMemsetAsync(gref, 0xFF, 8, st));
   TG_CUDA(cudaMemsetAsync(evals, 0, 8, st));
 
-  prep_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(
-      nb, poly, px2m[0], px2m[1], px2m[2], px2m[3], px2m[4], px2m[5], H, W, table,
-      cull_bits > 0 ? gref : nullptr);
-  int rc = tg_launch_check("prep_kernel");
+  int rc = tg_launch_prep(nb, poly, px2m, H, W, table, cull_bits > 0 ? gref : nullptr, st);
   if (rc == TG_OK) {
     const size_t smem = sizeof(S);
     cudaError_t e = cudaFuncSetAttribute(field_grid_kernel<L, SPR>,
@@ -530,10 +535,4 @@ extern "C" int tg_field_sum_points(int64_t nb, const double *poly, int64_t npts,
   field_points_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       nb, poly, npts, r_xy, out, out_is_c128);
   return tg_launch_check("field_points_kernel");
-}
-
-extern "C" int tg_field_sum_separable(int64_t, const double *, const double *, int, int, int, int,
-                                      void *, int, void *) {
-  tg_set_error("tg_field_sum_separable: tensor-core path not built in this round");
-  return TG_EUNSUPPORTED;
 }

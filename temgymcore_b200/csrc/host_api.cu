@@ -211,7 +211,8 @@ extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t n
                                            const double *waist_xy, const double *radii_xy,
                                            const double *wavelength, const double *theta,
                                            const double px2m[6], int H, int W, int row0, int nrows,
-                                           void *out, int out_is_c128, int cull_bits, int device) {
+                                           void *out, int out_is_c128, int cull_bits, int method,
+                                           int device) {
   TG_REQUIRE(model_host && rays && amplitude && waist_xy && radii_xy && wavelength && theta && px2m && out,
              "null pointer");
   TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad sizes");
@@ -270,7 +271,16 @@ extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t n
     if (rc == TG_OK)
       rc = tg_beamlet_coeffs_abcd_f64(nb, damp, dp0, dq, dabcd, dr[0], dr[1], dr[2], dr[3], dk, dpoly, s);
   }
-  if (rc == TG_OK) rc = tg_field_sum_grid(nb, dpoly, px2m, H, W, row0, nrows, dout, out_is_c128, cull_bits, nullptr, s);
+  if (rc == TG_OK) {
+    bool done = false;
+    if (method == TG_METHOD_AUTO || method == TG_METHOD_TENSOR) {
+      rc = tg_field_sum_separable(nb, dpoly, px2m, H, W, row0, nrows, dout, out_is_c128, s);
+      if (rc == TG_OK) done = true;
+      else if (rc == TG_ENOTSEPARABLE && method == TG_METHOD_AUTO) rc = TG_OK;
+    }
+    if (rc == TG_OK && !done)
+      rc = tg_field_sum_grid(nb, dpoly, px2m, H, W, row0, nrows, dout, out_is_c128, cull_bits, nullptr, s);
+  }
   if (rc == TG_OK) {
     e = cudaMemcpyAsync(out, dout, npix * elt, cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) {

@@ -1,0 +1,499 @@
+// K4: tensor-core field sum for SEPARABLE beamlets (tcgen05 / TMEM / TMA, sm_100a).
+//
+// When the pixel-space polynomial of every beamlet has no col*row term,
+//     exp(i P_n(row, col)) = U_n(row) * V_n(col)        (complex),
+// and the field sum of the reference (gaussian.py:319-369) is the complex GEMM
+//     F[row, col] = sum_n U[n,row] V[n,col],           K = number of beamlets.
+// BASELINE configs C2 and C3 are of this kind (isotropic beamlets through Lens / free space /
+// Biprism onto an axis-aligned detector).
+//
+// Real formulation (one real GEMM, output already interleaved re/im):
+//     A'[row][2n]   = Re U, A'[row][2n+1]   = Im U                    (M  x K', K' = 2 nb)
+//     B'[2col][2n]  = Re V, B'[2col][2n+1]  = -Im V   -> column 2col   = Re F
+//     B'[2col+1][2n]= Im V, B'[2col+1][2n+1]= Re V    -> column 2col+1 = Im F
+//     D = A' * B'^T                                                   (M x 2W)
+// Precision: operands are fp32 values split as x = hi + lo with hi = tf32(x) (round to
+// nearest), and D accumulates hi*hi + hi*lo + lo*hi on the tensor cores (kind::tf32, fp32
+// accumulation in TMEM) -> ~2^-22 relative per product.  The TMEM accumulator is drained
+// every 128 k-elements into fp32 registers (round-to-nearest adds), which bounds the
+// tensor-core accumulation length.
+//
+// Kernel structure (one CTA per 128 x 128 output tile, 384 threads):
+//   warp 0   : TMA producer  - 4 tiles (A_hi, A_lo, B_hi, B_lo; 128 rows x 32 tf32 = 128 B rows,
+//              SWIZZLE_128B) per k-block into a 3-stage shared-memory ring, mbarrier expect_tx
+//   warp 1   : MMA issuer    - one thread issues 12 tcgen05.mma (3 products x 4 K-steps of 8)
+//              per k-block into one of two 128-column TMEM accumulators; tcgen05.commit frees
+//              the smem stage / publishes the accumulator
+//   warp 2   : TMEM allocator (256 columns)
+//   warps 4-11: epilogue     - tcgen05.ld the finished accumulator (32x32b.x32), add into
+//              registers, release the accumulator; finally write doubles to the output
+#include <cuda.h>
+#include <math.h>
+#include <string.h>
+#include "tg_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;      // BK tf32 elements = 128 bytes = one swizzle row
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;         // 16 KiB
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;     // A_hi, A_lo, B_hi, B_lo
+constexpr int CHUNK_KB = 4;                     // k-blocks per TMEM accumulation chunk (128 k)
+constexpr int GEMM_THREADS = 384;
+constexpr int TMEM_COLS = 256;                  // two 128-column fp32 accumulators
+
+// ---------------------------------------------------------------- PTX wrappers (tcgen05, TMA)
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(tg_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(tg_smem_u32(bar)), "r"(c0),
+      "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tg_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   tg_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//  [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) | [32,46) SBO >> 4
+//  (1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(const void *smem_tile) {
+  const uint32_t addr = tg_smem_u32(smem_tile);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10),
+// K-major A and B, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                            ((uint32_t)(BM >> 4) << 24);
+
+struct GemmSmemCtl {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+// D[M x Np] (+)= A[M x K] * B[Np x K]^T with A = A_hi + A_lo, B = B_hi + B_lo (3 products).
+// out: doubles, row pitch ldo; rows >= M / columns >= Np are not written.
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                       const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                       int M, int Np, int K, double *__restrict__ out, long long ldo, int accumulate_out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem) + 1023) &
+                                                           ~uintptr_t(1023));
+  GemmSmemCtl *ctl = reinterpret_cast<GemmSmemCtl *>(tiles + STAGES * STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int nkb = (K + BK - 1) / BK;
+  const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tg_mbar_init(&ctl->full[s], 1);
+      tg_mbar_init(&ctl->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tg_mbar_init(&ctl->tmem_full[a], 1);
+      tg_mbar_init(&ctl->tmem_empty[a], 8);  // one arrive per epilogue warp
+    }
+    tg_fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     tg_smem_u32(&ctl->tmem_base)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)((kb / STAGES) & 1);
+        tg_mbar_wait(&ctl->empty[s], ph ^ 1u);
+        unsigned char *st = tiles + s * STAGE_BYTES;
+        tg_mbar_expect_tx(&ctl->full[s], STAGE_BYTES);
+        tma_load_2d(st + 0 * TILE_BYTES, &tmA_hi, &ctl->full[s], kb * BK, m0);
+        tma_load_2d(st + 1 * TILE_BYTES, &tmA_lo, &ctl->full[s], kb * BK, m0);
+        tma_load_2d(st + 2 * TILE_BYTES, &tmB_hi, &ctl->full[s], kb * BK, n0);
+        tma_load_2d(st + 3 * TILE_BYTES, &tmB_lo, &ctl->full[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)((kb / STAGES) & 1);
+        const bool chunk_start = (kb % CHUNK_KB) == 0;
+        if (chunk_start) {
+          tg_mbar_wait(&ctl->tmem_empty[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator
+          tc_fence_after();
+        }
+        tg_mbar_wait(&ctl->full[s], ph);
+        tc_fence_after();
+        unsigned char *st = tiles + s * STAGE_BYTES;
+        const uint64_t dAh = make_smem_desc(st + 0 * TILE_BYTES), dAl = make_smem_desc(st + 1 * TILE_BYTES);
+        const uint64_t dBh = make_smem_desc(st + 2 * TILE_BYTES), dBl = make_smem_desc(st + 3 * TILE_BYTES);
+        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 8; ++k4) {
+          const uint64_t ko = (uint64_t)(k4 * 32 >> 4);  // 8 tf32 = 32 bytes along the swizzled row
+          tc_mma_tf32(d, dAh + ko, dBh + ko, kIdesc, (chunk_start && k4 == 0) ? 0u : 1u);
+          tc_mma_tf32(d, dAh + ko, dBl + ko, kIdesc, 1u);
+          tc_mma_tf32(d, dAl + ko, dBh + ko, kIdesc, 1u);
+        }
+        tc_commit(&ctl->empty[s]);  // smem stage reusable once these MMAs have read it
+        if ((kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1) {
+          tc_commit(&ctl->tmem_full[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: 8 warps; warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half
+    const int q = warp & 3, h = (warp - 4) >> 2;
+    float accum[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) accum[i] = 0.f;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      tg_mbar_wait(&ctl->tmem_full[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + h * 64);
+      float v[32];
+      tc_ld32(taddr, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) accum[i] += v[i];
+      tc_ld32(taddr + 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) accum[32 + i] += v[i];
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1u;
+    }
+    const int row = m0 + q * 32 + lane;
+    if (row < M) {
+      double *o = out + (long long)row * ldo + n0 + h * 64;
+      const int ncol = min(64, Np - (n0 + h * 64));
+      if (ncol == 64 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) {
+          double2 w = make_double2((double)accum[i], (double)accum[i + 1]);
+          if (accumulate_out) {
+            const double2 p = *reinterpret_cast<double2 *>(o + i);
+            w.x += p.x;
+            w.y += p.y;
+          }
+          *reinterpret_cast<double2 *>(o + i) = w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i < ncol) o[i] = (accumulate_out ? o[i] : 0.0) + (double)accum[i];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- factor builders
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void cis_turns(double turns, float bits, float &re, float &im) {
+  const float fr = (float)(turns - rint(turns));
+  float amp, s, c;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(amp) : "f"(bits));
+  const float ang = fr * 6.28318530717958648f;
+  s = __sinf(ang);
+  c = __cosf(ang);
+  re = amp * c;
+  im = amp * s;
+}
+// max over c in [0, W-1] of E1 c + E3 c^2 (the column part of the envelope exponent, bits)
+__device__ __forceinline__ double col_env_max(double E1, double E3, double Wm1) {
+  double best = fmax(0.0, Wm1 * (E1 + E3 * Wm1));
+  if (E3 < 0.0) {
+    const double cs = fmin(fmax(-E1 / (2.0 * E3), 0.0), Wm1);
+    best = fmax(best, cs * (E1 + E3 * cs));
+  }
+  return isfinite(best) ? best : 0.0;
+}
+
+// table: pixel-space {T0..T5, E0..E5} per beamlet (prep_kernel of field.cu).
+// A[(row - row0)][2n..2n+1] for rows [row0, row0+M), beamlets [b0, b0+nbatch)
+__global__ void __launch_bounds__(256)
+    factor_rows_kernel(const double *__restrict__ table, long long b0, int nbatch, int row0, int M, int W,
+                       long long ldk, float *__restrict__ Ahi, float *__restrict__ Alo) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= nbatch || m >= M) return;
+  const double *t = table + (b0 + n) * 12;
+  const double u = (double)(row0 + m);
+  const double mu = col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
+  const double turns = t[0] + u * (t[2] + t[5] * u);
+  const float bits = (float)(t[6 + 0] + u * (t[6 + 2] + t[6 + 5] * u) + mu);
+  float re, im;
+  cis_turns(turns, bits, re, im);
+  const float rh = tf32_rna(re), ih = tf32_rna(im);
+  const long long o = (long long)m * ldk + 2 * n;
+  *reinterpret_cast<float2 *>(Ahi + o) = make_float2(rh, ih);
+  *reinterpret_cast<float2 *>(Alo + o) = make_float2(re - rh, im - ih);
+}
+// B[2c][2n..] = (Re V, -Im V), B[2c+1][2n..] = (Im V, Re V)
+__global__ void __launch_bounds__(256)
+    factor_cols_kernel(const double *__restrict__ table, long long b0, int nbatch, int W, long long ldk,
+                       float *__restrict__ Bhi, float *__restrict__ Blo) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (n >= nbatch || c >= W) return;
+  const double *t = table + (b0 + n) * 12;
+  const double v = (double)c;
+  const double mu = col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
+  const double turns = v * (t[1] + t[3] * v);
+  const float bits = (float)(v * (t[6 + 1] + t[6 + 3] * v) - mu);
+  float re, im;
+  cis_turns(turns, bits, re, im);
+  const float rh = tf32_rna(re), ih = tf32_rna(im);
+  const float rl = re - rh, il = im - ih;
+  const long long o0 = (long long)(2 * c) * ldk + 2 * n, o1 = o0 + ldk;
+  *reinterpret_cast<float2 *>(Bhi + o0) = make_float2(rh, -ih);
+  *reinterpret_cast<float2 *>(Blo + o0) = make_float2(rl, -il);
+  *reinterpret_cast<float2 *>(Bhi + o1) = make_float2(ih, rh);
+  *reinterpret_cast<float2 *>(Blo + o1) = make_float2(il, rl);
+}
+
+// max over beamlets of the cross-term contribution across the detector (turns, bits)
+__global__ void __launch_bounds__(256)
+    cross_term_kernel(const double *__restrict__ table, long long nb, double hw, unsigned long long *key) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (i < nb) {
+    const double t4 = fabs(table[i * 12 + 4]) * hw * 16777216.0;  // in units of 2^-24 turn
+    const double e4 = fabs(table[i * 12 + 10]) * hw * 1048576.0;  // in units of 2^-20 bit
+    v = fmax(t4, e4);
+    if (!(v == v)) v = 0.0;  // NaN beamlets are handled by the (NaN) factors themselves
+  }
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(key, (unsigned long long)__double_as_longlong(v));
+}
+
+__global__ void __launch_bounds__(256)
+    f64_to_c64_kernel(const double *__restrict__ in, float *__restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void *p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D fp32 row-major (rows x K, pitch ldk elements), box = 128 rows x 32 elements, 128B swizzle
+int make_map(CUtensorMap *m, const float *base, long long rows, long long K, long long ldk) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    tg_set_error("cuTensorMapEncodeTiled entry point not available");
+    return TG_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ldk * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tg_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return TG_ECUDA;
+  }
+  return TG_OK;
+}
+
+int launch_gemm(const float *Ahi, const float *Alo, const float *Bhi, const float *Blo, int M, int Np, int K,
+                long long ldk, double *out, long long ldo, int accumulate, cudaStream_t st) {
+  CUtensorMap ta, tb, tc, td;
+  int rc;
+  if ((rc = make_map(&ta, Ahi, M, K, ldk)) != TG_OK) return rc;
+  if ((rc = make_map(&tb, Alo, M, K, ldk)) != TG_OK) return rc;
+  if ((rc = make_map(&tc, Bhi, Np, K, ldk)) != TG_OK) return rc;
+  if ((rc = make_map(&td, Blo, Np, K, ldk)) != TG_OK) return rc;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
+  TG_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((Np + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
+  gemm_tf32x3_kernel<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, tc, td, M, Np, K, out, ldo, accumulate);
+  return tg_launch_check("gemm_tf32x3_kernel");
+}
+
+}  // namespace
+
+// D[M x N] = (A_hi + A_lo)[M x K] * (B_hi + B_lo)[N x K]^T on the tensor cores (3 x TF32), fp64 out.
+extern "C" int tg_gemm_tf32x3(int M, int N, int K, const float *A_hi, const float *A_lo, const float *B_hi,
+                              const float *B_lo, long long ldk, double *D, long long ldd, int accumulate,
+                              void *stream) {
+  TG_REQUIRE(M > 0 && N > 0 && K > 0, "bad GEMM shape");
+  TG_REQUIRE(A_hi && A_lo && B_hi && B_lo && D, "null pointer");
+  TG_REQUIRE(ldk >= K && (ldk % 4) == 0, "ldk must be >= K and a multiple of 4 (16-byte TMA pitch)");
+  TG_REQUIRE(((uintptr_t)A_hi % 16) == 0 && ((uintptr_t)A_lo % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 &&
+                 ((uintptr_t)B_lo % 16) == 0,
+             "operands must be 16-byte aligned");
+  return launch_gemm(A_hi, A_lo, B_hi, B_lo, M, N, K, ldk, D, ldd, accumulate, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6], int H, int W,
+                                      int row0, int nrows, void *out, int out_is_c128, void *stream) {
+  TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad shape");
+  TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
+  TG_REQUIRE(px2m && out, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nrows == 0) return TG_OK;
+  const size_t npix = (size_t)nrows * W;
+  if (nb == 0) {
+    TG_CUDA(cudaMemsetAsync(out, 0, npix * (out_is_c128 ? 16 : 8), st));
+    return TG_OK;
+  }
+  TG_REQUIRE(poly, "null poly");
+  int dev = 0;
+  TG_CUDA(cudaGetDevice(&dev));
+  tg_tune_mempool(dev);
+
+  const long long kBatch = 16384;  // beamlets per GEMM pass
+  const long long nbatch_max = nb < kBatch ? nb : kBatch;
+  const long long ldk = ((2 * nbatch_max + 31) / 32) * 32;
+  const int Np = 2 * W;
+  const size_t table_bytes = (((size_t)nb * 96 + 255) / 256) * 256;
+  const size_t a_bytes = (((size_t)nrows * ldk * 4 + 255) / 256) * 256;
+  const size_t b_bytes = (((size_t)Np * ldk * 4 + 255) / 256) * 256;
+  const size_t acc_bytes = out_is_c128 ? 0 : npix * 16;
+  unsigned char *ws = nullptr;
+  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), table_bytes + 256 + 2 * a_bytes + 2 * b_bytes + acc_bytes, st));
+  double *table = reinterpret_cast<double *>(ws);
+  unsigned long long *key = reinterpret_cast<unsigned long long *>(ws + table_bytes);
+  float *Ahi = reinterpret_cast<float *>(ws + table_bytes + 256);
+  float *Alo = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Ahi) + a_bytes);
+  float *Bhi = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Alo) + a_bytes);
+  float *Blo = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Bhi) + b_bytes);
+  double *acc = out_is_c128 ? static_cast<double *>(out)
+                            : reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(Blo) + b_bytes);
+  int rc = TG_OK;
+  cudaError_t e = cudaMemsetAsync(key, 0, 8, st);
+  if (e == cudaSuccess) rc = tg_launch_prep(nb, poly, px2m, H, W, table, nullptr, st);
+  if (e == cudaSuccess && rc == TG_OK) {
+    cross_term_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(table, nb, (double)H * (double)W, key);
+    rc = tg_launch_check("cross_term_kernel");
+  }
+  unsigned long long hkey = 0;
+  if (e == cudaSuccess && rc == TG_OK) {
+    e = cudaMemcpyAsync(&hkey, key, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  if (e != cudaSuccess) {
+    tg_set_error("tg_field_sum_separable: %s", cudaGetErrorString(e));
+    rc = TG_ECUDA;
+  }
+  if (rc == TG_OK) {
+    double worst;
+    memcpy(&worst, &hkey, 8);
+    if (worst > 1.0) {
+      tg_set_error("beamlets are not separable on this grid (cross term %.3g x tolerance)", worst);
+      rc = TG_ENOTSEPARABLE;
+    }
+  }
+  for (long long b0 = 0; b0 < nb && rc == TG_OK; b0 += kBatch) {
+    const int nbatch = (int)((nb - b0) < kBatch ? (nb - b0) : kBatch);
+    const int K = 2 * nbatch;
+    // (the tensor maps are encoded with the true K: the TMA unit zero-fills the K padding)
+    dim3 ga((unsigned)((nbatch + 255) / 256), (unsigned)nrows), gb((unsigned)((nbatch + 255) / 256), (unsigned)W);
+    factor_rows_kernel<<<ga, 256, 0, st>>>(table, b0, nbatch, row0, nrows, W, ldk, Ahi, Alo);
+    factor_cols_kernel<<<gb, 256, 0, st>>>(table, b0, nbatch, W, ldk, Bhi, Blo);
+    rc = tg_launch_check("factor kernels");
+    if (rc == TG_OK) rc = launch_gemm(Ahi, Alo, Bhi, Blo, nrows, Np, K, ldk, acc, (long long)Np, b0 > 0 ? 1 : 0, st);
+  }
+  if (rc == TG_OK && !out_is_c128) {
+    const size_t n = npix * 2;
+    f64_to_c64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, static_cast<float *>(out), n);
+    rc = tg_launch_check("f64_to_c64_kernel");
+  }
+  cudaFreeAsync(ws, st);
+  return rc;
+}

@@ -7,6 +7,8 @@
 
 void tg_set_error(const char *fmt, ...);
 void tg_tune_mempool(int dev);
+int tg_launch_prep(int64_t nb, const double *poly, const double px2m[6], int H, int W, double *table,
+                   unsigned long long *gref_key, cudaStream_t st);
 // k = 2 pi / wavelength, p0 = k * pathlength (reference gaussian.py:253-255); internal helper
 int tg_wave_numbers(int64_t nb, const double *wavelength, const double *pathlength, double *k,
                     double *p0, cudaStream_t st);

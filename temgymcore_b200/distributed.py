@@ -77,7 +77,7 @@ def gather_rows(local_rows, H: int, W: int, group=None):
 
 
 def make_gaussian_image_sharded(gaussian_rays, model, *, cull_bits=None, out_dtype=None,
-                                group=None, src: int = 0,
+                                method="auto", group=None, src: int = 0,
                                 rows_fn: Optional[Callable] = None,
                                 table_fn: Optional[Callable] = None):
     """Row-sharded ``make_gaussian_image`` over the ranks of ``group``.
@@ -99,6 +99,7 @@ def make_gaussian_image_sharded(gaussian_rays, model, *, cull_bits=None, out_dty
     poly = broadcast_table(poly, nb, src=src, group=group)
     r0, nr = row_shards(H, world)[rank]
     rows_fn = rows_fn or (lambda p, n, row0, nrows: _field_sum_grid(
-        p, n, grid, dev, row0=row0, nrows=nrows, out_dtype=out_dtype, cull_bits=cull_bits))
+        p, n, grid, dev, row0=row0, nrows=nrows, out_dtype=out_dtype, cull_bits=cull_bits,
+        method=method))
     local = rows_fn(poly, nb, r0, nr)
     return gather_rows(local, H, W, group=group)

@@ -157,9 +157,15 @@ def _wave_numbers(g, dev):
 
 
 def _field_sum_grid(poly, nb, grid: Grid, dev, row0=0, nrows=None, out_dtype=None, cull_bits=None,
-                    count_evals=False):
+                    count_evals=False, method="sfu"):
+    """Sum the beamlet field on rows [row0, row0+nrows) of ``grid``.
+
+    method: "sfu" = tiled SFU kernel (any beamlets); "tensor" = tcgen05 GEMM for separable
+    beamlets (raises if they are not); "auto" = tensor when separable, else sfu."""
     import torch
     lib = L.load()
+    if method not in L.TG_METHOD:
+        raise ValueError(f"method must be one of {sorted(L.TG_METHOD)}")
     H, W = int(grid.shape[0]), int(grid.shape[1])
     nrows = H - row0 if nrows is None else nrows
     out_dtype = torch.complex128 if out_dtype is None else out_dtype
@@ -168,6 +174,16 @@ def _field_sum_grid(poly, nb, grid: Grid, dev, row0=0, nrows=None, out_dtype=Non
     cull = DEFAULT_CULL_BITS if cull_bits is None else int(cull_bits)
     out = torch.empty((nrows, W), dtype=out_dtype, device=dev)
     nev = C.c_longlong(0)
+    if method in ("tensor", "auto") and not count_evals:
+        with torch.cuda.device(dev):
+            rc = lib.tg_field_sum_separable(nb, poly.data_ptr() if nb else None,
+                                            L.dbl_array(grid.px2m_affine), H, W, row0, nrows,
+                                            out.data_ptr(), int(out_dtype == torch.complex128),
+                                            A.current_stream_ptr(dev))
+        if rc == L.TG_OK:
+            return out
+        if not (rc == L.TG_ENOTSEPARABLE and method == "auto"):
+            L.check(rc, "tg_field_sum_separable")
     with torch.cuda.device(dev):
         L.check(lib.tg_field_sum_grid(nb, poly.data_ptr() if nb else None, L.dbl_array(grid.px2m_affine),
                                       H, W, row0, nrows, out.data_ptr(),
@@ -199,7 +215,7 @@ def _finish(out, kind):
 
 
 def make_gaussian_image_host(gaussian_rays, model, *, cull_bits=None, out_dtype=None, row0=0,
-                             nrows=None, device=None):
+                             nrows=None, device=None, method="auto"):
     """``make_gaussian_image`` for HOST inputs through the single host-buffer C-ABI call
     ``tg_make_gaussian_image_host`` (H2D copies, all kernels, D2H copy inside the call)."""
     import torch
@@ -233,7 +249,8 @@ def make_gaussian_image_host(gaussian_rays, model, *, cull_bits=None, out_dtype=
         C.byref(cm), n, L.ptr_array([r.ctypes.data for r in rays]), amp.ctypes.data,
         waist.ctypes.data, radii.ctypes.data, wl.ctypes.data, th.ctypes.data,
         L.dbl_array(grid.px2m_affine), H, W, row0, nrows, out.data_ptr(),
-        int(out_dtype == torch.complex128), cull, dev), "tg_make_gaussian_image_host")
+        int(out_dtype == torch.complex128), cull, L.TG_METHOD[method], dev),
+        "tg_make_gaussian_image_host")
     return out
 
 
@@ -280,24 +297,27 @@ def _to_np(v):
     return v.detach().cpu().numpy() if hasattr(v, "detach") else v
 
 
-def make_gaussian_image(gaussian_rays, model, batch_size=128, *, cull_bits=None, out_dtype=None):
+def make_gaussian_image(gaussian_rays, model, batch_size=128, *, cull_bits=None, out_dtype=None,
+                        method="auto"):
     """Field of all beamlets on the detector ``model[-1]`` -> ``(H, W)`` complex128
-    (gaussian.py:225-273)."""
+    (gaussian.py:225-273).  ``method``: "auto" (tensor cores when the beamlets are separable
+    on this grid, else the SFU kernel), "sfu", or "tensor"."""
     rays = gaussian_rays
     assert isinstance(rays, GaussianRay)
     grid = model[-1]
     assert isinstance(grid, Grid)
     kind = _result_kind(rays)
     if kind != A.KIND_CUDA:
-        out = make_gaussian_image_host(rays, model, cull_bits=cull_bits, out_dtype=out_dtype)
+        out = make_gaussian_image_host(rays, model, cull_bits=cull_bits, out_dtype=out_dtype,
+                                       method=method)
         return out if kind == A.KIND_TORCH_CPU else out.numpy()
     poly, n, dev = beamlet_polynomials(rays, model)
-    out = _field_sum_grid(poly, n, grid, dev, out_dtype=out_dtype, cull_bits=cull_bits)
+    out = _field_sum_grid(poly, n, grid, dev, out_dtype=out_dtype, cull_bits=cull_bits, method=method)
     return _finish(out, kind)
 
 
 def evaluate_gaussian_input_image(gaussian_rays, grid, batch_size=128, *, cull_bits=None,
-                                  out_dtype=None):
+                                  out_dtype=None, method="auto"):
     """Input-plane field of all beamlets on ``grid`` (gaussian.py:372-399)."""
     import torch
     lib = L.load()
@@ -316,7 +336,7 @@ def evaluate_gaussian_input_image(gaussian_rays, grid, batch_size=128, *, cull_b
         L.check(lib.tg_input_coeffs_f64(n, g["amplitude"].data_ptr(), p0.data_ptr(), q.data_ptr(),
                                         r1m.data_ptr(), th.data_ptr(), k.data_ptr(), poly.data_ptr(),
                                         A.current_stream_ptr(dev)), "tg_input_coeffs_f64")
-    out = _field_sum_grid(poly, n, grid, dev, out_dtype=out_dtype, cull_bits=cull_bits)
+    out = _field_sum_grid(poly, n, grid, dev, out_dtype=out_dtype, cull_bits=cull_bits, method=method)
     return _finish(out, kind)
 
 

@@ -312,7 +312,7 @@ def test_make_gaussian_image_parity(torch_cuda, name, cull_bits):
     from temgymcore_b200.gaussian import make_gaussian_image
     g, model = field_cases()[name]
     ref = O.make_gaussian_image(g, model)
-    got = make_gaussian_image(g, model, cull_bits=cull_bits)
+    got = make_gaussian_image(g, model, cull_bits=cull_bits, method="sfu")
     assert isinstance(got, np.ndarray) and got.dtype == np.complex128 and got.shape == tuple(model[-1].shape)
     err = rel_l2(got, ref)
     assert err < FIELD_TOL, f"{name}: rel L2 {err:.3e}"
@@ -448,3 +448,79 @@ def test_c3_culling_consistency(torch_cuda):
     assert ev_d == n * 1024 * 1024
     assert ev_c < ev_d / 4
     assert rel_l2(to_np(cull), to_np(dense)) < 1e-6
+
+
+# ------------------------------------------------------------------------------ K4 (tensor cores)
+def _tf32_split(torch, x):
+    """x = hi + lo with hi = cvt.rna.tf32(x) (round to nearest, ties away), like the factor kernels."""
+    bits = x.contiguous().view(torch.int32)
+    hi = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    return hi, x - hi
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 512), (256, 384, 1536), (200, 136, 1000),
+                                   (1024, 256, 4100), (77, 50, 36)])
+def test_gemm_tf32x3_against_fp64(torch_cuda, M, N, K):
+    import ctypes as C
+    from temgymcore_b200 import _lib as L
+    torch = torch_cuda
+    lib = L.load()
+    gen = torch.Generator(device="cuda").manual_seed(M * 1000 + K)
+    ldk = ((K + 3) // 4) * 4 + 8
+    A = torch.zeros((M, ldk), dtype=torch.float32, device="cuda")
+    B = torch.zeros((N, ldk), dtype=torch.float32, device="cuda")
+    A[:, :K] = torch.rand((M, K), generator=gen, device="cuda") * 2 - 1
+    B[:, :K] = torch.rand((N, K), generator=gen, device="cuda") * 2 - 1
+    A[:, K:] = 7.0   # pitch padding must never be read (the tensor map ends at K)
+    B[:, K:] = 7.0
+    Ah, Al = _tf32_split(torch, A)
+    Bh, Bl = _tf32_split(torch, B)
+    D = torch.full((M, N + 3), -1.0, dtype=torch.float64, device="cuda")
+    rc = lib.tg_gemm_tf32x3(M, N, K, Ah.data_ptr(), Al.data_ptr(), Bh.data_ptr(), Bl.data_ptr(), ldk,
+                            D.data_ptr(), N + 3, 0, torch.cuda.current_stream().cuda_stream)
+    L.check(rc, "tg_gemm_tf32x3")
+    ref = A[:, :K].double() @ B[:, :K].double().T
+    err = (D[:, :N] - ref).norm() / ref.norm()
+    assert float(err) < 3e-6, float(err)
+    assert bool((D[:, N:] == -1.0).all())  # columns beyond N untouched
+    rc = lib.tg_gemm_tf32x3(M, N, K, Ah.data_ptr(), Al.data_ptr(), Bh.data_ptr(), Bl.data_ptr(), ldk,
+                            D.data_ptr(), N + 3, 1, torch.cuda.current_stream().cuda_stream)
+    L.check(rc, "tg_gemm_tf32x3 accumulate")
+    assert float((D[:, :N] - 2 * ref).norm() / ref.norm()) < 4e-6
+
+
+@pytest.mark.parametrize("name", ["c2_aperture", "c3_biprism_separable"])
+def test_tensor_path_parity(torch_cuda, name):
+    from temgymcore_b200.gaussian import make_gaussian_image
+    g, model = field_cases()[name]
+    ref = O.make_gaussian_image(g, model)
+    got = make_gaussian_image(g, model, method="tensor")
+    assert got.shape == ref.shape and got.dtype == np.complex128
+    assert rel_l2(got, ref) < FIELD_TOL, rel_l2(got, ref)
+    sfu = make_gaussian_image(g, model, method="sfu", cull_bits=0)
+    assert rel_l2(got, sfu) < FIELD_TOL
+    auto = make_gaussian_image(g, model)  # auto picks the tensor path: same bits
+    np.testing.assert_array_equal(auto, got)
+
+
+def test_tensor_path_rejects_non_separable(torch_cuda):
+    from temgymcore_b200 import _lib as L
+    from temgymcore_b200.gaussian import make_gaussian_image
+    g, model = field_cases()["c3_biprism_general"]
+    with pytest.raises(L.TemGymError):
+        make_gaussian_image(g, model, method="tensor")
+    ref = O.make_gaussian_image(g, model)
+    assert rel_l2(make_gaussian_image(g, model, method="auto"), ref) < FIELD_TOL  # falls back to the SFU kernel
+
+
+def test_tensor_path_rows_c64_and_full_size(torch_cuda):
+    from temgymcore_b200.gaussian import _field_sum_grid, beamlet_polynomials
+    g, model = M.aperture_diffraction_case(10_000, (1024, 1024))
+    grid = model[-1]
+    poly, n, dev = beamlet_polynomials(g, model)
+    sfu = to_np(_field_sum_grid(poly, n, grid, dev, cull_bits=0, method="sfu"))
+    ten = to_np(_field_sum_grid(poly, n, grid, dev, method="tensor"))
+    assert rel_l2(ten, sfu) < FIELD_TOL, rel_l2(ten, sfu)
+    rows = to_np(_field_sum_grid(poly, n, grid, dev, row0=384, nrows=200, method="tensor",
+                                 out_dtype=torch_cuda.complex64))
+    assert rows.dtype == np.complex64 and rel_l2(rows, ten[384:584]) < 1e-6
