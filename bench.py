@@ -180,7 +180,8 @@ def run_ours(args):
     from tests import models as M
     from temgymcore_b200 import _lib as L
     from temgymcore_b200 import distributed as D
-    from temgymcore_b200.gaussian import (_field_sum_grid, beamlet_polynomials, make_gaussian_image_host)
+    from temgymcore_b200.gaussian import (_field_sum_grid, beamlet_polynomials, make_gaussian_image_device,
+                                          make_gaussian_image_host)
     from temgymcore_b200.ray import RAY_FIELDS, Ray
     from temgymcore_b200.run import run_to_end_abcd
 
@@ -223,11 +224,20 @@ def run_ours(args):
     r0, nr = D.row_shards(H, world)[rank]
     launches = {"n": 0}
 
+    method = args.method
+    # our kernels per step: trace, qinv, wave, coeffs + {sfu: prep, field, split-reduce |
+    # tensor: prep, cross-term, 2 factor kernels, GEMM | auto: both sets, the unused one exits at once}
+    LAUNCHES = {"sfu": 7, "tensor": 9, "auto": 12}
+
     def step_device():
-        """inputs resident in HBM: trace+ABCD, Q_inv, k/p0, coefficients (4 launches + torch glue),
-        broadcast, prep + field (+ split reduce), all-gather."""
-        img = D.make_gaussian_image_sharded(g_dev, model, cull_bits=0)
-        launches["n"] += 7
+        """inputs resident in HBM: trace+ABCD, Q_inv, k/p0, coefficients (4 launches), broadcast,
+        then either prep + cross-term check + 2 factor kernels + tcgen05 GEMM (separable -> C2), or
+        prep + SFU field kernel + split reduce; all-gather of the row blocks."""
+        if world == 1:   # one C-ABI call (tg_make_gaussian_image_f64), no host synchronisation inside
+            img = make_gaussian_image_device(g_dev, model, cull_bits=0, method=method)
+        else:
+            img = D.make_gaussian_image_sharded(g_dev, model, cull_bits=0, method=method)
+        launches["n"] += LAUNCHES[method]
         return img
 
     def timed(fn, steps, warmup, flush=True):
@@ -253,31 +263,74 @@ def run_ours(args):
     launches["n"] = 0
     times = timed(step_device, args.steps, args.warmup)
     total_ms = max_over_ranks(float(np.sum(times)))
-    n_launch = launches["n"] - 7 * args.warmup
+    n_launch = launches["n"] - LAUNCHES[method] * args.warmup
     evals_per_step = C2_NB * H * W
     ms_per_step = total_ms / args.steps
     value = evals_per_step / (ms_per_step * 1e-3)
 
-    # dominant kernel alone (prep + tiled field kernel + split reduce of this rank's rows)
     poly, nb, _ = beamlet_polynomials(g_dev, model)
-    kt = timed(lambda: _field_sum_grid(poly, nb, grid, dev, row0=r0, nrows=nr, cull_bits=0),
+    peak_mufu = sms * MUFU_PER_CLK_SM * pk["sm_max_mhz"] * 1e6
+
+    # general path (any beamlets): prep + tiled SFU field kernel + split reduce, this rank's rows
+    kt = timed(lambda: _field_sum_grid(poly, nb, grid, dev, row0=r0, nrows=nr, cull_bits=0, method="sfu"),
                args.steps, args.warmup)
     k_ms = float(np.mean(kt))
-    clocks = sampler.stop() if rank == 0 else None
     k_evals = nb * nr * W
     mufu_rate = k_evals * MUFU_PER_EVAL / (k_ms * 1e-3)
-    peak_mufu = sms * MUFU_PER_CLK_SM * pk["sm_max_mhz"] * 1e6
-    roofline = {"bound": "sfu", "kernel": "field_grid_kernel<16,8>", "achieved": mufu_rate / 1e9,
-                "peak": peak_mufu / 1e9, "unit": "GMUFU/s", "frac": mufu_rate / peak_mufu,
-                "traffic": None, "evals_per_s": k_evals / (k_ms * 1e-3), "kernel_ms": k_ms,
-                "peak_basis": f"{sms} SMs x 16 MUFU/clk x {pk['sm_max_mhz']:.0f} MHz (clocks.max.sm, "
-                              f"{pk['source']}); 3 MUFU per beamlet*pixel"}
+    roofline_sfu = {"bound": "sfu", "kernel": "field_grid_kernel<16,8> (+prep, split reduce)",
+                    "achieved": mufu_rate / 1e9, "peak": peak_mufu / 1e9, "unit": "GMUFU/s",
+                    "frac": mufu_rate / peak_mufu, "traffic": None, "evals_per_s": k_evals / (k_ms * 1e-3),
+                    "kernel_ms": k_ms,
+                    "peak_basis": f"{sms} SMs x 16 MUFU/clk x {pk['sm_max_mhz']:.0f} MHz (clocks.max.sm, "
+                                  f"{pk['source']}); 3 MUFU per beamlet*pixel"}
+
+    # separable path: the tcgen05 GEMM alone, same shape as this rank's share of C2
+    # (M = rows, N = 2W, K = 2 nb), operands random TF32-split fp32
+    roofline_tensor = None
+    if method != "sfu":
+        Mg, Ng, Kg = nr, 2 * W, 2 * nb
+        gen = torch.Generator(device=dev).manual_seed(1)
+
+        def split(x):
+            hi = ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+            return hi, x - hi
+        Ah, Al = split(torch.rand((Mg, Kg), generator=gen, device=dev) * 2 - 1)
+        Bh, Bl = split(torch.rand((Ng, Kg), generator=gen, device=dev) * 2 - 1)
+        Dg = torch.empty((Mg, Ng), dtype=torch.float64, device=dev)
+        lib = L.load()
+
+        def gemm():
+            L.check(lib.tg_gemm_tf32x3(Mg, Ng, Kg, Ah.data_ptr(), Al.data_ptr(), Bh.data_ptr(), Bl.data_ptr(),
+                                       Kg, Dg.data_ptr(), Ng, 0, torch.cuda.current_stream().cuda_stream),
+                    "tg_gemm_tf32x3")
+        gt = timed(gemm, args.steps, args.warmup)
+        g_ms = float(np.mean(gt))
+        alg_tf = 8.0 * nb * nr * W / (g_ms * 1e-3) / 1e12          # one complex MAC per beamlet*pixel
+        exe_tf = 2.0 * Mg * Ng * Kg * 3 / (g_ms * 1e-3) / 1e12      # 3 TF32 passes (hi*hi, hi*lo, lo*hi)
+        bf16 = None
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                bf16 = float(json.load(fh)["bf16_tflops"])
+        except Exception:
+            bf16 = 1590.0
+        roofline_tensor = {"bound": "tensor", "kernel": "gemm_tf32x3_kernel (tcgen05.mma kind::tf32)",
+                           "achieved": alg_tf, "peak": bf16, "unit": "TFLOP/s", "frac": alg_tf / bf16,
+                           "traffic": None, "kernel_ms": g_ms, "executed_tf32_tflops": exe_tf,
+                           "tf32_peak_assumed": bf16 / 2, "frac_executed_vs_tf32_peak": exe_tf / (bf16 / 2),
+                           "note": "achieved = algorithmic 8 real flop per beamlet*pixel; the kernel executes 3x "
+                                   "that in TF32 (hi/lo operand split needed for the 1e-5 parity); peak = "
+                                   "measured dense bf16 (MEASURED_PEAKS.json), TF32 peak taken as half of it",
+                           "evals_per_s": nb * nr * W / (g_ms * 1e-3)}
+        del Ah, Al, Bh, Bl, Dg
+    clocks = sampler.stop() if rank == 0 else None
     if clocks and clocks.get("sm_mhz"):
-        roofline["frac_at_observed_clock"] = mufu_rate / (sms * MUFU_PER_CLK_SM * clocks["sm_mhz"] * 1e6)
+        roofline_sfu["frac_at_observed_clock"] = mufu_rate / (sms * MUFU_PER_CLK_SM * clocks["sm_mhz"] * 1e6)
+    roofline = roofline_tensor if roofline_tensor else roofline_sfu
 
     # ---- end to end through the host-buffer C ABI (pinned inputs, D2H of the result)
     def step_e2e():
-        return make_gaussian_image_host(g_pin, model, cull_bits=0, row0=r0, nrows=nr, device=local)
+        return make_gaussian_image_host(g_pin, model, cull_bits=0, row0=r0, nrows=nr, device=local,
+                                        method=method)
     et = timed(step_e2e, args.steps, args.warmup, flush=False)
     # host call is synchronous: wall time == device-bracketed time; use the events' span
     e2e_ms = max_over_ranks(float(np.sum(et))) / args.steps
@@ -331,18 +384,20 @@ def run_ours(args):
         line = {
             "metric": "beamlet_pixel_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "tf32x3 (fp32-equivalent operands, fp32/fp64 accumulation)" if method != "sfu" else "f32",
             "data": "synthetic",
             "config": {"workload": "C2 aperture_diffraction: 1e4 Gaussian beamlets (fibonacci disc r=1e-7 m, "
                                    "lambda=2 pm, w0=1 nm) through ParallelBeam->Lens(f=1e-2)->Detector, summed "
                                    "on 1024x1024 px (dense, cull_bits=0)",
+                       "method": method + (" -> tensor-core path (C2 is separable)" if method == "auto" else ""),
                        "parallelism": f"detector rows sharded over {world} GPU(s); table broadcast + row "
                                       "all-gather" if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (256 MiB write); inputs (0.96 MB table) are "
                              "L2-resident by design",
                        "phase": "fp64 setup -> 32-bit fixed-point turns; fp32 MUFU sin/cos/ex2; fp64 "
                                 "accumulation across 128-beamlet chunks"},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": n_launch,
+            "roofline": roofline, "roofline_sfu_path": roofline_sfu, "e2e": e2e, "gpu_launches": n_launch,
             "rays": rays_section, "clocks": clocks,
         }
         if cpu:
@@ -359,6 +414,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--method", default="auto", choices=["auto", "sfu", "tensor"],
+                    help="field-sum path: auto = tensor cores when separable (C2 is), sfu = general kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

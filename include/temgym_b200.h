@@ -188,6 +188,15 @@ int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6],
                            int W, int row0, int nrows, void *out, int out_is_c128,
                            void *stream);
 
+/* Method dispatch for the grid field sum.  TG_METHOD_AUTO enqueues both paths with a DEVICE-side
+ * separability verdict (no host synchronisation): the kernels of the path that does not apply
+ * return immediately. */
+#define TG_METHOD_AUTO 0   /* tensor-core path when the beamlets are separable, else SFU kernel */
+#define TG_METHOD_SFU 1    /* tg_field_sum_grid */
+#define TG_METHOD_TENSOR 2 /* tg_field_sum_separable (TG_ENOTSEPARABLE if it does not apply) */
+int tg_field_sum(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
+                 int nrows, void *out, int out_is_c128, int cull_bits, int method, void *stream);
+
 /* D[M x N] = (A_hi + A_lo)[M x K] * (B_hi + B_lo)[N x K]^T, products hi*hi + hi*lo + lo*hi on the
  * tensor cores (kind::tf32, fp32 TMEM accumulation drained every 128 k), fp64 output with row pitch
  * ldd.  Operands: device fp32, row pitch ldk elements (multiple of 4), 16-byte aligned; hi parts
@@ -210,10 +219,14 @@ int tg_make_gaussian_image_host(const tg_model *model_host, int64_t nb,
                                 void *out, int out_is_c128, int cull_bits, int method,
                                 int device);
 
-/* `method` of tg_make_gaussian_image_host */
-#define TG_METHOD_AUTO 0   /* tensor-core path when the beamlets are separable, else SFU kernel */
-#define TG_METHOD_SFU 1    /* tg_field_sum_grid */
-#define TG_METHOD_TENSOR 2 /* tg_field_sum_separable (TG_ENOTSEPARABLE if it does not apply) */
+/* Same pipeline with DEVICE pointers, enqueued on `stream` (asynchronous): the whole of
+ * make_gaussian_image (gaussian.py:225-273) in one call for device-resident inputs. */
+int tg_make_gaussian_image_f64(const tg_model *model_host, int64_t nb, const double *const rays[7],
+                               const double *amplitude, const double *waist_xy,
+                               const double *radii_xy, const double *wavelength,
+                               const double *theta, const double px2m[6], int H, int W, int row0,
+                               int nrows, void *out, int out_is_c128, int cull_bits, int method,
+                               void *stream);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,9 @@ SIGNATURES = {
                                  C.POINTER(C.c_longlong), _vp]),
     "tg_field_sum_points": (_i32, [_i64, _vp, _i64, _vp, _vp, _i32, _vp]),
     "tg_field_sum_separable": (_i32, [_i64, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "tg_field_sum": (_i32, [_i64, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
+    "tg_make_gaussian_image_f64": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(_vp), _vp, _vp, _vp,
+                                          _vp, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "tg_gemm_tf32x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
     "tg_make_gaussian_image_host": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(_vp), _vp, _vp, _vp,
                                            _vp, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32]),

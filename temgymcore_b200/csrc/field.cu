@@ -146,7 +146,9 @@ __global__ void __launch_bounds__(kThreads, 2)
     field_grid_kernel(const double *__restrict__ table, const FieldGeom g,
                       const unsigned long long *__restrict__ gref_key, void *__restrict__ out,
                       int out_is_c128, double2 *__restrict__ partial,
-                      unsigned long long *__restrict__ evals) {
+                      unsigned long long *__restrict__ evals,
+                      const unsigned long long *__restrict__ sep_guard) {
+  if (sep_guard && tg_key_is_separable(*sep_guard)) return;  // the tensor-core path owns this call
   using S = FieldSmem<L, SPR>;
   constexpr int TC = S::TC, TR = S::TR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -363,7 +365,9 @@ __global__ void __launch_bounds__(kThreads, 2)
 
 __global__ void __launch_bounds__(256)
     split_reduce_kernel(const double2 *__restrict__ partial, int nsplit, size_t npix,
-                        void *__restrict__ out, int out_is_c128) {
+                        void *__restrict__ out, int out_is_c128,
+                        const unsigned long long *__restrict__ sep_guard) {
+  if (sep_guard && tg_key_is_separable(*sep_guard)) return;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   double re = 0.0, im = 0.0;
@@ -449,6 +453,15 @@ int tg_launch_prep(int64_t nb, const double *poly, const double px2m[6], int H, 
 extern "C" int tg_field_sum_grid(int64_t nb, const double *poly, const double px2m[6], int H, int W,
                                  int row0, int nrows, void *out, int out_is_c128, int cull_bits,
                                  long long *n_evals_out, void *stream) {
+  return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, n_evals_out,
+                           nullptr, static_cast<cudaStream_t>(stream));
+}
+
+// sep_guard != NULL: every kernel of this path returns at once when the device-side key says the
+// beamlets are separable (the tensor-core path, enqueued by the same call, does the work instead).
+int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
+                      int nrows, void *out, int out_is_c128, int cull_bits, long long *n_evals_out,
+                      const unsigned long long *sep_guard, cudaStream_t stream) {
   TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad shape");
   TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
   TG_REQUIRE(px2m && out, "null pointer");
@@ -503,11 +516,11 @@ extern "C" int tg_field_sum_grid(int64_t nb, const double *poly, const double px
       dim3 grid((unsigned)tiles, (unsigned)g.nsplit);
       field_grid_kernel<L, SPR><<<grid, kThreads, smem, st>>>(
           table, g, cull_bits > 0 ? gref : nullptr, out, out_is_c128, partial,
-          n_evals_out ? evals : nullptr);
+          n_evals_out ? evals : nullptr, sep_guard);
       rc = tg_launch_check("field_grid_kernel");
       if (rc == TG_OK && g.nsplit > 1) {
         split_reduce_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(partial, g.nsplit, npix,
-                                                                           out, out_is_c128);
+                                                                           out, out_is_c128, sep_guard);
         rc = tg_launch_check("split_reduce_kernel");
       }
     }

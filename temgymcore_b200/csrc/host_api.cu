@@ -206,6 +206,50 @@ extern "C" int tg_metres_to_pixels_host(int64_t n, const double *x, const double
   return rc;
 }
 
+// Device-resident make_gaussian_image (gaussian.py:225-273) as ONE call: ray kernel with ABCD,
+// Q_inv, wave numbers, coefficient builder, field sum (method dispatch), all enqueued on `stream`.
+extern "C" int tg_make_gaussian_image_f64(const tg_model *model_host, int64_t nb,
+                                          const double *const rays[7], const double *amplitude,
+                                          const double *waist_xy, const double *radii_xy,
+                                          const double *wavelength, const double *theta,
+                                          const double px2m[6], int H, int W, int row0, int nrows,
+                                          void *out, int out_is_c128, int cull_bits, int method,
+                                          void *stream) {
+  TG_REQUIRE(model_host && rays && px2m && out, "null pointer");
+  TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad sizes");
+  TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
+  if (nrows == 0) return TG_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (nb == 0) return tg_field_sum(0, nullptr, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, method, s);
+  TG_REQUIRE(amplitude && waist_xy && radii_xy && wavelength && theta, "null pointer");
+  int dev = 0;
+  TG_CUDA(cudaGetDevice(&dev));
+  tg_tune_mempool(dev);
+  double *scratch = nullptr;  // k n | p0 n | abcd 25n | qinv 8n | poly 12n
+  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)nb * 47 * 8, s));
+  double *dk = scratch, *dp0 = dk + nb, *dabcd = dp0 + nb, *dq = dabcd + 25 * nb, *dpoly = dq + 8 * nb;
+  tg_ray_in in;
+  for (int f = 0; f < 7; ++f) {
+    in.ptr[f] = rays[f];
+    in.value[f] = 0.0;
+    if (!rays[f]) {
+      cudaFreeAsync(scratch, s);
+      tg_set_error("tg_make_gaussian_image_f64: ray field %d is null", f);
+      return TG_EINVAL;
+    }
+  }
+  double *no_out[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int rc = tg_trace_f64(model_host, nb, &in, no_out, dabcd, TG_JAC_ABCD5, s);
+  if (rc == TG_OK) rc = tg_gaussian_qinv_f64(nb, waist_xy, radii_xy, wavelength, theta, dq, s);
+  if (rc == TG_OK) rc = tg_wave_numbers(nb, wavelength, rays[5], dk, dp0, s);
+  if (rc == TG_OK)
+    rc = tg_beamlet_coeffs_abcd_f64(nb, amplitude, dp0, dq, dabcd, rays[0], rays[1], rays[2], rays[3], dk, dpoly, s);
+  if (rc == TG_OK)
+    rc = tg_field_sum(nb, dpoly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, method, s);
+  cudaFreeAsync(scratch, s);
+  return rc;
+}
+
 extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t nb,
                                            const double *const rays[7], const double *amplitude,
                                            const double *waist_xy, const double *radii_xy,
@@ -228,11 +272,10 @@ extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t n
   if (rc != TG_OK) return rc;
   cudaStream_t s = st.s[0];
   const size_t npix = (size_t)nrows * W, elt = out_is_c128 ? 16 : 8;
-  // device layout (doubles): rays 7n | amp n | waist 2n | radii 2n | wl n | theta n | k n | p0 n |
-  //                          abcd 25n | qinv 8n | poly 12n | field
-  const size_t nd = (size_t)nb * (7 + 1 + 2 + 2 + 1 + 1 + 1 + 1 + 25 + 8 + 12);
+  // device layout (doubles): rays 7n | amp n | waist 2n | radii 2n | wl n | theta n | field
+  const size_t nd = (size_t)nb * 14;
   unsigned char *d = nullptr;
-  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d), nd * 8 + 256 + npix * elt, s));
+  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d), ((nd * 8 + 255) / 256) * 256 + npix * elt, s));
   double *p = reinterpret_cast<double *>(d);
   double *dr[7];
   for (int f = 0; f < 7; ++f) { dr[f] = p; p += nb; }
@@ -241,11 +284,6 @@ extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t n
   double *drad = p; p += 2 * nb;
   double *dwl = p; p += nb;
   double *dth = p; p += nb;
-  double *dk = p; p += nb;
-  double *dp0 = p; p += nb;
-  double *dabcd = p; p += 25 * nb;
-  double *dq = p; p += 8 * nb;
-  double *dpoly = p; p += 12 * nb;
   void *dout = d + ((nd * 8 + 255) / 256) * 256;
   cudaError_t e = cudaSuccess;
   auto up = [&](double *dst, const double *src, size_t cnt) {
@@ -261,26 +299,9 @@ extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t n
     tg_set_error("H2D copy: %s", cudaGetErrorString(e));
     rc = TG_ECUDA;
   }
-  if (rc == TG_OK && nb > 0) {
-    tg_ray_in in;
-    for (int f = 0; f < 7; ++f) { in.ptr[f] = dr[f]; in.value[f] = 0.0; }
-    double *no_out[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    rc = tg_trace_f64(model_host, nb, &in, no_out, dabcd, TG_JAC_ABCD5, s);
-    if (rc == TG_OK) rc = tg_gaussian_qinv_f64(nb, dw, drad, dwl, dth, dq, s);
-    if (rc == TG_OK) rc = tg_wave_numbers(nb, dwl, dr[5], dk, dp0, s);
-    if (rc == TG_OK)
-      rc = tg_beamlet_coeffs_abcd_f64(nb, damp, dp0, dq, dabcd, dr[0], dr[1], dr[2], dr[3], dk, dpoly, s);
-  }
-  if (rc == TG_OK) {
-    bool done = false;
-    if (method == TG_METHOD_AUTO || method == TG_METHOD_TENSOR) {
-      rc = tg_field_sum_separable(nb, dpoly, px2m, H, W, row0, nrows, dout, out_is_c128, s);
-      if (rc == TG_OK) done = true;
-      else if (rc == TG_ENOTSEPARABLE && method == TG_METHOD_AUTO) rc = TG_OK;
-    }
-    if (rc == TG_OK && !done)
-      rc = tg_field_sum_grid(nb, dpoly, px2m, H, W, row0, nrows, dout, out_is_c128, cull_bits, nullptr, s);
-  }
+  if (rc == TG_OK)
+    rc = tg_make_gaussian_image_f64(model_host, nb, dr, damp, dw, drad, dwl, dth, px2m, H, W, row0, nrows, dout,
+                                    out_is_c128, cull_bits, method, s);
   if (rc == TG_OK) {
     e = cudaMemcpyAsync(out, dout, npix * elt, cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) {

@@ -120,7 +120,9 @@ struct GemmSmemCtl {
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                        const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                       int M, int Np, int K, double *__restrict__ out, long long ldo, int accumulate_out) {
+                       int M, int Np, int K, double *__restrict__ out, long long ldo, int accumulate_out,
+                       const unsigned long long *__restrict__ sep_guard) {
+  if (sep_guard && !tg_key_is_separable(*sep_guard)) return;  // the SFU path owns this call
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem) + 1023) &
                                                            ~uintptr_t(1023));
@@ -291,7 +293,9 @@ __device__ __forceinline__ double col_env_max(double E1, double E3, double Wm1) 
 // A[(row - row0)][2n..2n+1] for rows [row0, row0+M), beamlets [b0, b0+nbatch)
 __global__ void __launch_bounds__(256)
     factor_rows_kernel(const double *__restrict__ table, long long b0, int nbatch, int row0, int M, int W,
-                       long long ldk, float *__restrict__ Ahi, float *__restrict__ Alo) {
+                       long long ldk, float *__restrict__ Ahi, float *__restrict__ Alo,
+                       const unsigned long long *__restrict__ sep_guard) {
+  if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   if (n >= nbatch || m >= M) return;
@@ -310,7 +314,9 @@ __global__ void __launch_bounds__(256)
 // B[2c][2n..] = (Re V, -Im V), B[2c+1][2n..] = (Im V, Re V)
 __global__ void __launch_bounds__(256)
     factor_cols_kernel(const double *__restrict__ table, long long b0, int nbatch, int W, long long ldk,
-                       float *__restrict__ Bhi, float *__restrict__ Blo) {
+                       float *__restrict__ Bhi, float *__restrict__ Blo,
+                       const unsigned long long *__restrict__ sep_guard) {
+  if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
   if (n >= nbatch || c >= W) return;
@@ -346,7 +352,9 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void __launch_bounds__(256)
-    f64_to_c64_kernel(const double *__restrict__ in, float *__restrict__ out, size_t n) {
+    f64_to_c64_kernel(const double *__restrict__ in, float *__restrict__ out, size_t n,
+                      const unsigned long long *__restrict__ sep_guard) {
+  if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (float)in[i];
 }
@@ -391,7 +399,8 @@ int make_map(CUtensorMap *m, const float *base, long long rows, long long K, lon
 }
 
 int launch_gemm(const float *Ahi, const float *Alo, const float *Bhi, const float *Blo, int M, int Np, int K,
-                long long ldk, double *out, long long ldo, int accumulate, cudaStream_t st) {
+                long long ldk, double *out, long long ldo, int accumulate,
+                const unsigned long long *sep_guard, cudaStream_t st) {
   CUtensorMap ta, tb, tc, td;
   int rc;
   if ((rc = make_map(&ta, Ahi, M, K, ldk)) != TG_OK) return rc;
@@ -401,7 +410,8 @@ int launch_gemm(const float *Ahi, const float *Alo, const float *Bhi, const floa
   const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
   TG_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((Np + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
-  gemm_tf32x3_kernel<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, tc, td, M, Np, K, out, ldo, accumulate);
+  gemm_tf32x3_kernel<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, tc, td, M, Np, K, out, ldo, accumulate,
+                                                       sep_guard);
   return tg_launch_check("gemm_tf32x3_kernel");
 }
 
@@ -417,15 +427,23 @@ extern "C" int tg_gemm_tf32x3(int M, int N, int K, const float *A_hi, const floa
   TG_REQUIRE(((uintptr_t)A_hi % 16) == 0 && ((uintptr_t)A_lo % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 &&
                  ((uintptr_t)B_lo % 16) == 0,
              "operands must be 16-byte aligned");
-  return launch_gemm(A_hi, A_lo, B_hi, B_lo, M, N, K, ldk, D, ldd, accumulate, static_cast<cudaStream_t>(stream));
+  return launch_gemm(A_hi, A_lo, B_hi, B_lo, M, N, K, ldk, D, ldd, accumulate, nullptr,
+                     static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6], int H, int W,
                                       int row0, int nrows, void *out, int out_is_c128, void *stream) {
+  return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
+                     int nrows, void *out, int out_is_c128, unsigned long long *key_async,
+                     cudaStream_t stream) {
   TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad shape");
   TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
   TG_REQUIRE(px2m && out, "null pointer");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaStream_t st = stream;
   if (nrows == 0) return TG_OK;
   const size_t npix = (size_t)nrows * W;
   if (nb == 0) {
@@ -448,7 +466,8 @@ extern "C" int tg_field_sum_separable(int64_t nb, const double *poly, const doub
   unsigned char *ws = nullptr;
   TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), table_bytes + 256 + 2 * a_bytes + 2 * b_bytes + acc_bytes, st));
   double *table = reinterpret_cast<double *>(ws);
-  unsigned long long *key = reinterpret_cast<unsigned long long *>(ws + table_bytes);
+  unsigned long long *key = key_async ? key_async : reinterpret_cast<unsigned long long *>(ws + table_bytes);
+  const unsigned long long *guard = key_async;  // async mode: kernels decide on the device
   float *Ahi = reinterpret_cast<float *>(ws + table_bytes + 256);
   float *Alo = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Ahi) + a_bytes);
   float *Bhi = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Alo) + a_bytes);
@@ -463,7 +482,7 @@ extern "C" int tg_field_sum_separable(int64_t nb, const double *poly, const doub
     rc = tg_launch_check("cross_term_kernel");
   }
   unsigned long long hkey = 0;
-  if (e == cudaSuccess && rc == TG_OK) {
+  if (e == cudaSuccess && rc == TG_OK && !key_async) {
     e = cudaMemcpyAsync(&hkey, key, 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   }
@@ -471,7 +490,7 @@ extern "C" int tg_field_sum_separable(int64_t nb, const double *poly, const doub
     tg_set_error("tg_field_sum_separable: %s", cudaGetErrorString(e));
     rc = TG_ECUDA;
   }
-  if (rc == TG_OK) {
+  if (rc == TG_OK && !key_async) {
     double worst;
     memcpy(&worst, &hkey, 8);
     if (worst > 1.0) {
@@ -484,16 +503,36 @@ extern "C" int tg_field_sum_separable(int64_t nb, const double *poly, const doub
     const int K = 2 * nbatch;
     // (the tensor maps are encoded with the true K: the TMA unit zero-fills the K padding)
     dim3 ga((unsigned)((nbatch + 255) / 256), (unsigned)nrows), gb((unsigned)((nbatch + 255) / 256), (unsigned)W);
-    factor_rows_kernel<<<ga, 256, 0, st>>>(table, b0, nbatch, row0, nrows, W, ldk, Ahi, Alo);
-    factor_cols_kernel<<<gb, 256, 0, st>>>(table, b0, nbatch, W, ldk, Bhi, Blo);
+    factor_rows_kernel<<<ga, 256, 0, st>>>(table, b0, nbatch, row0, nrows, W, ldk, Ahi, Alo, guard);
+    factor_cols_kernel<<<gb, 256, 0, st>>>(table, b0, nbatch, W, ldk, Bhi, Blo, guard);
     rc = tg_launch_check("factor kernels");
-    if (rc == TG_OK) rc = launch_gemm(Ahi, Alo, Bhi, Blo, nrows, Np, K, ldk, acc, (long long)Np, b0 > 0 ? 1 : 0, st);
+    if (rc == TG_OK) rc = launch_gemm(Ahi, Alo, Bhi, Blo, nrows, Np, K, ldk, acc, (long long)Np, b0 > 0 ? 1 : 0, guard, st);
   }
   if (rc == TG_OK && !out_is_c128) {
     const size_t n = npix * 2;
-    f64_to_c64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, static_cast<float *>(out), n);
+    f64_to_c64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, static_cast<float *>(out), n, guard);
     rc = tg_launch_check("f64_to_c64_kernel");
   }
   cudaFreeAsync(ws, st);
+  return rc;
+}
+
+// method dispatch: AUTO enqueues BOTH paths with a device-side separability verdict (no host sync)
+extern "C" int tg_field_sum(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
+                            int nrows, void *out, int out_is_c128, int cull_bits, int method, void *stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (method == TG_METHOD_SFU)
+    return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st);
+  if (method == TG_METHOD_TENSOR)
+    return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr, st);
+  TG_REQUIRE(method == TG_METHOD_AUTO, "unknown method");
+  if (nb == 0 || nrows == 0)
+    return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st);
+  unsigned long long *key = nullptr;
+  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&key), 8, st));
+  int rc = tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, key, st);
+  if (rc == TG_OK)
+    rc = tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, key, st);
+  cudaFreeAsync(key, st);
   return rc;
 }

@@ -13,6 +13,21 @@ int tg_launch_prep(int64_t nb, const double *poly, const double px2m[6], int H, 
 int tg_wave_numbers(int64_t nb, const double *wavelength, const double *pathlength, double *k,
                     double *p0, cudaStream_t st);
 
+int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
+                      int nrows, void *out, int out_is_c128, int cull_bits, long long *n_evals_out,
+                      const unsigned long long *sep_guard, cudaStream_t stream);
+// key_async != NULL: no host sync; the verdict stays on the device in *key_async and the kernels of
+// this path return at once when it says "not separable".
+int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
+                     int nrows, void *out, int out_is_c128, unsigned long long *key_async,
+                     cudaStream_t stream);
+// separability key = bits of max_n(cross term / tolerance) as a double (0 when there is none)
+__host__ __device__ inline bool tg_key_is_separable(unsigned long long key) {
+  union { unsigned long long u; double d; } c;
+  c.u = key;
+  return !(c.d > 1.0);
+}
+
 #define TG_CUDA(call)                                                                   \
   do {                                                                                  \
     cudaError_t err__ = (call);                                                         \

@@ -174,22 +174,19 @@ def _field_sum_grid(poly, nb, grid: Grid, dev, row0=0, nrows=None, out_dtype=Non
     cull = DEFAULT_CULL_BITS if cull_bits is None else int(cull_bits)
     out = torch.empty((nrows, W), dtype=out_dtype, device=dev)
     nev = C.c_longlong(0)
-    if method in ("tensor", "auto") and not count_evals:
-        with torch.cuda.device(dev):
-            rc = lib.tg_field_sum_separable(nb, poly.data_ptr() if nb else None,
-                                            L.dbl_array(grid.px2m_affine), H, W, row0, nrows,
-                                            out.data_ptr(), int(out_dtype == torch.complex128),
-                                            A.current_stream_ptr(dev))
-        if rc == L.TG_OK:
-            return out
-        if not (rc == L.TG_ENOTSEPARABLE and method == "auto"):
-            L.check(rc, "tg_field_sum_separable")
     with torch.cuda.device(dev):
-        L.check(lib.tg_field_sum_grid(nb, poly.data_ptr() if nb else None, L.dbl_array(grid.px2m_affine),
-                                      H, W, row0, nrows, out.data_ptr(),
-                                      int(out_dtype == torch.complex128), cull,
-                                      C.byref(nev) if count_evals else None,
-                                      A.current_stream_ptr(dev)), "tg_field_sum_grid")
+        if count_evals:
+            if method == "tensor":
+                raise ValueError("count_evals is a property of the SFU kernel")
+            L.check(lib.tg_field_sum_grid(nb, poly.data_ptr() if nb else None,
+                                          L.dbl_array(grid.px2m_affine), H, W, row0, nrows,
+                                          out.data_ptr(), int(out_dtype == torch.complex128), cull,
+                                          C.byref(nev), A.current_stream_ptr(dev)), "tg_field_sum_grid")
+        else:
+            L.check(lib.tg_field_sum(nb, poly.data_ptr() if nb else None, L.dbl_array(grid.px2m_affine),
+                                     H, W, row0, nrows, out.data_ptr(),
+                                     int(out_dtype == torch.complex128), cull, L.TG_METHOD[method],
+                                     A.current_stream_ptr(dev)), "tg_field_sum")
     return (out, int(nev.value)) if count_evals else out
 
 
@@ -311,9 +308,35 @@ def make_gaussian_image(gaussian_rays, model, batch_size=128, *, cull_bits=None,
         out = make_gaussian_image_host(rays, model, cull_bits=cull_bits, out_dtype=out_dtype,
                                        method=method)
         return out if kind == A.KIND_TORCH_CPU else out.numpy()
-    poly, n, dev = beamlet_polynomials(rays, model)
-    out = _field_sum_grid(poly, n, grid, dev, out_dtype=out_dtype, cull_bits=cull_bits, method=method)
-    return _finish(out, kind)
+    return make_gaussian_image_device(rays, model, cull_bits=cull_bits, out_dtype=out_dtype, method=method)
+
+
+def make_gaussian_image_device(gaussian_rays, model, *, cull_bits=None, out_dtype=None, method="auto",
+                               row0=0, nrows=None):
+    """``make_gaussian_image`` for device-resident inputs through the single C-ABI call
+    ``tg_make_gaussian_image_f64`` (everything enqueued on torch's current stream, no host
+    synchronisation); returns a CUDA tensor of rows ``[row0, row0+nrows)``."""
+    import torch
+    lib = L.load()
+    grid = model[-1]
+    H, W = int(grid.shape[0]), int(grid.shape[1])
+    nrows = H - row0 if nrows is None else nrows
+    dev = _device_for(gaussian_rays)
+    g = _beamlet_arrays(gaussian_rays, dev)
+    out_dtype = torch.complex128 if out_dtype is None else out_dtype
+    if out_dtype not in (torch.complex64, torch.complex128):
+        raise ValueError("out_dtype must be torch.complex64 or torch.complex128")
+    cull = DEFAULT_CULL_BITS if cull_bits is None else int(cull_bits)
+    out = torch.empty((nrows, W), dtype=out_dtype, device=dev)
+    cm = compile_model(model)
+    with torch.cuda.device(dev):
+        L.check(lib.tg_make_gaussian_image_f64(
+            C.byref(cm), g["n"], L.ptr_array([g[f].data_ptr() for f in RAY_FIELDS]),
+            g["amplitude"].data_ptr(), g["waist_xy"].data_ptr(), g["radii_of_curv"].data_ptr(),
+            g["wavelength"].data_ptr(), g["theta"].data_ptr(), L.dbl_array(grid.px2m_affine), H, W,
+            row0, nrows, out.data_ptr(), int(out_dtype == torch.complex128), cull, L.TG_METHOD[method],
+            A.current_stream_ptr(dev)), "tg_make_gaussian_image_f64")
+    return out
 
 
 def evaluate_gaussian_input_image(gaussian_rays, grid, batch_size=128, *, cull_bits=None,
