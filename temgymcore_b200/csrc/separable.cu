@@ -269,16 +269,6 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-__device__ __forceinline__ void cis_turns(double turns, float bits, float &re, float &im) {
-  const float fr = (float)(turns - rint(turns));
-  float amp, s, c;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(amp) : "f"(bits));
-  const float ang = fr * 6.28318530717958648f;
-  s = __sinf(ang);
-  c = __cosf(ang);
-  re = amp * c;
-  im = amp * s;
-}
 // max over c in [0, W-1] of E1 c + E3 c^2 (the column part of the envelope exponent, bits)
 __device__ __forceinline__ double col_env_max(double E1, double E3, double Wm1) {
   double best = fmax(0.0, Wm1 * (E1 + E3 * Wm1));
@@ -290,50 +280,102 @@ __device__ __forceinline__ double col_env_max(double E1, double E3, double Wm1) 
 }
 
 // table: pixel-space {T0..T5, E0..E5} per beamlet (prep_kernel of field.cu).
-// A[(row - row0)][2n..2n+1] for rows [row0, row0+M), beamlets [b0, b0+nbatch)
-__global__ void __launch_bounds__(256)
+//
+// One thread per beamlet walks a strip of FS consecutive rows (or columns): the table entry and
+// the fp64 strip setup are paid once per strip; along the strip the phase advances in 32-bit
+// fixed-point turns by exact integer differences and the envelope is the pivot-form fp32
+// quadratic of the SFU kernel (field.cu).  Stores are coalesced: for a fixed row, consecutive
+// threads (beamlets) write consecutive k' pairs.
+constexpr int FS = 32;
+constexpr double kMagicF = 1572864.0;  // 1.5 * 2^20
+
+struct Strip1D {
+  uint32_t t0, d0, dd;
+  float jp, ep, e1p, e2;
+};
+// quadratic phase (turns) p0 + p1 s + p2 s^2 and envelope (bits) q0 + q1 s + q2 s^2 on s = s0 + j
+__device__ __forceinline__ Strip1D strip_setup(double p0, double p1, double p2, double q0, double q1,
+                                               double q2, double s0) {
+  Strip1D r;
+  const double ph = p0 + s0 * (p1 + p2 * s0);
+  const double dl = p1 + p2 * (2.0 * s0 + 1.0);
+  const double d2 = 2.0 * p2;
+  r.t0 = (uint32_t)__double2loint((ph - rint(ph)) + kMagicF) + 0x100u;
+  r.d0 = (uint32_t)__double2loint((dl - rint(dl)) + kMagicF);
+  r.dd = (uint32_t)__double2loint((d2 - rint(d2)) + kMagicF);
+  // pivot = strip pixel nearest the envelope vertex
+  double js = 0.0;
+  if (q2 < -1e-12) js = -0.5 * q1 / q2 - s0;
+  const float jpf = fminf(fmaxf(rintf((float)js), 0.f), (float)(FS - 1));
+  const double sp = s0 + (double)jpf;
+  r.jp = jpf;
+  r.ep = (float)(q0 + sp * (q1 + q2 * sp));
+  r.e1p = (float)(q1 + 2.0 * q2 * sp);
+  r.e2 = (float)q2;
+  return r;
+}
+__device__ __forceinline__ void strip_eval(const Strip1D &r, int j, float &re, float &im) {
+  const uint32_t tj = r.t0 + (uint32_t)j * r.d0 + (uint32_t)(j * (j - 1) / 2) * r.dd;
+  const float ft = __uint_as_float((tj >> 9) | 0x3f800000u);
+  const float ang = fmaf(ft, 6.28318530717958648f, -9.42477796076937972f);  // 2 pi frac - pi
+  const float dj = (float)j - r.jp;
+  const float ej = fmaf(dj, fmaf(dj, r.e2, r.e1p), r.ep);
+  float amp;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(amp) : "f"(ej));
+  re = -amp * __cosf(ang);  // exp(i 2 pi frac) = -(cos ang + i sin ang)
+  im = -amp * __sinf(ang);
+}
+
+// A[(row - row0)][2n..2n+1] = U_n(row) for rows [row0, row0+M), beamlets [b0, b0+nbatch)
+__global__ void __launch_bounds__(128)
     factor_rows_kernel(const double *__restrict__ table, long long b0, int nbatch, int row0, int M, int W,
                        long long ldk, float *__restrict__ Ahi, float *__restrict__ Alo,
                        const unsigned long long *__restrict__ sep_guard) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int m = blockIdx.y;
-  if (n >= nbatch || m >= M) return;
+  const int m0 = blockIdx.y * FS;
+  if (n >= nbatch) return;
   const double *t = table + (b0 + n) * 12;
-  const double u = (double)(row0 + m);
   const double mu = col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
-  const double turns = t[0] + u * (t[2] + t[5] * u);
-  const float bits = (float)(t[6 + 0] + u * (t[6 + 2] + t[6 + 5] * u) + mu);
-  float re, im;
-  cis_turns(turns, bits, re, im);
-  const float rh = tf32_rna(re), ih = tf32_rna(im);
-  const long long o = (long long)m * ldk + 2 * n;
-  *reinterpret_cast<float2 *>(Ahi + o) = make_float2(rh, ih);
-  *reinterpret_cast<float2 *>(Alo + o) = make_float2(re - rh, im - ih);
+  const Strip1D st = strip_setup(t[0], t[2], t[5], t[6 + 0] + mu, t[6 + 2], t[6 + 5], (double)(row0 + m0));
+#pragma unroll 4
+  for (int j = 0; j < FS; ++j) {
+    if (m0 + j < M) {
+      float re, im;
+      strip_eval(st, j, re, im);
+      const float rh = tf32_rna(re), ih = tf32_rna(im);
+      const long long o = (long long)(m0 + j) * ldk + 2 * n;
+      *reinterpret_cast<float2 *>(Ahi + o) = make_float2(rh, ih);
+      *reinterpret_cast<float2 *>(Alo + o) = make_float2(re - rh, im - ih);
+    }
+  }
 }
-// B[2c][2n..] = (Re V, -Im V), B[2c+1][2n..] = (Im V, Re V)
-__global__ void __launch_bounds__(256)
+// B[2c][2n..] = (Re V, -Im V), B[2c+1][2n..] = (Im V, Re V), V_n(col) without the constant term
+__global__ void __launch_bounds__(128)
     factor_cols_kernel(const double *__restrict__ table, long long b0, int nbatch, int W, long long ldk,
                        float *__restrict__ Bhi, float *__restrict__ Blo,
                        const unsigned long long *__restrict__ sep_guard) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = blockIdx.y;
-  if (n >= nbatch || c >= W) return;
+  const int c0 = blockIdx.y * FS;
+  if (n >= nbatch) return;
   const double *t = table + (b0 + n) * 12;
-  const double v = (double)c;
   const double mu = col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
-  const double turns = v * (t[1] + t[3] * v);
-  const float bits = (float)(v * (t[6 + 1] + t[6 + 3] * v) - mu);
-  float re, im;
-  cis_turns(turns, bits, re, im);
-  const float rh = tf32_rna(re), ih = tf32_rna(im);
-  const float rl = re - rh, il = im - ih;
-  const long long o0 = (long long)(2 * c) * ldk + 2 * n, o1 = o0 + ldk;
-  *reinterpret_cast<float2 *>(Bhi + o0) = make_float2(rh, -ih);
-  *reinterpret_cast<float2 *>(Blo + o0) = make_float2(rl, -il);
-  *reinterpret_cast<float2 *>(Bhi + o1) = make_float2(ih, rh);
-  *reinterpret_cast<float2 *>(Blo + o1) = make_float2(il, rl);
+  const Strip1D st = strip_setup(0.0, t[1], t[3], -mu, t[6 + 1], t[6 + 3], (double)c0);
+#pragma unroll 4
+  for (int j = 0; j < FS; ++j) {
+    if (c0 + j < W) {
+      float re, im;
+      strip_eval(st, j, re, im);
+      const float rh = tf32_rna(re), ih = tf32_rna(im);
+      const float rl = re - rh, il = im - ih;
+      const long long o0 = (long long)(2 * (c0 + j)) * ldk + 2 * n, o1 = o0 + ldk;
+      *reinterpret_cast<float2 *>(Bhi + o0) = make_float2(rh, -ih);
+      *reinterpret_cast<float2 *>(Blo + o0) = make_float2(rl, -il);
+      *reinterpret_cast<float2 *>(Bhi + o1) = make_float2(ih, rh);
+      *reinterpret_cast<float2 *>(Blo + o1) = make_float2(il, rl);
+    }
+  }
 }
 
 // max over beamlets of the cross-term contribution across the detector (turns, bits)
@@ -502,9 +544,10 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
     const int nbatch = (int)((nb - b0) < kBatch ? (nb - b0) : kBatch);
     const int K = 2 * nbatch;
     // (the tensor maps are encoded with the true K: the TMA unit zero-fills the K padding)
-    dim3 ga((unsigned)((nbatch + 255) / 256), (unsigned)nrows), gb((unsigned)((nbatch + 255) / 256), (unsigned)W);
-    factor_rows_kernel<<<ga, 256, 0, st>>>(table, b0, nbatch, row0, nrows, W, ldk, Ahi, Alo, guard);
-    factor_cols_kernel<<<gb, 256, 0, st>>>(table, b0, nbatch, W, ldk, Bhi, Blo, guard);
+    dim3 ga((unsigned)((nbatch + 127) / 128), (unsigned)((nrows + FS - 1) / FS));
+    dim3 gb((unsigned)((nbatch + 127) / 128), (unsigned)((W + FS - 1) / FS));
+    factor_rows_kernel<<<ga, 128, 0, st>>>(table, b0, nbatch, row0, nrows, W, ldk, Ahi, Alo, guard);
+    factor_cols_kernel<<<gb, 128, 0, st>>>(table, b0, nbatch, W, ldk, Bhi, Blo, guard);
     rc = tg_launch_check("factor kernels");
     if (rc == TG_OK) rc = launch_gemm(Ahi, Alo, Bhi, Blo, nrows, Np, K, ldk, acc, (long long)Np, b0 > 0 ? 1 : 0, guard, st);
   }
