@@ -42,7 +42,7 @@ extern "C" {
 /* ---- model descriptor --------------------------------------------------- */
 
 #define TG_MAX_COMPS 24
-#define TG_NPARAM 26
+#define TG_NPARAM 48
 
 /* opcodes: one per reference component class on the path */
 enum tg_op {
@@ -52,7 +52,9 @@ enum tg_op {
   TG_OP_DEFLECTOR = 2, /* Deflector           (components.py:476-482)  p[0]=def_x p[1]=def_y */
   TG_OP_BIPRISM = 3,   /* Biprism             (components.py:553-559)  p[0]=def_x */
   TG_OP_KRIVANEK = 4,  /* AberratedLensKrivanek (components.py:192-215; aberrations.py:42-108)
-                          p[0]=focal_length, p[1..25]=KrivanekCoeffs in field order */
+                          p[0]=focal_length, p[1..25]=KrivanekCoeffs in field order,
+                          p[26+2t], p[27+2t] = cos(m phi0), sin(m phi0) of harmonic term t in the
+                          order C12 C21 C23 C32 C34 C41 C43 C45 C52 C54 C56 */
   TG_OP_OFFSET = 5,    /* Scanner / Descanner (components.py:279-285, 343-372)
                           p[0..3] = offsets added to x, y, dx, dy times _one */
   TG_OP_THICKLENS = 6, /* ThickLens           (components.py:431-452)  p[0]=focal_length,
@@ -110,6 +112,23 @@ int tg_trace_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in,
 /* host-buffer variant: pointers in `in`, `out`, `jac` are HOST memory. */
 int tg_trace_f64_host(const tg_model *model_host, int64_t n, const tg_ray_in *in,
                       double *const out[7], double *jac, int jac_layout, int device);
+
+/* ---- parameter tangents (run_with_grads, run.py:182-267) -------------------- */
+/* Jacobian of the output ray w.r.t. up to TG_GRAD_LANES directions per launch.  A direction
+ * ("lane") is seeded either on an input ray field (ray_lane[f] = lane, or -1) or on component
+ * parameters: seed {comp, slot, lane, weight} adds `weight` to lane `lane` of the tangent of
+ * parameter `slot` of component `comp`, slot 0 = z, slot k+1 = p[k] (so derived parameters are
+ * seeded as linear combinations by the caller).  jac = n * 7 * TG_GRAD_LANES doubles,
+ * jac[i][r][lane] = d out_r / d direction_lane, rows r in state-vector order. */
+#define TG_GRAD_LANES 8
+#define TG_MAX_SEEDS 32
+typedef struct {
+  int32_t comp, slot, lane, reserved;
+  double weight;
+} tg_seed;
+int tg_trace_grad_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in,
+                      const int32_t ray_lane[7], const tg_seed *seeds, int n_seeds,
+                      double *const out[7], double *jac, void *stream);
 
 /* ---- K5: metres -> pixels ------------------------------------------------ */
 /* replaces Grid.metres_to_pixels(cast=True) (grid.py:120-153) given the inverse 3x3

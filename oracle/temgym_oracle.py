@@ -345,8 +345,8 @@ def apply_component(comp, ray: Ray) -> Ray:
             dy=ray.dy + (sp_x * de.syo_pxi + sp_y * de.syo_pyi + de.offsyi - st_y) * ray._one,
         )
     if name == "Rotator":  # components.py:503-523
-        angle = np.deg2rad(comp.angle)
-        c, s = np.cos(angle), np.sin(angle)
+        angle = comp.angle * (np.pi / 180.0)  # jnp.deg2rad
+        c, s = _cos(angle), _sin(angle)
         return Ray(
             x=ray.x * c - ray.y * s,
             y=ray.x * s + ray.y * c,
@@ -415,6 +415,52 @@ def jacobian_run_to_end(ray, components: Sequence[Any]):
         o = getattr(out, f)
         if not isinstance(o, Dual):
             o = Dual(np.broadcast_to(np.asarray(o, dtype=np.float64), (n,)), np.zeros((n, 7)))
+        J[:, i, :] = o.t
+        vals.append(np.array(o.v))
+    return Ray(*vals), J
+
+
+def run_with_grads(ray, components: Sequence[Any], directions):
+    """``run_with_grads`` (run.py:182-267) restated with forward-mode duals.
+
+    directions: list of ``("ray", field)`` or ``(component_index, (attr, ...))`` -- one tangent
+    lane each.  Returns ``(out Ray of (N,) arrays, J (N, 7, K))``, J[n, i, k] = d out_i / d dir_k.
+    """
+    import dataclasses as _dc
+    if not isinstance(ray, Ray):
+        ray = Ray.from_obj(ray)
+    r = ray.as_arrays()
+    n = r.x.shape[0]
+    K = len(directions)
+
+    def seeded(value, k):
+        t = np.zeros((n, K))
+        if k is not None:
+            t[:, k] = 1.0
+        return Dual(np.broadcast_to(np.asarray(value, dtype=np.float64), (n,)).copy(), t)
+
+    ray_k = {f: None for f in RAY_FIELDS}
+    comps = list(components)
+    for k, d in enumerate(directions):
+        if d[0] == "ray":
+            ray_k[d[1]] = k
+        else:
+            ci, path = d
+            c = comps[ci]
+            if len(path) == 1:
+                c = _dc.replace(c, **{path[0]: seeded(getattr(c, path[0]), k)})
+            else:  # ("descan_error", name)
+                inner = getattr(c, path[0])
+                c = _dc.replace(c, **{path[0]: inner._replace(**{path[1]: seeded(getattr(inner, path[1]), k)})})
+            comps[ci] = c
+    d_ray = Ray(*(seeded(getattr(r, f), ray_k[f]) for f in RAY_FIELDS))
+    out = run_to_end(d_ray, comps)
+    J = np.zeros((n, 7, K))
+    vals = []
+    for i, f in enumerate(RAY_FIELDS):
+        o = getattr(out, f)
+        if not isinstance(o, Dual):
+            o = Dual(np.broadcast_to(np.asarray(o, dtype=np.float64), (n,)), np.zeros((n, K)))
         J[:, i, :] = o.t
         vals.append(np.array(o.v))
     return Ray(*vals), J

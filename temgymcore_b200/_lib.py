@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtemgym_b200.so")
 
 TG_MAX_COMPS = 24
-TG_NPARAM = 26
+TG_NPARAM = 48
 
 TG_OP_PLANE, TG_OP_LENS, TG_OP_DEFLECTOR, TG_OP_BIPRISM = 0, 1, 2, 3
 TG_OP_KRIVANEK, TG_OP_OFFSET, TG_OP_THICKLENS, TG_OP_ROTATOR = 4, 5, 6, 7
@@ -38,6 +38,15 @@ class tg_ray_in(C.Structure):
     _fields_ = [("ptr", C.c_void_p * 7), ("value", C.c_double * 7)]
 
 
+class tg_seed(C.Structure):
+    _fields_ = [("comp", C.c_int32), ("slot", C.c_int32), ("lane", C.c_int32), ("reserved", C.c_int32),
+                ("weight", C.c_double)]
+
+
+TG_GRAD_LANES = 8
+TG_MAX_SEEDS = 32
+
+
 class TemGymError(RuntimeError):
     pass
 
@@ -51,6 +60,8 @@ SIGNATURES = {
     "tg_device_count": (_i32, []),
     "tg_trace_f64": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(tg_ray_in), C.POINTER(_vp), _vp, _i32, _vp]),
     "tg_trace_f64_host": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(tg_ray_in), C.POINTER(_vp), _vp, _i32, _i32]),
+    "tg_trace_grad_f64": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(tg_ray_in), C.POINTER(C.c_int32),
+                                 C.POINTER(tg_seed), _i32, C.POINTER(_vp), _vp, _vp]),
     "tg_metres_to_pixels": (_i32, [_i64, _vp, _vp, _dp, _vp, _vp, _i32, _vp]),
     "tg_metres_to_pixels_host": (_i32, [_i64, _vp, _vp, _dp, _vp, _vp, _i32, _i32]),
     "tg_into_image_i64": (_i32, [_i64, _vp, _vp, _i32, _i32, _vp, _vp]),

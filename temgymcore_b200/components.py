@@ -8,7 +8,7 @@ like the reference's ``component(ray)``.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass, field, fields
 from typing import Any, NamedTuple
 
 import numpy as np
@@ -41,6 +41,20 @@ class Component(HasParamsMixin):
     def __call__(self, ray):
         from .run import _apply_component_only
         return _apply_component_only(ray, self)
+
+    # parameter -> kernel tangent seeds [(slot, weight)], slot 0 = z, slot k+1 = p[k]
+    # (include/temgym_b200.h, tg_trace_grad_f64).  Fields that do not influence the ray map to [].
+    _TG_SLOTS = {}
+
+    def _tg_param_seeds(self, path):
+        name = path[0]
+        if len(path) == 1 and name == "z":
+            return [(0, 1.0)]
+        if len(path) == 1 and name in self._TG_SLOTS:
+            return [(self._TG_SLOTS[name], 1.0)]
+        if len(path) == 1 and name in {f.name for f in fields(self)}:
+            return []
+        raise RuntimeError(f"Cannot find {path} in parameters of {type(self).__name__}")
 
 
 class DescanError(NamedTuple):  # components.py:27-115
@@ -83,6 +97,7 @@ class Plane(Component):  # components.py:118-134
 class Lens(Component):  # components.py:137-174
     z: float
     focal_length: float
+    _TG_SLOTS = {"focal_length": 1}
 
     def _tg_spec(self):
         return L.TG_OP_LENS, _f(self.z), (_f(self.focal_length),)
@@ -96,7 +111,20 @@ class AberratedLensKrivanek(Lens):  # components.py:177-215
         c = self.coeffs
         if isinstance(c, dict):
             c = KrivanekCoeffs(**c)
-        return L.TG_OP_KRIVANEK, _f(self.z), (_f(self.focal_length),) + tuple(_f(v) for v in c.as_tuple())
+        # harmonic terms (m, phi0) in the kernel's order; cos/sin(m*phi0) are model constants
+        terms = ((2, c.phi12), (1, c.phi21), (3, c.phi23), (2, c.phi32), (4, c.phi34), (1, c.phi41),
+                 (3, c.phi43), (5, c.phi45), (2, c.phi52), (4, c.phi54), (6, c.phi56))
+        trig = []
+        for m, ph0 in terms:
+            trig += [float(np.cos(m * _f(ph0))), float(np.sin(m * _f(ph0)))]
+        return (L.TG_OP_KRIVANEK, _f(self.z),
+                (_f(self.focal_length),) + tuple(_f(v) for v in c.as_tuple()) + tuple(trig))
+
+    def _tg_param_seeds(self, path):
+        if path[0] == "coeffs":
+            raise NotImplementedError("tangents w.r.t. Krivanek aberration coefficients are not "
+                                      "implemented in the CUDA gradient kernel")
+        return super()._tg_param_seeds(path)
 
 
 @dataclass(frozen=True)
@@ -119,6 +147,7 @@ class Scanner(Component):  # components.py:252-285
     scan_pos_y: float
     scan_tilt_x: float = 0.
     scan_tilt_y: float = 0.
+    _TG_SLOTS = {"scan_pos_x": 1, "scan_pos_y": 2, "scan_tilt_x": 3, "scan_tilt_y": 4}
 
     def _tg_spec(self):
         return L.TG_OP_OFFSET, _f(self.z), (_f(self.scan_pos_x), _f(self.scan_pos_y),
@@ -145,6 +174,32 @@ class Descanner(Component):  # components.py:288-372
             sp_x * _f(de.sxo_pxi) + sp_y * _f(de.sxo_pyi) + _f(de.offsxi) - st_x,
             sp_x * _f(de.syo_pxi) + sp_y * _f(de.syo_pyi) + _f(de.offsyi) - st_y,
         )
+
+    def _tg_param_seeds(self, path):
+        # the kernel sees the four offsets o1..o4 (slots 1..4); chain rule of components.py:343-372
+        de = self.descan_error
+        sp_x, sp_y = _f(self.scan_pos_x), _f(self.scan_pos_y)
+        if len(path) == 1:
+            n = path[0]
+            if n == "scan_pos_x":
+                return [(1, _f(de.pxo_pxi) - 1.0), (2, _f(de.pyo_pxi)), (3, _f(de.sxo_pxi)), (4, _f(de.syo_pxi))]
+            if n == "scan_pos_y":
+                return [(1, _f(de.pxo_pyi)), (2, _f(de.pyo_pyi) - 1.0), (3, _f(de.sxo_pyi)), (4, _f(de.syo_pyi))]
+            if n == "scan_tilt_x":
+                return [(3, -1.0)]
+            if n == "scan_tilt_y":
+                return [(4, -1.0)]
+            return super()._tg_param_seeds(path)
+        if len(path) == 2 and path[0] == "descan_error":
+            n = path[1]
+            if isinstance(n, int):
+                n = DescanError._fields[n]
+            table = {"pxo_pxi": (1, sp_x), "pxo_pyi": (1, sp_y), "pyo_pxi": (2, sp_x), "pyo_pyi": (2, sp_y),
+                     "sxo_pxi": (3, sp_x), "sxo_pyi": (3, sp_y), "syo_pxi": (4, sp_x), "syo_pyi": (4, sp_y),
+                     "offpxi": (1, 1.0), "offpyi": (2, 1.0), "offsxi": (3, 1.0), "offsyi": (4, 1.0)}
+            if n in table:
+                return [table[n]]
+        raise RuntimeError(f"Cannot find {path} in parameters of Descanner")
 
 
 @dataclass(frozen=True)
@@ -173,12 +228,23 @@ class ThickLens(Component):  # components.py:409-452
     def _tg_spec(self):
         return L.TG_OP_THICKLENS, _f(self.z_po), (_f(self.focal_length), _f(self.z_po) - _f(self.z_pi))
 
+    def _tg_param_seeds(self, path):
+        n = path[0]
+        if n == "focal_length":
+            return [(1, 1.0)]
+        if n == "z_po":      # plane position and the z jump p[1] = z_po - z_pi
+            return [(0, 1.0), (2, 1.0)]
+        if n == "z_pi":
+            return [(2, -1.0)]
+        raise RuntimeError(f"Cannot find {path} in parameters of ThickLens")
+
 
 @dataclass(frozen=True)
 class Deflector(Component):  # components.py:455-482
     z: float
     def_x: float
     def_y: float
+    _TG_SLOTS = {"def_x": 1, "def_y": 2}
 
     def _tg_spec(self):
         return L.TG_OP_DEFLECTOR, _f(self.z), (_f(self.def_x), _f(self.def_y))
@@ -193,6 +259,13 @@ class Rotator(Component):  # components.py:485-523
         a = np.deg2rad(_f(self.angle))
         return L.TG_OP_ROTATOR, _f(self.z), (float(np.cos(a)), float(np.sin(a)))
 
+    def _tg_param_seeds(self, path):
+        if path[0] == "angle":  # p = (cos a, sin a), a = angle * pi / 180
+            a = np.deg2rad(_f(self.angle))
+            k = np.pi / 180.0
+            return [(1, float(-np.sin(a) * k)), (2, float(np.cos(a) * k))]
+        return super()._tg_param_seeds(path)
+
 
 @dataclass(frozen=True)
 class Biprism(Component):  # components.py:526-559 (offset, rotation, side are unused there too)
@@ -201,6 +274,7 @@ class Biprism(Component):  # components.py:526-559 (offset, rotation, side are u
     rotation: Degrees = 0.0
     def_x: float = 0.0
     side: int = 1
+    _TG_SLOTS = {"def_x": 1}
 
     def _tg_spec(self):
         return L.TG_OP_BIPRISM, _f(self.z), (_f(self.def_x),)

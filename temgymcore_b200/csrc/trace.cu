@@ -210,6 +210,17 @@ template <int N>
 __device__ __forceinline__ Dual<N> dwhere_zero(const Dual<N> &a, double eps) {
   return a.v == 0.0 ? dconst<N>(eps) : a;
 }
+// 1 / a with ONE fp64 division (value and tangents share the reciprocal)
+template <int N>
+__device__ __forceinline__ Dual<N> drecip(const Dual<N> &a) {
+  Dual<N> r;
+  const double q = 1.0 / a.v;
+  r.v = q;
+  const double s = -(q * q);
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = a.t[k] * s;
+  return r;
+}
 template <int M, int N>
 __device__ __forceinline__ Dual<M> dnarrow(const Dual<N> &a) {
   // keep the value; keep tangents only if the destination tracks them
@@ -232,60 +243,84 @@ enum {
   K_PHI54, K_C56, K_PHI56
 };
 
-// One harmonic term: B += C cos(m (phi - phi0)),  T += (-m C) sin(m (phi - phi0)).
-// Terms with C == 0 contribute exactly zero in the reference as well and are skipped
-// (uniform branch on kernel-parameter constants).
+// One harmonic term: B += C cos(m (phi - phi0)),  T += (-m C) sin(m (phi - phi0)), with
+// cos/sin(m phi) = Re/Im ((ax + i ay)/|a|)^m (cm, sm) and cos/sin(m phi0) model constants:
+//   cos(m(phi-phi0)) = cm c0 + sm s0,  sin(m(phi-phi0)) = sm c0 - cm s0
+// -- no atan2 / sincos in the kernel.  Terms with C == 0 contribute exactly zero in the
+// reference as well and are skipped (uniform branch on kernel-parameter constants).
 template <int N>
-__device__ __forceinline__ void kriv_term(double C, double m, const Dual<N> &phi, double phi0,
-                                          Dual<N> &B, Dual<N> &T) {
+__device__ __forceinline__ void kriv_term(double C, double m, const Dual<N> &cm, const Dual<N> &sm,
+                                          double c0, double s0, Dual<N> &B, Dual<N> &T) {
   if (C == 0.0) return;
-  Dual<N> sk, ck;
-  dsincos(m * (phi - phi0), sk, ck);
+  const Dual<N> ck = cm * c0 + sm * s0;
+  const Dual<N> sk = sm * c0 - cm * s0;
   B = B + C * ck;
   T = T + (-m * C) * sk;
 }
 
-// (dW/dax, dW/day, W) of the Krivanek aberration function; N is the tangent width of the
-// arguments (2 inside the ray kernel: tangents w.r.t. (ax, ay), chained to the ray tangents
-// by the caller, which keeps the live register set small).
+// (dW/dax, dW/day, W) of the Krivanek aberration function (aberrations.py:42-108); N is the
+// tangent width of the arguments (2 inside the ray kernel: tangents w.r.t. (ax, ay), chained to
+// the ray tangents by the caller, which keeps the live register set small).
+// p = comp.p + 1: 25 coefficients, then 11 (cos, sin)(m phi0) pairs.
 template <int N>
 __device__ __forceinline__ void krivanek(const double *p, const Dual<N> &ax, const Dual<N> &ay,
                                          Dual<N> &dWx, Dual<N> &dWy, Dual<N> &W) {
   const Dual<N> a = dhypot(ax, ay);
-  const Dual<N> phi = datan2(ay, ax);
+  // unit phasor e^{i phi}; at the origin phi = atan2(0,0) = 0 with NaN derivative like JAX
+  Dual<N> c1, s1;
+  if (a.v == 0.0) {
+    c1 = dconst<N>(1.0);
+    s1 = dconst<N>(0.0);
+#pragma unroll
+    for (int k = 0; k < (N > 0 ? N : 1); ++k) {
+      c1.t[k] = a.t[k] * 0.0 + (N > 0 ? nan("") : 0.0);
+      s1.t[k] = c1.t[k];
+    }
+  } else {
+    const Dual<N> ia = drecip(a);
+    c1 = ax * ia;
+    s1 = ay * ia;
+  }
+  const Dual<N> c2 = c1 * c1 - s1 * s1, s2 = s1 * c1 + c1 * s1;
+  const Dual<N> c3 = c2 * c1 - s2 * s1, s3 = s2 * c1 + c2 * s1;
+  const Dual<N> c4 = c2 * c2 - s2 * s2, s4 = s2 * c2 + c2 * s2;
+  const Dual<N> c5 = c4 * c1 - s4 * s1, s5 = s4 * c1 + c4 * s1;
+  const Dual<N> c6 = c3 * c3 - s3 * s3, s6 = s3 * c3 + c3 * s3;
+  const double *g = p + 25;  // (cos, sin)(m phi0) pairs
   // brackets (aberrations.py:42-48) and the matching sin sums of dW/dphi (aberrations.py:78-98)
   Dual<N> B2 = dconst<N>(p[K_C10]), T2 = dconst<N>(0.0);
-  kriv_term(p[K_C12], 2.0, phi, p[K_PHI12], B2, T2);
+  kriv_term(p[K_C12], 2.0, c2, s2, g[0], g[1], B2, T2);
   Dual<N> B3 = dconst<N>(0.0), T3 = dconst<N>(0.0);
-  kriv_term(p[K_C21], 1.0, phi, p[K_PHI21], B3, T3);
-  kriv_term(p[K_C23], 3.0, phi, p[K_PHI23], B3, T3);
+  kriv_term(p[K_C21], 1.0, c1, s1, g[2], g[3], B3, T3);
+  kriv_term(p[K_C23], 3.0, c3, s3, g[4], g[5], B3, T3);
   Dual<N> B4 = dconst<N>(p[K_C30]), T4 = dconst<N>(0.0);
-  kriv_term(p[K_C32], 2.0, phi, p[K_PHI32], B4, T4);
-  kriv_term(p[K_C34], 4.0, phi, p[K_PHI34], B4, T4);
+  kriv_term(p[K_C32], 2.0, c2, s2, g[6], g[7], B4, T4);
+  kriv_term(p[K_C34], 4.0, c4, s4, g[8], g[9], B4, T4);
   Dual<N> B5 = dconst<N>(0.0), T5 = dconst<N>(0.0);
-  kriv_term(p[K_C41], 1.0, phi, p[K_PHI41], B5, T5);
-  kriv_term(p[K_C43], 3.0, phi, p[K_PHI43], B5, T5);
-  kriv_term(p[K_C45], 5.0, phi, p[K_PHI45], B5, T5);
+  kriv_term(p[K_C41], 1.0, c1, s1, g[10], g[11], B5, T5);
+  kriv_term(p[K_C43], 3.0, c3, s3, g[12], g[13], B5, T5);
+  kriv_term(p[K_C45], 5.0, c5, s5, g[14], g[15], B5, T5);
   Dual<N> B6 = dconst<N>(p[K_C50]), T6 = dconst<N>(0.0);
-  kriv_term(p[K_C52], 2.0, phi, p[K_PHI52], B6, T6);
-  kriv_term(p[K_C54], 4.0, phi, p[K_PHI54], B6, T6);
-  kriv_term(p[K_C56], 6.0, phi, p[K_PHI56], B6, T6);
+  kriv_term(p[K_C52], 2.0, c2, s2, g[16], g[17], B6, T6);
+  kriv_term(p[K_C54], 4.0, c4, s4, g[18], g[19], B6, T6);
+  kriv_term(p[K_C56], 6.0, c6, s6, g[20], g[21], B6, T6);
   const Dual<N> a2 = a * a;
   const Dual<N> a3 = a2 * a;
   const Dual<N> a4 = a2 * a2;
   const Dual<N> a5 = a4 * a;
   const Dual<N> a6 = a3 * a3;
   // W (aberrations.py:51-60)
-  W = 0.5 * a2 * B2 + (a3 / 3.0) * B3 + 0.25 * a4 * B4 + 0.2 * a4 * a * B5 + (a6 / 6.0) * B6;
+  const double third = 1.0 / 3.0, sixth = 1.0 / 6.0;  // a3 / 3.0, a6 / 6.0 as multiplies (<= 1 ulp)
+  W = 0.5 * a2 * B2 + (a3 * third) * B3 + 0.25 * a4 * B4 + 0.2 * a4 * a * B5 + (a6 * sixth) * B6;
   // grad (aberrations.py:63-108)
   const Dual<N> dW_dalpha = a * B2 + a2 * B3 + a3 * B4 + a4 * B5 + a5 * B6;
   Dual<N> dW_dphi = (0.5 * a2) * T2;
-  dW_dphi = dW_dphi + (a3 / 3.0) * T3;
+  dW_dphi = dW_dphi + (a3 * third) * T3;
   dW_dphi = dW_dphi + (0.25 * a4) * T4;
   dW_dphi = dW_dphi + (0.2 * a4 * a) * T5;
-  dW_dphi = dW_dphi + (a6 / 6.0) * T6;
+  dW_dphi = dW_dphi + (a6 * sixth) * T6;
   const Dual<N> a_safe = dwhere_zero(a, 1e-30);
-  const Dual<N> inv_a = 1.0 / a_safe;
+  const Dual<N> inv_a = drecip(a_safe);
   const Dual<N> inv_a2 = inv_a * inv_a;
   dWx = dW_dalpha * (ax * inv_a) + dW_dphi * ((-ay) * inv_a2);
   dWy = dW_dalpha * (ay * inv_a) + dW_dphi * (ax * inv_a2);
@@ -311,7 +346,7 @@ struct TraceOut {
 // is identically zero for every component on the path (z only ever receives component
 // constants), and pathlength never feeds back into x,y,dx,dy.
 template <int NC, bool KRIV>
-__global__ void __launch_bounds__(kTraceThreads)
+__global__ void __launch_bounds__(kTraceThreads, (KRIV && NC == 5) ? 3 : 1)
     trace_kernel(const __grid_constant__ tg_model model, const tg_ray_in in, const long long n,
                  const TraceOut out, double *__restrict__ jac) {
   constexpr bool FULL = (NC == 7);
@@ -353,12 +388,23 @@ __global__ void __launch_bounds__(kTraceThreads)
         case TG_OP_LENS:
         case TG_OP_THICKLENS: {  // components.py:161-174, 431-447
           const double f = cm.p[0];
-          const Dual<NC> ndx = (-x) / f + dx;
-          const Dual<NC> ndy = (-y) / f + dy;
-          pl = pl - dnarrow<NZ>((x * x + y * y) / (2.0 * f));
+          if constexpr (KRIV) {
+            // compute-bound instantiation (a Krivanek lens is in the model): one reciprocal per
+            // lens instead of 13 fp64 divisions, <= 1 ulp from the exact quotient
+            const double inv_f = 1.0 / f;
+            const Dual<NC> ndx = (-x) * inv_f + dx;
+            const Dual<NC> ndy = (-y) * inv_f + dy;
+            pl = pl - dnarrow<NZ>((x * x + y * y) * (0.5 * inv_f));
+            dx = ndx;
+            dy = ndy;
+          } else {
+            const Dual<NC> ndx = (-x) / f + dx;
+            const Dual<NC> ndy = (-y) / f + dy;
+            pl = pl - dnarrow<NZ>((x * x + y * y) / (2.0 * f));
+            dx = ndx;
+            dy = ndy;
+          }
           one = one * 1.0;
-          dx = ndx;
-          dy = ndy;
           if (cm.op == TG_OP_THICKLENS) z = z - cm.p[1];
         } break;
         case TG_OP_DEFLECTOR: {  // components.py:476-482
@@ -389,9 +435,10 @@ __global__ void __launch_bounds__(kTraceThreads)
         } break;
         case TG_OP_KRIVANEK: {  // components.py:192-215
           if constexpr (KRIV) {
-            const double f = cm.p[0];
-            const Dual<NC> idx = (-x) / f + dx;
-            const Dual<NC> idy = (-y) / f + dy;
+            // compute-bound op: one reciprocal of f instead of ~25 fp64 divisions (<= 1 ulp each)
+            const double inv_f = 1.0 / cm.p[0];
+            const Dual<NC> idx = (-x) * inv_f + dx;
+            const Dual<NC> idy = (-y) * inv_f + dy;
             Dual<NC> dWx, dWy, W;
             if constexpr (NC == 0) {
               krivanek<0>(cm.p + 1, idx, idy, dWx, dWy, W);
@@ -402,10 +449,10 @@ __global__ void __launch_bounds__(kTraceThreads)
               dWy = dchain<NC>(gy, idx, idy);
               W = dchain<NC>(w2, idx, idy);
             }
-            const Dual<NC> dux = (-dWx) / f, duy = (-dWy) / f;
+            const Dual<NC> dux = (-dWx) * inv_f, duy = (-dWy) * inv_f;
             dx = idx + dux;
             dy = idy + duy;
-            pl = pl - dnarrow<NZ>((x * x + y * y) / (2.0 * f)) + dnarrow<NZ>(W / f);
+            pl = pl - dnarrow<NZ>((x * x + y * y) * (0.5 * inv_f)) + dnarrow<NZ>(W * inv_f);
             one = one * 1.0;
           }
         } break;
@@ -497,6 +544,127 @@ int launch_trace(const tg_model *m, int64_t n, const tg_ray_in *in, double *cons
               : launch_trace_k<NC, false>(m, n, in, out, jac, st);
 }
 
+// ------------------------------------------------------------------ parameter tangents
+// run_with_grads (reference run.py:182-267): Jacobians of the output ray w.r.t. selected input
+// ray fields AND component parameters.  Same forward-mode duals, but every state variable
+// carries TG_GRAD_LANES tangent lanes and component parameters are duals too: a seed
+// (comp, slot, lane, weight) adds `weight` to lane `lane` of parameter `slot` (0 = z,
+// k+1 = p[k]) of component `comp`; ray field f is seeded on lane ray_lane[f] (or -1).
+struct GradSeeds {
+  int n;
+  int ray_lane[7];
+  tg_seed s[TG_MAX_SEEDS];
+};
+constexpr int NT = TG_GRAD_LANES;
+
+__device__ __forceinline__ Dual<NT> gparam(const tg_model &m, const GradSeeds &gs, int c, int slot) {
+  Dual<NT> r = dconst<NT>(slot == 0 ? m.comp[c].z : m.comp[c].p[slot - 1]);
+  for (int i = 0; i < gs.n; ++i) {
+    if (gs.s[i].comp == c && gs.s[i].slot == slot) {
+#pragma unroll
+      for (int k = 0; k < NT; ++k) r.t[k] += (gs.s[i].lane == k) ? gs.s[i].weight : 0.0;
+    }
+  }
+  return r;
+}
+
+template <bool KRIV>
+__global__ void __launch_bounds__(kTraceThreads)
+    trace_grad_kernel(const __grid_constant__ tg_model model, const __grid_constant__ GradSeeds gs,
+                      const tg_ray_in in, const long long n, const TraceOut out, double *__restrict__ jac) {
+  const long long i = (long long)blockIdx.x * kTraceThreads + threadIdx.x;
+  if (i >= n) return;
+  auto ld = [&](int f) -> double { return in.ptr[f] ? __ldg(in.ptr[f] + i) : in.value[f]; };
+  using D = Dual<NT>;
+  D x = dseed<NT>(ld(0), gs.ray_lane[0]), y = dseed<NT>(ld(1), gs.ray_lane[1]);
+  D dx = dseed<NT>(ld(2), gs.ray_lane[2]), dy = dseed<NT>(ld(3), gs.ray_lane[3]);
+  D z = dseed<NT>(ld(4), gs.ray_lane[4]), pl = dseed<NT>(ld(5), gs.ray_lane[5]);
+  D one = dseed<NT>(ld(6), gs.ray_lane[6]);
+  const int nc = model.n_comp;
+  for (int c = 0; c < nc; ++c) {
+    const tg_comp &cm = model.comp[c];
+    if (!(cm.flags & TG_F_NOPROP)) {
+      const D zc = gparam(model, gs, c, 0);
+      const D d = (cm.flags & TG_F_DIST) ? zc : zc - z;
+      x = x + dx * d;
+      y = y + dy * d;
+      z = z + d;
+      pl = pl + d;
+    }
+    switch (cm.op) {
+      case TG_OP_LENS:
+      case TG_OP_THICKLENS: {
+        const D f = gparam(model, gs, c, 1);
+        const D ndx = (-x) / f + dx;
+        const D ndy = (-y) / f + dy;
+        pl = pl - (x * x + y * y) / (2.0 * f);
+        one = one * 1.0;
+        dx = ndx;
+        dy = ndy;
+        if (cm.op == TG_OP_THICKLENS) z = z - gparam(model, gs, c, 2);
+      } break;
+      case TG_OP_DEFLECTOR: {
+        pl = pl + dx * x + dy * y;
+        dx = dx + gparam(model, gs, c, 1) * one;
+        dy = dy + gparam(model, gs, c, 2) * one;
+      } break;
+      case TG_OP_BIPRISM: {
+        pl = pl + dx * x + dy * y;
+        dx = dx + gparam(model, gs, c, 1) * one * dsign(x);
+      } break;
+      case TG_OP_OFFSET: {
+        x = x + gparam(model, gs, c, 1) * one;
+        y = y + gparam(model, gs, c, 2) * one;
+        dx = dx + gparam(model, gs, c, 3) * one;
+        dy = dy + gparam(model, gs, c, 4) * one;
+      } break;
+      case TG_OP_ROTATOR: {
+        const D cs = gparam(model, gs, c, 1), sn = gparam(model, gs, c, 2);
+        const D nx = x * cs - y * sn, ny = x * sn + y * cs;
+        const D ndx = dx * cs - dy * sn, ndy = dx * sn + dy * cs;
+        x = nx;
+        y = ny;
+        dx = ndx;
+        dy = ndy;
+      } break;
+      case TG_OP_KRIVANEK: {
+        if constexpr (KRIV) {
+          const D f = gparam(model, gs, c, 1);
+          const D idx = (-x) / f + dx;
+          const D idy = (-y) / f + dy;
+          Dual<2> gx, gy, w2;  // aberration coefficients are constants here (no coefficient tangents)
+          krivanek<2>(cm.p + 1, dseed<2>(idx.v, 0), dseed<2>(idy.v, 1), gx, gy, w2);
+          const D dWx = dchain<NT>(gx, idx, idy), dWy = dchain<NT>(gy, idx, idy), W = dchain<NT>(w2, idx, idy);
+          dx = idx + (-dWx) / f;
+          dy = idy + (-dWy) / f;
+          pl = pl - (x * x + y * y) / (2.0 * f) + W / f;
+          one = one * 1.0;
+        }
+      } break;
+      default:
+        break;
+    }
+  }
+  if (out.ptr[0]) out.ptr[0][i] = x.v;
+  if (out.ptr[1]) out.ptr[1][i] = y.v;
+  if (out.ptr[2]) out.ptr[2][i] = dx.v;
+  if (out.ptr[3]) out.ptr[3][i] = dy.v;
+  if (out.ptr[4]) out.ptr[4][i] = z.v;
+  if (out.ptr[5]) out.ptr[5][i] = pl.v;
+  if (out.ptr[6]) out.ptr[6][i] = one.v;
+  double *row = jac + i * (7 * NT);
+#pragma unroll
+  for (int k = 0; k < NT; ++k) {
+    row[0 * NT + k] = x.t[k];
+    row[1 * NT + k] = y.t[k];
+    row[2 * NT + k] = dx.t[k];
+    row[3 * NT + k] = dy.t[k];
+    row[4 * NT + k] = z.t[k];
+    row[5 * NT + k] = pl.t[k];
+    row[6 * NT + k] = one.t[k];
+  }
+}
+
 // ------------------------------------------------------------------ K5
 __global__ void __launch_bounds__(256)
     m2p_kernel(long long n, const double *__restrict__ x, const double *__restrict__ y,
@@ -572,4 +740,43 @@ extern "C" int tg_into_image_i64(int64_t n, const int32_t *py, const int32_t *px
   into_image_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       n, py, px, H, W, reinterpret_cast<unsigned long long *>(image));
   return tg_launch_check("into_image_kernel");
+}
+
+extern "C" int tg_trace_grad_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in,
+                                 const int32_t ray_lane[7], const tg_seed *seeds, int n_seeds,
+                                 double *const out[7], double *jac, void *stream) {
+  TG_REQUIRE(model_host && in && ray_lane && jac, "null pointer");
+  TG_REQUIRE(model_host->n_comp >= 0 && model_host->n_comp <= TG_MAX_COMPS, "bad n_comp");
+  TG_REQUIRE(n >= 0 && n_seeds >= 0 && n_seeds <= TG_MAX_SEEDS, "bad sizes");
+  TG_REQUIRE(n_seeds == 0 || seeds, "null seeds");
+  if (n == 0) return TG_OK;
+  GradSeeds gs;
+  gs.n = n_seeds;
+  for (int f = 0; f < 7; ++f) {
+    TG_REQUIRE(ray_lane[f] >= -1 && ray_lane[f] < TG_GRAD_LANES, "ray lane out of range");
+    gs.ray_lane[f] = ray_lane[f];
+  }
+  bool kriv = false;
+  for (int c = 0; c < model_host->n_comp; ++c) kriv |= (model_host->comp[c].op == TG_OP_KRIVANEK);
+  for (int i = 0; i < n_seeds; ++i) {
+    const tg_seed &sd = seeds[i];
+    TG_REQUIRE(sd.comp >= 0 && sd.comp < model_host->n_comp, "seed component out of range");
+    TG_REQUIRE(sd.slot >= 0 && sd.slot <= TG_NPARAM, "seed slot out of range");
+    TG_REQUIRE(sd.lane >= 0 && sd.lane < TG_GRAD_LANES, "seed lane out of range");
+    if (model_host->comp[sd.comp].op == TG_OP_KRIVANEK && sd.slot >= 2) {
+      tg_set_error("tangents w.r.t. Krivanek aberration coefficients are not implemented");
+      return TG_EUNSUPPORTED;
+    }
+    gs.s[i] = sd;
+  }
+  TraceOut o;
+  for (int f = 0; f < 7; ++f) o.ptr[f] = out ? out[f] : nullptr;
+  const long long blocks = (n + kTraceThreads - 1) / kTraceThreads;
+  TG_REQUIRE(blocks <= 0x7fffffffLL, "too many rays for one launch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (kriv)
+    trace_grad_kernel<true><<<(unsigned)blocks, kTraceThreads, 0, st>>>(*model_host, gs, *in, (long long)n, o, jac);
+  else
+    trace_grad_kernel<false><<<(unsigned)blocks, kTraceThreads, 0, st>>>(*model_host, gs, *in, (long long)n, o, jac);
+  return tg_launch_check("trace_grad_kernel");
 }

@@ -59,7 +59,7 @@ def gaussian_beam(x, y, q_inv, k, offset_x=0, offset_y=0):
     return np.exp(1j * k * ((x + offset_x) ** 2 + (y + offset_y) ** 2) / 2 * q_inv)
 
 
-@dataclass(frozen=True, kw_only=True)
+@dataclass(frozen=True, kw_only=True, eq=False)
 class GaussianRay(Ray):
     """Ray + Gaussian beam parameters (gaussian.py:113-177)."""
     amplitude: Any

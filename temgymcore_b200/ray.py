@@ -18,7 +18,7 @@ from .tree_utils import HasParamsMixin
 RAY_FIELDS = ("x", "y", "dx", "dy", "z", "pathlength", "_one")
 
 
-@dataclass(frozen=True)
+@dataclass(frozen=True, eq=False)
 class Ray(HasParamsMixin):
     x: Any
     y: Any

@@ -276,3 +276,93 @@ def solve_model(ray, model: Sequence[Any], propagator: BasePropagator = FreeSpac
         import torch
         return torch.stack(mats)
     return np.array(mats)
+
+
+def run_with_grads(input_ray, model: Sequence[Any], grad_vars: Sequence[Any]):
+    """Run the model and compute Jacobians w.r.t. selected variables (run.py:182-267).
+
+    ``grad_vars`` holds ``input_ray`` itself (all seven fields), ``input_ray.params.<field>`` or
+    ``component.params.<name>`` references (components of ``model`` are matched by identity).
+    Returns ``(value, grads)``: the output ``Ray`` and a dict mapping each variable's path
+    ``(root, key, ...)`` to a ``Ray``-shaped Jacobian (d out_field / d variable per ray).
+    One launch of the CUDA gradient kernel serves up to 8 variables.
+    """
+    from .tree_utils import ParamRef
+    lib = L.load()
+    comps = list(model)
+    directions = []          # (key, ray_field_index | None, [(comp, slot, weight)])
+    for var in grad_vars:
+        if var is input_ray:
+            for i, f in enumerate(RAY_FIELDS):
+                directions.append(((input_ray, f), i, []))
+            continue
+        if not isinstance(var, ParamRef):
+            raise RuntimeError(f"Cannot find {var!r} in parameters")
+        root, path = var._resolve_root(), var._build()[1:]
+        if root is input_ray:
+            if len(path) != 1 or path[0] not in RAY_FIELDS:
+                raise RuntimeError(f"Cannot find {var._build()} in parameters")
+            directions.append((var._build(), RAY_FIELDS.index(path[0]), []))
+            continue
+        idx = next((i for i, c in enumerate(comps) if c is root), None)
+        if idx is None or not path:
+            raise RuntimeError(f"Cannot find {var._build()} in parameters")
+        seeds = [(idx, slot, w) for slot, w in root._tg_param_seeds(path)]
+        directions.append((var._build(), None, seeds))
+    if not directions:
+        raise RuntimeError("Cannot find any variable in parameters")
+
+    import torch
+    cm = compile_model(comps)
+    vals = [getattr(input_ray, f) for f in RAY_FIELDS]
+    kinds = [A.kind_of(v) for v in vals]
+    kind = max(kinds)
+    n = max(A.numel(v) for v in vals)
+    shape = next((A.shape_of(v) for v, k in zip(vals, kinds) if k != A.KIND_SCALAR), ())
+    dev = A.cuda_device_of(vals) or torch.device("cuda", A.current_device_index())
+    rin = L.tg_ray_in()
+    keep = []
+    for i, (v, k) in enumerate(zip(vals, kinds)):
+        if k == A.KIND_SCALAR:
+            rin.ptr[i] = None
+            rin.value[i] = A.to_float(v)
+        else:
+            t = A.to_device_f64(v, dev)
+            keep.append(t)
+            rin.ptr[i] = t.data_ptr()
+    outs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(7)]
+    lanes = L.TG_GRAD_LANES
+    grads = {}
+
+    def finish(t):
+        t = t.reshape(shape)
+        if kind == A.KIND_CUDA:
+            return t
+        if kind == A.KIND_SCALAR:
+            return float(t.reshape(-1)[0].item())
+        return t.cpu() if kind == A.KIND_TORCH_CPU else t.cpu().numpy()
+
+    for g0 in range(0, len(directions), lanes):
+        group = directions[g0:g0 + lanes]
+        ray_lane = (C.c_int32 * 7)(*([-1] * 7))
+        seeds = []
+        for lane, (_, rf, sd) in enumerate(group):
+            if rf is not None:
+                if ray_lane[rf] != -1:
+                    raise RuntimeError("a ray field was requested twice")
+                ray_lane[rf] = lane
+            seeds += [(c, slot, lane, w) for c, slot, w in sd]
+        if len(seeds) > L.TG_MAX_SEEDS:
+            raise RuntimeError("too many parameter seeds in one group")
+        arr = (L.tg_seed * max(1, len(seeds)))()
+        for i, (c, slot, lane, w) in enumerate(seeds):
+            arr[i].comp, arr[i].slot, arr[i].lane, arr[i].weight = c, slot, lane, w
+        jac = torch.empty((n, 7, lanes), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.tg_trace_grad_f64(C.byref(cm), n, C.byref(rin), ray_lane, arr, len(seeds),
+                                          L.ptr_array([o.data_ptr() for o in outs]), jac.data_ptr(),
+                                          A.current_stream_ptr(dev)), "tg_trace_grad_f64")
+        for lane, (key, _, _) in enumerate(group):
+            grads[key] = Ray(*(finish(jac[:, r, lane]) for r in range(7)))
+    value = Ray(*(finish(o) for o in outs))
+    return value, grads

@@ -18,6 +18,9 @@ class Source(HasParamsMixin):
     def __call__(self, ray):
         return ray
 
+    def _tg_param_seeds(self, path):
+        return [(0, 1.0)] if tuple(path) == ("z",) else []
+
 
 @dataclass(frozen=True)
 class PointSource(Source):

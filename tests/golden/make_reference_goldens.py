@@ -39,6 +39,12 @@ G["readme_input_grads"] = {
     "d_dx_out_d_x_in": -1.0,
     "d_dy_out_d_x_in": 0.0,
 }
+# README.md:120-137 -- gradients wrt lens parameters (f, z): printed (0.125, 0.09999999)
+G["readme_param_grads"] = {
+    "cite": "README.md:120-137",
+    "ray_in": dict(x=0.1, y=0.2, dx=0.3, dy=0.4, z=0.0, pathlength=0.0),
+    "d_x_out_d_f": 0.125, "d_x_out_d_z": 0.1, "print_rtol": 1e-6,
+}
 # examples/aperture_diffraction.ipynb cell 13 (stored output)
 G["aperture_diffraction_abcd"] = {
     "cite": "examples/aperture_diffraction.ipynb cells 11,13",

@@ -524,3 +524,45 @@ def test_tensor_path_rows_c64_and_full_size(torch_cuda):
     rows = to_np(_field_sum_grid(poly, n, grid, dev, row0=384, nrows=200, method="tensor",
                                  out_dtype=torch_cuda.complex64))
     assert rows.dtype == np.complex64 and rel_l2(rows, ten[384:584]) < 1e-6
+
+
+# ------------------------------------------------------------------------------ parameter tangents
+def test_run_with_grads(torch_cuda, goldens):
+    from temgymcore_b200.ray import RAY_FIELDS, Ray
+    from temgymcore_b200.run import run_with_grads
+    g = goldens["readme_param_grads"]
+    lens, det = M.readme_model()
+    ray_in = Ray(**g["ray_in"])
+    value, grads = run_with_grads(ray_in, [lens, det], [lens.params.focal_length, lens.params.z])
+    assert isinstance(value.x, float) and value.x == 0.275
+    gf, gz = grads[(lens, "focal_length")], grads[(lens, "z")]
+    np.testing.assert_allclose([gf.x, gz.x], [g["d_x_out_d_f"], g["d_x_out_d_z"]], rtol=g["print_rtol"])
+    # rich model, 13 variables (two kernel launches), against the oracle's dual numbers
+    model = M.kitchen_sink_model()
+    rays = M.random_rays(3001, np.random.default_rng(11), scale=0.01, slope=0.01)
+    refs = [model[2].params.focal_length, model[2].params.z, model[4].params.def_x, model[4].params.def_y,
+            model[5].params.angle, model[6].params.z_po, model[6].params.z_pi, model[6].params.focal_length,
+            model[7].params.def_x, model[8].params.scan_pos_x, model[8].params.descan_error.pxo_pyi,
+            model[1].params.scan_tilt_y, rays.params.dx, model[10].params.z, model[7].params.offset]
+    dirs = [(2, ("focal_length",)), (2, ("z",)), (4, ("def_x",)), (4, ("def_y",)), (5, ("angle",)),
+            (6, ("z_po",)), (6, ("z_pi",)), (6, ("focal_length",)), (7, ("def_x",)), (8, ("scan_pos_x",)),
+            (8, ("descan_error", "pxo_pyi")), (1, ("scan_tilt_y",)), ("ray", "dx"), (10, ("z",))]
+    ref_out, J = O.run_with_grads(rays, model, dirs)
+    value, grads = run_with_grads(rays, model, refs)
+    assert len(grads) == len(refs)
+    for f in RAY_FIELDS:
+        close(getattr(value, f), getattr(ref_out, f))
+    for k, r in enumerate(refs[:-1]):
+        gr = grads[r._build()]
+        for i, f in enumerate(RAY_FIELDS):
+            close(getattr(gr, f), J[:, i, k])
+    zero = grads[refs[-1]._build()]          # Biprism.offset does not influence the ray
+    assert all(np.all(np.asarray(getattr(zero, f)) == 0) for f in RAY_FIELDS)
+    # all seven input fields at once + the whole-ray shorthand
+    _, gall = run_with_grads(rays, model, [rays])
+    _, J7 = O.jacobian_run_to_end(rays, model)
+    for j, fin in enumerate(RAY_FIELDS):
+        for i, fout in enumerate(RAY_FIELDS):
+            close(getattr(gall[(rays, fin)], fout), J7[:, i, j])
+    with pytest.raises(RuntimeError):
+        run_with_grads(rays, model, [M.readme_model()[0].params.focal_length])  # not in this model

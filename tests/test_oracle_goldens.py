@@ -210,3 +210,33 @@ def test_input_plane_phase_properties():
     k = 2 * np.pi / wl
     slope = np.angle(img[32, 33] * np.conj(img[32, 32])) / 1e-6
     assert abs(slope - k * tilt) / (k * tilt) < 2e-2
+
+
+def test_readme_param_grads(goldens):
+    # README.md:120-137: jax.jacobian(run_with_params, argnums=(0, 1))(f, z) -> grads.x = (0.125, 0.0999999)
+    g = goldens["readme_param_grads"]
+    _, J = O.run_with_grads(Ray(**g["ray_in"]), M.readme_model(), [(0, ("focal_length",)), (0, ("z",))])
+    np.testing.assert_allclose(J[0, 0, :], [g["d_x_out_d_f"], g["d_x_out_d_z"]], rtol=g["print_rtol"])
+    # cross-check the dual-number gradients against central finite differences on a rich model
+    model = M.kitchen_sink_model()
+    ray = M.random_rays(5, np.random.default_rng(3), scale=0.01, slope=0.01)
+    dirs = [(2, ("focal_length",)), (2, ("z",)), (4, ("def_x",)), (5, ("angle",)), (6, ("z_po",)),
+            (6, ("z_pi",)), (8, ("scan_pos_x",)), (8, ("descan_error", "pxo_pyi")), ("ray", "dx")]
+    _, J = O.run_with_grads(ray, model, dirs)
+    import dataclasses
+    for k, d in enumerate(dirs[:-1]):
+        ci, path = d
+        def shifted(h):
+            c = model[ci]
+            if len(path) == 1:
+                c2 = dataclasses.replace(c, **{path[0]: getattr(c, path[0]) + h})
+            else:
+                inner = getattr(c, path[0])
+                c2 = dataclasses.replace(c, **{path[0]: inner._replace(**{path[1]: getattr(inner, path[1]) + h})})
+            m2 = list(model); m2[ci] = c2
+            return O.run_to_end(ray, m2)
+        h = 1e-6
+        a, b = shifted(h), shifted(-h)
+        for i, f in enumerate(O.RAY_FIELDS):
+            fd = (np.asarray(getattr(a, f), float) - np.asarray(getattr(b, f), float)) / (2 * h)
+            np.testing.assert_allclose(J[:, i, k], np.broadcast_to(fd, (5,)), rtol=2e-5, atol=2e-8)
