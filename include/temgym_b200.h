@@ -130,6 +130,12 @@ int tg_trace_grad_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in
                       const int32_t ray_lane[7], const tg_seed *seeds, int n_seeds,
                       double *const out[7], double *jac, void *stream);
 
+/* transfer_rays (transfer.py:6-54): out[n][k][i] = sum_j T[k][i][j] rays[n][j] for m <= 32
+ * (already cumulative) 5x5 matrices given in HOST memory; rays (n,5), out (n,m,5) device fp64. */
+#define TG_MAX_TRANSFER 32
+int tg_transfer_rays_f64(int64_t n, const double *rays, int m, const double *matrices_host,
+                         double *out, void *stream);
+
 /* ---- K5: metres -> pixels ------------------------------------------------ */
 /* replaces Grid.metres_to_pixels(cast=True) (grid.py:120-153) given the inverse 3x3
  * m2px (row-major, acting on [y_m, x_m, 1], grid.py:50-63).  Evaluation order

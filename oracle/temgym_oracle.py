@@ -885,3 +885,24 @@ def fibonacci_spiral(nb_samples: int, radius: float, alpha=2):
     rr[0] = 0.0
     phi = ii * ga
     return rr * np.cos(phi), rr * np.sin(phi)
+
+
+# --------------------------------------------------------------------------
+# transfer.py
+# --------------------------------------------------------------------------
+
+
+def accumulate_matrices_cumulative(matrices):
+    """transfer.py:150-183 -- starts from the LAST matrix and left-multiplies backwards."""
+    total = matrices[-1]
+    out = [total]
+    for tm in reversed(list(matrices[:-1])):
+        total = tm @ total
+        out.append(total)
+    return np.stack(out, axis=0)
+
+
+def transfer_rays(ray_coords, transfer_matrices):
+    """transfer.py:6-54: einsum("mij,nj->nmi", cumulative, rays)."""
+    cum = accumulate_matrices_cumulative(np.asarray(transfer_matrices, dtype=np.float64))
+    return np.einsum("mij,nj->nmi", cum, np.asarray(ray_coords, dtype=np.float64))

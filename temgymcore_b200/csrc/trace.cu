@@ -665,6 +665,33 @@ __global__ void __launch_bounds__(kTraceThreads)
   }
 }
 
+// ------------------------------------------------------------------ transfer_rays
+// transfer_rays (reference transfer.py:6-54): out[n, m, i] = sum_j T[m, i, j] * rays[n, j] for
+// M <= TG_MAX_TRANSFER cumulative 5x5 matrices held in kernel-parameter constant memory.
+struct TransferMats {
+  int m;
+  double t[TG_MAX_TRANSFER][25];
+};
+__global__ void __launch_bounds__(128)
+    transfer_rays_kernel(const __grid_constant__ TransferMats tm, long long n,
+                         const double *__restrict__ rays, double *__restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) r[j] = rays[i * 5 + j];
+  double *o = out + i * (long long)tm.m * 5;
+  for (int m = 0; m < tm.m; ++m) {
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      double acc = tm.t[m][a * 5] * r[0];
+#pragma unroll
+      for (int j = 1; j < 5; ++j) acc = acc + tm.t[m][a * 5 + j] * r[j];
+      o[m * 5 + a] = acc;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ K5
 __global__ void __launch_bounds__(256)
     m2p_kernel(long long n, const double *__restrict__ x, const double *__restrict__ y,
@@ -779,4 +806,18 @@ extern "C" int tg_trace_grad_f64(const tg_model *model_host, int64_t n, const tg
   else
     trace_grad_kernel<false><<<(unsigned)blocks, kTraceThreads, 0, st>>>(*model_host, gs, *in, (long long)n, o, jac);
   return tg_launch_check("trace_grad_kernel");
+}
+
+extern "C" int tg_transfer_rays_f64(int64_t n, const double *rays, int m, const double *matrices_host,
+                                    double *out, void *stream) {
+  TG_REQUIRE(n >= 0 && m >= 0 && m <= TG_MAX_TRANSFER, "bad sizes (m <= TG_MAX_TRANSFER)");
+  if (n == 0 || m == 0) return TG_OK;
+  TG_REQUIRE(rays && matrices_host && out, "null pointer");
+  TransferMats tm;
+  tm.m = m;
+  for (int k = 0; k < m; ++k)
+    for (int j = 0; j < 25; ++j) tm.t[k][j] = matrices_host[k * 25 + j];
+  const long long blocks = (n + 127) / 128;
+  transfer_rays_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(tm, n, rays, out);
+  return tg_launch_check("transfer_rays_kernel");
 }

@@ -59,6 +59,41 @@ def gaussian_beam(x, y, q_inv, k, offset_x=0, offset_y=0):
     return np.exp(1j * k * ((x + offset_x) ** 2 + (y + offset_y) ** 2) / 2 * q_inv)
 
 
+def decompose_Q_inv(Q_inv, wavelength, eps=1e-12):
+    """``(waist_x, waist_y, r_x, r_y, theta)`` from 2x2 complex ``Q_inv`` (batched), host numpy
+    (gaussian.py:35-89): principal axes from the symmetric imaginary part (``eigh``), right-handed
+    eigenvectors, larger waist first, waists from Im, radii from Re of the rotated diagonal."""
+    Q = np.asarray(_to_np(Q_inv), dtype=np.complex128)
+    Sm = np.imag(Q)
+    Sm = 0.5 * (Sm + np.swapaxes(Sm, -1, -2))
+    _, ev = np.linalg.eigh(Sm)
+
+    def right_handed(e):
+        sgn = np.where(np.linalg.det(e) < 0, -1.0, 1.0)
+        e = e.copy()
+        e[..., :, 1] *= sgn[..., None]
+        return e
+
+    ev = right_handed(ev)
+    Qd = np.swapaxes(ev, -1, -2) @ Q @ ev
+    qd = np.stack([Qd[..., 0, 0], Qd[..., 1, 1]], axis=-1)
+
+    def waists_of(q):
+        im = np.imag(q)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.sqrt(np.where(np.abs(im) > eps, np.abs(wavelength / (np.pi * im)), np.inf))
+
+    swap = waists_of(qd)[..., 0] < waists_of(qd)[..., 1]
+    qd = np.where(swap[..., None], qd[..., ::-1], qd)
+    ev = right_handed(np.where(swap[..., None, None], ev[..., :, ::-1], ev))
+    w = waists_of(qd)
+    re = np.real(qd)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        radii = np.where(np.abs(re) > eps, 1.0 / re, np.inf)
+    theta = np.arctan2(ev[..., 1, 0], ev[..., 0, 0])
+    return w[..., 0], w[..., 1], radii[..., 0], radii[..., 1], theta
+
+
 @dataclass(frozen=True, kw_only=True, eq=False)
 class GaussianRay(Ray):
     """Ray + Gaussian beam parameters (gaussian.py:113-177)."""

@@ -2,9 +2,9 @@
 
 In a model a ``Source`` is a no-op plane at its ``z`` (source.py:21-34): the ray kernel
 only needs that ``z``.  Ray *generation* (``make_rays`` / ``generate_array``,
-source.py:36-188) is host-side numpy input preparation and outside the accelerated path
-(SURVEY.md section 2); ``ParallelBeam`` / ``PointSource`` are provided so reference models
-can be written unchanged.
+source.py:36-188) is host-side numpy input preparation in the reference as well; it is
+provided here (numpy) so reference scripts run unchanged, and its output feeds the CUDA ray
+kernel through ``run_to_end``.
 """
 from dataclasses import dataclass
 from typing import Any
@@ -21,6 +21,22 @@ class Source(HasParamsMixin):
     def _tg_param_seeds(self, path):
         return [(0, 1.0)] if tuple(path) == ("z",) else []
 
+    def generate_array(self, num: int, random: bool = False):
+        """(N, 5) rows ``[x, y, dx, dy, 1]`` (source.py:36-56)."""
+        raise NotImplementedError
+
+    def make_rays(self, num: int, random: bool = False):
+        """``Ray`` with vector ``x, y, dx, dy`` and scalar ``z = self.z``, ``pathlength = 0``
+        (source.py:58-79); a single generated ray gives scalar fields."""
+        from .ray import Ray
+        r = self.generate_array(num, random=random)
+        sl = 0 if r.shape[0] == 1 else slice(None)
+        return Ray(x=r[sl, 0], y=r[sl, 1], dx=r[sl, 2], dy=r[sl, 3], z=self.z, pathlength=0.)
+
+    def _disc(self, num, scale, random):
+        from .utils import concentric_rings, random_coords
+        return random_coords(num) * scale if random else concentric_rings(num, scale)
+
 
 @dataclass(frozen=True)
 class PointSource(Source):
@@ -28,9 +44,27 @@ class PointSource(Source):
     semi_conv: float
     offset_xy: Any = (0.0, 0.0)
 
+    def generate_array(self, num: int, random: bool = False):
+        # all rays leave the offset point; slopes fill the cone of semi-convergence (source.py:107-135)
+        import numpy as np
+        dy, dx = self._disc(num, self.semi_conv, random).T
+        r = np.zeros((dx.size, 5), dtype=np.float64)
+        r[:, 0] += self.offset_xy[0]
+        r[:, 1] += self.offset_xy[1]
+        r[:, 2], r[:, 3], r[:, 4] = dx, dy, 1.0
+        return r
+
 
 @dataclass(frozen=True)
 class ParallelBeam(Source):
     z: float
     radius: float
     offset_xy: Any = (0.0, 0.0)
+
+    def generate_array(self, num: int, random: bool = False):
+        # parallel rays (zero slope) filling the aperture disc (source.py:160-188)
+        import numpy as np
+        y, x = self._disc(num, self.radius, random).T
+        r = np.zeros((x.size, 5), dtype=np.float64)
+        r[:, 0], r[:, 1], r[:, 4] = x + self.offset_xy[0], y + self.offset_xy[1], 1.0
+        return r

@@ -59,3 +59,38 @@ def fibonacci_spiral(nb_samples: int, radius: float, alpha=2):
     rr[0] = 0.
     phi = ii * ga
     return rr * np.cos(phi), rr * np.sin(phi)
+
+
+def concentric_rings(num_points_approx: int, radius: float):
+    """Approximately uniform ``(y, x)`` samples on concentric rings of a disc
+    (utils.py:117-175; host-side input preparation, numpy as in the reference).  Ring k holds
+    ~2*pi*k points; the angles of a ring start at 0 and advance by running sums of 2*pi/n_k,
+    like the reference's ``multi_cumsum_inplace`` (utils.py:46-80)."""
+    import numpy as np
+    n_rings = max(1, int(np.floor((-1 + np.sqrt(1 + 4 * num_points_approx / np.pi)) / 2)))
+    circumference = np.round(2 * np.pi * np.arange(1, n_rings + 1)).astype(int)
+    per_ring = np.round(circumference * (num_points_approx / circumference.sum())).astype(int)
+    radii = np.linspace(0, radius, n_rings + 1, endpoint=True)[1:]
+    reps = per_ring.tolist()
+    all_radii = np.repeat(radii, reps)
+    ang = np.repeat(2 * np.pi / per_ring, reps)
+    # Running angle sums restart from 0 where the reference's multi_cumsum_inplace restarts them:
+    # its partition counter lags by one, so segment k begins k elements after ring k does
+    # (utils.py:69-80).  Reproduced as is: these are the ray directions users get.
+    start, k = 0, 0
+    while start < ang.size:
+        stop = min(ang.size, start + reps[k] + 1)
+        ang[start] = 0.0
+        ang[start:stop] = np.cumsum(ang[start:stop])
+        start, k = stop, min(k + 1, len(reps) - 1)
+    return np.stack((all_radii * np.sin(ang), all_radii * np.cos(ang)), axis=-1)
+
+
+def random_coords(num: int):
+    """Uniform random ``(y, x)`` points in the unit disc, at least one (utils.py:178-205)."""
+    import numpy as np
+    while True:
+        yx = np.random.uniform(-1, 1, size=(max(1, int(num * 1.28)), 2))
+        keep = np.sqrt((yx ** 2).sum(axis=1)) < 1
+        if keep.sum() > 0:
+            return yx[keep, :]

