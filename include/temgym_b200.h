@@ -136,6 +136,23 @@ int tg_trace_grad_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in
 int tg_transfer_rays_f64(int64_t n, const double *rays, int m, const double *matrices_host,
                          double *out, void *stream);
 
+/* ---- fused 4D-STEM shadow-image backprojection (BASELINE config C5) -------- */
+/* One ray per (scan position, detector pixel): detector pixel -> metres (Detector.pixels_to_metres,
+ * grid.py:155-182) -> slopes at the point source -> sample plane (transfer_rays_pt_src,
+ * transfer.py:57-123, with the descan-error 5th column affine in the scan position,
+ * components.py:343-372) -> sample-grid pixel (metres_to_pixels, grid.py:120-153) -> bounds-checked
+ * accumulation (inplace_sum, utils.py:83-114).  shapes = {Sy,Sx,Dy,Dx,Oy,Ox}; geom = 42 doubles:
+ * Ts[6] scan px->m | Td[6] detector px->m | To[6] out grid m->px (rows: y-form then x-form,
+ * value = (a*row + b*col) + c) | cdet[2]=Adet r0 | edet[6]=e0,e1,e2 (x,y each) | Binv[4] |
+ * csamp[2] | Bsamp[4] | esamp[6].  data4d: device (Sy,Sx,Dy,Dx) float32 or uint16; scan positions
+ * [s_begin, s_begin+s_count) are processed (multi-GPU shards); out: device (Oy,Ox) float32,
+ * accumulated into (zero it first). */
+int tg_stem4d_backproject(const int shapes[6], const double geom[42], const void *data4d,
+                          int data_is_f32, int s_begin, int s_count, float *out, void *stream);
+/* the (py, px) int32 pixel pairs of the same rays, idx[(s*Dy*Dx + p)*2 + {0,1}] (parity checks) */
+int tg_stem4d_indices(const int shapes[6], const double geom[42], int s_begin, int s_count,
+                      int32_t *idx, void *stream);
+
 /* ---- K5: metres -> pixels ------------------------------------------------ */
 /* replaces Grid.metres_to_pixels(cast=True) (grid.py:120-153) given the inverse 3x3
  * m2px (row-major, acting on [y_m, x_m, 1], grid.py:50-63).  Evaluation order

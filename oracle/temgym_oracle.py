@@ -906,3 +906,63 @@ def transfer_rays(ray_coords, transfer_matrices):
     """transfer.py:6-54: einsum("mij,nj->nmi", cumulative, rays)."""
     cum = accumulate_matrices_cumulative(np.asarray(transfer_matrices, dtype=np.float64))
     return np.einsum("mij,nj->nmi", cum, np.asarray(ray_coords, dtype=np.float64))
+
+
+# --------------------------------------------------------------------------
+# 4D-STEM shadow-image backprojection, composed from the reference's building blocks
+# (Scanner / Descanner components.py:252-372, Grid maps grid.py:120-182,
+#  transfer_rays_pt_src transfer.py:57-123, inplace_sum utils.py:83-114).
+# The composite itself is not in the reference (SURVEY.md F8): parity is per building block.
+# --------------------------------------------------------------------------
+
+
+def stem4d_pixel_indices(model_fn, scan_grid, detector, source_xy=(0.0, 0.0), out_grid=None):
+    """(Sy*Sx, Dy*Dx, 2) int32 sample-grid (py, px) of every (scan position, detector pixel) ray."""
+    out_grid = scan_grid if out_grid is None else out_grid
+    r0 = np.array([float(source_xy[0]), float(source_xy[1])])
+
+    def mats(spx, spy):
+        model = list(model_fn(spx, spy))
+        idx = next(i for i, c in enumerate(model) if c is scan_grid)
+        ray = Ray(x=r0[0], y=r0[1], dx=0.0, dy=0.0, z=float(component_z(model[0])), pathlength=0.0)
+        return abcd_run_to_end(ray, model)[1][0], abcd_run_to_end(ray, model[:idx + 1])[1][0]
+
+    d00, s00 = mats(0.0, 0.0)
+    d10, s10 = mats(1.0, 0.0)
+    d01, s01 = mats(0.0, 1.0)
+    Adet, Bdet = d00[0:2, 0:2], d00[0:2, 2:4]
+    Asamp, Bsamp = s00[0:2, 0:2], s00[0:2, 2:4]
+    Binv = np.linalg.inv(Bdet)
+    cdet, csamp = Adet @ r0, Asamp @ r0
+    Sy, Sx = scan_grid.shape
+    Dy, Dx = detector.shape
+    sy, sx = np.meshgrid(np.arange(Sy), np.arange(Sx), indexing="ij")
+    spy, spx = apply_transformation(sy.ravel(), sx.ravel(), grid_pixels_to_metres_mat(scan_grid))
+    dy, dx = np.meshgrid(np.arange(Dy), np.arange(Dx), indexing="ij")
+    yd, xd = apply_transformation(dy.ravel(), dx.ravel(), grid_pixels_to_metres_mat(detector))
+    spx, spy = spx[:, None], spy[:, None]
+    edx = (d00[0, 4] + spx * (d10[0, 4] - d00[0, 4])) + spy * (d01[0, 4] - d00[0, 4])
+    edy = (d00[1, 4] + spx * (d10[1, 4] - d00[1, 4])) + spy * (d01[1, 4] - d00[1, 4])
+    esx = (s00[0, 4] + spx * (s10[0, 4] - s00[0, 4])) + spy * (s01[0, 4] - s00[0, 4])
+    esy = (s00[1, 4] + spx * (s10[1, 4] - s00[1, 4])) + spy * (s01[1, 4] - s00[1, 4])
+    rx = (xd[None, :] - cdet[0]) - edx
+    ry = (yd[None, :] - cdet[1]) - edy
+    tx = Binv[0, 0] * rx + Binv[0, 1] * ry
+    ty = Binv[1, 0] * rx + Binv[1, 1] * ry
+    xs = (csamp[0] + (Bsamp[0, 0] * tx + Bsamp[0, 1] * ty)) + esx
+    ys = (csamp[1] + (Bsamp[1, 0] * tx + Bsamp[1, 1] * ty)) + esy
+    py, px = apply_transformation(ys, xs, grid_metres_to_pixels_mat(out_grid))
+    return np.stack([round_to_int32(py), round_to_int32(px)], axis=-1)
+
+
+def stem4d_backproject(data4d, model_fn, scan_grid, detector, source_xy=(0.0, 0.0), out_grid=None):
+    """Shadow-image backprojection: out[py, px] += data (bounds-checked, utils.py:83-114)."""
+    out_grid = scan_grid if out_grid is None else out_grid
+    idx = stem4d_pixel_indices(model_fn, scan_grid, detector, source_xy, out_grid)
+    Oy, Ox = out_grid.shape
+    py, px = idx[..., 0].ravel(), idx[..., 1].ravel()
+    vals = np.asarray(data4d, dtype=np.float64).ravel()
+    ok = (py >= 0) & (py < Oy) & (px >= 0) & (px < Ox)
+    out = np.zeros((Oy, Ox))
+    np.add.at(out, (py[ok], px[ok]), vals[ok])
+    return out

@@ -63,6 +63,8 @@ SIGNATURES = {
     "tg_trace_grad_f64": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(tg_ray_in), C.POINTER(C.c_int32),
                                  C.POINTER(tg_seed), _i32, C.POINTER(_vp), _vp, _vp]),
     "tg_transfer_rays_f64": (_i32, [_i64, _vp, _i32, _dp, _vp, _vp]),
+    "tg_stem4d_backproject": (_i32, [C.POINTER(C.c_int), _dp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "tg_stem4d_indices": (_i32, [C.POINTER(C.c_int), _dp, _i32, _i32, _vp, _vp]),
     "tg_metres_to_pixels": (_i32, [_i64, _vp, _vp, _dp, _vp, _vp, _i32, _vp]),
     "tg_metres_to_pixels_host": (_i32, [_i64, _vp, _vp, _dp, _vp, _vp, _i32, _i32]),
     "tg_into_image_i64": (_i32, [_i64, _vp, _vp, _i32, _i32, _vp, _vp]),

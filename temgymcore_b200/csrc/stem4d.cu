@@ -1,0 +1,173 @@
+// Fused 4D-STEM shadow-image backprojection (BASELINE config C5).
+//
+// Every (scan position s, detector pixel p) pair is one ray.  The reference ships the building
+// blocks only (Scanner / Descanner / DescanError components.py:27-115, 252-372; ScanGrid /
+// Detector pixel<->metre maps grid.py:120-182; transfer_rays_pt_src transfer.py:57-123;
+// inplace_sum utils.py:83-114) -- the composite workflow lives in a private downstream repo
+// (SURVEY.md F8).  This kernel fuses them:
+//   (spx, spy) = ScanGrid.pixels_to_metres(sy, sx)                      scan position [m]
+//   (xd, yd)   = Detector.pixels_to_metres(dy, dx)                      detector pixel centre [m]
+//   theta      = Bdet^-1 ((xd, yd) - Adet r0 - edet(s))                 slopes at the point source
+//   (xs, ys)   = Asamp r0 + Bsamp theta + esamp(s)                      transfer_rays_pt_src to the sample plane
+//   (py, px)   = OutGrid.metres_to_pixels(xs, ys), round half to even   sample-plane pixel
+//   out[py, px] += data[sy, sx, dy, dx]                                 inplace_sum (bounds-checked)
+// where the 5th ABCD column (descan error!) is affine in the scan position:
+//   e(s) = e0 + spx e1 + spy e2   (Scanner / Descanner add offsets linear in scan_pos times _one).
+// All coordinate arithmetic is fp64 with a fixed operation order and no FMA contraction
+// (-fmad=false), so pixel indices are bit-reproducible against the numpy oracle.
+//
+// Mapping: one CTA per scan position streams that position's detector frame (coalesced fp32 /
+// uint loads, 4 B per ray: the kernel is HBM-read-bound on the 4D dataset) and accumulates into a
+// 64 x 64 shared-memory tile centred on the frame's footprint on the sample plane (a frame lands
+// on a few hundred sample pixels: privatisation turns 65 536 contended global atomics per frame
+// into a few hundred); rays falling outside the tile go straight to global atomics.
+#include <math.h>
+#include "tg_common.cuh"
+
+namespace {
+
+constexpr int kTile = 64;
+constexpr int kThreads4d = 256;
+
+struct Stem4dGeom {
+  int Sy, Sx, Dy, Dx, Oy, Ox;
+  double Ts[6];      // scan px->m : y = Ts0*sy + Ts1*sx + Ts2 ; x = Ts3*sy + Ts4*sx + Ts5
+  double Td[6];      // detector px->m, same layout
+  double To[6];      // output grid m->px : py = To0*y + To1*x + To2 ; px = To3*y + To4*x + To5
+  double cdet[2];    // Adet r0          (x, y)
+  double edet[6];    // e0x e0y e1x e1y e2x e2y
+  double Binv[4];    // Bdet^-1 row-major
+  double csamp[2];   // Asamp r0
+  double Bs[4];      // Bsamp row-major
+  double esamp[6];
+};
+
+__device__ __forceinline__ void ray_to_pixel(const Stem4dGeom &g, double spx, double spy, double edx, double edy,
+                                             double esx, double esy, int dy, int dx, int &py, int &px) {
+  const double fy = (double)dy, fx = (double)dx;
+  const double yd = (g.Td[0] * fy + g.Td[1] * fx) + g.Td[2];
+  const double xd = (g.Td[3] * fy + g.Td[4] * fx) + g.Td[5];
+  const double rx = (xd - g.cdet[0]) - edx;
+  const double ry = (yd - g.cdet[1]) - edy;
+  const double tx = g.Binv[0] * rx + g.Binv[1] * ry;
+  const double ty = g.Binv[2] * rx + g.Binv[3] * ry;
+  const double xs = (g.csamp[0] + (g.Bs[0] * tx + g.Bs[1] * ty)) + esx;
+  const double ys = (g.csamp[1] + (g.Bs[2] * tx + g.Bs[3] * ty)) + esy;
+  const double fpy = (g.To[0] * ys + g.To[1] * xs) + g.To[2];
+  const double fpx = (g.To[3] * ys + g.To[4] * xs) + g.To[5];
+  py = isnan(fpy) ? 0 : __double2int_rn(fpy);
+  px = isnan(fpx) ? 0 : __double2int_rn(fpx);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads4d)
+    stem4d_backproject_kernel(const __grid_constant__ Stem4dGeom g, const T *__restrict__ data,
+                              float *__restrict__ out, int s_begin) {
+  __shared__ float tile[kTile * kTile];
+  const int s = s_begin + blockIdx.x;
+  const int sy = s / g.Sx, sx = s % g.Sx;
+  for (int k = threadIdx.x; k < kTile * kTile; k += kThreads4d) tile[k] = 0.f;
+  // per-scan-position quantities (every thread computes the same values)
+  const double fsy = (double)sy, fsx = (double)sx;
+  const double spy = (g.Ts[0] * fsy + g.Ts[1] * fsx) + g.Ts[2];
+  const double spx = (g.Ts[3] * fsy + g.Ts[4] * fsx) + g.Ts[5];
+  const double edx = (g.edet[0] + spx * g.edet[2]) + spy * g.edet[4];
+  const double edy = (g.edet[1] + spx * g.edet[3]) + spy * g.edet[5];
+  const double esx = (g.esamp[0] + spx * g.esamp[2]) + spy * g.esamp[4];
+  const double esy = (g.esamp[1] + spx * g.esamp[3]) + spy * g.esamp[5];
+  int cy, cx;  // footprint centre = image of the central detector pixel
+  ray_to_pixel(g, spx, spy, edx, edy, esx, esy, g.Dy / 2, g.Dx / 2, cy, cx);
+  const int ty0 = cy - kTile / 2, tx0 = cx - kTile / 2;
+  __syncthreads();
+
+  const long long npix = (long long)g.Dy * g.Dx;
+  const T *frame = data + (long long)s * npix;
+  for (long long p = threadIdx.x; p < npix; p += kThreads4d) {
+    const float v = (float)frame[p];
+    const int dy = (int)(p / g.Dx), dx = (int)(p % g.Dx);
+    int py, px;
+    ray_to_pixel(g, spx, spy, edx, edy, esx, esy, dy, dx, py, px);
+    if (py < 0 || py >= g.Oy || px < 0 || px >= g.Ox) continue;  // inplace_sum bounds check
+    const int ly = py - ty0, lx = px - tx0;
+    if (ly >= 0 && ly < kTile && lx >= 0 && lx < kTile)
+      atomicAdd(&tile[ly * kTile + lx], v);
+    else
+      atomicAdd(&out[(long long)py * g.Ox + px], v);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < kTile * kTile; k += kThreads4d) {
+    const float v = tile[k];
+    if (v != 0.f) {
+      const int py = ty0 + k / kTile, px = tx0 + k % kTile;
+      if (py >= 0 && py < g.Oy && px >= 0 && px < g.Ox) atomicAdd(&out[(long long)py * g.Ox + px], v);
+    }
+  }
+}
+
+// pixel indices only (parity / debugging): idx[(s*npix + p)*2 + {0,1}] = (py, px)
+__global__ void __launch_bounds__(kThreads4d)
+    stem4d_indices_kernel(const __grid_constant__ Stem4dGeom g, int32_t *__restrict__ idx, int s_begin) {
+  const int s = s_begin + blockIdx.x;
+  const int sy = s / g.Sx, sx = s % g.Sx;
+  const double fsy = (double)sy, fsx = (double)sx;
+  const double spy = (g.Ts[0] * fsy + g.Ts[1] * fsx) + g.Ts[2];
+  const double spx = (g.Ts[3] * fsy + g.Ts[4] * fsx) + g.Ts[5];
+  const double edx = (g.edet[0] + spx * g.edet[2]) + spy * g.edet[4];
+  const double edy = (g.edet[1] + spx * g.edet[3]) + spy * g.edet[5];
+  const double esx = (g.esamp[0] + spx * g.esamp[2]) + spy * g.esamp[4];
+  const double esy = (g.esamp[1] + spx * g.esamp[3]) + spy * g.esamp[5];
+  const long long npix = (long long)g.Dy * g.Dx;
+  for (long long p = threadIdx.x; p < npix; p += kThreads4d) {
+    int py, px;
+    ray_to_pixel(g, spx, spy, edx, edy, esx, esy, (int)(p / g.Dx), (int)(p % g.Dx), py, px);
+    idx[((long long)s * npix + p) * 2 + 0] = py;
+    idx[((long long)s * npix + p) * 2 + 1] = px;
+  }
+}
+
+int fill_geom(Stem4dGeom &g, const int shapes[6], const double *geom44) {
+  g.Sy = shapes[0]; g.Sx = shapes[1]; g.Dy = shapes[2]; g.Dx = shapes[3]; g.Oy = shapes[4]; g.Ox = shapes[5];
+  TG_REQUIRE(g.Sy > 0 && g.Sx > 0 && g.Dy > 0 && g.Dx > 0 && g.Oy > 0 && g.Ox > 0, "bad shapes");
+  const double *p = geom44;
+  for (int i = 0; i < 6; ++i) g.Ts[i] = *p++;
+  for (int i = 0; i < 6; ++i) g.Td[i] = *p++;
+  for (int i = 0; i < 6; ++i) g.To[i] = *p++;
+  for (int i = 0; i < 2; ++i) g.cdet[i] = *p++;
+  for (int i = 0; i < 6; ++i) g.edet[i] = *p++;
+  for (int i = 0; i < 4; ++i) g.Binv[i] = *p++;
+  for (int i = 0; i < 2; ++i) g.csamp[i] = *p++;
+  for (int i = 0; i < 4; ++i) g.Bs[i] = *p++;
+  for (int i = 0; i < 6; ++i) g.esamp[i] = *p++;
+  return TG_OK;
+}
+
+}  // namespace
+
+extern "C" int tg_stem4d_backproject(const int shapes[6], const double geom[42], const void *data4d,
+                                     int data_is_f32, int s_begin, int s_count, float *out, void *stream) {
+  TG_REQUIRE(shapes && geom && data4d && out, "null pointer");
+  Stem4dGeom g;
+  int rc = fill_geom(g, shapes, geom);
+  if (rc != TG_OK) return rc;
+  TG_REQUIRE(s_begin >= 0 && s_count >= 0 && (long long)s_begin + s_count <= (long long)g.Sy * g.Sx, "bad scan range");
+  if (s_count == 0) return TG_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (data_is_f32)
+    stem4d_backproject_kernel<float><<<(unsigned)s_count, kThreads4d, 0, st>>>(g, static_cast<const float *>(data4d), out, s_begin);
+  else
+    stem4d_backproject_kernel<unsigned short><<<(unsigned)s_count, kThreads4d, 0, st>>>(
+        g, static_cast<const unsigned short *>(data4d), out, s_begin);
+  return tg_launch_check("stem4d_backproject_kernel");
+}
+
+extern "C" int tg_stem4d_indices(const int shapes[6], const double geom[42], int s_begin, int s_count,
+                                 int32_t *idx, void *stream) {
+  TG_REQUIRE(shapes && geom && idx, "null pointer");
+  Stem4dGeom g;
+  int rc = fill_geom(g, shapes, geom);
+  if (rc != TG_OK) return rc;
+  TG_REQUIRE(s_begin >= 0 && s_count >= 0 && (long long)s_begin + s_count <= (long long)g.Sy * g.Sx, "bad scan range");
+  if (s_count == 0) return TG_OK;
+  stem4d_indices_kernel<<<(unsigned)s_count, kThreads4d, 0, static_cast<cudaStream_t>(stream)>>>(g, idx, s_begin);
+  return tg_launch_check("stem4d_indices_kernel");
+}

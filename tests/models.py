@@ -157,3 +157,18 @@ def biprism_case(nb, shape, fov=1024 * 55e-6 / 2, general=False, rng=None):
         model[-1] = Detector(z=det.z, pixel_size=det.pixel_size, shape=det.shape, rotation=17.0)
     g = gaussian_rays(x, y, z=model[0].z, wavelength=wavelength, w0=w0, amplitude=amp, **kw)
     return g, model
+
+
+def stem4d_case(scan_shape=(16, 12), det_shape=(24, 20), rng=None, z_src=-1e-5):
+    """BASELINE config C5 geometry at a reduced size: point source just above
+    the sample (ScanGrid) plane, Scanner, Descanner with a random DescanError, Detector."""
+    rng = rng or np.random.default_rng(SEED)
+    scan_grid = ScanGrid(z=0.0, pixel_size=(1e-9, 1e-9), shape=scan_shape, rotation=13.0)
+    detector = Detector(z=0.5, pixel_size=(55e-6, 55e-6), shape=det_shape, flip_y=True)
+    err = DescanError(*rng.uniform(-1e-3, 1e-3, 12))
+    src = PointSource(z=z_src, semi_conv=1e-2)
+
+    def model_fn(spx, spy):
+        return [src, scan_grid, Scanner(z=0.0, scan_pos_x=spx, scan_pos_y=spy),
+                Descanner(z=0.1, scan_pos_x=spx, scan_pos_y=spy, descan_error=err), detector]
+    return model_fn, scan_grid, detector

@@ -616,3 +616,34 @@ def test_decompose_q_inv_round_trip(torch_cuda):
                          wavelength=wl, theta=oth).to_vector()
         img2 = evaluate_gaussian_input_image(g2, det)
         np.testing.assert_allclose(np.abs(img2), np.abs(img), rtol=2e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------ C5: 4D-STEM
+def test_stem4d_backprojection(torch_cuda):
+    from temgymcore_b200.stem4d import backproject_4dstem, backproject_indices, system_geometry
+    model_fn, scan_grid, detector = M.stem4d_case()
+    ref_idx = O.stem4d_pixel_indices(model_fn, scan_grid, detector)
+    got_idx = backproject_indices(model_fn, scan_grid, detector)
+    assert got_idx.shape == ref_idx.shape == (16 * 12, 24 * 20, 2)
+    np.testing.assert_array_equal(got_idx, ref_idx)               # pixel indexing is bit-exact
+    inside = ((ref_idx[..., 0] >= 0) & (ref_idx[..., 0] < 16) & (ref_idx[..., 1] >= 0) & (ref_idx[..., 1] < 12))
+    assert 0.05 < inside.mean() < 1.0                              # rays fall both on and off the sample grid
+    rng = np.random.default_rng(2)
+    data = rng.integers(0, 50, size=(16, 12, 24, 20)).astype(np.float32)   # integer counts: sums are exact
+    ref = O.stem4d_backproject(data, model_fn, scan_grid, detector)
+    got = backproject_4dstem(data, model_fn, scan_grid, detector)
+    assert got.dtype == np.float32 and got.shape == (16, 12)
+    np.testing.assert_array_equal(got.astype(np.float64), ref)
+    got16 = backproject_4dstem(data.astype(np.uint16), model_fn, scan_grid, detector)
+    np.testing.assert_array_equal(got16, got)
+    # scan-position shards accumulate to the same image (the multi-GPU partition)
+    geo = system_geometry(model_fn, scan_grid, detector)
+    img = torch_cuda.zeros((16, 12), dtype=torch_cuda.float32, device="cuda")
+    flat = torch_cuda.as_tensor(data, device="cuda").reshape(16 * 12, -1)
+    for b, c in ((0, 50), (50, 1), (51, 141)):
+        backproject_4dstem(flat[b:b + c].contiguous(), None, scan_grid, detector, scan_range=(b, c), out=img, geometry=geo)
+    np.testing.assert_array_equal(img.cpu().numpy(), got)
+    # total accumulated intensity equals the in-bounds intensity
+    assert got.sum() == data.reshape(16 * 12, -1)[inside].sum()
+    with pytest.raises(ValueError):
+        system_geometry(lambda a, b: model_fn(a * (1 + b), b), scan_grid, detector)   # not affine in scan position
