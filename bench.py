@@ -31,6 +31,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 C2_NB, C2_SHAPE = 10_000, (1024, 1024)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures
+# summarised under profiles/ (round 1, same workloads as timed here)
+NCU_TRAFFIC = {
+    "gemm_tf32x3_kernel": (491.98e6 + 4.20e6, "profiles/r1_gemm_tf32x3_kernel_v1.md"),
+    "field_grid_kernel": (1.00e6 + 81.65e6, "profiles/r1_field_grid_kernel_v1.md"),
+    "trace_kernel_1e7": (560.0e6 + 2499.5e6, "profiles/r1_trace_kernel_1e7.md"),
+    "stem4d_backproject": (17.18e9, "profiles/r1_stem4d_backproject_kernel.md"),
+}
 MUFU_PER_EVAL = 3          # sin, cos, ex2
 MUFU_PER_CLK_SM = 16
 RAY_BYTES_ABCD = 312       # 56 in + 56 out + 200 ABCD, fp64
@@ -295,7 +303,9 @@ def run_ours(args):
     mufu_rate = k_evals * MUFU_PER_EVAL / (k_ms * 1e-3)
     roofline_sfu = {"bound": "sfu", "kernel": "field_grid_kernel<16,8> (+prep, split reduce)",
                     "achieved": mufu_rate / 1e9, "peak": peak_mufu / 1e9, "unit": "GMUFU/s",
-                    "frac": mufu_rate / peak_mufu, "traffic": None, "evals_per_s": k_evals / (k_ms * 1e-3),
+                    "frac": mufu_rate / peak_mufu, "traffic": NCU_TRAFFIC["field_grid_kernel"][0],
+                    "traffic_source": NCU_TRAFFIC["field_grid_kernel"][1],
+                    "evals_per_s": k_evals / (k_ms * 1e-3),
                     "kernel_ms": k_ms,
                     "peak_basis": f"{sms} SMs x 16 MUFU/clk x {pk['sm_max_mhz']:.0f} MHz (clocks.max.sm, "
                                   f"{pk['source']}); 3 MUFU per beamlet*pixel"}
@@ -331,7 +341,9 @@ def run_ours(args):
             bf16 = 1590.0
         roofline_tensor = {"bound": "tensor", "kernel": "gemm_tf32x3_kernel (tcgen05.mma kind::tf32)",
                            "achieved": alg_tf, "peak": bf16, "unit": "TFLOP/s", "frac": alg_tf / bf16,
-                           "traffic": None, "kernel_ms": g_ms, "executed_tf32_tflops": exe_tf,
+                           "traffic": NCU_TRAFFIC["gemm_tf32x3_kernel"][0],
+                           "traffic_source": NCU_TRAFFIC["gemm_tf32x3_kernel"][1],
+                           "kernel_ms": g_ms, "executed_tf32_tflops": exe_tf,
                            "tf32_peak_assumed": bf16 / 2, "frac_executed_vs_tf32_peak": exe_tf / (bf16 / 2),
                            "note": "achieved = algorithmic 8 real flop per beamlet*pixel; the kernel executes 3x "
                                    "that in TF32 (hi/lo operand split needed for the 1e-5 parity); peak = "
@@ -375,7 +387,9 @@ def run_ours(args):
         rays_section[label] = {
             "rays_per_s": rate, "ms_per_launch": r_ms, "rays_per_gpu": per, "scaling": "weak",
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": gbs / pk["hbm_gbs"], "traffic": None,
+                         "frac": gbs / pk["hbm_gbs"],
+                         "traffic": NCU_TRAFFIC["trace_kernel_1e7"][0] if per == 10_000_000 else None,
+                         "traffic_source": NCU_TRAFFIC["trace_kernel_1e7"][1] if per == 10_000_000 else None,
                          "bytes_per_ray": RAY_BYTES_ABCD, "peak_source": pk["source"]}}
         del rd, keep
         torch.cuda.empty_cache()
@@ -387,6 +401,36 @@ def run_ours(args):
     rays_section["e2e_c1_1e6"] = {"rays_per_s": 1_000_000 * world / (re_ms * 1e-3), "ms_per_call": re_ms,
                                   "h2d_bytes_per_step": 56_000_000, "d2h_bytes_per_step": 256_000_000,
                                   "api": "tg_trace_f64_host (run_to_end_abcd with host buffers)"}
+
+    # ---- C5: fused 4D-STEM shadow-image backprojection, 256x256 scan x 256x256 detector rays;
+    # scan positions sharded over the ranks (no communication on the data path), one all-reduce of
+    # the 256x256 image at the end
+    from temgymcore_b200.stem4d import backproject_4dstem, system_geometry
+    model_fn5, scan5, det5 = M.stem4d_case((256, 256), (256, 256), z_src=-1e-6)
+    geo5 = system_geometry(model_fn5, scan5, det5)
+    nscan = 256 * 256
+    sb, se = D.shard_range(nscan, rank, world)
+    data5 = torch.rand((se - sb, 256, 256), device=dev, dtype=torch.float32)
+    img5 = torch.zeros((256, 256), dtype=torch.float32, device=dev)
+
+    def step5():
+        img5.zero_()
+        backproject_4dstem(data5, None, scan5, det5, scan_range=(sb, se - sb), out=img5, geometry=geo5)
+        if world > 1:
+            dist.all_reduce(img5)
+    t5 = timed(step5, max(3, args.steps // 2), 2, flush=False)
+    ms5 = max_over_ranks(float(np.mean(t5)))
+    gbs5 = (se - sb) * 65536 * 4 / (ms5 * 1e-3) / 1e9
+    stem4d = {"workload": "C5: 256x256 scan x 256x256 detector rays with descan error, float32 4D dataset "
+                          "(17.2 GB), shadow image on the 256x256 sample grid",
+              "rays_per_s": nscan * 65536 / (ms5 * 1e-3), "ms_per_pass": ms5, "scaling": "strong",
+              "roofline": {"bound": "hbm", "achieved": gbs5, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                           "frac": gbs5 / pk["hbm_gbs"],
+                           "traffic": NCU_TRAFFIC["stem4d_backproject"][0] / world,
+                           "traffic_source": NCU_TRAFFIC["stem4d_backproject"][1], "bytes_per_ray": 4,
+                           "kernel": "stem4d_backproject_kernel<float>"}}
+    del data5
+    torch.cuda.empty_cache()
 
     # ---- CPU baseline (rank 0, N = 1): the numpy oracle port on a bounded sample
     cpu = None
@@ -415,7 +459,7 @@ def run_ours(args):
                        "phase": "fp64 setup -> 32-bit fixed-point turns; fp32 MUFU sin/cos/ex2; fp64 "
                                 "accumulation across 128-beamlet chunks"},
             "roofline": roofline, "roofline_sfu_path": roofline_sfu, "e2e": e2e, "gpu_launches": n_launch,
-            "rays": rays_section, "clocks": clocks,
+            "rays": rays_section, "stem4d": stem4d, "clocks": clocks,
         }
         if cpu:
             line["cpu_baseline"] = cpu

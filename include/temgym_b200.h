@@ -144,7 +144,10 @@ int tg_transfer_rays_f64(int64_t n, const double *rays, int m, const double *mat
  * accumulation (inplace_sum, utils.py:83-114).  shapes = {Sy,Sx,Dy,Dx,Oy,Ox}; geom = 42 doubles:
  * Ts[6] scan px->m | Td[6] detector px->m | To[6] out grid m->px (rows: y-form then x-form,
  * value = (a*row + b*col) + c) | cdet[2]=Adet r0 | edet[6]=e0,e1,e2 (x,y each) | Binv[4] |
- * csamp[2] | Bsamp[4] | esamp[6].  data4d: device (Sy,Sx,Dy,Dx) float32 or uint16; scan positions
+ * csamp[2] | Bsamp[4] | esamp[6].  data4d: device (Sy,Sx,Dy,Dx) float32 (data_is_f32 bit 0 set) or
+ * uint16; bit 1 of data_is_f32 forces the plain step-wise kernel (the default fast kernel evaluates
+ * the per-frame affine map with FMAs and re-evaluates step-wise near rounding ties, giving
+ * identical pixel indices); scan positions
  * [s_begin, s_begin+s_count) are processed (multi-GPU shards); out: device (Oy,Ox) float32,
  * accumulated into (zero it first). */
 int tg_stem4d_backproject(const int shapes[6], const double geom[42], const void *data4d,

@@ -104,6 +104,140 @@ __global__ void __launch_bounds__(kThreads4d)
   }
 }
 
+// ---- fast path -------------------------------------------------------------------------
+// The map (dy, dx) -> (fpy, fpx) is affine for a fixed scan position.  The fast kernel evaluates
+// it with two FMAs per coordinate from per-CTA coefficients; whenever the result lies within a
+// small tolerance of a half-integer (a rounding tie, or the edge of the grid) the ray is
+// re-evaluated with the step-wise arithmetic above, so the pixel index is ALWAYS the step-wise
+// one (bit-exact parity) while ~all rays cost 4 FMAs instead of ~37 fp64 operations.
+// Each thread owns 8 consecutive detector pixels of a row (two 16-byte loads) and merges runs of
+// equal target pixels in registers before touching the shared-memory tile.
+struct AffineYX {
+  double by, bx;      // value at (dy, dx) = (0, 0)
+  double ry, rx;      // per detector row
+  double cy, cx;      // per detector column
+};
+
+// round-half-even of f via the 1.5*2^52 mantissa trick (3 DADD): the integer is the low word of
+// f + magic.  `flag` is raised when f is within 1e-6 of a half-integer (composite-vs-step-wise
+// discrepancy is < 1e-7 for |f| < 2^20) or is NaN; |f| >= 2^20 is reported as far out of bounds
+// (both evaluations agree there: grids are limited to 2^20 pixels per side).
+__device__ __forceinline__ int round_guarded(double f, bool &flag, bool &far) {
+  const double kMagic = 6755399441055744.0;
+  const double t = f + kMagic;
+  const double frac = f - (t - kMagic);
+  flag |= !(fabs(frac) <= 0.5 - 1e-6);
+  far |= !(fabs(f) < 1048576.0);
+  return __double2loint(t);
+}
+
+template <typename T>
+__device__ __forceinline__ void load8(const T *p, float v[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float *p, float v[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4 *>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<unsigned short>(const unsigned short *p, float v[8]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p));
+  v[0] = (float)(a.x & 0xffffu); v[1] = (float)(a.x >> 16); v[2] = (float)(a.y & 0xffffu); v[3] = (float)(a.y >> 16);
+  v[4] = (float)(a.z & 0xffffu); v[5] = (float)(a.z >> 16); v[6] = (float)(a.w & 0xffffu); v[7] = (float)(a.w >> 16);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads4d)
+    stem4d_backproject_fast_kernel(const __grid_constant__ Stem4dGeom g, const T *__restrict__ data,
+                                   float *__restrict__ out, int s_begin) {
+  __shared__ float tile[kTile * kTile];
+  const int s = s_begin + blockIdx.x;
+  const int sy = s / g.Sx, sx = s % g.Sx;
+  for (int k = threadIdx.x; k < kTile * kTile; k += kThreads4d) tile[k] = 0.f;
+  const double fsy = (double)sy, fsx = (double)sx;
+  const double spy = (g.Ts[0] * fsy + g.Ts[1] * fsx) + g.Ts[2];
+  const double spx = (g.Ts[3] * fsy + g.Ts[4] * fsx) + g.Ts[5];
+  const double edx = (g.edet[0] + spx * g.edet[2]) + spy * g.edet[4];
+  const double edy = (g.edet[1] + spx * g.edet[3]) + spy * g.edet[5];
+  const double esx = (g.esamp[0] + spx * g.esamp[2]) + spy * g.esamp[4];
+  const double esy = (g.esamp[1] + spx * g.esamp[3]) + spy * g.esamp[5];
+  // composite affine coefficients (same for every thread of the CTA)
+  AffineYX a;
+  {
+    // constant term: the step-wise chain at (dy, dx) = (0, 0), kept in floating point
+    const double yd = g.Td[2], xd = g.Td[5];
+    const double rx = (xd - g.cdet[0]) - edx, ry = (yd - g.cdet[1]) - edy;
+    const double tx = g.Binv[0] * rx + g.Binv[1] * ry, ty = g.Binv[2] * rx + g.Binv[3] * ry;
+    const double xs = (g.csamp[0] + (g.Bs[0] * tx + g.Bs[1] * ty)) + esx;
+    const double ys = (g.csamp[1] + (g.Bs[2] * tx + g.Bs[3] * ty)) + esy;
+    a.by = (g.To[0] * ys + g.To[1] * xs) + g.To[2];
+    a.bx = (g.To[3] * ys + g.To[4] * xs) + g.To[5];
+    // slopes: d(out px)/d(det row) and /d(det col) through Td -> Binv -> Bs -> To
+    auto slope = [&](double dyd, double dxd, double &oy, double &ox) {
+      const double ttx = g.Binv[0] * dxd + g.Binv[1] * dyd, tty = g.Binv[2] * dxd + g.Binv[3] * dyd;
+      const double dxs = g.Bs[0] * ttx + g.Bs[1] * tty, dys = g.Bs[2] * ttx + g.Bs[3] * tty;
+      oy = g.To[0] * dys + g.To[1] * dxs;
+      ox = g.To[3] * dys + g.To[4] * dxs;
+    };
+    slope(g.Td[0], g.Td[3], a.ry, a.rx);
+    slope(g.Td[1], g.Td[4], a.cy, a.cx);
+  }
+  int cy, cx;
+  ray_to_pixel(g, spx, spy, edx, edy, esx, esy, g.Dy / 2, g.Dx / 2, cy, cx);
+  const int ty0 = cy - kTile / 2, tx0 = cx - kTile / 2;
+  __syncthreads();
+
+  const int groups_per_row = g.Dx >> 3;
+  const int ngroups = g.Dy * groups_per_row;
+  const T *frame = data + (long long)s * g.Dy * g.Dx;
+  for (int grp = threadIdx.x; grp < ngroups; grp += kThreads4d) {
+    const int dy = grp / groups_per_row, dx0 = (grp - dy * groups_per_row) << 3;
+    float v[8];
+    load8<T>(frame + (long long)dy * g.Dx + dx0, v);
+    const double fx0 = (double)dx0;
+    const double y0v = fma(fx0, a.cy, fma((double)dy, a.ry, a.by));
+    const double x0v = fma(fx0, a.cx, fma((double)dy, a.rx, a.bx));
+    int cur = -2;        // shared-tile slot with a pending partial sum (-2: none)
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      bool tie = false, far = false;
+      int py = round_guarded(fma((double)j, a.cy, y0v), tie, far);
+      int px = round_guarded(fma((double)j, a.cx, x0v), tie, far);
+      if (far) {
+        if (!(fma((double)j, a.cy, y0v) == fma((double)j, a.cy, y0v)) ||
+            !(fma((double)j, a.cx, x0v) == fma((double)j, a.cx, x0v)))
+          tie = true;          // NaN geometry: let the step-wise path decide (it maps NaN to pixel 0)
+        else
+          continue;            // far outside every admissible grid
+      }
+      if (tie) ray_to_pixel(g, spx, spy, edx, edy, esx, esy, dy, dx0 + j, py, px);  // exact step-wise path
+      if ((unsigned)py >= (unsigned)g.Oy || (unsigned)px >= (unsigned)g.Ox) continue;  // inplace_sum bounds
+      const int ly = py - ty0, lx = px - tx0;
+      if ((unsigned)ly < (unsigned)kTile && (unsigned)lx < (unsigned)kTile) {
+        const int key = ly * kTile + lx;
+        if (key != cur) {
+          if (cur >= 0) atomicAdd(&tile[cur], sum);
+          cur = key;
+          sum = 0.f;
+        }
+        sum += v[j];
+      } else {
+        atomicAdd(&out[(long long)py * g.Ox + px], v[j]);
+      }
+    }
+    if (cur >= 0) atomicAdd(&tile[cur], sum);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < kTile * kTile; k += kThreads4d) {
+    const float t = tile[k];
+    if (t != 0.f) {
+      const int py = ty0 + k / kTile, px = tx0 + k % kTile;
+      if (py >= 0 && py < g.Oy && px >= 0 && px < g.Ox) atomicAdd(&out[(long long)py * g.Ox + px], t);
+    }
+  }
+}
+
 // pixel indices only (parity / debugging): idx[(s*npix + p)*2 + {0,1}] = (py, px)
 __global__ void __launch_bounds__(kThreads4d)
     stem4d_indices_kernel(const __grid_constant__ Stem4dGeom g, int32_t *__restrict__ idx, int s_begin) {
@@ -128,6 +262,7 @@ __global__ void __launch_bounds__(kThreads4d)
 int fill_geom(Stem4dGeom &g, const int shapes[6], const double *geom44) {
   g.Sy = shapes[0]; g.Sx = shapes[1]; g.Dy = shapes[2]; g.Dx = shapes[3]; g.Oy = shapes[4]; g.Ox = shapes[5];
   TG_REQUIRE(g.Sy > 0 && g.Sx > 0 && g.Dy > 0 && g.Dx > 0 && g.Oy > 0 && g.Ox > 0, "bad shapes");
+  TG_REQUIRE(g.Oy <= (1 << 20) && g.Ox <= (1 << 20), "output grid larger than 2^20 pixels per side");
   const double *p = geom44;
   for (int i = 0; i < 6; ++i) g.Ts[i] = *p++;
   for (int i = 0; i < 6; ++i) g.Td[i] = *p++;
@@ -152,6 +287,21 @@ extern "C" int tg_stem4d_backproject(const int shapes[6], const double geom[42],
   TG_REQUIRE(s_begin >= 0 && s_count >= 0 && (long long)s_begin + s_count <= (long long)g.Sy * g.Sx, "bad scan range");
   if (s_count == 0) return TG_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool force_stepwise = (data_is_f32 & 2) != 0;
+  data_is_f32 &= 1;
+  const size_t esz = data_is_f32 ? 4 : 2;
+  const bool fast = !force_stepwise && (g.Dx % 8) == 0 && ((reinterpret_cast<uintptr_t>(data4d) +
+                                         (size_t)s_begin * g.Dy * g.Dx * esz) % 16) == 0 &&
+                    (((size_t)g.Dy * g.Dx * esz) % 16) == 0;
+  if (fast) {
+    if (data_is_f32)
+      stem4d_backproject_fast_kernel<float><<<(unsigned)s_count, kThreads4d, 0, st>>>(
+          g, static_cast<const float *>(data4d), out, s_begin);
+    else
+      stem4d_backproject_fast_kernel<unsigned short><<<(unsigned)s_count, kThreads4d, 0, st>>>(
+          g, static_cast<const unsigned short *>(data4d), out, s_begin);
+    return tg_launch_check("stem4d_backproject_fast_kernel");
+  }
   if (data_is_f32)
     stem4d_backproject_kernel<float><<<(unsigned)s_count, kThreads4d, 0, st>>>(g, static_cast<const float *>(data4d), out, s_begin);
   else

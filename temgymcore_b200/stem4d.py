@@ -79,7 +79,7 @@ def system_geometry(model_fn, scan_grid, detector, source_xy=(0.0, 0.0), out_gri
 
 
 def backproject_4dstem(data4d, model_fn, scan_grid, detector, *, source_xy=(0.0, 0.0), out_grid=None,
-                       scan_range=None, out=None, geometry=None):
+                       scan_range=None, out=None, geometry=None, stepwise_only=False):
     """Sum every detector pixel of every scan position onto the sample grid -> ``(Oy, Ox)`` float32.
 
     data4d: ``(Sy, Sx, Dy, Dx)`` float32 or uint16 (numpy / torch; stays on the GPU if it is
@@ -111,7 +111,8 @@ def backproject_4dstem(data4d, model_fn, scan_grid, detector, *, source_xy=(0.0,
     ptr = base.data_ptr() - begin * shapes[2] * shapes[3] * base.element_size()
     with torch.cuda.device(dev):
         L.check(lib.tg_stem4d_backproject((C.c_int * 6)(*shapes), L.dbl_array(geom), ptr,
-                                          int(d.dtype == torch.float32), begin, count, img.data_ptr(),
+                                          int(d.dtype == torch.float32) | (2 if stepwise_only else 0), begin,
+                                          count, img.data_ptr(),
                                           A.current_stream_ptr(dev)), "tg_stem4d_backproject")
     if out is not None or kind == A.KIND_CUDA:
         return img

@@ -647,3 +647,12 @@ def test_stem4d_backprojection(torch_cuda):
     assert got.sum() == data.reshape(16 * 12, -1)[inside].sum()
     with pytest.raises(ValueError):
         system_geometry(lambda a, b: model_fn(a * (1 + b), b), scan_grid, detector)   # not affine in scan position
+    # fast kernel (guarded affine map, 8-pixel vector loads, run merging) == step-wise kernel == oracle
+    model_fn, scan_grid, detector = M.stem4d_case((48, 40), (72, 64), z_src=-2e-6)
+    data = rng.integers(0, 20, size=(48, 40, 72, 64)).astype(np.float32)
+    fast = backproject_4dstem(data, model_fn, scan_grid, detector)
+    slow = backproject_4dstem(data, model_fn, scan_grid, detector, stepwise_only=True)
+    np.testing.assert_array_equal(fast, slow)
+    np.testing.assert_array_equal(fast.astype(np.float64), O.stem4d_backproject(data, model_fn, scan_grid, detector))
+    assert fast.sum() > 0
+    np.testing.assert_array_equal(backproject_4dstem(data.astype(np.uint16), model_fn, scan_grid, detector), fast)

@@ -32,3 +32,12 @@ if what in ("trace_c4", "all"):
     for _ in range(3):
         o = run_to_end_abcd(rd, M.six_component_column())
     torch.cuda.synchronize()
+if what in ("stem4d", "all"):
+    from temgymcore_b200.stem4d import backproject_4dstem, system_geometry
+    fn, sg, det = M.stem4d_case((256, 256), (256, 256), z_src=-1e-6)
+    geo = system_geometry(fn, sg, det)
+    data = torch.rand((65536, 256, 256), device=dev, dtype=torch.float32)
+    img = torch.zeros((256, 256), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        backproject_4dstem(data, None, sg, det, scan_range=(0, 65536), out=img, geometry=geo)
+    torch.cuda.synchronize()
