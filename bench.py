@@ -370,7 +370,7 @@ def run_ours(args):
 
     # ---- ray half of the path: rays/s with the 5x5 ABCD, sharded, no communication
     rays_section = {}
-    for label, n_rays in (("c1_1e6", 1_000_000), ("steady_1e7", 10_000_000)):
+    for label, n_rays in (("c1_1e6", 1_000_000), ("steady_1e7", 10_000_000), ("steady_1e8", 100_000_000)):
         per = n_rays  # weak: every rank traces its own n_rays (C1 shape per GPU)
         rng = np.random.default_rng(M.SEED + rank)
         rr = M.random_rays(per, rng)

@@ -341,14 +341,45 @@ struct TraceOut {
   double *ptr[7];
 };
 
+// Kernel-parameter model descriptors.  Components other than the Krivanek lens use at most four
+// parameters, so models without one travel as a compact 1.2 KB block (the full tg_model is
+// 9.6 KB; a large parameter block measurably slows block launch in this HBM-bound kernel).
+struct CompLite {
+  int32_t op, flags;
+  double z;
+  double p[4];
+};
+struct ModelLite {
+  int32_t n_comp, reserved;
+  CompLite comp[TG_MAX_COMPS];
+};
+template <bool KRIV>
+struct ModelFor {
+  using type = ModelLite;
+};
+template <>
+struct ModelFor<true> {
+  using type = tg_model;
+};
+inline void to_lite(const tg_model &m, ModelLite &l) {
+  l.n_comp = m.n_comp;
+  l.reserved = 0;
+  for (int c = 0; c < m.n_comp; ++c) {
+    l.comp[c].op = m.comp[c].op;
+    l.comp[c].flags = m.comp[c].flags;
+    l.comp[c].z = m.comp[c].z;
+    for (int k = 0; k < 4; ++k) l.comp[c].p[k] = m.comp[c].p[k];
+  }
+}
+
 // NC = number of tangent columns (0 none, 5 = [x,y,dx,dy,_one], 7 = all Ray leaves).
 // In the 5-column mode z and pathlength carry no tangents: d z_out / d {x,y,dx,dy,_one}
 // is identically zero for every component on the path (z only ever receives component
 // constants), and pathlength never feeds back into x,y,dx,dy.
 template <int NC, bool KRIV>
-__global__ void __launch_bounds__(kTraceThreads, (KRIV && NC == 5) ? 3 : 1)
-    trace_kernel(const __grid_constant__ tg_model model, const tg_ray_in in, const long long n,
-                 const TraceOut out, double *__restrict__ jac) {
+__global__ void __launch_bounds__(kTraceThreads, KRIV ? (NC == 5 ? 3 : 1) : (NC == 7 ? 3 : 6))
+    trace_kernel(const __grid_constant__ typename ModelFor<KRIV>::type model, const tg_ray_in in,
+                 const long long n, const TraceOut out, double *__restrict__ jac) {
   constexpr bool FULL = (NC == 7);
   constexpr int NZ = FULL ? 7 : 0;  // tangent width of z and pathlength
   constexpr int ROWS = (NC == 7) ? 7 : 5;
@@ -373,7 +404,7 @@ __global__ void __launch_bounds__(kTraceThreads, (KRIV && NC == 5) ? 3 : 1)
 
     const int nc = model.n_comp;
     for (int c = 0; c < nc; ++c) {
-      const tg_comp &cm = model.comp[c];
+      const auto &cm = model.comp[c];
       if (!(cm.flags & TG_F_NOPROP)) {
         // distance = component.z - ray.z (run.py:77); FreeSpaceParaxial (propagator.py:67-72)
         const Dual<NZ> d = (cm.flags & TG_F_DIST) ? dconst<NZ>(cm.z) : cm.z - z;
@@ -531,7 +562,13 @@ int launch_trace_k(const tg_model *m, int64_t n, const tg_ray_in *in, double *co
   }
   const long long blocks = (n + kTraceThreads - 1) / kTraceThreads;
   TG_REQUIRE(blocks <= 0x7fffffffLL, "too many rays for one launch");
-  trace_kernel<NC, KRIV><<<(unsigned)blocks, kTraceThreads, smem, st>>>(*m, *in, (long long)n, o, jac);
+  if constexpr (KRIV) {
+    trace_kernel<NC, true><<<(unsigned)blocks, kTraceThreads, smem, st>>>(*m, *in, (long long)n, o, jac);
+  } else {
+    ModelLite lite;
+    to_lite(*m, lite);
+    trace_kernel<NC, false><<<(unsigned)blocks, kTraceThreads, smem, st>>>(lite, *in, (long long)n, o, jac);
+  }
   return tg_launch_check("trace_kernel");
 }
 
