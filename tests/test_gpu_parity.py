@@ -656,3 +656,19 @@ def test_stem4d_backprojection(torch_cuda):
     np.testing.assert_array_equal(fast.astype(np.float64), O.stem4d_backproject(data, model_fn, scan_grid, detector))
     assert fast.sum() > 0
     np.testing.assert_array_equal(backproject_4dstem(data.astype(np.uint16), model_fn, scan_grid, detector), fast)
+
+
+def test_gaussian_image_plan_cuda_graph(torch_cuda):
+    from dataclasses import fields, replace
+    from temgymcore_b200.gaussian import GaussianImagePlan, make_gaussian_image
+    for name in ("c2_aperture", "c3_biprism_general"):     # tensor-core path and SFU path
+        g, model = field_cases()[name]
+        gd = replace(g, **{f.name: torch_cuda.as_tensor(getattr(g, f.name), device="cuda") for f in fields(g)})
+        plan = GaussianImagePlan(gd, model, cull_bits=0)
+        ref = O.make_gaussian_image(g, model)
+        assert rel_l2(to_np(plan.run()), ref) < FIELD_TOL
+        # new beamlet parameters, same shapes: update + replay
+        g2 = replace(g, x=g.x * 0.5, amplitude=g.amplitude * 2.0)
+        out2 = to_np(plan.update(g2).run()).copy()
+        assert rel_l2(out2, O.make_gaussian_image(g2, model)) < FIELD_TOL
+        np.testing.assert_array_equal(out2, make_gaussian_image(g2, model, cull_bits=0))
