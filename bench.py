@@ -376,30 +376,52 @@ def run_ours(args):
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
            "api": "tg_make_gaussian_image_host (make_gaussian_image with host buffers)"}
 
-    # ---- ray half of the path: rays/s with the 5x5 ABCD, sharded, no communication
+    # ---- ray half of the path: rays/s with the 5x5 ABCD, sharded, no communication.
+    # Timed as RayTracePlan replays (model compiled once, static buffers, one graph node): the
+    # events then bracket the kernel, not the Python/ctypes call overhead (~0.1 ms, reported
+    # separately as ms_per_call_direct for the plain run_to_end_abcd call).
+    from temgymcore_b200.run import RayTracePlan
     rays_section = {}
-    for label, n_rays in (("c1_1e6", 1_000_000), ("steady_1e7", 10_000_000), ("steady_1e8", 100_000_000)):
-        per = n_rays  # weak: every rank traces its own n_rays (C1 shape per GPU)
+    ray_cases = (("c1_1e6", 1_000_000, "c1"), ("steady_1e7", 10_000_000, "c1"),
+                 ("steady_1e8", 100_000_000, "c1"), ("c4_krivanek_1e7", 10_000_000, "c4"))
+    for label, n_rays, which in ray_cases:
+        per = n_rays  # weak: every rank traces its own n_rays
         rng = np.random.default_rng(M.SEED + rank)
-        rr = M.random_rays(per, rng)
+        if which == "c1":
+            rr = M.random_rays(per, rng)
+            rmodel = M.readme_model()
+            wl = "C1 README Lens(f=1, z=0.5) + Detector(128x128)"
+        else:   # C4: 6-component column with the Krivanek-aberrated lens, rays on a 0.2 nm disc
+            rr = M.random_rays(per, rng, scale=0.2e-9, slope=1e-9)
+            rmodel = M.six_component_column()
+            wl = "C4 aberrated_probe 6-component column (AberratedLensKrivanek, Deflector, Lens, Biprism)"
         rd = Ray(*(torch.as_tensor(getattr(rr, f), device=dev) for f in RAY_FIELDS))
-        rmodel = M.readme_model()
-        keep = {}
-
-        def ray_step():
-            keep["o"] = run_to_end_abcd(rd, rmodel)
-        rt = timed(ray_step, args.steps, args.warmup, flush=(per * RAY_BYTES_ABCD < (200 << 20)))
+        del rr
+        rplan = RayTracePlan(rd, rmodel)
+        rt = timed(rplan.run, args.steps, args.warmup, flush=(per * RAY_BYTES_ABCD < (200 << 20)))
         r_ms = max_over_ranks(float(np.sum(rt))) / args.steps
+        direct = None
+        if per <= 10_000_000:
+            keep = {}
+
+            def ray_step():
+                keep["o"] = run_to_end_abcd(rd, rmodel)
+            dt = timed(ray_step, args.steps, args.warmup, flush=(per * RAY_BYTES_ABCD < (200 << 20)))
+            direct = max_over_ranks(float(np.sum(dt))) / args.steps
+            del keep
         rate = per * world / (r_ms * 1e-3)
         gbs = per * RAY_BYTES_ABCD / (r_ms * 1e-3) / 1e9
+        tkey = {"steady_1e7": "trace_kernel_1e7", "c4_krivanek_1e7": "trace_kernel_c4"}.get(label)
         rays_section[label] = {
-            "rays_per_s": rate, "ms_per_launch": r_ms, "rays_per_gpu": per, "scaling": "weak",
+            "workload": wl, "rays_per_s": rate, "ms_per_launch": r_ms, "ms_per_call_direct": direct,
+            "rays_per_gpu": per, "scaling": "weak", "launch": "RayTracePlan (CUDA graph replay)",
+            "l2": "flushed between launches" if per * RAY_BYTES_ABCD < (200 << 20) else "working set >> L2",
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": gbs / pk["hbm_gbs"],
-                         "traffic": NCU_TRAFFIC["trace_kernel_1e7"][0] if per == 10_000_000 else None,
-                         "traffic_source": NCU_TRAFFIC["trace_kernel_1e7"][1] if per == 10_000_000 else None,
+                         "traffic": NCU_TRAFFIC[tkey][0] if tkey in NCU_TRAFFIC else None,
+                         "traffic_source": NCU_TRAFFIC[tkey][1] if tkey in NCU_TRAFFIC else None,
                          "bytes_per_ray": RAY_BYTES_ABCD, "peak_source": pk["source"]}}
-        del rd, keep
+        del rd, rplan
         torch.cuda.empty_cache()
     # ray e2e through the host C ABI (pinned numpy in/out), 1e6 rays per rank
     rr = M.random_rays(1_000_000, np.random.default_rng(M.SEED + rank))
@@ -428,6 +450,12 @@ def run_ours(args):
             dist.all_reduce(img5)
     t5 = timed(step5, max(3, args.steps // 2), 2, flush=False)
     ms5 = max_over_ranks(float(np.mean(t5)))
+
+    def step5_affine():
+        img5.zero_()
+        backproject_4dstem(data5, None, scan5, det5, scan_range=(sb, se - sb), out=img5, geometry=geo5,
+                           kernel="affine")
+    ms5_affine = max_over_ranks(float(np.mean(timed(step5_affine, 3, 1, flush=False))))
     gbs5 = (se - sb) * 65536 * 4 / (ms5 * 1e-3) / 1e9
     stem4d = {"workload": "C5: 256x256 scan x 256x256 detector rays with descan error, float32 4D dataset "
                           "(17.2 GB), shadow image on the 256x256 sample grid",
@@ -436,7 +464,8 @@ def run_ours(args):
                            "frac": gbs5 / pk["hbm_gbs"],
                            "traffic": NCU_TRAFFIC["stem4d_backproject"][0] / world,
                            "traffic_source": NCU_TRAFFIC["stem4d_backproject"][1], "bytes_per_ray": 4,
-                           "kernel": "stem4d_backproject_kernel<float>"}}
+                           "kernel": "stem4d_backproject_dda_kernel<float> (integer fixed-point stepping)"},
+              "ms_per_pass_guarded_fp64_affine_kernel": ms5_affine}
     del data5
     torch.cuda.empty_cache()
 

@@ -238,6 +238,171 @@ __global__ void __launch_bounds__(kThreads4d)
   }
 }
 
+// ---- integer DDA path ---------------------------------------------------------------------
+// When a frame's footprint fits inside the 64 x 64 tile (checked on the host from the slopes, which
+// do not depend on the scan position) the per-ray work is integer only.  Tile-local coordinates
+// u = f - tile_origin + 0.5 + g are carried in fixed point: a 64-bit accumulator with 40 fractional
+// bits walks the thread's strips (exact integer stepping down the frame), the 8 rays of a strip use
+// 32-bit values with 24 fractional bits (F' = F0 + j*C).  floor(u) is the rounded pixel unless u is
+// within the guard g = 2^-19 px of a rounding tie; total fixed-point + composite-vs-step-wise error is
+// < 10 * 2^-24 px << g, so a strip with any ray inside the guard window -- or any coordinate outside
+// [0, 64) -- is redone with the step-wise fp64 chain (ray_to_pixel) and indices ALWAYS equal the
+// step-wise definition.  Per ray: 2 IADD, 4 ops of guard (LOP, LOP, MIN, SETP.OR), 3 ops of key,
+// compare + FADD for the run merge -- no fp64 in the steady state.  Rays outside the output grid land
+// in tile cells that the flush discards (the reference's inplace_sum bounds check).
+constexpr int kFrac = 24;                     // fractional bits of the per-strip 32-bit coordinates
+constexpr int kQFrac = 40;                    // fractional bits of the 64-bit strip accumulators
+constexpr int kGuardLog = 19;                 // guard g = 2^-19 px; window [0, 2g) on F' = F + g
+constexpr unsigned kFracMask = (1u << kFrac) - 1u;
+constexpr unsigned kWindow = 1u << (kFrac - kGuardLog + 1);
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads4d, 4)
+    stem4d_backproject_dda_kernel(const __grid_constant__ Stem4dGeom g, const T *__restrict__ data,
+                                  float *__restrict__ out, int s_begin) {
+  __shared__ float tile[kTile * kTile];
+  const int s = s_begin + blockIdx.x;
+  const int sy = s / g.Sx, sx = s % g.Sx;
+  for (int k = threadIdx.x; k < kTile * kTile; k += kThreads4d) tile[k] = 0.f;
+  const double fsy = (double)sy, fsx = (double)sx;
+  const double spy = (g.Ts[0] * fsy + g.Ts[1] * fsx) + g.Ts[2];
+  const double spx = (g.Ts[3] * fsy + g.Ts[4] * fsx) + g.Ts[5];
+  const double edx = (g.edet[0] + spx * g.edet[2]) + spy * g.edet[4];
+  const double edy = (g.edet[1] + spx * g.edet[3]) + spy * g.edet[5];
+  const double esx = (g.esamp[0] + spx * g.esamp[2]) + spy * g.esamp[4];
+  const double esy = (g.esamp[1] + spx * g.esamp[3]) + spy * g.esamp[5];
+  int cy, cx;
+  ray_to_pixel(g, spx, spy, edx, edy, esx, esy, g.Dy / 2, g.Dx / 2, cy, cx);
+  const int ty0 = cy - kTile / 2, tx0 = cx - kTile / 2;
+
+  const int gpr = g.Dx >> 3;                   // strips (groups of 8 pixels) per detector row
+  const int ngroups = g.Dy * gpr;
+  // 64-bit fixed-point strip origin for this thread's first strip, and its strides
+  long long qy, qx, stepy, stepx, wrapy, wrapx;
+  int cy32, cx32;
+  int dy = threadIdx.x / gpr, cg = threadIdx.x - dy * gpr;
+  const int drow = kThreads4d / gpr, dcol = kThreads4d - drow * gpr;
+  {
+    const double yd = g.Td[2], xd = g.Td[5];
+    const double rx = (xd - g.cdet[0]) - edx, ry = (yd - g.cdet[1]) - edy;
+    const double tx = g.Binv[0] * rx + g.Binv[1] * ry, ty = g.Binv[2] * rx + g.Binv[3] * ry;
+    const double xs = (g.csamp[0] + (g.Bs[0] * tx + g.Bs[1] * ty)) + esx;
+    const double ys = (g.csamp[1] + (g.Bs[2] * tx + g.Bs[3] * ty)) + esy;
+    const double by = (g.To[0] * ys + g.To[1] * xs) + g.To[2];
+    const double bx = (g.To[3] * ys + g.To[4] * xs) + g.To[5];
+    double ry_, rx_, cy_, cx_;
+    auto slope = [&](double dyd, double dxd, double &oy, double &ox) {
+      const double ttx = g.Binv[0] * dxd + g.Binv[1] * dyd, tty = g.Binv[2] * dxd + g.Binv[3] * dyd;
+      const double dxs = g.Bs[0] * ttx + g.Bs[1] * tty, dys = g.Bs[2] * ttx + g.Bs[3] * tty;
+      oy = g.To[0] * dys + g.To[1] * dxs;
+      ox = g.To[3] * dys + g.To[4] * dxs;
+    };
+    slope(g.Td[0], g.Td[3], ry_, rx_);
+    slope(g.Td[1], g.Td[4], cy_, cx_);
+    const double kS = 1099511627776.0;         // 2^40
+    const double off = 0.5 + 1.0 / (double)(1 << kGuardLog);
+    const long long By = __double2ll_rn(((by - (double)ty0) + off) * kS);
+    const long long Bx = __double2ll_rn(((bx - (double)tx0) + off) * kS);
+    const long long Ry = __double2ll_rn(ry_ * kS), Rx = __double2ll_rn(rx_ * kS);
+    const long long Cy = __double2ll_rn(cy_ * kS), Cx = __double2ll_rn(cx_ * kS);
+    qy = By + (long long)dy * Ry + (long long)(cg * 8) * Cy;
+    qx = Bx + (long long)dy * Rx + (long long)(cg * 8) * Cx;
+    stepy = (long long)drow * Ry + (long long)(dcol * 8) * Cy;
+    stepx = (long long)drow * Rx + (long long)(dcol * 8) * Cx;
+    wrapy = Ry - (long long)(gpr * 8) * Cy;
+    wrapx = Rx - (long long)(gpr * 8) * Cx;
+    cy32 = (int)((Cy + (1ll << (kQFrac - kFrac - 1))) >> (kQFrac - kFrac));
+    cx32 = (int)((Cx + (1ll << (kQFrac - kFrac - 1))) >> (kQFrac - kFrac));
+  }
+  __syncthreads();
+
+  // one strip of 8 rays: fixed-point keys + guard, run merge into the tile; then advance to this
+  // thread's next strip (exact integer stepping)
+  auto strip = [&](const float (&v)[8]) {
+    const int fy0 = (int)(qy >> (kQFrac - kFrac)), fx0 = (int)(qx >> (kQFrac - kFrac));
+    int key[8];
+    unsigned near = 0xffffffffu, range = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int fy = fy0 + j * cy32, fx = fx0 + j * cx32;
+      near = min(near, min((unsigned)fy & kFracMask, (unsigned)fx & kFracMask));
+      if (j == 0 || j == 7) range |= (unsigned)fy | (unsigned)fx;
+      key[j] = ((fy >> kFrac) << 6) + (fx >> kFrac);
+    }
+    if (near >= kWindow && (range >> (kFrac + 6)) == 0u) {
+      int cur = key[0];
+      float sum = v[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) {
+        if (key[j] != cur) {
+          if (sum != 0.f) atomicAdd(&tile[cur], sum);
+          cur = key[j];
+          sum = v[j];
+        } else {
+          sum += v[j];
+        }
+      }
+      if (sum != 0.f) atomicAdd(&tile[cur], sum);
+    } else {                                   // a tie / out-of-tile strip: exact step-wise chain
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {
+        float vj = v[0];                        // register select (no dynamic indexing -> no stack)
+#pragma unroll
+        for (int t = 1; t < 8; ++t) vj = (j == t) ? v[t] : vj;
+        int py, px;
+        ray_to_pixel(g, spx, spy, edx, edy, esx, esy, dy, cg * 8 + j, py, px);
+        if ((unsigned)py >= (unsigned)g.Oy || (unsigned)px >= (unsigned)g.Ox) continue;
+        const int ly = py - ty0, lx = px - tx0;
+        if ((unsigned)ly < (unsigned)kTile && (unsigned)lx < (unsigned)kTile)
+          atomicAdd(&tile[ly * kTile + lx], vj);
+        else
+          atomicAdd(&out[(long long)py * g.Ox + px], vj);
+      }
+    }
+    dy += drow; cg += dcol; qy += stepy; qx += stepx;
+    if (cg >= gpr) { cg -= gpr; ++dy; qy += wrapy; qx += wrapx; }
+  };
+
+  const T *frame = data + (long long)s * g.Dy * g.Dx;
+  float va[8], vb[8];                          // ping-pong: the next strip's loads are always in flight
+  int grp = threadIdx.x;
+  if (grp < ngroups) load8<T>(frame + (long long)grp * 8, va);
+  while (grp < ngroups) {
+    if (grp + kThreads4d < ngroups) load8<T>(frame + (long long)(grp + kThreads4d) * 8, vb);
+    strip(va);
+    grp += kThreads4d;
+    if (grp >= ngroups) break;
+    if (grp + kThreads4d < ngroups) load8<T>(frame + (long long)(grp + kThreads4d) * 8, va);
+    strip(vb);
+    grp += kThreads4d;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < kTile * kTile; k += kThreads4d) {
+    const float t = tile[k];
+    if (t != 0.f) {
+      const int py = ty0 + k / kTile, px = tx0 + k % kTile;
+      if (py >= 0 && py < g.Oy && px >= 0 && px < g.Ox) atomicAdd(&out[(long long)py * g.Ox + px], t);
+    }
+  }
+}
+
+// host-side dispatch test: does every frame's footprint stay inside the tile?  (The linear part of
+// the detector-pixel -> sample-pixel map does not depend on the scan position.)
+bool footprint_fits_tile(const Stem4dGeom &g) {
+  auto slope = [&](double dyd, double dxd, double &oy, double &ox) {
+    const double ttx = g.Binv[0] * dxd + g.Binv[1] * dyd, tty = g.Binv[2] * dxd + g.Binv[3] * dyd;
+    const double dxs = g.Bs[0] * ttx + g.Bs[1] * tty, dys = g.Bs[2] * ttx + g.Bs[3] * tty;
+    oy = g.To[0] * dys + g.To[1] * dxs;
+    ox = g.To[3] * dys + g.To[4] * dxs;
+  };
+  double ry, rx, cy, cx;
+  slope(g.Td[0], g.Td[3], ry, rx);
+  slope(g.Td[1], g.Td[4], cy, cx);
+  const double hy = 0.5 * g.Dy + 1.0, hx = 0.5 * g.Dx + 1.0;
+  const double ey = fabs(ry) * hy + fabs(cy) * hx, ex = fabs(rx) * hy + fabs(cx) * hx;
+  return ey <= kTile / 2 - 3 && ex <= kTile / 2 - 3;   // false for NaN
+}
+
 // pixel indices only (parity / debugging): idx[(s*npix + p)*2 + {0,1}] = (py, px)
 __global__ void __launch_bounds__(kThreads4d)
     stem4d_indices_kernel(const __grid_constant__ Stem4dGeom g, int32_t *__restrict__ idx, int s_begin) {
@@ -288,11 +453,21 @@ extern "C" int tg_stem4d_backproject(const int shapes[6], const double geom[42],
   if (s_count == 0) return TG_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool force_stepwise = (data_is_f32 & 2) != 0;
+  const bool no_dda = (data_is_f32 & 4) != 0;      // A/B switch: guarded fp64 affine kernel instead of the DDA
   data_is_f32 &= 1;
   const size_t esz = data_is_f32 ? 4 : 2;
   const bool fast = !force_stepwise && (g.Dx % 8) == 0 && ((reinterpret_cast<uintptr_t>(data4d) +
                                          (size_t)s_begin * g.Dy * g.Dx * esz) % 16) == 0 &&
                     (((size_t)g.Dy * g.Dx * esz) % 16) == 0;
+  if (fast && !no_dda && footprint_fits_tile(g)) {
+    if (data_is_f32)
+      stem4d_backproject_dda_kernel<float><<<(unsigned)s_count, kThreads4d, 0, st>>>(
+          g, static_cast<const float *>(data4d), out, s_begin);
+    else
+      stem4d_backproject_dda_kernel<unsigned short><<<(unsigned)s_count, kThreads4d, 0, st>>>(
+          g, static_cast<const unsigned short *>(data4d), out, s_begin);
+    return tg_launch_check("stem4d_backproject_dda_kernel");
+  }
   if (fast) {
     if (data_is_f32)
       stem4d_backproject_fast_kernel<float><<<(unsigned)s_count, kThreads4d, 0, st>>>(

@@ -256,6 +256,53 @@ def run_to_end_abcd(ray, components: Sequence[Any],
     return _trace(ray, compile_model(components), L.TG_JAC_ABCD5, want_rays=want_rays)
 
 
+class RayTracePlan:
+    """``run_to_end`` (+ ABCD) for a fixed model and ray count, captured once in a CUDA graph.
+
+    A C1-sized launch (1e6 rays) is a ~55 us kernel; building the descriptor, allocating the
+    results and crossing ctypes costs the host more than that per call.  The plan compiles the
+    model once, owns static input / output buffers and replays one graph node per ``run()``:
+    ``update(ray)`` copies new rays (same count) in, ``run()`` returns ``(Ray, abcd)`` views of
+    the static outputs (``abcd`` is None when ``jacobian`` is False).  The model is baked in.
+    """
+
+    def __init__(self, ray, components: Sequence[Any], *, jacobian: bool = True, device=None):
+        import torch
+        vals = [getattr(ray, f) for f in RAY_FIELDS]
+        dev = A.cuda_device_of(vals) or torch.device("cuda", A.current_device_index()
+                                                     if device is None else device)
+        self.device = dev
+        self._layout = L.TG_JAC_ABCD5 if jacobian else L.TG_JAC_NONE
+        self._model = compile_model(components)
+        self._static = Ray(*(v if A.kind_of(v) == A.KIND_SCALAR else A.to_device_f64(v, dev).clone()
+                             for v in vals))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm-up outside the capture
+            _trace(self._static, self._model, self._layout)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._out = _trace(self._static, self._model, self._layout)
+
+    def update(self, ray):
+        for f in RAY_FIELDS:
+            dst, src = getattr(self._static, f), getattr(ray, f)
+            if A.kind_of(dst) == A.KIND_SCALAR:
+                if A.to_float(src) != dst:
+                    raise ValueError(f"scalar ray field {f!r} is baked into the plan")
+                continue
+            dst.copy_(A.to_device_f64(src, self.device), non_blocking=True)
+        return self
+
+    def run(self):
+        self._graph.replay()
+        return self._out
+
+    __call__ = run
+
+
 def ray_jacobian(ray, components: Sequence[Any], propagator: BasePropagator = FreeSpaceParaxial()):
     """``jax.jacobian(run_to_end)(ray, model)`` (README.md:227-234): the full Ray-of-Ray
     Jacobian as a :class:`~temgymcore_b200.utils.RayJacobian` (attribute access

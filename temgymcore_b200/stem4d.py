@@ -79,13 +79,19 @@ def system_geometry(model_fn, scan_grid, detector, source_xy=(0.0, 0.0), out_gri
 
 
 def backproject_4dstem(data4d, model_fn, scan_grid, detector, *, source_xy=(0.0, 0.0), out_grid=None,
-                       scan_range=None, out=None, geometry=None, stepwise_only=False):
+                       scan_range=None, out=None, geometry=None, stepwise_only=False, kernel="auto"):
     """Sum every detector pixel of every scan position onto the sample grid -> ``(Oy, Ox)`` float32.
 
     data4d: ``(Sy, Sx, Dy, Dx)`` float32 or uint16 (numpy / torch; stays on the GPU if it is
     there).  ``scan_range=(begin, count)`` restricts to a shard of flattened scan positions;
-    ``out`` accumulates into an existing CUDA image.
+    ``out`` accumulates into an existing CUDA image.  ``kernel`` selects the implementation for
+    A/B checks: "auto" (integer DDA kernel when a frame's footprint fits the 64 x 64 shared-memory
+    tile, else the guarded fp64 affine kernel, else the step-wise kernel), "affine" (never the DDA
+    kernel) or "stepwise" (= ``stepwise_only``).  All three give identical pixel indices.
     """
+    if kernel not in ("auto", "affine", "stepwise"):
+        raise ValueError(f"unknown kernel {kernel!r}")
+    mode_bits = 2 if (stepwise_only or kernel == "stepwise") else (4 if kernel == "affine" else 0)
     import torch
     lib = L.load()
     shapes, geom = geometry if geometry is not None else system_geometry(model_fn, scan_grid, detector, source_xy,
@@ -111,7 +117,7 @@ def backproject_4dstem(data4d, model_fn, scan_grid, detector, *, source_xy=(0.0,
     ptr = base.data_ptr() - begin * shapes[2] * shapes[3] * base.element_size()
     with torch.cuda.device(dev):
         L.check(lib.tg_stem4d_backproject((C.c_int * 6)(*shapes), L.dbl_array(geom), ptr,
-                                          int(d.dtype == torch.float32) | (2 if stepwise_only else 0), begin,
+                                          int(d.dtype == torch.float32) | mode_bits, begin,
                                           count, img.data_ptr(),
                                           A.current_stream_ptr(dev)), "tg_stem4d_backproject")
     if out is not None or kind == A.KIND_CUDA:

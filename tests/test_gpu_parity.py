@@ -656,6 +656,51 @@ def test_stem4d_backprojection(torch_cuda):
     np.testing.assert_array_equal(fast.astype(np.float64), O.stem4d_backproject(data, model_fn, scan_grid, detector))
     assert fast.sum() > 0
     np.testing.assert_array_equal(backproject_4dstem(data.astype(np.uint16), model_fn, scan_grid, detector), fast)
+    np.testing.assert_array_equal(backproject_4dstem(data, model_fn, scan_grid, detector, kernel="affine"), fast)
+
+
+def test_stem4d_rounding_ties(torch_cuda):
+    """Power-of-two geometry: every other ray lands EXACTLY on a rounding tie (x.5 sample pixels), so the
+    integer-DDA and guarded-affine kernels must hand those rays to the step-wise chain (half-to-even)."""
+    from temgymcore_b200.components import Descanner, DescanError, Detector, ScanGrid, Scanner
+    from temgymcore_b200.source import PointSource
+    from temgymcore_b200.stem4d import backproject_4dstem
+    ps_s, ps_d = 2.0 ** -32, 2.0 ** -14
+    zs = -2.0 ** -20
+    scan_grid = ScanGrid(z=0.0, pixel_size=(ps_s, ps_s), shape=(12, 10))
+    out_grid = ScanGrid(z=0.0, pixel_size=(ps_s, ps_s), shape=(40, 36), centre=(ps_s / 4, ps_s / 4))
+    detector = Detector(z=0.5 + zs, pixel_size=(ps_d, ps_d), shape=(32, 64))
+    src = PointSource(z=zs, semi_conv=1e-2)
+
+    def model_fn(spx, spy):
+        return [src, scan_grid, Scanner(z=0.0, scan_pos_x=spx, scan_pos_y=spy),
+                Descanner(z=0.1, scan_pos_x=spx, scan_pos_y=spy, descan_error=DescanError()), detector]
+    idx = O.stem4d_pixel_indices(model_fn, scan_grid, detector, out_grid=out_grid)
+    # the oracle's un-rounded coordinates really are ties for a large share of the rays
+    data = np.random.default_rng(5).integers(0, 9, size=(12, 10, 32, 64)).astype(np.float32)
+    ref = O.stem4d_backproject(data, model_fn, scan_grid, detector, out_grid=out_grid)
+    assert ref.sum() > 0 and len(np.unique(idx[..., 1])) > 8
+    for kernel in ("auto", "affine", "stepwise"):
+        got = backproject_4dstem(data, model_fn, scan_grid, detector, out_grid=out_grid, kernel=kernel)
+        np.testing.assert_array_equal(got.astype(np.float64), ref, err_msg=kernel)
+
+
+def test_stem4d_large_frames_dda_equals_stepwise(torch_cuda):
+    """C5-shaped frames (256 x 256 detector, 13 deg scan rotation, descan error) on a 24 x 20 scan: the
+    integer DDA kernel, the guarded affine kernel and the step-wise kernel give the same image for
+    integer counts (exact sums); frames at the scan edge fall partly off the sample grid."""
+    from temgymcore_b200.stem4d import backproject_4dstem, system_geometry
+    model_fn, scan_grid, detector = M.stem4d_case((24, 20), (256, 256), z_src=-1e-6)
+    geo = system_geometry(model_fn, scan_grid, detector)
+    data = torch_cuda.randint(0, 7, (24, 20, 256, 256), device="cuda", dtype=torch_cuda.int32).to(torch_cuda.float32)
+    imgs = {k: backproject_4dstem(data, None, scan_grid, detector, geometry=geo, kernel=k).cpu().numpy()
+            for k in ("auto", "affine", "stepwise")}
+    np.testing.assert_array_equal(imgs["auto"], imgs["stepwise"])
+    np.testing.assert_array_equal(imgs["affine"], imgs["stepwise"])
+    assert 0 < imgs["auto"].sum() < float(data.sum().item())       # some rays miss the 24 x 20 sample grid
+    d16 = data.to(torch_cuda.uint16)
+    np.testing.assert_array_equal(backproject_4dstem(d16, None, scan_grid, detector, geometry=geo).cpu().numpy(),
+                                  imgs["auto"])
 
 
 def test_gaussian_image_plan_cuda_graph(torch_cuda):
@@ -672,3 +717,26 @@ def test_gaussian_image_plan_cuda_graph(torch_cuda):
         out2 = to_np(plan.update(g2).run()).copy()
         assert rel_l2(out2, O.make_gaussian_image(g2, model)) < FIELD_TOL
         np.testing.assert_array_equal(out2, make_gaussian_image(g2, model, cull_bits=0))
+
+
+def test_ray_trace_plan_cuda_graph(torch_cuda):
+    from temgymcore_b200.ray import RAY_FIELDS
+    from temgymcore_b200.run import RayTracePlan, run_to_end, run_to_end_abcd
+    rays = M.random_rays(5000)
+    model = M.kitchen_sink_model()
+    dr = ray_to_cuda(torch_cuda, rays)
+    plan = RayTracePlan(dr, model)
+    out, abcd = plan.run()
+    ref_out, ref_abcd = O.abcd_run_to_end(rays, model)
+    for f in RAY_FIELDS:
+        close(to_np(getattr(out, f)), getattr(ref_out, f))
+    close(to_np(abcd), ref_abcd)
+    # new rays, same count: update + replay == a direct call
+    rays2 = M.random_rays(5000, np.random.default_rng(7))
+    out2, abcd2 = plan.update(rays2).run()
+    d_out, d_abcd = run_to_end_abcd(ray_to_cuda(torch_cuda, rays2), model)
+    np.testing.assert_array_equal(to_np(abcd2), to_np(d_abcd))
+    np.testing.assert_array_equal(to_np(out2.x), to_np(d_out.x))
+    o3, j3 = RayTracePlan(dr, model, jacobian=False).run()
+    assert j3 is None
+    np.testing.assert_array_equal(to_np(o3.dy), to_np(run_to_end(dr, model).dy))
