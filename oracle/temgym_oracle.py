@@ -916,8 +916,9 @@ def transfer_rays(ray_coords, transfer_matrices):
 # --------------------------------------------------------------------------
 
 
-def stem4d_pixel_indices(model_fn, scan_grid, detector, source_xy=(0.0, 0.0), out_grid=None):
-    """(Sy*Sx, Dy*Dx, 2) int32 sample-grid (py, px) of every (scan position, detector pixel) ray."""
+def stem4d_pixel_indices(model_fn, scan_grid, detector, source_xy=(0.0, 0.0), out_grid=None, unrounded=False):
+    """(Sy*Sx, Dy*Dx, 2) int32 sample-grid (py, px) of every (scan position, detector pixel) ray
+    (``unrounded``: the fp64 pixel coordinates before ``round``, for tie statistics in tests)."""
     out_grid = scan_grid if out_grid is None else out_grid
     r0 = np.array([float(source_xy[0]), float(source_xy[1])])
 
@@ -952,6 +953,8 @@ def stem4d_pixel_indices(model_fn, scan_grid, detector, source_xy=(0.0, 0.0), ou
     xs = (csamp[0] + (Bsamp[0, 0] * tx + Bsamp[0, 1] * ty)) + esx
     ys = (csamp[1] + (Bsamp[1, 0] * tx + Bsamp[1, 1] * ty)) + esy
     py, px = apply_transformation(ys, xs, grid_metres_to_pixels_mat(out_grid))
+    if unrounded:
+        return np.stack([py, px], axis=-1)
     return np.stack([round_to_int32(py), round_to_int32(px)], axis=-1)
 
 

@@ -386,9 +386,158 @@ __global__ void __launch_bounds__(kThreads4d, 4)
   }
 }
 
+// ---- integer DDA, single-crossing strips ---------------------------------------------------
+// When additionally 7 |slope| < 1 px per detector column for both coordinates (checked on the host),
+// a strip of 8 rays crosses at most ONE pixel boundary per coordinate, so its rays fall into at most
+// three cells: (y, x) not crossed / one crossed / both crossed.  Each coordinate is carried MIRRORED
+// if it decreases along the strip (U = 63 - u), so both always increase; t = frac(U_0) - 1 + j |c| is
+// negative before the crossing and >= 0 after it (the class predicate is a sign test), and the
+// smallest non-negative t is the only candidate for a near-tie apart from frac(U_0) itself.  The strip
+// is summed branch-free into three class sums with predicated FADDs and flushed with at most three
+// shared-memory atomics: no divergent run-merge loop (which cost 2/3 of the general DDA kernel's
+// issue slots).  The tile is indexed in mirrored cells; the final flush un-mirrors.
+__device__ __forceinline__ void smem_red_add(unsigned addr, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads4d, 4)
+    stem4d_backproject_dda1x_kernel(const __grid_constant__ Stem4dGeom g, const T *__restrict__ data,
+                                    float *__restrict__ out, int s_begin) {
+  __shared__ float tile[kTile * kTile];
+  const int s = s_begin + blockIdx.x;
+  const int sy = s / g.Sx, sx = s % g.Sx;
+  for (int k = threadIdx.x; k < kTile * kTile; k += kThreads4d) tile[k] = 0.f;
+  const double fsy = (double)sy, fsx = (double)sx;
+  const double spy = (g.Ts[0] * fsy + g.Ts[1] * fsx) + g.Ts[2];
+  const double spx = (g.Ts[3] * fsy + g.Ts[4] * fsx) + g.Ts[5];
+  const double edx = (g.edet[0] + spx * g.edet[2]) + spy * g.edet[4];
+  const double edy = (g.edet[1] + spx * g.edet[3]) + spy * g.edet[5];
+  const double esx = (g.esamp[0] + spx * g.esamp[2]) + spy * g.esamp[4];
+  const double esy = (g.esamp[1] + spx * g.esamp[3]) + spy * g.esamp[5];
+  int cy, cx;
+  ray_to_pixel(g, spx, spy, edx, edy, esx, esy, g.Dy / 2, g.Dx / 2, cy, cx);
+  const int ty0 = cy - kTile / 2, tx0 = cx - kTile / 2;
+  const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
+
+  const int gpr = g.Dx >> 3;
+  const int ngroups = g.Dy * gpr;
+  long long qy, qx, stepy, stepx, wrapy, wrapx;
+  int cy32, cx32;            // |slope| per detector column, 24 fractional bits (>= 0)
+  bool my, mx;               // coordinate is carried mirrored
+  int dy = threadIdx.x / gpr, cg = threadIdx.x - dy * gpr;
+  const int drow = kThreads4d / gpr, dcol = kThreads4d - drow * gpr;
+  {
+    const double yd = g.Td[2], xd = g.Td[5];
+    const double rx = (xd - g.cdet[0]) - edx, ry = (yd - g.cdet[1]) - edy;
+    const double tx = g.Binv[0] * rx + g.Binv[1] * ry, ty = g.Binv[2] * rx + g.Binv[3] * ry;
+    const double xs = (g.csamp[0] + (g.Bs[0] * tx + g.Bs[1] * ty)) + esx;
+    const double ys = (g.csamp[1] + (g.Bs[2] * tx + g.Bs[3] * ty)) + esy;
+    const double by = (g.To[0] * ys + g.To[1] * xs) + g.To[2];
+    const double bx = (g.To[3] * ys + g.To[4] * xs) + g.To[5];
+    double ry_, rx_, cy_, cx_;
+    auto slope = [&](double dyd, double dxd, double &oy, double &ox) {
+      const double ttx = g.Binv[0] * dxd + g.Binv[1] * dyd, tty = g.Binv[2] * dxd + g.Binv[3] * dyd;
+      const double dxs = g.Bs[0] * ttx + g.Bs[1] * tty, dys = g.Bs[2] * ttx + g.Bs[3] * tty;
+      oy = g.To[0] * dys + g.To[1] * dxs;
+      ox = g.To[3] * dys + g.To[4] * dxs;
+    };
+    slope(g.Td[0], g.Td[3], ry_, rx_);
+    slope(g.Td[1], g.Td[4], cy_, cx_);
+    my = cy_ < 0.0;
+    mx = cx_ < 0.0;
+    const double kS = 1099511627776.0;         // 2^40
+    const double off = 0.5 + 1.0 / (double)(1 << kGuardLog);
+    const double uy = by - (double)ty0, ux = bx - (double)tx0;
+    const long long By = __double2ll_rn(((my ? (double)(kTile - 1) - uy : uy) + off) * kS);
+    const long long Bx = __double2ll_rn(((mx ? (double)(kTile - 1) - ux : ux) + off) * kS);
+    const long long Ry = __double2ll_rn((my ? -ry_ : ry_) * kS), Rx = __double2ll_rn((mx ? -rx_ : rx_) * kS);
+    const long long Cy = __double2ll_rn(fabs(cy_) * kS), Cx = __double2ll_rn(fabs(cx_) * kS);
+    qy = By + (long long)dy * Ry + (long long)(cg * 8) * Cy;
+    qx = Bx + (long long)dy * Rx + (long long)(cg * 8) * Cx;
+    stepy = (long long)drow * Ry + (long long)(dcol * 8) * Cy;
+    stepx = (long long)drow * Rx + (long long)(dcol * 8) * Cx;
+    wrapy = Ry - (long long)(gpr * 8) * Cy;
+    wrapx = Rx - (long long)(gpr * 8) * Cx;
+    cy32 = (int)((Cy + (1ll << (kQFrac - kFrac - 1))) >> (kQFrac - kFrac));
+    cx32 = (int)((Cx + (1ll << (kQFrac - kFrac - 1))) >> (kQFrac - kFrac));
+  }
+  __syncthreads();
+
+  auto strip = [&](const float (&v)[8]) {
+    const int wy0 = (int)(qy >> (kQFrac - kFrac)), wx0 = (int)(qx >> (kQFrac - kFrac));
+    const int ky = wy0 >> kFrac, kx = wx0 >> kFrac;                   // mirrored cell of ray 0
+    const unsigned fy = (unsigned)wy0 & kFracMask, fx = (unsigned)wx0 & kFracMask;
+    int ty = (int)fy - (1 << kFrac), tx = (int)fx - (1 << kFrac);     // < 0 until the crossing
+    const int ty_first = ty, tx_first = tx;
+    unsigned near = min(fy, fx);
+    float s00 = 0.f, s11 = 0.f, smid = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // class selection by sign masks on the float's bits (branch-free: 2 SHF, 3 LOP3, 3 FADD)
+      const int ny = ty >> 31, nx = tx >> 31;            // all ones until the coordinate has crossed
+      const int bits = __float_as_int(v[j]);
+      near = min(near, min((unsigned)ty, (unsigned)tx));
+      s00 += __int_as_float(bits & ny & nx);
+      s11 += __int_as_float(bits & ~ny & ~nx);
+      smid += __int_as_float(bits & (ny ^ nx));
+      ty += cy32;
+      tx += cx32;
+    }
+    if (near >= kWindow && (unsigned)(ky - 1) < (unsigned)(kTile - 2) && (unsigned)(kx - 1) < (unsigned)(kTile - 2)) {
+      const unsigned a00 = tile_s + 4u * (unsigned)(ky * kTile + kx);
+      // which coordinate crosses first: (-ty_first)/cy < (-tx_first)/cx, cross-multiplied (exact)
+      const bool yfirst = (long long)(-ty_first) * cx32 < (long long)(-tx_first) * cy32;
+      if (s00 != 0.f) smem_red_add(a00, s00);
+      if (smid != 0.f) smem_red_add(a00 + (yfirst ? 4u * kTile : 4u), smid);
+      if (s11 != 0.f) smem_red_add(a00 + 4u * (kTile + 1), s11);
+    } else {                                   // a tie / out-of-tile strip: exact step-wise chain
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {
+        float vj = v[0];
+#pragma unroll
+        for (int t = 1; t < 8; ++t) vj = (j == t) ? v[t] : vj;
+        int py, px;
+        ray_to_pixel(g, spx, spy, edx, edy, esx, esy, dy, cg * 8 + j, py, px);
+        if ((unsigned)py >= (unsigned)g.Oy || (unsigned)px >= (unsigned)g.Ox) continue;
+        const int ly = py - ty0, lx = px - tx0;
+        if ((unsigned)ly < (unsigned)kTile && (unsigned)lx < (unsigned)kTile)
+          atomicAdd(&tile[(my ? kTile - 1 - ly : ly) * kTile + (mx ? kTile - 1 - lx : lx)], vj);
+        else
+          atomicAdd(&out[(long long)py * g.Ox + px], vj);
+      }
+    }
+    dy += drow; cg += dcol; qy += stepy; qx += stepx;
+    if (cg >= gpr) { cg -= gpr; ++dy; qy += wrapy; qx += wrapx; }
+  };
+
+  const T *frame = data + (long long)s * g.Dy * g.Dx;
+  float va[8], vb[8];
+  int grp = threadIdx.x;
+  if (grp < ngroups) load8<T>(frame + (long long)grp * 8, va);
+  while (grp < ngroups) {
+    if (grp + kThreads4d < ngroups) load8<T>(frame + (long long)(grp + kThreads4d) * 8, vb);
+    strip(va);
+    grp += kThreads4d;
+    if (grp >= ngroups) break;
+    if (grp + kThreads4d < ngroups) load8<T>(frame + (long long)(grp + kThreads4d) * 8, va);
+    strip(vb);
+    grp += kThreads4d;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < kTile * kTile; k += kThreads4d) {
+    const float t = tile[k];
+    if (t != 0.f) {
+      const int ly = k / kTile, lx = k % kTile;
+      const int py = ty0 + (my ? kTile - 1 - ly : ly), px = tx0 + (mx ? kTile - 1 - lx : lx);
+      if (py >= 0 && py < g.Oy && px >= 0 && px < g.Ox) atomicAdd(&out[(long long)py * g.Ox + px], t);
+    }
+  }
+}
+
 // host-side dispatch test: does every frame's footprint stay inside the tile?  (The linear part of
 // the detector-pixel -> sample-pixel map does not depend on the scan position.)
-bool footprint_fits_tile(const Stem4dGeom &g) {
+int footprint_fits_tile(const Stem4dGeom &g) {
   auto slope = [&](double dyd, double dxd, double &oy, double &ox) {
     const double ttx = g.Binv[0] * dxd + g.Binv[1] * dyd, tty = g.Binv[2] * dxd + g.Binv[3] * dyd;
     const double dxs = g.Bs[0] * ttx + g.Bs[1] * tty, dys = g.Bs[2] * ttx + g.Bs[3] * tty;
@@ -400,7 +549,9 @@ bool footprint_fits_tile(const Stem4dGeom &g) {
   slope(g.Td[1], g.Td[4], cy, cx);
   const double hy = 0.5 * g.Dy + 1.0, hx = 0.5 * g.Dx + 1.0;
   const double ey = fabs(ry) * hy + fabs(cy) * hx, ex = fabs(rx) * hy + fabs(cx) * hx;
-  return ey <= kTile / 2 - 3 && ex <= kTile / 2 - 3;   // false for NaN
+  if (!(ey <= kTile / 2 - 3 && ex <= kTile / 2 - 3)) return 0;   // (NaN -> 0)
+  // single-crossing strips: 7 |slope per column| < 1 with a margin for the fixed-point rounding
+  return (7.0 * fabs(cy) < 0.999 && 7.0 * fabs(cx) < 0.999) ? 2 : 1;
 }
 
 // pixel indices only (parity / debugging): idx[(s*npix + p)*2 + {0,1}] = (py, px)
@@ -454,12 +605,23 @@ extern "C" int tg_stem4d_backproject(const int shapes[6], const double geom[42],
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool force_stepwise = (data_is_f32 & 2) != 0;
   const bool no_dda = (data_is_f32 & 4) != 0;      // A/B switch: guarded fp64 affine kernel instead of the DDA
+  const bool general_dda = (data_is_f32 & 8) != 0; // A/B switch: run-merging DDA even for single-crossing strips
   data_is_f32 &= 1;
   const size_t esz = data_is_f32 ? 4 : 2;
   const bool fast = !force_stepwise && (g.Dx % 8) == 0 && ((reinterpret_cast<uintptr_t>(data4d) +
                                          (size_t)s_begin * g.Dy * g.Dx * esz) % 16) == 0 &&
                     (((size_t)g.Dy * g.Dx * esz) % 16) == 0;
-  if (fast && !no_dda && footprint_fits_tile(g)) {
+  const int fits = (fast && !no_dda) ? footprint_fits_tile(g) : 0;
+  if (fits == 2 && !general_dda) {
+    if (data_is_f32)
+      stem4d_backproject_dda1x_kernel<float><<<(unsigned)s_count, kThreads4d, 0, st>>>(
+          g, static_cast<const float *>(data4d), out, s_begin);
+    else
+      stem4d_backproject_dda1x_kernel<unsigned short><<<(unsigned)s_count, kThreads4d, 0, st>>>(
+          g, static_cast<const unsigned short *>(data4d), out, s_begin);
+    return tg_launch_check("stem4d_backproject_dda1x_kernel");
+  }
+  if (fits) {
     if (data_is_f32)
       stem4d_backproject_dda_kernel<float><<<(unsigned)s_count, kThreads4d, 0, st>>>(
           g, static_cast<const float *>(data4d), out, s_begin);

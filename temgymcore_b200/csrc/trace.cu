@@ -21,6 +21,18 @@
 #include <math.h>
 #include "tg_common.cuh"
 
+// Models containing an AberratedLensKrivanek are compute-bound (fp64 pipe), not HBM-bound, and the
+// lens's algebraic harmonic evaluation is not bit-comparable to the reference's hypot / arctan2 / cos
+// chain anyway (parity is 1e-12 relative).  Their kernel instantiations are therefore built from this
+// same source a second time with FMA contraction ON (build.sh: -DTG_TRACE_KRIV_TU, default -fmad):
+// 30 % fewer fp64 instructions.  Everything else stays -fmad=false and bit-faithful.
+namespace tg_internal {
+int launch_trace_kriv(int nc, const tg_model *m, int64_t n, const tg_ray_in *in, double *const out[7],
+                      double *jac, cudaStream_t st);
+int launch_trace_grad_kriv(const tg_model *m, const void *grad_seeds, const tg_ray_in *in, int64_t n,
+                           double *const out[7], double *jac, cudaStream_t st);
+}  // namespace tg_internal
+
 namespace {
 
 constexpr int kTraceThreads = 128;
@@ -281,11 +293,18 @@ __device__ __forceinline__ void krivanek(const double *p, const Dual<N> &ax, con
     c1 = ax * ia;
     s1 = ay * ia;
   }
-  const Dual<N> c2 = c1 * c1 - s1 * s1, s2 = s1 * c1 + c1 * s1;
-  const Dual<N> c3 = c2 * c1 - s2 * s1, s3 = s2 * c1 + c2 * s1;
-  const Dual<N> c4 = c2 * c2 - s2 * s2, s4 = s2 * c2 + c2 * s2;
-  const Dual<N> c5 = c4 * c1 - s4 * s1, s5 = s4 * c1 + c4 * s1;
-  const Dual<N> c6 = c3 * c3 - s3 * s3, s6 = s3 * c3 + c3 * s3;
+  // harmonics actually present in the model (uniform branches on kernel-parameter constants):
+  // powers of the unit phasor are only formed up to the highest order in use
+  const bool u6 = p[K_C56] != 0.0, u5 = p[K_C45] != 0.0;
+  const bool u4 = p[K_C34] != 0.0 || p[K_C54] != 0.0 || u5;
+  const bool u3 = p[K_C23] != 0.0 || p[K_C43] != 0.0 || u6 || u5;
+  const bool u2 = p[K_C12] != 0.0 || p[K_C32] != 0.0 || p[K_C52] != 0.0 || u3 || u4;
+  Dual<N> c2 = dconst<N>(0.0), s2 = c2, c3 = c2, s3 = c2, c4 = c2, s4 = c2, c5 = c2, s5 = c2, c6 = c2, s6 = c2;
+  if (u2) { c2 = c1 * c1 - s1 * s1; s2 = s1 * c1 + c1 * s1; }
+  if (u3) { c3 = c2 * c1 - s2 * s1; s3 = s2 * c1 + c2 * s1; }
+  if (u4) { c4 = c2 * c2 - s2 * s2; s4 = s2 * c2 + c2 * s2; }
+  if (u5) { c5 = c4 * c1 - s4 * s1; s5 = s4 * c1 + c4 * s1; }
+  if (u6) { c6 = c3 * c3 - s3 * s3; s6 = s3 * c3 + c3 * s3; }
   const double *g = p + 25;  // (cos, sin)(m phi0) pairs
   // brackets (aberrations.py:42-48) and the matching sin sums of dW/dphi (aberrations.py:78-98)
   Dual<N> B2 = dconst<N>(p[K_C10]), T2 = dconst<N>(0.0);
@@ -577,8 +596,12 @@ int launch_trace(const tg_model *m, int64_t n, const tg_ray_in *in, double *cons
                  double *jac, cudaStream_t st) {
   bool kriv = false;
   for (int c = 0; c < m->n_comp; ++c) kriv |= (m->comp[c].op == TG_OP_KRIVANEK);
-  return kriv ? launch_trace_k<NC, true>(m, n, in, out, jac, st)
+#ifdef TG_TRACE_KRIV_TU
+  return launch_trace_k<NC, true>(m, n, in, out, jac, st);
+#else
+  return kriv ? tg_internal::launch_trace_kriv(NC, m, n, in, out, jac, st)
               : launch_trace_k<NC, false>(m, n, in, out, jac, st);
+#endif
 }
 
 // ------------------------------------------------------------------ parameter tangents
@@ -762,6 +785,29 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace
 
+#ifdef TG_TRACE_KRIV_TU
+// ---- second translation unit (FMA contraction on): only the Krivanek instantiations
+namespace tg_internal {
+int launch_trace_kriv(int nc, const tg_model *m, int64_t n, const tg_ray_in *in, double *const out[7],
+                      double *jac, cudaStream_t st) {
+  switch (nc) {
+    case 0: return launch_trace_k<0, true>(m, n, in, out, jac, st);
+    case 5: return launch_trace_k<5, true>(m, n, in, out, jac, st);
+    default: return launch_trace_k<7, true>(m, n, in, out, jac, st);
+  }
+}
+int launch_trace_grad_kriv(const tg_model *m, const void *grad_seeds, const tg_ray_in *in, int64_t n,
+                           double *const out[7], double *jac, cudaStream_t st) {
+  TraceOut o;
+  for (int f = 0; f < 7; ++f) o.ptr[f] = out ? out[f] : nullptr;
+  const long long blocks = (n + kTraceThreads - 1) / kTraceThreads;
+  trace_grad_kernel<true><<<(unsigned)blocks, kTraceThreads, 0, st>>>(
+      *m, *static_cast<const GradSeeds *>(grad_seeds), *in, (long long)n, o, jac);
+  return tg_launch_check("trace_grad_kernel");
+}
+}  // namespace tg_internal
+#else
+
 extern "C" int tg_trace_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in,
                             double *const out[7], double *jac, int jac_layout, void *stream) {
   TG_REQUIRE(model_host && in, "null model or input");
@@ -838,10 +884,8 @@ extern "C" int tg_trace_grad_f64(const tg_model *model_host, int64_t n, const tg
   const long long blocks = (n + kTraceThreads - 1) / kTraceThreads;
   TG_REQUIRE(blocks <= 0x7fffffffLL, "too many rays for one launch");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (kriv)
-    trace_grad_kernel<true><<<(unsigned)blocks, kTraceThreads, 0, st>>>(*model_host, gs, *in, (long long)n, o, jac);
-  else
-    trace_grad_kernel<false><<<(unsigned)blocks, kTraceThreads, 0, st>>>(*model_host, gs, *in, (long long)n, o, jac);
+  if (kriv) return tg_internal::launch_trace_grad_kriv(model_host, &gs, in, n, out, jac, st);
+  trace_grad_kernel<false><<<(unsigned)blocks, kTraceThreads, 0, st>>>(*model_host, gs, *in, (long long)n, o, jac);
   return tg_launch_check("trace_grad_kernel");
 }
 
@@ -858,3 +902,4 @@ extern "C" int tg_transfer_rays_f64(int64_t n, const double *rays, int m, const 
   transfer_rays_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(tm, n, rays, out);
   return tg_launch_check("transfer_rays_kernel");
 }
+#endif  // TG_TRACE_KRIV_TU

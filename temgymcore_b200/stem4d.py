@@ -85,13 +85,14 @@ def backproject_4dstem(data4d, model_fn, scan_grid, detector, *, source_xy=(0.0,
     data4d: ``(Sy, Sx, Dy, Dx)`` float32 or uint16 (numpy / torch; stays on the GPU if it is
     there).  ``scan_range=(begin, count)`` restricts to a shard of flattened scan positions;
     ``out`` accumulates into an existing CUDA image.  ``kernel`` selects the implementation for
-    A/B checks: "auto" (integer DDA kernel when a frame's footprint fits the 64 x 64 shared-memory
-    tile, else the guarded fp64 affine kernel, else the step-wise kernel), "affine" (never the DDA
-    kernel) or "stepwise" (= ``stepwise_only``).  All three give identical pixel indices.
+    A/B checks: "auto" (integer DDA kernels when a frame's footprint fits the 64 x 64 shared-memory
+    tile -- the single-crossing variant when 7 |slope| < 1 px/px, else the run-merging one -- else the
+    guarded fp64 affine kernel, else the step-wise kernel), "dda" (run-merging DDA only), "affine"
+    (never a DDA kernel) or "stepwise" (= ``stepwise_only``).  All give identical pixel indices.
     """
-    if kernel not in ("auto", "affine", "stepwise"):
+    if kernel not in ("auto", "dda", "affine", "stepwise"):
         raise ValueError(f"unknown kernel {kernel!r}")
-    mode_bits = 2 if (stepwise_only or kernel == "stepwise") else (4 if kernel == "affine" else 0)
+    mode_bits = 2 if (stepwise_only or kernel == "stepwise") else {"affine": 4, "dda": 8}.get(kernel, 0)
     import torch
     lib = L.load()
     shapes, geom = geometry if geometry is not None else system_geometry(model_fn, scan_grid, detector, source_xy,

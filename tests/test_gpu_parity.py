@@ -660,29 +660,33 @@ def test_stem4d_backprojection(torch_cuda):
 
 
 def test_stem4d_rounding_ties(torch_cuda):
-    """Power-of-two geometry: every other ray lands EXACTLY on a rounding tie (x.5 sample pixels), so the
-    integer-DDA and guarded-affine kernels must hand those rays to the step-wise chain (half-to-even)."""
+    """Power-of-two geometries in which a large share of the rays land EXACTLY on a rounding tie (x.5
+    sample pixels): every fast kernel must hand those rays to the step-wise chain (half-to-even).
+    Slope 0.5 px/px exercises the run-merging DDA kernel, slope 0.125 the single-crossing one."""
     from temgymcore_b200.components import Descanner, DescanError, Detector, ScanGrid, Scanner
     from temgymcore_b200.source import PointSource
     from temgymcore_b200.stem4d import backproject_4dstem
-    ps_s, ps_d = 2.0 ** -32, 2.0 ** -14
+    ps_s = 2.0 ** -32
     zs = -2.0 ** -20
-    scan_grid = ScanGrid(z=0.0, pixel_size=(ps_s, ps_s), shape=(12, 10))
-    out_grid = ScanGrid(z=0.0, pixel_size=(ps_s, ps_s), shape=(40, 36), centre=(ps_s / 4, ps_s / 4))
-    detector = Detector(z=0.5 + zs, pixel_size=(ps_d, ps_d), shape=(32, 64))
-    src = PointSource(z=zs, semi_conv=1e-2)
+    rng = np.random.default_rng(5)
+    for ps_d, off in ((2.0 ** -14, 0.25), (2.0 ** -16, 0.4375), (2.0 ** -16, -0.4375)):
+        scan_grid = ScanGrid(z=0.0, pixel_size=(ps_s, ps_s), shape=(12, 10))
+        out_grid = ScanGrid(z=0.0, pixel_size=(ps_s, ps_s), shape=(40, 36), centre=(ps_s * off, ps_s * off))
+        detector = Detector(z=0.5 + zs, pixel_size=(ps_d, ps_d), shape=(32, 64))
+        src = PointSource(z=zs, semi_conv=1e-2)
 
-    def model_fn(spx, spy):
-        return [src, scan_grid, Scanner(z=0.0, scan_pos_x=spx, scan_pos_y=spy),
-                Descanner(z=0.1, scan_pos_x=spx, scan_pos_y=spy, descan_error=DescanError()), detector]
-    idx = O.stem4d_pixel_indices(model_fn, scan_grid, detector, out_grid=out_grid)
-    # the oracle's un-rounded coordinates really are ties for a large share of the rays
-    data = np.random.default_rng(5).integers(0, 9, size=(12, 10, 32, 64)).astype(np.float32)
-    ref = O.stem4d_backproject(data, model_fn, scan_grid, detector, out_grid=out_grid)
-    assert ref.sum() > 0 and len(np.unique(idx[..., 1])) > 8
-    for kernel in ("auto", "affine", "stepwise"):
-        got = backproject_4dstem(data, model_fn, scan_grid, detector, out_grid=out_grid, kernel=kernel)
-        np.testing.assert_array_equal(got.astype(np.float64), ref, err_msg=kernel)
+        def model_fn(spx, spy):
+            return [src, scan_grid, Scanner(z=0.0, scan_pos_x=spx, scan_pos_y=spy),
+                    Descanner(z=0.1, scan_pos_x=spx, scan_pos_y=spy, descan_error=DescanError()), detector]
+        raw = O.stem4d_pixel_indices(model_fn, scan_grid, detector, out_grid=out_grid, unrounded=True)
+        ties = (raw - np.floor(raw)) == 0.5
+        assert ties[..., 0].mean() > 0.1 or ties[..., 1].mean() > 0.1      # the oracle really sees exact ties
+        data = rng.integers(0, 9, size=(12, 10, 32, 64)).astype(np.float32)
+        ref = O.stem4d_backproject(data, model_fn, scan_grid, detector, out_grid=out_grid)
+        assert ref.sum() > 0
+        for kernel in ("auto", "dda", "affine", "stepwise"):
+            got = backproject_4dstem(data, model_fn, scan_grid, detector, out_grid=out_grid, kernel=kernel)
+            np.testing.assert_array_equal(got.astype(np.float64), ref, err_msg=f"{kernel} ps_d={ps_d} off={off}")
 
 
 def test_stem4d_large_frames_dda_equals_stepwise(torch_cuda):
@@ -694,8 +698,9 @@ def test_stem4d_large_frames_dda_equals_stepwise(torch_cuda):
     geo = system_geometry(model_fn, scan_grid, detector)
     data = torch_cuda.randint(0, 7, (24, 20, 256, 256), device="cuda", dtype=torch_cuda.int32).to(torch_cuda.float32)
     imgs = {k: backproject_4dstem(data, None, scan_grid, detector, geometry=geo, kernel=k).cpu().numpy()
-            for k in ("auto", "affine", "stepwise")}
+            for k in ("auto", "dda", "affine", "stepwise")}
     np.testing.assert_array_equal(imgs["auto"], imgs["stepwise"])
+    np.testing.assert_array_equal(imgs["dda"], imgs["stepwise"])
     np.testing.assert_array_equal(imgs["affine"], imgs["stepwise"])
     assert 0 < imgs["auto"].sum() < float(data.sum().item())       # some rays miss the 24 x 20 sample grid
     d16 = data.to(torch_cuda.uint16)
