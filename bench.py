@@ -37,7 +37,8 @@ NCU_TRAFFIC = {
     "gemm_tf32x3_kernel": (491.98e6 + 4.20e6, "profiles/r1_gemm_tf32x3_kernel_v1.md"),
     "field_grid_kernel": (1.00e6 + 81.65e6, "profiles/r1_field_grid_kernel_v1.md"),
     "trace_kernel_1e7": (560.0e6 + 2499.5e6, "profiles/r1_trace_kernel_1e7.md"),
-    "stem4d_backproject": (17.18e9, "profiles/r1_stem4d_backproject_kernel.md"),
+    "stem4d_backproject": (17.18e9 + 3.6e6, "profiles/r1_stem4d_dda1x_kernel.md"),
+    "trace_kernel_c4": (560.1e6 + 2506.8e6, "profiles/r1_trace_kernel_c4_v3.md"),
 }
 MUFU_PER_EVAL = 3          # sin, cos, ex2
 MUFU_PER_CLK_SM = 16
@@ -464,7 +465,7 @@ def run_ours(args):
                            "frac": gbs5 / pk["hbm_gbs"],
                            "traffic": NCU_TRAFFIC["stem4d_backproject"][0] / world,
                            "traffic_source": NCU_TRAFFIC["stem4d_backproject"][1], "bytes_per_ray": 4,
-                           "kernel": "stem4d_backproject_dda_kernel<float> (integer fixed-point stepping)"},
+                           "kernel": "stem4d_backproject_dda1x_kernel<float> (integer fixed-point stepping, single-crossing strips)"},
               "ms_per_pass_guarded_fp64_affine_kernel": ms5_affine}
     del data5
     torch.cuda.empty_cache()

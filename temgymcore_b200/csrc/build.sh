@@ -1,7 +1,6 @@
 #!/usr/bin/env bash
 # Builds libtemgym_b200.so (sm_100a only) next to the Python package.
-# trace.cu / coeffs.cu: -fmad=false (bit-faithful fp64, see the file headers); field.cu: FMA on;
-# trace.cu is compiled a second time with FMA on for the compute-bound Krivanek-lens instantiations.
+# trace.cu / coeffs.cu: -fmad=false (bit-faithful fp64, see the file headers); field.cu: FMA on.
 set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 root="$(cd "$here/../.." && pwd)"
@@ -14,12 +13,11 @@ COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$root/include -I$here $ARCH"
 VERBOSE="${TG_PTXAS_V:+-Xptxas -v}"
 pids=()
 $NVCC $COMMON $VERBOSE -fmad=false -c "$here/trace.cu"    -o "$obj/trace.o" & pids+=($!)
-$NVCC $COMMON $VERBOSE -DTG_TRACE_KRIV_TU -c "$here/trace.cu" -o "$obj/trace_kriv.o" & pids+=($!)
 $NVCC $COMMON $VERBOSE -fmad=false -c "$here/coeffs.cu"   -o "$obj/coeffs.o" & pids+=($!)
 $NVCC $COMMON $VERBOSE -fmad=false -c "$here/stem4d.cu"   -o "$obj/stem4d.o" & pids+=($!)
 $NVCC $COMMON $VERBOSE             -c "$here/field.cu"    -o "$obj/field.o" & pids+=($!)
 $NVCC $COMMON $VERBOSE             -c "$here/host_api.cu" -o "$obj/host_api.o" & pids+=($!)
 $NVCC $COMMON $VERBOSE             -c "$here/separable.cu" -o "$obj/separable.o" & pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
-$NVCC $ARCH -shared -o "$out" "$obj/trace.o" "$obj/trace_kriv.o" "$obj/coeffs.o" "$obj/field.o" "$obj/host_api.o" "$obj/separable.o" "$obj/stem4d.o" -cudart static
+$NVCC $ARCH -shared -o "$out" "$obj/trace.o" "$obj/coeffs.o" "$obj/field.o" "$obj/host_api.o" "$obj/separable.o" "$obj/stem4d.o" -cudart static
 echo "built $out"

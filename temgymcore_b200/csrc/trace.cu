@@ -19,19 +19,8 @@
 // conflicts) and emits them as ONE contiguous bulk async copy through the TMA unit
 // (cp.async.bulk.global.shared::cta), so HBM sees full lines only.
 #include <math.h>
+#include <stdlib.h>
 #include "tg_common.cuh"
-
-// Models containing an AberratedLensKrivanek are compute-bound (fp64 pipe), not HBM-bound, and the
-// lens's algebraic harmonic evaluation is not bit-comparable to the reference's hypot / arctan2 / cos
-// chain anyway (parity is 1e-12 relative).  Their kernel instantiations are therefore built from this
-// same source a second time with FMA contraction ON (build.sh: -DTG_TRACE_KRIV_TU, default -fmad):
-// 30 % fewer fp64 instructions.  Everything else stays -fmad=false and bit-faithful.
-namespace tg_internal {
-int launch_trace_kriv(int nc, const tg_model *m, int64_t n, const tg_ray_in *in, double *const out[7],
-                      double *jac, cudaStream_t st);
-int launch_trace_grad_kriv(const tg_model *m, const void *grad_seeds, const tg_ray_in *in, int64_t n,
-                           double *const out[7], double *jac, cudaStream_t st);
-}  // namespace tg_internal
 
 namespace {
 
@@ -255,6 +244,63 @@ enum {
   K_PHI54, K_C56, K_PHI56
 };
 
+// The Krivanek lens makes the ray kernel compute-bound (fp64 pipe), so its arithmetic is written
+// with EXPLICIT fused multiply-adds (this TU is built with -fmad=false; fma() calls are honoured):
+// ~30 % fewer fp64 instructions than separate multiplies and adds.  The helpers are used by every
+// instantiation (value-only, 5- and 7-column, gradient kernel) with the same value arithmetic, so
+// run_to_end and run_to_end_abcd still agree bit for bit.  (The algebraic harmonic evaluation is not
+// bit-comparable to the reference's hypot / arctan2 / cos chain anyway; parity is 1e-12 relative.)
+template <int N>
+__device__ __forceinline__ Dual<N> kmul(const Dual<N> &a, const Dual<N> &b) {           // a b
+  Dual<N> r;
+  r.v = a.v * b.v;
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = N > 0 ? fma(a.t[k], b.v, a.v * b.t[k]) : 0.0;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> kmul2(const Dual<N> &a, const Dual<N> &b, const Dual<N> &c,
+                                         const Dual<N> &d, double sgn) {                   // a b + sgn c d
+  Dual<N> r;
+  r.v = fma(a.v, b.v, sgn * (c.v * d.v));
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k)
+    r.t[k] = N > 0 ? fma(a.t[k], b.v, fma(a.v, b.t[k], sgn * fma(c.t[k], d.v, c.v * d.t[k]))) : 0.0;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> klin(const Dual<N> &a, double s, const Dual<N> &b, double t) {  // s a + t b
+  Dual<N> r;
+  r.v = fma(a.v, s, b.v * t);
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = N > 0 ? fma(a.t[k], s, b.t[k] * t) : 0.0;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> kaxpy(const Dual<N> &a, double s, const Dual<N> &b) {  // s a + b
+  Dual<N> r;
+  r.v = fma(a.v, s, b.v);
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = N > 0 ? fma(a.t[k], s, b.t[k]) : 0.0;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> kfma(const Dual<N> &a, const Dual<N> &b, const Dual<N> &c) {  // a b + c
+  Dual<N> r;
+  r.v = fma(a.v, b.v, c.v);
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = N > 0 ? fma(a.t[k], b.v, fma(a.v, b.t[k], c.t[k])) : 0.0;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> kscale(const Dual<N> &a, double s) {
+  Dual<N> r;
+  r.v = a.v * s;
+#pragma unroll
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) r.t[k] = N > 0 ? a.t[k] * s : 0.0;
+  return r;
+}
+
 // One harmonic term: B += C cos(m (phi - phi0)),  T += (-m C) sin(m (phi - phi0)), with
 // cos/sin(m phi) = Re/Im ((ax + i ay)/|a|)^m (cm, sm) and cos/sin(m phi0) model constants:
 //   cos(m(phi-phi0)) = cm c0 + sm s0,  sin(m(phi-phi0)) = sm c0 - cm s0
@@ -264,10 +310,8 @@ template <int N>
 __device__ __forceinline__ void kriv_term(double C, double m, const Dual<N> &cm, const Dual<N> &sm,
                                           double c0, double s0, Dual<N> &B, Dual<N> &T) {
   if (C == 0.0) return;
-  const Dual<N> ck = cm * c0 + sm * s0;
-  const Dual<N> sk = sm * c0 - cm * s0;
-  B = B + C * ck;
-  T = T + (-m * C) * sk;
+  B = kaxpy(klin(cm, c0, sm, s0), C, B);
+  T = kaxpy(klin(sm, c0, cm, -s0), -m * C, T);
 }
 
 // (dW/dax, dW/day, W) of the Krivanek aberration function (aberrations.py:42-108); N is the
@@ -279,7 +323,7 @@ __device__ __forceinline__ void krivanek(const double *p, const Dual<N> &ax, con
                                          Dual<N> &dWx, Dual<N> &dWy, Dual<N> &W) {
   const Dual<N> a = dhypot(ax, ay);
   // unit phasor e^{i phi}; at the origin phi = atan2(0,0) = 0 with NaN derivative like JAX
-  Dual<N> c1, s1;
+  Dual<N> c1, s1, ia;
   if (a.v == 0.0) {
     c1 = dconst<N>(1.0);
     s1 = dconst<N>(0.0);
@@ -288,10 +332,11 @@ __device__ __forceinline__ void krivanek(const double *p, const Dual<N> &ax, con
       c1.t[k] = a.t[k] * 0.0 + (N > 0 ? nan("") : 0.0);
       s1.t[k] = c1.t[k];
     }
+    ia = drecip(dconst<N>(1e-30));   // jnp.where(alpha == 0, 1e-30, alpha) (aberrations.py:100)
   } else {
-    const Dual<N> ia = drecip(a);
-    c1 = ax * ia;
-    s1 = ay * ia;
+    ia = drecip(a);
+    c1 = kmul(ax, ia);
+    s1 = kmul(ay, ia);
   }
   // harmonics actually present in the model (uniform branches on kernel-parameter constants):
   // powers of the unit phasor are only formed up to the highest order in use
@@ -300,11 +345,11 @@ __device__ __forceinline__ void krivanek(const double *p, const Dual<N> &ax, con
   const bool u3 = p[K_C23] != 0.0 || p[K_C43] != 0.0 || u6 || u5;
   const bool u2 = p[K_C12] != 0.0 || p[K_C32] != 0.0 || p[K_C52] != 0.0 || u3 || u4;
   Dual<N> c2 = dconst<N>(0.0), s2 = c2, c3 = c2, s3 = c2, c4 = c2, s4 = c2, c5 = c2, s5 = c2, c6 = c2, s6 = c2;
-  if (u2) { c2 = c1 * c1 - s1 * s1; s2 = s1 * c1 + c1 * s1; }
-  if (u3) { c3 = c2 * c1 - s2 * s1; s3 = s2 * c1 + c2 * s1; }
-  if (u4) { c4 = c2 * c2 - s2 * s2; s4 = s2 * c2 + c2 * s2; }
-  if (u5) { c5 = c4 * c1 - s4 * s1; s5 = s4 * c1 + c4 * s1; }
-  if (u6) { c6 = c3 * c3 - s3 * s3; s6 = s3 * c3 + c3 * s3; }
+  if (u2) { c2 = kmul2(c1, c1, s1, s1, -1.0); s2 = kscale(kmul(c1, s1), 2.0); }
+  if (u3) { c3 = kmul2(c2, c1, s2, s1, -1.0); s3 = kmul2(s2, c1, c2, s1, 1.0); }
+  if (u4) { c4 = kmul2(c2, c2, s2, s2, -1.0); s4 = kscale(kmul(c2, s2), 2.0); }
+  if (u5) { c5 = kmul2(c4, c1, s4, s1, -1.0); s5 = kmul2(s4, c1, c4, s1, 1.0); }
+  if (u6) { c6 = kmul2(c3, c3, s3, s3, -1.0); s6 = kscale(kmul(c3, s3), 2.0); }
   const double *g = p + 25;  // (cos, sin)(m phi0) pairs
   // brackets (aberrations.py:42-48) and the matching sin sums of dW/dphi (aberrations.py:78-98)
   Dual<N> B2 = dconst<N>(p[K_C10]), T2 = dconst<N>(0.0);
@@ -323,26 +368,22 @@ __device__ __forceinline__ void krivanek(const double *p, const Dual<N> &ax, con
   kriv_term(p[K_C52], 2.0, c2, s2, g[16], g[17], B6, T6);
   kriv_term(p[K_C54], 4.0, c4, s4, g[18], g[19], B6, T6);
   kriv_term(p[K_C56], 6.0, c6, s6, g[20], g[21], B6, T6);
-  const Dual<N> a2 = a * a;
-  const Dual<N> a3 = a2 * a;
-  const Dual<N> a4 = a2 * a2;
-  const Dual<N> a5 = a4 * a;
-  const Dual<N> a6 = a3 * a3;
-  // W (aberrations.py:51-60)
-  const double third = 1.0 / 3.0, sixth = 1.0 / 6.0;  // a3 / 3.0, a6 / 6.0 as multiplies (<= 1 ulp)
-  W = 0.5 * a2 * B2 + (a3 * third) * B3 + 0.25 * a4 * B4 + 0.2 * a4 * a * B5 + (a6 * sixth) * B6;
-  // grad (aberrations.py:63-108)
-  const Dual<N> dW_dalpha = a * B2 + a2 * B3 + a3 * B4 + a4 * B5 + a5 * B6;
-  Dual<N> dW_dphi = (0.5 * a2) * T2;
-  dW_dphi = dW_dphi + (a3 * third) * T3;
-  dW_dphi = dW_dphi + (0.25 * a4) * T4;
-  dW_dphi = dW_dphi + (0.2 * a4 * a) * T5;
-  dW_dphi = dW_dphi + (a6 * sixth) * T6;
-  const Dual<N> a_safe = dwhere_zero(a, 1e-30);
-  const Dual<N> inv_a = drecip(a_safe);
-  const Dual<N> inv_a2 = inv_a * inv_a;
-  dWx = dW_dalpha * (ax * inv_a) + dW_dphi * ((-ay) * inv_a2);
-  dWy = dW_dalpha * (ay * inv_a) + dW_dphi * (ax * inv_a2);
+  // radial weights a^n / n (aberrations.py:51-60); a3 / 3.0, a6 / 6.0 as multiplies (<= 1 ulp)
+  const Dual<N> a2 = kmul(a, a);
+  const Dual<N> a3 = kmul(a2, a);
+  const Dual<N> a4 = kmul(a2, a2);
+  const Dual<N> a5 = kmul(a4, a);
+  const Dual<N> w2 = kscale(a2, 0.5), w3 = kscale(a3, 1.0 / 3.0), w4 = kscale(a4, 0.25);
+  const Dual<N> w5 = kscale(a5, 0.2), w6 = kscale(kmul(a3, a3), 1.0 / 6.0);
+  // W (aberrations.py:51-60), dW/dalpha and dW/dphi (aberrations.py:63-98) as fused sums
+  W = kfma(w2, B2, kfma(w3, B3, kfma(w4, B4, kfma(w5, B5, kmul(w6, B6)))));
+  const Dual<N> dW_dalpha = kfma(a, B2, kfma(a2, B3, kfma(a3, B4, kfma(a4, B5, kmul(a5, B6)))));
+  const Dual<N> dW_dphi = kfma(w2, T2, kfma(w3, T3, kfma(w4, T4, kfma(w5, T5, kmul(w6, T6)))));
+  // (aberrations.py:100-108) with cos phi = ax / a, sin phi = ay / a:
+  //   dW/dx = dW/dalpha cos phi - dW/dphi sin phi / a ;  dW/dy = dW/dalpha sin phi + dW/dphi cos phi / a
+  const Dual<N> q = kmul(dW_dphi, ia);
+  dWx = kmul2(dW_dalpha, c1, q, s1, -1.0);
+  dWy = kmul2(dW_dalpha, s1, q, c1, 1.0);
 }
 
 // chain rule: r = f(ax, ay) given as Dual<2> (tangents w.r.t. ax, ay) -> tangents of width N
@@ -351,7 +392,7 @@ __device__ __forceinline__ Dual<N> dchain(const Dual<2> &r, const Dual<N> &ax, c
   Dual<N> o;
   o.v = r.v;
 #pragma unroll
-  for (int k = 0; k < (N > 0 ? N : 1); ++k) o.t[k] = N > 0 ? r.t[0] * ax.t[k] + r.t[1] * ay.t[k] : 0.0;
+  for (int k = 0; k < (N > 0 ? N : 1); ++k) o.t[k] = N > 0 ? fma(r.t[0], ax.t[k], r.t[1] * ay.t[k]) : 0.0;
   return o;
 }
 
@@ -596,12 +637,8 @@ int launch_trace(const tg_model *m, int64_t n, const tg_ray_in *in, double *cons
                  double *jac, cudaStream_t st) {
   bool kriv = false;
   for (int c = 0; c < m->n_comp; ++c) kriv |= (m->comp[c].op == TG_OP_KRIVANEK);
-#ifdef TG_TRACE_KRIV_TU
-  return launch_trace_k<NC, true>(m, n, in, out, jac, st);
-#else
-  return kriv ? tg_internal::launch_trace_kriv(NC, m, n, in, out, jac, st)
+  return kriv ? launch_trace_k<NC, true>(m, n, in, out, jac, st)
               : launch_trace_k<NC, false>(m, n, in, out, jac, st);
-#endif
 }
 
 // ------------------------------------------------------------------ parameter tangents
@@ -785,29 +822,6 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace
 
-#ifdef TG_TRACE_KRIV_TU
-// ---- second translation unit (FMA contraction on): only the Krivanek instantiations
-namespace tg_internal {
-int launch_trace_kriv(int nc, const tg_model *m, int64_t n, const tg_ray_in *in, double *const out[7],
-                      double *jac, cudaStream_t st) {
-  switch (nc) {
-    case 0: return launch_trace_k<0, true>(m, n, in, out, jac, st);
-    case 5: return launch_trace_k<5, true>(m, n, in, out, jac, st);
-    default: return launch_trace_k<7, true>(m, n, in, out, jac, st);
-  }
-}
-int launch_trace_grad_kriv(const tg_model *m, const void *grad_seeds, const tg_ray_in *in, int64_t n,
-                           double *const out[7], double *jac, cudaStream_t st) {
-  TraceOut o;
-  for (int f = 0; f < 7; ++f) o.ptr[f] = out ? out[f] : nullptr;
-  const long long blocks = (n + kTraceThreads - 1) / kTraceThreads;
-  trace_grad_kernel<true><<<(unsigned)blocks, kTraceThreads, 0, st>>>(
-      *m, *static_cast<const GradSeeds *>(grad_seeds), *in, (long long)n, o, jac);
-  return tg_launch_check("trace_grad_kernel");
-}
-}  // namespace tg_internal
-#else
-
 extern "C" int tg_trace_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in,
                             double *const out[7], double *jac, int jac_layout, void *stream) {
   TG_REQUIRE(model_host && in, "null model or input");
@@ -884,8 +898,10 @@ extern "C" int tg_trace_grad_f64(const tg_model *model_host, int64_t n, const tg
   const long long blocks = (n + kTraceThreads - 1) / kTraceThreads;
   TG_REQUIRE(blocks <= 0x7fffffffLL, "too many rays for one launch");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (kriv) return tg_internal::launch_trace_grad_kriv(model_host, &gs, in, n, out, jac, st);
-  trace_grad_kernel<false><<<(unsigned)blocks, kTraceThreads, 0, st>>>(*model_host, gs, *in, (long long)n, o, jac);
+  if (kriv)
+    trace_grad_kernel<true><<<(unsigned)blocks, kTraceThreads, 0, st>>>(*model_host, gs, *in, (long long)n, o, jac);
+  else
+    trace_grad_kernel<false><<<(unsigned)blocks, kTraceThreads, 0, st>>>(*model_host, gs, *in, (long long)n, o, jac);
   return tg_launch_check("trace_grad_kernel");
 }
 
@@ -902,4 +918,3 @@ extern "C" int tg_transfer_rays_f64(int64_t n, const double *rays, int m, const 
   transfer_rays_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(tm, n, rays, out);
   return tg_launch_check("transfer_rays_kernel");
 }
-#endif  // TG_TRACE_KRIV_TU
