@@ -424,6 +424,27 @@ def run_ours(args):
                          "bytes_per_ray": RAY_BYTES_ABCD, "peak_source": pk["source"]}}
         del rd, rplan
         torch.cuda.empty_cache()
+    # ---- higher-order derivatives (calculate_derivatives, run.py:119-147): orders 1..3 in one launch of
+    # the hyper-dual kernel; the dense (7,7), (7,7,7), (7,7,7,7) tensors per ray are the traffic
+    from temgymcore_b200.run import calculate_derivatives
+    JET_BYTES = 56 + 8 * (49 + 343 + 2401)
+    n_jet = 200_000
+    for label, which in (("jets_order3_c1", "c1"), ("jets_order3_c4", "c4")):
+        rng = np.random.default_rng(M.SEED + rank)
+        rr = M.random_rays(n_jet, rng) if which == "c1" else M.random_rays(n_jet, rng, scale=0.2e-9, slope=1e-9)
+        jmodel = M.readme_model() if which == "c1" else M.six_component_column()
+        rd = Ray(*(torch.as_tensor(getattr(rr, f), device=dev) for f in RAY_FIELDS))
+        jt = timed(lambda: calculate_derivatives(rd, jmodel, 3), max(3, args.steps // 2), 2, flush=False)
+        j_ms = max_over_ranks(float(np.mean(jt)))
+        gbs = n_jet * JET_BYTES / (j_ms * 1e-3) / 1e9
+        rays_section[label] = {
+            "workload": f"d1, d2, d3 of run_to_end w.r.t. the ray ({which} model), {n_jet} rays per GPU",
+            "rays_per_s": n_jet * world / (j_ms * 1e-3), "ms_per_call": j_ms, "rays_per_gpu": n_jet,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / pk["hbm_gbs"], "traffic": None, "bytes_per_ray": JET_BYTES,
+                         "kernel": "jets_kernel<3> (hyper-dual, one thread per sorted index triple)"}}
+        del rd
+        torch.cuda.empty_cache()
     # ray e2e through the host C ABI (pinned numpy in/out), 1e6 rays per rank
     rr = M.random_rays(1_000_000, np.random.default_rng(M.SEED + rank))
     rp = Ray(*(torch.as_tensor(getattr(rr, f)).pin_memory() for f in RAY_FIELDS))

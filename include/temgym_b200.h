@@ -130,6 +130,15 @@ int tg_trace_grad_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in
                       const int32_t ray_lane[7], const tg_seed *seeds, int n_seeds,
                       double *const out[7], double *jac, void *stream);
 
+/* ---- higher-order derivatives w.r.t. the input ray (calculate_derivatives, run.py:119-147) ---- */
+/* What `order` nested jax.jacfwd(run_to_end, argnums=0) calls produce, as dense tensors in Ray
+ * field order: d1 (n,7,7) = d out_f / d in_a, d2 (n,7,7,7) = d2 out_f / d in_a d in_b,
+ * d3 (n,7,7,7,7); order in 1..3 (TG_EUNSUPPORTED beyond), tensors above `order` may be NULL.  One
+ * kernel launch evaluates the model in hyper-dual arithmetic, one thread per sorted index tuple;
+ * out[f] (may be NULL) receives the output ray like tg_trace_f64.  Device pointers, async on stream. */
+int tg_trace_jets_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in, int order,
+                      double *const out[7], double *d1, double *d2, double *d3, void *stream);
+
 /* transfer_rays (transfer.py:6-54): out[n][k][i] = sum_j T[k][i][j] rays[n][j] for m <= 32
  * (already cumulative) 5x5 matrices given in HOST memory; rays (n,5), out (n,m,5) device fp64. */
 #define TG_MAX_TRANSFER 32

@@ -98,26 +98,180 @@ class Dual:
         return Dual(self.v ** p, self.t * (p * self.v ** (p - 1))[..., None])
 
 
+# --------------------------------------------------------------------------
+# truncated multivariate Taylor polynomials ("jets") -- restates nested jax.jacfwd
+# (run.py:119-147, calculate_derivatives) for derivative orders <= 3.  A Jet holds the Taylor
+# coefficients c_i (f(v0 + h) = sum_i c_i h^i, |i| <= order) of a quantity in the 7 input-ray
+# variables; d^i f = i! c_i.  Deliberately a different algorithm from the CUDA kernel's hyper-dual
+# numbers (and it follows the reference's hypot / arctan2 / cos / sin formulas literally).
+# --------------------------------------------------------------------------
+
+
+class JetSpace:
+    """Monomial bookkeeping for ``nvar`` variables up to total degree ``order``."""
+
+    def __init__(self, nvar: int, order: int):
+        self.nvar, self.order = nvar, order
+        monos = [()]
+        for deg in range(1, order + 1):
+            monos += [m for m in _multisets(nvar, deg)]
+        # a monomial is the sorted tuple of its variable indices (with repetition)
+        self.monos = monos
+        self.index = {m: k for k, m in enumerate(monos)}
+        pairs = []
+        for i, a in enumerate(monos):
+            for j, b in enumerate(monos):
+                if len(a) + len(b) <= order:
+                    pairs.append((i, j, self.index[tuple(sorted(a + b))]))
+        self.pairs = pairs
+
+
+def _multisets(nvar, deg, start=0):
+    if deg == 0:
+        yield ()
+        return
+    for v in range(start, nvar):
+        for rest in _multisets(nvar, deg - 1, v):
+            yield (v,) + rest
+
+
+class Jet:
+    """Taylor coefficients ``c`` of shape (N, n_monomials) in ``space``."""
+
+    __slots__ = ("c", "space")
+    __array_priority__ = 1000
+
+    def __init__(self, c, space):
+        self.c = np.asarray(c, dtype=np.float64)
+        self.space = space
+
+    @staticmethod
+    def const(v, like: "Jet") -> "Jet":
+        c = np.zeros(like.c.shape)
+        c[:, 0] = v
+        return Jet(c, like.space)
+
+    @staticmethod
+    def variable(v, var: int, space: JetSpace) -> "Jet":
+        v = np.asarray(v, dtype=np.float64)
+        c = np.zeros((v.shape[0], len(space.monos)))
+        c[:, 0] = v
+        if space.order >= 1:
+            c[:, space.index[(var,)]] = 1.0
+        return Jet(c, space)
+
+    def _lift(self, o):
+        return o if isinstance(o, Jet) else Jet.const(np.asarray(o, dtype=np.float64), self)
+
+    def __add__(self, o):
+        return Jet(self.c + self._lift(o).c, self.space)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return Jet(self.c - self._lift(o).c, self.space)
+
+    def __rsub__(self, o):
+        return Jet(self._lift(o).c - self.c, self.space)
+
+    def __neg__(self):
+        return Jet(-self.c, self.space)
+
+    def __mul__(self, o):
+        if not isinstance(o, Jet):
+            o = np.asarray(o, dtype=np.float64)
+            return Jet(self.c * (o[..., None] if o.ndim else o), self.space)
+        out = np.zeros(self.c.shape)
+        for i, j, k in self.space.pairs:
+            out[:, k] += self.c[:, i] * o.c[:, j]
+        return Jet(out, self.space)
+
+    __rmul__ = __mul__
+
+    def compose(self, taylor):
+        """g(self) from the Taylor coefficients ``taylor[k] = g^(k)(a0) / k!`` at a0 = self.c[:, 0]."""
+        n = Jet(self.c.copy(), self.space)
+        n.c[:, 0] = 0.0
+        out = Jet.const(taylor[0], self)
+        pw = None
+        for k in range(1, self.space.order + 1):
+            pw = n if pw is None else pw * n
+            out = out + pw * np.asarray(taylor[k])
+        return out
+
+    def recip(self):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            i = 1.0 / self.c[:, 0]
+            return self.compose([i, -i ** 2, i ** 3, -i ** 4])
+
+    def sqrt(self):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            a0 = self.c[:, 0]
+            s = np.sqrt(a0)
+            return self.compose([s, 0.5 / s, -0.125 / (s * a0), 0.0625 / (s * a0 * a0)])
+
+    def __truediv__(self, o):
+        if isinstance(o, Jet):
+            return self * o.recip()
+        o = np.asarray(o, dtype=np.float64)
+        return Jet(self.c / (o[..., None] if o.ndim else o), self.space)
+
+    def __rtruediv__(self, o):
+        return self.recip() * o
+
+    def __pow__(self, p):
+        if p == 2:
+            return self * self
+        raise NotImplementedError
+
+    def derivative_tensor(self, k: int) -> np.ndarray:
+        """Dense symmetric (N, nvar, ..., nvar) tensor of the k-th derivatives (i! c_i)."""
+        nv = self.space.nvar
+        out = np.zeros((self.c.shape[0],) + (nv,) * k)
+        import itertools
+        import math
+        for m in _multisets(nv, k):
+            fact = 1
+            for v in set(m):
+                fact *= math.factorial(m.count(v))
+            val = self.c[:, self.space.index[m]] * fact
+            for perm in set(itertools.permutations(m)):
+                out[(slice(None),) + perm] = val
+        return out
+
+
 def _sign(x):
     # jnp.sign: derivative is zero; sign(0) == 0  (components.py:556)
+    if isinstance(x, Jet):
+        return Jet.const(np.sign(x.c[:, 0]), x)
     if isinstance(x, Dual):
         return Dual(np.sign(x.v), np.zeros_like(x.t))
     return np.sign(x)
 
 
 def _cos(x):
+    if isinstance(x, Jet):
+        c, sn = np.cos(x.c[:, 0]), np.sin(x.c[:, 0])
+        return x.compose([c, -sn, -c / 2.0, sn / 6.0])
     if isinstance(x, Dual):
         return Dual(np.cos(x.v), -np.sin(x.v)[..., None] * x.t)
     return np.cos(x)
 
 
 def _sin(x):
+    if isinstance(x, Jet):
+        c, sn = np.cos(x.c[:, 0]), np.sin(x.c[:, 0])
+        return x.compose([sn, c, -sn / 2.0, -c / 6.0])
     if isinstance(x, Dual):
         return Dual(np.sin(x.v), np.cos(x.v)[..., None] * x.t)
     return np.sin(x)
 
 
 def _hypot(a, b):
+    if isinstance(a, Jet) or isinstance(b, Jet):
+        like = a if isinstance(a, Jet) else b
+        a, b = like._lift(a), like._lift(b)
+        return (a * a + b * b).sqrt()
     if isinstance(a, Dual) or isinstance(b, Dual):
         like = a if isinstance(a, Dual) else b
         a, b = Dual.lift(a, like), Dual.lift(b, like)
@@ -129,6 +283,14 @@ def _hypot(a, b):
 
 
 def _arctan2(y, x):
+    if isinstance(y, Jet) or isinstance(x, Jet):
+        like = y if isinstance(y, Jet) else x
+        y, x = like._lift(y), like._lift(x)
+        y0, x0 = y.c[:, 0], x.c[:, 0]
+        # rotate by -phi0: u = tan(phi - phi0) has no constant term, atan(u) = u - u^3/3 + O(u^5)
+        u = (y * x0 - x * y0) / (x * x0 + y * y0)
+        u.c[:, 0] = 0.0
+        return Jet.const(np.arctan2(y0, x0), like) + u - (u * u * u) * (1.0 / 3.0)
     if isinstance(y, Dual) or isinstance(x, Dual):
         like = y if isinstance(y, Dual) else x
         y, x = Dual.lift(y, like), Dual.lift(x, like)
@@ -141,6 +303,11 @@ def _arctan2(y, x):
 
 def _where_zero(a, eps):
     # jnp.where(a == 0, eps, a)  (aberrations.py:101-102)
+    if isinstance(a, Jet):
+        m = a.c[:, 0] == 0
+        c = np.where(m[:, None], 0.0, a.c)
+        c[:, 0] = np.where(m, eps, a.c[:, 0])
+        return Jet(c, a.space)
     if isinstance(a, Dual):
         m = a.v == 0
         return Dual(np.where(m, eps, a.v), np.where(m[..., None], 0.0, a.t))
@@ -418,6 +585,29 @@ def jacobian_run_to_end(ray, components: Sequence[Any]):
         J[:, i, :] = o.t
         vals.append(np.array(o.v))
     return Ray(*vals), J
+
+
+def calculate_derivatives(ray, components: Sequence[Any], order: int):
+    """``calculate_derivatives(ray, model, order)`` (run.py:119-147): the k-th entry is what ``order``
+    nested ``jax.jacfwd(run_to_end, argnums=0)`` calls produce, as a dense array
+    ``D_k[n, f, a_1, ..., a_k] = d^k out_f / d in_a1 ... d in_ak`` in ``RAY_FIELDS`` order
+    (the reference returns the same numbers as nested Ray pytrees: ``derivs[1].x.dx.dy``)."""
+    if not isinstance(ray, Ray):
+        ray = Ray.from_obj(ray)
+    r = ray.as_arrays()
+    n = r.x.shape[0]
+    space = JetSpace(7, order)
+    seeded = Ray(*(Jet.variable(getattr(r, f), i, space) for i, f in enumerate(RAY_FIELDS)))
+    out = run_to_end(seeded, components)
+    derivs = []
+    for k in range(1, order + 1):
+        Dk = np.zeros((n, 7) + (7,) * k)
+        for i, f in enumerate(RAY_FIELDS):
+            o = getattr(out, f)
+            if isinstance(o, Jet):
+                Dk[:, i] = o.derivative_tensor(k)
+        derivs.append(Dk)
+    return derivs
 
 
 def run_with_grads(ray, components: Sequence[Any], directions):

@@ -313,6 +313,55 @@ def ray_jacobian(ray, components: Sequence[Any], propagator: BasePropagator = Fr
     return RayJacobian(jac)
 
 
+def calculate_derivatives(ray, model: Sequence[Any], order: int):
+    """Successive forward-mode derivatives of ``run_to_end`` w.r.t. the ray (run.py:119-147).
+
+    Returns a list of ``order`` :class:`~temgymcore_b200.utils.RayDerivative` objects; entry ``k-1``
+    holds the dense tensor ``d^k out_f / d in_a1 ... d in_ak`` (shape ``batch + (7,) * (k + 1)``) that
+    ``k`` nested ``jax.jacfwd(run_to_end, argnums=0)`` calls produce, with the reference's nested
+    attribute access (``derivs[1].x.dx.dy``).  One launch of the hyper-dual CUDA kernel
+    (``tg_trace_jets_f64``) serves all orders up to 3; higher orders are not implemented."""
+    from .utils import RayDerivative
+    import torch
+    order = int(order)
+    if order < 1:
+        return []
+    if order > 3:
+        raise NotImplementedError("calculate_derivatives: the CUDA jet kernel implements orders 1..3")
+    lib = L.load()
+    cm = compile_model(model)
+    vals = [getattr(ray, f) for f in RAY_FIELDS]
+    kinds = [A.kind_of(v) for v in vals]
+    kind = max(kinds)
+    n = max(A.numel(v) for v in vals)
+    shape = next((A.shape_of(v) for v, k in zip(vals, kinds) if k != A.KIND_SCALAR), ())
+    dev = A.cuda_device_of(vals) or torch.device("cuda", A.current_device_index())
+    rin = L.tg_ray_in()
+    keep = []
+    for i, (v, k) in enumerate(zip(vals, kinds)):
+        if k == A.KIND_SCALAR:
+            rin.ptr[i] = None
+            rin.value[i] = A.to_float(v)
+        else:
+            t = A.to_device_f64(v, dev)
+            keep.append(t)
+            rin.ptr[i] = t.data_ptr()
+    tensors = [torch.empty((n,) + (7,) * (k + 1), dtype=torch.float64, device=dev) for k in range(1, order + 1)]
+    ptrs = [t.data_ptr() for t in tensors] + [None] * (3 - order)
+    with torch.cuda.device(dev):
+        L.check(lib.tg_trace_jets_f64(C.byref(cm), n, C.byref(rin), order, L.ptr_array([None] * 7),
+                                      ptrs[0], ptrs[1], ptrs[2], A.current_stream_ptr(dev)),
+                "tg_trace_jets_f64")
+
+    def finish(t, k):
+        t = t.reshape(shape + (7,) * (k + 1))
+        if kind == A.KIND_CUDA:
+            return t
+        return t.cpu() if kind == A.KIND_TORCH_CPU else t.cpu().numpy()
+
+    return [RayDerivative(finish(t, k), k) for k, t in enumerate(tensors, start=1)]
+
+
 def solve_model(ray, model: Sequence[Any], propagator: BasePropagator = FreeSpaceParaxial()):
     """Per-step 5x5 ABCD matrices, shape ``(2 * n_components, 5, 5)`` (run.py:150-179)."""
     from .utils import custom_jacobian_matrix

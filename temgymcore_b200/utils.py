@@ -36,6 +36,26 @@ class RayJacobian:
         raise AttributeError(name)
 
 
+class RayDerivative:
+    """Order-k derivative of the output ray w.r.t. the input ray: ``tensor[..., f, a_1, ..., a_k] =
+    d^k out_f / d in_a1 ... d in_ak`` in ``RAY_FIELDS`` order.  Attribute access peels one index at a
+    time like the reference's nested Ray pytrees: ``derivs[1].x.dx.dy`` (run.py:119-147)."""
+
+    def __init__(self, tensor, order, _depth=0):
+        self.tensor = tensor
+        self.order = order
+        self._depth = _depth
+
+    def __getattr__(self, name):
+        if name in RAY_FIELDS:
+            axis = self.tensor.ndim - (self.order + 1 - self._depth)
+            sub = self.tensor[(slice(None),) * axis + (RAY_FIELDS.index(name),)]
+            if self._depth == self.order:
+                return sub
+            return RayDerivative(sub, self.order, self._depth + 1)
+        raise AttributeError(name)
+
+
 def custom_jacobian_matrix(ray_jac):
     """-> ``(..., 5, 5)`` over ``[x, y, dx, dy, _one]`` (utils.py:34-43)."""
     m = ray_jac.matrix if isinstance(ray_jac, RayJacobian) else ray_jac

@@ -745,3 +745,60 @@ def test_ray_trace_plan_cuda_graph(torch_cuda):
     o3, j3 = RayTracePlan(dr, model, jacobian=False).run()
     assert j3 is None
     np.testing.assert_array_equal(to_np(o3.dy), to_np(run_to_end(dr, model).dy))
+
+
+# ------------------------------------------------------------------------------ higher-order derivatives
+@pytest.mark.parametrize("name", sorted(MODELS))
+def test_calculate_derivatives_parity(torch_cuda, name):
+    """calculate_derivatives (reference run.py:119-147, nested jacfwd): the hyper-dual CUDA kernel vs
+    the oracle's truncated-Taylor jets (pinned against sympy in tests/test_oracle_jets.py)."""
+    from temgymcore_b200.run import calculate_derivatives, ray_jacobian
+    n = 203
+    model = MODELS[name]()
+    rays = rays_for(name, n)
+    ref = O.calculate_derivatives(rays, model, 3)
+    for order in (1, 2, 3):
+        got = calculate_derivatives(ray_to_cuda(torch_cuda, rays), model, order)
+        assert len(got) == order
+        for k in range(order):
+            g = to_np(got[k].tensor)
+            assert g.shape == ref[k].shape == (n,) + (7,) * (k + 2)
+            # per output field: the tensors span 20+ orders of magnitude.  The Krivanek lens is
+            # evaluated algebraically on the GPU and through hypot / arctan2 / cos jets (1 / alpha^k
+            # factors that cancel against alpha^n) in the oracle: its third-order slab agrees to
+            # ~5e-10 of the slab's scale, everything else to 1e-10.
+            tol = 5e-9 if (name == "six_component_krivanek" and k == 2) else 1e-10
+            for f in range(7):
+                close(g[:, f], ref[k][:, f], rtol=tol)
+    # nested attribute access like the reference's Ray-of-Ray-of-Ray pytrees
+    d1, d2, d3 = got
+    np.testing.assert_array_equal(to_np(d2.x.dx.dy), to_np(d2.tensor)[:, 0, 2, 3])
+    np.testing.assert_array_equal(to_np(d3.pathlength.x.x.dy), to_np(d3.tensor)[:, 5, 0, 0, 3])
+    np.testing.assert_array_equal(to_np(d1.dx.x), to_np(d1.tensor)[:, 2, 0])
+    # symmetric in the differentiation indices
+    t3 = to_np(d3.tensor)
+    np.testing.assert_array_equal(t3, t3.transpose(0, 1, 3, 2, 4))
+    np.testing.assert_array_equal(t3, t3.transpose(0, 1, 4, 3, 2))
+    # first order == the ray kernel's full Jacobian
+    J = to_np(ray_jacobian(ray_to_cuda(torch_cuda, rays), model).matrix)
+    for f in range(7):
+        close(to_np(d1.tensor)[:, f], J[:, f], rtol=1e-12)
+
+
+def test_calculate_derivatives_host_inputs_and_limits(torch_cuda):
+    from temgymcore_b200.ray import Ray
+    from temgymcore_b200.run import calculate_derivatives
+    model = M.readme_model()
+    ray = Ray(x=0.1, y=0.2, dx=0.05, dy=-0.02, z=0.0, pathlength=0.0)      # README scalar ray
+    d1, d2 = calculate_derivatives(ray, model, 2)
+    assert isinstance(d2.tensor, np.ndarray) and d2.tensor.shape == (7, 7, 7)
+    ref = O.calculate_derivatives(O.Ray.from_obj(ray), model, 2)
+    close(d1.tensor, ref[0][0])
+    close(d2.tensor, ref[1][0])
+    assert abs(d2.x.dx.z - (-0.5)) < 1e-15   # d2 x_out / d dx d z = 0.5 * d(0.5 - z)/dz through the lens
+    rays = M.random_rays(17)
+    d = calculate_derivatives(rays, model, 3)
+    assert isinstance(d[2].tensor, np.ndarray) and d[2].tensor.shape == (17, 7, 7, 7, 7)
+    assert calculate_derivatives(rays, model, 0) == []
+    with pytest.raises(NotImplementedError):
+        calculate_derivatives(rays, model, 4)
