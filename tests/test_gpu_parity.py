@@ -459,7 +459,7 @@ def _tf32_split(torch, x):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 512), (256, 384, 1536), (200, 136, 1000),
-                                   (1024, 256, 4100), (77, 50, 36)])
+                                   (1024, 256, 4100), (77, 50, 36), (1536, 2304, 300), (1024, 2048, 2000)])
 def test_gemm_tf32x3_against_fp64(torch_cuda, M, N, K):
     import ctypes as C
     from temgymcore_b200 import _lib as L
