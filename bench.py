@@ -491,6 +491,37 @@ def run_ours(args):
     del data5
     torch.cuda.empty_cache()
 
+    # ---- C3: biprism two-beam interference, 1e5 beamlets on 2048x2048 (4.19e11 nominal evaluations).
+    # Separable -> tensor-core path (7 GEMM passes of 16 384 beamlets); the SFU path is run with
+    # envelope culling (each beamlet covers ~11 px: the dense SFU sum would take ~0.3 s) and must
+    # give the same image.  Weak scaling: every rank images its own frame.
+    c3 = None
+    if not args.skip_c3:
+        g3, model3 = M.biprism_case(100_000, (2048, 2048))
+        if world > 1:
+            g3 = replace(g3, x=g3.x + 1e-9 * rank)
+        g3d = replace(g3, **{f.name: torch.as_tensor(getattr(g3, f.name), device=dev) for f in fields(g3)})
+        keep3 = {}
+
+        def c3_tensor():
+            keep3["t"] = make_gaussian_image_device(g3d, model3, cull_bits=0, method="auto")
+
+        def c3_sfu():
+            keep3["s"] = make_gaussian_image_device(g3d, model3, method="sfu")     # default culling (40 bits)
+        t3 = max_over_ranks(float(np.mean(timed(c3_tensor, 3, 1, flush=False))))
+        s3 = max_over_ranks(float(np.mean(timed(c3_sfu, 3, 1, flush=False))))
+        diff = float((keep3["t"] - keep3["s"]).abs().pow(2).sum().sqrt() / keep3["t"].abs().pow(2).sum().sqrt())
+        ev3 = 100_000 * 2048 * 2048
+        c3 = {"workload": "C3 biprism two_beam_interference: 1e5 beamlets through Lens, Biprism, Lens onto 2048x2048",
+              "nominal_evals": ev3,
+              "tensor_path": {"ms_per_image": t3, "nominal_evals_per_s": ev3 * world / (t3 * 1e-3),
+                              "executed_tf32_tflops": 3 * 2.0 * 2048 * 4096 * 200_000 / (t3 * 1e-3) / 1e12},
+              "sfu_path_culled": {"ms_per_image": s3, "nominal_evals_per_s": ev3 * world / (s3 * 1e-3),
+                                  "cull_bits": 40},
+              "rel_l2_tensor_vs_culled_sfu": diff, "scaling": "weak"}
+        del keep3, g3d
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline (rank 0, N = 1): the numpy oracle port on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -520,7 +551,7 @@ def run_ours(args):
                        "phase": "fp64 setup -> 32-bit fixed-point turns; fp32 MUFU sin/cos/ex2; fp64 "
                                 "accumulation across 128-beamlet chunks"},
             "roofline": roofline, "roofline_sfu_path": roofline_sfu, "e2e": e2e, "gpu_launches": n_launch,
-            "rays": rays_section, "stem4d": stem4d, "clocks": clocks,
+            "rays": rays_section, "stem4d": stem4d, "c3_biprism": c3, "clocks": clocks,
         }
         if cpu:
             line["cpu_baseline"] = cpu
@@ -538,6 +569,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-c3", action="store_true", help="skip the C3 (1e5 beamlets x 2048^2) section")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch the step's kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--method", default="auto", choices=["auto", "sfu", "tensor"],

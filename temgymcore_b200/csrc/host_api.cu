@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <algorithm>
+#include <stdlib.h>
 #include "tg_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -289,6 +290,12 @@ extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t n
   auto up = [&](double *dst, const double *src, size_t cnt) {
     if (e == cudaSuccess && cnt) e = cudaMemcpyAsync(dst, src, cnt * 8, cudaMemcpyHostToDevice, s);
   };
+  static const bool timing = getenv("TG_HOST_TIMING") != nullptr;   // debug: per-phase times on stderr
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (timing) {
+    for (auto &x : ev) cudaEventCreate(&x);
+    cudaEventRecord(ev[0], s);
+  }
   for (int f = 0; f < 7; ++f) up(dr[f], rays[f], nb);
   up(damp, amplitude, nb);
   up(dw, waist_xy, 2 * nb);
@@ -299,9 +306,11 @@ extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t n
     tg_set_error("H2D copy: %s", cudaGetErrorString(e));
     rc = TG_ECUDA;
   }
+  if (timing) cudaEventRecord(ev[1], s);
   if (rc == TG_OK)
     rc = tg_make_gaussian_image_f64(model_host, nb, dr, damp, dw, drad, dwl, dth, px2m, H, W, row0, nrows, dout,
                                     out_is_c128, cull_bits, method, s);
+  if (timing) cudaEventRecord(ev[2], s);
   if (rc == TG_OK) {
     e = cudaMemcpyAsync(out, dout, npix * elt, cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) {
@@ -309,11 +318,20 @@ extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t n
       rc = TG_ECUDA;
     }
   }
+  if (timing) cudaEventRecord(ev[3], s);
   cudaFreeAsync(d, s);
   cudaError_t e2 = cudaStreamSynchronize(s);
   if (rc == TG_OK && e2 != cudaSuccess) {
     tg_set_error("stream sync: %s", cudaGetErrorString(e2));
     rc = TG_ECUDA;
+  }
+  if (timing) {
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, ev[0], ev[1]);
+    cudaEventElapsedTime(&b, ev[1], ev[2]);
+    cudaEventElapsedTime(&c, ev[2], ev[3]);
+    fprintf(stderr, "tg_make_gaussian_image_host: H2D %.3f ms, kernels %.3f ms, D2H %.3f ms\n", a, b, c);
+    for (auto &x : ev) cudaEventDestroy(x);
   }
   return rc;
 }

@@ -41,3 +41,10 @@ if what in ("stem4d", "all"):
     for _ in range(3):
         backproject_4dstem(data, None, sg, det, scan_range=(0, 65536), out=img, geometry=geo)
     torch.cuda.synchronize()
+if what in ("jets", "all"):
+    from temgymcore_b200.run import calculate_derivatives
+    rr = M.random_rays(200_000)
+    rd = Ray(*(torch.as_tensor(getattr(rr, f), device=dev) for f in RAY_FIELDS))
+    for _ in range(3):
+        d = calculate_derivatives(rd, M.readme_model(), 3)
+    torch.cuda.synchronize()
