@@ -139,6 +139,14 @@ int tg_trace_grad_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in
 int tg_trace_jets_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in, int order,
                       double *const out[7], double *d1, double *d2, double *d3, void *stream);
 
+/* W_krivanek / grad_W_krivanek (aberrations.py:51-108) on n slope pairs (device fp64): coeffs = the 25
+ * KrivanekCoeffs fields in declaration order followed by 11 (cos, sin)(m * phi0) pairs in the order
+ * (2,phi12) (1,phi21) (3,phi23) (2,phi32) (4,phi34) (1,phi41) (3,phi43) (5,phi45) (2,phi52) (4,phi54)
+ * (6,phi56) -- the parameter block of an AberratedLensKrivanek component minus its focal length.
+ * Any of W, dWx, dWy may be NULL. */
+int tg_krivanek_f64(int64_t n, const double *alpha_x, const double *alpha_y, const double coeffs[47],
+                    double *W, double *dWx, double *dWy, void *stream);
+
 /* transfer_rays (transfer.py:6-54): out[n][k][i] = sum_j T[k][i][j] rays[n][j] for m <= 32
  * (already cumulative) 5x5 matrices given in HOST memory; rays (n,5), out (n,m,5) device fp64. */
 #define TG_MAX_TRANSFER 32

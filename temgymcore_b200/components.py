@@ -108,17 +108,8 @@ class AberratedLensKrivanek(Lens):  # components.py:177-215
     coeffs: Any = field(default_factory=KrivanekCoeffs)
 
     def _tg_spec(self):
-        c = self.coeffs
-        if isinstance(c, dict):
-            c = KrivanekCoeffs(**c)
-        # harmonic terms (m, phi0) in the kernel's order; cos/sin(m*phi0) are model constants
-        terms = ((2, c.phi12), (1, c.phi21), (3, c.phi23), (2, c.phi32), (4, c.phi34), (1, c.phi41),
-                 (3, c.phi43), (5, c.phi45), (2, c.phi52), (4, c.phi54), (6, c.phi56))
-        trig = []
-        for m, ph0 in terms:
-            trig += [float(np.cos(m * _f(ph0))), float(np.sin(m * _f(ph0)))]
-        return (L.TG_OP_KRIVANEK, _f(self.z),
-                (_f(self.focal_length),) + tuple(_f(v) for v in c.as_tuple()) + tuple(trig))
+        from .aberrations import krivanek_param_block
+        return (L.TG_OP_KRIVANEK, _f(self.z), (_f(self.focal_length),) + krivanek_param_block(self.coeffs))
 
     def _tg_param_seeds(self, path):
         if path[0] == "coeffs":

@@ -789,6 +789,25 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ------------------------------------------------------------------ Krivanek aberration function
+// W_krivanek / grad_W_krivanek (aberrations.py:51-108) on arrays of slopes: the same value arithmetic
+// the ray kernel uses for AberratedLensKrivanek.  kp = 25 coefficients + 11 (cos, sin)(m phi0) pairs.
+struct KrivParams {
+  double p[47];
+};
+__global__ void __launch_bounds__(256)
+    krivanek_kernel(const __grid_constant__ KrivParams kp, long long n, const double *__restrict__ ax,
+                    const double *__restrict__ ay, double *__restrict__ W, double *__restrict__ dWx,
+                    double *__restrict__ dWy) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Dual<0> gx, gy, w;
+  krivanek<0>(kp.p, dconst<0>(ax[i]), dconst<0>(ay[i]), gx, gy, w);
+  if (W) W[i] = w.v;
+  if (dWx) dWx[i] = gx.v;
+  if (dWy) dWy[i] = gy.v;
+}
+
 // ------------------------------------------------------------------ K5
 __global__ void __launch_bounds__(256)
     m2p_kernel(long long n, const double *__restrict__ x, const double *__restrict__ y,
@@ -903,6 +922,18 @@ extern "C" int tg_trace_grad_f64(const tg_model *model_host, int64_t n, const tg
   else
     trace_grad_kernel<false><<<(unsigned)blocks, kTraceThreads, 0, st>>>(*model_host, gs, *in, (long long)n, o, jac);
   return tg_launch_check("trace_grad_kernel");
+}
+
+extern "C" int tg_krivanek_f64(int64_t n, const double *alpha_x, const double *alpha_y, const double coeffs[47],
+                               double *W, double *dWx, double *dWy, void *stream) {
+  TG_REQUIRE(n >= 0 && coeffs, "bad arguments");
+  if (n == 0) return TG_OK;
+  TG_REQUIRE(alpha_x && alpha_y, "null pointer");
+  KrivParams kp;
+  for (int k = 0; k < 47; ++k) kp.p[k] = coeffs[k];
+  krivanek_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(kp, n, alpha_x, alpha_y,
+                                                                                           W, dWx, dWy);
+  return tg_launch_check("krivanek_kernel");
 }
 
 extern "C" int tg_transfer_rays_f64(int64_t n, const double *rays, int m, const double *matrices_host,

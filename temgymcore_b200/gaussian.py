@@ -122,6 +122,27 @@ class GaussianRay(Ray):
         return type(self)(**{f.name: v1(getattr(self, f.name)) for f in fields(self)})
 
     @property
+    def q_inv(self):
+        """``(1/q_x, 1/q_y)`` on the principal axes: ``-1/R + i lambda / (pi w^2)``, ``R = inf`` giving a
+        purely imaginary value (gaussian.py:138-155).  O(n) input preparation on the arrays' own side
+        (numpy or torch); the rotated 2x2 ``Q_inv`` below comes from the CUDA kernel."""
+        w, Rc, wl = self.waist_xy, self.radii_of_curv, self.wavelength
+        if hasattr(w, "detach") or hasattr(Rc, "detach") or hasattr(wl, "detach"):
+            import torch
+            w, Rc = torch.as_tensor(w, dtype=torch.float64), torch.as_tensor(Rc, dtype=torch.float64)
+            wl = torch.as_tensor(wl, dtype=torch.float64, device=w.device)
+            im = wl[..., None] / (torch.pi * w ** 2) if wl.ndim else wl / (torch.pi * w ** 2)
+            re = torch.where(torch.isinf(Rc), torch.zeros_like(Rc), -1.0 / Rc)
+            q = torch.complex(re, im)
+        else:
+            w, Rc, wl = np.asarray(w, float), np.asarray(Rc, float), np.asarray(wl, float)
+            wl = wl[..., None] if wl.ndim else wl
+            with np.errstate(divide="ignore"):
+                re = np.where(np.isinf(Rc), 0.0, -1.0 / Rc)
+            q = re + 1j * wl / (np.pi * w ** 2)          # the reference's expression, term for term
+        return q[..., 0], q[..., 1]
+
+    @property
     def Q_inv(self):
         """(n, 2, 2) complex ``R diag(1/q_x, 1/q_y) R^T`` (gaussian.py:138-177), computed by
         ``tg_gaussian_qinv_f64``; a CUDA complex128 tensor."""
@@ -316,6 +337,34 @@ def beamlet_polynomials(gaussian_rays: GaussianRay, model):
 
 
 # ------------------------------------------------------------------------------ public API
+# small einsum helpers with the reference's index conventions (per beamlet: the reference vmaps them)
+def _einsum(spec, *ops):
+    if any(hasattr(o, "detach") for o in ops):
+        import torch
+        return torch.einsum(spec, *ops)
+    return np.einsum(spec, *ops)
+
+
+def matrix_vector_mul(M, v):                  # gaussian.py:180-187
+    return _einsum("ij,j->i", M, v)
+
+
+def matrix_matrix_mul(M1, M2):                # gaussian.py:190-197
+    return _einsum("ij,jk->ik", M1, M2)
+
+
+def matrix_quadratic_mul(v, M):               # gaussian.py:200-207
+    return _einsum("i,ij,j->", v, M, v)
+
+
+def matrix_linear_mul(v, M, w):               # gaussian.py:210-218
+    return _einsum("i,ij,nj->n", v, M, w)
+
+
+def matrix_matrix_matrix_mul(M1, M2, M3):     # gaussian.py:221-222
+    return _einsum("nij,njk,npk->nip", M1, M2, M3)
+
+
 def Qinv_ABCD(Qinv, A_, B, C_, D):
     """``solve(A + B Qinv, C + D Qinv)`` (gaussian.py:92-96) -- tiny host helper (numpy);
     inside the field sum this is evaluated per beamlet by the coefficient kernel."""

@@ -114,3 +114,91 @@ def random_coords(num: int):
         keep = np.sqrt((yx ** 2).sum(axis=1)) < 1
         if keep.sum() > 0:
             return yx[keep, :]
+
+
+# ------------------------------------------------------------------------------------------
+# Host-side helpers of the reference's utils.py that sit beside the hot path (numpy, like the
+# reference; ``xp`` may be any numpy-compatible namespace, e.g. ``torch`` is NOT one -- pass arrays
+# of the namespace you choose).
+
+
+def multi_cumsum_inplace(values, partitions, start):
+    """Cumulative sums restarted per partition, in place (utils.py:46-80) -- including the reference's
+    restart rule (the running counter is compared BEFORE it is advanced, so partition k restarts k
+    elements late); ``concentric_rings`` depends on exactly this."""
+    part_idx, part_count = 0, 0
+    current = partitions[0]
+    values[0] = start
+    for i in range(1, len(values)):
+        if current == part_count:
+            part_count = 0
+            part_idx += 1
+            current = partitions[part_idx]
+            values[i] = start
+        else:
+            values[i] += values[i - 1]
+            part_count += 1
+
+
+def inplace_sum(px_y, px_x, mask, frame, buffer):
+    """``buffer[py, px] += frame`` for masked, in-bounds entries (utils.py:83-114), host arrays.
+    (The CUDA histogram ``Grid.into_image`` / ``tg_into_image_i64`` is the device counterpart.)"""
+    import numpy as np
+    py, px = np.asarray(px_y), np.asarray(px_x)
+    h, w = buffer.shape
+    ok = np.asarray(mask, dtype=bool) & (py >= 0) & (py < h) & (px >= 0) & (px < w)
+    np.add.at(buffer, (py[ok], px[ok]), np.asarray(frame)[ok])
+
+
+def try_ravel(val):
+    """``val.ravel()`` when it has one, else ``val`` (utils.py:208-225)."""
+    try:
+        return val.ravel()
+    except AttributeError:
+        return val
+
+
+def try_reshape(val, maybe_has_shape):
+    """``val.reshape(maybe_has_shape.shape)`` when possible, else ``val`` (utils.py:228-245)."""
+    try:
+        return val.reshape(maybe_has_shape.shape)
+    except AttributeError:
+        return val
+
+
+def FresnelPropagator(u1, L, wavelength, z, xp=None):
+    """Paraxial free-space propagation of a sampled field over ``z`` by the transfer-function method
+    (utils.py:248-265): the validator the reference's wave-optics tests compare the beamlet sum with.
+    ``L`` is the side length of the (square-pixel) window; the pixel pitch is ``L / rows``."""
+    if xp is None:
+        import numpy as xp
+    rows, cols = u1.shape
+    pitch = L / rows
+    fx = xp.fft.fftfreq(cols, d=pitch)
+    fy = xp.fft.fftfreq(rows, d=pitch)
+    FX, FY = xp.meshgrid(fx, fy)
+    H = xp.exp(-1j * xp.pi * wavelength * z * (FX ** 2 + FY ** 2))
+    return xp.fft.ifft2(H * xp.fft.fft2(u1))
+
+
+def fresnel_lens_imaging_solution(E0, Y, X, ps, lambda0, z1, f, z2):
+    """Fresnel propagation over z1, thin-lens phase, Fresnel propagation over z2 (utils.py:268-275)."""
+    import numpy as np
+    k = 2 * np.pi / lambda0
+    L = E0.shape[0] * ps
+    at_lens = FresnelPropagator(E0, L, lambda0, z1) * np.exp((-1j * k) / (2 * f) * (X ** 2 + Y ** 2))
+    return FresnelPropagator(at_lens, L, lambda0, z2)
+
+
+def zero_phase(u, idx_x, idx_y):
+    """Rotate the global phase so that ``u[idx_x, idx_y]`` is real and positive, in place
+    (utils.py:278-282)."""
+    import numpy as np
+    u *= np.exp(-1j * np.angle(u[idx_x, idx_y]))
+    return u
+
+
+def make_aperture(X, Y, aperture_ratio=0.1):
+    """Boolean disc mask of radius ``aperture_ratio * max|X|`` (utils.py:285-294)."""
+    import numpy as np
+    return X ** 2 + Y ** 2 < (np.max(np.abs(X)) * aperture_ratio) ** 2

@@ -802,3 +802,33 @@ def test_calculate_derivatives_host_inputs_and_limits(torch_cuda):
     assert calculate_derivatives(rays, model, 0) == []
     with pytest.raises(NotImplementedError):
         calculate_derivatives(rays, model, 4)
+
+
+def test_krivanek_functions(torch_cuda):
+    """W_krivanek / grad_W_krivanek (aberrations.py:51-108) called directly: the ray kernel's device code
+    on arrays of slopes vs the oracle's literal hypot / arctan2 / cos restatement."""
+    from temgymcore_b200.aberrations import KrivanekCoeffs, W_krivanek, grad_W_krivanek
+    rng = np.random.default_rng(M.SEED)
+    p = KrivanekCoeffs(C10=0.3, C12=0.2, phi12=0.4, C21=1.5, phi21=-0.3, C23=0.7, phi23=1.1, C30=2.0,
+                       C32=0.5, phi32=0.2, C34=-0.4, phi34=0.9, C41=0.3, phi41=1.3, C43=0.2, phi43=-0.8,
+                       C45=0.6, phi45=0.1, C50=1.1, C52=-0.2, phi52=0.7, C54=0.35, phi54=-1.2, C56=0.15, phi56=0.5)
+    ax, ay = rng.uniform(-0.3, 0.3, 1000), rng.uniform(-0.3, 0.3, 1000)
+    gx, gy = grad_W_krivanek(ax, ay, p)
+    rx, ry = O.grad_W_krivanek(ax, ay, p)
+    close(gx, rx)
+    close(gy, ry)
+    alpha, phi = np.hypot(ax, ay), np.arctan2(ay, ax)
+    close(W_krivanek(alpha, phi, p), O.W_krivanek(alpha, phi, p))
+    # gradient is consistent with W: central differences
+    h = 1e-6
+    Wp = W_krivanek(np.hypot(ax + h, ay), np.arctan2(ay, ax + h), p)
+    Wm = W_krivanek(np.hypot(ax - h, ay), np.arctan2(ay, ax - h), p)
+    np.testing.assert_allclose((Wp - Wm) / (2 * h), gx, rtol=1e-6, atol=1e-8)
+    # CUDA tensors in -> CUDA tensors out; scalars -> floats
+    tx = torch_cuda.as_tensor(ax, device="cuda")
+    ty = torch_cuda.as_tensor(ay, device="cuda")
+    dgx, _ = grad_W_krivanek(tx, ty, p)
+    assert dgx.is_cuda
+    np.testing.assert_array_equal(to_np(dgx), gx)
+    sgx, sgy = grad_W_krivanek(0.1, -0.2, p)
+    assert isinstance(sgx, float) and abs(sgx - O.grad_W_krivanek(np.array([0.1]), np.array([-0.2]), p)[0][0]) < 1e-14

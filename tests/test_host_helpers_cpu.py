@@ -4,6 +4,8 @@ ray samplers / sources (reference utils.py:117-205, source.py:58-188), 5x5 matri
 import numpy as np
 import pytest
 
+from oracle import temgym_oracle as O
+
 from temgymcore_b200.source import ParallelBeam, PointSource
 from temgymcore_b200.transfer import accumulate_matrices, accumulate_matrices_cumulative
 from temgymcore_b200.utils import concentric_rings, fibonacci_spiral, random_coords
@@ -98,3 +100,62 @@ def test_param_refs():
     assert r.params._one._build() == (r, "_one")
     assert {(r, "x"): 1}[(r, "x")] == 1          # rays hash by identity (usable as dict keys)
     assert lens.new_with(focal_length=2.0).focal_length == 2.0
+
+
+def test_reference_utils_helpers():
+    """Host-side helpers of the reference's utils.py / gaussian.py that sit beside the hot path."""
+    from temgymcore_b200 import utils as U
+    from temgymcore_b200.gaussian import (matrix_linear_mul, matrix_matrix_matrix_mul, matrix_matrix_mul,
+                                          matrix_quadratic_mul, matrix_vector_mul)
+    # multi_cumsum_inplace: the reference's restart rule (utils.py:69-80): partition k restarts k elements late
+    v = np.ones(9)
+    U.multi_cumsum_inplace(v, np.array([2, 3, 4]), 0.0)
+    np.testing.assert_array_equal(v, [0, 1, 2, 0, 1, 2, 3, 0, 1])
+    # inplace_sum: mask + bounds (utils.py:83-114)
+    buf = np.zeros((3, 3), np.float32)
+    U.inplace_sum(np.array([0, 1, 5, 1, -1]), np.array([0, 1, 1, 1, 0]), np.array([1, 1, 1, 0, 1], bool),
+                  np.array([1, 2, 3, 4, 5], np.float32), buf)
+    assert buf[0, 0] == 1 and buf[1, 1] == 2 and buf.sum() == 3
+    assert U.try_ravel(3.0) == 3.0 and U.try_ravel(np.zeros((2, 2))).shape == (4,)
+    assert U.try_reshape(np.arange(4), np.zeros((2, 2))).shape == (2, 2) and U.try_reshape(np.arange(4), 1.0).shape == (4,)
+    # FresnelPropagator: energy conserving, identity at z = 0, Gaussian keeps its centre
+    n, L, wl = 128, 2e-3, 500e-9
+    x = (np.arange(n) - n // 2) * (L / n)
+    X, Y = np.meshgrid(x, x)
+    u0 = np.exp(-(X ** 2 + Y ** 2) / (2e-4) ** 2).astype(complex)
+    np.testing.assert_allclose(U.FresnelPropagator(u0, L, wl, 0.0), u0, atol=1e-12)
+    u1 = U.FresnelPropagator(u0, L, wl, 0.05)
+    np.testing.assert_allclose(np.sum(np.abs(u1) ** 2), np.sum(np.abs(u0) ** 2), rtol=1e-10)
+    assert np.unravel_index(np.argmax(np.abs(u1)), u1.shape) == (n // 2, n // 2)
+    z = U.zero_phase(u1.copy(), n // 2, n // 2)
+    assert abs(np.angle(z[n // 2, n // 2])) < 1e-12
+    m = U.make_aperture(X, Y, aperture_ratio=0.5)
+    assert m[n // 2, n // 2] and not m[0, 0]
+    two_f = U.fresnel_lens_imaging_solution(u0, Y, X, L / n, wl, 0.1, 0.05, 0.1)   # 2f-2f imaging of a centred,
+    np.testing.assert_allclose(np.abs(two_f), np.abs(u0), atol=0.05)               # symmetric beam: |image| = |object|
+    # einsum helpers keep the reference's (per-beamlet) index conventions (gaussian.py:180-222)
+    rng = np.random.default_rng(0)
+    Mx, v, w = rng.normal(size=(2, 2)), rng.normal(size=2), rng.normal(size=(5, 2))
+    np.testing.assert_allclose(matrix_vector_mul(Mx, v), Mx @ v)
+    np.testing.assert_allclose(matrix_matrix_mul(Mx, Mx), Mx @ Mx)
+    np.testing.assert_allclose(matrix_quadratic_mul(v, Mx), v @ Mx @ v)
+    np.testing.assert_allclose(matrix_linear_mul(v, Mx, w), w @ (Mx.T @ v))
+    B = rng.normal(size=(3, 2, 2))
+    np.testing.assert_allclose(matrix_matrix_matrix_mul(B, B, B), np.einsum("nij,njk,npk->nip", B, B, B))
+
+
+def test_gaussian_ray_q_inv_property():
+    from temgymcore_b200.gaussian import GaussianRay
+    n = 4
+    wl = np.full(n, 2e-12)
+    w = np.array([[1e-9, 2e-9]] * n)
+    Rc = np.array([[np.inf, 0.5]] * n)
+    g = GaussianRay(x=np.zeros(n), y=np.zeros(n), dx=np.zeros(n), dy=np.zeros(n), z=np.zeros(n),
+                    pathlength=np.zeros(n), _one=np.ones(n), amplitude=np.ones(n), waist_xy=w,
+                    radii_of_curv=Rc, wavelength=wl, theta=np.zeros(n))
+    qx, qy = g.q_inv
+    np.testing.assert_allclose(qx, 1j * wl / (np.pi * 1e-18))                       # R = inf: purely imaginary
+    np.testing.assert_allclose(qy, -2.0 + 1j * wl / (np.pi * 4e-18))
+    ox, oy = O.gaussian_q_inv(w, Rc, wl)
+    np.testing.assert_array_equal(qx, ox)
+    np.testing.assert_array_equal(qy, oy)
