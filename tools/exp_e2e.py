@@ -17,3 +17,10 @@ for _ in range(10):
     make_gaussian_image_host(gp, model, cull_bits=0, device=0)
     ts.append((time.perf_counter() - t0) * 1e3)
 print("wall ms per call: median %.3f min %.3f" % (np.median(ts), min(ts)))
+import cProfile, pstats
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(200):
+    make_gaussian_image_host(gp, model, cull_bits=0, device=0)
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
