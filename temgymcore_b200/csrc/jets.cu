@@ -171,27 +171,51 @@ __device__ __forceinline__ void hkrivanek(const double *p, const HD<P> &ax, cons
   if (u5) { c5 = c4 * c1 - s4 * s1; s5 = s4 * c1 + c4 * s1; }
   if (u6) { c6 = c3 * c3 - s3 * s3; s6 = (c3 * s3) * 2.0; }
   const double *g = p + 25;                           // (cos, sin)(m phi0) pairs
-  S B2 = hconst<P>(p[K_C10]), T2 = hconst<P>(0.0);
-  hterm(p[K_C12], 2.0, c2, s2, g[0], g[1], B2, T2);
-  S B3 = hconst<P>(0.0), T3 = B3;
-  hterm(p[K_C21], 1.0, c1, s1, g[2], g[3], B3, T3);
-  hterm(p[K_C23], 3.0, c3, s3, g[4], g[5], B3, T3);
-  S B4 = hconst<P>(p[K_C30]), T4 = hconst<P>(0.0);
-  hterm(p[K_C32], 2.0, c2, s2, g[6], g[7], B4, T4);
-  hterm(p[K_C34], 4.0, c4, s4, g[8], g[9], B4, T4);
-  S B5 = hconst<P>(0.0), T5 = B5;
-  hterm(p[K_C41], 1.0, c1, s1, g[10], g[11], B5, T5);
-  hterm(p[K_C43], 3.0, c3, s3, g[12], g[13], B5, T5);
-  hterm(p[K_C45], 5.0, c5, s5, g[14], g[15], B5, T5);
-  S B6 = hconst<P>(p[K_C50]), T6 = hconst<P>(0.0);
-  hterm(p[K_C52], 2.0, c2, s2, g[16], g[17], B6, T6);
-  hterm(p[K_C54], 4.0, c4, s4, g[18], g[19], B6, T6);
-  hterm(p[K_C56], 6.0, c6, s6, g[20], g[21], B6, T6);
-  const S a2 = a * a, a3 = a2 * a, a4 = a2 * a2, a5 = a4 * a;
-  const S w2 = a2 * 0.5, w3 = a3 * (1.0 / 3.0), w4 = a4 * 0.25, w5 = a5 * 0.2, w6 = (a3 * a3) * (1.0 / 6.0);
-  W = w2 * B2 + w3 * B3 + w4 * B4 + w5 * B5 + w6 * B6;
-  const S dWa = a * B2 + a2 * B3 + a3 * B4 + a4 * B5 + a5 * B6;
-  const S q = (w2 * T2 + w3 * T3 + w4 * T4 + w5 * T5 + w6 * T6) * ia;
+  // Radial orders n = 2..6 are folded into W, dW/dalpha and dW/dphi one at a time (aberrations.py:51-98)
+  // so that a bracket B_n / T_n dies as soon as it is used: the live set stays at three accumulators,
+  // the phasor powers and one power of alpha (order 3 needs 8 doubles per quantity).
+  S an = a;                                           // alpha^(n-1)
+  S dWa = hconst<P>(0.0), q = dWa;
+  W = dWa;
+  auto fold = [&](const S &Bn, const S &Tn, double inv_n) {
+    dWa = dWa + an * Bn;                              // alpha^(n-1) B_n
+    const S wn = (an * a) * inv_n;                    // alpha^n / n
+    W = W + wn * Bn;
+    q = q + wn * Tn;
+    an = an * a;
+  };
+  {
+    S B = hconst<P>(p[K_C10]), T = hconst<P>(0.0);
+    hterm(p[K_C12], 2.0, c2, s2, g[0], g[1], B, T);
+    fold(B, T, 0.5);
+  }
+  {
+    S B = hconst<P>(0.0), T = B;
+    hterm(p[K_C21], 1.0, c1, s1, g[2], g[3], B, T);
+    hterm(p[K_C23], 3.0, c3, s3, g[4], g[5], B, T);
+    fold(B, T, 1.0 / 3.0);
+  }
+  {
+    S B = hconst<P>(p[K_C30]), T = hconst<P>(0.0);
+    hterm(p[K_C32], 2.0, c2, s2, g[6], g[7], B, T);
+    hterm(p[K_C34], 4.0, c4, s4, g[8], g[9], B, T);
+    fold(B, T, 0.25);
+  }
+  {
+    S B = hconst<P>(0.0), T = B;
+    hterm(p[K_C41], 1.0, c1, s1, g[10], g[11], B, T);
+    hterm(p[K_C43], 3.0, c3, s3, g[12], g[13], B, T);
+    hterm(p[K_C45], 5.0, c5, s5, g[14], g[15], B, T);
+    fold(B, T, 0.2);
+  }
+  {
+    S B = hconst<P>(p[K_C50]), T = hconst<P>(0.0);
+    hterm(p[K_C52], 2.0, c2, s2, g[16], g[17], B, T);
+    hterm(p[K_C54], 4.0, c4, s4, g[18], g[19], B, T);
+    hterm(p[K_C56], 6.0, c6, s6, g[20], g[21], B, T);
+    fold(B, T, 1.0 / 6.0);
+  }
+  q = q * ia;
   dWx = dWa * c1 - q * s1;
   dWy = dWa * s1 + q * c1;
 }
@@ -265,19 +289,17 @@ __global__ void __launch_bounds__(Tuples<P>::N * JetCfg<P>::kRays, KRIV ? 2 : (P
   constexpr int NT = Tuples<P>::N, R = JetCfg<P>::kRays, NTHREADS = NT * R;
   extern __shared__ __align__(16) double s_t[];        // [order][ray][7^(order+1)]
   double *s_d1 = s_t, *s_d2 = s_d1 + R * 49, *s_d3 = s_d2 + (P >= 2 ? R * 343 : 0);
-  for (int k = threadIdx.x; k < R * jet_doubles_per_ray<P>(); k += NTHREADS) s_t[k] = 0.0;
   const int rl = threadIdx.x / NT;
   const int tup = threadIdx.x - rl * NT;
   const long long i0 = (long long)blockIdx.x * R;
   const long long i = i0 + rl;
   const bool active = i < n;
-  __syncthreads();
+  int var[P];
+  S st[7];
 
   if (active) {
-    int var[P];
     Tuples<P>::decode(tup, var);
     auto ld = [&](int f) -> double { return in.ptr[f] ? __ldg(in.ptr[f] + i) : in.value[f]; };
-    S st[7];
 #pragma unroll
     for (int f = 0; f < 7; ++f) st[f] = hconst<P>(ld(f));
 #pragma unroll
@@ -302,9 +324,10 @@ __global__ void __launch_bounds__(Tuples<P>::N * JetCfg<P>::kRays, KRIV ? 2 : (P
       switch (cm.op) {
         case TG_OP_LENS:
         case TG_OP_THICKLENS: {   // components.py:161-174, 431-447
-          const double f = cm.p[0];
-          const S ndx = (-x) / f + dx, ndy = (-y) / f + dy;
-          pl = pl - (x * x + y * y) / (2.0 * f);
+          // one reciprocal instead of 24 fp64 divisions (<= 1 ulp per coefficient; parity is 1e-10)
+          const double inv_f = 1.0 / cm.p[0];
+          const S ndx = dx - x * inv_f, ndy = dy - y * inv_f;
+          pl = pl - (x * x + y * y) * (0.5 * inv_f);
           dx = ndx;
           dy = ndy;
           one = one * 1.0;
@@ -339,11 +362,12 @@ __global__ void __launch_bounds__(Tuples<P>::N * JetCfg<P>::kRays, KRIV ? 2 : (P
         case TG_OP_KRIVANEK: if constexpr (KRIV) {    // components.py:192-215
           const double inv_f = 1.0 / cm.p[0];
           const S idx = (-x) * inv_f + dx, idy = (-y) * inv_f + dy;
+          pl = pl - (x * x + y * y) * (0.5 * inv_f);
           S dWx, dWy, W;
           hkrivanek<P>(cm.p + 1, idx, idy, dWx, dWy, W);
           dx = idx - dWx * inv_f;
           dy = idy - dWy * inv_f;
-          pl = pl - (x * x + y * y) * (0.5 * inv_f) + W * inv_f;
+          pl = pl + W * inv_f;
           one = one * 1.0;
         } break;
         default:
@@ -351,6 +375,10 @@ __global__ void __launch_bounds__(Tuples<P>::N * JetCfg<P>::kRays, KRIV ? 2 : (P
       }
     }
 
+  }
+  for (int k = threadIdx.x; k < R * jet_doubles_per_ray<P>(); k += NTHREADS) s_t[k] = 0.0;
+  __syncthreads();
+  if (active) {
     // ---- outputs.  Sorted tuple (v0 <= v1 <= v2) in live-variable numbering; w_u = Ray field index.
     int w[P];
 #pragma unroll
