@@ -689,6 +689,22 @@ def test_stem4d_rounding_ties(torch_cuda):
             np.testing.assert_array_equal(got.astype(np.float64), ref, err_msg=f"{kernel} ps_d={ps_d} off={off}")
 
 
+@pytest.mark.parametrize("det_shape,z_src", [((16, 512), -4e-7), ((96, 8), -2e-6), ((40, 136), -1e-6), ((8, 2048), -1e-7)])
+def test_stem4d_strip_layouts(torch_cuda, det_shape, z_src):
+    """Detector widths that exercise the strip bookkeeping of the DDA kernels: more strips per row than
+    lanes (512 / 2048 columns), one strip per row (8 columns), a ragged strip count (136 columns)."""
+    from temgymcore_b200.stem4d import backproject_4dstem, system_geometry
+    model_fn, scan_grid, detector = M.stem4d_case((5, 4), det_shape, z_src=z_src)
+    geo = system_geometry(model_fn, scan_grid, detector)
+    data = torch_cuda.randint(0, 9, (5, 4) + det_shape, device="cuda", dtype=torch_cuda.int32).to(torch_cuda.float32)
+    ref = backproject_4dstem(data, None, scan_grid, detector, geometry=geo, kernel="stepwise").cpu().numpy()
+    assert ref.sum() > 0
+    for k in ("auto", "dda", "affine"):
+        np.testing.assert_array_equal(backproject_4dstem(data, None, scan_grid, detector, geometry=geo,
+                                                         kernel=k).cpu().numpy(), ref, err_msg=k)
+    np.testing.assert_array_equal(ref.astype(np.float64), O.stem4d_backproject(data.cpu().numpy(), model_fn, scan_grid, detector))
+
+
 def test_stem4d_large_frames_dda_equals_stepwise(torch_cuda):
     """C5-shaped frames (256 x 256 detector, 13 deg scan rotation, descan error) on a 24 x 20 scan: the
     integer DDA kernel, the guarded affine kernel and the step-wise kernel give the same image for
