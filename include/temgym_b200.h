@@ -147,6 +147,10 @@ int tg_trace_jets_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in
 int tg_krivanek_f64(int64_t n, const double *alpha_x, const double *alpha_y, const double coeffs[47],
                     double *W, double *dWx, double *dWy, void *stream);
 
+/* fibonacci_spiral(nb_samples, radius, alpha) (utils.py:297-325) written to device arrays x, y: the
+ * beamlet-centre sampler of the aperture / biprism examples, generated on the GPU. */
+int tg_fibonacci_spiral_f64(int64_t n, double radius, double alpha, double *x, double *y, void *stream);
+
 /* transfer_rays (transfer.py:6-54): out[n][k][i] = sum_j T[k][i][j] rays[n][j] for m <= 32
  * (already cumulative) 5x5 matrices given in HOST memory; rays (n,5), out (n,m,5) device fp64. */
 #define TG_MAX_TRANSFER 32

@@ -282,6 +282,34 @@ int tg_wave_numbers(int64_t nb, const double *wavelength, const double *pathleng
   return tg_launch_check("wave_kernel");
 }
 
+// fibonacci_spiral (reference utils.py:297-325): beamlet centres on a disc, generated where they are
+// consumed (no host staging for 1e6-beamlet runs).  Same fp64 formula as the host sampler.
+namespace {
+__global__ void __launch_bounds__(256)
+    fibonacci_kernel(long long n, double radius, double np_boundary, double *__restrict__ x, double *__restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double ga = 3.14159265358979323846 * (3.0 - sqrt(5.0));
+  const double fi = (double)i, fn = (double)n;
+  double rr = (fi > fn - (np_boundary + 1.0)) ? radius
+                                              : radius * sqrt((fi + 0.5) / (fn - 0.5 * (np_boundary + 1.0)));
+  if (i == 0) rr = 0.0;
+  double sn, cs;
+  sincos(fi * ga, &sn, &cs);
+  x[i] = rr * cs;
+  y[i] = rr * sn;
+}
+}  // namespace
+
+extern "C" int tg_fibonacci_spiral_f64(int64_t n, double radius, double alpha, double *x, double *y, void *stream) {
+  TG_REQUIRE(n >= 0, "negative n");
+  if (n == 0) return TG_OK;
+  TG_REQUIRE(x && y, "null pointer");
+  const double np_boundary = nearbyint(alpha * sqrt((double)n));    // np.round: half to even
+  fibonacci_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, radius, np_boundary, x, y);
+  return tg_launch_check("fibonacci_kernel");
+}
+
 extern "C" int tg_wave_numbers_f64(int64_t nb, const double *wavelength, const double *pathlength,
                                    double *k, double *phase_offset, void *stream) {
   TG_REQUIRE(nb >= 0, "negative nb");

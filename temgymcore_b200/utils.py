@@ -67,9 +67,27 @@ def custom_jacobian_matrix(ray_jac):
     return m[..., idx, :][..., :, idx]
 
 
-def fibonacci_spiral(nb_samples: int, radius: float, alpha=2):
-    """Host-side beamlet-centre sampler (utils.py:297-325); input preparation only."""
+def fibonacci_spiral(nb_samples: int, radius: float, alpha=2, device=None):
+    """Beamlet-centre sampler (utils.py:297-325).  Host numpy by default like the reference; with
+    ``device="cuda"`` (or a torch device) the points are generated on the GPU
+    (``tg_fibonacci_spiral_f64``) and returned as CUDA tensors -- no host staging."""
     import numpy as np
+    if device is not None:
+        import torch
+        from . import _arrays as A
+        from . import _lib as L
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError("device must be a CUDA device (omit it for the host sampler)")
+        if dev.index is None:
+            dev = torch.device("cuda", A.current_device_index())
+        x = torch.empty(int(nb_samples), dtype=torch.float64, device=dev)
+        y = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            L.check(L.load().tg_fibonacci_spiral_f64(int(nb_samples), float(radius), float(alpha), x.data_ptr(),
+                                                     y.data_ptr(), A.current_stream_ptr(dev)),
+                    "tg_fibonacci_spiral_f64")
+        return x, y
     ga = np.pi * (3.0 - np.sqrt(5.0))
     np_boundary = np.round(alpha * np.sqrt(nb_samples))
     ii = np.arange(nb_samples)

@@ -848,3 +848,13 @@ def test_krivanek_functions(torch_cuda):
     np.testing.assert_array_equal(to_np(dgx), gx)
     sgx, sgy = grad_W_krivanek(0.1, -0.2, p)
     assert isinstance(sgx, float) and abs(sgx - O.grad_W_krivanek(np.array([0.1]), np.array([-0.2]), p)[0][0]) < 1e-14
+
+
+def test_fibonacci_spiral_on_device(torch_cuda):
+    from temgymcore_b200.utils import fibonacci_spiral
+    for n, alpha in ((1, 2), (10, 0), (10_000, 0), (65_537, 2)):
+        hx, hy = fibonacci_spiral(n, 1e-7, alpha=alpha)
+        dx, dy = fibonacci_spiral(n, 1e-7, alpha=alpha, device="cuda")
+        assert dx.is_cuda and dx.dtype == torch_cuda.float64 and tuple(dx.shape) == (n,)
+        np.testing.assert_allclose(to_np(dx), hx, rtol=0, atol=1e-7 * 1e-12)    # phi = i * 2.4 up to 1.6e5 rad
+        np.testing.assert_allclose(to_np(dy), hy, rtol=0, atol=1e-7 * 1e-12)
