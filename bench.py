@@ -35,12 +35,13 @@ C2_NB, C2_SHAPE = 10_000, (1024, 1024)
 # summarised under profiles/ (round 1, same workloads as timed here)
 NCU_TRAFFIC = {
     "gemm_tf32x3_kernel": (491.98e6 + 4.20e6, "profiles/r1_gemm_tf32x3_kernel_v1.md"),
-    "field_grid_kernel": (1.00e6 + 81.65e6, "profiles/r1_field_grid_kernel_v1.md"),
+    "field_grid_kernel": (1.00e6 + 81.65e6, "profiles/r1_field_grid_kernel_v3.md"),
     "trace_kernel_1e7": (560.0e6 + 2499.5e6, "profiles/r1_trace_kernel_1e7.md"),
     "stem4d_backproject": (17.18e9 + 3.6e6, "profiles/r1_stem4d_dda1x_kernel.md"),
     "trace_kernel_c4": (560.1e6 + 2506.8e6, "profiles/r1_trace_kernel_c4_v3.md"),
 }
-MUFU_PER_EVAL = 3          # sin, cos, ex2
+MUFU_PER_EVAL = 2          # executed: 1 ex2 per pixel + sin/cos seeds of z and w every 4 pixels (field.cu)
+MUFU_PER_EVAL_NAIVE = 3    # SURVEY.md section 8d's count (sin, cos, ex2 per beamlet*pixel)
 MUFU_PER_CLK_SM = 16
 RAY_BYTES_ABCD = 312       # 56 in + 56 out + 200 ABCD, fp64
 
@@ -317,7 +318,10 @@ def run_ours(args):
                     "evals_per_s": k_evals / (k_ms * 1e-3),
                     "kernel_ms": k_ms,
                     "peak_basis": f"{sms} SMs x 16 MUFU/clk x {pk['sm_max_mhz']:.0f} MHz (clocks.max.sm, "
-                                  f"{pk['source']}); 3 MUFU per beamlet*pixel"}
+                                  f"{pk['source']}); the kernel executes 2 MUFU per beamlet*pixel (phasor "
+                                  "recurrence re-seeded every 4 pixels) instead of the naive 3",
+                    "frac_vs_naive_3_mufu_roofline": k_evals * MUFU_PER_EVAL_NAIVE / (k_ms * 1e-3) / peak_mufu,
+                    "co_limiters": "issue slots 75 % and XU pipe 78 % busy (ncu, profiles/r1_field_grid_kernel_v3.md)"}
 
     # separable path: the tcgen05 GEMM alone, same shape as this rank's share of C2
     # (M = rows, N = 2W, K = 2 nb), operands random TF32-split fp32

@@ -3,7 +3,8 @@
 // Replaces map_reduce(_beam_field_outer, jnp.add, ...) of the reference
 // (src/temgym_core/gaussian.py:319-369) -- every complex Gaussian on every pixel.
 //
-// Design (SFU-bound; 3 MUFU per beamlet*pixel: sin, cos, ex2):
+// Design (SFU / issue bound; 2 MUFU per beamlet*pixel: ex2 + sin/cos seeds of a phasor recurrence,
+// instead of the naive 3):
 //  * prep kernel: metre-space complex quadratic (K2 output) -> pixel-space table, phase in
 //    TURNS (Re P / 2pi) and envelope in BITS (-Im P * log2 e), fp64, 96 B per beamlet.
 //  * main kernel: a CTA owns a TR x TC pixel tile and streams the beamlet table through
@@ -15,8 +16,10 @@
 //  * every thread owns a strip of L consecutive pixels of one row.  Per (thread, beamlet) it
 //    evaluates the strip-start phase and first difference in fp64 and converts them to
 //    32-bit FIXED-POINT turns; along the strip the phase advances by exact integer second
-//    differences (wrap-around mod 1 turn is free), the top 23 bits become an fp32 angle in
-//    [-pi, pi) for MUFU.SIN/COS, the envelope is a 2-FFMA Horner in fp32 for MUFU.EX2.
+//    differences (wrap-around mod 1 turn is free).  Every 4 pixels the top 23 bits become an fp32
+//    angle in [-pi, pi) for MUFU.SIN/COS -- exact seeds of the unit phasor z and of its step w;
+//    in between z_{j+1} = z_j w_j, w_{j+1} = w_j c (c = exp(i dd), per beamlet, fp64 sincospi).
+//    The envelope is a 2-FFMA Horner in fp32 for MUFU.EX2 on every pixel.
 //  * fp32 partial sums over one chunk (<= 128 terms) are flushed into fp64 accumulators held
 //    in shared memory, so accumulation error does not grow with the number of beamlets.
 //  * grid = tiles x beamlet-splits, split count chosen so the CTA count fills whole waves
@@ -29,7 +32,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kChunk = 128;          // beamlets per staged chunk
-constexpr int kRecDoubles = 16;      // tile-local record: 6 phase + 6 envelope + vertex(2) + {dd,e2} + pad
+constexpr int kRecDoubles = 16;      // tile-local record: 6 phase + 6 envelope + vertex(2) + {dd,e2} + {cr,ci}
 constexpr double kMagic = 1572864.0; // 1.5 * 2^20: ulp = 2^-32 -> low mantissa word = frac * 2^32
 constexpr double kInv2Pi = 0.15915494309189533577;
 constexpr double kLog2e = 1.4426950408889634074;
@@ -125,7 +128,7 @@ struct __align__(16) Rec {
   double vs0, vs1; // column of the envelope's vertex along row u: vs0 + vs1 * u (0,0 if none)
   uint32_t dd;    // second difference of the phase along a row, fixed point 2^-32 turn
   float e2;       // en[3] as fp32
-  double pad;
+  float cr, ci;   // exp(i 2 pi dd): the phasor of the second difference (fp64 sincospi, rounded once)
 };
 static_assert(sizeof(Rec) == kRecDoubles * 8, "record size");
 
@@ -236,7 +239,12 @@ __global__ void __launch_bounds__(kThreads, 2)
       rec.en[4] = e[4];
       rec.en[5] = e[5];
       rec.e2 = (float)e[3];
-      rec.pad = 0.0;
+      {
+        double sd, cd;
+        sincospi(2.0 * (dd - rint(dd)), &sd, &cd);
+        rec.cr = (float)cd;
+        rec.ci = (float)sd;
+      }
       // vertex of the (concave) envelope exponent along a row: d/dv = 0
       rec.vs0 = 0.0;
       rec.vs1 = 0.0;
@@ -308,20 +316,51 @@ __global__ void __launch_bounds__(kThreads, 2)
       const float ep = (float)(q.en[0] + ud * (q.en[2] + q.en[5] * ud) + vp * (r1 + q.en[3] * vp));
       const float e1p = (float)(r1 + 2.0 * q.en[3] * vp);
       const float e2 = q.e2;
+      // Phasor recurrence: along the strip the phase is t0 + j d0 + j(j-1)/2 dd, so
+      //   z_{j+1} = z_j w_j,  w_{j+1} = w_j c,   z_j = exp(i phase_j), w_j = exp(i (d0 + j dd)), c = exp(i dd).
+      // z and w are re-seeded EXACTLY from the fixed-point phase every 4 pixels (MUFU sin / cos), c is
+      // a per-beamlet constant from the staging step: 2.0 MUFU (+ 1 ex2... see below) per pixel become
+      // 4 sin/cos per 4 pixels -- 2 MUFU per pixel instead of 3 -- and the error of a seed is carried
+      // for at most 3 multiplications (<= ~1e-6 absolute on a unit phasor).
+      const float cr = q.cr, ci = q.ci;
 #pragma unroll
-      for (int j = 0; j < L; ++j) {
-        const uint32_t tj = t0 + (uint32_t)j * d0 + (uint32_t)(j * (j - 1) / 2) * dd;
-        const float ft = __uint_as_float((tj >> 9) | 0x3f800000u);       // 1 + frac(turns)
-        const float ang = fmaf(ft, 6.28318530717958648f, -9.42477796076937972f);  // 2pi frac - pi
-        const float dj = (float)j - jp;
-        const float ej = fmaf(dj, fmaf(dj, e2, e1p), ep);
-        float amp, sn, cs;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(amp) : "f"(ej));
-        sn = __sinf(ang);
-        cs = __cosf(ang);
-        // exp(i 2pi frac) = -(cos ang + i sin ang)
-        pr[j] = fmaf(-amp, cs, pr[j]);
-        pi[j] = fmaf(-amp, sn, pi[j]);
+      for (int s4 = 0; s4 < L; s4 += 4) {
+        const uint32_t tj = t0 + (uint32_t)s4 * d0 + (uint32_t)(s4 * (s4 - 1) / 2) * dd;
+        const uint32_t dj = d0 + (uint32_t)s4 * dd + 0x100u;
+        float zr, zi, wr, wi;
+        {
+          // exp(i 2pi frac) = -(cos ang + i sin ang), ang = 2 pi frac - pi in [-pi, pi)
+          const float fz = __uint_as_float((tj >> 9) | 0x3f800000u);       // 1 + frac(turns)
+          const float az = fmaf(fz, 6.28318530717958648f, -9.42477796076937972f);
+          const float fw = __uint_as_float((dj >> 9) | 0x3f800000u);
+          const float aw = fmaf(fw, 6.28318530717958648f, -9.42477796076937972f);
+          zr = -__cosf(az);
+          zi = -__sinf(az);
+          wr = -__cosf(aw);
+          wi = -__sinf(aw);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = s4 + k;
+          const float dj_ = (float)j - jp;
+          const float ej = fmaf(dj_, fmaf(dj_, e2, e1p), ep);
+          float amp;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(amp) : "f"(ej));
+          pr[j] = fmaf(amp, zr, pr[j]);
+          pi[j] = fmaf(amp, zi, pi[j]);
+          if (k < 3) {
+            const float nzr = fmaf(zr, wr, -(zi * wi));
+            const float nzi = fmaf(zr, wi, zi * wr);
+            zr = nzr;
+            zi = nzi;
+          }
+          if (k < 2) {
+            const float nwr = fmaf(wr, cr, -(wi * ci));
+            const float nwi = fmaf(wr, ci, wi * cr);
+            wr = nwr;
+            wi = nwi;
+          }
+        }
       }
     }
 
