@@ -88,6 +88,10 @@ def test_jets_krivanek_vs_sympy():
     for i, fld in enumerate(O.RAY_FIELDS):
         assert abs(float(exprs[i].evalf(30, subs=subs)) - float(np.asarray(getattr(vals, fld)).reshape(-1)[0])) < 1e-13
     _check(exprs, derivs, point, np.random.default_rng(1), 6, rtol=1e-10, outputs=(0, 2, 3, 5))
+    # the first-order jets are the Krivanek Jacobian of the forward-mode duals (what the ABCD tests use):
+    # both restatements agree, and sympy pins them
+    J = O.jacobian_run_to_end(ray, model)[1]
+    np.testing.assert_allclose(derivs[0], J, rtol=1e-11, atol=1e-13 * np.abs(J).max())
 
 
 def test_jets_pathlength_input_is_additive():

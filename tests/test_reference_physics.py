@@ -124,3 +124,40 @@ def test_offset_tilted_beam_vs_fresnel(backend):
         # stronger than the reference's check: the whole normalised amplitude profile agrees
         a, b = np.abs(out) / np.abs(out).max(), np.abs(fres) / np.abs(fres).max()
         assert np.abs(a - b).max() < 0.05
+
+
+def test_astigmatic_rotated_beam_axis(backend):
+    """An elliptical beamlet (w_x = 2 w_y) rotated by theta: the major axis of its input-plane intensity
+    (second moments) points along theta (test_gaussians.py:820-883, tolerance 0.1 rad there; the
+    moments are exact to ~1e-3 rad here).  After free-space propagation the far field of the NARROW axis
+    spreads faster, so the major axis has turned by 90 degrees -- checked through make_gaussian_image,
+    which the reference's test does not do."""
+    det = Detector(z=0.0, pixel_size=(2e-5, 2e-5), shape=(256, 256))
+    X, Y = det_axes(det)
+
+    def major_axis(field):
+        I = np.abs(field) ** 2
+        w = I.sum()
+        xc, yc = X - (I * X).sum() / w, Y - (I * Y).sum() / w
+        C = np.array([[(I * xc * xc).sum(), (I * xc * yc).sum()], [(I * xc * yc).sum(), (I * yc * yc).sum()]]) / w
+        vals, vecs = np.linalg.eigh(C)
+        v = vecs[:, np.argmax(vals)]
+        return (np.arctan2(v[1], v[0]) + np.pi / 2) % np.pi - np.pi / 2
+
+    def axis_diff(a, b):
+        d = np.arctan2(np.sin(a - b), np.cos(a - b))
+        return min(abs(d), abs(d + np.pi), abs(d - np.pi))
+
+    for theta in (np.pi / 3, np.pi / 6, 0.0, -np.pi / 6, -np.pi / 3, -np.pi / 2 + 0.1):
+        g = M.gaussian_rays([0.0], [0.0], wavelength=500e-9, waist_xy=[[2e-4, 1e-4]], theta=[theta])
+        img = backend.input_image(g, det)
+        assert axis_diff(major_axis(img), theta) < 5e-3
+        far = Detector(z=2.0, pixel_size=(8e-5, 8e-5), shape=(256, 256))     # z >> z_R of both axes
+        Xf, Yf = det_axes(far)
+        out = backend.image(g, [far])
+        I = np.abs(out) ** 2
+        w = I.sum()
+        C = np.array([[(I * Xf * Xf).sum(), (I * Xf * Yf).sum()], [(I * Xf * Yf).sum(), (I * Yf * Yf).sum()]]) / w
+        vals, vecs = np.linalg.eigh(C)
+        v = vecs[:, np.argmax(vals)]
+        assert axis_diff(np.arctan2(v[1], v[0]), theta + np.pi / 2) < 2e-2
