@@ -161,3 +161,39 @@ def test_astigmatic_rotated_beam_axis(backend):
         vals, vecs = np.linalg.eigh(C)
         v = vecs[:, np.argmax(vals)]
         assert axis_diff(np.arctan2(v[1], v[0]), theta + np.pi / 2) < 2e-2
+
+
+def test_offset_tilted_beam_through_lens_vs_fresnel(backend):
+    """A misaligned beamlet (offset AND tilted central ray) through a thin lens onto a detector that is
+    NOT in the image plane: every block of the ABCD matrix is non-trivial (A = 1 - z2/f, B = z1 + z2 -
+    z1 z2/f, C = -1/f, D = 1 - z1/f).  Compared with Fresnel propagation -> lens phase -> Fresnel
+    propagation of the sampled input field (the reference's fresnel_lens_imaging_solution validator,
+    utils.py:268-275; its own lens test, test_gaussians.py:374-518, is on-axis with rtol 0.5)."""
+    from temgymcore_b200.components import Lens
+    from temgymcore_b200.utils import fresnel_lens_imaging_solution
+    wl, w0 = 500e-9, 2e-4
+    z1, f, z2 = 0.3, 0.2, 0.25
+    n, px = 512, 1e-5
+    det_in = Detector(z=0.0, pixel_size=(px, px), shape=(n, n))
+    det_out = Detector(z=z1 + z2, pixel_size=(px, px), shape=(n, n))
+    X, Y = det_axes(det_in)
+    rng = np.random.default_rng(M.SEED + 3)
+    for _ in range(2):
+        r1m = rng.uniform(-3e-4, 3e-4, 2)
+        th = rng.uniform(-2e-4, 2e-4, 2)
+        g = M.gaussian_rays([r1m[0]], [r1m[1]], dx=[th[0]], dy=[th[1]], wavelength=wl, w0=w0)
+        u0 = backend.input_image(g, det_in)
+        ref = fresnel_lens_imaging_solution(u0, Y, X, px, wl, z1, f, z2)
+        out = backend.image(g, [Lens(z=z1, focal_length=f), det_out])
+        pa = np.unravel_index(np.argmax(np.abs(out)), out.shape)
+        pf = np.unravel_index(np.argmax(np.abs(ref)), ref.shape)
+        assert abs(pa[0] - pf[0]) <= 2 and abs(pa[1] - pf[1]) <= 2
+        # the ray-optics prediction of the spot centre agrees too: x_out = A x + B dx
+        A_, B_ = 1 - z2 / f, z1 + z2 - z1 * z2 / f
+        assert abs(X[pa] - (A_ * r1m[0] + B_ * th[0])) <= 2 * px and abs(Y[pa] - (A_ * r1m[1] + B_ * th[1])) <= 2 * px
+        a, b = np.abs(out) / np.abs(out).max(), np.abs(ref) / np.abs(ref).max()
+        assert np.abs(a - b).max() < 0.03
+        # phase relative to the peak pixel where the beam is bright
+        strong = b > 0.3
+        dphi = np.angle(out * np.conj(out[pf]) * np.conj(ref * np.conj(ref[pf])))
+        assert np.abs(dphi[strong]).max() < 0.1
