@@ -286,6 +286,10 @@ __device__ __forceinline__ double col_env_max(double E1, double E3, double Wm1) 
 // fixed-point turns by exact integer differences and the envelope is the pivot-form fp32
 // quadratic of the SFU kernel (field.cu).  Stores are coalesced: for a fixed row, consecutive
 // threads (beamlets) write consecutive k' pairs.
+// AUTO hands a separable problem to the culled SFU kernel when its estimated executed evaluations are
+// below this fraction of nb*H*W (measured break-even on B200: GEMM 4.1e-14 s per nominal evaluation,
+// SFU 6.3e-13 s per executed one -> 6.6 %; the estimate counts whole tiles, so stay below that)
+constexpr double kSfuWinsBelow = 0.045;
 constexpr int FS = 32;
 constexpr double kMagicF = 1572864.0;  // 1.5 * 2^20
 
@@ -393,6 +397,55 @@ __global__ void __launch_bounds__(256)
   if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(key, (unsigned long long)__double_as_longlong(v));
 }
 
+// ---- cost-aware dispatch (AUTO only) -----------------------------------------------------
+// The GEMM is dense: it spends 24 TF32 flops on every beamlet*pixel whether the beamlet reaches the
+// pixel or not, while the SFU kernel skips (tile, beamlet) pairs below the culling threshold.  For
+// narrow beamlets on a large detector (BASELINE C3: ~11 px envelopes on 2048^2) the culled SFU sum
+// executes a few per cent of the nominal evaluations and wins.  This kernel estimates the SFU work
+// from the bounding box of each beamlet's region {envelope >= brightest on-detector peak - cull_bits}
+// in whole 32 x 128 tiles; verdict_kernel then hands the call to the SFU path (by raising the
+// separability key above 1) when the estimate is below `ratio` of the nominal nb*H*W evaluations.
+__global__ void __launch_bounds__(256)
+    sfu_cost_kernel(const double *__restrict__ table, long long nb, int H, int W,
+                    const unsigned long long *__restrict__ gref_key, int cull_bits, double *est_tiles) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double tiles = 0.0;
+  const double all_tiles = (double)((W + 127) / 128) * (double)((H + 31) / 32);
+  if (i < nb) {
+    const unsigned long long k = *gref_key;
+    const double *e = table + i * 12 + 6;               // E(c, r) = e0 + e1 c + e2 r + e3 c^2 + e4 c r + e5 r^2 [bits]
+    tiles = all_tiles;                                   // default: the beamlet reaches everything
+    if (k != ~0ULL) {
+      // ordered-uint key of the smallest -E on the detector (field.cu enc_ordered): decode
+      const unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;
+      const double e_thr = -(__longlong_as_double((long long)b) + (double)cull_bits);
+      const double det = e[3] * e[5] - 0.25 * e[4] * e[4];
+      if (e[3] < 0.0 && e[5] < 0.0 && det > 0.0) {
+        const double cs = (0.5 * e[4] * e[2] - e[5] * e[1]) / (2.0 * det);   // vertex column
+        const double rs = (0.5 * e[4] * e[1] - e[3] * e[2]) / (2.0 * det);   // vertex row
+        const double emax = e[0] + 0.5 * (e[1] * cs + e[2] * rs);
+        const double d = emax - e_thr;
+        if (d < 0.0) {
+          tiles = 0.0;
+        } else if (isfinite(d) && isfinite(cs) && isfinite(rs)) {
+          const double hc = sqrt(d * (-e[5]) / det), hr = sqrt(d * (-e[3]) / det);
+          const double c_lo = fmax(cs - hc, 0.0), c_hi = fmin(cs + hc, (double)(W - 1));
+          const double r_lo = fmax(rs - hr, 0.0), r_hi = fmin(rs + hr, (double)(H - 1));
+          if (c_hi < c_lo || r_hi < r_lo) tiles = 0.0;
+          else tiles = (floor(c_hi / 128.0) - floor(c_lo / 128.0) + 1.0) * (floor(r_hi / 32.0) - floor(r_lo / 32.0) + 1.0);
+        }
+      }
+    }
+    if (!(tiles == tiles)) tiles = all_tiles;
+  }
+  for (int o = 16; o > 0; o >>= 1) tiles += __shfl_xor_sync(0xffffffffu, tiles, o);
+  if ((threadIdx.x & 31) == 0 && tiles > 0.0) atomicAdd(est_tiles, tiles);
+}
+__global__ void verdict_kernel(unsigned long long *key, const double *est_tiles, double nominal_evals, double ratio) {
+  if (*est_tiles * 4096.0 < ratio * nominal_evals)
+    atomicMax(key, (unsigned long long)__double_as_longlong(2.0));   // > 1: "not for the tensor path"
+}
+
 __global__ void __launch_bounds__(256)
     f64_to_c64_kernel(const double *__restrict__ in, float *__restrict__ out, size_t n,
                       const unsigned long long *__restrict__ sep_guard) {
@@ -476,12 +529,12 @@ extern "C" int tg_gemm_tf32x3(int M, int N, int K, const float *A_hi, const floa
 extern "C" int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6], int H, int W,
                                       int row0, int nrows, void *out, int out_is_c128, void *stream) {
   return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr,
-                          static_cast<cudaStream_t>(stream));
+                          static_cast<cudaStream_t>(stream), 0);
 }
 
 int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                      int nrows, void *out, int out_is_c128, unsigned long long *key_async,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int cost_cull_bits) {
   TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad shape");
   TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
   TG_REQUIRE(px2m && out, "null pointer");
@@ -518,10 +571,21 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
                             : reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(Blo) + b_bytes);
   int rc = TG_OK;
   cudaError_t e = cudaMemsetAsync(key, 0, 8, st);
-  if (e == cudaSuccess) rc = tg_launch_prep(nb, poly, px2m, H, W, table, nullptr, st);
+  // cost model (AUTO with culling enabled): brightest-peak key and tile estimate live after the key slot
+  const bool cost = key_async != nullptr && cost_cull_bits > 0;
+  unsigned long long *gref = reinterpret_cast<unsigned long long *>(ws + table_bytes + 64);
+  double *est = reinterpret_cast<double *>(ws + table_bytes + 128);
+  if (cost && e == cudaSuccess) e = cudaMemsetAsync(gref, 0xFF, 8, st);
+  if (cost && e == cudaSuccess) e = cudaMemsetAsync(est, 0, 8, st);
+  if (e == cudaSuccess) rc = tg_launch_prep(nb, poly, px2m, H, W, table, cost ? gref : nullptr, st);
   if (e == cudaSuccess && rc == TG_OK) {
     cross_term_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(table, nb, (double)H * (double)W, key);
     rc = tg_launch_check("cross_term_kernel");
+  }
+  if (cost && e == cudaSuccess && rc == TG_OK) {
+    sfu_cost_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(table, nb, H, W, gref, cost_cull_bits, est);
+    verdict_kernel<<<1, 1, 0, st>>>(key, est, (double)nb * (double)H * (double)W, kSfuWinsBelow);
+    rc = tg_launch_check("cost kernels");
   }
   unsigned long long hkey = 0;
   if (e == cudaSuccess && rc == TG_OK && !key_async) {
@@ -567,13 +631,13 @@ extern "C" int tg_field_sum(int64_t nb, const double *poly, const double px2m[6]
   if (method == TG_METHOD_SFU)
     return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st);
   if (method == TG_METHOD_TENSOR)
-    return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr, st);
+    return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr, st, 0);
   TG_REQUIRE(method == TG_METHOD_AUTO, "unknown method");
   if (nb == 0 || nrows == 0)
     return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st);
   unsigned long long *key = nullptr;
   TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&key), 8, st));
-  int rc = tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, key, st);
+  int rc = tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, key, st, cull_bits);
   if (rc == TG_OK)
     rc = tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, key, st);
   cudaFreeAsync(key, st);

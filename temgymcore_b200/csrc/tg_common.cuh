@@ -18,9 +18,11 @@ int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int 
                       const unsigned long long *sep_guard, cudaStream_t stream);
 // key_async != NULL: no host sync; the verdict stays on the device in *key_async and the kernels of
 // this path return at once when it says "not separable".
+// cost_cull_bits > 0 (async mode only): also estimate the culled SFU work and leave the call to the SFU
+// path when that is clearly cheaper than the dense GEMM.
 int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                      int nrows, void *out, int out_is_c128, unsigned long long *key_async,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int cost_cull_bits);
 // separability key = bits of max_n(cross term / tolerance) as a double (0 when there is none)
 __host__ __device__ inline bool tg_key_is_separable(unsigned long long key) {
   union { unsigned long long u; double d; } c;

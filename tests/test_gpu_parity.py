@@ -858,3 +858,27 @@ def test_fibonacci_spiral_on_device(torch_cuda):
         assert dx.is_cuda and dx.dtype == torch_cuda.float64 and tuple(dx.shape) == (n,)
         np.testing.assert_allclose(to_np(dx), hx, rtol=0, atol=1e-7 * 1e-12)    # phi = i * 2.4 up to 1.6e5 rad
         np.testing.assert_allclose(to_np(dy), hy, rtol=0, atol=1e-7 * 1e-12)
+
+
+def test_auto_dispatch_is_cost_aware(torch_cuda):
+    """method="auto": separable beamlets go to the tensor cores unless the device-side cost model finds
+    that the culled SFU sum executes far fewer evaluations than the dense GEMM (narrow beamlets on a big
+    detector, BASELINE C3).  Both kernels are deterministic, so the path taken shows up bit for bit."""
+    from temgymcore_b200.gaussian import _field_sum_grid, beamlet_polynomials
+    # C3 geometry: ~11 px envelopes on 1024^2 -> culled SFU
+    g, model = M.biprism_case(4000, (1024, 1024))
+    poly, n, dev = beamlet_polynomials(g, model)
+    auto = _field_sum_grid(poly, n, model[-1], dev, method="auto")
+    sfu = _field_sum_grid(poly, n, model[-1], dev, method="sfu")
+    tens = _field_sum_grid(poly, n, model[-1], dev, method="tensor")
+    assert torch_cuda.equal(auto, sfu) and not torch_cuda.equal(auto, tens)
+    assert rel_l2(to_np(auto), to_np(tens)) < 3e-6
+    # with culling disabled the SFU sum would be dense: tensor cores
+    auto0 = _field_sum_grid(poly, n, model[-1], dev, method="auto", cull_bits=0)
+    assert torch_cuda.equal(auto0, tens)
+    # C2 geometry: every beamlet covers the whole detector -> tensor cores whatever cull_bits says
+    g, model = M.aperture_diffraction_case(1500, (512, 512))
+    poly, n, dev = beamlet_polynomials(g, model)
+    auto = _field_sum_grid(poly, n, model[-1], dev, method="auto")
+    tens = _field_sum_grid(poly, n, model[-1], dev, method="tensor")
+    assert torch_cuda.equal(auto, tens)
