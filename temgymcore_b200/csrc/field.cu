@@ -121,14 +121,51 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// Detector-space bounding box (whole pixels, clipped to the detector, +-1 px slack) of the region where a
+// beamlet's envelope exceeds the culling threshold  E >= (brightest on-detector peak) - cull_bits.
+// Non-concave envelopes get the whole detector; beamlets below the threshold everywhere an empty box.
+__global__ void __launch_bounds__(256)
+    bbox_kernel(long long nb, const double *__restrict__ table, int H, int W,
+                const unsigned long long *__restrict__ gref_key, int cull_bits, short4 *__restrict__ bbox) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  short4 bb = make_short4(0, (short)min(W - 1, 32767), 0, (short)min(H - 1, 32767));
+  const unsigned long long k = *gref_key;
+  const double *e = table + i * 12 + 6;   // E(c, r) = e0 + e1 c + e2 r + e3 c^2 + e4 c r + e5 r^2 [bits]
+  const double det = e[3] * e[5] - 0.25 * e[4] * e[4];
+  if (k != ~0ULL && e[3] < 0.0 && e[5] < 0.0 && det > 0.0) {
+    const double e_thr = -(dec_ordered(k) + (double)cull_bits);
+    const double cs = (0.5 * e[4] * e[2] - e[5] * e[1]) / (2.0 * det);
+    const double rs = (0.5 * e[4] * e[1] - e[3] * e[2]) / (2.0 * det);
+    const double d = (e[0] + 0.5 * (e[1] * cs + e[2] * rs)) - e_thr;
+    if (d < 0.0) {
+      bb = make_short4(1, 0, 1, 0);        // empty
+    } else if (isfinite(d) && isfinite(cs) && isfinite(rs)) {
+      const double hc = sqrt(d * (-e[5]) / det) + 1.0, hr = sqrt(d * (-e[3]) / det) + 1.0;
+      const double c_lo = floor(cs - hc), c_hi = ceil(cs + hc), r_lo = floor(rs - hr), r_hi = ceil(rs + hr);
+      if (c_hi < 0.0 || r_hi < 0.0 || c_lo > (double)(W - 1) || r_lo > (double)(H - 1)) {
+        bb = make_short4(1, 0, 1, 0);
+      } else {
+        bb.x = (short)fmin(fmax(c_lo, 0.0), 32767.0);
+        bb.y = (short)fmin(fmin(c_hi, (double)(W - 1)), 32767.0);
+        bb.z = (short)fmin(fmax(r_lo, 0.0), 32767.0);
+        bb.w = (short)fmin(fmin(r_hi, (double)(H - 1)), 32767.0);
+      }
+    }
+  }
+  bbox[i] = bb;
+}
+
 // ---- main tiled kernel ----------------------------------------------------------------
 struct __align__(16) Rec {
   double th[6];   // tile-local phase coefficients, turns, reduced to [-0.5, 0.5]
   double en[6];   // tile-local envelope coefficients (bits, amplitude = 2^en(u,v))
-  double vs0, vs1; // column of the envelope's vertex along row u: vs0 + vs1 * u (0,0 if none)
+  float vs0, vs1; // column of the envelope's vertex along row u: vs0 + vs1 * u (0,0 if none); only picks the pivot pixel
   uint32_t dd;    // second difference of the phase along a row, fixed point 2^-32 turn
   float e2;       // en[3] as fp32
   float cr, ci;   // exp(i 2 pi dd): the phasor of the second difference (fp64 sincospi, rounded once)
+  uint32_t cspan; // tile columns that can hold a contribution above the culling threshold: lo | hi << 16
+  uint32_t pad;
 };
 static_assert(sizeof(Rec) == kRecDoubles * 8, "record size");
 
@@ -144,11 +181,13 @@ struct FieldSmem {
   int n_active;
 };
 
-template <int L, int SPR>
+// WCULL: culling is enabled -> lane = row / warp = strip mapping with the per-warp column skip; the
+// dense instantiation keeps lane = strip (8 strips x 4 rows per warp), which measures ~7 % faster.
+template <int L, int SPR, bool WCULL>
 __global__ void __launch_bounds__(kThreads, 2)
     field_grid_kernel(const double *__restrict__ table, const FieldGeom g,
-                      const unsigned long long *__restrict__ gref_key, void *__restrict__ out,
-                      int out_is_c128, double2 *__restrict__ partial,
+                      const unsigned long long *__restrict__ gref_key, const short4 *__restrict__ bbox,
+                      void *__restrict__ out, int out_is_c128, double2 *__restrict__ partial,
                       unsigned long long *__restrict__ evals,
                       const unsigned long long *__restrict__ sep_guard) {
   if (sep_guard && tg_key_is_separable(*sep_guard)) return;  // the tensor-core path owns this call
@@ -163,8 +202,12 @@ __global__ void __launch_bounds__(kThreads, 2)
   const int ty = tile / g.tiles_x, tx = tile % g.tiles_x;
   const int r0 = g.row0 + ty * TR;   // tile origin in full-detector pixel coordinates
   const int c0 = tx * TC;
-  const int u = tid / SPR;           // row inside tile
-  const int v0 = (tid % SPR) * L;    // first column of this thread's strip inside the tile
+  // lane = row inside the tile, warp = strip of L columns: a warp owns a TR x L pixel block, so a
+  // beamlet can be skipped per warp (no divergence) when it cannot reach those columns -- culling at
+  // 32 x 16 instead of 32 x 128 pixels for narrow beamlets (BASELINE C3)
+  static_assert(S::TR == 32 && kThreads / 32 == SPR, "lane <-> row mapping");
+  const int u = WCULL ? (tid & 31) : tid / SPR;                 // row inside tile
+  const int v0 = (WCULL ? (tid >> 5) : (tid % SPR)) * L;        // first column of this thread's strip inside the tile
 
   // beamlet range of this split
   const long long per = (g.nb + g.nsplit - 1) / g.nsplit;
@@ -192,6 +235,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 
   // per-thread strip constants (exact small integers in fp64)
   const double ud = (double)u, vd = (double)v0;
+  const float uf = (float)u, vf = (float)v0;
 
 
   double thr_bits = INFINITY;  // cull when min envelope exponent g over tile > thr_bits
@@ -204,6 +248,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
   for (int j = 0; j < L; ++j) { pr[j] = 0.f; pi[j] = 0.f; }
   unsigned long long my_active = 0;
+  int pending = 0;                   // terms in the fp32 partials since the last flush (<= 1.5 kChunk)
 
   for (int c = 0; c < nchunks; ++c) {
     if (tid == 0 && c + 1 < nchunks) issue(c + 1);
@@ -214,7 +259,14 @@ __global__ void __launch_bounds__(kThreads, 2)
     const int cnt = (int)((b_end - b) < kChunk ? (b_end - b) : kChunk);
     bool keep = false;
     Rec rec;
-    if (tid < cnt) {
+    bool near = tid < cnt;
+    if (near && bbox && thr_bits < INFINITY) {
+      // cheap reject: the beamlet's detector-space bounding box of {envelope >= threshold} (bbox_kernel)
+      // misses this tile -- skips the fp64 re-centring for the ~99 % of beamlets that are far away
+      const short4 bb = __ldg(bbox + b + tid);          // col_lo, col_hi, row_lo, row_hi (detector pixels)
+      near = !(bb.y < c0 || bb.x > c0 + TC - 1 || bb.w < r0 || bb.z > r0 + TR - 1);
+    }
+    if (near) {
       const double *a = sm.raw[c & 1] + tid * 12;
       const double cc = (double)c0, rr = (double)r0;
       // phase, turns
@@ -239,6 +291,8 @@ __global__ void __launch_bounds__(kThreads, 2)
       rec.en[4] = e[4];
       rec.en[5] = e[5];
       rec.e2 = (float)e[3];
+      rec.pad = 0u;
+      rec.cspan = (uint32_t)(TC - 1) << 16;      // all columns unless the culling test below narrows it
       {
         double sd, cd;
         sincospi(2.0 * (dd - rint(dd)), &sd, &cd);
@@ -246,12 +300,16 @@ __global__ void __launch_bounds__(kThreads, 2)
         rec.ci = (float)sd;
       }
       // vertex of the (concave) envelope exponent along a row: d/dv = 0
-      rec.vs0 = 0.0;
-      rec.vs1 = 0.0;
+      rec.vs0 = 0.f;
+      rec.vs1 = 0.f;
       if (rec.en[3] < -1e-12) {
         const double inv = -0.5 / rec.en[3];
         const double a0 = rec.en[1] * inv, a1 = rec.en[4] * inv;
-        if (isfinite(a0) && isfinite(a1)) { rec.vs0 = a0; rec.vs1 = a1; }
+        // clamped far outside the tile: the pivot is clamped to the strip anyway
+        if (isfinite(a0) && isfinite(a1)) {
+          rec.vs0 = (float)fmin(fmax(a0, -1e6), 1e6);
+          rec.vs1 = (float)fmin(fmax(a1, -1e4), 1e4);
+        }
       }
       keep = true;
       if (thr_bits < INFINITY) {
@@ -260,6 +318,21 @@ __global__ void __launch_bounds__(kThreads, 2)
         for (int j = 0; j < 6; ++j) G[j] = -rec.en[j];
         const double gmin = quad_min_rect(G, (double)(TR - 1), (double)(TC - 1));
         keep = !(gmin > thr_bits);  // NaN keeps
+        // column extent of {G <= thr} (bounding box of the ellipse), for the per-warp skip
+        const double det4 = 4.0 * G[3] * G[5] - G[4] * G[4];
+        if (keep && G[3] > 0.0 && G[5] > 0.0 && det4 > 0.0) {
+          const double vs = (-2.0 * G[5] * G[1] + G[4] * G[2]) / det4;
+          const double us = (-2.0 * G[3] * G[2] + G[4] * G[1]) / det4;
+          const double dlt = thr_bits - (G[0] + 0.5 * (G[1] * vs + G[2] * us));
+          const double hv = sqrt(fmax(dlt, 0.0) * 4.0 * G[5] / det4);
+          const double lo = floor(vs - hv) - 1.0, hi = ceil(vs + hv) + 1.0;   // one pixel of slack
+          if (isfinite(lo) && isfinite(hi)) {
+            const int ilo = (int)fmin(fmax(lo, 0.0), (double)(TC - 1));
+            const int ihi = (int)fmin(fmax(hi, 0.0), (double)(TC - 1));
+            if (hi < 0.0 || lo > (double)(TC - 1)) keep = false;             // wholly beside the tile
+            rec.cspan = (uint32_t)ilo | ((uint32_t)ihi << 16);
+          }
+        }
       }
     }
     int n_active;
@@ -288,11 +361,16 @@ __global__ void __launch_bounds__(kThreads, 2)
       __syncthreads();
       n_active = cnt;
     }
-    my_active += (unsigned long long)n_active;
 
     // ---- evaluate: every thread, its strip of L pixels, all active beamlets of the chunk
     for (int n = 0; n < n_active; ++n) {
       const Rec &q = sm.rec[n];
+      if constexpr (WCULL) {
+        const uint32_t cs = q.cspan;                                  // warp-uniform: same q, same v0
+        if (v0 + L - 1 < (int)(cs & 0xffffu) || v0 > (int)(cs >> 16)) continue;
+      }
+      ++my_active;
+      ++pending;
       // strip-start phase and first difference (turns), fp64 -> 2^-32 fixed point
       // (Horner in v then u: only the two per-thread constants ud, vd stay live in registers)
       const double rt = fma(q.th[4], ud, q.th[1]);                  // T1 + T4 u
@@ -308,8 +386,9 @@ __global__ void __launch_bounds__(kThreads, 2)
       // fp32 never cancels where the amplitude matters; broad envelopes are insensitive to jp.
       // pivot = clamp(round(vertex column - strip start), 0, L-1), all without the XU pipe:
       // round via the 1.5*2^52 mantissa trick, clamp as integer, rebuild float/double by bits
-      const double jsd = fma(q.vs1, ud, q.vs0 - vd) + 6755399441055744.0;
-      const int ji = min(max(__double2loint(jsd), 0), L - 1);
+      // (fp32: the vertex only selects which pixel of the strip the expansion is centred on)
+      const float jsf = fmaf(q.vs1, uf, q.vs0 - vf) + 12582912.0f;       // 1.5 * 2^23: low mantissa bits = round(js)
+      const int ji = min(max((int)(__float_as_uint(jsf) & 0x7fffffu) - 0x400000, 0), L - 1);
       const float jp = __uint_as_float(0x4b000000u | (uint32_t)ji) - 8388608.0f;
       const double vp = __hiloint2double(0x43300000, ji) + (vd - 4503599627370496.0);
       const double r1 = q.en[1] + q.en[4] * ud;
@@ -364,15 +443,26 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
     }
 
-    // ---- flush fp32 chunk partials into the fp64 accumulators
+    // ---- flush the fp32 partials into the fp64 accumulators once they hold ~kChunk terms (bounds the
+    // fp32 accumulation length; when most beamlets are culled for this strip the flush is rare)
+    if (pending >= kChunk / 2) {
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        sm.acc[j * kThreads + tid] += (double)pr[j];
+        sm.acc[(L + j) * kThreads + tid] += (double)pi[j];
+        pr[j] = 0.f;
+        pi[j] = 0.f;
+      }
+      pending = 0;
+    }
+    __syncthreads();  // records and raw[c&1] are free for the next stage / TMA
+  }
+  if (pending) {
 #pragma unroll
     for (int j = 0; j < L; ++j) {
       sm.acc[j * kThreads + tid] += (double)pr[j];
       sm.acc[(L + j) * kThreads + tid] += (double)pi[j];
-      pr[j] = 0.f;
-      pi[j] = 0.f;
     }
-    __syncthreads();  // records and raw[c&1] are free for the next stage / TMA
   }
 
   // ---- write the tile
@@ -394,11 +484,10 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
     }
   }
-  if (evals && tid == 0) {
+  if (evals) {   // executed evaluations: beamlets this thread evaluated x valid pixels of its strip
     const int rows_valid = min(TR, g.row0 + g.nrows - r0);
-    const int cols_valid = min(TC, g.W - c0);
-    atomicAdd(evals, my_active * (unsigned long long)(rows_valid > 0 ? rows_valid : 0) *
-                         (unsigned long long)(cols_valid > 0 ? cols_valid : 0));
+    const int cols_valid = min(L, g.W - c0 - v0);
+    if (u < rows_valid && cols_valid > 0 && my_active) atomicAdd(evals, my_active * (unsigned long long)cols_valid);
   }
 }
 
@@ -531,11 +620,14 @@ int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int 
   TG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   g.nsplit = choose_split(tiles, nb, 2 * sms, cull_bits > 0, npix);
 
-  // workspace: table (nb*96 B) | gref key (8) | evals (8) | split partials
+  // workspace: table (nb*96 B) | gref key (8) | evals (8) | split partials | per-beamlet bounding boxes
   const size_t table_bytes = (size_t)nb * 96;
   const size_t part_bytes = g.nsplit > 1 ? (size_t)g.nsplit * npix * 16 : 0;
+  const bool use_bbox = cull_bits > 0 && H <= 32768 && W <= 32768;
+  const size_t bbox_bytes = use_bbox ? (size_t)nb * sizeof(short4) : 0;
   unsigned char *ws = nullptr;
-  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), table_bytes + 256 + part_bytes, st));
+  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), table_bytes + 256 + part_bytes + bbox_bytes, st));
+  short4 *bbox = use_bbox ? reinterpret_cast<short4 *>(ws + table_bytes + 256 + part_bytes) : nullptr;
   double *table = reinterpret_cast<double *>(ws);
   unsigned long long *gref = reinterpret_cast<unsigned long long *>(ws + table_bytes);
   unsigned long long *evals = gref + 1;
@@ -544,17 +636,21 @@ int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int 
   TG_CUDA(cudaMemsetAsync(evals, 0, 8, st));
 
   int rc = tg_launch_prep(nb, poly, px2m, H, W, table, cull_bits > 0 ? gref : nullptr, st);
+  if (rc == TG_OK && use_bbox) {
+    bbox_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, table, H, W, gref, cull_bits, bbox);
+    rc = tg_launch_check("bbox_kernel");
+  }
   if (rc == TG_OK) {
     const size_t smem = sizeof(S);
-    cudaError_t e = cudaFuncSetAttribute(field_grid_kernel<L, SPR>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = cull_bits > 0 ? field_grid_kernel<L, SPR, true> : field_grid_kernel<L, SPR, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       tg_set_error("cudaFuncSetAttribute(field_grid_kernel): %s", cudaGetErrorString(e));
       rc = TG_ECUDA;
     } else {
       dim3 grid((unsigned)tiles, (unsigned)g.nsplit);
-      field_grid_kernel<L, SPR><<<grid, kThreads, smem, st>>>(
-          table, g, cull_bits > 0 ? gref : nullptr, out, out_is_c128, partial,
+      kern<<<grid, kThreads, smem, st>>>(
+          table, g, cull_bits > 0 ? gref : nullptr, bbox, out, out_is_c128, partial,
           n_evals_out ? evals : nullptr, sep_guard);
       rc = tg_launch_check("field_grid_kernel");
       if (rc == TG_OK && g.nsplit > 1) {
