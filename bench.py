@@ -34,7 +34,8 @@ C2_NB, C2_SHAPE = 10_000, (1024, 1024)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures
 # summarised under profiles/ (round 1, same workloads as timed here)
 NCU_TRAFFIC = {
-    "gemm_tf32x3_kernel": (491.98e6 + 4.20e6, "profiles/r1_gemm_tf32x3_kernel_v1.md"),
+    "gemm_x3_kernel_tf32": (491.98e6 + 4.20e6, "profiles/r1_gemm_tf32x3_kernel_v1.md"),
+    "gemm_x3_kernel_f16": (None, None),
     "field_grid_kernel": (1.00e6 + 81.65e6, "profiles/r1_field_grid_kernel_v3.md"),
     "trace_kernel_1e7": (560.0e6 + 2499.5e6, "profiles/r1_trace_kernel_1e7.md"),
     "stem4d_backproject": (17.18e9 + 3.6e6, "profiles/r1_stem4d_dda1x_kernel.md"),
@@ -242,8 +243,8 @@ def run_ours(args):
 
     method = args.method
     # our kernels per step: trace, qinv, wave, coeffs + {sfu: prep, field, split-reduce |
-    # tensor: prep, cross-term, 2 factor kernels, GEMM | auto: both sets, the unused one exits at once}
-    LAUNCHES = {"sfu": 7, "tensor": 9, "auto": 12}
+    # tensor: prep, cross-term, row-peak, pre-scale, 2 factor kernels, GEMM | auto: both sets, the unused one exits at once}
+    LAUNCHES = {"sfu": 7, "tensor": 11, "tensor_tf32": 11, "auto": 14}
 
     def step_device():
         """inputs resident in HBM: trace+ABCD, Q_inv, k/p0, coefficients (4 launches), broadcast,
@@ -324,45 +325,58 @@ def run_ours(args):
                     "co_limiters": "issue slots 75 % and XU pipe 78 % busy (ncu, profiles/r1_field_grid_kernel_v3.md)"}
 
     # separable path: the tcgen05 GEMM alone, same shape as this rank's share of C2
-    # (M = rows, N = 2W, K = 2 nb), operands random TF32-split fp32
+    # (M = rows, N = 2W, K = 2 nb), operands random split fp32 (fp16 x 3 = what the path runs; tf32 x 3 beside it)
     roofline_tensor = None
     if method != "sfu":
         Mg, Ng, Kg = nr, 2 * W, 2 * nb
         gen = torch.Generator(device=dev).manual_seed(1)
-
-        def split(x):
-            hi = ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
-            return hi, x - hi
-        Ah, Al = split(torch.rand((Mg, Kg), generator=gen, device=dev) * 2 - 1)
-        Bh, Bl = split(torch.rand((Ng, Kg), generator=gen, device=dev) * 2 - 1)
-        Dg = torch.empty((Mg, Ng), dtype=torch.float64, device=dev)
         lib = L.load()
-
-        def gemm():
-            L.check(lib.tg_gemm_tf32x3(Mg, Ng, Kg, Ah.data_ptr(), Al.data_ptr(), Bh.data_ptr(), Bl.data_ptr(),
-                                       Kg, Dg.data_ptr(), Ng, 0, torch.cuda.current_stream().cuda_stream),
-                    "tg_gemm_tf32x3")
-        gt = timed(gemm, args.steps, args.warmup)
-        g_ms = float(np.mean(gt))
-        alg_tf = 8.0 * nb * nr * W / (g_ms * 1e-3) / 1e12          # one complex MAC per beamlet*pixel
-        exe_tf = 2.0 * Mg * Ng * Kg * 3 / (g_ms * 1e-3) / 1e12      # 3 TF32 passes (hi*hi, hi*lo, lo*hi)
         bf16 = None
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
                 bf16 = float(json.load(fh)["bf16_tflops"])
         except Exception:
             bf16 = 1590.0
-        roofline_tensor = {"bound": "tensor", "kernel": "gemm_tf32x3_kernel (tcgen05.mma kind::tf32)",
+
+        def split_tf32(x):
+            hi = ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+            return hi, x - hi
+
+        def split_f16(x):
+            hi = x.half()
+            return hi, (x - hi.float()).half()
+        A32 = torch.rand((Mg, Kg), generator=gen, device=dev) * 2 - 1
+        B32 = torch.rand((Ng, Kg), generator=gen, device=dev) * 2 - 1
+        Dg = torch.empty((Mg, Ng), dtype=torch.float64, device=dev)
+        gemm_ms = {}
+        for kind, split, fn in (("f16", split_f16, lib.tg_gemm_f16x3), ("tf32", split_tf32, lib.tg_gemm_tf32x3)):
+            Ah, Al = split(A32)
+            Bh, Bl = split(B32)
+
+            def gemm():
+                L.check(fn(Mg, Ng, Kg, Ah.data_ptr(), Al.data_ptr(), Bh.data_ptr(), Bl.data_ptr(),
+                           Kg, Dg.data_ptr(), Ng, 0, torch.cuda.current_stream().cuda_stream), "tg_gemm_*x3")
+            gemm_ms[kind] = float(np.mean(timed(gemm, args.steps, args.warmup)))
+            del Ah, Al, Bh, Bl
+        tensor_kind = "tf32" if method == "tensor_tf32" else "f16"
+        g_ms = gemm_ms[tensor_kind]
+        kind_peak = bf16 if tensor_kind == "f16" else bf16 / 2
+        alg_tf = 8.0 * nb * nr * W / (g_ms * 1e-3) / 1e12          # one complex MAC per beamlet*pixel
+        exe_tf = 2.0 * Mg * Ng * Kg * 3 / (g_ms * 1e-3) / 1e12      # 3 passes (hi*hi, hi*lo, lo*hi)
+        roofline_tensor = {"bound": "tensor",
+                           "kernel": f"gemm_x3_kernel<{tensor_kind}> (tcgen05.mma kind::{tensor_kind})",
                            "achieved": alg_tf, "peak": bf16, "unit": "TFLOP/s", "frac": alg_tf / bf16,
-                           "traffic": NCU_TRAFFIC["gemm_tf32x3_kernel"][0],
-                           "traffic_source": NCU_TRAFFIC["gemm_tf32x3_kernel"][1],
-                           "kernel_ms": g_ms, "executed_tf32_tflops": exe_tf,
-                           "tf32_peak_assumed": bf16 / 2, "frac_executed_vs_tf32_peak": exe_tf / (bf16 / 2),
+                           "traffic": NCU_TRAFFIC[f"gemm_x3_kernel_{tensor_kind}"][0],
+                           "traffic_source": NCU_TRAFFIC[f"gemm_x3_kernel_{tensor_kind}"][1],
+                           "kernel_ms": g_ms, "executed_tflops": exe_tf,
+                           "executed_kind_peak": kind_peak, "frac_executed_vs_kind_peak": exe_tf / kind_peak,
+                           "kernel_ms_by_operand_format": gemm_ms,
                            "note": "achieved = algorithmic 8 real flop per beamlet*pixel; the kernel executes 3x "
-                                   "that in TF32 (hi/lo operand split needed for the 1e-5 parity); peak = "
-                                   "measured dense bf16 (MEASURED_PEAKS.json), TF32 peak taken as half of it",
+                                   "that (hi/lo operand split needed for the 1e-5 parity) in fp16 operands with "
+                                   "fp32 accumulation; peak = measured dense bf16 (MEASURED_PEAKS.json) = the "
+                                   "kind::f16 rate; the TF32 peak is taken as half of it",
                            "evals_per_s": nb * nr * W / (g_ms * 1e-3)}
-        del Ah, Al, Bh, Bl, Dg
+        del A32, B32, Dg
     clocks = sampler.stop() if rank == 0 else None
     if clocks and clocks.get("sm_mhz"):
         roofline_sfu["frac_at_observed_clock"] = mufu_rate / (sms * MUFU_PER_CLK_SM * clocks["sm_mhz"] * 1e6)
@@ -522,7 +536,7 @@ def run_ours(args):
         c3 = {"workload": "C3 biprism two_beam_interference: 1e5 beamlets through Lens, Biprism, Lens onto 2048x2048",
               "nominal_evals": ev3,
               "tensor_path": {"ms_per_image": t3, "nominal_evals_per_s": ev3 * world / (t3 * 1e-3),
-                              "executed_tf32_tflops": 3 * 2.0 * 2048 * 4096 * 200_000 / (t3 * 1e-3) / 1e12},
+                              "executed_f16_tflops": 3 * 2.0 * 2048 * 4096 * 200_000 / (t3 * 1e-3) / 1e12},
               "sfu_path_culled": {"ms_per_image": s3, "nominal_evals_per_s": ev3 * world / (s3 * 1e-3),
                                   "cull_bits": 40},
               "auto_default": {"ms_per_image": a3, "nominal_evals_per_s": ev3 * world / (a3 * 1e-3),
@@ -545,7 +559,10 @@ def run_ours(args):
             "metric": "beamlet_pixel_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32x3 (fp32-equivalent operands, fp32/fp64 accumulation)" if method != "sfu" else "f32",
+            "dtype": ("f32" if method == "sfu" else "tf32x3 (fp32 values split hi+lo, fp32/fp64 accumulation)"
+                      if method == "tensor_tf32" else
+                      "f16x3 (fp32 values split into fp16 hi+lo, 3 products, fp32/fp64 accumulation: "
+                      "fp32-equivalent, parity 1e-5 gate holds at ~1e-6)"),
             "data": "synthetic",
             "config": {"workload": "C2 aperture_diffraction: 1e4 Gaussian beamlets (fibonacci disc r=1e-7 m, "
                                    "lambda=2 pm, w0=1 nm) through ParallelBeam->Lens(f=1e-2)->Detector, summed "
@@ -582,7 +599,7 @@ def main():
     ap.add_argument("--skip-c3", action="store_true", help="skip the C3 (1e5 beamlets x 2048^2) section")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch the step's kernels directly instead of replaying a CUDA graph")
-    ap.add_argument("--method", default="auto", choices=["auto", "sfu", "tensor"],
+    ap.add_argument("--method", default="auto", choices=["auto", "sfu", "tensor", "tensor_tf32"],
                     help="field-sum path: auto = tensor cores when separable (C2 is), sfu = general kernel")
     args = ap.parse_args()
     if args.impl == "reference":

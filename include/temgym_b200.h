@@ -259,7 +259,8 @@ int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6],
  * return immediately. */
 #define TG_METHOD_AUTO 0   /* tensor-core path when the beamlets are separable, else SFU kernel */
 #define TG_METHOD_SFU 1    /* tg_field_sum_grid */
-#define TG_METHOD_TENSOR 2 /* tg_field_sum_separable (TG_ENOTSEPARABLE if it does not apply) */
+#define TG_METHOD_TENSOR 2 /* tg_field_sum_separable (TG_ENOTSEPARABLE if it does not apply): fp16 x 3 */
+#define TG_METHOD_TENSOR_TF32 3 /* the same GEMM with tf32 x 3 operands (fp32 exponent range, half the rate) */
 int tg_field_sum(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                  int nrows, void *out, int out_is_c128, int cull_bits, int method, void *stream);
 
@@ -270,6 +271,13 @@ int tg_field_sum(int64_t nb, const double *poly, const double px2m[6], int H, in
 int tg_gemm_tf32x3(int M, int N, int K, const float *A_hi, const float *A_lo, const float *B_hi,
                    const float *B_lo, long long ldk, double *D, long long ldd, int accumulate,
                    void *stream);
+/* The same with fp16 operands (device IEEE binary16, row pitch ldk elements, multiple of 8; hi and lo
+ * parts fp16 values): kind::f16 at twice the TF32 rate.  This is the engine tg_field_sum_separable and
+ * TG_METHOD_AUTO/TENSOR use; they pre-scale the factors on the device so that fp16's exponent range
+ * suffices and undo the scaling in the fp64 epilogue. */
+int tg_gemm_f16x3(int M, int N, int K, const void *A_hi, const void *A_lo, const void *B_hi,
+                  const void *B_lo, long long ldk, double *D, long long ldd, int accumulate,
+                  void *stream);
 
 /* ---- host-buffer field sum (make_gaussian_image end to end, gaussian.py:225-273) -- */
 /* All pointers HOST.  rays[7] are the central rays (length nb each), waist_xy /

@@ -20,7 +20,7 @@ TG_OP_KRIVANEK, TG_OP_OFFSET, TG_OP_THICKLENS, TG_OP_ROTATOR = 4, 5, 6, 7
 TG_F_NOPROP = 1
 TG_F_DIST = 2
 TG_JAC_NONE, TG_JAC_ABCD5, TG_JAC_FULL7 = 0, 1, 2
-TG_METHOD = {"auto": 0, "sfu": 1, "tensor": 2}
+TG_METHOD = {"auto": 0, "sfu": 1, "tensor": 2, "tensor_tf32": 3}
 TG_OK, TG_EINVAL, TG_ECUDA, TG_ENOTSEPARABLE, TG_EUNSUPPORTED = 0, -1, -2, -3, -4
 
 
@@ -85,6 +85,7 @@ SIGNATURES = {
     "tg_make_gaussian_image_f64": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(_vp), _vp, _vp, _vp,
                                           _vp, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "tg_gemm_tf32x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
+    "tg_gemm_f16x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
     "tg_make_gaussian_image_host": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(_vp), _vp, _vp, _vp,
                                            _vp, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32]),
 }

@@ -12,33 +12,47 @@
 //     B'[2col][2n]  = Re V, B'[2col][2n+1]  = -Im V   -> column 2col   = Re F
 //     B'[2col+1][2n]= Im V, B'[2col+1][2n+1]= Re V    -> column 2col+1 = Im F
 //     D = A' * B'^T                                                   (M x 2W)
-// Precision: operands are fp32 values split as x = hi + lo with hi = tf32(x) (round to
-// nearest), and D accumulates hi*hi + hi*lo + lo*hi on the tensor cores (kind::tf32, fp32
-// accumulation in TMEM) -> ~2^-22 relative per product.  The TMEM accumulator is drained
-// every 128 k-elements into fp32 registers (round-to-nearest adds), which bounds the
-// tensor-core accumulation length.
+// Precision: operands are fp32 values split as x = hi + lo, and D accumulates
+// hi*hi + hi*lo + lo*hi on the tensor cores with fp32 accumulation in TMEM -> ~2^-22 relative per
+// product.  Two operand formats (template parameter F16):
+//   * fp16 x 3 (default): hi = fp16(x), lo = fp16(x - hi); kind::f16 runs at twice the TF32 rate and
+//     the operands are half the bytes.  fp16 has 5 exponent bits, so the factors are pre-scaled on
+//     the device: U by 2^(14 - G) with G = ceil(log2 of the brightest row-factor peak of the call)
+//     and V (|V| <= 1 by construction) by 2^14; the epilogue multiplies by 2^(G - 28) in fp64
+//     (exact).  A factor keeps 22 bits down to 2^-17 of the brightest peak and degrades
+//     gracefully to an absolute floor of 2^-38 of it (fp16 subnormals).
+//   * tf32 x 3 (TG_METHOD_TENSOR_TF32): hi = tf32(x) (round to nearest), lo = x - hi; fp32 range.
+// The TMEM accumulator is drained every 128 k-elements into fp32 registers (round-to-nearest
+// adds), which bounds the tensor-core accumulation length.
 //
 // Kernel structure (one CTA per 128 x 128 output tile, 384 threads):
-//   warp 0   : TMA producer  - 4 tiles (A_hi, A_lo, B_hi, B_lo; 128 rows x 32 tf32 = 128 B rows,
-//              SWIZZLE_128B) per k-block into a 3-stage shared-memory ring, mbarrier expect_tx
-//   warp 1   : MMA issuer    - one thread issues 12 tcgen05.mma (3 products x 4 K-steps of 8)
+//   warp 0   : TMA producer  - 4 tiles (A_hi, A_lo, B_hi, B_lo; 128 rows x 128 B = 64 fp16 or
+//              32 tf32, SWIZZLE_128B) per k-block into a 3-stage shared-memory ring, mbarrier expect_tx
+//   warp 1   : MMA issuer    - one thread issues 12 tcgen05.mma (3 products x 4 K-steps of 32 B)
 //              per k-block into one of two 128-column TMEM accumulators; tcgen05.commit frees
 //              the smem stage / publishes the accumulator
 //   warp 2   : TMEM allocator (256 columns)
 //   warps 4-11: epilogue     - tcgen05.ld the finished accumulator (32x32b.x32), add into
 //              registers, release the accumulator; finally write doubles to the output
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <string.h>
 #include "tg_common.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32;      // BK tf32 elements = 128 bytes = one swizzle row
+constexpr int BM = 128, BN = 128;
+constexpr int BK_BYTES = 128;                   // one k-block = one 128-byte swizzle row per tile row
 constexpr int STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 4;         // 16 KiB
+constexpr int TILE_BYTES = BM * BK_BYTES;       // 16 KiB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;     // A_hi, A_lo, B_hi, B_lo
-constexpr int CHUNK_KB = 4;                     // k-blocks per TMEM accumulation chunk (128 k)
+constexpr int CHUNK_K = 128;                    // k-elements per TMEM accumulation chunk
+template <bool F16> struct GemmCfg {
+  static constexpr int ELEM = F16 ? 2 : 4;               // operand bytes
+  static constexpr int BK = BK_BYTES / ELEM;             // k-elements per k-block (64 fp16 / 32 tf32)
+  static constexpr int CHUNK_KB = CHUNK_K / BK;          // k-blocks per accumulation chunk
+};
 constexpr int GEMM_THREADS = 384;
 constexpr int TMEM_COLS = 256;                  // two 128-column fp32 accumulators
 
@@ -61,16 +75,28 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
                    tg_smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <bool F16>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  if constexpr (F16) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
   uint32_t r[32];
@@ -102,10 +128,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(const void *smem_tile) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10),
-// K-major A and B, N>>3 at bit 17, M>>4 at bit 24
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                            ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a/b format at bits 7/10
+// (F16 = 0, TF32 = 2), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
+template <bool F16> struct Idesc {
+  static constexpr uint32_t value = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) |
+                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
 
 struct GemmSmemCtl {
   uint64_t full[STAGES];
@@ -116,13 +144,17 @@ struct GemmSmemCtl {
 };
 
 // D[M x Np] (+)= A[M x K] * B[Np x K]^T with A = A_hi + A_lo, B = B_hi + B_lo (3 products).
-// out: doubles, row pitch ldo; rows >= M / columns >= Np are not written.
+// out: doubles, row pitch ldo; rows >= M / columns >= Np are not written.  out_scale (device, may be
+// NULL = 1): power-of-two factor applied to the accumulators in fp64 (undoes the fp16 pre-scaling).
+template <bool F16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-    gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                       const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                       int M, int Np, int K, double *__restrict__ out, long long ldo, int accumulate_out,
-                       const unsigned long long *__restrict__ sep_guard) {
+    gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                   int M, int Np, int K, double *__restrict__ out, long long ldo, int accumulate_out,
+                   const double *__restrict__ out_scale, const unsigned long long *__restrict__ sep_guard) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;  // the SFU path owns this call
+  constexpr int BK = GemmCfg<F16>::BK, CHUNK_KB = GemmCfg<F16>::CHUNK_KB;
+  constexpr uint32_t kIdesc = Idesc<F16>::value;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem) + 1023) &
                                                            ~uintptr_t(1023));
@@ -191,11 +223,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const uint64_t dBh = make_smem_desc(st + 2 * TILE_BYTES), dBl = make_smem_desc(st + 3 * TILE_BYTES);
         const uint32_t d = tmem_base + (uint32_t)(acc * BN);
 #pragma unroll
-        for (int k4 = 0; k4 < BK / 8; ++k4) {
-          const uint64_t ko = (uint64_t)(k4 * 32 >> 4);  // 8 tf32 = 32 bytes along the swizzled row
-          tc_mma_tf32(d, dAh + ko, dBh + ko, kIdesc, (chunk_start && k4 == 0) ? 0u : 1u);
-          tc_mma_tf32(d, dAh + ko, dBl + ko, kIdesc, 1u);
-          tc_mma_tf32(d, dAl + ko, dBh + ko, kIdesc, 1u);
+        for (int k4 = 0; k4 < BK_BYTES / 32; ++k4) {
+          const uint64_t ko = (uint64_t)(k4 * 32 >> 4);  // one MMA = 32 bytes (8 tf32 / 16 fp16) of the swizzled row
+          tc_mma<F16>(d, dAh + ko, dBh + ko, kIdesc, (chunk_start && k4 == 0) ? 0u : 1u);
+          tc_mma<F16>(d, dAh + ko, dBl + ko, kIdesc, 1u);
+          tc_mma<F16>(d, dAl + ko, dBh + ko, kIdesc, 1u);
         }
         tc_commit(&ctl->empty[s]);  // smem stage reusable once these MMAs have read it
         if ((kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1) {
@@ -231,13 +263,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (acc == 0) acc_ph ^= 1u;
     }
     const int row = m0 + q * 32 + lane;
+    const double sc = out_scale ? *out_scale : 1.0;
     if (row < M) {
       double *o = out + (long long)row * ldo + n0 + h * 64;
       const int ncol = min(64, Np - (n0 + h * 64));
       if (ncol == 64 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
         for (int i = 0; i < 64; i += 2) {
-          double2 w = make_double2((double)accum[i], (double)accum[i + 1]);
+          double2 w = make_double2((double)accum[i] * sc, (double)accum[i + 1] * sc);
           if (accumulate_out) {
             const double2 p = *reinterpret_cast<double2 *>(o + i);
             w.x += p.x;
@@ -248,7 +281,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       } else {
 #pragma unroll
         for (int i = 0; i < 64; ++i)
-          if (i < ncol) o[i] = (accumulate_out ? o[i] : 0.0) + (double)accum[i];
+          if (i < ncol) o[i] = (accumulate_out ? o[i] : 0.0) + (double)accum[i] * sc;
       }
     }
   }
@@ -291,6 +324,7 @@ __device__ __forceinline__ double col_env_max(double E1, double E3, double Wm1) 
 // SFU 6.3e-13 s per executed one -> 6.6 %; the estimate counts whole tiles, so stay below that)
 constexpr double kSfuWinsBelow = 0.045;
 constexpr int FS = 32;
+constexpr long long kBatch = 16384;  // beamlets per GEMM pass
 constexpr double kMagicF = 1572864.0;  // 1.5 * 2^20
 
 struct Strip1D {
@@ -330,54 +364,122 @@ __device__ __forceinline__ void strip_eval(const Strip1D &r, int j, float &re, f
   im = -amp * __sinf(ang);
 }
 
+// operand stores: one (re, im) pair of hi and of lo per call
+template <bool F16> struct Operand;
+template <> struct Operand<false> {
+  typedef float T;
+  static __device__ __forceinline__ void split(float x, float &hi, float &lo) {
+    hi = tf32_rna(x);
+    lo = x - hi;
+  }
+  static __device__ __forceinline__ void store2(void *base, long long o, float a, float b) {
+    *reinterpret_cast<float2 *>(static_cast<float *>(base) + o) = make_float2(a, b);
+  }
+};
+template <> struct Operand<true> {
+  typedef __half T;
+  static __device__ __forceinline__ void split(float x, float &hi, float &lo) {
+    hi = __half2float(__float2half_rn(x));
+    lo = __half2float(__float2half_rn(x - hi));
+  }
+  static __device__ __forceinline__ void store2(void *base, long long o, float a, float b) {
+    *reinterpret_cast<__half2 *>(static_cast<__half *>(base) + o) = __floats2half2_rn(a, b);  // exact: already fp16 values
+  }
+};
+// factors are scaled so that their peaks are <= 2^headroom: 14 for fp16 (max 65504); the tf32 factors get
+// the same treatment with headroom 0, which keeps weak beamlets out of the fp32 flush-to-zero range
+template <bool F16> struct Headroom { static constexpr double value = F16 ? 14.0 : 0.0; };
+
+// fp16 pre-scaling: G = ceil(max over beamlets of the peak of log2|U_n(row)| over the call's rows)
+__device__ __forceinline__ unsigned long long enc_ordered_max(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+__global__ void __launch_bounds__(256)
+    row_peak_kernel(const double *__restrict__ table, long long nb, int row0, int nrows, int W,
+                    unsigned long long *__restrict__ peak_key) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double best = -INFINITY;
+  if (i < nb) {
+    const double *t = table + i * 12;
+    const double q0 = t[6 + 0] + col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1)), q1 = t[6 + 2], q2 = t[6 + 5];
+    const double s_lo = (double)row0, s_hi = (double)(row0 + nrows - 1);
+    best = fmax(q0 + s_lo * (q1 + q2 * s_lo), q0 + s_hi * (q1 + q2 * s_hi));
+    if (q2 < 0.0) {
+      const double sv = fmin(fmax(-0.5 * q1 / q2, s_lo), s_hi);
+      best = fmax(best, q0 + sv * (q1 + q2 * sv));
+    }
+    if (!isfinite(best)) best = -INFINITY;  // NaN / inf beamlets do not set the scale (their factors carry them)
+  }
+  for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best > -INFINITY) atomicMax(peak_key, enc_ordered_max(best));
+}
+// shift[0] = G (bits subtracted from the row-factor exponent), shift[1] = 2^(G - 2*headroom) (epilogue scale)
+__global__ void prescale_kernel(const unsigned long long *__restrict__ peak_key, double headroom,
+                                double *__restrict__ shift) {
+  const unsigned long long k = *peak_key;
+  double G = 0.0;
+  if (k != 0ULL) {
+    const unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;
+    G = ceil(__longlong_as_double((long long)b));
+  }
+  G = fmin(fmax(G, -960.0), 960.0);
+  shift[0] = G;
+  shift[1] = exp2(G - 2.0 * headroom);
+}
+
 // A[(row - row0)][2n..2n+1] = U_n(row) for rows [row0, row0+M), beamlets [b0, b0+nbatch)
+template <bool F16>
 __global__ void __launch_bounds__(128)
     factor_rows_kernel(const double *__restrict__ table, long long b0, int nbatch, int row0, int M, int W,
-                       long long ldk, float *__restrict__ Ahi, float *__restrict__ Alo,
-                       const unsigned long long *__restrict__ sep_guard) {
+                       long long ldk, void *__restrict__ Ahi, void *__restrict__ Alo,
+                       const double *__restrict__ shift, const unsigned long long *__restrict__ sep_guard) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int m0 = blockIdx.y * FS;
   if (n >= nbatch) return;
   const double *t = table + (b0 + n) * 12;
-  const double mu = col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
+  double mu = col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
+  mu += Headroom<F16>::value - shift[0];
   const Strip1D st = strip_setup(t[0], t[2], t[5], t[6 + 0] + mu, t[6 + 2], t[6 + 5], (double)(row0 + m0));
 #pragma unroll 4
   for (int j = 0; j < FS; ++j) {
     if (m0 + j < M) {
-      float re, im;
+      float re, im, rh, rl, ih, il;
       strip_eval(st, j, re, im);
-      const float rh = tf32_rna(re), ih = tf32_rna(im);
+      Operand<F16>::split(re, rh, rl);
+      Operand<F16>::split(im, ih, il);
       const long long o = (long long)(m0 + j) * ldk + 2 * n;
-      *reinterpret_cast<float2 *>(Ahi + o) = make_float2(rh, ih);
-      *reinterpret_cast<float2 *>(Alo + o) = make_float2(re - rh, im - ih);
+      Operand<F16>::store2(Ahi, o, rh, ih);
+      Operand<F16>::store2(Alo, o, rl, il);
     }
   }
 }
 // B[2c][2n..] = (Re V, -Im V), B[2c+1][2n..] = (Im V, Re V), V_n(col) without the constant term
+template <bool F16>
 __global__ void __launch_bounds__(128)
     factor_cols_kernel(const double *__restrict__ table, long long b0, int nbatch, int W, long long ldk,
-                       float *__restrict__ Bhi, float *__restrict__ Blo,
+                       void *__restrict__ Bhi, void *__restrict__ Blo,
                        const unsigned long long *__restrict__ sep_guard) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = blockIdx.y * FS;
   if (n >= nbatch) return;
   const double *t = table + (b0 + n) * 12;
-  const double mu = col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
+  const double mu = col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1)) - Headroom<F16>::value;
   const Strip1D st = strip_setup(0.0, t[1], t[3], -mu, t[6 + 1], t[6 + 3], (double)c0);
 #pragma unroll 4
   for (int j = 0; j < FS; ++j) {
     if (c0 + j < W) {
-      float re, im;
+      float re, im, rh, rl, ih, il;
       strip_eval(st, j, re, im);
-      const float rh = tf32_rna(re), ih = tf32_rna(im);
-      const float rl = re - rh, il = im - ih;
+      Operand<F16>::split(re, rh, rl);
+      Operand<F16>::split(im, ih, il);
       const long long o0 = (long long)(2 * (c0 + j)) * ldk + 2 * n, o1 = o0 + ldk;
-      *reinterpret_cast<float2 *>(Bhi + o0) = make_float2(rh, -ih);
-      *reinterpret_cast<float2 *>(Blo + o0) = make_float2(rl, -il);
-      *reinterpret_cast<float2 *>(Bhi + o1) = make_float2(ih, rh);
-      *reinterpret_cast<float2 *>(Blo + o1) = make_float2(il, rl);
+      Operand<F16>::store2(Bhi, o0, rh, -ih);
+      Operand<F16>::store2(Blo, o0, rl, -il);
+      Operand<F16>::store2(Bhi, o1, ih, rh);
+      Operand<F16>::store2(Blo, o1, il, rl);
     }
   }
 }
@@ -472,20 +574,22 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D fp32 row-major (rows x K, pitch ldk elements), box = 128 rows x 32 elements, 128B swizzle
-int make_map(CUtensorMap *m, const float *base, long long rows, long long K, long long ldk) {
+// 2-D row-major operand (rows x K elements of 4 (tf32) or 2 (fp16) bytes, pitch ldk elements),
+// box = 128 rows x 128 bytes, 128B swizzle
+template <bool F16>
+int make_map(CUtensorMap *m, const void *base, long long rows, long long K, long long ldk) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     tg_set_error("cuTensorMapEncodeTiled entry point not available");
     return TG_ECUDA;
   }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ldk * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint64_t strides[1] = {(cuuint64_t)ldk * GemmCfg<F16>::ELEM};
+  cuuint32_t box[2] = {(cuuint32_t)GemmCfg<F16>::BK, (cuuint32_t)BM};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(m, F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     tg_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return TG_ECUDA;
@@ -493,21 +597,44 @@ int make_map(CUtensorMap *m, const float *base, long long rows, long long K, lon
   return TG_OK;
 }
 
-int launch_gemm(const float *Ahi, const float *Alo, const float *Bhi, const float *Blo, int M, int Np, int K,
-                long long ldk, double *out, long long ldo, int accumulate,
+template <bool F16>
+int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *Blo, int M, int Np, int K,
+                long long ldk, double *out, long long ldo, int accumulate, const double *out_scale,
                 const unsigned long long *sep_guard, cudaStream_t st) {
   CUtensorMap ta, tb, tc, td;
   int rc;
-  if ((rc = make_map(&ta, Ahi, M, K, ldk)) != TG_OK) return rc;
-  if ((rc = make_map(&tb, Alo, M, K, ldk)) != TG_OK) return rc;
-  if ((rc = make_map(&tc, Bhi, Np, K, ldk)) != TG_OK) return rc;
-  if ((rc = make_map(&td, Blo, Np, K, ldk)) != TG_OK) return rc;
+  if ((rc = make_map<F16>(&ta, Ahi, M, K, ldk)) != TG_OK) return rc;
+  if ((rc = make_map<F16>(&tb, Alo, M, K, ldk)) != TG_OK) return rc;
+  if ((rc = make_map<F16>(&tc, Bhi, Np, K, ldk)) != TG_OK) return rc;
+  if ((rc = make_map<F16>(&td, Blo, Np, K, ldk)) != TG_OK) return rc;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
-  TG_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((Np + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
-  gemm_tf32x3_kernel<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, tc, td, M, Np, K, out, ldo, accumulate,
-                                                       sep_guard);
-  return tg_launch_check("gemm_tf32x3_kernel");
+  gemm_x3_kernel<F16><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, tc, td, M, Np, K, out, ldo, accumulate, out_scale,
+                                                        sep_guard);
+  return tg_launch_check(F16 ? "gemm_x3_kernel<f16>" : "gemm_x3_kernel<tf32>");
+}
+
+template <bool F16>
+int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, long long ldk, void *Ahi, void *Alo,
+                void *Bhi, void *Blo, double *acc, const double *shift, const unsigned long long *guard,
+                cudaStream_t st) {
+  const int Np = 2 * W;
+  int rc = TG_OK;
+  for (long long b0 = 0; b0 < nb && rc == TG_OK; b0 += kBatch) {
+    const int nbatch = (int)((nb - b0) < kBatch ? (nb - b0) : kBatch);
+    const int K = 2 * nbatch;
+    // (the tensor maps are encoded with the true K: the TMA unit zero-fills the K padding)
+    dim3 ga((unsigned)((nbatch + 127) / 128), (unsigned)((nrows + FS - 1) / FS));
+    dim3 gb((unsigned)((nbatch + 127) / 128), (unsigned)((W + FS - 1) / FS));
+    factor_rows_kernel<F16><<<ga, 128, 0, st>>>(table, b0, nbatch, row0, nrows, W, ldk, Ahi, Alo, shift, guard);
+    factor_cols_kernel<F16><<<gb, 128, 0, st>>>(table, b0, nbatch, W, ldk, Bhi, Blo, guard);
+    rc = tg_launch_check("factor kernels");
+    if (rc == TG_OK)
+      rc = launch_gemm<F16>(Ahi, Alo, Bhi, Blo, nrows, Np, K, ldk, acc, (long long)Np, b0 > 0 ? 1 : 0,
+                            shift + 1, guard, st);
+  }
+  return rc;
 }
 
 }  // namespace
@@ -522,19 +649,32 @@ extern "C" int tg_gemm_tf32x3(int M, int N, int K, const float *A_hi, const floa
   TG_REQUIRE(((uintptr_t)A_hi % 16) == 0 && ((uintptr_t)A_lo % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 &&
                  ((uintptr_t)B_lo % 16) == 0,
              "operands must be 16-byte aligned");
-  return launch_gemm(A_hi, A_lo, B_hi, B_lo, M, N, K, ldk, D, ldd, accumulate, nullptr,
-                     static_cast<cudaStream_t>(stream));
+  return launch_gemm<false>(A_hi, A_lo, B_hi, B_lo, M, N, K, ldk, D, ldd, accumulate, nullptr, nullptr,
+                            static_cast<cudaStream_t>(stream));
+}
+// the same with fp16 operands (IEEE binary16, 2 bytes each): 3 x kind::f16 at twice the TF32 rate
+extern "C" int tg_gemm_f16x3(int M, int N, int K, const void *A_hi, const void *A_lo, const void *B_hi,
+                             const void *B_lo, long long ldk, double *D, long long ldd, int accumulate,
+                             void *stream) {
+  TG_REQUIRE(M > 0 && N > 0 && K > 0, "bad GEMM shape");
+  TG_REQUIRE(A_hi && A_lo && B_hi && B_lo && D, "null pointer");
+  TG_REQUIRE(ldk >= K && (ldk % 8) == 0, "ldk must be >= K and a multiple of 8 (16-byte TMA pitch)");
+  TG_REQUIRE(((uintptr_t)A_hi % 16) == 0 && ((uintptr_t)A_lo % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 &&
+                 ((uintptr_t)B_lo % 16) == 0,
+             "operands must be 16-byte aligned");
+  return launch_gemm<true>(A_hi, A_lo, B_hi, B_lo, M, N, K, ldk, D, ldd, accumulate, nullptr, nullptr,
+                           static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6], int H, int W,
                                       int row0, int nrows, void *out, int out_is_c128, void *stream) {
   return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr,
-                          static_cast<cudaStream_t>(stream), 0);
+                          static_cast<cudaStream_t>(stream), 0, 1);
 }
 
 int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                      int nrows, void *out, int out_is_c128, unsigned long long *key_async,
-                     cudaStream_t stream, int cost_cull_bits) {
+                     cudaStream_t stream, int cost_cull_bits, int f16) {
   TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad shape");
   TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
   TG_REQUIRE(px2m && out, "null pointer");
@@ -550,27 +690,27 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   TG_CUDA(cudaGetDevice(&dev));
   tg_tune_mempool(dev);
 
-  const long long kBatch = 16384;  // beamlets per GEMM pass
   const long long nbatch_max = nb < kBatch ? nb : kBatch;
-  const long long ldk = ((2 * nbatch_max + 31) / 32) * 32;
+  const long long ldk = ((2 * nbatch_max + 63) / 64) * 64;  // whole 128-byte k-blocks in either format
+  const size_t elem = f16 ? 2 : 4;
   const int Np = 2 * W;
   const size_t table_bytes = (((size_t)nb * 96 + 255) / 256) * 256;
-  const size_t a_bytes = (((size_t)nrows * ldk * 4 + 255) / 256) * 256;
-  const size_t b_bytes = (((size_t)Np * ldk * 4 + 255) / 256) * 256;
+  const size_t a_bytes = (((size_t)nrows * ldk * elem + 255) / 256) * 256;
+  const size_t b_bytes = (((size_t)Np * ldk * elem + 255) / 256) * 256;
   const size_t acc_bytes = out_is_c128 ? 0 : npix * 16;
   unsigned char *ws = nullptr;
   TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), table_bytes + 256 + 2 * a_bytes + 2 * b_bytes + acc_bytes, st));
   double *table = reinterpret_cast<double *>(ws);
+  // control block after the table: key (8) | peak key (8) | shift[2] (16) || gref (8) at +64 || est (8) at +128
   unsigned long long *key = key_async ? key_async : reinterpret_cast<unsigned long long *>(ws + table_bytes);
+  unsigned long long *peak = reinterpret_cast<unsigned long long *>(ws + table_bytes + 8);
+  double *shift = reinterpret_cast<double *>(ws + table_bytes + 16);
   const unsigned long long *guard = key_async;  // async mode: kernels decide on the device
-  float *Ahi = reinterpret_cast<float *>(ws + table_bytes + 256);
-  float *Alo = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Ahi) + a_bytes);
-  float *Bhi = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Alo) + a_bytes);
-  float *Blo = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Bhi) + b_bytes);
-  double *acc = out_is_c128 ? static_cast<double *>(out)
-                            : reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(Blo) + b_bytes);
+  unsigned char *Ahi = ws + table_bytes + 256, *Alo = Ahi + a_bytes, *Bhi = Alo + a_bytes, *Blo = Bhi + b_bytes;
+  double *acc = out_is_c128 ? static_cast<double *>(out) : reinterpret_cast<double *>(Blo + b_bytes);
   int rc = TG_OK;
-  cudaError_t e = cudaMemsetAsync(key, 0, 8, st);
+  cudaError_t e = cudaMemsetAsync(ws + table_bytes, 0, 32, st);  // own key slot, peak key, shift
+  if (key_async && e == cudaSuccess) e = cudaMemsetAsync(key, 0, 8, st);
   // cost model (AUTO with culling enabled): brightest-peak key and tile estimate live after the key slot
   const bool cost = key_async != nullptr && cost_cull_bits > 0;
   unsigned long long *gref = reinterpret_cast<unsigned long long *>(ws + table_bytes + 64);
@@ -586,6 +726,11 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
     sfu_cost_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(table, nb, H, W, gref, cost_cull_bits, est);
     verdict_kernel<<<1, 1, 0, st>>>(key, est, (double)nb * (double)H * (double)W, kSfuWinsBelow);
     rc = tg_launch_check("cost kernels");
+  }
+  if (e == cudaSuccess && rc == TG_OK) {
+    row_peak_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(table, nb, row0, nrows, W, peak);
+    prescale_kernel<<<1, 1, 0, st>>>(peak, f16 ? Headroom<true>::value : Headroom<false>::value, shift);
+    rc = tg_launch_check("pre-scaling kernels");
   }
   unsigned long long hkey = 0;
   if (e == cudaSuccess && rc == TG_OK && !key_async) {
@@ -604,17 +749,9 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
       rc = TG_ENOTSEPARABLE;
     }
   }
-  for (long long b0 = 0; b0 < nb && rc == TG_OK; b0 += kBatch) {
-    const int nbatch = (int)((nb - b0) < kBatch ? (nb - b0) : kBatch);
-    const int K = 2 * nbatch;
-    // (the tensor maps are encoded with the true K: the TMA unit zero-fills the K padding)
-    dim3 ga((unsigned)((nbatch + 127) / 128), (unsigned)((nrows + FS - 1) / FS));
-    dim3 gb((unsigned)((nbatch + 127) / 128), (unsigned)((W + FS - 1) / FS));
-    factor_rows_kernel<<<ga, 128, 0, st>>>(table, b0, nbatch, row0, nrows, W, ldk, Ahi, Alo, guard);
-    factor_cols_kernel<<<gb, 128, 0, st>>>(table, b0, nbatch, W, ldk, Bhi, Blo, guard);
-    rc = tg_launch_check("factor kernels");
-    if (rc == TG_OK) rc = launch_gemm(Ahi, Alo, Bhi, Blo, nrows, Np, K, ldk, acc, (long long)Np, b0 > 0 ? 1 : 0, guard, st);
-  }
+  if (rc == TG_OK)
+    rc = f16 ? run_batches<true>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, shift, guard, st)
+             : run_batches<false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, shift, guard, st);
   if (rc == TG_OK && !out_is_c128) {
     const size_t n = npix * 2;
     f64_to_c64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, static_cast<float *>(out), n, guard);
@@ -630,14 +767,15 @@ extern "C" int tg_field_sum(int64_t nb, const double *poly, const double px2m[6]
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (method == TG_METHOD_SFU)
     return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st);
-  if (method == TG_METHOD_TENSOR)
-    return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr, st, 0);
+  if (method == TG_METHOD_TENSOR || method == TG_METHOD_TENSOR_TF32)
+    return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr, st, 0,
+                            method == TG_METHOD_TENSOR);
   TG_REQUIRE(method == TG_METHOD_AUTO, "unknown method");
   if (nb == 0 || nrows == 0)
     return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st);
   unsigned long long *key = nullptr;
   TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&key), 8, st));
-  int rc = tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, key, st, cull_bits);
+  int rc = tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, key, st, cull_bits, 1);
   if (rc == TG_OK)
     rc = tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, key, st);
   cudaFreeAsync(key, st);

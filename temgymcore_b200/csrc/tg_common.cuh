@@ -20,9 +20,10 @@ int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int 
 // this path return at once when it says "not separable".
 // cost_cull_bits > 0 (async mode only): also estimate the culled SFU work and leave the call to the SFU
 // path when that is clearly cheaper than the dense GEMM.
+// f16 != 0: fp16 x 3 operands (kind::f16, device-side pre-scaling), else tf32 x 3.
 int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                      int nrows, void *out, int out_is_c128, unsigned long long *key_async,
-                     cudaStream_t stream, int cost_cull_bits);
+                     cudaStream_t stream, int cost_cull_bits, int f16);
 // separability key = bits of max_n(cross term / tolerance) as a double (0 when there is none)
 __host__ __device__ inline bool tg_key_is_separable(unsigned long long key) {
   union { unsigned long long u; double d; } c;

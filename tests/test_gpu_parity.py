@@ -489,18 +489,73 @@ def test_gemm_tf32x3_against_fp64(torch_cuda, M, N, K):
     assert float((D[:, :N] - 2 * ref).norm() / ref.norm()) < 4e-6
 
 
+def _f16_split(torch, x):
+    """x = hi + lo with hi = fp16(x), lo = fp16(x - hi), like the fp16 factor kernels."""
+    hi = x.half()
+    return hi, (x - hi.float()).half()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 512), (256, 384, 1536), (200, 136, 1000),
+                                   (1024, 256, 4100), (77, 50, 36), (1536, 2304, 300), (1024, 2048, 2000)])
+def test_gemm_f16x3_against_fp64(torch_cuda, M, N, K):
+    from temgymcore_b200 import _lib as L
+    torch = torch_cuda
+    lib = L.load()
+    gen = torch.Generator(device="cuda").manual_seed(M * 1000 + K)
+    ldk = ((K + 7) // 8) * 8 + 16
+    A = torch.zeros((M, ldk), dtype=torch.float32, device="cuda")
+    B = torch.zeros((N, ldk), dtype=torch.float32, device="cuda")
+    A[:, :K] = torch.rand((M, K), generator=gen, device="cuda") * 2 - 1
+    B[:, :K] = torch.rand((N, K), generator=gen, device="cuda") * 2 - 1
+    A[:, K:] = 7.0   # pitch padding must never be read (the tensor map ends at K)
+    B[:, K:] = 7.0
+    Ah, Al = _f16_split(torch, A)
+    Bh, Bl = _f16_split(torch, B)
+    D = torch.full((M, N + 3), -1.0, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.tg_gemm_f16x3(M, N, K, Ah.data_ptr(), Al.data_ptr(), Bh.data_ptr(), Bl.data_ptr(), ldk,
+                           D.data_ptr(), N + 3, 0, st)
+    L.check(rc, "tg_gemm_f16x3")
+    ref = A[:, :K].double() @ B[:, :K].double().T
+    err = (D[:, :N] - ref).norm() / ref.norm()
+    assert float(err) < 3e-6, float(err)
+    assert bool((D[:, N:] == -1.0).all())  # columns beyond N untouched
+    rc = lib.tg_gemm_f16x3(M, N, K, Ah.data_ptr(), Al.data_ptr(), Bh.data_ptr(), Bl.data_ptr(), ldk,
+                           D.data_ptr(), N + 3, 1, st)
+    L.check(rc, "tg_gemm_f16x3 accumulate")
+    assert float((D[:, :N] - 2 * ref).norm() / ref.norm()) < 4e-6
+
+
+@pytest.mark.parametrize("method", ["tensor", "tensor_tf32"])
 @pytest.mark.parametrize("name", ["c2_aperture", "c3_biprism_separable"])
-def test_tensor_path_parity(torch_cuda, name):
+def test_tensor_path_parity(torch_cuda, name, method):
     from temgymcore_b200.gaussian import make_gaussian_image
     g, model = field_cases()[name]
     ref = O.make_gaussian_image(g, model)
-    got = make_gaussian_image(g, model, method="tensor")
+    got = make_gaussian_image(g, model, method=method)
     assert got.shape == ref.shape and got.dtype == np.complex128
     assert rel_l2(got, ref) < FIELD_TOL, rel_l2(got, ref)
     sfu = make_gaussian_image(g, model, method="sfu", cull_bits=0)
     assert rel_l2(got, sfu) < FIELD_TOL
-    auto = make_gaussian_image(g, model)  # auto picks the tensor path: same bits
-    np.testing.assert_array_equal(auto, got)
+    if method == "tensor":
+        auto = make_gaussian_image(g, model)  # auto picks the fp16 tensor path: same bits
+        np.testing.assert_array_equal(auto, got)
+
+
+@pytest.mark.parametrize("scale", [1e-30, 1.0, 1e25])
+def test_tensor_path_fp16_dynamic_range(torch_cuda, scale):
+    """fp16 operands: amplitudes spread over six decades and an arbitrary global scale must not cost
+    accuracy (the factors are pre-scaled on the device, the epilogue undoes it in fp64)."""
+    from dataclasses import replace
+    from temgymcore_b200.gaussian import make_gaussian_image
+    g, model = field_cases()["c3_biprism_separable"]
+    rng = np.random.default_rng(M.SEED + 5)
+    amp = np.asarray(g.amplitude, dtype=np.float64) * 10.0 ** rng.uniform(-6, 0, np.shape(g.amplitude)) * scale
+    g2 = replace(g, amplitude=amp)
+    ref = O.make_gaussian_image(g2, model)
+    for method in ("tensor", "tensor_tf32"):
+        got = make_gaussian_image(g2, model, method=method)
+        assert rel_l2(got, ref) < FIELD_TOL, (method, rel_l2(got, ref))
 
 
 def test_tensor_path_rejects_non_separable(torch_cuda):
