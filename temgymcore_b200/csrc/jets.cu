@@ -134,90 +134,194 @@ enum {
   K_PHI34, K_C41, K_PHI41, K_C43, K_PHI43, K_C45, K_PHI45, K_C50, K_C52, K_PHI52, K_C54,
   K_PHI54, K_C56, K_PHI56
 };
+// Polynomial form (see trace.cu): with w = ax + i ay, r2 = |w|^2 and z_nm = C_nm / (n + 1) exp(-i m phi_nm)
+//     W = Re[ F0(w) + r2 F1(w) + r2^2 F2(w) + r2^3 F3 ],   F_b = sum of z_nm w^m over the terms with (n + 1 - m) / 2 = b,
+//     dW/dax + i dW/day = sum_b [ r2^b conj(F_b'(w)) + 2 b r2^(b-1) w Re F_b(w) ],
+// evaluated directly in hyper-dual arithmetic: products and sums only (no hypot / arctan2 / reciprocal
+// compositions), 13 hyper-dual products for the BASELINE C4 coefficients instead of ~40 in polar form.
+// The products inside use fused multiply-adds (this TU is built with -fmad=false; fma() is honoured).
 template <int P>
-__device__ __forceinline__ void hterm(double C, double m, const HD<P> &cm, const HD<P> &sm, double c0,
-                                      double s0, HD<P> &B, HD<P> &T) {
+__device__ __forceinline__ HD<P> hfmul(const HD<P> &a, const HD<P> &b) {
+  HD<P> r;
+#pragma unroll
+  for (int m = 0; m < HD<P>::M; ++m) {
+    double acc = a.c[0] * b.c[m];
+#pragma unroll
+    for (int s = 1; s < HD<P>::M; ++s)
+      if ((s & m) == s) acc = fma(a.c[s], b.c[m ^ s], acc);
+    r.c[m] = acc;
+  }
+  return r;
+}
+template <int P>
+__device__ __forceinline__ void haxpy(HD<P> &acc, double s, const HD<P> &a) {   // acc += s a
+#pragma unroll
+  for (int m = 0; m < HD<P>::M; ++m) acc.c[m] = fma(s, a.c[m], acc.c[m]);
+}
+template <int P>
+struct CH {
+  HD<P> re, im;
+};
+template <int P>
+__device__ __forceinline__ CH<P> chmul(const CH<P> &a, const CH<P> &b) {
+  CH<P> r;
+  r.re = hfmul(a.re, b.re) - hfmul(a.im, b.im);
+  r.im = hfmul(a.re, b.im) + hfmul(a.im, b.re);
+  return r;
+}
+template <int P>
+__device__ __forceinline__ CH<P> chsqr(const CH<P> &a) {
+  CH<P> r;
+  r.re = hfmul(a.re, a.re) - hfmul(a.im, a.im);
+  r.im = hfmul(a.re, a.im) * 2.0;
+  return r;
+}
+// one group r2^B Re F_B(w) of the polynomial form
+template <int P>
+struct KGroup {
+  double f0;            // the m = 0 term (real constant)
+  double d1r, d1i;      // the m = 1 term's coefficient = constant part of F_B'
+  CH<P> F, D;           // sum_{m >= 1} z w^m,  sum_{m >= 2} m z w^(m-1)
+  bool hasF, hasD;
+};
+template <int P>
+__device__ __forceinline__ void kgroup_init(KGroup<P> &G, double f0) {
+  G.f0 = f0;
+  G.d1r = G.d1i = 0.0;
+  G.F.re = G.F.im = G.D.re = G.D.im = hconst<P>(0.0);
+  G.hasF = G.hasD = false;
+}
+// term z w^K, z = kappa C (c0 - i s0); wk = w^K, wkm1 = w^(K-1)
+template <int K, int P>
+__device__ __forceinline__ void kgroup_term(KGroup<P> &G, double C, double kappa, double c0, double s0,
+                                            const CH<P> &wk, const CH<P> &wkm1) {
   if (C == 0.0) return;
-  B = B + (cm * c0 + sm * s0) * C;
-  T = T + (sm * c0 - cm * s0) * (-m * C);
+  const double s = C * kappa, zr = s * c0, zi = -(s * s0);
+  haxpy(G.F.re, zr, wk.re);
+  haxpy(G.F.re, -zi, wk.im);
+  haxpy(G.F.im, zr, wk.im);
+  haxpy(G.F.im, zi, wk.re);
+  G.hasF = true;
+  if constexpr (K == 1) {
+    G.d1r += zr;
+    G.d1i += zi;
+  } else {
+    const double kr = (double)K * zr, ki = (double)K * zi;
+    haxpy(G.D.re, kr, wkm1.re);
+    haxpy(G.D.re, -ki, wkm1.im);
+    haxpy(G.D.im, kr, wkm1.im);
+    haxpy(G.D.im, ki, wkm1.re);
+    G.hasD = true;
+  }
+}
+// fold a group into W and (Gx, Gy): rho = r2^B, rhom = r2^(B-1) (B >= 2)
+template <int B, int P>
+__device__ __forceinline__ void kgroup_fold(const KGroup<P> &G, const HD<P> &u, const HD<P> &v, const HD<P> &rho,
+                                            const HD<P> &rhom, HD<P> &W, HD<P> &Gx, HD<P> &Gy) {
+  using S = HD<P>;
+  if constexpr (B == 0) {
+    W = W + G.F.re;
+    Gx = Gx + G.D.re;
+    Gy = Gy - G.D.im;
+  } else {
+    // W += rho Re F ; grad += rho conj(F') + 2 B rho^(B-1) w Re F
+    haxpy(W, G.f0, rho);
+    if (G.hasF) W = W + hfmul(rho, G.F.re);
+    haxpy(Gx, G.d1r, rho);
+    haxpy(Gy, -G.d1i, rho);
+    if (G.hasD) {
+      Gx = Gx + hfmul(rho, G.D.re);
+      Gy = Gy - hfmul(rho, G.D.im);
+    }
+    if (B == 1 && !G.hasF) {
+      haxpy(Gx, 2.0 * G.f0, u);
+      haxpy(Gy, 2.0 * G.f0, v);
+    } else {
+      S t;
+      if constexpr (B == 1) {
+        t = G.F.re + G.f0;
+      } else {
+        t = rhom * G.f0;
+        if (G.hasF) t = t + hfmul(rhom, G.F.re);
+      }
+      t = t * (2.0 * (double)B);
+      Gx = Gx + hfmul(u, t);
+      Gy = Gy + hfmul(v, t);
+    }
+  }
 }
 template <int P>
 __device__ __forceinline__ void hkrivanek(const double *p, const HD<P> &ax, const HD<P> &ay, HD<P> &dWx,
                                           HD<P> &dWy, HD<P> &W) {
   using S = HD<P>;
-  const S a = hsqrt(ax * ax + ay * ay);               // jnp.hypot; derivatives are NaN at the origin like JAX's
-  S ia, c1, s1;                                       // unit phasor e^{i phi} = (ax + i ay) / |a|
-  if (a.c[0] == 0.0) {
-    // on-axis ray: phi = arctan2(0, 0) = 0 and alpha_safe = 1e-30 in the reference (aberrations.py:66,
-    // 100-102), with NaN derivatives through hypot / arctan2 -- values stay finite, derivatives are NaN
-    ia = hconst<P>(1e30);
-    c1 = hconst<P>(1.0);
-    s1 = hconst<P>(0.0);
-#pragma unroll
-    for (int m = 1; m < HD<P>::M; ++m) c1.c[m] = s1.c[m] = nan("");
-  } else {
-    ia = hrecip(a);
-    c1 = ax * ia;
-    s1 = ay * ia;
-  }
-  const bool u6 = p[K_C56] != 0.0, u5 = p[K_C45] != 0.0;
-  const bool u4 = p[K_C34] != 0.0 || p[K_C54] != 0.0 || u5;
-  const bool u3 = p[K_C23] != 0.0 || p[K_C43] != 0.0 || u6 || u5;
-  const bool u2 = p[K_C12] != 0.0 || p[K_C32] != 0.0 || p[K_C52] != 0.0 || u3 || u4;
-  S c2 = hconst<P>(0.0), s2 = c2, c3 = c2, s3 = c2, c4 = c2, s4 = c2, c5 = c2, s5 = c2, c6 = c2, s6 = c2;
-  if (u2) { c2 = c1 * c1 - s1 * s1; s2 = (c1 * s1) * 2.0; }
-  if (u3) { c3 = c2 * c1 - s2 * s1; s3 = s2 * c1 + c2 * s1; }
-  if (u4) { c4 = c2 * c2 - s2 * s2; s4 = (c2 * s2) * 2.0; }
-  if (u5) { c5 = c4 * c1 - s4 * s1; s5 = s4 * c1 + c4 * s1; }
-  if (u6) { c6 = c3 * c3 - s3 * s3; s6 = (c3 * s3) * 2.0; }
   const double *g = p + 25;                           // (cos, sin)(m phi0) pairs
-  // Radial orders n = 2..6 are folded into W, dW/dalpha and dW/dphi one at a time (aberrations.py:51-98)
-  // so that a bracket B_n / T_n dies as soon as it is used: the live set stays at three accumulators,
-  // the phasor powers and one power of alpha (order 3 needs 8 doubles per quantity).
-  S an = a;                                           // alpha^(n-1)
-  S dWa = hconst<P>(0.0), q = dWa;
-  W = dWa;
-  auto fold = [&](const S &Bn, const S &Tn, double inv_n) {
-    dWa = dWa + an * Bn;                              // alpha^(n-1) B_n
-    const S wn = (an * a) * inv_n;                    // alpha^n / n
-    W = W + wn * Bn;
-    q = q + wn * Tn;
-    an = an * a;
-  };
-  {
-    S B = hconst<P>(p[K_C10]), T = hconst<P>(0.0);
-    hterm(p[K_C12], 2.0, c2, s2, g[0], g[1], B, T);
-    fold(B, T, 0.5);
+  // highest power of w in use (uniform branches on kernel-parameter constants)
+  int kmax = 0;
+  if (p[K_C21] != 0.0 || p[K_C41] != 0.0) kmax = 1;
+  if (p[K_C12] != 0.0 || p[K_C32] != 0.0 || p[K_C52] != 0.0) kmax = 2;
+  if (p[K_C23] != 0.0 || p[K_C43] != 0.0) kmax = 3;
+  if (p[K_C34] != 0.0 || p[K_C54] != 0.0) kmax = 4;
+  if (p[K_C45] != 0.0) kmax = 5;
+  if (p[K_C56] != 0.0) kmax = 6;
+  const S uu = hfmul(ax, ax), vv = hfmul(ay, ay);
+  const S r2 = uu + vv;
+  CH<P> w0, w1, w2, w3, w4, w5, w6;
+  w0.re = hconst<P>(1.0);
+  w0.im = hconst<P>(0.0);
+  w1.re = ax;
+  w1.im = ay;
+  w2 = w3 = w4 = w5 = w6 = w0;
+  if (kmax >= 2) {
+    w2.re = uu - vv;
+    w2.im = hfmul(ax, ay) * 2.0;
   }
-  {
-    S B = hconst<P>(0.0), T = B;
-    hterm(p[K_C21], 1.0, c1, s1, g[2], g[3], B, T);
-    hterm(p[K_C23], 3.0, c3, s3, g[4], g[5], B, T);
-    fold(B, T, 1.0 / 3.0);
+  if (kmax >= 3) w3 = chmul(w2, w1);
+  if (kmax >= 4) w4 = chsqr(w2);
+  if (kmax >= 5) w5 = chmul(w4, w1);
+  if (kmax >= 6) w6 = chsqr(w3);
+  W = hconst<P>(0.0);
+  dWx = W;
+  dWy = W;
+  KGroup<P> G;
+  // b = 0: m = n + 1
+  if (p[K_C12] != 0.0 || p[K_C23] != 0.0 || p[K_C34] != 0.0 || p[K_C45] != 0.0 || p[K_C56] != 0.0) {
+    kgroup_init(G, 0.0);
+    kgroup_term<2>(G, p[K_C12], 0.5, g[0], g[1], w2, w1);
+    kgroup_term<3>(G, p[K_C23], 1.0 / 3.0, g[4], g[5], w3, w2);
+    kgroup_term<4>(G, p[K_C34], 0.25, g[8], g[9], w4, w3);
+    kgroup_term<5>(G, p[K_C45], 0.2, g[14], g[15], w5, w4);
+    kgroup_term<6>(G, p[K_C56], 1.0 / 6.0, g[20], g[21], w6, w5);
+    kgroup_fold<0>(G, ax, ay, r2, r2, W, dWx, dWy);
   }
-  {
-    S B = hconst<P>(p[K_C30]), T = hconst<P>(0.0);
-    hterm(p[K_C32], 2.0, c2, s2, g[6], g[7], B, T);
-    hterm(p[K_C34], 4.0, c4, s4, g[8], g[9], B, T);
-    fold(B, T, 0.25);
+  // b = 1: m = n - 1
+  if (p[K_C10] != 0.0 || p[K_C21] != 0.0 || p[K_C32] != 0.0 || p[K_C43] != 0.0 || p[K_C54] != 0.0) {
+    kgroup_init(G, 0.5 * p[K_C10]);
+    kgroup_term<1>(G, p[K_C21], 1.0 / 3.0, g[2], g[3], w1, w0);
+    kgroup_term<2>(G, p[K_C32], 0.25, g[6], g[7], w2, w1);
+    kgroup_term<3>(G, p[K_C43], 0.2, g[12], g[13], w3, w2);
+    kgroup_term<4>(G, p[K_C54], 1.0 / 6.0, g[18], g[19], w4, w3);
+    kgroup_fold<1>(G, ax, ay, r2, r2, W, dWx, dWy);
   }
-  {
-    S B = hconst<P>(0.0), T = B;
-    hterm(p[K_C41], 1.0, c1, s1, g[10], g[11], B, T);
-    hterm(p[K_C43], 3.0, c3, s3, g[12], g[13], B, T);
-    hterm(p[K_C45], 5.0, c5, s5, g[14], g[15], B, T);
-    fold(B, T, 0.2);
+  const bool b2 = p[K_C30] != 0.0 || p[K_C41] != 0.0 || p[K_C52] != 0.0, b3 = p[K_C50] != 0.0;
+  if (b2 || b3) {
+    const S r4 = hfmul(r2, r2);
+    if (b2) {   // b = 2: m = n - 3
+      kgroup_init(G, 0.25 * p[K_C30]);
+      kgroup_term<1>(G, p[K_C41], 0.2, g[10], g[11], w1, w0);
+      kgroup_term<2>(G, p[K_C52], 1.0 / 6.0, g[16], g[17], w2, w1);
+      kgroup_fold<2>(G, ax, ay, r4, r2, W, dWx, dWy);
+    }
+    if (b3) {   // b = 3: C50 alpha^6 / 6
+      kgroup_init(G, p[K_C50] * (1.0 / 6.0));
+      kgroup_fold<3>(G, ax, ay, hfmul(r4, r2), r4, W, dWx, dWy);
+    }
   }
-  {
-    S B = hconst<P>(p[K_C50]), T = hconst<P>(0.0);
-    hterm(p[K_C52], 2.0, c2, s2, g[16], g[17], B, T);
-    hterm(p[K_C54], 4.0, c4, s4, g[18], g[19], B, T);
-    hterm(p[K_C56], 6.0, c6, s6, g[20], g[21], B, T);
-    fold(B, T, 1.0 / 6.0);
+  if (ax.c[0] == 0.0 && ay.c[0] == 0.0) {
+    // on-axis ray: jnp.hypot / arctan2 have NaN derivatives at the origin (aberrations.py:66-67), so every
+    // derivative through the lens is NaN in the reference; values stay finite
+#pragma unroll
+    for (int m = 1; m < HD<P>::M; ++m) dWx.c[m] = dWy.c[m] = W.c[m] = nan("");
   }
-  q = q * ia;
-  dWx = dWa * c1 - q * s1;
-  dWy = dWa * s1 + q * c1;
 }
 
 // ---- index tuples ------------------------------------------------------------------------

@@ -301,89 +301,174 @@ __device__ __forceinline__ Dual<N> kscale(const Dual<N> &a, double s) {
   return r;
 }
 
-// One harmonic term: B += C cos(m (phi - phi0)),  T += (-m C) sin(m (phi - phi0)), with
-// cos/sin(m phi) = Re/Im ((ax + i ay)/|a|)^m (cm, sm) and cos/sin(m phi0) model constants:
-//   cos(m(phi-phi0)) = cm c0 + sm s0,  sin(m(phi-phi0)) = sm c0 - cm s0
-// -- no atan2 / sincos in the kernel.  Terms with C == 0 contribute exactly zero in the
-// reference as well and are skipped (uniform branch on kernel-parameter constants).
-template <int N>
-__device__ __forceinline__ void kriv_term(double C, double m, const Dual<N> &cm, const Dual<N> &sm,
-                                          double c0, double s0, Dual<N> &B, Dual<N> &T) {
+// ---- polynomial form of the Krivanek aberration function ---------------------------------------
+// Every term of aberrations.py:42-60 is a POLYNOMIAL in the slope components: with w = ax + i ay,
+// r2 = |w|^2, b = (n + 1 - m) / 2 and z_nm = C_nm / (n + 1) * exp(-i m phi_nm),
+//     C_nm alpha^(n+1) / (n+1) cos(m (phi - phi_nm)) = r2^b Re(z_nm w^m),
+// so   W = Re[ F0(w) + r2 F1(w) + r2^2 F2(w) + r2^3 F3 ]   with the holomorphic polynomials
+//     F0 = z12 w^2 + z23 w^3 + z34 w^4 + z45 w^5 + z56 w^6      F2 = z30 + z41 w + z52 w^2
+//     F1 = z10 + z21 w + z32 w^2 + z43 w^3 + z54 w^4            F3 = z50.
+// For holomorphic F: grad Re F = conj(F') (as gx + i gy) and Hess Re F = [[Re F'', -Im F''], [-Im F'', -Re F'']],
+// and the product rule with r2^b gives grad W (aberrations.py:63-108) and its Jacobian in closed form:
+// no hypot / atan2 / division / normalised phasors, ~4x fewer fp64 instructions than differentiating
+// the polar form, and nothing singular at the origin (where the reference's hypot / arctan2 gradients
+// are NaN; that is reproduced explicitly).  Terms with C == 0 contribute exactly zero in the reference
+// as well and are skipped (uniform branches on kernel-parameter constants).
+struct Cx {
+  double re, im;
+};
+__device__ __forceinline__ Cx cx_mul(const Cx &a, const Cx &b) {
+  Cx r;
+  r.re = fma(a.re, b.re, -(a.im * b.im));
+  r.im = fma(a.re, b.im, a.im * b.re);
+  return r;
+}
+struct KrivF {
+  Cx F, F1, F2;  // F_b(w), F_b'(w), F_b''(w)
+};
+// accumulate the term z w^K, z = kappa C (c0 - i s0); wkm2 = w^(K-2) (only read when K >= 3)
+template <int K, bool HESS>
+__device__ __forceinline__ void kriv_poly_term(double C, double kappa, double c0, double s0, const Cx &w,
+                                               const Cx &wkm2, KrivF &A) {
   if (C == 0.0) return;
-  B = kaxpy(klin(cm, c0, sm, s0), C, B);
-  T = kaxpy(klin(sm, c0, cm, -s0), -m * C, T);
+  const double s = C * kappa;
+  Cx z;
+  z.re = s * c0;
+  z.im = -(s * s0);
+  if constexpr (K == 1) {
+    const Cx t = cx_mul(z, w);
+    A.F.re += t.re;
+    A.F.im += t.im;
+    A.F1.re += z.re;
+    A.F1.im += z.im;
+  } else {
+    const Cx T = (K == 2) ? z : cx_mul(z, wkm2);  // z w^(K-2)
+    if constexpr (HESS) {
+      A.F2.re = fma((double)(K * (K - 1)), T.re, A.F2.re);
+      A.F2.im = fma((double)(K * (K - 1)), T.im, A.F2.im);
+    }
+    const Cx T1 = cx_mul(T, w);
+    A.F1.re = fma((double)K, T1.re, A.F1.re);
+    A.F1.im = fma((double)K, T1.im, A.F1.im);
+    const Cx T2 = cx_mul(T1, w);
+    A.F.re += T2.re;
+    A.F.im += T2.im;
+  }
+}
+struct KrivOut {
+  double W, Gx, Gy, Hxx, Hxy, Hyy;
+};
+// add the group r2^B Re F_B(w): rho = r2^B, rho1 = B r2^(B-1), rho2 = B (B-1) r2^(B-2)
+template <int B, bool HESS>
+__device__ __forceinline__ void kriv_poly_combine(const KrivF &A, double u, double v, double rho, double rho1,
+                                                  double rho2, KrivOut &o) {
+  const double f = A.F.re, gx = A.F1.re, gy = -A.F1.im;
+  if constexpr (B == 0) {
+    o.W += f;
+    o.Gx += gx;
+    o.Gy += gy;
+    if constexpr (HESS) {
+      o.Hxx += A.F2.re;
+      o.Hxy -= A.F2.im;
+      o.Hyy -= A.F2.re;
+    }
+  } else {
+    const double t1 = 2.0 * rho1, t1f = t1 * f;      // grad rho = t1 (u, v)
+    o.W = fma(rho, f, o.W);
+    o.Gx = fma(rho, gx, fma(t1f, u, o.Gx));
+    o.Gy = fma(rho, gy, fma(t1f, v, o.Gy));
+    if constexpr (HESS) {
+      // f Hess rho + grad rho grad f^T + grad f grad rho^T + rho Hess f
+      const double t2f = 4.0 * rho2 * f;
+      const double pu = t1 * u, pv = t1 * v;
+      o.Hxx = fma(rho, A.F2.re, fma(2.0 * pu, gx, fma(t2f * u, u, o.Hxx + t1f)));
+      o.Hyy = fma(-rho, A.F2.re, fma(2.0 * pv, gy, fma(t2f * v, v, o.Hyy + t1f)));
+      o.Hxy = fma(-rho, A.F2.im, fma(pu, gy, fma(pv, gx, fma(t2f * u, v, o.Hxy))));
+    }
+  }
+}
+// p = comp.p + 1: 25 coefficients, then 11 (cos, sin)(m phi0) pairs
+template <bool HESS>
+__device__ __forceinline__ KrivOut krivanek_poly(const double *p, double u, double v) {
+  const double *g = p + 25;
+  Cx w;
+  w.re = u;
+  w.im = v;
+  const double r2 = fma(u, u, v * v);
+  Cx w2, w3, w4;
+  w2.re = w2.im = w3.re = w3.im = w4.re = w4.im = 0.0;
+  const bool n4 = p[K_C56] != 0.0, n3 = p[K_C45] != 0.0;
+  const bool n2 = p[K_C34] != 0.0 || p[K_C54] != 0.0 || n3 || n4;
+  if (n2) w2 = cx_mul(w, w);
+  if (n3) w3 = cx_mul(w2, w);
+  if (n4) w4 = cx_mul(w2, w2);
+  KrivOut o;
+  o.W = o.Gx = o.Gy = o.Hxx = o.Hxy = o.Hyy = 0.0;
+  KrivF A;
+  // b = 0: m = n + 1
+  if (p[K_C12] != 0.0 || p[K_C23] != 0.0 || p[K_C34] != 0.0 || p[K_C45] != 0.0 || p[K_C56] != 0.0) {
+    A.F.re = A.F.im = A.F1.re = A.F1.im = A.F2.re = A.F2.im = 0.0;
+    kriv_poly_term<2, HESS>(p[K_C12], 0.5, g[0], g[1], w, w, A);
+    kriv_poly_term<3, HESS>(p[K_C23], 1.0 / 3.0, g[4], g[5], w, w, A);
+    kriv_poly_term<4, HESS>(p[K_C34], 0.25, g[8], g[9], w, w2, A);
+    kriv_poly_term<5, HESS>(p[K_C45], 0.2, g[14], g[15], w, w3, A);
+    kriv_poly_term<6, HESS>(p[K_C56], 1.0 / 6.0, g[20], g[21], w, w4, A);
+    kriv_poly_combine<0, HESS>(A, u, v, 1.0, 0.0, 0.0, o);
+  }
+  // b = 1: m = n - 1
+  if (p[K_C10] != 0.0 || p[K_C21] != 0.0 || p[K_C32] != 0.0 || p[K_C43] != 0.0 || p[K_C54] != 0.0) {
+    A.F.re = 0.5 * p[K_C10];
+    A.F.im = A.F1.re = A.F1.im = A.F2.re = A.F2.im = 0.0;
+    kriv_poly_term<1, HESS>(p[K_C21], 1.0 / 3.0, g[2], g[3], w, w, A);
+    kriv_poly_term<2, HESS>(p[K_C32], 0.25, g[6], g[7], w, w, A);
+    kriv_poly_term<3, HESS>(p[K_C43], 0.2, g[12], g[13], w, w, A);
+    kriv_poly_term<4, HESS>(p[K_C54], 1.0 / 6.0, g[18], g[19], w, w2, A);
+    kriv_poly_combine<1, HESS>(A, u, v, r2, 1.0, 0.0, o);
+  }
+  // b = 2: m = n - 3
+  if (p[K_C30] != 0.0 || p[K_C41] != 0.0 || p[K_C52] != 0.0) {
+    A.F.re = 0.25 * p[K_C30];
+    A.F.im = A.F1.re = A.F1.im = A.F2.re = A.F2.im = 0.0;
+    kriv_poly_term<1, HESS>(p[K_C41], 0.2, g[10], g[11], w, w, A);
+    kriv_poly_term<2, HESS>(p[K_C52], 1.0 / 6.0, g[16], g[17], w, w, A);
+    kriv_poly_combine<2, HESS>(A, u, v, r2 * r2, 2.0 * r2, 2.0, o);
+  }
+  // b = 3: C50 alpha^6 / 6
+  if (p[K_C50] != 0.0) {
+    A.F.re = p[K_C50] * (1.0 / 6.0);
+    A.F.im = A.F1.re = A.F1.im = A.F2.re = A.F2.im = 0.0;
+    const double r4 = r2 * r2;
+    kriv_poly_combine<3, HESS>(A, u, v, r4 * r2, 3.0 * r4, 6.0 * r2, o);
+  }
+  return o;
 }
 
-// (dW/dax, dW/day, W) of the Krivanek aberration function (aberrations.py:42-108); N is the
-// tangent width of the arguments (2 inside the ray kernel: tangents w.r.t. (ax, ay), chained to
-// the ray tangents by the caller, which keeps the live register set small).
-// p = comp.p + 1: 25 coefficients, then 11 (cos, sin)(m phi0) pairs.
+// (dW/dax, dW/day, W) of the Krivanek aberration function (aberrations.py:42-108).  N = 0: values only;
+// N = 2: the arguments are the seeds (ax, e0), (ay, e1), the tangents returned are the derivatives
+// w.r.t. (ax, ay) -- the symmetric Hessian of W for dWx / dWy, the gradient for W -- and the caller
+// chains them to the ray tangents, which keeps the live register set small.
 template <int N>
 __device__ __forceinline__ void krivanek(const double *p, const Dual<N> &ax, const Dual<N> &ay,
                                          Dual<N> &dWx, Dual<N> &dWy, Dual<N> &W) {
-  const Dual<N> a = dhypot(ax, ay);
-  // unit phasor e^{i phi}; at the origin phi = atan2(0,0) = 0 with NaN derivative like JAX
-  Dual<N> c1, s1, ia;
-  if (a.v == 0.0) {
-    c1 = dconst<N>(1.0);
-    s1 = dconst<N>(0.0);
-#pragma unroll
-    for (int k = 0; k < (N > 0 ? N : 1); ++k) {
-      c1.t[k] = a.t[k] * 0.0 + (N > 0 ? nan("") : 0.0);
-      s1.t[k] = c1.t[k];
-    }
-    ia = drecip(dconst<N>(1e-30));   // jnp.where(alpha == 0, 1e-30, alpha) (aberrations.py:100)
+  static_assert(N == 0 || N == 2, "krivanek: value-only or tangents w.r.t. its own two arguments");
+  const KrivOut o = krivanek_poly<(N == 2)>(p, ax.v, ay.v);
+  dWx.v = o.Gx;
+  dWy.v = o.Gy;
+  W.v = o.W;
+  if constexpr (N == 2) {
+    // jnp.hypot / arctan2 have NaN gradients at the origin (aberrations.py:66-67): every derivative
+    // through the lens is NaN there in the reference
+    const bool origin = ax.v == 0.0 && ay.v == 0.0;
+    const double qn = nan("");
+    dWx.t[0] = origin ? qn : o.Hxx;
+    dWx.t[1] = origin ? qn : o.Hxy;
+    dWy.t[0] = origin ? qn : o.Hxy;
+    dWy.t[1] = origin ? qn : o.Hyy;
+    W.t[0] = origin ? qn : o.Gx;
+    W.t[1] = origin ? qn : o.Gy;
   } else {
-    ia = drecip(a);
-    c1 = kmul(ax, ia);
-    s1 = kmul(ay, ia);
+    dWx.t[0] = dWy.t[0] = W.t[0] = 0.0;
   }
-  // harmonics actually present in the model (uniform branches on kernel-parameter constants):
-  // powers of the unit phasor are only formed up to the highest order in use
-  const bool u6 = p[K_C56] != 0.0, u5 = p[K_C45] != 0.0;
-  const bool u4 = p[K_C34] != 0.0 || p[K_C54] != 0.0 || u5;
-  const bool u3 = p[K_C23] != 0.0 || p[K_C43] != 0.0 || u6 || u5;
-  const bool u2 = p[K_C12] != 0.0 || p[K_C32] != 0.0 || p[K_C52] != 0.0 || u3 || u4;
-  Dual<N> c2 = dconst<N>(0.0), s2 = c2, c3 = c2, s3 = c2, c4 = c2, s4 = c2, c5 = c2, s5 = c2, c6 = c2, s6 = c2;
-  if (u2) { c2 = kmul2(c1, c1, s1, s1, -1.0); s2 = kscale(kmul(c1, s1), 2.0); }
-  if (u3) { c3 = kmul2(c2, c1, s2, s1, -1.0); s3 = kmul2(s2, c1, c2, s1, 1.0); }
-  if (u4) { c4 = kmul2(c2, c2, s2, s2, -1.0); s4 = kscale(kmul(c2, s2), 2.0); }
-  if (u5) { c5 = kmul2(c4, c1, s4, s1, -1.0); s5 = kmul2(s4, c1, c4, s1, 1.0); }
-  if (u6) { c6 = kmul2(c3, c3, s3, s3, -1.0); s6 = kscale(kmul(c3, s3), 2.0); }
-  const double *g = p + 25;  // (cos, sin)(m phi0) pairs
-  // brackets (aberrations.py:42-48) and the matching sin sums of dW/dphi (aberrations.py:78-98)
-  Dual<N> B2 = dconst<N>(p[K_C10]), T2 = dconst<N>(0.0);
-  kriv_term(p[K_C12], 2.0, c2, s2, g[0], g[1], B2, T2);
-  Dual<N> B3 = dconst<N>(0.0), T3 = dconst<N>(0.0);
-  kriv_term(p[K_C21], 1.0, c1, s1, g[2], g[3], B3, T3);
-  kriv_term(p[K_C23], 3.0, c3, s3, g[4], g[5], B3, T3);
-  Dual<N> B4 = dconst<N>(p[K_C30]), T4 = dconst<N>(0.0);
-  kriv_term(p[K_C32], 2.0, c2, s2, g[6], g[7], B4, T4);
-  kriv_term(p[K_C34], 4.0, c4, s4, g[8], g[9], B4, T4);
-  Dual<N> B5 = dconst<N>(0.0), T5 = dconst<N>(0.0);
-  kriv_term(p[K_C41], 1.0, c1, s1, g[10], g[11], B5, T5);
-  kriv_term(p[K_C43], 3.0, c3, s3, g[12], g[13], B5, T5);
-  kriv_term(p[K_C45], 5.0, c5, s5, g[14], g[15], B5, T5);
-  Dual<N> B6 = dconst<N>(p[K_C50]), T6 = dconst<N>(0.0);
-  kriv_term(p[K_C52], 2.0, c2, s2, g[16], g[17], B6, T6);
-  kriv_term(p[K_C54], 4.0, c4, s4, g[18], g[19], B6, T6);
-  kriv_term(p[K_C56], 6.0, c6, s6, g[20], g[21], B6, T6);
-  // radial weights a^n / n (aberrations.py:51-60); a3 / 3.0, a6 / 6.0 as multiplies (<= 1 ulp)
-  const Dual<N> a2 = kmul(a, a);
-  const Dual<N> a3 = kmul(a2, a);
-  const Dual<N> a4 = kmul(a2, a2);
-  const Dual<N> a5 = kmul(a4, a);
-  const Dual<N> w2 = kscale(a2, 0.5), w3 = kscale(a3, 1.0 / 3.0), w4 = kscale(a4, 0.25);
-  const Dual<N> w5 = kscale(a5, 0.2), w6 = kscale(kmul(a3, a3), 1.0 / 6.0);
-  // W (aberrations.py:51-60), dW/dalpha and dW/dphi (aberrations.py:63-98) as fused sums
-  W = kfma(w2, B2, kfma(w3, B3, kfma(w4, B4, kfma(w5, B5, kmul(w6, B6)))));
-  const Dual<N> dW_dalpha = kfma(a, B2, kfma(a2, B3, kfma(a3, B4, kfma(a4, B5, kmul(a5, B6)))));
-  const Dual<N> dW_dphi = kfma(w2, T2, kfma(w3, T3, kfma(w4, T4, kfma(w5, T5, kmul(w6, T6)))));
-  // (aberrations.py:100-108) with cos phi = ax / a, sin phi = ay / a:
-  //   dW/dx = dW/dalpha cos phi - dW/dphi sin phi / a ;  dW/dy = dW/dalpha sin phi + dW/dphi cos phi / a
-  const Dual<N> q = kmul(dW_dphi, ia);
-  dWx = kmul2(dW_dalpha, c1, q, s1, -1.0);
-  dWy = kmul2(dW_dalpha, s1, q, c1, 1.0);
 }
 
 // chain rule: r = f(ax, ay) given as Dual<2> (tangents w.r.t. ax, ay) -> tangents of width N
@@ -437,7 +522,7 @@ inline void to_lite(const tg_model &m, ModelLite &l) {
 // is identically zero for every component on the path (z only ever receives component
 // constants), and pathlength never feeds back into x,y,dx,dy.
 template <int NC, bool KRIV>
-__global__ void __launch_bounds__(kTraceThreads, KRIV ? (NC == 5 ? 3 : 1) : (NC == 7 ? 3 : 6))
+__global__ void __launch_bounds__(kTraceThreads, KRIV ? (NC == 5 ? 4 : 2) : (NC == 7 ? 3 : 6))
     trace_kernel(const __grid_constant__ typename ModelFor<KRIV>::type model, const tg_ray_in in,
                  const long long n, const TraceOut out, double *__restrict__ jac) {
   constexpr bool FULL = (NC == 7);
@@ -468,8 +553,13 @@ __global__ void __launch_bounds__(kTraceThreads, KRIV ? (NC == 5 ? 3 : 1) : (NC 
       if (!(cm.flags & TG_F_NOPROP)) {
         // distance = component.z - ray.z (run.py:77); FreeSpaceParaxial (propagator.py:67-72)
         const Dual<NZ> d = (cm.flags & TG_F_DIST) ? dconst<NZ>(cm.z) : cm.z - z;
-        x = x + dx * d;
-        y = y + dy * d;
+        if constexpr (KRIV && !FULL) {  // compute-bound instantiation: fused multiply-adds (see kmul)
+          x = kaxpy(dx, d.v, x);
+          y = kaxpy(dy, d.v, y);
+        } else {
+          x = x + dx * d;
+          y = y + dy * d;
+        }
         z = z + d;
         pl = pl + d;
       }
@@ -483,6 +573,8 @@ __global__ void __launch_bounds__(kTraceThreads, KRIV ? (NC == 5 ? 3 : 1) : (NC 
             // compute-bound instantiation (a Krivanek lens is in the model): one reciprocal per
             // lens instead of 13 fp64 divisions, <= 1 ulp from the exact quotient
             const double inv_f = 1.0 / f;
+            // (separate multiply and add: x.t * (1/f) rounds to exactly 1 where the reference's x.t / f does,
+            // e.g. a lens one focal length behind a parallel beam, and the zero stays an exact zero)
             const Dual<NC> ndx = (-x) * inv_f + dx;
             const Dual<NC> ndy = (-y) * inv_f + dy;
             pl = pl - dnarrow<NZ>((x * x + y * y) * (0.5 * inv_f));
@@ -500,12 +592,18 @@ __global__ void __launch_bounds__(kTraceThreads, KRIV ? (NC == 5 ? 3 : 1) : (NC 
         } break;
         case TG_OP_DEFLECTOR: {  // components.py:476-482
           pl = pl + dnarrow<NZ>(dx * x) + dnarrow<NZ>(dy * y);
-          dx = dx + cm.p[0] * one;
-          dy = dy + cm.p[1] * one;
+          if constexpr (KRIV) {
+            dx = kaxpy(one, cm.p[0], dx);
+            dy = kaxpy(one, cm.p[1], dy);
+          } else {
+            dx = dx + cm.p[0] * one;
+            dy = dy + cm.p[1] * one;
+          }
         } break;
         case TG_OP_BIPRISM: {  // components.py:553-559
           pl = pl + dnarrow<NZ>(dx * x) + dnarrow<NZ>(dy * y);
-          dx = dx + cm.p[0] * one * dsign(x);
+          if constexpr (KRIV) dx = kaxpy(one, cm.p[0] * dsign(x).v, dx);
+          else dx = dx + cm.p[0] * one * dsign(x);
         } break;
         case TG_OP_OFFSET: {  // Scanner / Descanner, components.py:279-285, 343-372
           x = x + cm.p[0] * one;
@@ -528,21 +626,29 @@ __global__ void __launch_bounds__(kTraceThreads, KRIV ? (NC == 5 ? 3 : 1) : (NC 
           if constexpr (KRIV) {
             // compute-bound op: one reciprocal of f instead of ~25 fp64 divisions (<= 1 ulp each)
             const double inv_f = 1.0 / cm.p[0];
-            const Dual<NC> idx = (-x) * inv_f + dx;
+            const Dual<NC> idx = (-x) * inv_f + dx;   // unfused on purpose, see TG_OP_LENS
             const Dual<NC> idy = (-y) * inv_f + dy;
-            Dual<NC> dWx, dWy, W;
+            Dual<NC> W;
             if constexpr (NC == 0) {
+              Dual<0> dWx, dWy;
               krivanek<0>(cm.p + 1, idx, idy, dWx, dWy, W);
+              dx.v = fma(dWx.v, -inv_f, idx.v);
+              dy.v = fma(dWy.v, -inv_f, idy.v);
             } else {
               Dual<2> gx, gy, w2;
               krivanek<2>(cm.p + 1, dseed<2>(idx.v, 0), dseed<2>(idy.v, 1), gx, gy, w2);
-              dWx = dchain<NC>(gx, idx, idy);
-              dWy = dchain<NC>(gy, idx, idy);
               W = dchain<NC>(w2, idx, idy);
+              // (dx, dy) = (idx, idy) - grad W / f: tangents through the 2x2 matrix I - Hess W / f
+              const double m00 = fma(gx.t[0], -inv_f, 1.0), m01 = gx.t[1] * -inv_f;
+              const double m10 = gy.t[0] * -inv_f, m11 = fma(gy.t[1], -inv_f, 1.0);
+              dx.v = fma(gx.v, -inv_f, idx.v);
+              dy.v = fma(gy.v, -inv_f, idy.v);
+#pragma unroll
+              for (int k = 0; k < NC; ++k) {
+                dx.t[k] = fma(m00, idx.t[k], m01 * idy.t[k]);
+                dy.t[k] = fma(m10, idx.t[k], m11 * idy.t[k]);
+              }
             }
-            const Dual<NC> dux = (-dWx) * inv_f, duy = (-dWy) * inv_f;
-            dx = idx + dux;
-            dy = idy + duy;
             pl = pl - dnarrow<NZ>((x * x + y * y) * (0.5 * inv_f)) + dnarrow<NZ>(W * inv_f);
             one = one * 1.0;
           }

@@ -1,5 +1,5 @@
 """Launches exactly the kernels we profile, a few times each, so `ncu -k regex:... -s N -c 1`
-hits a warm, full-size launch.  Usage: python tools/prof_kernels.py [field|trace|trace_c4|all]"""
+hits a warm, full-size launch.  Usage: python tools/prof_kernels.py [field|gemm|trace|trace_c4|stem4d|jets|field_c3|all]"""
 import os
 import sys
 
@@ -19,6 +19,12 @@ if what in ("field", "all"):
     poly, n, _ = beamlet_polynomials(g, model)
     for _ in range(3):
         _field_sum_grid(poly, n, model[-1], dev, cull_bits=0)
+    torch.cuda.synchronize()
+if what in ("gemm",):
+    g, model = M.aperture_diffraction_case(10_000, (1024, 1024))
+    poly, n, _ = beamlet_polynomials(g, model)
+    for _ in range(3):
+        _field_sum_grid(poly, n, model[-1], dev, method="tensor")
     torch.cuda.synchronize()
 if what in ("trace", "all"):
     rr = M.random_rays(10_000_000)
