@@ -291,17 +291,31 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = evals_per_step / (ms_per_step * 1e-3)
 
-    # north_star's row-sharded mode for ONE image: broadcast table, local rows, all-gather
+    # north_star's row-sharded mode for ONE image, two exchange styles:
+    #  fused_peer : every rank builds the table, sums its rows and the producing kernels store the row
+    #               block into every rank's image over NVLink peer memory; device-side barrier (PeerImage)
+    #  nccl       : broadcast table, local rows, all-gather
     row_sharded = None
     if world > 1:
         row_sharded = {}
+        pimg = D.PeerImage(H, W) if world <= 8 else None
         for mth in ("auto", "sfu"):
+            if pimg is not None:
+                tt = timed(lambda: D.make_gaussian_image_sharded(g_dev, model, cull_bits=0, method=mth,
+                                                                 peer_image=pimg), args.steps, args.warmup)
+                ms = max_over_ranks(float(np.sum(tt))) / args.steps
+                row_sharded[mth + "_fused_peer"] = {
+                    "ms_per_image": ms, "evals_per_s": C2_NB * H * W / (ms * 1e-3), "scaling": "strong",
+                    "exchange": "none as a collective: GEMM epilogue / split-reduce store each row block into all "
+                                "ranks' images (NVLink P2P), tg_peer_barrier closes the step"}
             tt = timed(lambda: D.make_gaussian_image_sharded(g_dev, model, cull_bits=0, method=mth),
                        args.steps, args.warmup)
             ms = max_over_ranks(float(np.sum(tt))) / args.steps
-            row_sharded[mth] = {"ms_per_image": ms, "evals_per_s": C2_NB * H * W / (ms * 1e-3),
-                                "scaling": "strong", "collectives": "dist.broadcast(table 0.96 MB) + "
-                                "dist.all_gather(row blocks, 16.8 MB complex128)"}
+            row_sharded[mth + "_nccl"] = {"ms_per_image": ms, "evals_per_s": C2_NB * H * W / (ms * 1e-3),
+                                          "scaling": "strong", "collectives": "dist.broadcast(table 0.96 MB) + "
+                                          "dist.all_gather(row blocks, 16.8 MB complex128)"}
+        if pimg is not None:
+            pimg.close()
 
     poly, nb, _ = beamlet_polynomials(g_dev, model)
     peak_mufu = sms * MUFU_PER_CLK_SM * pk["sm_max_mhz"] * 1e6

@@ -302,6 +302,33 @@ int tg_make_gaussian_image_f64(const tg_model *model_host, int64_t nb, const dou
                                int nrows, void *out, int out_is_c128, int cull_bits, int method,
                                void *stream);
 
+/* ---- multi-GPU: row-sharded field sum over peer memory -----------------------------
+ * One process per GPU.  Each rank owns a full (H, W) image buffer allocated with tg_peer_alloc and maps
+ * the buffers of the other ranks of the node with tg_peer_open (CUDA IPC; the handles travel through
+ * torch.distributed / any host channel).  tg_field_sum_peers computes this rank's detector rows
+ * [row0, row0 + nrows) (the reference has no multi-device path; this shards gaussian.py:319-369 by
+ * detector rows) and the kernel that produces the final values stores them into ALL `npeers` images at
+ * that row offset -- its own and, through NVLink P2P stores, its peers' -- so the gather of the row
+ * blocks is fused into the compute kernels instead of being a separate collective.  tg_peer_barrier is
+ * the matching device-side barrier over peer memory (flag arrays of npeers uint64, one per rank, inside
+ * peer allocations): after it completes on every rank's stream, every rank's image is complete. */
+#define TG_MAX_PEERS 8
+typedef struct tg_ipc_handle { unsigned char bytes[64]; } tg_ipc_handle;
+/* cudaMalloc (zero-filled) + IPC handle of the allocation */
+int tg_peer_alloc(uint64_t bytes, void **dptr, tg_ipc_handle *handle);
+/* map another process's allocation into this process (peer access enabled lazily) */
+int tg_peer_open(const tg_ipc_handle *handle, void **dptr);
+int tg_peer_close(void *dptr);
+int tg_peer_free(void *dptr);
+/* images[p]: base of rank p's (H, W) image as seen from this process (images[self] is local). */
+int tg_field_sum_peers(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
+                       int nrows, void *const images[], int npeers, int self, int out_is_c128,
+                       int cull_bits, int method, void *stream);
+/* flags[p]: base of rank p's flag array (npeers uint64, zero-initialised) as seen from this process.
+ * Signals `epoch` (strictly increasing per use) to every peer and waits until every peer has signalled it;
+ * traps after ~10 s instead of hanging. */
+int tg_peer_barrier(void *const flags[], int npeers, int self, uint64_t epoch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

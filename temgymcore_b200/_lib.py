@@ -12,6 +12,7 @@ from typing import Sequence
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtemgym_b200.so")
 
+TG_MAX_PEERS = 8
 TG_MAX_COMPS = 24
 TG_NPARAM = 48
 
@@ -86,6 +87,13 @@ SIGNATURES = {
                                           _vp, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "tg_gemm_tf32x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
     "tg_gemm_f16x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
+    "tg_peer_alloc": (_i32, [C.c_uint64, C.POINTER(_vp), _vp]),
+    "tg_peer_open": (_i32, [_vp, C.POINTER(_vp)]),
+    "tg_peer_close": (_i32, [_vp]),
+    "tg_peer_free": (_i32, [_vp]),
+    "tg_field_sum_peers": (_i32, [_i64, _vp, _dp, _i32, _i32, _i32, _i32, C.POINTER(_vp), _i32, _i32, _i32, _i32,
+                                  _i32, _vp]),
+    "tg_peer_barrier": (_i32, [C.POINTER(_vp), _i32, _i32, C.c_uint64, _vp]),
     "tg_make_gaussian_image_host": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(_vp), _vp, _vp, _vp,
                                            _vp, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32]),
 }

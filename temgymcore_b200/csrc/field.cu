@@ -44,6 +44,7 @@ struct FieldGeom {
   int nsplit;
   long long nb;
   int cull_bits;
+  int via_partial;   // tiles go to the split-partials buffer (nsplit > 1, or peer destinations)
 };
 
 // ---- ordered-uint encoding of doubles for atomicMin ---------------------------------
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     for (int j = 0; j < L; ++j) {
       if (c0 + v0 + j < g.W) {
         const double re = sm.acc[j * kThreads + tid], im = sm.acc[(L + j) * kThreads + tid];
-        if (g.nsplit > 1) {
+        if (g.via_partial) {
           partial[(size_t)split * ((size_t)g.nrows * g.W) + base + j] = make_double2(re, im);
         } else if (out_is_c128) {
           static_cast<double2 *>(out)[base + j] = make_double2(re, im);
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 __global__ void __launch_bounds__(256)
     split_reduce_kernel(const double2 *__restrict__ partial, int nsplit, size_t npix,
                         void *__restrict__ out, int out_is_c128,
-                        const unsigned long long *__restrict__ sep_guard) {
+                        const unsigned long long *__restrict__ sep_guard, const TgPeers peers) {
   if (sep_guard && tg_key_is_separable(*sep_guard)) return;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
@@ -504,8 +505,13 @@ __global__ void __launch_bounds__(256)
     re += v.x;
     im += v.y;
   }
-  if (out_is_c128) static_cast<double2 *>(out)[i] = make_double2(re, im);
-  else static_cast<float2 *>(out)[i] = make_float2((float)re, (float)im);
+  if (out_is_c128) {
+    static_cast<double2 *>(out)[i] = make_double2(re, im);
+    for (int p = 0; p < peers.n; ++p) static_cast<double2 *>(peers.ptr[p])[i] = make_double2(re, im);  // NVLink P2P
+  } else {
+    static_cast<float2 *>(out)[i] = make_float2((float)re, (float)im);
+    for (int p = 0; p < peers.n; ++p) static_cast<float2 *>(peers.ptr[p])[i] = make_float2((float)re, (float)im);
+  }
 }
 
 // ---- arbitrary observation points ------------------------------------------------------
@@ -589,7 +595,7 @@ extern "C" int tg_field_sum_grid(int64_t nb, const double *poly, const double px
 // beamlets are separable (the tensor-core path, enqueued by the same call, does the work instead).
 int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                       int nrows, void *out, int out_is_c128, int cull_bits, long long *n_evals_out,
-                      const unsigned long long *sep_guard, cudaStream_t stream) {
+                      const unsigned long long *sep_guard, cudaStream_t stream, const TgPeers *peers) {
   TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad shape");
   TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
   TG_REQUIRE(px2m && out, "null pointer");
@@ -599,8 +605,12 @@ int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int 
   if (nrows == 0) return TG_OK;
   const size_t npix = (size_t)nrows * W;
   const size_t elt = out_is_c128 ? 16 : 8;
+  TgPeers no_peers;
+  no_peers.n = 0;
+  const TgPeers &pe = peers ? *peers : no_peers;
   if (nb == 0) {
     TG_CUDA(cudaMemsetAsync(out, 0, npix * elt, st));
+    for (int p = 0; p < pe.n; ++p) TG_CUDA(cudaMemsetAsync(pe.ptr[p], 0, npix * elt, st));
     return TG_OK;
   }
   TG_REQUIRE(poly, "null poly");
@@ -619,10 +629,11 @@ int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int 
   tg_tune_mempool(dev);
   TG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   g.nsplit = choose_split(tiles, nb, 2 * sms, cull_bits > 0, npix);
+  g.via_partial = (g.nsplit > 1 || pe.n > 0) ? 1 : 0;   // peer stores are issued by the reduce kernel (coalesced)
 
   // workspace: table (nb*96 B) | gref key (8) | evals (8) | split partials | per-beamlet bounding boxes
   const size_t table_bytes = (size_t)nb * 96;
-  const size_t part_bytes = g.nsplit > 1 ? (size_t)g.nsplit * npix * 16 : 0;
+  const size_t part_bytes = g.via_partial ? (size_t)g.nsplit * npix * 16 : 0;
   const bool use_bbox = cull_bits > 0 && H <= 32768 && W <= 32768;
   const size_t bbox_bytes = use_bbox ? (size_t)nb * sizeof(short4) : 0;
   unsigned char *ws = nullptr;
@@ -653,9 +664,9 @@ int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int 
           table, g, cull_bits > 0 ? gref : nullptr, bbox, out, out_is_c128, partial,
           n_evals_out ? evals : nullptr, sep_guard);
       rc = tg_launch_check("field_grid_kernel");
-      if (rc == TG_OK && g.nsplit > 1) {
+      if (rc == TG_OK && g.via_partial) {
         split_reduce_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(partial, g.nsplit, npix,
-                                                                           out, out_is_c128, sep_guard);
+                                                                           out, out_is_c128, sep_guard, pe);
         rc = tg_launch_check("split_reduce_kernel");
       }
     }

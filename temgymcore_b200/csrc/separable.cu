@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    int M, int Np, int K, double *__restrict__ out, long long ldo, int accumulate_out,
-                   const double *__restrict__ out_scale, const unsigned long long *__restrict__ sep_guard) {
+                   const double *__restrict__ out_scale, const unsigned long long *__restrict__ sep_guard,
+                   const __grid_constant__ TgPeers peers) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;  // the SFU path owns this call
   constexpr int BK = GemmCfg<F16>::BK, CHUNK_KB = GemmCfg<F16>::CHUNK_KB;
   constexpr uint32_t kIdesc = Idesc<F16>::value;
@@ -277,11 +278,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             w.y += p.y;
           }
           *reinterpret_cast<double2 *>(o + i) = w;
+          // row-sharded multi-GPU sum: the same values go straight into the peers' images (NVLink P2P stores)
+          for (int p = 0; p < peers.n; ++p)
+            *reinterpret_cast<double2 *>(static_cast<double *>(peers.ptr[p]) + (o - out) + i) = w;
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 64; ++i)
-          if (i < ncol) o[i] = (accumulate_out ? o[i] : 0.0) + (double)accum[i] * sc;
+          if (i < ncol) {
+            const double wv = (accumulate_out ? o[i] : 0.0) + (double)accum[i] * sc;
+            o[i] = wv;
+            for (int p = 0; p < peers.n; ++p) (static_cast<double *>(peers.ptr[p]) + (o - out))[i] = wv;
+          }
       }
     }
   }
@@ -550,10 +558,14 @@ __global__ void verdict_kernel(unsigned long long *key, const double *est_tiles,
 
 __global__ void __launch_bounds__(256)
     f64_to_c64_kernel(const double *__restrict__ in, float *__restrict__ out, size_t n,
-                      const unsigned long long *__restrict__ sep_guard) {
+                      const unsigned long long *__restrict__ sep_guard, const TgPeers peers) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (float)in[i];
+  if (i < n) {
+    const float v = (float)in[i];
+    out[i] = v;
+    for (int p = 0; p < peers.n; ++p) static_cast<float *>(peers.ptr[p])[i] = v;
+  }
 }
 
 // ---------------------------------------------------------------- host side
@@ -600,7 +612,7 @@ int make_map(CUtensorMap *m, const void *base, long long rows, long long K, long
 template <bool F16>
 int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *Blo, int M, int Np, int K,
                 long long ldk, double *out, long long ldo, int accumulate, const double *out_scale,
-                const unsigned long long *sep_guard, cudaStream_t st) {
+                const unsigned long long *sep_guard, cudaStream_t st, const TgPeers &peers) {
   CUtensorMap ta, tb, tc, td;
   int rc;
   if ((rc = make_map<F16>(&ta, Ahi, M, K, ldk)) != TG_OK) return rc;
@@ -611,16 +623,18 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
   TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((Np + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
   gemm_x3_kernel<F16><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, tc, td, M, Np, K, out, ldo, accumulate, out_scale,
-                                                        sep_guard);
+                                                        sep_guard, peers);
   return tg_launch_check(F16 ? "gemm_x3_kernel<f16>" : "gemm_x3_kernel<tf32>");
 }
 
 template <bool F16>
 int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, long long ldk, void *Ahi, void *Alo,
                 void *Bhi, void *Blo, double *acc, const double *shift, const unsigned long long *guard,
-                cudaStream_t st) {
+                cudaStream_t st, const TgPeers &gemm_peers) {
   const int Np = 2 * W;
   int rc = TG_OK;
+  TgPeers none;
+  none.n = 0;
   for (long long b0 = 0; b0 < nb && rc == TG_OK; b0 += kBatch) {
     const int nbatch = (int)((nb - b0) < kBatch ? (nb - b0) : kBatch);
     const int K = 2 * nbatch;
@@ -632,7 +646,7 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
     rc = tg_launch_check("factor kernels");
     if (rc == TG_OK)
       rc = launch_gemm<F16>(Ahi, Alo, Bhi, Blo, nrows, Np, K, ldk, acc, (long long)Np, b0 > 0 ? 1 : 0,
-                            shift + 1, guard, st);
+                            shift + 1, guard, st, (b0 + kBatch >= nb) ? gemm_peers : none);  // peers: final batch only
   }
   return rc;
 }
@@ -649,8 +663,10 @@ extern "C" int tg_gemm_tf32x3(int M, int N, int K, const float *A_hi, const floa
   TG_REQUIRE(((uintptr_t)A_hi % 16) == 0 && ((uintptr_t)A_lo % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 &&
                  ((uintptr_t)B_lo % 16) == 0,
              "operands must be 16-byte aligned");
+  TgPeers none;
+  none.n = 0;
   return launch_gemm<false>(A_hi, A_lo, B_hi, B_lo, M, N, K, ldk, D, ldd, accumulate, nullptr, nullptr,
-                            static_cast<cudaStream_t>(stream));
+                            static_cast<cudaStream_t>(stream), none);
 }
 // the same with fp16 operands (IEEE binary16, 2 bytes each): 3 x kind::f16 at twice the TF32 rate
 extern "C" int tg_gemm_f16x3(int M, int N, int K, const void *A_hi, const void *A_lo, const void *B_hi,
@@ -662,8 +678,10 @@ extern "C" int tg_gemm_f16x3(int M, int N, int K, const void *A_hi, const void *
   TG_REQUIRE(((uintptr_t)A_hi % 16) == 0 && ((uintptr_t)A_lo % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 &&
                  ((uintptr_t)B_lo % 16) == 0,
              "operands must be 16-byte aligned");
+  TgPeers none;
+  none.n = 0;
   return launch_gemm<true>(A_hi, A_lo, B_hi, B_lo, M, N, K, ldk, D, ldd, accumulate, nullptr, nullptr,
-                           static_cast<cudaStream_t>(stream));
+                           static_cast<cudaStream_t>(stream), none);
 }
 
 extern "C" int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6], int H, int W,
@@ -674,15 +692,19 @@ extern "C" int tg_field_sum_separable(int64_t nb, const double *poly, const doub
 
 int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                      int nrows, void *out, int out_is_c128, unsigned long long *key_async,
-                     cudaStream_t stream, int cost_cull_bits, int f16) {
+                     cudaStream_t stream, int cost_cull_bits, int f16, const TgPeers *peers) {
   TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad shape");
   TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
   TG_REQUIRE(px2m && out, "null pointer");
   cudaStream_t st = stream;
   if (nrows == 0) return TG_OK;
   const size_t npix = (size_t)nrows * W;
+  TgPeers none;
+  none.n = 0;
+  const TgPeers &pe = peers ? *peers : none;
   if (nb == 0) {
     TG_CUDA(cudaMemsetAsync(out, 0, npix * (out_is_c128 ? 16 : 8), st));
+    for (int p = 0; p < pe.n; ++p) TG_CUDA(cudaMemsetAsync(pe.ptr[p], 0, npix * (out_is_c128 ? 16 : 8), st));
     return TG_OK;
   }
   TG_REQUIRE(poly, "null poly");
@@ -750,11 +772,13 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
     }
   }
   if (rc == TG_OK)
-    rc = f16 ? run_batches<true>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, shift, guard, st)
-             : run_batches<false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, shift, guard, st);
+    rc = f16 ? run_batches<true>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, shift, guard, st,
+                                 out_is_c128 ? pe : none)
+             : run_batches<false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, shift, guard, st,
+                                  out_is_c128 ? pe : none);
   if (rc == TG_OK && !out_is_c128) {
     const size_t n = npix * 2;
-    f64_to_c64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, static_cast<float *>(out), n, guard);
+    f64_to_c64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, static_cast<float *>(out), n, guard, pe);
     rc = tg_launch_check("f64_to_c64_kernel");
   }
   cudaFreeAsync(ws, st);
@@ -764,20 +788,26 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
 // method dispatch: AUTO enqueues BOTH paths with a device-side separability verdict (no host sync)
 extern "C" int tg_field_sum(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                             int nrows, void *out, int out_is_c128, int cull_bits, int method, void *stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return tg_field_sum_impl(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, method,
+                           static_cast<cudaStream_t>(stream), nullptr);
+}
+int tg_field_sum_impl(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0, int nrows,
+                      void *out, int out_is_c128, int cull_bits, int method, cudaStream_t st, const TgPeers *peers) {
   if (method == TG_METHOD_SFU)
-    return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st);
+    return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st,
+                             peers);
   if (method == TG_METHOD_TENSOR || method == TG_METHOD_TENSOR_TF32)
     return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr, st, 0,
-                            method == TG_METHOD_TENSOR);
+                            method == TG_METHOD_TENSOR, peers);
   TG_REQUIRE(method == TG_METHOD_AUTO, "unknown method");
   if (nb == 0 || nrows == 0)
-    return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st);
+    return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st,
+                             peers);
   unsigned long long *key = nullptr;
   TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&key), 8, st));
-  int rc = tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, key, st, cull_bits, 1);
+  int rc = tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, key, st, cull_bits, 1, peers);
   if (rc == TG_OK)
-    rc = tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, key, st);
+    rc = tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, key, st, peers);
   cudaFreeAsync(key, st);
   return rc;
 }

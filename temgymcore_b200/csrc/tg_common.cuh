@@ -13,9 +13,17 @@ int tg_launch_prep(int64_t nb, const double *poly, const double px2m[6], int H, 
 int tg_wave_numbers(int64_t nb, const double *wavelength, const double *pathlength, double *k,
                     double *p0, cudaStream_t st);
 
+// Extra destinations of a field sum: the same row block inside the images of peer GPUs (device pointers
+// mapped over NVLink, already offset to the block).  The kernels that produce the final values store them
+// to `out` and to every peer, so the row-block "all-gather" of the row-sharded multi-GPU field sum happens
+// inside the compute kernels, tile by tile, instead of as a separate collective.
+struct TgPeers {
+  int n;
+  void *ptr[TG_MAX_PEERS];
+};
 int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                       int nrows, void *out, int out_is_c128, int cull_bits, long long *n_evals_out,
-                      const unsigned long long *sep_guard, cudaStream_t stream);
+                      const unsigned long long *sep_guard, cudaStream_t stream, const TgPeers *peers = nullptr);
 // key_async != NULL: no host sync; the verdict stays on the device in *key_async and the kernels of
 // this path return at once when it says "not separable".
 // cost_cull_bits > 0 (async mode only): also estimate the culled SFU work and leave the call to the SFU
@@ -23,7 +31,9 @@ int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int 
 // f16 != 0: fp16 x 3 operands (kind::f16, device-side pre-scaling), else tf32 x 3.
 int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                      int nrows, void *out, int out_is_c128, unsigned long long *key_async,
-                     cudaStream_t stream, int cost_cull_bits, int f16);
+                     cudaStream_t stream, int cost_cull_bits, int f16, const TgPeers *peers = nullptr);
+int tg_field_sum_impl(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0, int nrows,
+                      void *out, int out_is_c128, int cull_bits, int method, cudaStream_t st, const TgPeers *peers);
 // separability key = bits of max_n(cross term / tolerance) as a double (0 when there is none)
 __host__ __device__ inline bool tg_key_is_separable(unsigned long long key) {
   union { unsigned long long u; double d; } c;

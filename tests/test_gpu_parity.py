@@ -937,3 +937,35 @@ def test_auto_dispatch_is_cost_aware(torch_cuda):
     auto = _field_sum_grid(poly, n, model[-1], dev, method="auto")
     tens = _field_sum_grid(poly, n, model[-1], dev, method="tensor")
     assert torch_cuda.equal(auto, tens)
+
+
+# ------------------------------------------------------------------------------ peer-memory field sum
+@pytest.mark.parametrize("method,dtype_name", [("sfu", "complex128"), ("tensor", "complex128"), ("auto", "complex128"),
+                                               ("tensor", "complex64"), ("sfu", "complex64")])
+def test_peer_image_world_size_one(torch_cuda, method, dtype_name):
+    """tg_field_sum_peers / tg_peer_barrier on one GPU (a world of one rank): the IPC-shareable image,
+    the via-partial store path of the SFU kernel and the device-side barrier give the plain result."""
+    from temgymcore_b200.distributed import PeerImage, make_gaussian_image_sharded
+    from temgymcore_b200.gaussian import _field_sum_grid, beamlet_polynomials
+    torch = torch_cuda
+    dtype = getattr(torch, dtype_name)
+    g, model = field_cases()["c2_aperture"]
+    grid = model[-1]
+    poly, n, dev = beamlet_polynomials(g, model)
+    ref = _field_sum_grid(poly, n, grid, dev, cull_bits=0, method=method, out_dtype=dtype)
+    pi = PeerImage(grid.shape[0], grid.shape[1], dtype=dtype)
+    try:
+        for _ in range(2):      # epochs advance
+            pi.image.zero_()
+            out = make_gaussian_image_sharded(g, model, cull_bits=0, method=method, peer_image=pi)
+            torch.cuda.synchronize()
+            assert out.dtype == dtype and tuple(out.shape) == tuple(ref.shape)
+            np.testing.assert_array_equal(to_np(out), to_np(ref))
+        # empty beamlet set: zeros
+        pi.image.fill_(1.0)
+        pi.field_sum(poly[:0], 0, grid, cull_bits=0, method=method)
+        pi.barrier()
+        torch.cuda.synchronize()
+        assert not to_np(pi.image).any()
+    finally:
+        pi.close()
