@@ -35,11 +35,11 @@ C2_NB, C2_SHAPE = 10_000, (1024, 1024)
 # summarised under profiles/ (round 1, same workloads as timed here)
 NCU_TRAFFIC = {
     "gemm_x3_kernel_tf32": (491.98e6 + 4.20e6, "profiles/r1_gemm_tf32x3_kernel_v1.md"),
-    "gemm_x3_kernel_f16": (None, None),
+    "gemm_x3_kernel_f16": (246.86e6 + 4.22e6, "profiles/r1_gemm_f16x3_kernel_v1.md"),
     "field_grid_kernel": (1.00e6 + 81.65e6, "profiles/r1_field_grid_kernel_v3.md"),
     "trace_kernel_1e7": (560.0e6 + 2499.5e6, "profiles/r1_trace_kernel_1e7.md"),
     "stem4d_backproject": (17.18e9 + 3.6e6, "profiles/r1_stem4d_dda1x_kernel.md"),
-    "trace_kernel_c4": (560.1e6 + 2506.8e6, "profiles/r1_trace_kernel_c4_v3.md"),
+    "trace_kernel_c4": (560.06e6 + 2499.7e6, "profiles/r1_trace_kernel_c4_v4.md"),
 }
 MUFU_PER_EVAL = 2          # executed: 1 ex2 per pixel + sin/cos seeds of z and w every 4 pixels (field.cu)
 MUFU_PER_EVAL_NAIVE = 3    # SURVEY.md section 8d's count (sin, cos, ex2 per beamlet*pixel)
