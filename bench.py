@@ -298,7 +298,11 @@ def run_ours(args):
     row_sharded = None
     if world > 1:
         row_sharded = {}
-        pimg = D.PeerImage(H, W) if world <= 8 else None
+        try:
+            pimg = D.PeerImage(H, W) if world <= 8 else None
+        except Exception as exc:   # e.g. CUDA IPC not permitted in this container: keep the NCCL numbers
+            pimg = None
+            row_sharded["fused_peer_error"] = repr(exc)[:200]
         for mth in ("auto", "sfu"):
             if pimg is not None:
                 tt = timed(lambda: D.make_gaussian_image_sharded(g_dev, model, cull_bits=0, method=mth,
