@@ -639,9 +639,11 @@ def run_with_grads(ray, components: Sequence[Any], directions):
             c = comps[ci]
             if len(path) == 1:
                 c = _dc.replace(c, **{path[0]: seeded(getattr(c, path[0]), k)})
-            else:  # ("descan_error", name)
+            else:  # ("descan_error", name) -- a NamedTuple -- or ("coeffs", name) -- a dataclass
                 inner = getattr(c, path[0])
-                c = _dc.replace(c, **{path[0]: inner._replace(**{path[1]: seeded(getattr(inner, path[1]), k)})})
+                new = {path[1]: seeded(getattr(inner, path[1]), k)}
+                inner = inner._replace(**new) if hasattr(inner, "_replace") else _dc.replace(inner, **new)
+                c = _dc.replace(c, **{path[0]: inner})
             comps[ci] = c
     d_ray = Ray(*(seeded(getattr(r, f), ray_k[f]) for f in RAY_FIELDS))
     out = run_to_end(d_ray, comps)

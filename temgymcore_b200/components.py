@@ -113,8 +113,14 @@ class AberratedLensKrivanek(Lens):  # components.py:177-215
 
     def _tg_param_seeds(self, path):
         if path[0] == "coeffs":
-            raise NotImplementedError("tangents w.r.t. Krivanek aberration coefficients are not "
-                                      "implemented in the CUDA gradient kernel")
+            # slot 1 = focal_length, slots 2..26 = the 25 KrivanekCoeffs fields in field order
+            names = [f.name for f in fields(type(self.coeffs))] if not isinstance(self.coeffs, dict) else None
+            if names is None:
+                from .aberrations import KrivanekCoeffs
+                names = [f.name for f in fields(KrivanekCoeffs)]
+            if len(path) == 2 and path[1] in names:
+                return [(2 + names.index(path[1]), 1.0)]
+            raise RuntimeError(f"Cannot find {path} in parameters of AberratedLensKrivanek")
         return super()._tg_param_seeds(path)
 
 

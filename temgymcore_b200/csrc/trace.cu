@@ -443,6 +443,34 @@ __device__ __forceinline__ KrivOut krivanek_poly(const double *p, double u, doub
   return o;
 }
 
+// Partial derivatives of (W, dW/dax, dW/day) w.r.t. ONE KrivanekCoeffs field (0..24 in field order), for the
+// parameter tangents of run_with_grads: the polynomial form is linear in every C_nm, and a phase phi_nm only
+// enters through z_nm = kappa C_nm (cos m phi - i sin m phi), whose derivative swaps the (cos, sin) pair for
+// (-m sin, m cos).  So the derivative is the same polynomial evaluated on a one-term coefficient set.
+__device__ __noinline__ KrivOut krivanek_poly_dfield(const double *p, int field, double u, double v) {
+  // harmonic pair index (order C12 C21 C23 C32 C34 C41 C43 C45 C52 C54 C56) and m per field; -1: no phase
+  const signed char pair[25] = {-1, 0, 0, 1, 1, 2, 2, -1, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, -1, 8, 8, 9, 9, 10, 10};
+  const signed char mval[25] = {0, 2, 2, 1, 1, 3, 3, 0, 2, 2, 4, 4, 1, 1, 3, 3, 5, 5, 0, 2, 2, 4, 4, 6, 6};
+  const bool is_phi[25] = {false, false, true, false, true, false, true, false, false, true, false, true, false,
+                           true, false, true, false, true, false, false, true, false, true, false, true};
+  double q[47];
+  for (int k = 0; k < 47; ++k) q[k] = 0.0;
+  const int t = pair[field];
+  const double m = (double)mval[field];
+  if (!is_phi[field]) {
+    q[field] = 1.0;
+    if (t >= 0) {
+      q[25 + 2 * t] = p[25 + 2 * t];
+      q[26 + 2 * t] = p[26 + 2 * t];
+    }
+  } else {
+    q[field - 1] = p[field - 1];
+    q[25 + 2 * t] = -m * p[26 + 2 * t];
+    q[26 + 2 * t] = m * p[25 + 2 * t];
+  }
+  return krivanek_poly<false>(q, u, v);
+}
+
 // (dW/dax, dW/day, W) of the Krivanek aberration function (aberrations.py:42-108).  N = 0: values only;
 // N = 2: the arguments are the seeds (ax, e0), (ay, e1), the tangents returned are the derivatives
 // w.r.t. (ax, ay) -- the symmetric Hessian of W for dWx / dWy, the gradient for W -- and the caller
@@ -835,9 +863,23 @@ __global__ void __launch_bounds__(kTraceThreads)
           const D f = gparam(model, gs, c, 1);
           const D idx = (-x) / f + dx;
           const D idy = (-y) / f + dy;
-          Dual<2> gx, gy, w2;  // aberration coefficients are constants here (no coefficient tangents)
+          Dual<2> gx, gy, w2;
           krivanek<2>(cm.p + 1, dseed<2>(idx.v, 0), dseed<2>(idy.v, 1), gx, gy, w2);
-          const D dWx = dchain<NT>(gx, idx, idy), dWy = dchain<NT>(gy, idx, idy), W = dchain<NT>(w2, idx, idy);
+          D dWx = dchain<NT>(gx, idx, idy), dWy = dchain<NT>(gy, idx, idy), W = dchain<NT>(w2, idx, idy);
+          // tangents w.r.t. the aberration coefficients (slots 2..26 = KrivanekCoeffs fields 0..24)
+          for (int sI = 0; sI < gs.n; ++sI) {
+            if (gs.s[sI].comp != c || gs.s[sI].slot < 2 || gs.s[sI].slot > 26) continue;
+            const KrivOut dp = krivanek_poly_dfield(cm.p + 1, gs.s[sI].slot - 2, idx.v, idy.v);
+            const double wgt = gs.s[sI].weight;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+              if (gs.s[sI].lane == k) {
+                dWx.t[k] += wgt * dp.Gx;
+                dWy.t[k] += wgt * dp.Gy;
+                W.t[k] += wgt * dp.W;
+              }
+            }
+          }
           dx = idx + (-dWx) / f;
           dy = idy + (-dWy) / f;
           pl = pl - (x * x + y * y) / (2.0 * f) + W / f;
@@ -1012,8 +1054,9 @@ extern "C" int tg_trace_grad_f64(const tg_model *model_host, int64_t n, const tg
     TG_REQUIRE(sd.comp >= 0 && sd.comp < model_host->n_comp, "seed component out of range");
     TG_REQUIRE(sd.slot >= 0 && sd.slot <= TG_NPARAM, "seed slot out of range");
     TG_REQUIRE(sd.lane >= 0 && sd.lane < TG_GRAD_LANES, "seed lane out of range");
-    if (model_host->comp[sd.comp].op == TG_OP_KRIVANEK && sd.slot >= 2) {
-      tg_set_error("tangents w.r.t. Krivanek aberration coefficients are not implemented");
+    if (model_host->comp[sd.comp].op == TG_OP_KRIVANEK && sd.slot > 26) {
+      // slots 2..26 are the 25 KrivanekCoeffs fields; 27.. hold derived (cos, sin)(m phi0) pairs
+      tg_set_error("Krivanek slots above 26 are derived constants: seed the phi field (slots 2..26) instead");
       return TG_EUNSUPPORTED;
     }
     gs.s[i] = sd;

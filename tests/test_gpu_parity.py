@@ -623,6 +623,36 @@ def test_run_with_grads(torch_cuda, goldens):
         run_with_grads(rays, model, [M.readme_model()[0].params.focal_length])  # not in this model
 
 
+def test_run_with_grads_krivanek_coefficients(torch_cuda):
+    """Tangents w.r.t. the aberration coefficients and phases of AberratedLensKrivanek (the README idiom
+    jax.jacobian(run_with_params, argnums=(0, 1)) applied to coeffs): CUDA kernel vs the oracle's duals
+    through the reference's polar formulas (the oracle itself agrees with central differences)."""
+    from dataclasses import replace
+    from temgymcore_b200.aberrations import KrivanekCoeffs
+    from temgymcore_b200.components import AberratedLensKrivanek
+    from temgymcore_b200.ray import RAY_FIELDS
+    from temgymcore_b200.run import run_with_grads
+    model = M.six_component_column()
+    full = KrivanekCoeffs(C10=3e-9, C12=1e-1, phi12=0.3, C21=1e3, phi21=-0.7, C23=1e3, phi23=0.2, C30=1e8,
+                          C32=2e7, phi32=1.1, C34=-3e7, phi34=0.4, C41=1e11, phi41=2.0, C43=-2e11, phi43=-1.3,
+                          C45=1e11, phi45=0.9, C50=1e15, C52=3e14, phi52=-0.5, C54=2e14, phi54=1.7, C56=-1e14,
+                          phi56=0.1)
+    model[1] = replace(model[1], coeffs=full)
+    rays = M.random_rays(2003, np.random.default_rng(5), scale=0.2e-9, slope=1e-6)
+    names = ["C10", "C12", "phi12", "C21", "phi23", "C30", "phi32", "C34", "phi41", "C43", "C45", "phi45", "C50",
+             "C52", "phi54", "C56", "phi56"]
+    refs = [getattr(model[1].params.coeffs, nm) for nm in names] + [model[1].params.focal_length, rays.params.x]
+    dirs = [(1, ("coeffs", nm)) for nm in names] + [(1, ("focal_length",)), ("ray", "x")]
+    ref_out, J = O.run_with_grads(rays, model, dirs)
+    value, grads = run_with_grads(rays, model, refs)
+    for f in RAY_FIELDS:
+        close(getattr(value, f), getattr(ref_out, f))
+    for k, r in enumerate(refs):
+        gr = grads[r._build()]
+        for i, f in enumerate(RAY_FIELDS):
+            close(getattr(gr, f), J[:, i, k], rtol=1e-10)
+
+
 # ------------------------------------------------------------------------------ transfer.py
 def test_transfer_rays(torch_cuda):
     from temgymcore_b200.transfer import transfer_rays, transfer_rays_pt_src
