@@ -11,7 +11,7 @@ from dataclasses import dataclass, fields
 import numpy as np
 
 
-@dataclass
+@dataclass(unsafe_hash=True)   # hashable: components holding it are dictionary keys of run_with_grads
 class KrivanekCoeffs:
     C10: float = 0.0
     C12: float = 0.0
