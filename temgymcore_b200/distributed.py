@@ -98,6 +98,9 @@ class PeerImage:
     ``field_sum(poly, nb, grid, ...)`` computes this rank's row block and the producing kernels
     store it into ALL ranks' images (``tg_field_sum_peers``), then ``barrier()`` runs the
     device-side barrier; afterwards ``self.image`` holds the complete image on every rank.
+    The image buffer is reused by the next ``field_sum`` (which first runs a barrier so that no rank
+    overwrites a peer's image that is still being consumed): use or copy ``image`` on the same stream
+    before calling it again.
     One process per GPU, all ranks on one node.  World size 1 works (and is what the 1-GPU tests run).
     """
 
@@ -160,6 +163,10 @@ class PeerImage:
         L = self._L
         r0, nr = row_shards(self.H, self.world)[self.rank]
         cull = DEFAULT_CULL_BITS if cull_bits is None else int(cull_bits)
+        if self.epoch > 0 and self.world > 1:
+            # the image is reused: no rank may store into its peers' images before every rank has consumed the
+            # previous result (their consumers precede this barrier on their streams)
+            self.barrier()
         with torch.cuda.device(self.device):
             L.check(self._lib.tg_field_sum_peers(
                 int(nb), poly.data_ptr() if nb else None, L.dbl_array(grid.px2m_affine), self.H, self.W, r0, nr,
