@@ -237,28 +237,54 @@ __global__ void __launch_bounds__(128)
 }
 
 // GaussianRay.q_inv / Q_inv (gaussian.py:138-177)
+__device__ __forceinline__ M2<cd> qinv_of(double wx, double wy, double Rx, double Ry, double lam, double theta) {
+  const double pi = 3.141592653589793;
+  const cd qx = isinf(Rx) ? cd{0.0, lam / (pi * (wx * wx))} : cd{-1.0 / Rx, lam / (pi * (wx * wx))};
+  const cd qy = isinf(Ry) ? cd{0.0, lam / (pi * (wy * wy))} : cd{-1.0 / Ry, lam / (pi * (wy * wy))};
+  double s, c;
+  sincos(theta, &s, &c);
+  // einsum("nij,njk,npk->nip", R, diag, R), R = [[c,-s],[s,c]]
+  M2<cd> Q;
+  Q.a00 = (c * qx) * c + ((-s) * qy) * (-s);
+  Q.a01 = (c * qx) * s + ((-s) * qy) * c;
+  Q.a10 = (s * qx) * c + (c * qy) * (-s);
+  Q.a11 = (s * qx) * s + (c * qy) * c;
+  return Q;
+}
 __global__ void __launch_bounds__(128)
     qinv_kernel(long long nb, const double *__restrict__ waist, const double *__restrict__ radii,
                 const double *__restrict__ wl, const double *__restrict__ theta,
                 double *__restrict__ Qi) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nb) return;
-  const double wx = waist[i * 2], wy = waist[i * 2 + 1];
-  const double Rx = radii[i * 2], Ry = radii[i * 2 + 1];
-  const double lam = wl[i];
-  const double pi = 3.141592653589793;
-  const cd qx = isinf(Rx) ? cd{0.0, lam / (pi * (wx * wx))} : cd{-1.0 / Rx, lam / (pi * (wx * wx))};
-  const cd qy = isinf(Ry) ? cd{0.0, lam / (pi * (wy * wy))} : cd{-1.0 / Ry, lam / (pi * (wy * wy))};
-  double s, c;
-  sincos(theta[i], &s, &c);
-  // einsum("nij,njk,npk->nip", R, diag, R), R = [[c,-s],[s,c]]
-  const cd Q00 = (c * qx) * c + ((-s) * qy) * (-s);
-  const cd Q01 = (c * qx) * s + ((-s) * qy) * c;
-  const cd Q10 = (s * qx) * c + (c * qy) * (-s);
-  const cd Q11 = (s * qx) * s + (c * qy) * c;
+  const M2<cd> Q = qinv_of(waist[i * 2], waist[i * 2 + 1], radii[i * 2], radii[i * 2 + 1], wl[i], theta[i]);
   double *o = Qi + i * 8;
-  o[0] = Q00.re; o[1] = Q00.im; o[2] = Q01.re; o[3] = Q01.im;
-  o[4] = Q10.re; o[5] = Q10.im; o[6] = Q11.re; o[7] = Q11.im;
+  o[0] = Q.a00.re; o[1] = Q.a00.im; o[2] = Q.a01.re; o[3] = Q.a01.im;
+  o[4] = Q.a10.re; o[5] = Q.a10.im; o[6] = Q.a11.re; o[7] = Q.a11.im;
+}
+
+// make_gaussian_image's per-beamlet chain in ONE kernel (gaussian.py:240-262): Q_inv from the beam
+// parameters, k = 2 pi / lambda, p0 = k * pathlength, then the coefficients from the traced ABCD.
+// Same device functions, same operation order as qinv_kernel -> wave_kernel -> coeffs_abcd_kernel.
+__global__ void __launch_bounds__(128)
+    coeffs_from_beam_kernel(long long nb, const double *__restrict__ amp, const double *__restrict__ pl,
+                            const double *__restrict__ waist, const double *__restrict__ radii,
+                            const double *__restrict__ wl, const double *__restrict__ theta,
+                            const double *__restrict__ abcd, const double *__restrict__ r1x,
+                            const double *__restrict__ r1y, const double *__restrict__ thx,
+                            const double *__restrict__ thy, double *__restrict__ poly) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const M2<cd> Q = qinv_of(waist[i * 2], waist[i * 2 + 1], radii[i * 2], radii[i * 2 + 1], wl[i], theta[i]);
+  const double kk = (2.0 * 3.141592653589793) / wl[i];  // gaussian.py:254
+  const double p0 = kk * pl[i];                          // gaussian.py:255
+  const double *m = abcd + i * 25;
+  const M2<double> A{m[0], m[1], m[5], m[6]};
+  const M2<double> B{m[2], m[3], m[7], m[8]};
+  const M2<double> C{m[10], m[11], m[15], m[16]};
+  const M2<double> D{m[12], m[13], m[17], m[18]};
+  beamlet_poly(amp[i], p0, Q, A, B, C, D, m[4], m[9], m[14], m[19], r1x[i], r1y[i], thx[i], thy[i], kk,
+               poly + i * 12);
 }
 
 __global__ void __launch_bounds__(128)
@@ -345,6 +371,17 @@ extern "C" int tg_beamlet_coeffs_abcd_f64(int64_t nb, const double *amp,
   coeffs_abcd_kernel<<<nblocks(nb, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       nb, amp, phase_offset, Q1_inv, abcd, r1m_x, r1m_y, th_x, th_y, k, poly);
   return tg_launch_check("coeffs_abcd_kernel");
+}
+
+// internal (host_api.cu): the fused chain of tg_make_gaussian_image_f64
+int tg_coeffs_from_beam(int64_t nb, const double *amp, const double *pathlength, const double *waist_xy,
+                        const double *radii_xy, const double *wavelength, const double *theta,
+                        const double *abcd, const double *r1x, const double *r1y, const double *thx,
+                        const double *thy, double *poly, cudaStream_t st) {
+  if (nb == 0) return TG_OK;
+  coeffs_from_beam_kernel<<<nblocks(nb, 128), 128, 0, st>>>(nb, amp, pathlength, waist_xy, radii_xy, wavelength,
+                                                           theta, abcd, r1x, r1y, thx, thy, poly);
+  return tg_launch_check("coeffs_from_beam_kernel");
 }
 
 extern "C" int tg_input_coeffs_f64(int64_t nb, const double *amp, const double *phase_offset,

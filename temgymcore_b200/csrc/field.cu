@@ -92,33 +92,65 @@ __device__ __forceinline__ double quad_min_rect(const double *G, double U, doubl
 __global__ void __launch_bounds__(128)
     prep_kernel(long long nb, const double *__restrict__ poly, double X0, double Xc, double Xr,
                 double Y0, double Yc, double Yr, int H, int W, double *__restrict__ table,
-                unsigned long long *__restrict__ gref_key) {
+                unsigned long long *__restrict__ gref_key, const TgPrepExtra ex) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nb) return;
-  const double *c = poly + i * 12;
-  double a[2][6];
+  double cross = 0.0, peak = -INFINITY;
+  if (i < nb) {
+    const double *c = poly + i * 12;
+    double a[2][6];
 #pragma unroll
-  for (int p = 0; p < 2; ++p) {
-    const double c0 = c[0 + p], c1 = c[2 + p], c2 = c[4 + p], c3 = c[6 + p], c4 = c[8 + p],
-                 c5 = c[10 + p];
-    a[p][3] = c3 * Xc * Xc + c4 * Xc * Yc + c5 * Yc * Yc;
-    a[p][5] = c3 * Xr * Xr + c4 * Xr * Yr + c5 * Yr * Yr;
-    a[p][4] = 2.0 * c3 * Xc * Xr + c4 * (Xc * Yr + Xr * Yc) + 2.0 * c5 * Yc * Yr;
-    a[p][1] = c1 * Xc + c2 * Yc + 2.0 * c3 * X0 * Xc + c4 * (X0 * Yc + Y0 * Xc) + 2.0 * c5 * Y0 * Yc;
-    a[p][2] = c1 * Xr + c2 * Yr + 2.0 * c3 * X0 * Xr + c4 * (X0 * Yr + Y0 * Xr) + 2.0 * c5 * Y0 * Yr;
-    a[p][0] = c0 + c1 * X0 + c2 * Y0 + c3 * X0 * X0 + c4 * X0 * Y0 + c5 * Y0 * Y0;
-  }
-  double *t = table + i * 12;
-  double G[6];
+    for (int p = 0; p < 2; ++p) {
+      const double c0 = c[0 + p], c1 = c[2 + p], c2 = c[4 + p], c3 = c[6 + p], c4 = c[8 + p],
+                   c5 = c[10 + p];
+      a[p][3] = c3 * Xc * Xc + c4 * Xc * Yc + c5 * Yc * Yc;
+      a[p][5] = c3 * Xr * Xr + c4 * Xr * Yr + c5 * Yr * Yr;
+      a[p][4] = 2.0 * c3 * Xc * Xr + c4 * (Xc * Yr + Xr * Yc) + 2.0 * c5 * Yc * Yr;
+      a[p][1] = c1 * Xc + c2 * Yc + 2.0 * c3 * X0 * Xc + c4 * (X0 * Yc + Y0 * Xc) + 2.0 * c5 * Y0 * Yc;
+      a[p][2] = c1 * Xr + c2 * Yr + 2.0 * c3 * X0 * Xr + c4 * (X0 * Yr + Y0 * Xr) + 2.0 * c5 * Y0 * Yr;
+      a[p][0] = c0 + c1 * X0 + c2 * Y0 + c3 * X0 * X0 + c4 * X0 * Y0 + c5 * Y0 * Y0;
+    }
+    double *t = table + i * 12;
+    double G[6], T4 = 0.0;
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    t[j] = a[0][j] * kInv2Pi;
-    G[j] = a[1][j] * kLog2e;   // envelope exponent in bits: |field| = 2^-g
-    t[6 + j] = -G[j];
+    for (int j = 0; j < 6; ++j) {
+      const double tj = a[0][j] * kInv2Pi;
+      t[j] = tj;
+      if (j == 4) T4 = tj;
+      G[j] = a[1][j] * kLog2e;   // envelope exponent in bits: |field| = 2^-g
+      t[6 + j] = -G[j];
+    }
+    if (gref_key) {
+      const double gmin = quad_min_rect(G, (double)(H - 1), (double)(W - 1));
+      if (isfinite(gmin)) atomicMin(gref_key, enc_ordered(gmin));
+    }
+    if (ex.sep_key) {
+      // cross-term contribution across the detector, in units of the separability tolerances
+      // (2^-24 turn of phase, 2^-20 bit of envelope); NaN beamlets are carried by the factors themselves
+      const double hw = (double)H * (double)W;
+      cross = fmax(fabs(T4) * hw * 16777216.0, fabs(G[4]) * hw * 1048576.0);
+      if (!(cross == cross)) cross = 0.0;
+    }
+    if (ex.peak_key) {
+      // peak over the call's rows of log2 |U_n(row)| = (E0 + max_col part) + E2 r + E5 r^2, E = -G
+      const double q0 = -G[0] + tg_col_env_max(-G[1], -G[3], (double)(W - 1)), q1 = -G[2], q2 = -G[5];
+      const double s_lo = (double)ex.row0, s_hi = (double)(ex.row0 + ex.nrows - 1);
+      peak = fmax(q0 + s_lo * (q1 + q2 * s_lo), q0 + s_hi * (q1 + q2 * s_hi));
+      if (q2 < 0.0) {
+        const double sv = fmin(fmax(-0.5 * q1 / q2, s_lo), s_hi);
+        peak = fmax(peak, q0 + sv * (q1 + q2 * sv));
+      }
+      if (!isfinite(peak)) peak = -INFINITY;   // NaN / inf beamlets do not set the scale
+    }
   }
-  if (gref_key) {
-    const double gmin = quad_min_rect(G, (double)(H - 1), (double)(W - 1));
-    if (isfinite(gmin)) atomicMin(gref_key, enc_ordered(gmin));
+  if (ex.sep_key || ex.peak_key) {             // block-uniform: every lane of every warp gets here
+    for (int o = 16; o > 0; o >>= 1) {
+      cross = fmax(cross, __shfl_xor_sync(0xffffffffu, cross, o));
+      peak = fmax(peak, __shfl_xor_sync(0xffffffffu, peak, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (ex.sep_key && cross > 0.0) atomicMax(ex.sep_key, (unsigned long long)__double_as_longlong(cross));
+      if (ex.peak_key && peak > -INFINITY) atomicMax(ex.peak_key, tg_enc_ordered(peak));
+    }
   }
 }
 
@@ -578,9 +610,14 @@ int choose_split(long long tiles, long long nb, int slots, bool culling, size_t 
 
 // shared with separable.cu: metre-space polynomials -> pixel-space {turns, bits} table
 int tg_launch_prep(int64_t nb, const double *poly, const double px2m[6], int H, int W, double *table,
-                   unsigned long long *gref_key, cudaStream_t st) {
+                   unsigned long long *gref_key, cudaStream_t st, const TgPrepExtra *extra) {
+  TgPrepExtra ex;
+  ex.sep_key = ex.peak_key = nullptr;
+  ex.row0 = 0;
+  ex.nrows = H;
+  if (extra) ex = *extra;
   prep_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(nb, poly, px2m[0], px2m[1], px2m[2], px2m[3],
-                                                            px2m[4], px2m[5], H, W, table, gref_key);
+                                                            px2m[4], px2m[5], H, W, table, gref_key, ex);
   return tg_launch_check("prep_kernel");
 }
 

@@ -207,8 +207,8 @@ extern "C" int tg_metres_to_pixels_host(int64_t n, const double *x, const double
   return rc;
 }
 
-// Device-resident make_gaussian_image (gaussian.py:225-273) as ONE call: ray kernel with ABCD,
-// Q_inv, wave numbers, coefficient builder, field sum (method dispatch), all enqueued on `stream`.
+// Device-resident make_gaussian_image (gaussian.py:225-273) as ONE call: ray kernel with ABCD, one
+// kernel for Q_inv + wave numbers + coefficients, field sum (method dispatch), all enqueued on `stream`.
 extern "C" int tg_make_gaussian_image_f64(const tg_model *model_host, int64_t nb,
                                           const double *const rays[7], const double *amplitude,
                                           const double *waist_xy, const double *radii_xy,
@@ -226,9 +226,9 @@ extern "C" int tg_make_gaussian_image_f64(const tg_model *model_host, int64_t nb
   int dev = 0;
   TG_CUDA(cudaGetDevice(&dev));
   tg_tune_mempool(dev);
-  double *scratch = nullptr;  // k n | p0 n | abcd 25n | qinv 8n | poly 12n
-  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)nb * 47 * 8, s));
-  double *dk = scratch, *dp0 = dk + nb, *dabcd = dp0 + nb, *dq = dabcd + 25 * nb, *dpoly = dq + 8 * nb;
+  double *scratch = nullptr;  // abcd 25n | poly 12n
+  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)nb * 37 * 8, s));
+  double *dabcd = scratch, *dpoly = dabcd + 25 * nb;
   tg_ray_in in;
   for (int f = 0; f < 7; ++f) {
     in.ptr[f] = rays[f];
@@ -241,10 +241,9 @@ extern "C" int tg_make_gaussian_image_f64(const tg_model *model_host, int64_t nb
   }
   double *no_out[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int rc = tg_trace_f64(model_host, nb, &in, no_out, dabcd, TG_JAC_ABCD5, s);
-  if (rc == TG_OK) rc = tg_gaussian_qinv_f64(nb, waist_xy, radii_xy, wavelength, theta, dq, s);
-  if (rc == TG_OK) rc = tg_wave_numbers(nb, wavelength, rays[5], dk, dp0, s);
-  if (rc == TG_OK)
-    rc = tg_beamlet_coeffs_abcd_f64(nb, amplitude, dp0, dq, dabcd, rays[0], rays[1], rays[2], rays[3], dk, dpoly, s);
+  if (rc == TG_OK)   // Q_inv, k, p0 and the coefficients in one kernel
+    rc = tg_coeffs_from_beam(nb, amplitude, rays[5], waist_xy, radii_xy, wavelength, theta, dabcd, rays[0], rays[1],
+                             rays[2], rays[3], dpoly, s);
   if (rc == TG_OK)
     rc = tg_field_sum(nb, dpoly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, method, s);
   cudaFreeAsync(scratch, s);

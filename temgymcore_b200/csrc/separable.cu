@@ -145,15 +145,16 @@ struct GemmSmemCtl {
 };
 
 // D[M x Np] (+)= A[M x K] * B[Np x K]^T with A = A_hi + A_lo, B = B_hi + B_lo (3 products).
-// out: doubles, row pitch ldo; rows >= M / columns >= Np are not written.  out_scale (device, may be
-// NULL = 1): power-of-two factor applied to the accumulators in fp64 (undoes the fp16 pre-scaling).
+// out: doubles, row pitch ldo; rows >= M / columns >= Np are not written.  peak_key (device, may be NULL):
+// the accumulators are multiplied in fp64 by 2^(G - 2 headroom), G = tg_prescale_G(*peak_key) -- the exact
+// power of two that undoes the pre-scaling of the factors.
 template <bool F16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    int M, int Np, int K, double *__restrict__ out, long long ldo, int accumulate_out,
-                   const double *__restrict__ out_scale, const unsigned long long *__restrict__ sep_guard,
-                   const __grid_constant__ TgPeers peers) {
+                   const unsigned long long *__restrict__ peak_key, double headroom,
+                   const unsigned long long *__restrict__ sep_guard, const __grid_constant__ TgPeers peers) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;  // the SFU path owns this call
   constexpr int BK = GemmCfg<F16>::BK, CHUNK_KB = GemmCfg<F16>::CHUNK_KB;
   constexpr uint32_t kIdesc = Idesc<F16, BN>::value, kIdesc2 = Idesc<F16, 2 * BN>::value;
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (acc == 0) acc_ph ^= 1u;
     }
     const int row = m0 + q * 32 + lane;
-    const double sc = out_scale ? *out_scale : 1.0;
+    const double sc = peak_key ? scalbn(1.0, (int)(tg_prescale_G(*peak_key) - 2.0 * headroom)) : 1.0;
     if (row < M) {
       double *o = out + (long long)row * ldo + n0 + h * 64;
       const int ncol = min(64, Np - (n0 + h * 64));
@@ -319,16 +320,6 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-// max over c in [0, W-1] of E1 c + E3 c^2 (the column part of the envelope exponent, bits)
-__device__ __forceinline__ double col_env_max(double E1, double E3, double Wm1) {
-  double best = fmax(0.0, Wm1 * (E1 + E3 * Wm1));
-  if (E3 < 0.0) {
-    const double cs = fmin(fmax(-E1 / (2.0 * E3), 0.0), Wm1);
-    best = fmax(best, cs * (E1 + E3 * cs));
-  }
-  return isfinite(best) ? best : 0.0;
-}
-
 // table: pixel-space {T0..T5, E0..E5} per beamlet (prep_kernel of field.cu).
 //
 // One thread per beamlet walks a strip of FS consecutive rows (or columns): the table entry and
@@ -407,57 +398,23 @@ template <> struct Operand<true> {
 // the same treatment with headroom 0, which keeps weak beamlets out of the fp32 flush-to-zero range
 template <bool F16> struct Headroom { static constexpr double value = F16 ? 14.0 : 0.0; };
 
-// fp16 pre-scaling: G = ceil(max over beamlets of the peak of log2|U_n(row)| over the call's rows)
-__device__ __forceinline__ unsigned long long enc_ordered_max(double v) {
-  unsigned long long b = (unsigned long long)__double_as_longlong(v);
-  return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
-}
-__global__ void __launch_bounds__(256)
-    row_peak_kernel(const double *__restrict__ table, long long nb, int row0, int nrows, int W,
-                    unsigned long long *__restrict__ peak_key) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  double best = -INFINITY;
-  if (i < nb) {
-    const double *t = table + i * 12;
-    const double q0 = t[6 + 0] + col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1)), q1 = t[6 + 2], q2 = t[6 + 5];
-    const double s_lo = (double)row0, s_hi = (double)(row0 + nrows - 1);
-    best = fmax(q0 + s_lo * (q1 + q2 * s_lo), q0 + s_hi * (q1 + q2 * s_hi));
-    if (q2 < 0.0) {
-      const double sv = fmin(fmax(-0.5 * q1 / q2, s_lo), s_hi);
-      best = fmax(best, q0 + sv * (q1 + q2 * sv));
-    }
-    if (!isfinite(best)) best = -INFINITY;  // NaN / inf beamlets do not set the scale (their factors carry them)
-  }
-  for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
-  if ((threadIdx.x & 31) == 0 && best > -INFINITY) atomicMax(peak_key, enc_ordered_max(best));
-}
-// shift[0] = G (bits subtracted from the row-factor exponent), shift[1] = 2^(G - 2*headroom) (epilogue scale)
-__global__ void prescale_kernel(const unsigned long long *__restrict__ peak_key, double headroom,
-                                double *__restrict__ shift) {
-  const unsigned long long k = *peak_key;
-  double G = 0.0;
-  if (k != 0ULL) {
-    const unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;
-    G = ceil(__longlong_as_double((long long)b));
-  }
-  G = fmin(fmax(G, -960.0), 960.0);
-  shift[0] = G;
-  shift[1] = exp2(G - 2.0 * headroom);
-}
-
+// Pre-scaling: G = ceil(max over beamlets of the peak of log2|U_n(row)| over the call's rows) comes from
+// the prep kernel's peak key (TgPrepExtra); the row factors are scaled by 2^(headroom - G), the column
+// factors by 2^headroom, the GEMM epilogue by 2^(G - 2 headroom).
 // A[(row - row0)][2n..2n+1] = U_n(row) for rows [row0, row0+M), beamlets [b0, b0+nbatch)
 template <bool F16>
 __global__ void __launch_bounds__(128)
     factor_rows_kernel(const double *__restrict__ table, long long b0, int nbatch, int row0, int M, int W,
                        long long ldk, void *__restrict__ Ahi, void *__restrict__ Alo,
-                       const double *__restrict__ shift, const unsigned long long *__restrict__ sep_guard) {
+                       const unsigned long long *__restrict__ peak_key,
+                       const unsigned long long *__restrict__ sep_guard) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int m0 = blockIdx.y * FS;
   if (n >= nbatch) return;
   const double *t = table + (b0 + n) * 12;
-  double mu = col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
-  mu += Headroom<F16>::value - shift[0];
+  double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
+  mu += Headroom<F16>::value - tg_prescale_G(*peak_key);
   const Strip1D st = strip_setup(t[0], t[2], t[5], t[6 + 0] + mu, t[6 + 2], t[6 + 5], (double)(row0 + m0));
 #pragma unroll 4
   for (int j = 0; j < FS; ++j) {
@@ -483,7 +440,7 @@ __global__ void __launch_bounds__(128)
   const int c0 = blockIdx.y * FS;
   if (n >= nbatch) return;
   const double *t = table + (b0 + n) * 12;
-  const double mu = col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1)) - Headroom<F16>::value;
+  const double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1)) - Headroom<F16>::value;
   const Strip1D st = strip_setup(0.0, t[1], t[3], -mu, t[6 + 1], t[6 + 3], (double)c0);
 #pragma unroll 4
   for (int j = 0; j < FS; ++j) {
@@ -499,21 +456,6 @@ __global__ void __launch_bounds__(128)
       Operand<F16>::store2(Blo, o1, il, rl);
     }
   }
-}
-
-// max over beamlets of the cross-term contribution across the detector (turns, bits)
-__global__ void __launch_bounds__(256)
-    cross_term_kernel(const double *__restrict__ table, long long nb, double hw, unsigned long long *key) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  double v = 0.0;
-  if (i < nb) {
-    const double t4 = fabs(table[i * 12 + 4]) * hw * 16777216.0;  // in units of 2^-24 turn
-    const double e4 = fabs(table[i * 12 + 10]) * hw * 1048576.0;  // in units of 2^-20 bit
-    v = fmax(t4, e4);
-    if (!(v == v)) v = 0.0;  // NaN beamlets are handled by the (NaN) factors themselves
-  }
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(key, (unsigned long long)__double_as_longlong(v));
 }
 
 // ---- cost-aware dispatch (AUTO only) -----------------------------------------------------
@@ -620,7 +562,7 @@ int make_map(CUtensorMap *m, const void *base, long long rows, long long K, long
 
 template <bool F16>
 int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *Blo, int M, int Np, int K,
-                long long ldk, double *out, long long ldo, int accumulate, const double *out_scale,
+                long long ldk, double *out, long long ldo, int accumulate, const unsigned long long *peak_key,
                 const unsigned long long *sep_guard, cudaStream_t st, const TgPeers &peers) {
   CUtensorMap ta, tb, tc, td;
   int rc;
@@ -631,14 +573,14 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
   const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
   TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((Np + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
-  gemm_x3_kernel<F16><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, tc, td, M, Np, K, out, ldo, accumulate, out_scale,
-                                                        sep_guard, peers);
+  gemm_x3_kernel<F16><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, tc, td, M, Np, K, out, ldo, accumulate, peak_key,
+                                                        Headroom<F16>::value, sep_guard, peers);
   return tg_launch_check(F16 ? "gemm_x3_kernel<f16>" : "gemm_x3_kernel<tf32>");
 }
 
 template <bool F16>
 int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, long long ldk, void *Ahi, void *Alo,
-                void *Bhi, void *Blo, double *acc, const double *shift, const unsigned long long *guard,
+                void *Bhi, void *Blo, double *acc, const unsigned long long *peak, const unsigned long long *guard,
                 cudaStream_t st, const TgPeers &gemm_peers) {
   const int Np = 2 * W;
   int rc = TG_OK;
@@ -650,12 +592,12 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
     // (the tensor maps are encoded with the true K: the TMA unit zero-fills the K padding)
     dim3 ga((unsigned)((nbatch + 127) / 128), (unsigned)((nrows + FS - 1) / FS));
     dim3 gb((unsigned)((nbatch + 127) / 128), (unsigned)((W + FS - 1) / FS));
-    factor_rows_kernel<F16><<<ga, 128, 0, st>>>(table, b0, nbatch, row0, nrows, W, ldk, Ahi, Alo, shift, guard);
+    factor_rows_kernel<F16><<<ga, 128, 0, st>>>(table, b0, nbatch, row0, nrows, W, ldk, Ahi, Alo, peak, guard);
     factor_cols_kernel<F16><<<gb, 128, 0, st>>>(table, b0, nbatch, W, ldk, Bhi, Blo, guard);
     rc = tg_launch_check("factor kernels");
     if (rc == TG_OK)
       rc = launch_gemm<F16>(Ahi, Alo, Bhi, Blo, nrows, Np, K, ldk, acc, (long long)Np, b0 > 0 ? 1 : 0,
-                            shift + 1, guard, st, (b0 + kBatch >= nb) ? gemm_peers : none);  // peers: final batch only
+                            peak, guard, st, (b0 + kBatch >= nb) ? gemm_peers : none);  // peers: final batch only
   }
   return rc;
 }
@@ -732,15 +674,14 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   unsigned char *ws = nullptr;
   TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), table_bytes + 256 + 2 * a_bytes + 2 * b_bytes + acc_bytes, st));
   double *table = reinterpret_cast<double *>(ws);
-  // control block after the table: key (8) | peak key (8) | shift[2] (16) || gref (8) at +64 || est (8) at +128
+  // control block after the table: key (8) | peak key (8) || gref (8) at +64 || est (8) at +128
   unsigned long long *key = key_async ? key_async : reinterpret_cast<unsigned long long *>(ws + table_bytes);
   unsigned long long *peak = reinterpret_cast<unsigned long long *>(ws + table_bytes + 8);
-  double *shift = reinterpret_cast<double *>(ws + table_bytes + 16);
   const unsigned long long *guard = key_async;  // async mode: kernels decide on the device
   unsigned char *Ahi = ws + table_bytes + 256, *Alo = Ahi + a_bytes, *Bhi = Alo + a_bytes, *Blo = Bhi + b_bytes;
   double *acc = out_is_c128 ? static_cast<double *>(out) : reinterpret_cast<double *>(Blo + b_bytes);
   int rc = TG_OK;
-  cudaError_t e = cudaMemsetAsync(ws + table_bytes, 0, 32, st);  // own key slot, peak key, shift
+  cudaError_t e = cudaMemsetAsync(ws + table_bytes, 0, 16, st);  // own key slot, peak key
   if (key_async && e == cudaSuccess) e = cudaMemsetAsync(key, 0, 8, st);
   // cost model (AUTO with culling enabled): brightest-peak key and tile estimate live after the key slot
   const bool cost = key_async != nullptr && cost_cull_bits > 0;
@@ -748,20 +689,19 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   double *est = reinterpret_cast<double *>(ws + table_bytes + 128);
   if (cost && e == cudaSuccess) e = cudaMemsetAsync(gref, 0xFF, 8, st);
   if (cost && e == cudaSuccess) e = cudaMemsetAsync(est, 0, 8, st);
-  if (e == cudaSuccess) rc = tg_launch_prep(nb, poly, px2m, H, W, table, cost ? gref : nullptr, st);
-  if (e == cudaSuccess && rc == TG_OK) {
-    cross_term_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(table, nb, (double)H * (double)W, key);
-    rc = tg_launch_check("cross_term_kernel");
+  if (e == cudaSuccess) {
+    // one O(nb) kernel: pixel-space table + separability verdict + pre-scaling peak (+ brightest-peak key)
+    TgPrepExtra ex;
+    ex.sep_key = key;
+    ex.peak_key = peak;
+    ex.row0 = row0;
+    ex.nrows = nrows;
+    rc = tg_launch_prep(nb, poly, px2m, H, W, table, cost ? gref : nullptr, st, &ex);
   }
   if (cost && e == cudaSuccess && rc == TG_OK) {
     sfu_cost_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(table, nb, H, W, gref, cost_cull_bits, est);
     verdict_kernel<<<1, 1, 0, st>>>(key, est, (double)nb * (double)H * (double)W, kSfuWinsBelow);
     rc = tg_launch_check("cost kernels");
-  }
-  if (e == cudaSuccess && rc == TG_OK) {
-    row_peak_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(table, nb, row0, nrows, W, peak);
-    prescale_kernel<<<1, 1, 0, st>>>(peak, f16 ? Headroom<true>::value : Headroom<false>::value, shift);
-    rc = tg_launch_check("pre-scaling kernels");
   }
   unsigned long long hkey = 0;
   if (e == cudaSuccess && rc == TG_OK && !key_async) {
@@ -781,9 +721,9 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
     }
   }
   if (rc == TG_OK)
-    rc = f16 ? run_batches<true>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, shift, guard, st,
+    rc = f16 ? run_batches<true>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
                                  out_is_c128 ? pe : none)
-             : run_batches<false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, shift, guard, st,
+             : run_batches<false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
                                   out_is_c128 ? pe : none);
   if (rc == TG_OK && !out_is_c128) {
     const size_t n = npix * 2;

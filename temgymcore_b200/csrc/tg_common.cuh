@@ -7,8 +7,16 @@
 
 void tg_set_error(const char *fmt, ...);
 void tg_tune_mempool(int dev);
+// Optional by-products of the prep kernel for the tensor-core path (one launch instead of three):
+// sep_key  <- atomicMax of the bits of max_n(cross term / tolerance)   (separability verdict)
+// peak_key <- atomicMax of the ordered-uint key of max_n peak log2|U_n(row)| over rows [row0, row0+nrows)
+struct TgPrepExtra {
+  unsigned long long *sep_key;
+  unsigned long long *peak_key;
+  int row0, nrows;
+};
 int tg_launch_prep(int64_t nb, const double *poly, const double px2m[6], int H, int W, double *table,
-                   unsigned long long *gref_key, cudaStream_t st);
+                   unsigned long long *gref_key, cudaStream_t st, const TgPrepExtra *extra = nullptr);
 // k = 2 pi / wavelength, p0 = k * pathlength (reference gaussian.py:253-255); internal helper
 int tg_wave_numbers(int64_t nb, const double *wavelength, const double *pathlength, double *k,
                     double *p0, cudaStream_t st);
@@ -21,6 +29,11 @@ struct TgPeers {
   int n;
   void *ptr[TG_MAX_PEERS];
 };
+// Q_inv + wave numbers + coefficients from the traced ABCD in one kernel (coeffs.cu)
+int tg_coeffs_from_beam(int64_t nb, const double *amp, const double *pathlength, const double *waist_xy,
+                        const double *radii_xy, const double *wavelength, const double *theta,
+                        const double *abcd, const double *r1x, const double *r1y, const double *thx,
+                        const double *thy, double *poly, cudaStream_t st);
 int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                       int nrows, void *out, int out_is_c128, int cull_bits, long long *n_evals_out,
                       const unsigned long long *sep_guard, cudaStream_t stream, const TgPeers *peers = nullptr);
@@ -40,6 +53,34 @@ __host__ __device__ inline bool tg_key_is_separable(unsigned long long key) {
   c.u = key;
   return !(c.d > 1.0);
 }
+
+#ifdef __CUDACC__
+// max over c in [0, W-1] of E1 c + E3 c^2 (the column part of the envelope exponent, bits)
+__device__ __forceinline__ double tg_col_env_max(double E1, double E3, double Wm1) {
+  double best = fmax(0.0, Wm1 * (E1 + E3 * Wm1));
+  if (E3 < 0.0) {
+    const double cs = fmin(fmax(-E1 / (2.0 * E3), 0.0), Wm1);
+    best = fmax(best, cs * (E1 + E3 * cs));
+  }
+  return isfinite(best) ? best : 0.0;
+}
+// monotone map double -> uint64 (for atomicMax / atomicMin on doubles) and back
+__device__ __forceinline__ unsigned long long tg_enc_ordered(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double tg_dec_ordered(unsigned long long k) {
+  unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;
+  return __longlong_as_double((long long)b);
+}
+// pre-scaling exponent of the tensor-core factors: G = ceil(brightest row-factor peak, bits), clamped;
+// key == 0: no finite beamlet set the peak
+__device__ __forceinline__ double tg_prescale_G(unsigned long long peak_key) {
+  double G = 0.0;
+  if (peak_key != 0ULL) G = ceil(tg_dec_ordered(peak_key));
+  return fmin(fmax(G, -960.0), 960.0);
+}
+#endif
 
 #define TG_CUDA(call)                                                                   \
   do {                                                                                  \

@@ -54,6 +54,14 @@ if what in ("jets", "all"):
     for _ in range(3):
         d = calculate_derivatives(rd, M.readme_model(), 3)
     torch.cuda.synchronize()
+if what in ("c3_tensor",):
+    from dataclasses import fields, replace
+    from temgymcore_b200.gaussian import make_gaussian_image_device
+    g3, model3 = M.biprism_case(100_000, (2048, 2048))
+    g3d = replace(g3, **{f.name: torch.as_tensor(getattr(g3, f.name), device=dev) for f in fields(g3)})
+    for _ in range(2):
+        make_gaussian_image_device(g3d, model3, cull_bits=0, method="tensor")
+    torch.cuda.synchronize()
 if what in ("field_c3",):
     from dataclasses import fields, replace
     from temgymcore_b200.gaussian import make_gaussian_image_device
