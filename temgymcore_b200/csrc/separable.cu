@@ -37,6 +37,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include "tg_common.cuh"
 
@@ -328,9 +329,12 @@ __device__ __forceinline__ float tf32_rna(float x) {
 // quadratic of the SFU kernel (field.cu).  Stores are coalesced: for a fixed row, consecutive
 // threads (beamlets) write consecutive k' pairs.
 // AUTO hands a separable problem to the culled SFU kernel when its estimated executed evaluations are
-// below this fraction of nb*H*W (measured break-even on B200: GEMM 4.1e-14 s per nominal evaluation,
-// SFU 6.3e-13 s per executed one -> 6.6 %; the estimate counts whole tiles, so stay below that)
-constexpr double kSfuWinsBelow = 0.045;
+// below this fraction of nb*H*W.  Measured on B200 with the fp16 x 3 GEMM (2.1e-14 s per nominal
+// evaluation) on the C3 geometry (~11 px envelopes): the tensor path wins at 1e5 beamlets on 2048^2
+// (8.6 vs 9.3 ms, estimate between 2 and 3 %), at 2e4 and 4e3 beamlets on 2048^2 and at 4e3 on 1024^2
+// (estimate 3-4.5 %), so the culled SFU sum only takes over below 2 % (tools/exp_auto.py; the
+// environment variable TG_SFU_WINS_BELOW overrides the constant).
+constexpr double kSfuWinsBelow = 0.02;
 constexpr int FS = 32;
 constexpr long long kBatch = 16384;  // beamlets per GEMM pass
 constexpr double kMagicF = 1572864.0;  // 1.5 * 2^20
@@ -700,7 +704,12 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   }
   if (cost && e == cudaSuccess && rc == TG_OK) {
     sfu_cost_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(table, nb, H, W, gref, cost_cull_bits, est);
-    verdict_kernel<<<1, 1, 0, st>>>(key, est, (double)nb * (double)H * (double)W, kSfuWinsBelow);
+    static const double sfu_wins_below = [] {       // tuning knob: TG_SFU_WINS_BELOW overrides the constant
+      const char *e = getenv("TG_SFU_WINS_BELOW");
+      const double v = e ? atof(e) : kSfuWinsBelow;
+      return (v >= 0.0 && v <= 1.0) ? v : kSfuWinsBelow;
+    }();
+    verdict_kernel<<<1, 1, 0, st>>>(key, est, (double)nb * (double)H * (double)W, sfu_wins_below);
     rc = tg_launch_check("cost kernels");
   }
   unsigned long long hkey = 0;
