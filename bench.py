@@ -205,6 +205,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
+    numa_cpus = None   # D.bind_to_gpu_numa(local): measured no effect on this pool (one NUMA node, all GPUs local to it)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -413,6 +414,8 @@ def run_ours(args):
     e2e = {"value": evals_per_step / (e2e_ms * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
            "api": "tg_make_gaussian_image_host (make_gaussian_image with host buffers)"}
+    if numa_cpus:
+        e2e["host_affinity"] = f"rank pinned to the {len(numa_cpus)} CPU cores local to its GPU (NVML)"
 
     # ---- ray half of the path: rays/s with the 5x5 ABCD, sharded, no communication.
     # Timed as RayTracePlan replays (model compiled once, static buffers, one graph node): the

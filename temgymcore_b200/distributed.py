@@ -24,6 +24,31 @@ from typing import Callable, Optional, Sequence, Tuple
 ROW_ALIGN = 32  # the field kernel's tile height: aligned shards keep tile origins identical
 
 
+def bind_to_gpu_numa(device_index: int):
+    """Pin this process to the CPU cores NVML reports as local to CUDA device ``device_index`` (one process
+    per GPU).  Pinned host buffers allocated afterwards land on the GPU's NUMA node, so the host<->device
+    copies of the host-buffer entry points (``tg_*_host``) do not cross the socket interconnect when eight
+    ranks share the box.  Returns the CPU list, or ``None`` when NVML / the affinity call is unavailable."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = [i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous ``[begin, end)`` of ``n`` independent units for ``rank``; sizes differ by
     at most one; every unit is owned by exactly one rank."""
