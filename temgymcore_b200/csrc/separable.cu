@@ -44,9 +44,19 @@
 namespace {
 
 constexpr int BM = 128, BN = 128;
-constexpr int BK_BYTES = 128;                   // one k-block = one 128-byte swizzle row per tile row
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = BM * BK_BYTES;       // 16 KiB
+// One k-block = one swizzle row (BK_BYTES) per tile row.  The ring holds 192 KB either way; what matters is
+// the share of it that can be in flight while one stage is being multiplied, (STAGES - 1) / STAGES: the
+// operand fetch (L2 hit ~1500 clk, HBM more) has to fit into the time the other stages take to be consumed.
+// 3 x 128-byte stages leave a window of 2 x 768 = 1536 clk, 6 x 64-byte stages 5 x 384 = 1920 clk -- but
+// measured on B200 the 64-byte variant (SWIZZLE_64B boxes) is SLOWER: C2 0.256 vs 0.226 ms, C3 10.3 vs 8.7 ms
+// (64-byte rows halve the TMA request size and the MMA's operand fetch efficiency), so 128 stays.
+#ifndef TG_GEMM_BK_BYTES
+#define TG_GEMM_BK_BYTES 128
+#endif
+constexpr int BK_BYTES = TG_GEMM_BK_BYTES;      // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+static_assert(BK_BYTES == 128 || BK_BYTES == 64, "k-block = one 128-byte or 64-byte swizzle row");
+constexpr int STAGES = 384 / BK_BYTES;          // 3 or 6 stages of 4 tiles: 192 KiB
+constexpr int TILE_BYTES = BM * BK_BYTES;       // 16 or 8 KiB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;     // A_hi, A_lo, B_hi, B_lo
 constexpr int CHUNK_K = 128;                    // k-elements per TMEM accumulation chunk
 template <bool F16> struct GemmCfg {
@@ -119,15 +129,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //  [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) | [32,46) SBO >> 4
-//  (1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+//  (8 swizzle rows between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B) / 4 (SWIZZLE_64B)
 __device__ __forceinline__ uint64_t make_smem_desc(const void *smem_tile) {
   const uint32_t addr = tg_smem_u32(smem_tile);
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((8 * BK_BYTES) >> 4) << 32;            // SBO: 8 rows of one swizzle row each
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(BK_BYTES == 128 ? 2 : 4) << 61;        // UMMA::LayoutType SWIZZLE_128B = 2, SWIZZLE_64B = 4
   return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a/b format at bits 7/10
@@ -556,7 +566,8 @@ int make_map(CUtensorMap *m, const void *base, long long rows, long long K, long
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  BK_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     tg_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return TG_ECUDA;
