@@ -423,9 +423,12 @@ def run_ours(args):
     # separately as ms_per_call_direct for the plain run_to_end_abcd call).
     from temgymcore_b200.run import RayTracePlan
     rays_section = {}
-    ray_cases = (("c1_1e6", 1_000_000, "c1"), ("steady_1e7", 10_000_000, "c1"),
-                 ("steady_1e8", 100_000_000, "c1"), ("c4_krivanek_1e7", 10_000_000, "c4"))
-    for label, n_rays, which in ray_cases:
+    ray_cases = (("c1_1e6", 1_000_000, "c1", True), ("steady_1e7", 10_000_000, "c1", True),
+                 ("steady_1e8", 100_000_000, "c1", True), ("c4_krivanek_1e7", 10_000_000, "c4", True),
+                 # rays/s WITHOUT the ABCD as well (run_to_end only: 56 B in + 56 B out per ray)
+                 ("c1_1e7_rays_only", 10_000_000, "c1", False), ("c4_1e7_rays_only", 10_000_000, "c4", False))
+    for label, n_rays, which, with_abcd in ray_cases:
+        ray_bytes = RAY_BYTES_ABCD if with_abcd else 112
         per = n_rays  # weak: every rank traces its own n_rays
         rng = np.random.default_rng(M.SEED + rank)
         if which == "c1":
@@ -438,30 +441,30 @@ def run_ours(args):
             wl = "C4 aberrated_probe 6-component column (AberratedLensKrivanek, Deflector, Lens, Biprism)"
         rd = Ray(*(torch.as_tensor(getattr(rr, f), device=dev) for f in RAY_FIELDS))
         del rr
-        rplan = RayTracePlan(rd, rmodel)
-        rt = timed(rplan.run, args.steps, args.warmup, flush=(per * RAY_BYTES_ABCD < (200 << 20)))
+        rplan = RayTracePlan(rd, rmodel, jacobian=with_abcd)
+        rt = timed(rplan.run, args.steps, args.warmup, flush=(per * ray_bytes < (200 << 20)))
         r_ms = max_over_ranks(float(np.sum(rt))) / args.steps
         direct = None
-        if per <= 10_000_000:
+        if per <= 10_000_000 and with_abcd:
             keep = {}
 
             def ray_step():
                 keep["o"] = run_to_end_abcd(rd, rmodel)
-            dt = timed(ray_step, args.steps, args.warmup, flush=(per * RAY_BYTES_ABCD < (200 << 20)))
+            dt = timed(ray_step, args.steps, args.warmup, flush=(per * ray_bytes < (200 << 20)))
             direct = max_over_ranks(float(np.sum(dt))) / args.steps
             del keep
         rate = per * world / (r_ms * 1e-3)
-        gbs = per * RAY_BYTES_ABCD / (r_ms * 1e-3) / 1e9
+        gbs = per * ray_bytes / (r_ms * 1e-3) / 1e9
         tkey = {"steady_1e7": "trace_kernel_1e7", "c4_krivanek_1e7": "trace_kernel_c4"}.get(label)
         rays_section[label] = {
-            "workload": wl, "rays_per_s": rate, "ms_per_launch": r_ms, "ms_per_call_direct": direct,
+            "workload": wl + ("" if with_abcd else " -- rays only, no ABCD"), "rays_per_s": rate, "ms_per_launch": r_ms, "ms_per_call_direct": direct,
             "rays_per_gpu": per, "scaling": "weak", "launch": "RayTracePlan (CUDA graph replay)",
-            "l2": "flushed between launches" if per * RAY_BYTES_ABCD < (200 << 20) else "working set >> L2",
+            "l2": "flushed between launches" if per * ray_bytes < (200 << 20) else "working set >> L2",
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": gbs / pk["hbm_gbs"],
                          "traffic": NCU_TRAFFIC[tkey][0] if tkey in NCU_TRAFFIC else None,
                          "traffic_source": NCU_TRAFFIC[tkey][1] if tkey in NCU_TRAFFIC else None,
-                         "bytes_per_ray": RAY_BYTES_ABCD, "peak_source": pk["source"]}}
+                         "bytes_per_ray": ray_bytes, "peak_source": pk["source"]}}
         del rd, rplan
         torch.cuda.empty_cache()
     # ---- higher-order derivatives (calculate_derivatives, run.py:119-147): orders 1..3 in one launch of
