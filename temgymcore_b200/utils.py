@@ -188,6 +188,19 @@ def FresnelPropagator(u1, L, wavelength, z, xp=None):
     """Paraxial free-space propagation of a sampled field over ``z`` by the transfer-function method
     (utils.py:248-265): the validator the reference's wave-optics tests compare the beamlet sum with.
     ``L`` is the side length of the (square-pixel) window; the pixel pitch is ``L / rows``."""
+    if xp is None and type(u1).__module__.startswith("torch"):
+        # device-side validator (SURVEY 8f rank 4): the same transfer-function method with torch.fft (cuFFT on
+        # a CUDA tensor), so a beamlet image can be cross-checked against wave optics without leaving the GPU
+        import math
+        import torch
+        rows, cols = u1.shape
+        pitch = L / rows
+        rdt = torch.float64 if u1.dtype in (torch.complex128, torch.float64) else torch.float32
+        fx = torch.fft.fftfreq(cols, d=pitch, dtype=rdt, device=u1.device)
+        fy = torch.fft.fftfreq(rows, d=pitch, dtype=rdt, device=u1.device)
+        FY, FX = torch.meshgrid(fy, fx, indexing="ij")
+        H = torch.exp(-1j * math.pi * wavelength * z * (FX ** 2 + FY ** 2))
+        return torch.fft.ifft2(H * torch.fft.fft2(u1))
     if xp is None:
         import numpy as xp
     rows, cols = u1.shape
@@ -204,7 +217,13 @@ def fresnel_lens_imaging_solution(E0, Y, X, ps, lambda0, z1, f, z2):
     import numpy as np
     k = 2 * np.pi / lambda0
     L = E0.shape[0] * ps
-    at_lens = FresnelPropagator(E0, L, lambda0, z1) * np.exp((-1j * k) / (2 * f) * (X ** 2 + Y ** 2))
+    if type(E0).__module__.startswith("torch"):     # torch tensors (CPU or CUDA): stay on their device
+        import torch
+        X, Y = torch.as_tensor(X, device=E0.device), torch.as_tensor(Y, device=E0.device)
+        lens = torch.exp((-1j * k) / (2 * f) * (X ** 2 + Y ** 2))
+    else:
+        lens = np.exp((-1j * k) / (2 * f) * (X ** 2 + Y ** 2))
+    at_lens = FresnelPropagator(E0, L, lambda0, z1) * lens
     return FresnelPropagator(at_lens, L, lambda0, z2)
 
 

@@ -159,3 +159,20 @@ def test_gaussian_ray_q_inv_property():
     ox, oy = O.gaussian_q_inv(w, Rc, wl)
     np.testing.assert_array_equal(qx, ox)
     np.testing.assert_array_equal(qy, oy)
+
+
+def test_fresnel_validators_torch_path_matches_numpy():
+    """FresnelPropagator / fresnel_lens_imaging_solution (utils.py:248-275) accept torch tensors (CPU here,
+    CUDA on the GPU box: torch.fft = cuFFT) and give the numpy result."""
+    import torch
+    from temgymcore_b200.utils import FresnelPropagator, fresnel_lens_imaging_solution
+    rng = np.random.default_rng(0)
+    u = rng.normal(size=(64, 48)) + 1j * rng.normal(size=(64, 48))
+    a = FresnelPropagator(u, 1e-3, 5e-7, 0.02)
+    b = FresnelPropagator(torch.as_tensor(u), 1e-3, 5e-7, 0.02).numpy()
+    np.testing.assert_allclose(b, a, rtol=0, atol=1e-13 * np.abs(a).max())
+    u = rng.normal(size=(64, 64)) + 1j * rng.normal(size=(64, 64))
+    y, x = np.meshgrid(np.linspace(-1, 1, 64) * 5e-4, np.linspace(-1, 1, 64) * 5e-4, indexing="ij")
+    a = fresnel_lens_imaging_solution(u, y, x, 1e-3 / 64, 5e-7, 0.05, 0.03, 0.07)
+    b = fresnel_lens_imaging_solution(torch.as_tensor(u), y, x, 1e-3 / 64, 5e-7, 0.05, 0.03, 0.07).numpy()
+    np.testing.assert_allclose(b, a, rtol=0, atol=1e-13 * np.abs(a).max())

@@ -197,3 +197,32 @@ def test_offset_tilted_beam_through_lens_vs_fresnel(backend):
         strong = b > 0.3
         dphi = np.angle(out * np.conj(out[pf]) * np.conj(ref * np.conj(ref[pf])))
         assert np.abs(dphi[strong]).max() < 0.1
+
+
+@pytest.mark.gpu
+def test_device_side_fresnel_cross_check():
+    """the wave-optics cross-check without leaving the GPU -- the beamlet image comes back
+    as a CUDA tensor, the validator (FresnelPropagator on torch.fft / cuFFT) runs on the same device."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dataclasses import fields, replace
+    from temgymcore_b200.gaussian import make_gaussian_image_device
+    from temgymcore_b200.utils import FresnelPropagator
+    wavelength, w0, z = 1e-3, 0.1, 1e-3
+    n = 500
+    det = Detector(z=z, pixel_size=(2e-3, 2e-3), shape=(n, n))
+    g = M.gaussian_rays([0.0], [0.0], wavelength=wavelength, w0=w0)
+    gd = replace(g, **{f.name: torch.as_tensor(np.asarray(getattr(g, f.name)), device="cuda") for f in fields(g)})
+    analytic = make_gaussian_image_device(gd, [det], cull_bits=0)
+    assert analytic.is_cuda
+    X, Y = det_axes(det)
+    u0 = torch.as_tensor(np.exp(-(X ** 2 + Y ** 2) / w0 ** 2).astype(complex), device="cuda")
+    fres = FresnelPropagator(u0, n * det.pixel_size[0], wavelength, z)
+    assert fres.is_cuda
+    np.testing.assert_allclose(fres.cpu().numpy(), fresnel_transfer(u0.cpu().numpy(), n * det.pixel_size[0],
+                                                                  wavelength, z), atol=1e-12)
+    a = analytic / analytic.abs().max()
+    f_ = fres / fres.abs().max()
+    mask = torch.as_tensor(X ** 2 + Y ** 2 < (0.4 * np.abs(X).max()) ** 2, device="cuda")
+    assert float((a.abs() - f_.abs())[mask].abs().max()) < 2e-2
