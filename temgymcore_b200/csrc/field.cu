@@ -198,7 +198,8 @@ struct __align__(16) Rec {
   float e2;       // en[3] as fp32
   float cr, ci;   // exp(i 2 pi dd): the phasor of the second difference (fp64 sincospi, rounded once)
   uint32_t cspan; // tile columns that can hold a contribution above the culling threshold: lo | hi << 16
-  uint32_t pad;
+  float rho;      // 2^(2 e2) when the envelope is SMOOTH on this tile (|d envelope / d column| <= 16 bits per pixel
+                  // everywhere): the amplitude then follows a ratio recurrence like the phasor; 0 = use ex2 per pixel
 };
 static_assert(sizeof(Rec) == kRecDoubles * 8, "record size");
 
@@ -324,7 +325,16 @@ __global__ void __launch_bounds__(kThreads, 2)
       rec.en[4] = e[4];
       rec.en[5] = e[5];
       rec.e2 = (float)e[3];
-      rec.pad = 0u;
+      rec.rho = 0.f;
+      {
+        // smooth-envelope test: the per-pixel step of the exponent along a row, E1 + E4 u + E3 (2 v + 1), at
+        // the four corners of the tile (it is affine in u, v); NaN / inf coefficients fail the test
+        const double s00 = rec.en[1] + rec.en[3];
+        const double s01 = s00 + rec.en[3] * (2.0 * (TC - 1));
+        const double su = rec.en[4] * (double)(TR - 1);
+        const double worst = fmax(fmax(fabs(s00), fabs(s01)), fmax(fabs(s00 + su), fabs(s01 + su)));
+        if (worst <= 16.0) rec.rho = (float)exp2(2.0 * rec.en[3]);
+      }
       rec.cspan = (uint32_t)(TC - 1) << 16;      // all columns unless the culling test below narrows it
       {
         double sd, cd;
@@ -435,6 +445,52 @@ __global__ void __launch_bounds__(kThreads, 2)
       // 4 sin/cos per 4 pixels -- 2 MUFU per pixel instead of 3 -- and the error of a seed is carried
       // for at most 3 multiplications (<= ~1e-6 absolute on a unit phasor).
       const float cr = q.cr, ci = q.ci;
+      const float rho = q.rho;
+      if (rho > 0.f) {
+        // SMOOTH envelope (warp-uniform: every thread works on the same beamlet): the whole complex term
+        // V_j = amp_j z_j follows the same kind of recurrence, V_{j+1} = V_j R_j, R_{j+1} = R_j C' with
+        // R_j = 2^(e_{j+1} - e_j) w_j and C' = 2^(2 e2) c.  Seeds every 4 pixels: amp_j, the amplitude ratio
+        // (2 ex2) and z_j, w_j (4 sin / cos): 1.5 MUFU and ~12 issue slots per pixel instead of 2 and ~14.5.
+        // |exponent step| <= 16 bits per pixel keeps every ratio far inside the fp32 range; steep (sub-pixel)
+        // envelopes take the per-pixel path below.
+        const float Cr = rho * cr, Ci = rho * ci;
+#pragma unroll
+        for (int s4 = 0; s4 < L; s4 += 4) {
+          const uint32_t tj = t0 + (uint32_t)s4 * d0 + (uint32_t)(s4 * (s4 - 1) / 2) * dd;
+          const uint32_t dj = d0 + (uint32_t)s4 * dd + 0x100u;
+          const float fz = __uint_as_float((tj >> 9) | 0x3f800000u);       // 1 + frac(turns)
+          const float az = fmaf(fz, 6.28318530717958648f, -9.42477796076937972f);
+          const float fw = __uint_as_float((dj >> 9) | 0x3f800000u);
+          const float aw = fmaf(fw, 6.28318530717958648f, -9.42477796076937972f);
+          const float dj_ = (float)s4 - jp;
+          const float ej = fmaf(dj_, fmaf(dj_, e2, e1p), ep);            // exponent at the group's first pixel
+          const float gj = fmaf(e2, fmaf(2.0f, dj_, 1.0f), e1p);          // exponent step to the next pixel
+          float amp, rat;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(amp) : "f"(ej));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(rat) : "f"(gj));
+          float vr = -amp * __cosf(az), vi = -amp * __sinf(az);          // V = amp exp(i 2 pi frac)
+          float rr = -rat * __cosf(aw), ri = -rat * __sinf(aw);          // R = ratio exp(i step)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int j = s4 + k;
+            pr[j] += vr;
+            pi[j] += vi;
+            if (k < 3) {
+              const float nvr = fmaf(vr, rr, -(vi * ri));
+              const float nvi = fmaf(vr, ri, vi * rr);
+              vr = nvr;
+              vi = nvi;
+            }
+            if (k < 2) {
+              const float nrr = fmaf(rr, Cr, -(ri * Ci));
+              const float nri = fmaf(rr, Ci, ri * Cr);
+              rr = nrr;
+              ri = nri;
+            }
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int s4 = 0; s4 < L; s4 += 4) {
         const uint32_t tj = t0 + (uint32_t)s4 * d0 + (uint32_t)(s4 * (s4 - 1) / 2) * dd;
