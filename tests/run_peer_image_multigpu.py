@@ -69,6 +69,24 @@ def main():
                               f"max|diff|/max = {err:.2e}", flush=True)
             finally:
                 pi.close()
+    # complex64 images and the explicit tensor method: the f64 -> c64 conversion kernel and the c64 branch of the
+    # split-reduce kernel issue the peer stores there
+    g, model = M.aperture_diffraction_case(3000, (512, 768))
+    gd = replace(g, **{f.name: torch.as_tensor(getattr(g, f.name), device=dev) for f in fields(g)})
+    grid = model[-1]
+    poly, n, _ = beamlet_polynomials(gd, model)
+    for method in ("tensor", "sfu"):
+        single = _field_sum_grid(poly, n, grid, dev, cull_bits=0, method=method, out_dtype=torch.complex64)
+        pi = D.PeerImage(grid.shape[0], grid.shape[1], dtype=torch.complex64)
+        try:
+            out = D.make_gaussian_image_sharded(gd, model, cull_bits=0, method=method, peer_image=pi)
+            torch.cuda.synchronize()
+            err = float((out - single).abs().max() / single.abs().max())
+            ok &= out.dtype == torch.complex64 and err < 1e-6
+            if rank == 0:
+                print(f"c64      {method:6s} fused_peer   world={world} max|diff|/max = {err:.2e}", flush=True)
+        finally:
+            pi.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
