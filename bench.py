@@ -36,7 +36,7 @@ C2_NB, C2_SHAPE = 10_000, (1024, 1024)
 NCU_TRAFFIC = {
     "gemm_x3_kernel_tf32": (491.98e6 + 4.20e6, "profiles/r1_gemm_tf32x3_kernel_v1.md"),
     "gemm_x3_kernel_f16": (246.86e6 + 4.22e6, "profiles/r1_gemm_f16x3_kernel_v1.md"),
-    "field_grid_kernel": (1.00e6 + 81.65e6, "profiles/r1_field_grid_kernel_v3.md"),
+    "field_grid_kernel": (1.10e6 + 82.33e6, "profiles/r1_field_grid_kernel_v4.md"),
     "trace_kernel_1e7": (560.0e6 + 2499.5e6, "profiles/r1_trace_kernel_1e7.md"),
     "stem4d_backproject": (17.18e9 + 3.6e6, "profiles/r1_stem4d_dda1x_kernel.md"),
     "trace_kernel_c4": (560.06e6 + 2499.7e6, "profiles/r1_trace_kernel_c4_v4.md"),
@@ -347,8 +347,8 @@ def run_ours(args):
                                   "amplitude recurrence re-seeded every 4 pixels) and 2 on steep ones",
                     "executed_mufu_per_eval": MUFU_PER_EVAL_EXEC,
                     "frac_executed_mufu": mufu_exec / peak_mufu,
-                    "co_limiters": "issue-slot bound: ~12 issue slots per evaluation (ncu of the previous 2-MUFU "
-                                   "version: issue 75 %, XU 78 %, profiles/r1_field_grid_kernel_v3.md)"}
+                    "co_limiters": "issue-slot bound: issue 76 % active, XU pipe 62 %, FMA pipe 53 %, 16 thread-"
+                                   "instructions per evaluation incl. staging (ncu, profiles/r1_field_grid_kernel_v4.md)"}
 
     # separable path: the tcgen05 GEMM alone, same shape as this rank's share of C2
     # (M = rows, N = 2W, K = 2 nb), operands random split fp32 (fp16 x 3 = what the path runs; tf32 x 3 beside it)
