@@ -213,6 +213,8 @@ struct FieldSmem {
   alignas(8) uint64_t full[2];
   int warp_cnt[kChunk / 32];
   int n_active;
+  int cand[kChunk + kThreads];   // gather mode: beamlets (relative to the split) whose bounding box meets the tile
+  int gcnt[kThreads / 32];
 };
 
 // WCULL: culling is enabled -> lane = row / warp = strip mapping with the per-warp column skip; the
@@ -265,18 +267,24 @@ __global__ void __launch_bounds__(kThreads, 2)
     tg_mbar_expect_tx(&sm.full[c & 1], bytes);
     tg_bulk_g2s(sm.raw[c & 1], table + b * 12, bytes, &sm.full[c & 1]);
   };
-  if (tid == 0 && nchunks > 0) issue(0);
-
-  // per-thread strip constants (exact small integers in fp64)
-  const double ud = (double)u, vd = (double)v0;
-  const float uf = (float)u, vf = (float)v0;
-
-
   double thr_bits = INFINITY;  // cull when min envelope exponent g over tile > thr_bits
   if (g.cull_bits > 0 && gref_key) {
     const unsigned long long key = *gref_key;
     if (key != ~0ULL) thr_bits = dec_ordered(key) + (double)g.cull_bits;
   }
+  // GATHER mode (culling with bounding boxes): instead of streaming the whole table through shared memory
+  // and evaluating the few survivors of every 128-beamlet chunk (one barrier-bound evaluation phase per
+  // chunk: ncu showed 2.4 barrier stalls per issue and the XU pipe at 41 % on BASELINE C3), all 256 threads
+  // scan the 8-byte bounding boxes, survivors are appended IN ORDER to a candidate list, and an evaluation
+  // phase starts only when 128 candidates are waiting (or the input is exhausted); their table rows are read
+  // straight from L2.  Same beamlet order per pixel, so the sums keep their summation order.
+  const bool gather = WCULL && bbox != nullptr && thr_bits < INFINITY;
+  if (tid == 0 && nchunks > 0 && !gather) issue(0);
+
+  // per-thread strip constants (exact small integers in fp64)
+  const double ud = (double)u, vd = (double)v0;
+  const float uf = (float)u, vf = (float)v0;
+
 
   float pr[L], pi[L];
 #pragma unroll
@@ -284,24 +292,59 @@ __global__ void __launch_bounds__(kThreads, 2)
   unsigned long long my_active = 0;
   int pending = 0;                   // terms in the fp32 partials since the last flush (<= 1.5 kChunk)
 
-  for (int c = 0; c < nchunks; ++c) {
-    if (tid == 0 && c + 1 < nchunks) issue(c + 1);
-    tg_mbar_wait(&sm.full[c & 1], (uint32_t)((c >> 1) & 1));
+  int ncand = 0;                     // gather mode: candidates waiting in sm.cand
+  long long bpos = b_begin;          // gather mode: next beamlet to scan
+  for (int c = 0;; ++c) {
+    int cnt;
+    bool near;
+    const double *a = nullptr;
+    if (!gather) {
+      if (c >= nchunks) break;
+      if (tid == 0 && c + 1 < nchunks) issue(c + 1);
+      tg_mbar_wait(&sm.full[c & 1], (uint32_t)((c >> 1) & 1));
+      const long long b = b_begin + (long long)c * kChunk;
+      cnt = (int)((b_end - b) < kChunk ? (b_end - b) : kChunk);
+      near = tid < cnt;
+      if (near && bbox && thr_bits < INFINITY) {
+        // cheap reject: the beamlet's detector-space bounding box of {envelope >= threshold} (bbox_kernel)
+        const short4 bb = __ldg(bbox + b + tid);        // col_lo, col_hi, row_lo, row_hi (detector pixels)
+        near = !(bb.y < c0 || bb.x > c0 + TC - 1 || bb.w < r0 || bb.z > r0 + TR - 1);
+      }
+      a = sm.raw[c & 1] + tid * 12;
+    } else {
+      while (ncand < kChunk && bpos < b_end) {           // block-uniform conditions
+        const long long i = bpos + tid;
+        bool hit = false;
+        if (i < b_end) {
+          const short4 bb = __ldg(bbox + i);
+          hit = !(bb.y < c0 || bb.x > c0 + TC - 1 || bb.w < r0 || bb.z > r0 + TR - 1);
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        const int warp = tid >> 5, lane = tid & 31;
+        if (lane == 0) sm.gcnt[warp] = __popc(ballot);
+        __syncthreads();
+        int base = ncand, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) {
+          const int n_w = sm.gcnt[w];
+          base += (w < warp) ? n_w : 0;
+          tot += n_w;
+        }
+        if (hit) sm.cand[base + __popc(ballot & ((1u << lane) - 1u))] = (int)(i - b_begin);
+        __syncthreads();                                 // candidates visible, gcnt reusable
+        ncand += tot;
+        bpos += kThreads;
+      }
+      if (ncand == 0) break;
+      cnt = ncand < kChunk ? ncand : kChunk;
+      near = tid < cnt;
+      if (near) a = table + (b_begin + (long long)sm.cand[tid]) * 12;
+    }
 
     // ---- stage: one thread per beamlet re-centres on the tile origin, culls, compacts
-    const long long b = b_begin + (long long)c * kChunk;
-    const int cnt = (int)((b_end - b) < kChunk ? (b_end - b) : kChunk);
     bool keep = false;
     Rec rec;
-    bool near = tid < cnt;
-    if (near && bbox && thr_bits < INFINITY) {
-      // cheap reject: the beamlet's detector-space bounding box of {envelope >= threshold} (bbox_kernel)
-      // misses this tile -- skips the fp64 re-centring for the ~99 % of beamlets that are far away
-      const short4 bb = __ldg(bbox + b + tid);          // col_lo, col_hi, row_lo, row_hi (detector pixels)
-      near = !(bb.y < c0 || bb.x > c0 + TC - 1 || bb.w < r0 || bb.z > r0 + TR - 1);
-    }
     if (near) {
-      const double *a = sm.raw[c & 1] + tid * 12;
       const double cc = (double)c0, rr = (double)r0;
       // phase, turns
       double t0 = a[0] + cc * (a[1] + a[3] * cc + a[4] * rr) + rr * (a[2] + a[5] * rr);
@@ -545,6 +588,14 @@ __global__ void __launch_bounds__(kThreads, 2)
       pending = 0;
     }
     __syncthreads();  // records and raw[c&1] are free for the next stage / TMA
+    if (gather) {       // drop the processed candidates: the rest (< kThreads) moves to the front of the list
+      const int rest = ncand - cnt;
+      const int mv = tid < rest ? sm.cand[cnt + tid] : 0;
+      __syncthreads();
+      if (tid < rest) sm.cand[tid] = mv;
+      __syncthreads();
+      ncand = rest;
+    }
   }
   if (pending) {
 #pragma unroll

@@ -339,12 +339,12 @@ __device__ __forceinline__ float tf32_rna(float x) {
 // quadratic of the SFU kernel (field.cu).  Stores are coalesced: for a fixed row, consecutive
 // threads (beamlets) write consecutive k' pairs.
 // AUTO hands a separable problem to the culled SFU kernel when its estimated executed evaluations are
-// below this fraction of nb*H*W.  Measured on B200 with the fp16 x 3 GEMM (2.1e-14 s per nominal
-// evaluation) on the C3 geometry (~11 px envelopes): the tensor path wins at 1e5 beamlets on 2048^2
-// (8.6 vs 9.3 ms, estimate between 2 and 3 %), at 2e4 and 4e3 beamlets on 2048^2 and at 4e3 on 1024^2
-// (estimate 3-4.5 %), so the culled SFU sum only takes over below 2 % (tools/exp_auto.py; the
-// environment variable TG_SFU_WINS_BELOW overrides the constant).
-constexpr double kSfuWinsBelow = 0.02;
+// below this fraction of nb*H*W.  Measured on B200 (tools/exp_auto.py, threshold sweeps through the
+// environment variable TG_SFU_WINS_BELOW) on the C3 geometry (~11 px envelopes) with the fp16 x 3 GEMM
+// (2.1e-14 s per nominal evaluation) and the gather-mode culled SFU kernel: 1e5 beamlets on 2048^2 (estimate
+// between 2 and 3 %): SFU 6.1 ms vs GEMM 8.7 ms; 2e4 beamlets: 1.34 vs 1.79 ms; 4e3 beamlets on 1024^2
+// (estimate 3-4.5 %): about equal.  Break-even estimate ~3.6 %.
+constexpr double kSfuWinsBelow = 0.03;
 constexpr int FS = 32;
 constexpr long long kBatch = 16384;  // beamlets per GEMM pass
 constexpr double kMagicF = 1572864.0;  // 1.5 * 2^20
