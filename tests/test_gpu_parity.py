@@ -450,6 +450,33 @@ def test_c3_culling_consistency(torch_cuda):
     assert rel_l2(to_np(cull), to_np(dense)) < 1e-6
 
 
+@pytest.mark.parametrize("nb", [1, 127, 129, 255, 257, 1000])
+def test_culled_gather_mode_ragged_counts(torch_cuda, nb):
+    """Gather mode of the culled SFU kernel (candidate list filled 256 bounding boxes at a time, evaluation
+    phases of 128): beamlet counts around the scan / phase sizes, narrow beamlets that miss most tiles, a row
+    shard, and a detector no beamlet reaches -- always the dense sum."""
+    from temgymcore_b200.components import Detector
+    from temgymcore_b200.gaussian import _field_sum_grid, beamlet_polynomials
+    g, model = M.biprism_case(nb, (320, 416), fov=3 * 1024 * 55e-6 / 2)
+    grid = model[-1]
+    poly, n, dev = beamlet_polynomials(g, model)
+    dense = _field_sum_grid(poly, n, grid, dev, cull_bits=0, method="sfu")
+    cull, ev = _field_sum_grid(poly, n, grid, dev, cull_bits=40, method="sfu", count_evals=True)
+    assert ev <= n * 320 * 416
+    assert rel_l2(to_np(cull), to_np(dense)) < 1e-6
+    rows = _field_sum_grid(poly, n, grid, dev, cull_bits=40, method="sfu", row0=96, nrows=130)
+    np.testing.assert_array_equal(to_np(rows), to_np(cull)[96:226])
+    # the same beamlets seen by a detector far off to the side: every bounding box misses every tile
+    det = grid
+    far = Detector(z=det.z, pixel_size=det.pixel_size, shape=det.shape, centre=(10 * 320 * det.pixel_size[0], 0.0))
+    model_far = list(model[:-1]) + [far]
+    poly_f, n_f, _ = beamlet_polynomials(g, model_far)
+    dense_f = _field_sum_grid(poly_f, n_f, far, dev, cull_bits=0, method="sfu")
+    cull_f = _field_sum_grid(poly_f, n_f, far, dev, cull_bits=40, method="sfu")
+    scale = float(dense.abs().max())
+    assert float((cull_f - dense_f).abs().max()) <= 1e-9 * scale
+
+
 # ------------------------------------------------------------------------------ K4 (tensor cores)
 def _tf32_split(torch, x):
     """x = hi + lo with hi = cvt.rna.tf32(x) (round to nearest, ties away), like the factor kernels."""
