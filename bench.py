@@ -42,8 +42,9 @@ NCU_TRAFFIC = {
     "trace_kernel_c4": (560.06e6 + 2499.7e6, "profiles/r1_trace_kernel_c4_v4.md"),
 }
 MUFU_PER_EVAL = 3          # ALGORITHMIC count of SURVEY.md section 8d (sin, cos, ex2 per beamlet*pixel): roofline basis
-MUFU_PER_EVAL_EXEC = 1.5   # executed on smooth envelopes (C2): per 4 pixels 2 ex2 + sin/cos seeds of V and R (field.cu);
-                           # steep (sub-pixel) envelopes execute 2 (1 ex2 per pixel + 4 sin/cos per 4 pixels)
+MUFU_PER_EVAL_EXEC = 15 / 16   # executed on smooth envelopes (C2): per 16-pixel strip one seed of the ratio R (ex2, sin,
+                               # cos) and four seeds of V (ex2, sin, cos) (field.cu); steep (sub-pixel) envelopes
+                               # execute 2 (1 ex2 per pixel + 4 sin/cos per 4 pixels)
 MUFU_PER_CLK_SM = 16
 RAY_BYTES_ABCD = 312       # 56 in + 56 out + 200 ABCD, fp64
 
@@ -343,8 +344,9 @@ def run_ours(args):
                     "peak_basis": f"{sms} SMs x 16 MUFU/clk x {pk['sm_max_mhz']:.0f} MHz (clocks.max.sm, "
                                   f"{pk['source']}); achieved = SURVEY 8d's algorithmic 3 MUFU (sin, cos, ex2) per "
                                   "beamlet*pixel, so frac > 1 means the kernel beats the roofline of the naive "
-                                  "formulation: it executes 1.5 MUFU per evaluation on smooth envelopes (complex "
-                                  "amplitude recurrence re-seeded every 4 pixels) and 2 on steep ones",
+                                  "formulation: it executes 0.94 MUFU per evaluation on smooth envelopes (complex "
+                                  "amplitude recurrence, V re-seeded every 4 pixels, ratio once per strip) and 2 on "
+                                  "steep ones",
                     "executed_mufu_per_eval": MUFU_PER_EVAL_EXEC,
                     "frac_executed_mufu": mufu_exec / peak_mufu,
                     "co_limiters": "issue-slot bound: issue 76 % active, XU pipe 62 %, FMA pipe 53 %, 16 thread-"

@@ -32,7 +32,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kChunk = 128;          // beamlets per staged chunk
-constexpr int kRecDoubles = 16;      // tile-local record: 6 phase + 6 envelope + vertex(2) + {dd,e2} + {cr,ci}
+constexpr int kRecDoubles = 18;      // tile-local record: 6 phase + 6 envelope + vertex(2) + {dd,e2} + {cr,ci}
 constexpr double kMagic = 1572864.0; // 1.5 * 2^20: ulp = 2^-32 -> low mantissa word = frac * 2^32
 constexpr double kInv2Pi = 0.15915494309189533577;
 constexpr double kLog2e = 1.4426950408889634074;
@@ -200,6 +200,8 @@ struct __align__(16) Rec {
   uint32_t cspan; // tile columns that can hold a contribution above the culling threshold: lo | hi << 16
   float rho;      // 2^(2 e2) when the envelope is SMOOTH on this tile (|d envelope / d column| <= 16 bits per pixel
                   // everywhere): the amplitude then follows a ratio recurrence like the phasor; 0 = use ex2 per pixel
+  float c4r, c4i; // (rho c)^4: the ratio R of the smooth path advances by it from one 4-pixel group to the next
+  float pad2[2];
 };
 static_assert(sizeof(Rec) == kRecDoubles * 8, "record size");
 
@@ -376,7 +378,16 @@ __global__ void __launch_bounds__(kThreads, 2)
         const double s01 = s00 + rec.en[3] * (2.0 * (TC - 1));
         const double su = rec.en[4] * (double)(TR - 1);
         const double worst = fmax(fmax(fabs(s00), fabs(s01)), fmax(fabs(s00 + su), fabs(s01 + su)));
-        if (worst <= 16.0) rec.rho = (float)exp2(2.0 * rec.en[3]);
+        rec.c4r = rec.c4i = 0.f;
+        rec.pad2[0] = rec.pad2[1] = 0.f;
+        if (worst <= 16.0) {
+          rec.rho = (float)exp2(2.0 * rec.en[3]);
+          const double d4 = 4.0 * dd, r4 = exp2(8.0 * rec.en[3]);
+          double s4, c4;
+          sincospi(2.0 * (d4 - rint(d4)), &s4, &c4);
+          rec.c4r = (float)(r4 * c4);
+          rec.c4i = (float)(r4 * s4);
+        }
       }
       rec.cspan = (uint32_t)(TC - 1) << 16;      // all columns unless the culling test below narrows it
       {
@@ -497,22 +508,38 @@ __global__ void __launch_bounds__(kThreads, 2)
         // |exponent step| <= 16 bits per pixel keeps every ratio far inside the fp32 range; steep (sub-pixel)
         // envelopes take the per-pixel path below.
         const float Cr = rho * cr, Ci = rho * ci;
+        const float C4r = q.c4r, C4i = q.c4i;
+        // the ratio R is seeded once per strip (ex2 + sin / cos) and advanced from group to group by C'^4 (fp64-
+        // rounded in the staging step); V is re-seeded exactly for every group: 3 MUFU per 4 pixels after the first
+        float gr, gi;
+        {
+          const uint32_t dj = d0 + 0x100u;
+          const float fw = __uint_as_float((dj >> 9) | 0x3f800000u);
+          const float aw = fmaf(fw, 6.28318530717958648f, -9.42477796076937972f);
+          const float dj_ = -jp;
+          const float gj = fmaf(e2, fmaf(2.0f, dj_, 1.0f), e1p);          // exponent step from pixel 0 to pixel 1
+          float rat;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(rat) : "f"(gj));
+          gr = -rat * __cosf(aw);
+          gi = -rat * __sinf(aw);
+        }
 #pragma unroll
         for (int s4 = 0; s4 < L; s4 += 4) {
           const uint32_t tj = t0 + (uint32_t)s4 * d0 + (uint32_t)(s4 * (s4 - 1) / 2) * dd;
-          const uint32_t dj = d0 + (uint32_t)s4 * dd + 0x100u;
           const float fz = __uint_as_float((tj >> 9) | 0x3f800000u);       // 1 + frac(turns)
           const float az = fmaf(fz, 6.28318530717958648f, -9.42477796076937972f);
-          const float fw = __uint_as_float((dj >> 9) | 0x3f800000u);
-          const float aw = fmaf(fw, 6.28318530717958648f, -9.42477796076937972f);
           const float dj_ = (float)s4 - jp;
           const float ej = fmaf(dj_, fmaf(dj_, e2, e1p), ep);            // exponent at the group's first pixel
-          const float gj = fmaf(e2, fmaf(2.0f, dj_, 1.0f), e1p);          // exponent step to the next pixel
-          float amp, rat;
+          float amp;
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(amp) : "f"(ej));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(rat) : "f"(gj));
           float vr = -amp * __cosf(az), vi = -amp * __sinf(az);          // V = amp exp(i 2 pi frac)
-          float rr = -rat * __cosf(aw), ri = -rat * __sinf(aw);          // R = ratio exp(i step)
+          float rr = gr, ri = gi;                                        // R of the group's first pixel
+          if (s4 + 4 < L) {                                              // R of the next group
+            const float ngr = fmaf(gr, C4r, -(gi * C4i));
+            const float ngi = fmaf(gr, C4i, gi * C4r);
+            gr = ngr;
+            gi = ngi;
+          }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int j = s4 + k;
