@@ -88,3 +88,65 @@ def test_sharded_image_plumbing_gloo(H, W):
         ok_table, ok_img, shape = ret[r]
         assert ok_table, "broadcast did not deliver rank 0's table"
         assert ok_img and shape == (H, W)
+
+
+class _SharedMemPeerImage:
+    """CPU stand-in for distributed.PeerImage with the same interface: one full image per rank in shared host
+    memory (the peers' images 'mapped' into every process), field_sum writes this rank's row block into ALL of
+    them, barrier is a gloo barrier.  The compute is the CPU oracle."""
+
+    def __init__(self, images, rank, world, rows_of):
+        self.images, self.rank, self.world = images, rank, world
+        self.H, self.W = images[0].shape
+        self.image = images[rank]
+        self.rows_of = rows_of
+        self.calls = []
+
+    def field_sum(self, poly, nb, grid, *, cull_bits=None, method="auto"):
+        r0, nr = D.row_shards(self.H, self.world)[self.rank]
+        block = self.rows_of(r0, nr)
+        for img in self.images:                       # the kernels' peer stores
+            img[r0:r0 + nr] = block
+        self.calls.append((r0, nr, method))
+        return r0, nr
+
+    def barrier(self):
+        dist.barrier()
+
+
+def _peer_worker(rank, world, port, images, nb, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import temgym_oracle as O
+        from tests import models as M
+        H, W = images[0].shape
+        g, model = M.aperture_diffraction_case(nb, (H, W))
+        ref = torch.from_numpy(O.make_gaussian_image(g, model))
+
+        def table_fn():                               # every rank builds the table itself: nothing is broadcast
+            return torch.full((nb, 12), float(rank), dtype=torch.float64), nb, "cpu"
+
+        pi = _SharedMemPeerImage(images, rank, world, lambda r0, nr: ref[r0:r0 + nr])
+        out = D.make_gaussian_image_sharded(g, model, method="sfu", table_fn=table_fn, peer_image=pi)
+        dist.barrier()
+        ret[rank] = (bool(torch.equal(out, ref)), out.data_ptr() == images[rank].data_ptr(), pi.calls)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("H,W", [(96, 40), (70, 33)])
+def test_fused_peer_image_plumbing_gloo(H, W):
+    """make_gaussian_image_sharded(peer_image=...): no broadcast, every rank's row block lands in every rank's
+    image, the barrier closes the step and each rank returns its own (complete) image."""
+    world, nb = 2, 24
+    images = [torch.zeros((H, W), dtype=torch.complex128).share_memory_() for _ in range(world)]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_peer_worker, args=(world, port, images, nb, ret), nprocs=world, join=True)
+    shards = D.row_shards(H, world)
+    for r in range(world):
+        ok_img, own, calls = ret[r]
+        assert ok_img and own
+        assert calls == [(shards[r][0], shards[r][1], "sfu")]
