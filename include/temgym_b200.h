@@ -279,6 +279,15 @@ int tg_gemm_f16x3(int M, int N, int K, const void *A_hi, const void *A_lo, const
                   const void *B_lo, long long ldk, double *D, long long ldd, int accumulate,
                   void *stream);
 
+/* The GEMM is one persistent kernel (one CTA per SM): whole 128 x 128 tiles per CTA while they fill waves of
+ * `sms` CTAs, and a stream-K split of the remaining tiles (or of ALL tiles when the problem has fewer tiles
+ * than SMs, e.g. the row shard of one rank of a multi-GPU field sum) so that every SM gets the same amount of
+ * K.  This host-only call returns that decomposition for a shape (no device needed; used by the CPU tests):
+ * units[6 i ..] = {cta, tile, chunk_begin, chunk_end, slot, nparts} (chunks of 128 k-elements),
+ * sched_out[10] = {tiles_n, tiles, k_blocks, chunks, ctas, streamk_tiles, head_chunks, tail_chunks,
+ * helper_chunks, max_parts}.  Returns the number of units (only max_units are written). */
+int tg_gemm_schedule(int M, int N, int K, int f16, int sms, int32_t *units, int max_units, int32_t *sched_out);
+
 /* ---- host-buffer field sum (make_gaussian_image end to end, gaussian.py:225-273) -- */
 /* All pointers HOST.  rays[7] are the central rays (length nb each), waist_xy /
  * radii_xy (nb,2), wavelength / theta / amplitude (nb,).  Traces the rays through
@@ -324,10 +333,24 @@ int tg_peer_free(void *dptr);
 int tg_field_sum_peers(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                        int nrows, void *const images[], int npeers, int self, int out_is_c128,
                        int cull_bits, int method, void *stream);
+/* The whole of make_gaussian_image (gaussian.py:225-273: ray kernel + ABCD, coefficients, field sum) for this
+ * rank's rows, with the peer stores of tg_field_sum_peers: the per-step call of a row-sharded multi-GPU job,
+ * capturable into a CUDA graph (every rank builds the same table from the same inputs: no broadcast). */
+int tg_make_gaussian_image_peers(const tg_model *model_host, int64_t nb, const double *const rays[7],
+                                 const double *amplitude, const double *waist_xy, const double *radii_xy,
+                                 const double *wavelength, const double *theta, const double px2m[6], int H,
+                                 int W, int row0, int nrows, void *const images[], int npeers, int self,
+                                 int out_is_c128, int cull_bits, int method, void *stream);
 /* flags[p]: base of rank p's flag array (npeers uint64, zero-initialised) as seen from this process.
  * Signals `epoch` (strictly increasing per use) to every peer and waits until every peer has signalled it;
- * traps after ~10 s instead of hanging. */
+ * traps after TG_PEER_BARRIER_TIMEOUT_S seconds (environment, default 10) instead of hanging. */
 int tg_peer_barrier(void *const flags[], int npeers, int self, uint64_t epoch, void *stream);
+/* The same barrier with its epoch kept on the device: state = 2 uint64 in LOCAL device memory, zero-initialised,
+ * {epoch counter, status}.  Every launch increments the counter and uses the new value, so the launch can be
+ * captured into a CUDA graph and replayed (all ranks must run the same number of barriers).  A timeout
+ * (timeout_s seconds; <= 0: TG_PEER_BARRIER_TIMEOUT_S, default 10) does not trap: status becomes 1 + the rank
+ * that did not arrive and the kernel returns, leaving the context usable. */
+int tg_peer_barrier_auto(void *const flags[], int npeers, int self, void *state, double timeout_s, void *stream);
 
 #ifdef __cplusplus
 }

@@ -766,7 +766,8 @@ extern "C" int tg_field_sum_grid(int64_t nb, const double *poly, const double px
 // beamlets are separable (the tensor-core path, enqueued by the same call, does the work instead).
 int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                       int nrows, void *out, int out_is_c128, int cull_bits, long long *n_evals_out,
-                      const unsigned long long *sep_guard, cudaStream_t stream, const TgPeers *peers) {
+                      const unsigned long long *sep_guard, cudaStream_t stream, const TgPeers *peers,
+                      const TgEmit *emit) {
   TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad shape");
   TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
   TG_REQUIRE(px2m && out, "null pointer");
@@ -774,41 +775,55 @@ int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n_evals_out) *n_evals_out = 0;
   if (nrows == 0) return TG_OK;
+  if (n_evals_out && tg_stream_is_capturing(st)) {
+    tg_set_error("counting executed evaluations reads a counter back and cannot be captured into a CUDA graph");
+    return TG_EUNSUPPORTED;
+  }
   const size_t npix = (size_t)nrows * W;
   const size_t elt = out_is_c128 ? 16 : 8;
   TgPeers no_peers;
   no_peers.n = 0;
   const TgPeers &pe = peers ? *peers : no_peers;
+  TG_REQUIRE(!(emit && pe.n > 0), "row-block emission and peer images are separate modes");
   if (nb == 0) {
     TG_CUDA(cudaMemsetAsync(out, 0, npix * elt, st));
     for (int p = 0; p < pe.n; ++p) TG_CUDA(cudaMemsetAsync(pe.ptr[p], 0, npix * elt, st));
+    if (emit) return tg_emit_block(emit, 0, st, out, 0, npix * elt);
     return TG_OK;
   }
   TG_REQUIRE(poly, "null poly");
 
   constexpr int L = 16, SPR = 8;
   using S = FieldSmem<L, SPR>;
+  int block_rows = nrows;
+  if (emit) {
+    TG_REQUIRE(emit->block_rows > 0 && emit->block_rows % S::TR == 0 && emit->host_out && emit->ev,
+               "bad emission block");
+    block_rows = emit->block_rows < nrows ? emit->block_rows : nrows;
+  }
   FieldGeom g;
-  g.H = H; g.W = W; g.row0 = row0; g.nrows = nrows;
+  g.H = H; g.W = W;
   g.tiles_x = (W + S::TC - 1) / S::TC;
-  g.tiles_y = (nrows + S::TR - 1) / S::TR;
   g.nb = nb;
   g.cull_bits = cull_bits;
-  const long long tiles = (long long)g.tiles_x * g.tiles_y;
   int dev = 0, sms = 148;
   TG_CUDA(cudaGetDevice(&dev));
   tg_tune_mempool(dev);
   TG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  g.nsplit = choose_split(tiles, nb, 2 * sms, cull_bits > 0, npix);
-  g.via_partial = (g.nsplit > 1 || pe.n > 0) ? 1 : 0;   // peer stores are issued by the reduce kernel (coalesced)
+  // the split count of a full block (the last, shorter block uses its own)
+  const size_t blk_pix = (size_t)block_rows * W;
+  const int nsplit_max = choose_split((long long)g.tiles_x * ((block_rows + S::TR - 1) / S::TR), nb, 2 * sms,
+                                      cull_bits > 0, blk_pix);
+  const bool via_partial_max = nsplit_max > 1 || pe.n > 0;
 
-  // workspace: table (nb*96 B) | gref key (8) | evals (8) | split partials | per-beamlet bounding boxes
+  // workspace: table (nb*96 B) | gref key (8) | evals (8) | split partials of one block | per-beamlet bounding boxes
   const size_t table_bytes = (size_t)nb * 96;
-  const size_t part_bytes = g.via_partial ? (size_t)g.nsplit * npix * 16 : 0;
+  const size_t part_bytes = via_partial_max ? (size_t)nsplit_max * blk_pix * 16 : 0;
   const bool use_bbox = cull_bits > 0 && H <= 32768 && W <= 32768;
   const size_t bbox_bytes = use_bbox ? (size_t)nb * sizeof(short4) : 0;
-  unsigned char *ws = nullptr;
-  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), table_bytes + 256 + part_bytes + bbox_bytes, st));
+  TgAsyncBuf wsb(st);
+  TG_CUDA(wsb.alloc(table_bytes + 256 + part_bytes + bbox_bytes));
+  unsigned char *ws = wsb.as<unsigned char>();
   short4 *bbox = use_bbox ? reinterpret_cast<short4 *>(ws + table_bytes + 256 + part_bytes) : nullptr;
   double *table = reinterpret_cast<double *>(ws);
   unsigned long long *gref = reinterpret_cast<unsigned long long *>(ws + table_bytes);
@@ -818,43 +833,52 @@ int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int 
   TG_CUDA(cudaMemsetAsync(evals, 0, 8, st));
 
   int rc = tg_launch_prep(nb, poly, px2m, H, W, table, cull_bits > 0 ? gref : nullptr, st);
-  if (rc == TG_OK && use_bbox) {
+  if (rc != TG_OK) return rc;
+  if (use_bbox) {
     bbox_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, table, H, W, gref, cull_bits, bbox);
     rc = tg_launch_check("bbox_kernel");
+    if (rc != TG_OK) return rc;
   }
-  if (rc == TG_OK) {
-    const size_t smem = sizeof(S);
-    auto kern = cull_bits > 0 ? field_grid_kernel<L, SPR, true> : field_grid_kernel<L, SPR, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      tg_set_error("cudaFuncSetAttribute(field_grid_kernel): %s", cudaGetErrorString(e));
-      rc = TG_ECUDA;
-    } else {
-      dim3 grid((unsigned)tiles, (unsigned)g.nsplit);
-      kern<<<grid, kThreads, smem, st>>>(
-          table, g, cull_bits > 0 ? gref : nullptr, bbox, out, out_is_c128, partial,
-          n_evals_out ? evals : nullptr, sep_guard);
-      rc = tg_launch_check("field_grid_kernel");
-      if (rc == TG_OK && g.via_partial) {
-        split_reduce_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(partial, g.nsplit, npix,
-                                                                           out, out_is_c128, sep_guard, pe);
-        rc = tg_launch_check("split_reduce_kernel");
-      }
+  const size_t smem = sizeof(S);
+  auto kern = cull_bits > 0 ? field_grid_kernel<L, SPR, true> : field_grid_kernel<L, SPR, false>;
+  TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int blk = 0;
+  for (int r = 0; r < nrows; r += block_rows, ++blk) {
+    const int nr = (nrows - r) < block_rows ? (nrows - r) : block_rows;
+    g.row0 = row0 + r;
+    g.nrows = nr;
+    g.tiles_y = (nr + S::TR - 1) / S::TR;
+    const long long tiles = (long long)g.tiles_x * g.tiles_y;
+    const size_t bpix = (size_t)nr * W;
+    g.nsplit = nr == block_rows ? nsplit_max : choose_split(tiles, nb, 2 * sms, cull_bits > 0, bpix);
+    if (g.nsplit > nsplit_max) g.nsplit = nsplit_max;          // the partial buffer is sized for nsplit_max
+    g.via_partial = (g.nsplit > 1 || pe.n > 0) ? 1 : 0;        // peer stores are issued by the reduce kernel (coalesced)
+    unsigned char *out_r = static_cast<unsigned char *>(out) + (size_t)r * W * elt;
+    dim3 grid((unsigned)tiles, (unsigned)g.nsplit);
+    kern<<<grid, kThreads, smem, st>>>(table, g, cull_bits > 0 ? gref : nullptr, bbox, out_r, out_is_c128, partial,
+                                       n_evals_out ? evals : nullptr, sep_guard);
+    rc = tg_launch_check("field_grid_kernel");
+    if (rc != TG_OK) return rc;
+    if (g.via_partial) {
+      TgPeers pr = pe;
+      for (int p = 0; p < pr.n; ++p) pr.ptr[p] = static_cast<unsigned char *>(pr.ptr[p]) + (size_t)r * W * elt;
+      split_reduce_kernel<<<(unsigned)((bpix + 255) / 256), 256, 0, st>>>(partial, g.nsplit, bpix, out_r,
+                                                                         out_is_c128, sep_guard, pr);
+      rc = tg_launch_check("split_reduce_kernel");
+      if (rc != TG_OK) return rc;
+    }
+    if (emit) {
+      rc = tg_emit_block(emit, blk, st, out_r, (size_t)r * W * elt, bpix * elt);
+      if (rc != TG_OK) return rc;
     }
   }
-  if (rc == TG_OK && n_evals_out) {
+  if (n_evals_out) {
     unsigned long long h = 0;
-    cudaError_t e = cudaMemcpyAsync(&h, evals, 8, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) {
-      tg_set_error("n_evals readback: %s", cudaGetErrorString(e));
-      rc = TG_ECUDA;
-    } else {
-      *n_evals_out = (long long)h;
-    }
+    TG_CUDA(cudaMemcpyAsync(&h, evals, 8, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaStreamSynchronize(st));
+    *n_evals_out = (long long)h;
   }
-  cudaFreeAsync(ws, st);
-  return rc;
+  return TG_OK;
 }
 
 extern "C" int tg_field_sum_points(int64_t nb, const double *poly, int64_t npts, const double *r_xy,

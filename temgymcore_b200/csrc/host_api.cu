@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <stdlib.h>
 #include "tg_common.cuh"
 
@@ -42,14 +43,14 @@ constexpr int64_t kChunkRays = 1 << 18;
 // Keep freed stream-ordered allocations cached in the device's default pool instead of
 // returning them to the driver at every synchronisation (the default threshold is 0).
 void tg_tune_mempool(int dev) {
-  static bool done[64] = {false};
-  if (dev < 0 || dev >= 64 || done[dev]) return;
+  static std::atomic<bool> done[64];     // zero-initialised; setting the attribute twice is harmless
+  if (dev < 0 || dev >= 64 || done[dev].load(std::memory_order_acquire)) return;
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     unsigned long long thr = ~0ULL;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
-  done[dev] = true;
+  done[dev].store(true, std::memory_order_release);
 }
 
 namespace {
@@ -209,6 +210,44 @@ extern "C" int tg_metres_to_pixels_host(int64_t n, const double *x, const double
 
 // Device-resident make_gaussian_image (gaussian.py:225-273) as ONE call: ray kernel with ABCD, one
 // kernel for Q_inv + wave numbers + coefficients, field sum (method dispatch), all enqueued on `stream`.
+int tg_make_gaussian_image_impl(const tg_model *model_host, int64_t nb, const double *const rays[7],
+                                const double *amplitude, const double *waist_xy, const double *radii_xy,
+                                const double *wavelength, const double *theta, const double px2m[6], int H,
+                                int W, int row0, int nrows, void *out, int out_is_c128, int cull_bits,
+                                int method, cudaStream_t s, const TgEmit *emit, const TgPeers *peers) {
+  TG_REQUIRE(model_host && rays && px2m && out, "null pointer");
+  TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad sizes");
+  TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
+  if (nrows == 0) return TG_OK;
+  if (nb == 0)
+    return tg_field_sum_impl(0, nullptr, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, method, s, peers,
+                             emit);
+  TG_REQUIRE(amplitude && waist_xy && radii_xy && wavelength && theta, "null pointer");
+  int dev = 0;
+  TG_CUDA(cudaGetDevice(&dev));
+  tg_tune_mempool(dev);
+  tg_ray_in in;
+  for (int f = 0; f < 7; ++f) {
+    in.ptr[f] = rays[f];
+    in.value[f] = 0.0;
+    if (!rays[f]) {
+      tg_set_error("tg_make_gaussian_image_f64: ray field %d is null", f);
+      return TG_EINVAL;
+    }
+  }
+  TgAsyncBuf scratch(s);  // abcd 25n | poly 12n
+  TG_CUDA(scratch.alloc((size_t)nb * 37 * 8));
+  double *dabcd = scratch.as<double>(), *dpoly = dabcd + 25 * nb;
+  double *no_out[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int rc = tg_trace_f64(model_host, nb, &in, no_out, dabcd, TG_JAC_ABCD5, s);
+  if (rc == TG_OK)   // Q_inv, k, p0 and the coefficients in one kernel
+    rc = tg_coeffs_from_beam(nb, amplitude, rays[5], waist_xy, radii_xy, wavelength, theta, dabcd, rays[0], rays[1],
+                             rays[2], rays[3], dpoly, s);
+  if (rc == TG_OK)
+    rc = tg_field_sum_impl(nb, dpoly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, method, s, peers, emit);
+  return rc;
+}
+
 extern "C" int tg_make_gaussian_image_f64(const tg_model *model_host, int64_t nb,
                                           const double *const rays[7], const double *amplitude,
                                           const double *waist_xy, const double *radii_xy,
@@ -216,40 +255,43 @@ extern "C" int tg_make_gaussian_image_f64(const tg_model *model_host, int64_t nb
                                           const double px2m[6], int H, int W, int row0, int nrows,
                                           void *out, int out_is_c128, int cull_bits, int method,
                                           void *stream) {
-  TG_REQUIRE(model_host && rays && px2m && out, "null pointer");
-  TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad sizes");
-  TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
-  if (nrows == 0) return TG_OK;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (nb == 0) return tg_field_sum(0, nullptr, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, method, s);
-  TG_REQUIRE(amplitude && waist_xy && radii_xy && wavelength && theta, "null pointer");
-  int dev = 0;
-  TG_CUDA(cudaGetDevice(&dev));
-  tg_tune_mempool(dev);
-  double *scratch = nullptr;  // abcd 25n | poly 12n
-  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), (size_t)nb * 37 * 8, s));
-  double *dabcd = scratch, *dpoly = dabcd + 25 * nb;
-  tg_ray_in in;
-  for (int f = 0; f < 7; ++f) {
-    in.ptr[f] = rays[f];
-    in.value[f] = 0.0;
-    if (!rays[f]) {
-      cudaFreeAsync(scratch, s);
-      tg_set_error("tg_make_gaussian_image_f64: ray field %d is null", f);
-      return TG_EINVAL;
-    }
-  }
-  double *no_out[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  int rc = tg_trace_f64(model_host, nb, &in, no_out, dabcd, TG_JAC_ABCD5, s);
-  if (rc == TG_OK)   // Q_inv, k, p0 and the coefficients in one kernel
-    rc = tg_coeffs_from_beam(nb, amplitude, rays[5], waist_xy, radii_xy, wavelength, theta, dabcd, rays[0], rays[1],
-                             rays[2], rays[3], dpoly, s);
-  if (rc == TG_OK)
-    rc = tg_field_sum(nb, dpoly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, method, s);
-  cudaFreeAsync(scratch, s);
-  return rc;
+  return tg_make_gaussian_image_impl(model_host, nb, rays, amplitude, waist_xy, radii_xy, wavelength, theta, px2m, H,
+                                     W, row0, nrows, out, out_is_c128, cull_bits, method,
+                                     static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
 
+namespace {
+// Streams and events of the host-buffer pipeline, created once per host thread and device (creating and
+// destroying two streams per call cost more than the H2D copies they carried).
+constexpr int kMaxEmitBlocks = 64;
+struct HostPipe {
+  cudaStream_t compute = nullptr, copy = nullptr;
+  cudaEvent_t ev[kMaxEmitBlocks] = {};
+  bool ok = false;
+};
+HostPipe *host_pipe(int dev) {
+  static thread_local HostPipe pipes[16];
+  if (dev < 0 || dev >= 16) return nullptr;
+  HostPipe &p = pipes[dev];
+  if (!p.ok) {
+    if (cudaStreamCreateWithFlags(&p.compute, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&p.copy, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (auto &e : p.ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    p.ok = true;
+  }
+  return &p;
+}
+int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+}  // namespace
+
+// Host-buffer make_gaussian_image.  Pipeline: (1) H2D of the beamlet parameters -- ONE copy when the twelve
+// arrays lie back to back in host memory (pack them that way: temgymcore_b200.gaussian.pack_beamlets_pinned),
+// otherwise one per contiguous run; (2) ray kernel, coefficient kernel, verdict; (3) the field sum in blocks of
+// detector rows, the D2H of every finished block on a second stream while the next block is being computed.
 extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t nb,
                                            const double *const rays[7], const double *amplitude,
                                            const double *waist_xy, const double *radii_xy,
@@ -267,70 +309,78 @@ extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t n
     tg_set_error("cudaSetDevice(%d) failed", device);
     return TG_ECUDA;
   }
-  Streams st;
-  int rc = st.init(1);
-  if (rc != TG_OK) return rc;
-  cudaStream_t s = st.s[0];
+  HostPipe *pipe = host_pipe(device);
+  if (!pipe) {
+    tg_set_error("could not create the streams of the host pipeline: %s", cudaGetErrorString(cudaGetLastError()));
+    return TG_ECUDA;
+  }
+  cudaStream_t s = pipe->compute;
   const size_t npix = (size_t)nrows * W, elt = out_is_c128 ? 16 : 8;
   // device layout (doubles): rays 7n | amp n | waist 2n | radii 2n | wl n | theta n | field
   const size_t nd = (size_t)nb * 14;
-  unsigned char *d = nullptr;
-  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d), ((nd * 8 + 255) / 256) * 256 + npix * elt, s));
-  double *p = reinterpret_cast<double *>(d);
-  double *dr[7];
-  for (int f = 0; f < 7; ++f) { dr[f] = p; p += nb; }
-  double *damp = p; p += nb;
-  double *dw = p; p += 2 * nb;
-  double *drad = p; p += 2 * nb;
-  double *dwl = p; p += nb;
-  double *dth = p; p += nb;
-  void *dout = d + ((nd * 8 + 255) / 256) * 256;
-  cudaError_t e = cudaSuccess;
-  auto up = [&](double *dst, const double *src, size_t cnt) {
-    if (e == cudaSuccess && cnt) e = cudaMemcpyAsync(dst, src, cnt * 8, cudaMemcpyHostToDevice, s);
-  };
-  static const bool timing = getenv("TG_HOST_TIMING") != nullptr;   // debug: per-phase times on stderr
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  if (timing) {
-    for (auto &x : ev) cudaEventCreate(&x);
-    cudaEventRecord(ev[0], s);
-  }
-  for (int f = 0; f < 7; ++f) up(dr[f], rays[f], nb);
-  up(damp, amplitude, nb);
-  up(dw, waist_xy, 2 * nb);
-  up(drad, radii_xy, 2 * nb);
-  up(dwl, wavelength, nb);
-  up(dth, theta, nb);
-  if (e != cudaSuccess) {
-    tg_set_error("H2D copy: %s", cudaGetErrorString(e));
-    rc = TG_ECUDA;
-  }
-  if (timing) cudaEventRecord(ev[1], s);
-  if (rc == TG_OK)
-    rc = tg_make_gaussian_image_f64(model_host, nb, dr, damp, dw, drad, dwl, dth, px2m, H, W, row0, nrows, dout,
-                                    out_is_c128, cull_bits, method, s);
-  if (timing) cudaEventRecord(ev[2], s);
-  if (rc == TG_OK) {
-    e = cudaMemcpyAsync(out, dout, npix * elt, cudaMemcpyDeviceToHost, s);
-    if (e != cudaSuccess) {
-      tg_set_error("D2H copy: %s", cudaGetErrorString(e));
+  int rc = TG_OK;
+  {
+    TgAsyncBuf dbuf(s);
+    TG_CUDA(dbuf.alloc(((nd * 8 + 255) / 256) * 256 + npix * elt));
+    unsigned char *d = dbuf.as<unsigned char>();
+    double *p = reinterpret_cast<double *>(d);
+    // the twelve segments in device order
+    const double *src[12] = {rays[0], rays[1], rays[2], rays[3], rays[4], rays[5], rays[6],
+                             amplitude, waist_xy, radii_xy, wavelength, theta};
+    const size_t len[12] = {(size_t)nb, (size_t)nb, (size_t)nb, (size_t)nb, (size_t)nb, (size_t)nb, (size_t)nb,
+                            (size_t)nb, 2 * (size_t)nb, 2 * (size_t)nb, (size_t)nb, (size_t)nb};
+    double *dst[12];
+    for (int i = 0; i < 12; ++i) {
+      TG_REQUIRE(src[i] || nb == 0, "null ray field");
+      dst[i] = p;
+      p += len[i];
+    }
+    void *dout = d + ((nd * 8 + 255) / 256) * 256;
+    static const bool timing = getenv("TG_HOST_TIMING") != nullptr;   // debug: per-phase times on stderr
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (timing) {
+      for (auto &x : ev) cudaEventCreate(&x);
+      cudaEventRecord(ev[0], s);
+    }
+    int ncopies = 0;
+    for (int i = 0; i < 12 && nb > 0;) {   // merge runs that are contiguous on the host
+      int j = i;
+      size_t cnt = len[i];
+      while (j + 1 < 12 && src[j + 1] == src[j] + len[j]) cnt += len[++j];
+      TG_CUDA(cudaMemcpyAsync(dst[i], src[i], cnt * 8, cudaMemcpyHostToDevice, s));
+      ++ncopies;
+      i = j + 1;
+    }
+    if (timing) cudaEventRecord(ev[1], s);
+    // rows per emitted block: a few blocks per image so that the D2H of block i hides behind block i+1
+    static const int blk_env = env_int("TG_E2E_BLOCK_ROWS", 0);
+    int block_rows = blk_env > 0 ? ((blk_env + 127) / 128) * 128 : 256;
+    if (blk_env < 0) block_rows = nrows;                     // TG_E2E_BLOCK_ROWS=-1: one block (A/B runs)
+    while ((nrows + block_rows - 1) / block_rows > kMaxEmitBlocks) block_rows *= 2;
+    block_rows = ((block_rows + 127) / 128) * 128;
+    TgEmit emit;
+    emit.host_out = static_cast<unsigned char *>(out);
+    emit.block_rows = block_rows;
+    emit.copy = pipe->copy;
+    emit.ev = pipe->ev;
+    const double *dr[7] = {dst[0], dst[1], dst[2], dst[3], dst[4], dst[5], dst[6]};
+    rc = tg_make_gaussian_image_impl(model_host, nb, dr, dst[7], dst[8], dst[9], dst[10], dst[11], px2m, H, W, row0,
+                                     nrows, dout, out_is_c128, cull_bits, method, s, &emit, nullptr);
+    if (timing) cudaEventRecord(ev[2], s);
+    cudaError_t e1 = cudaStreamSynchronize(s);
+    cudaError_t e2 = cudaStreamSynchronize(pipe->copy);
+    if (rc == TG_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+      tg_set_error("stream sync: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
       rc = TG_ECUDA;
     }
-  }
-  if (timing) cudaEventRecord(ev[3], s);
-  cudaFreeAsync(d, s);
-  cudaError_t e2 = cudaStreamSynchronize(s);
-  if (rc == TG_OK && e2 != cudaSuccess) {
-    tg_set_error("stream sync: %s", cudaGetErrorString(e2));
-    rc = TG_ECUDA;
-  }
-  if (timing) {
-    float a = 0, b = 0, c = 0;
-    cudaEventElapsedTime(&a, ev[0], ev[1]);
-    cudaEventElapsedTime(&b, ev[1], ev[2]);
-    cudaEventElapsedTime(&c, ev[2], ev[3]);
-    fprintf(stderr, "tg_make_gaussian_image_host: H2D %.3f ms, kernels %.3f ms, D2H %.3f ms\n", a, b, c);
-    for (auto &x : ev) cudaEventDestroy(x);
-  }
+    if (timing) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, ev[0], ev[1]);
+      cudaEventElapsedTime(&b, ev[1], ev[2]);
+      fprintf(stderr, "tg_make_gaussian_image_host: H2D %.3f ms (%d copies), kernels %.3f ms, blocks of %d rows\n",
+              a, ncopies, b, block_rows);
+      for (auto &x : ev) cudaEventDestroy(x);
+    }
+  }   // device buffers released (stream-ordered) after both streams have drained
   return rc;
 }

@@ -155,17 +155,105 @@ struct GemmSmemCtl {
   uint32_t tmem_base;
 };
 
+// ---- work decomposition: data-parallel tiles + a stream-K part that fills the machine ----------------
+// The GEMM is a persistent kernel of G CTAs (one per SM).  T output tiles of 128 x 128, each nch accumulation
+// chunks (CHUNK_K k-elements) deep.  Tiles [R, T) are "data-parallel": CTA c owns tiles R + c, R + c + G, ...
+// over the whole K.  Tiles [0, R) (R < G: the partial last wave, or ALL tiles when the problem has fewer tiles
+// than SMs, e.g. one rank's row shard) are split along K so that every CTA gets the same number of chunks:
+//   head  : CTA r < R takes chunks [0, q) of tile r -- the R heads walk K in lockstep, so the operand tiles
+//           they share are fetched from HBM once and served from L2 (a plain stream-K split loses exactly
+//           that: measured in round 1);
+//   tails : the remaining Tl = nch - q chunks of the R tiles are laid end to end and cut into runs of qh
+//           chunks for the G - R helper CTAs.
+// Every (tile, CTA) piece is a UNIT.  A unit that does not cover the whole K writes its fp32 partial tile to a
+// scratch slot; the last unit of a tile to arrive (atomic counter per tile and epilogue warp) adds the slots
+// in slot order and writes the output -- deterministic, no atomics on the data path.
+struct SkSched {
+  int tiles_n, T, nkb, nch, G, R, q, Tl, qh, maxparts;
+};
+struct SkUnit {
+  int tile, ch0, ch1, slot, nparts;
+};
+__host__ __device__ inline int sk_nparts(const SkSched &s, int tile) {
+  if (s.Tl <= 0) return 1;
+  const int first = (int)(((long long)tile * s.Tl) / s.qh);
+  const int last = (int)((((long long)tile + 1) * s.Tl - 1) / s.qh);
+  return 2 + last - first;
+}
+struct SkIter {
+  int phase;  // 0: head of a stream-K tile pending, 1: helper walking its run of tail chunks, 2: data-parallel tiles
+  int f0, f1, t;
+  __host__ __device__ __forceinline__ void init(const SkSched &s, int cta) {
+    phase = 2;
+    f0 = f1 = 0;
+    t = s.R + cta;
+    if (s.R > 0) {
+      if (cta < s.R) {
+        phase = 0;
+      } else {
+        phase = 1;
+        const long long tot = (long long)s.R * s.Tl;
+        long long a = (long long)(cta - s.R) * s.qh, b = a + s.qh;
+        if (a > tot) a = tot;
+        if (b > tot) b = tot;
+        f0 = (int)a;
+        f1 = (int)b;
+      }
+    }
+  }
+  __host__ __device__ __forceinline__ bool next(const SkSched &s, int cta, SkUnit &u) {
+    if (phase == 0) {
+      phase = 2;
+      u.tile = cta;
+      u.ch0 = 0;
+      u.ch1 = s.q;
+      u.slot = 0;
+      u.nparts = sk_nparts(s, cta);
+      return true;
+    }
+    if (phase == 1) {
+      if (f0 < f1) {
+        const int tile = f0 / s.Tl, c0 = f0 - tile * s.Tl;
+        int c1 = c0 + (f1 - f0);
+        if (c1 > s.Tl) c1 = s.Tl;
+        u.tile = tile;
+        u.ch0 = s.q + c0;
+        u.ch1 = s.q + c1;
+        u.slot = 1 + (cta - s.R) - (int)(((long long)tile * s.Tl) / s.qh);
+        u.nparts = sk_nparts(s, tile);
+        f0 += c1 - c0;
+        return true;
+      }
+      phase = 2;
+    }
+    if (t < s.T) {
+      u.tile = t;
+      u.ch0 = 0;
+      u.ch1 = s.nch;
+      u.slot = 0;
+      u.nparts = 1;
+      t += s.G;
+      return true;
+    }
+    return false;
+  }
+};
+
 // D[M x Np] (+)= A[M x K] * B[Np x K]^T with A = A_hi + A_lo, B = B_hi + B_lo (3 products).
 // out: doubles, row pitch ldo; rows >= M / columns >= Np are not written.  peak_key (device, may be NULL):
 // the accumulators are multiplied in fp64 by 2^(G - 2 headroom), G = tg_prescale_G(*peak_key) -- the exact
 // power of two that undoes the pre-scaling of the factors.
+// scratch / counters: stream-K partial tiles (sched.R * sched.maxparts slots of 128 x 128 floats) and one
+// arrival counter per (stream-K tile, epilogue warp), zero on entry and zero again on exit.
 template <bool F16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    int M, int Np, int K, double *__restrict__ out, long long ldo, int accumulate_out,
                    const unsigned long long *__restrict__ peak_key, double headroom,
-                   const unsigned long long *__restrict__ sep_guard, const __grid_constant__ TgPeers peers) {
+                   const unsigned long long *__restrict__ sep_guard, const __grid_constant__ TgPeers peers,
+                   const __grid_constant__ SkSched sched, float *__restrict__ scratch,
+                   unsigned int *__restrict__ counters) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;  // the SFU path owns this call
   constexpr int BK = GemmCfg<F16>::BK, CHUNK_KB = GemmCfg<F16>::CHUNK_KB;
   constexpr uint32_t kIdesc = Idesc<F16, BN>::value, kIdesc2 = Idesc<F16, 2 * BN>::value;
@@ -175,9 +263,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   GemmSmemCtl *ctl = reinterpret_cast<GemmSmemCtl *>(tiles + STAGES * STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  const int nkb = (K + BK - 1) / BK;
-  const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+  const int cta = blockIdx.x;
+  const int nkb = sched.nkb;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -203,114 +290,158 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: the shared-memory ring runs on across unit boundaries =====
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)((kb / STAGES) & 1);
-        tg_mbar_wait(&ctl->empty[s], ph ^ 1u);
-        unsigned char *st = tiles + s * STAGE_BYTES;
-        tg_mbar_expect_tx(&ctl->full[s], STAGE_BYTES);
-        tma_load_2d(st + 0 * TILE_BYTES, &tmA_hi, &ctl->full[s], kb * BK, m0);
-        tma_load_2d(st + 1 * TILE_BYTES, &tmA_lo, &ctl->full[s], kb * BK, m0);
-        tma_load_2d(st + 2 * TILE_BYTES, &tmB_hi, &ctl->full[s], kb * BK, n0);
-        tma_load_2d(st + 3 * TILE_BYTES, &tmB_lo, &ctl->full[s], kb * BK, n0);
+      SkIter itr;
+      itr.init(sched, cta);
+      SkUnit u;
+      uint32_t it = 0;
+      while (itr.next(sched, cta, u)) {
+        const int m0 = (u.tile / sched.tiles_n) * BM, n0 = (u.tile % sched.tiles_n) * BN;
+        const int kb0 = u.ch0 * CHUNK_KB, kb1 = min(u.ch1 * CHUNK_KB, nkb);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = (int)(it % STAGES);
+          const uint32_t ph = (it / STAGES) & 1u;
+          tg_mbar_wait(&ctl->empty[s], ph ^ 1u);
+          unsigned char *st = tiles + s * STAGE_BYTES;
+          tg_mbar_expect_tx(&ctl->full[s], STAGE_BYTES);
+          tma_load_2d(st + 0 * TILE_BYTES, &tmA_hi, &ctl->full[s], kb * BK, m0);
+          tma_load_2d(st + 1 * TILE_BYTES, &tmA_lo, &ctl->full[s], kb * BK, m0);
+          tma_load_2d(st + 2 * TILE_BYTES, &tmB_hi, &ctl->full[s], kb * BK, n0);
+          tma_load_2d(st + 3 * TILE_BYTES, &tmB_lo, &ctl->full[s], kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      int acc = 0;
-      uint32_t acc_ph = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)((kb / STAGES) & 1);
-        const bool chunk_start = (kb % CHUNK_KB) == 0;
-        if (chunk_start) {
-          tg_mbar_wait(&ctl->tmem_empty[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator
+      SkIter itr;
+      itr.init(sched, cta);
+      SkUnit u;
+      uint32_t it = 0, chn = 0;
+      while (itr.next(sched, cta, u)) {
+        const int kb0 = u.ch0 * CHUNK_KB, kb1 = min(u.ch1 * CHUNK_KB, nkb);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = (int)(it % STAGES);
+          const uint32_t ph = (it / STAGES) & 1u;
+          const bool chunk_start = ((kb - kb0) % CHUNK_KB) == 0;
+          const int acc = (int)(chn & 1u);
+          if (chunk_start) {
+            tg_mbar_wait(&ctl->tmem_empty[acc], ((chn >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+            tc_fence_after();
+          }
+          tg_mbar_wait(&ctl->full[s], ph);
           tc_fence_after();
-        }
-        tg_mbar_wait(&ctl->full[s], ph);
-        tc_fence_after();
-        unsigned char *st = tiles + s * STAGE_BYTES;
-        const uint64_t dAh = make_smem_desc(st + 0 * TILE_BYTES), dAl = make_smem_desc(st + 1 * TILE_BYTES);
-        const uint64_t dBh = make_smem_desc(st + 2 * TILE_BYTES), dBl = make_smem_desc(st + 3 * TILE_BYTES);
-        const uint32_t d = tmem_base + (uint32_t)(acc * ACC_COLS);
-        // Two MMAs per K-step instead of three: the B_hi and B_lo tiles are adjacent in the stage, so one
-        // N = 256 MMA forms A_hi [B_hi; B_lo]^T into columns [0,128) | [128,256) reading A_hi once, and
-        // A_lo B_hi^T is added to the second half.  Same tensor work, 17 % less shared-memory operand
-        // traffic (20 KB instead of 24 KB per K-step; the N = 128 form runs at the 128 B/clk smem limit),
-        // and the small cross terms accumulate apart from the large hi*hi term.
-        (void)dBl;
+          unsigned char *st = tiles + s * STAGE_BYTES;
+          const uint64_t dAh = make_smem_desc(st + 0 * TILE_BYTES), dAl = make_smem_desc(st + 1 * TILE_BYTES);
+          const uint64_t dBh = make_smem_desc(st + 2 * TILE_BYTES);
+          const uint32_t d = tmem_base + (uint32_t)(acc * ACC_COLS);
+          // Two MMAs per K-step instead of three: the B_hi and B_lo tiles are adjacent in the stage, so one
+          // N = 256 MMA forms A_hi [B_hi; B_lo]^T into columns [0,128) | [128,256) reading A_hi once, and
+          // A_lo B_hi^T is added to the second half.  Same tensor work, 17 % less shared-memory operand
+          // traffic (20 KB instead of 24 KB per K-step; the N = 128 form runs at the 128 B/clk smem limit),
+          // and the small cross terms accumulate apart from the large hi*hi term.
 #pragma unroll
-        for (int k4 = 0; k4 < BK_BYTES / 32; ++k4) {
-          const uint64_t ko = (uint64_t)(k4 * 32 >> 4);  // one MMA = 32 bytes (8 tf32 / 16 fp16) of the swizzled row
-          tc_mma<F16>(d, dAh + ko, dBh + ko, kIdesc2, (chunk_start && k4 == 0) ? 0u : 1u);
-          tc_mma<F16>(d + (uint32_t)BN, dAl + ko, dBh + ko, kIdesc, 1u);
-        }
-        tc_commit(&ctl->empty[s]);  // smem stage reusable once these MMAs have read it
-        if ((kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1) {
-          tc_commit(&ctl->tmem_full[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_ph ^= 1u;
+          for (int k4 = 0; k4 < BK_BYTES / 32; ++k4) {
+            const uint64_t ko = (uint64_t)(k4 * 32 >> 4);  // one MMA = 32 bytes (8 tf32 / 16 fp16) of the swizzled row
+            tc_mma<F16>(d, dAh + ko, dBh + ko, kIdesc2, (chunk_start && k4 == 0) ? 0u : 1u);
+            tc_mma<F16>(d + (uint32_t)BN, dAl + ko, dBh + ko, kIdesc, 1u);
+          }
+          tc_commit(&ctl->empty[s]);  // smem stage reusable once these MMAs have read it
+          if (((kb - kb0) % CHUNK_KB) == CHUNK_KB - 1 || kb == kb1 - 1) {
+            tc_commit(&ctl->tmem_full[acc]);
+            ++chn;
+          }
         }
       }
     }
   } else if (warp >= 4) {
     // ===== epilogue: 8 warps; warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half
-    const int q = warp & 3, h = (warp - 4) >> 2;
-    float accum[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) accum[i] = 0.f;
-    int acc = 0;
-    uint32_t acc_ph = 0;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      tg_mbar_wait(&ctl->tmem_full[acc], acc_ph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + h * 64);
-      float v[32];
-#pragma unroll
-      for (int part = 0; part < 2; ++part) {   // hi*hi columns, then the cross-term columns
-        tc_ld32(taddr + part * BN, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) accum[i] += v[i];
-        tc_ld32(taddr + part * BN + 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) accum[32 + i] += v[i];
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_ph ^= 1u;
-    }
-    const int row = m0 + q * 32 + lane;
+    const int q = warp & 3, h = (warp - 4) >> 2, ew = warp - 4;
     const double sc = peak_key ? scalbn(1.0, (int)(tg_prescale_G(*peak_key) - 2.0 * headroom)) : 1.0;
-    if (row < M) {
-      double *o = out + (long long)row * ldo + n0 + h * 64;
-      const int ncol = min(64, Np - (n0 + h * 64));
-      if (ncol == 64 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+    float accum[64];
+    SkIter itr;
+    itr.init(sched, cta);
+    SkUnit u;
+    uint32_t chn = 0;
+    while (itr.next(sched, cta, u)) {
+      const int m0 = (u.tile / sched.tiles_n) * BM, n0 = (u.tile % sched.tiles_n) * BN;
+      const int kb0 = u.ch0 * CHUNK_KB, kb1 = min(u.ch1 * CHUNK_KB, nkb);
+      const int nchunks = (kb1 - kb0 + CHUNK_KB - 1) / CHUNK_KB;
 #pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          double2 w = make_double2((double)accum[i] * sc, (double)accum[i + 1] * sc);
-          if (accumulate_out) {
-            const double2 p = *reinterpret_cast<double2 *>(o + i);
-            w.x += p.x;
-            w.y += p.y;
-          }
-          *reinterpret_cast<double2 *>(o + i) = w;
-          // row-sharded multi-GPU sum: the same values go straight into the peers' images (NVLink P2P stores)
-          for (int p = 0; p < peers.n; ++p)
-            *reinterpret_cast<double2 *>(static_cast<double *>(peers.ptr[p]) + (o - out) + i) = w;
+      for (int i = 0; i < 64; ++i) accum[i] = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch, ++chn) {
+        const int acc = (int)(chn & 1u);
+        tg_mbar_wait(&ctl->tmem_full[acc], (chn >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + h * 64);
+        float v[32];
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {   // hi*hi columns, then the cross-term columns
+          tc_ld32(taddr + part * BN, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) accum[i] += v[i];
+          tc_ld32(taddr + part * BN + 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) accum[32 + i] += v[i];
         }
-      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
+      }
+      if (u.nparts > 1) {
+        // stream-K piece: park the fp32 partial ([slot][epilogue warp][column][lane]: coalesced), count the
+        // arrival; the last piece of this tile sums the slots in slot order (fp32, like the chunk sums)
+        float *slot0 = scratch + ((size_t)u.tile * sched.maxparts) * (size_t)(BM * BN) + (size_t)ew * 2048 + lane;
+        float *mine = slot0 + (size_t)u.slot * (size_t)(BM * BN);
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i < ncol) {
-            const double wv = (accumulate_out ? o[i] : 0.0) + (double)accum[i] * sc;
-            o[i] = wv;
-            for (int p = 0; p < peers.n; ++p) (static_cast<double *>(peers.ptr[p]) + (o - out))[i] = wv;
+        for (int i = 0; i < 64; ++i) __stcg(mine + i * 32, accum[i]);
+        __threadfence();
+        __syncwarp();
+        unsigned int prev = 0;
+        if (lane == 0) {
+          __threadfence();
+          prev = atomicAdd(counters + u.tile * 8 + ew, 1u);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        if (prev != (unsigned)(u.nparts - 1)) continue;   // not the last piece
+        __threadfence();
+        if (lane == 0) counters[u.tile * 8 + ew] = 0u;    // leave the counters clean for the next launch
+#pragma unroll
+        for (int i = 0; i < 64; ++i) accum[i] = 0.f;
+        for (int s = 0; s < u.nparts; ++s) {
+          const float *src = slot0 + (size_t)s * (size_t)(BM * BN);
+#pragma unroll
+          for (int i = 0; i < 64; ++i) accum[i] += __ldcg(src + i * 32);
+        }
+      }
+      const int row = m0 + q * 32 + lane;
+      if (row < M) {
+        double *o = out + (long long)row * ldo + n0 + h * 64;
+        const int ncol = min(64, Np - (n0 + h * 64));
+        if (ncol == 64 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            double2 w = make_double2((double)accum[i] * sc, (double)accum[i + 1] * sc);
+            if (accumulate_out) {
+              const double2 p = *reinterpret_cast<double2 *>(o + i);
+              w.x += p.x;
+              w.y += p.y;
+            }
+            *reinterpret_cast<double2 *>(o + i) = w;
+            // row-sharded multi-GPU sum: the same values go straight into the peers' images (NVLink P2P stores)
+            for (int p = 0; p < peers.n; ++p)
+              *reinterpret_cast<double2 *>(static_cast<double *>(peers.ptr[p]) + (o - out) + i) = w;
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i < ncol) {
+              const double wv = (accumulate_out ? o[i] : 0.0) + (double)accum[i] * sc;
+              o[i] = wv;
+              for (int p = 0; p < peers.n; ++p) (static_cast<double *>(peers.ptr[p]) + (o - out))[i] = wv;
+            }
+        }
       }
     }
   }
@@ -575,6 +706,55 @@ int make_map(CUtensorMap *m, const void *base, long long rows, long long K, long
   return TG_OK;
 }
 
+// Host side of the work decomposition (see SkSched).  Stream-K is used when it pays: the tiles do not fill
+// whole waves of the `sms` CTAs and K is deep enough (>= 8 chunks per tile) for the pieces to amortise
+// their partial-tile round trip.  TG_GEMM_STREAMK=0 forces the plain one-tile-at-a-time schedule (A/B runs).
+SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms) {
+  SkSched s;
+  const int tiles_m = (M + BM - 1) / BM;
+  s.tiles_n = (Np + BN - 1) / BN;
+  s.T = tiles_m * s.tiles_n;
+  s.nkb = (K + BK - 1) / BK;
+  s.nch = (s.nkb + chunk_kb - 1) / chunk_kb;
+  s.G = s.T < sms ? s.T : sms;
+  s.R = 0;
+  s.q = s.nch;
+  s.Tl = 0;
+  s.qh = 1;
+  s.maxparts = 1;
+  static const bool allow = [] {
+    const char *e = getenv("TG_GEMM_STREAMK");
+    return !(e && atoi(e) == 0);
+  }();
+  if (allow && s.nch >= 8 && sms > 1) {
+    int G = sms, R = s.T % sms;
+    if (s.T < sms) {
+      const long long cap = (long long)s.T * s.nch / 4;   // at least ~4 chunks per CTA
+      G = (int)(cap < sms ? (cap > s.T ? cap : s.T) : sms);
+      R = G > s.T ? s.T : 0;
+    }
+    if (R > 0 && G > R) {
+      s.G = G;
+      s.R = R;
+      s.q = (int)(((long long)R * s.nch + G - 1) / G);
+      s.Tl = s.nch - s.q;
+      if (s.Tl <= 0) {
+        s.q = s.nch;
+        s.Tl = 0;
+      } else {
+        s.qh = (int)(((long long)R * s.Tl + (G - R) - 1) / (G - R));
+        for (int t = 0; t < R; ++t) {
+          const int n = sk_nparts(s, t);
+          if (n > s.maxparts) s.maxparts = n;
+        }
+      }
+    } else if (s.T >= sms) {
+      s.G = sms;
+    }
+  }
+  return s;
+}
+
 template <bool F16>
 int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *Blo, int M, int Np, int K,
                 long long ldk, double *out, long long ldo, int accumulate, const unsigned long long *peak_key,
@@ -587,16 +767,55 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
   if ((rc = make_map<F16>(&td, Blo, Np, K, ldk)) != TG_OK) return rc;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
   TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)((Np + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
-  gemm_x3_kernel<F16><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, tc, td, M, Np, K, out, ldo, accumulate, peak_key,
-                                                        Headroom<F16>::value, sep_guard, peers);
-  return tg_launch_check(F16 ? "gemm_x3_kernel<f16>" : "gemm_x3_kernel<tf32>");
+  int dev = 0, sms = 148;
+  TG_CUDA(cudaGetDevice(&dev));
+  static int sms_cache[64] = {0};
+  if (dev >= 0 && dev < 64 && sms_cache[dev] > 0) {
+    sms = sms_cache[dev];
+  } else {
+    TG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < 64) sms_cache[dev] = sms;
+  }
+  const SkSched sched = make_sched(M, Np, K, GemmCfg<F16>::BK, GemmCfg<F16>::CHUNK_KB, sms);
+  // stream-K scratch: arrival counters (zeroed here, left zero by the kernel) | partial tiles
+  unsigned char *sk = nullptr;
+  const size_t cnt_bytes = (((size_t)sched.R * 8 * sizeof(unsigned int)) + 255) / 256 * 256;
+  const size_t part_bytes = (size_t)sched.R * sched.maxparts * (size_t)(BM * BN) * sizeof(float);
+  if (sched.R > 0 && sched.maxparts > 1) {
+    TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&sk), cnt_bytes + part_bytes, st));
+    cudaError_t e = cudaMemsetAsync(sk, 0, cnt_bytes, st);
+    if (e != cudaSuccess) {
+      cudaFreeAsync(sk, st);
+      tg_set_error("stream-K counters: %s", cudaGetErrorString(e));
+      return TG_ECUDA;
+    }
+  }
+  gemm_x3_kernel<F16><<<(unsigned)sched.G, GEMM_THREADS, smem, st>>>(
+      ta, tb, tc, td, M, Np, K, out, ldo, accumulate, peak_key, Headroom<F16>::value, sep_guard, peers, sched,
+      sk ? reinterpret_cast<float *>(sk + cnt_bytes) : nullptr, reinterpret_cast<unsigned int *>(sk));
+  rc = tg_launch_check(F16 ? "gemm_x3_kernel<f16>" : "gemm_x3_kernel<tf32>");
+  if (sk) cudaFreeAsync(sk, st);
+  return rc;
 }
 
+// explicit tensor method under stream capture: the verdict cannot be read on the host, so a non-separable
+// input poisons the output instead of being silently ignored
+__global__ void __launch_bounds__(256)
+    nan_fill_kernel(double *__restrict__ out, size_t n, const unsigned long long *__restrict__ key) {
+  if (tg_key_is_separable(*key)) return;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// Batches of kBatch beamlets (outer loop: the column factors of a batch are built once) x row blocks (inner
+// loop: row factors + GEMM of one block; blocks exist for the host-buffer pipeline, whose D2H of a finished
+// block overlaps the GEMMs of the following ones).  acc: fp64 (nrows x 2W) accumulator = the output itself
+// for complex128.  A_hi / A_lo hold one row block.
 template <bool F16>
 int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, long long ldk, void *Ahi, void *Alo,
                 void *Bhi, void *Blo, double *acc, const unsigned long long *peak, const unsigned long long *guard,
-                cudaStream_t st, const TgPeers &gemm_peers) {
+                cudaStream_t st, const TgPeers &gemm_peers, int block_rows, const TgEmit *emit, void *out,
+                int out_is_c128) {
   const int Np = 2 * W;
   int rc = TG_OK;
   TgPeers none;
@@ -604,20 +823,72 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
   for (long long b0 = 0; b0 < nb && rc == TG_OK; b0 += kBatch) {
     const int nbatch = (int)((nb - b0) < kBatch ? (nb - b0) : kBatch);
     const int K = 2 * nbatch;
+    const bool last = b0 + kBatch >= nb;
     // (the tensor maps are encoded with the true K: the TMA unit zero-fills the K padding)
-    dim3 ga((unsigned)((nbatch + 127) / 128), (unsigned)((nrows + FS - 1) / FS));
     dim3 gb((unsigned)((nbatch + 127) / 128), (unsigned)((W + FS - 1) / FS));
-    factor_rows_kernel<F16><<<ga, 128, 0, st>>>(table, b0, nbatch, row0, nrows, W, ldk, Ahi, Alo, peak, guard);
     factor_cols_kernel<F16><<<gb, 128, 0, st>>>(table, b0, nbatch, W, ldk, Bhi, Blo, guard);
-    rc = tg_launch_check("factor kernels");
-    if (rc == TG_OK)
-      rc = launch_gemm<F16>(Ahi, Alo, Bhi, Blo, nrows, Np, K, ldk, acc, (long long)Np, b0 > 0 ? 1 : 0,
-                            peak, guard, st, (b0 + kBatch >= nb) ? gemm_peers : none);  // peers: final batch only
+    rc = tg_launch_check("factor_cols_kernel");
+    int blk = 0;
+    for (int r = 0; r < nrows && rc == TG_OK; r += block_rows, ++blk) {
+      const int nr = (nrows - r) < block_rows ? (nrows - r) : block_rows;
+      dim3 ga((unsigned)((nbatch + 127) / 128), (unsigned)((nr + FS - 1) / FS));
+      factor_rows_kernel<F16><<<ga, 128, 0, st>>>(table, b0, nbatch, row0 + r, nr, W, ldk, Ahi, Alo, peak, guard);
+      rc = tg_launch_check("factor_rows_kernel");
+      if (rc != TG_OK) break;
+      TgPeers pe = none;
+      if (last) {                                         // peers: final batch only
+        pe = gemm_peers;
+        for (int p = 0; p < pe.n; ++p) pe.ptr[p] = static_cast<double *>(pe.ptr[p]) + (size_t)r * Np;
+      }
+      double *acc_r = acc + (size_t)r * Np;
+      rc = launch_gemm<F16>(Ahi, Alo, Bhi, Blo, nr, Np, K, ldk, acc_r, (long long)Np, b0 > 0 ? 1 : 0, peak, guard,
+                            st, pe);
+      if (rc == TG_OK && last && !out_is_c128) {
+        const size_t n = (size_t)nr * Np;
+        TgPeers pc = none;   // complex64 peers are written by the conversion
+        float *o = static_cast<float *>(out) + (size_t)r * Np;
+        f64_to_c64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc_r, o, n, guard, pc);
+        rc = tg_launch_check("f64_to_c64_kernel");
+      }
+      if (rc == TG_OK && last && emit) {
+        const size_t row_bytes = (size_t)Np * (out_is_c128 ? 8 : 4);
+        rc = tg_emit_block(emit, blk, st, static_cast<unsigned char *>(out) + (size_t)r * row_bytes,
+                           (size_t)r * row_bytes, (size_t)nr * row_bytes);
+      }
+    }
   }
   return rc;
 }
 
 }  // namespace
+
+// The work decomposition of the persistent GEMM for a given shape, as the kernel's three roles enumerate it
+// (host-side mirror, no device needed): units[6 i..] = {cta, tile, chunk_begin, chunk_end, slot, nparts};
+// sched_out[10] = SkSched fields.  Returns the number of units (written up to max_units), < 0 on error.
+extern "C" int tg_gemm_schedule(int M, int N, int K, int f16, int sms, int32_t *units, int max_units,
+                                int32_t *sched_out) {
+  TG_REQUIRE(M > 0 && N > 0 && K > 0 && sms > 0, "bad GEMM shape");
+  const SkSched s = f16 ? make_sched(M, N, K, GemmCfg<true>::BK, GemmCfg<true>::CHUNK_KB, sms)
+                        : make_sched(M, N, K, GemmCfg<false>::BK, GemmCfg<false>::CHUNK_KB, sms);
+  if (sched_out) {
+    const int v[10] = {s.tiles_n, s.T, s.nkb, s.nch, s.G, s.R, s.q, s.Tl, s.qh, s.maxparts};
+    for (int i = 0; i < 10; ++i) sched_out[i] = v[i];
+  }
+  int n = 0;
+  for (int cta = 0; cta < s.G; ++cta) {
+    SkIter it;
+    it.init(s, cta);
+    SkUnit u;
+    while (it.next(s, cta, u)) {
+      if (units && n < max_units) {
+        int32_t *o = units + 6 * (size_t)n;
+        o[0] = cta; o[1] = u.tile; o[2] = u.ch0; o[3] = u.ch1; o[4] = u.slot; o[5] = u.nparts;
+      }
+      ++n;
+    }
+  }
+  return n;
+}
 
 // D[M x N] = (A_hi + A_lo)[M x K] * (B_hi + B_lo)[N x K]^T on the tensor cores (3 x TF32), fp64 out.
 extern "C" int tg_gemm_tf32x3(int M, int N, int K, const float *A_hi, const float *A_lo, const float *B_hi,
@@ -658,19 +929,25 @@ extern "C" int tg_field_sum_separable(int64_t nb, const double *poly, const doub
 
 int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                      int nrows, void *out, int out_is_c128, unsigned long long *key_async,
-                     cudaStream_t stream, int cost_cull_bits, int f16, const TgPeers *peers) {
+                     cudaStream_t stream, int cost_cull_bits, int f16, const TgPeers *peers, const TgEmit *emit,
+                     int flags) {
   TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad shape");
   TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
   TG_REQUIRE(px2m && out, "null pointer");
+  const bool verdict_only = (flags & TG_SEP_VERDICT_ONLY) != 0;
+  TG_REQUIRE(!verdict_only || key_async, "verdict-only mode needs a device key");
   cudaStream_t st = stream;
   if (nrows == 0) return TG_OK;
   const size_t npix = (size_t)nrows * W;
   TgPeers none;
   none.n = 0;
   const TgPeers &pe = peers ? *peers : none;
+  TG_REQUIRE(!(emit && pe.n > 0), "row-block emission and peer images are separate modes");
   if (nb == 0) {
+    TG_REQUIRE(!verdict_only, "verdict of an empty beamlet set");
     TG_CUDA(cudaMemsetAsync(out, 0, npix * (out_is_c128 ? 16 : 8), st));
     for (int p = 0; p < pe.n; ++p) TG_CUDA(cudaMemsetAsync(pe.ptr[p], 0, npix * (out_is_c128 ? 16 : 8), st));
+    if (emit) return tg_emit_block(emit, 0, st, out, 0, npix * (out_is_c128 ? 16 : 8));
     return TG_OK;
   }
   TG_REQUIRE(poly, "null poly");
@@ -678,42 +955,55 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   TG_CUDA(cudaGetDevice(&dev));
   tg_tune_mempool(dev);
 
+  // An explicit tensor method normally reads the separability verdict back (8 bytes + a stream synchronise)
+  // to report TG_ENOTSEPARABLE; that is illegal while the stream is being captured into a CUDA graph.  Then
+  // the verdict stays on the device like in AUTO mode: the kernels of this path return at once when the
+  // beamlets are not separable and the output is filled with NaN instead.
+  const bool capturing = !key_async && !(flags & TG_SEP_TRUSTED) && tg_stream_is_capturing(st);
+  const bool host_check = !key_async && !(flags & TG_SEP_TRUSTED) && !capturing;
+
+  int block_rows = nrows;
+  if (emit) {
+    TG_REQUIRE(emit->block_rows > 0 && emit->block_rows % BM == 0 && emit->host_out && emit->ev, "bad emission block");
+    block_rows = emit->block_rows < nrows ? emit->block_rows : nrows;
+  }
   const long long nbatch_max = nb < kBatch ? nb : kBatch;
   const long long ldk = ((2 * nbatch_max + 63) / 64) * 64;  // whole 128-byte k-blocks in either format
   const size_t elem = f16 ? 2 : 4;
   const int Np = 2 * W;
   const size_t table_bytes = (((size_t)nb * 96 + 255) / 256) * 256;
-  const size_t a_bytes = (((size_t)nrows * ldk * elem + 255) / 256) * 256;
-  const size_t b_bytes = (((size_t)Np * ldk * elem + 255) / 256) * 256;
-  const size_t acc_bytes = out_is_c128 ? 0 : npix * 16;
-  unsigned char *ws = nullptr;
-  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), table_bytes + 256 + 2 * a_bytes + 2 * b_bytes + acc_bytes, st));
+  const size_t a_bytes = verdict_only ? 0 : (((size_t)block_rows * ldk * elem + 255) / 256) * 256;
+  const size_t b_bytes = verdict_only ? 0 : (((size_t)Np * ldk * elem + 255) / 256) * 256;
+  const size_t acc_bytes = (out_is_c128 || verdict_only) ? 0 : npix * 16;
+  TgAsyncBuf wsb(st);
+  TG_CUDA(wsb.alloc(table_bytes + 256 + 2 * a_bytes + 2 * b_bytes + acc_bytes));
+  unsigned char *ws = wsb.as<unsigned char>();
   double *table = reinterpret_cast<double *>(ws);
   // control block after the table: key (8) | peak key (8) || gref (8) at +64 || est (8) at +128
   unsigned long long *key = key_async ? key_async : reinterpret_cast<unsigned long long *>(ws + table_bytes);
   unsigned long long *peak = reinterpret_cast<unsigned long long *>(ws + table_bytes + 8);
-  const unsigned long long *guard = key_async;  // async mode: kernels decide on the device
+  const unsigned long long *guard = key_async ? key_async : (capturing ? key : nullptr);  // kernels decide on the device
   unsigned char *Ahi = ws + table_bytes + 256, *Alo = Ahi + a_bytes, *Bhi = Alo + a_bytes, *Blo = Bhi + b_bytes;
   double *acc = out_is_c128 ? static_cast<double *>(out) : reinterpret_cast<double *>(Blo + b_bytes);
-  int rc = TG_OK;
-  cudaError_t e = cudaMemsetAsync(ws + table_bytes, 0, 16, st);  // own key slot, peak key
-  if (key_async && e == cudaSuccess) e = cudaMemsetAsync(key, 0, 8, st);
+  TG_CUDA(cudaMemsetAsync(ws + table_bytes, 0, 16, st));  // own key slot, peak key
+  if (key_async) TG_CUDA(cudaMemsetAsync(key, 0, 8, st));
   // cost model (AUTO with culling enabled): brightest-peak key and tile estimate live after the key slot
   const bool cost = key_async != nullptr && cost_cull_bits > 0;
   unsigned long long *gref = reinterpret_cast<unsigned long long *>(ws + table_bytes + 64);
   double *est = reinterpret_cast<double *>(ws + table_bytes + 128);
-  if (cost && e == cudaSuccess) e = cudaMemsetAsync(gref, 0xFF, 8, st);
-  if (cost && e == cudaSuccess) e = cudaMemsetAsync(est, 0, 8, st);
-  if (e == cudaSuccess) {
-    // one O(nb) kernel: pixel-space table + separability verdict + pre-scaling peak (+ brightest-peak key)
-    TgPrepExtra ex;
-    ex.sep_key = key;
-    ex.peak_key = peak;
-    ex.row0 = row0;
-    ex.nrows = nrows;
-    rc = tg_launch_prep(nb, poly, px2m, H, W, table, cost ? gref : nullptr, st, &ex);
+  if (cost) {
+    TG_CUDA(cudaMemsetAsync(gref, 0xFF, 8, st));
+    TG_CUDA(cudaMemsetAsync(est, 0, 8, st));
   }
-  if (cost && e == cudaSuccess && rc == TG_OK) {
+  // one O(nb) kernel: pixel-space table + separability verdict + pre-scaling peak (+ brightest-peak key)
+  TgPrepExtra ex;
+  ex.sep_key = key;
+  ex.peak_key = peak;
+  ex.row0 = row0;
+  ex.nrows = nrows;
+  int rc = tg_launch_prep(nb, poly, px2m, H, W, table, cost ? gref : nullptr, st, &ex);
+  if (rc != TG_OK) return rc;
+  if (cost) {
     sfu_cost_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(table, nb, H, W, gref, cost_cull_bits, est);
     static const double sfu_wins_below = [] {       // tuning knob: TG_SFU_WINS_BELOW overrides the constant
       const char *e = getenv("TG_SFU_WINS_BELOW");
@@ -722,35 +1012,35 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
     }();
     verdict_kernel<<<1, 1, 0, st>>>(key, est, (double)nb * (double)H * (double)W, sfu_wins_below);
     rc = tg_launch_check("cost kernels");
+    if (rc != TG_OK) return rc;
   }
-  unsigned long long hkey = 0;
-  if (e == cudaSuccess && rc == TG_OK && !key_async) {
-    e = cudaMemcpyAsync(&hkey, key, 8, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  }
-  if (e != cudaSuccess) {
-    tg_set_error("tg_field_sum_separable: %s", cudaGetErrorString(e));
-    rc = TG_ECUDA;
-  }
-  if (rc == TG_OK && !key_async) {
+  if (verdict_only) return TG_OK;
+  if (host_check) {
+    unsigned long long hkey = 0;
+    TG_CUDA(cudaMemcpyAsync(&hkey, key, 8, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaStreamSynchronize(st));
     double worst;
     memcpy(&worst, &hkey, 8);
     if (worst > 1.0) {
       tg_set_error("beamlets are not separable on this grid (cross term %.3g x tolerance)", worst);
-      rc = TG_ENOTSEPARABLE;
+      return TG_ENOTSEPARABLE;
     }
   }
-  if (rc == TG_OK)
-    rc = f16 ? run_batches<true>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
-                                 out_is_c128 ? pe : none)
-             : run_batches<false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
-                                  out_is_c128 ? pe : none);
-  if (rc == TG_OK && !out_is_c128) {
+  rc = f16 ? run_batches<true>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
+                               out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128)
+           : run_batches<false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
+                                out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128);
+  if (rc == TG_OK && !out_is_c128 && pe.n > 0) {
+    // complex64 peer images: one more pass over the converted rows (the GEMM's peer stores are fp64-only)
     const size_t n = npix * 2;
     f64_to_c64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, static_cast<float *>(out), n, guard, pe);
     rc = tg_launch_check("f64_to_c64_kernel");
   }
-  cudaFreeAsync(ws, st);
+  if (rc == TG_OK && capturing) {
+    const size_t n = npix * (out_is_c128 ? 2 : 1);   // complex64: one NaN double covers (re, im)
+    nan_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<double *>(out), n, key);
+    rc = tg_launch_check("nan_fill_kernel");
+  }
   return rc;
 }
 
@@ -761,22 +1051,38 @@ extern "C" int tg_field_sum(int64_t nb, const double *poly, const double px2m[6]
                            static_cast<cudaStream_t>(stream), nullptr);
 }
 int tg_field_sum_impl(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0, int nrows,
-                      void *out, int out_is_c128, int cull_bits, int method, cudaStream_t st, const TgPeers *peers) {
+                      void *out, int out_is_c128, int cull_bits, int method, cudaStream_t st, const TgPeers *peers,
+                      const TgEmit *emit) {
   if (method == TG_METHOD_SFU)
     return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st,
-                             peers);
+                             peers, emit);
   if (method == TG_METHOD_TENSOR || method == TG_METHOD_TENSOR_TF32)
     return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr, st, 0,
-                            method == TG_METHOD_TENSOR, peers);
+                            method == TG_METHOD_TENSOR, peers, emit);
   TG_REQUIRE(method == TG_METHOD_AUTO, "unknown method");
   if (nb == 0 || nrows == 0)
     return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st,
-                             peers);
-  unsigned long long *key = nullptr;
-  TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&key), 8, st));
+                             peers, emit);
+  TgAsyncBuf keyb(st);
+  TG_CUDA(keyb.alloc(8));
+  unsigned long long *key = keyb.as<unsigned long long>();
+  if (emit) {
+    // host-buffer pipeline: the call is synchronous anyway, so the verdict is read back once (8 bytes) and only
+    // the path that applies is enqueued -- block by block, each block's D2H behind its own event
+    int rc = tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, key, st, cull_bits, 1, nullptr,
+                              nullptr, TG_SEP_VERDICT_ONLY);
+    if (rc != TG_OK) return rc;
+    unsigned long long hkey = 0;
+    TG_CUDA(cudaMemcpyAsync(&hkey, key, 8, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaStreamSynchronize(st));
+    if (tg_key_is_separable(hkey))
+      return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr, st, 0, 1, peers, emit,
+                              TG_SEP_TRUSTED);
+    return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st,
+                             peers, emit);
+  }
   int rc = tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, key, st, cull_bits, 1, peers);
   if (rc == TG_OK)
     rc = tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, key, st, peers);
-  cudaFreeAsync(key, st);
   return rc;
 }

@@ -29,6 +29,49 @@ struct TgPeers {
   int n;
   void *ptr[TG_MAX_PEERS];
 };
+// Row-block emission of a field sum into HOST memory (the host-buffer entry points): the image is computed in
+// blocks of `block_rows` detector rows on the compute stream, and each finished block is copied to the host on
+// `copy` (event + cudaMemcpyAsync) while the next blocks are still being computed.
+struct TgEmit {
+  unsigned char *host_out;  // rows [row0, row0 + nrows) of the call: (nrows, W) complex128 / complex64
+  int block_rows;           // multiple of 128 (GEMM tile) -- hence of 32 (SFU tile)
+  cudaStream_t copy;
+  cudaEvent_t *ev;          // >= ceil(nrows / block_rows) events (cudaEventDisableTiming)
+};
+#define TG_SEP_VERDICT_ONLY 1 /* tg_separable_run: table + separability / cost verdict into *key_async, nothing else */
+#define TG_SEP_TRUSTED 2      /* tg_separable_run: the caller has read the verdict; skip the host-side check */
+
+// stream-ordered scratch allocation, released (stream-ordered) when the scope ends -- also on error returns
+struct TgAsyncBuf {
+  void *p = nullptr;
+  cudaStream_t st;
+  explicit TgAsyncBuf(cudaStream_t s) : st(s) {}
+  TgAsyncBuf(const TgAsyncBuf &) = delete;
+  TgAsyncBuf &operator=(const TgAsyncBuf &) = delete;
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 8, st); }
+  template <class T> T *as() const { return static_cast<T *>(p); }
+  ~TgAsyncBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+};
+// copy rows of a finished block to the host behind an event (see TgEmit)
+static inline int tg_emit_block(const TgEmit *emit, int block, cudaStream_t compute, const void *dev_rows,
+                                size_t byte_offset, size_t bytes) {
+  cudaError_t e = cudaEventRecord(emit->ev[block], compute);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(emit->copy, emit->ev[block], 0);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(emit->host_out + byte_offset, dev_rows, bytes, cudaMemcpyDeviceToHost, emit->copy);
+  if (e != cudaSuccess) {
+    tg_set_error("row-block D2H: %s", cudaGetErrorString(e));
+    return TG_ECUDA;
+  }
+  return TG_OK;
+}
+static inline bool tg_stream_is_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+}
+
 // Q_inv + wave numbers + coefficients from the traced ABCD in one kernel (coeffs.cu)
 int tg_coeffs_from_beam(int64_t nb, const double *amp, const double *pathlength, const double *waist_xy,
                         const double *radii_xy, const double *wavelength, const double *theta,
@@ -36,7 +79,8 @@ int tg_coeffs_from_beam(int64_t nb, const double *amp, const double *pathlength,
                         const double *thy, double *poly, cudaStream_t st);
 int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                       int nrows, void *out, int out_is_c128, int cull_bits, long long *n_evals_out,
-                      const unsigned long long *sep_guard, cudaStream_t stream, const TgPeers *peers = nullptr);
+                      const unsigned long long *sep_guard, cudaStream_t stream, const TgPeers *peers = nullptr,
+                      const TgEmit *emit = nullptr);
 // key_async != NULL: no host sync; the verdict stays on the device in *key_async and the kernels of
 // this path return at once when it says "not separable".
 // cost_cull_bits > 0 (async mode only): also estimate the culled SFU work and leave the call to the SFU
@@ -44,9 +88,17 @@ int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int 
 // f16 != 0: fp16 x 3 operands (kind::f16, device-side pre-scaling), else tf32 x 3.
 int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                      int nrows, void *out, int out_is_c128, unsigned long long *key_async,
-                     cudaStream_t stream, int cost_cull_bits, int f16, const TgPeers *peers = nullptr);
+                     cudaStream_t stream, int cost_cull_bits, int f16, const TgPeers *peers = nullptr,
+                     const TgEmit *emit = nullptr, int flags = 0);
 int tg_field_sum_impl(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0, int nrows,
-                      void *out, int out_is_c128, int cull_bits, int method, cudaStream_t st, const TgPeers *peers);
+                      void *out, int out_is_c128, int cull_bits, int method, cudaStream_t st, const TgPeers *peers,
+                      const TgEmit *emit = nullptr);
+// the whole of make_gaussian_image for device-resident inputs (host_api.cu); emit / peers optional
+int tg_make_gaussian_image_impl(const tg_model *model_host, int64_t nb, const double *const rays[7],
+                                const double *amplitude, const double *waist_xy, const double *radii_xy,
+                                const double *wavelength, const double *theta, const double px2m[6], int H,
+                                int W, int row0, int nrows, void *out, int out_is_c128, int cull_bits,
+                                int method, cudaStream_t s, const TgEmit *emit, const TgPeers *peers);
 // separability key = bits of max_n(cross term / tolerance) as a double (0 when there is none)
 __host__ __device__ inline bool tg_key_is_separable(unsigned long long key) {
   union { unsigned long long u; double d; } c;

@@ -116,27 +116,32 @@ class _CudaBuf:
 
 
 class PeerImage:
-    """A full ``(H, W)`` complex image per rank in IPC-shared device memory, with every peer's
-    image (and barrier flags) mapped into this process over NVLink (``tg_peer_alloc`` /
-    ``tg_peer_open``; the 64-byte handles travel through ``dist.all_gather_object``).
+    """Two full ``(H, W)`` complex images per rank (ping-pong) in IPC-shared device memory, with every peer's
+    images and barrier flags mapped into this process over NVLink (``tg_peer_alloc`` / ``tg_peer_open``; the
+    64-byte handles travel through ``dist.all_gather_object``).
 
-    ``field_sum(poly, nb, grid, ...)`` computes this rank's row block and the producing kernels
-    store it into ALL ranks' images (``tg_field_sum_peers``), then ``barrier()`` runs the
-    device-side barrier; afterwards ``self.image`` holds the complete image on every rank.
-    The image buffer is reused by the next ``field_sum`` (which first runs a barrier so that no rank
-    overwrites a peer's image that is still being consumed): use or copy ``image`` on the same stream
-    before calling it again.
+    ``field_sum(poly, nb, grid, ...)`` computes this rank's row block and the producing kernels store it into
+    the current buffer of ALL ranks (``tg_field_sum_peers``); ``barrier()`` runs the device-side barrier and
+    flips the buffers; afterwards ``image`` holds the complete image of that step on every rank.
+    ``step(...)`` is both.  Because consecutive steps write different buffers, ONE barrier per step is enough:
+    a rank can only start storing step k+1 into a peer's other buffer after it has passed barrier k, which the
+    peer enters only after (in stream order) it has consumed the result of step k-1 -- the last user of that
+    buffer.  So: use or copy ``image`` on the same stream before the next step.
+    The barrier keeps its epoch in device memory (``tg_peer_barrier_auto``), so a whole step can be captured
+    into a CUDA graph (``PeerImagePlan``).  A barrier timeout (``barrier_timeout_s``, default
+    ``TG_PEER_BARRIER_TIMEOUT_S`` or 10 s) does not trap; ``status()`` reports it.
     One process per GPU, all ranks on one node.  World size 1 works (and is what the 1-GPU tests run).
     """
 
     FLAG_BYTES = 256
 
-    def __init__(self, H: int, W: int, dtype=None, group=None, device=None):
+    def __init__(self, H: int, W: int, dtype=None, group=None, device=None, barrier_timeout_s: float = 0.0):
         import ctypes as C
         import torch
         from . import _lib as L
         dist = _dist()
         self._L, self._lib = L, L.load()
+        self._own = None
         self.group = group
         inited = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(group) if inited else 1
@@ -147,13 +152,16 @@ class PeerImage:
         if self.dtype not in (torch.complex128, torch.complex64):
             raise ValueError("dtype must be complex128 or complex64")
         self.H, self.W = int(H), int(W)
+        self.barrier_timeout_s = float(barrier_timeout_s)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         elt = 16 if self.dtype == torch.complex128 else 8
         self.image_bytes = ((self.H * self.W * elt + 255) // 256) * 256
+        # layout: image 0 | image 1 | flags (npeers uint64) | state {epoch, status} at +128 of the flag block
+        total = 2 * self.image_bytes + self.FLAG_BYTES
         with torch.cuda.device(self.device):
             ptr = C.c_void_p()
             handle = (C.c_ubyte * 64)()
-            L.check(self._lib.tg_peer_alloc(self.image_bytes + self.FLAG_BYTES, C.byref(ptr), handle), "tg_peer_alloc")
+            L.check(self._lib.tg_peer_alloc(total, C.byref(ptr), handle), "tg_peer_alloc")
             self._own = int(ptr.value)
             handles = [None] * self.world
             if self.world > 1:
@@ -171,41 +179,95 @@ class PeerImage:
                 self._ptrs.append(int(q.value))
             if self.world > 1:
                 dist.barrier(group=group)      # every rank has zeroed and mapped before anyone signals
-        self.epoch = 0
+        self.parity = 0
         typestr = "<c16" if self.dtype == torch.complex128 else "<c8"
-        self.image = torch.as_tensor(_CudaBuf(self._own, (self.H, self.W), typestr, self), device=self.device)
+        self.images = [torch.as_tensor(_CudaBuf(self._own + b * self.image_bytes, (self.H, self.W), typestr, self),
+                                       device=self.device) for b in range(2)]
+        self._status = torch.as_tensor(_CudaBuf(self._own + 2 * self.image_bytes + 128, (2,), "<u8", self),
+                                       device=self.device)
+        self.image = self.images[0]
 
-    def _images(self):
-        return self._L.ptr_array(self._ptrs)
+    # -- plumbing
+    def _images(self, parity):
+        return self._L.ptr_array([p + parity * self.image_bytes for p in self._ptrs])
 
     def _flags(self):
-        return self._L.ptr_array([p + self.image_bytes for p in self._ptrs])
+        return self._L.ptr_array([p + 2 * self.image_bytes for p in self._ptrs])
 
-    def field_sum(self, poly, nb: int, grid, *, cull_bits=None, method="auto"):
-        """This rank's tile-aligned row block of the grid field sum, written into every rank's image."""
+    def _state_ptr(self):
+        return self._own + 2 * self.image_bytes + 128
+
+    def check_grid(self, grid, out_dtype=None):
+        H, W = int(grid.shape[0]), int(grid.shape[1])
+        if (H, W) != (self.H, self.W):
+            raise ValueError(f"PeerImage is {self.H}x{self.W} but the detector is {H}x{W}")
+        if out_dtype is not None and out_dtype != self.dtype:
+            raise ValueError(f"PeerImage holds {self.dtype} but out_dtype={out_dtype} was requested")
+
+    def rows(self):
+        return row_shards(self.H, self.world)[self.rank]
+
+    def field_sum(self, poly, nb: int, grid, *, cull_bits=None, method="auto", parity=None):
+        """This rank's tile-aligned row block of the grid field sum, written into buffer ``parity`` (default: the
+        current one) of every rank."""
         import torch
         from .gaussian import DEFAULT_CULL_BITS
         L = self._L
-        r0, nr = row_shards(self.H, self.world)[self.rank]
+        self.check_grid(grid)
+        r0, nr = self.rows()
         cull = DEFAULT_CULL_BITS if cull_bits is None else int(cull_bits)
-        if self.epoch > 0 and self.world > 1:
-            # the image is reused: no rank may store into its peers' images before every rank has consumed the
-            # previous result (their consumers precede this barrier on their streams)
-            self.barrier()
+        par = self.parity if parity is None else int(parity)
         with torch.cuda.device(self.device):
             L.check(self._lib.tg_field_sum_peers(
                 int(nb), poly.data_ptr() if nb else None, L.dbl_array(grid.px2m_affine), self.H, self.W, r0, nr,
-                self._images(), self.world, self.rank, int(self.dtype == torch.complex128), cull,
+                self._images(par), self.world, self.rank, int(self.dtype == torch.complex128), cull,
                 L.TG_METHOD[method], torch.cuda.current_stream().cuda_stream), "tg_field_sum_peers")
         return r0, nr
 
-    def barrier(self):
-        """Device-side barrier over peer memory on the current stream (asynchronous for the host)."""
+    def image_step(self, g_arrays, cm, grid, *, cull_bits=None, method="auto", parity=None):
+        """The whole of ``make_gaussian_image`` for this rank's rows with peer stores
+        (``tg_make_gaussian_image_peers``); ``g_arrays`` = flat fp64 CUDA tensors of the GaussianRay fields."""
+        import ctypes as C
         import torch
-        self.epoch += 1
+        from .gaussian import DEFAULT_CULL_BITS
+        from .ray import RAY_FIELDS
+        L = self._L
+        self.check_grid(grid)
+        r0, nr = self.rows()
+        cull = DEFAULT_CULL_BITS if cull_bits is None else int(cull_bits)
+        par = self.parity if parity is None else int(parity)
+        g = g_arrays
         with torch.cuda.device(self.device):
-            self._L.check(self._lib.tg_peer_barrier(self._flags(), self.world, self.rank, self.epoch,
-                                                    torch.cuda.current_stream().cuda_stream), "tg_peer_barrier")
+            L.check(self._lib.tg_make_gaussian_image_peers(
+                C.byref(cm), g["n"], L.ptr_array([g[f].data_ptr() for f in RAY_FIELDS]), g["amplitude"].data_ptr(),
+                g["waist_xy"].data_ptr(), g["radii_of_curv"].data_ptr(), g["wavelength"].data_ptr(),
+                g["theta"].data_ptr(), L.dbl_array(grid.px2m_affine), self.H, self.W, r0, nr, self._images(par),
+                self.world, self.rank, int(self.dtype == torch.complex128), cull, L.TG_METHOD[method],
+                torch.cuda.current_stream().cuda_stream), "tg_make_gaussian_image_peers")
+
+    def barrier(self, flip: bool = True):
+        """Device-side barrier over peer memory on the current stream (asynchronous for the host); afterwards
+        ``image`` is the buffer the step just completed and the next step writes the other one."""
+        import torch
+        with torch.cuda.device(self.device):
+            self._L.check(self._lib.tg_peer_barrier_auto(self._flags(), self.world, self.rank, self._state_ptr(),
+                                                         self.barrier_timeout_s,
+                                                         torch.cuda.current_stream().cuda_stream),
+                          "tg_peer_barrier_auto")
+        if flip:
+            self.image = self.images[self.parity]
+            self.parity ^= 1
+
+    def step(self, poly, nb: int, grid, *, cull_bits=None, method="auto"):
+        self.field_sum(poly, nb, grid, cull_bits=cull_bits, method=method)
+        self.barrier()
+        return self.image
+
+    def status(self):
+        """``(barriers completed, timeout code)`` read back from the device (synchronises): the code is 0, or
+        1 + the rank a barrier gave up waiting for."""
+        st = self._status.cpu()
+        return int(st[0]), int(st[1])
 
     def close(self):
         import torch
@@ -220,8 +282,89 @@ class PeerImage:
                 if r != self.rank:
                     self._lib.tg_peer_close(p)
             self.image = None
+            self.images = None
+            self._status = None
             self._lib.tg_peer_free(self._own)
         self._own = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        # last resort (interpreter shutdown may already have torn torch.distributed down): a single-rank image
+        # can always be released; a multi-rank one is only unmapped by an explicit, collective close()
+        try:
+            if getattr(self, "_own", None) is not None and self.world == 1:
+                self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class PeerImagePlan:
+    """Row-sharded ``make_gaussian_image`` of ONE image over all ranks, captured into two CUDA graphs (one per
+    ping-pong buffer) and replayed: per step every rank runs the ray kernel, the coefficient kernel and the
+    field sum of its row block -- whose final stores go into every rank's image over NVLink -- and ONE
+    device-side barrier, with no host work between the kernels.  All ranks must call ``run()`` the same number
+    of times.  ``update(rays)`` copies new beamlet parameters into the static buffers (same on all ranks)."""
+
+    def __init__(self, gaussian_rays, model, peer_image: "PeerImage", *, cull_bits=None, method="auto"):
+        import torch
+        from .gaussian import _beamlet_arrays, _device_for
+        from .run import compile_model
+        self.pimg = peer_image
+        grid = model[-1]
+        peer_image.check_grid(grid)
+        dev = _device_for(gaussian_rays)
+        self.device = dev
+        garr = _beamlet_arrays(gaussian_rays, dev)
+        self._g = {k: (v.clone() if hasattr(v, "clone") else v) for k, v in garr.items()}
+        cm = compile_model(model)
+        kw = dict(cull_bits=cull_bits, method=method)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm-up outside the capture (both buffers)
+            for par in (0, 1):
+                peer_image.image_step(self._g, cm, grid, parity=par, **kw)
+                peer_image.barrier(flip=False)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._graphs = []
+        for par in (0, 1):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                peer_image.image_step(self._g, cm, grid, parity=par, **kw)
+                peer_image.barrier(flip=False)
+            self._graphs.append(gr)
+        self._parity = 0
+
+    def update(self, gaussian_rays):
+        from dataclasses import fields
+        from . import _arrays as A
+        for f in fields(gaussian_rays):
+            dst = self._g[f.name]
+            dst.copy_(A.to_device_f64(getattr(gaussian_rays, f.name), self.device).reshape(dst.shape),
+                      non_blocking=True)
+        return self
+
+    def run(self):
+        """Replay one step; returns the complete ``(H, W)`` image (valid on the current stream; overwritten
+        by the step after next)."""
+        self._graphs[self._parity].replay()
+        img = self.pimg.images[self._parity]
+        self._parity ^= 1
+        return img
+
+    __call__ = run
+
+
+# Below this many nominal evaluations (beamlets x pixels) one GPU finishes the tensor-core path before the
+# exchange of a sharded step would (measured on 8 x B200, bench.py "row_sharded_single_image"): `auto` then
+# computes the whole image on every rank instead of sharding it.
+SHARD_MIN_EVALS = 4.0e9
 
 
 def make_gaussian_image_sharded(gaussian_rays, model, *, cull_bits=None, out_dtype=None,
@@ -235,9 +378,10 @@ def make_gaussian_image_sharded(gaussian_rays, model, *, cull_bits=None, out_dty
     broadcast; every rank sums its row block; the blocks are all-gathered.  ``rows_fn`` /
     ``table_fn`` exist so the plumbing can be exercised on CPU with gloo.
 
-    With ``peer_image`` (a ``PeerImage`` of the detector's shape) the exchange is fused into the
-    compute kernels over NVLink peer memory instead: no broadcast, no all-gather; returns
-    ``peer_image.image`` (valid on the current stream after the device-side barrier).
+    With ``peer_image`` (a ``PeerImage`` of the detector's shape and of ``out_dtype``) the exchange is fused
+    into the compute kernels over NVLink peer memory instead: no broadcast (every rank builds the same table
+    from the inputs it holds; ``src`` is not used), no all-gather; returns ``peer_image.image`` (valid on the
+    current stream after the device-side barrier).
     """
     import torch
     dist = _dist()
@@ -247,14 +391,16 @@ def make_gaussian_image_sharded(gaussian_rays, model, *, cull_bits=None, out_dty
     inited = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size(group) if inited else 1
     rank = dist.get_rank(group) if inited else 0
+    if peer_image is not None and rows_fn is not None:
+        raise ValueError("rows_fn injects the per-rank compute of the NCCL path; the peer-image path runs "
+                         "tg_field_sum_peers itself")
     table_fn = table_fn or (lambda: beamlet_polynomials(gaussian_rays, model))
     poly, nb, dev = table_fn()          # every rank holds the inputs; src's table wins
     if peer_image is not None:
         # fused path: every rank builds the (deterministic) table from the inputs it holds -- no broadcast --
         # and its row block lands in every rank's image through NVLink stores issued by the compute kernels
-        peer_image.field_sum(poly, nb, grid, cull_bits=cull_bits, method=method)
-        peer_image.barrier()
-        return peer_image.image
+        peer_image.check_grid(grid, out_dtype)
+        return peer_image.step(poly, nb, grid, cull_bits=cull_bits, method=method)
     poly = broadcast_table(poly, nb, src=src, group=group)
     r0, nr = row_shards(H, world)[rank]
     rows_fn = rows_fn or (lambda p, n, row0, nrows: _field_sum_grid(

@@ -267,6 +267,36 @@ def _finish(out, kind):
     return host if kind == A.KIND_TORCH_CPU else host.numpy()
 
 
+_PACK_ORDER = RAY_FIELDS + ("amplitude", "waist_xy", "radii_of_curv", "wavelength", "theta")
+
+
+def pack_beamlets_pinned(gaussian_rays):
+    """The same ``GaussianRay`` with every field a view into ONE page-locked host slab, in the order the
+    host-buffer call uploads them (rays, amplitude, waist_xy, radii_of_curv, wavelength, theta): the H2D of
+    ``make_gaussian_image`` / ``tg_make_gaussian_image_host`` is then a single PCIe copy of 112 bytes per
+    beamlet instead of twelve small ones.  Fields are numpy views; writing into them updates the slab."""
+    import torch
+    g = gaussian_rays
+    n = 1
+    for f in RAY_FIELDS + ("amplitude", "wavelength", "theta"):
+        n = max(n, A.numel(getattr(g, f)))
+    n = max(n, A.numel(g.waist_xy) // 2, A.numel(g.radii_of_curv) // 2)
+    slab = torch.empty(14 * n, dtype=torch.float64, pin_memory=True).numpy()
+    views, off = {}, 0
+    for f in _PACK_ORDER:
+        width = 2 if f in ("waist_xy", "radii_of_curv") else 1
+        h = A.to_host_f64(getattr(g, f))
+        if h.size == width and n > 1:
+            h = np.broadcast_to(h.reshape(1, width), (n, width)).reshape(-1)
+        if h.size != n * width:
+            raise ValueError(f"GaussianRay field {f!r} has {h.size} entries, expected {n * width}")
+        v = slab[off:off + n * width]
+        v[:] = h
+        views[f] = v.reshape(n, 2) if width == 2 else v
+        off += n * width
+    return type(g)(**views)
+
+
 def make_gaussian_image_host(gaussian_rays, model, *, cull_bits=None, out_dtype=None, row0=0,
                              nrows=None, device=None, method="auto"):
     """``make_gaussian_image`` for HOST inputs through the single host-buffer C-ABI call
@@ -440,8 +470,10 @@ class GaussianImagePlan:
         self._kw = dict(cull_bits=cull_bits, out_dtype=out_dtype, method=method)
         dev = _device_for(gaussian_rays)
         self.device = dev
-        self._static = replace_fields(gaussian_rays, lambda v: A.to_device_f64(v, dev).clone()
-                                      if A.kind_of(v) != A.KIND_SCALAR else v)
+        # every field (Python scalars too) becomes an expanded static CUDA tensor BEFORE the capture: a scalar
+        # left in place would turn into a pageable H2D copy inside the graph
+        garr = _beamlet_arrays(gaussian_rays, dev)
+        self._static = type(gaussian_rays)(**{f.name: garr[f.name].clone() for f in fields(gaussian_rays)})
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                      # warm-up outside the capture
@@ -457,9 +489,13 @@ class GaussianImagePlan:
         """Copy new beamlet parameters (same shapes) into the plan's static buffers."""
         for f in fields(gaussian_rays):
             dst, src = getattr(self._static, f.name), getattr(gaussian_rays, f.name)
-            if A.kind_of(dst) == A.KIND_SCALAR:
-                continue
-            dst.copy_(A.to_device_f64(src, self.device).reshape(dst.shape), non_blocking=True)
+            t = A.to_device_f64(src, self.device)
+            if t.numel() != dst.numel():
+                if t.numel() not in (1, 2) or dst.numel() % t.numel():
+                    raise ValueError(f"GaussianImagePlan.update: field {f.name!r} has {t.numel()} entries, "
+                                     f"the plan was built for {dst.numel()}")
+                t = t.reshape(1, -1).expand(dst.numel() // t.numel(), t.numel())
+            dst.copy_(t.reshape(dst.shape), non_blocking=True)
         return self
 
     def run(self):

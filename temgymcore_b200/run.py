@@ -374,6 +374,23 @@ def solve_model(ray, model: Sequence[Any], propagator: BasePropagator = FreeSpac
     return np.array(mats)
 
 
+def _expand_param_leaves(root, path):
+    """``[(key_suffix, leaf_path)]`` for the parameter of ``root`` at ``path``: a scalar leaf is itself
+    (empty suffix); a NamedTuple / dataclass node expands into its fields in field order, keyed by index."""
+    import dataclasses
+    try:
+        v = root
+        for k in path:
+            v = getattr(v, k) if isinstance(k, str) else v[k]
+    except (AttributeError, IndexError, KeyError, TypeError):
+        return [((), path)]                 # let _tg_param_seeds raise the reference's RuntimeError
+    if isinstance(v, tuple) and hasattr(v, "_fields"):
+        return [((i,), path + (name,)) for i, name in enumerate(v._fields)]
+    if dataclasses.is_dataclass(v) and not isinstance(v, type):
+        return [((i,), path + (f.name,)) for i, f in enumerate(dataclasses.fields(v))]
+    return [((), path)]
+
+
 def run_with_grads(input_ray, model: Sequence[Any], grad_vars: Sequence[Any]):
     """Run the model and compute Jacobians w.r.t. selected variables (run.py:182-267).
 
@@ -403,8 +420,12 @@ def run_with_grads(input_ray, model: Sequence[Any], grad_vars: Sequence[Any]):
         idx = next((i for i, c in enumerate(comps) if c is root), None)
         if idx is None or not path:
             raise RuntimeError(f"Cannot find {var._build()} in parameters")
-        seeds = [(idx, slot, w) for slot, w in root._tg_param_seeds(path)]
-        directions.append((var._build(), None, seeds))
+        # a reference to a container-valued parameter (DescanError, KrivanekCoeffs) stands for all of its
+        # leaves: the reference expands the node into one variable per leaf, keyed path + (leaf index,)
+        # (PathBuilder._find_in, tree_utils.py:100-122)
+        for suffix, leaf in _expand_param_leaves(root, tuple(path)):
+            seeds = [(idx, slot, w) for slot, w in root._tg_param_seeds(leaf)]
+            directions.append((var._build() + suffix, None, seeds))
     if not directions:
         raise RuntimeError("Cannot find any variable in parameters")
 

@@ -69,6 +69,33 @@ def main():
                               f"max|diff|/max = {err:.2e}", flush=True)
             finally:
                 pi.close()
+    # the graph-captured step (PeerImagePlan: ray kernel + coefficients + field sum with peer stores + ONE barrier,
+    # ping-pong images) on both C2 paths and on C3-like narrow beamlets through the culled SFU kernel
+    from temgymcore_b200.gaussian import make_gaussian_image_device
+    for name, (g, model), kw in (("c2", M.aperture_diffraction_case(10_000, (1024, 1024)), dict(cull_bits=0, method="auto")),
+                                 ("c2", M.aperture_diffraction_case(10_000, (1024, 1024)), dict(cull_bits=0, method="sfu")),
+                                 ("c3_20k", M.biprism_case(20_000, (2048, 2048)), dict(method="auto"))):
+        gd = replace(g, **{f.name: torch.as_tensor(getattr(g, f.name), device=dev) for f in fields(g)})
+        grid = model[-1]
+        single = make_gaussian_image_device(gd, model, **kw)
+        with D.PeerImage(grid.shape[0], grid.shape[1]) as pi:
+            plan = D.PeerImagePlan(gd, model, pi, **kw)
+            outs = [plan.run().clone() for _ in range(5)]          # odd count: both buffers, ends on buffer 0
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                plan.run()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / 20], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            errs = [float((o - single).norm() / single.norm()) for o in outs]
+            ok &= max(errs) < 1e-6 and pi.status()[1] == 0
+            if rank == 0:
+                print(f"{name:8s} {kw['method']:5s} graph_plan   world={world} {float(t):.3f} ms/image "
+                      f"rel-L2 vs single GPU = {max(errs):.2e}", flush=True)
     # complex64 images and the explicit tensor method: the f64 -> c64 conversion kernel and the c64 branch of the
     # split-reduce kernel issue the peer stores there
     g, model = M.aperture_diffraction_case(3000, (512, 768))

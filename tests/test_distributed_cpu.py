@@ -113,6 +113,14 @@ class _SharedMemPeerImage:
     def barrier(self):
         dist.barrier()
 
+    def check_grid(self, grid, out_dtype=None):
+        assert tuple(int(v) for v in grid.shape) == (self.H, self.W)
+
+    def step(self, poly, nb, grid, *, cull_bits=None, method="auto"):
+        self.field_sum(poly, nb, grid, cull_bits=cull_bits, method=method)
+        self.barrier()
+        return self.image
+
 
 def _peer_worker(rank, world, port, images, nb, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))

@@ -1,0 +1,86 @@
+"""CPU test of the persistent GEMM's work decomposition (csrc/separable.cu: SkSched / SkIter, exported as
+tg_gemm_schedule): every (tile, accumulation chunk) is covered exactly once, stream-K pieces of a tile have
+distinct slots 0..nparts-1, and the CTAs' loads are balanced.  No GPU needed: the same host/device code
+enumerates the units in the kernel's producer, MMA and epilogue roles."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from temgymcore_b200 import _lib as L
+
+SHAPES = [
+    # (M, N, K, f16)                       what it is
+    (1024, 2048, 20000, 1),              # BASELINE C2: 128 tiles on 148 SMs -> all tiles stream-K
+    (128, 2048, 20000, 1),               # C2 row shard of one rank at N = 8: 16 tiles
+    (256, 2048, 20000, 1),               # N = 4 shard / e2e row block
+    (2048, 4096, 32768, 1),              # C3 batch: 512 tiles = 3 waves + 68
+    (2048, 4096, 3392, 1),               # C3 last batch
+    (100, 72, 40, 1), (128, 128, 128, 1), (130, 260, 1000, 1), (1, 1, 1, 1), (4096, 128, 64, 1),
+    (1024, 2048, 20000, 0), (300, 500, 4000, 0), (128, 2048, 777, 0),
+    (19 * 128, 128, 5000, 1),            # 19 tiles
+    (148 * 128, 128, 4096, 1),           # exactly one wave: no stream-K
+    (149 * 128, 128, 4096, 1),           # one wave + 1 tile
+]
+
+
+def schedule(M, N, K, f16, sms=148):
+    lib = L.load()
+    sched = (C.c_int32 * 10)()
+    n = lib.tg_gemm_schedule(M, N, K, f16, sms, None, 0, sched)
+    assert n > 0
+    units = np.zeros((n, 6), dtype=np.int32)
+    n2 = lib.tg_gemm_schedule(M, N, K, f16, sms, units.ctypes.data, n, sched)
+    assert n2 == n
+    keys = ("tiles_n", "T", "nkb", "nch", "G", "R", "q", "Tl", "qh", "maxparts")
+    return units, dict(zip(keys, list(sched)))
+
+
+@pytest.mark.parametrize("M,N,K,f16", SHAPES)
+def test_every_chunk_covered_once(M, N, K, f16):
+    units, s = schedule(M, N, K, f16)
+    T, nch = s["T"], s["nch"]
+    assert T == -(-M // 128) * -(-N // 128)
+    cover = np.zeros((T, nch), dtype=np.int32)
+    slots = {}
+    for cta, tile, c0, c1, slot, nparts in units:
+        assert 0 <= cta < s["G"] <= 148
+        assert 0 <= tile < T and 0 <= c0 < c1 <= nch, (tile, c0, c1)
+        cover[tile, c0:c1] += 1
+        slots.setdefault(tile, []).append((slot, nparts))
+        assert nparts <= s["maxparts"]
+        if tile >= s["R"]:
+            assert (c0, c1, slot, nparts) == (0, nch, 0, 1)       # data-parallel tile: whole K, direct store
+    assert (cover == 1).all()
+    for tile, sl in slots.items():
+        nparts = sl[0][1]
+        assert all(n == nparts for _, n in sl)
+        assert sorted(x for x, _ in sl) == list(range(nparts)), (tile, sl)   # the counter reaches nparts exactly
+
+
+@pytest.mark.parametrize("M,N,K,f16", [s for s in SHAPES if s[2] >= 4000])
+def test_load_balance(M, N, K, f16):
+    units, s = schedule(M, N, K, f16)
+    load = np.zeros(s["G"], dtype=np.int64)
+    for cta, tile, c0, c1, slot, nparts in units:
+        load[cta] += c1 - c0
+    total = s["T"] * s["nch"]
+    assert load.sum() == total
+    ideal = total / s["G"]
+    # the busiest CTA sets the time: within 3 % (+ one chunk) of a perfect split over the CTAs used
+    assert load.max() <= 1.03 * ideal + 1, (load.max(), ideal, s)
+    if total >= 148 * 8:
+        assert s["G"] == 148
+
+
+def test_c2_uses_every_sm_and_heads_walk_in_lockstep():
+    units, s = schedule(1024, 2048, 20000, 1)
+    assert s["G"] == 148 and s["R"] == 128 and s["maxparts"] <= 3
+    heads = units[units[:, 4] == 0]
+    assert len(heads) == 128 and (heads[:, 2] == 0).all() and (heads[:, 3] == s["q"]).all()
+
+
+def test_streamk_can_be_disabled_by_shape():
+    # shallow K: not worth splitting
+    units, s = schedule(128, 2048, 512, 1)
+    assert s["R"] == 0 and s["G"] == 16 and len(units) == 16

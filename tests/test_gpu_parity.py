@@ -51,6 +51,12 @@ def ray_to_cuda(torch, ray):
                  for f in RAY_FIELDS))
 
 
+def gaussian_to_cuda(torch, g):
+    from dataclasses import fields, replace
+    return replace(g, **{f.name: torch.as_tensor(np.asarray(getattr(g, f.name), dtype=np.float64), device="cuda")
+                         for f in fields(g)})
+
+
 MODELS = {
     "readme": M.readme_model,
     "kitchen_sink": M.kitchen_sink_model,
@@ -436,6 +442,86 @@ def test_c2_full_size_field(torch_cuda):
     np.testing.assert_array_equal(to_np(culled), full)
 
 
+# ---- full BASELINE sizes against the ORACLE (not CUDA against CUDA): sampled pixels --------------------
+_ORACLE_SAMPLES = {}
+
+
+def _oracle_at_pixels(key, g, model, pix):
+    """The oracle's field (gaussian.py:225-369 restated) at flat pixel indices ``pix`` of ``model[-1]``;
+    cached per ``key`` so the methods of one configuration share the ~30 s of CPU work."""
+    if key not in _ORACLE_SAMPLES:
+        grid = model[-1]
+        r2 = O.grid_coords(grid)[pix]
+        gd = O._gr_arrays(g)
+        central = O.Ray(*(gd[f] for f in O.RAY_FIELDS))
+        _, J = O.jacobian_run_to_end(central, model)
+        ab = O.custom_jacobian_matrix(J)
+        Q1 = O.gaussian_Q_inv(gd["waist_xy"], gd["radii_of_curv"], gd["wavelength"], gd["theta"])
+        k = 2 * np.pi / gd["wavelength"]
+        _ORACLE_SAMPLES[key] = O.propagate_misaligned_gaussian(
+            gd["amplitude"], k * gd["pathlength"], Q1, ab[:, 0:2, 0:2], ab[:, 0:2, 2:4], ab[:, 2:4, 0:2],
+            ab[:, 2:4, 2:4], ab[:, 0:2, 4], ab[:, 2:4, 4], np.stack([gd["x"], gd["y"]], -1),
+            np.stack([gd["dx"], gd["dy"]], -1), k, r2)
+    return _ORACLE_SAMPLES[key]
+
+
+def _sample_pixels(H, W, n_random=1024, n_border=512, bright_from=None, n_bright=512, seed=7):
+    """Flat indices: uniform random pixels, pixels on / next to every tile border of the two kernels (SFU tiles
+    32 x 128, GEMM tiles 128 rows x 64 complex columns, strips of 16) and -- chosen from ``bright_from``, a
+    computed image, only to decide WHERE to look -- pixels among the brightest 2 %."""
+    rng = np.random.default_rng(seed)
+    pix = [rng.integers(0, H * W, n_random)]
+    rows = np.array([r for b in range(0, H + 1, 32) for r in (b - 1, b) if 0 <= r < H])
+    cols = np.array([c for b in range(0, W + 1, 16) for c in (b - 1, b) if 0 <= c < W])
+    pix.append(rng.choice(rows, n_border // 2) * W + rng.integers(0, W, n_border // 2))
+    pix.append(rng.integers(0, H, n_border // 2) * W + rng.choice(cols, n_border // 2))
+    if bright_from is not None:
+        a = np.abs(bright_from).reshape(-1)
+        top = np.argpartition(a, -(H * W // 50))[-(H * W // 50):]
+        pix.append(rng.choice(top, n_bright))
+    return np.unique(np.concatenate(pix))
+
+
+def test_c2_full_size_tensor_path_vs_oracle(torch_cuda):
+    """BASELINE C2 (1e4 beamlets x 1024^2) on the HEADLINE path -- fp16 x 3 tcgen05 GEMM, every tile a stream-K
+    tile -- against the oracle itself on > 2048 sampled pixels (round 1 compared it with the SFU image)."""
+    from temgymcore_b200.gaussian import make_gaussian_image_device
+    g, model = M.aperture_diffraction_case(10_000, (1024, 1024))
+    gd = gaussian_to_cuda(torch_cuda, g)
+    for method in ("tensor", "auto", "tensor_tf32"):
+        img = to_np(make_gaussian_image_device(gd, model, cull_bits=0, method=method))
+        pix = _sample_pixels(1024, 1024, bright_from=img if method == "tensor" else None)
+        ref = _oracle_at_pixels(("c2", len(pix)), g, model, pix)
+        err = rel_l2(img.reshape(-1)[pix], ref)
+        assert len(pix) >= 2048 and err < FIELD_TOL, (method, err)
+
+
+@pytest.mark.parametrize("variant", ["separable", "general"])
+def test_c3_full_size_vs_oracle(torch_cuda, variant):
+    """BASELINE C3 at FULL size (1e5 beamlets x 2048^2 = 4.2e11 nominal evaluations) against the oracle on
+    > 2048 sampled pixels: seven accumulating GEMM batches, 1e5-term fp32 -> fp64 flushes and the gather mode
+    of the culled SFU kernel at 1e5 beamlets, through `tensor`, culled `sfu`, `auto`, and SURVEY 8d's
+    non-separable variant (rotated astigmatic beamlets on a rotated detector: culled SFU kernel only)."""
+    from temgymcore_b200.gaussian import make_gaussian_image_device
+    general = variant == "general"
+    g, model = M.biprism_case(100_000, (2048, 2048), general=general)
+    gd = gaussian_to_cuda(torch_cuda, g)
+    first = to_np(make_gaussian_image_device(gd, model))                      # API defaults: auto, 40-bit culling
+    pix = _sample_pixels(2048, 2048, bright_from=first)
+    assert len(pix) >= 2048
+    ref = _oracle_at_pixels(("c3", variant), g, model, pix)
+    errs = {"auto": rel_l2(first.reshape(-1)[pix], ref)}
+    del first
+    runs = [("sfu_culled", dict(method="sfu"))]
+    if not general:
+        runs += [("tensor", dict(method="tensor", cull_bits=0)), ("auto_dense", dict(method="auto", cull_bits=0))]
+    for name, kw in runs:
+        img = to_np(make_gaussian_image_device(gd, model, **kw))
+        errs[name] = rel_l2(img.reshape(-1)[pix], ref)
+        del img
+    assert all(e < FIELD_TOL for e in errs.values()), errs
+
+
 def test_c3_culling_consistency(torch_cuda):
     """Config C3 geometry (narrow envelopes): the tile-culled sum equals the dense sum and
     executes far fewer evaluations."""
@@ -486,7 +572,8 @@ def _tf32_split(torch, x):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 512), (256, 384, 1536), (200, 136, 1000),
-                                   (1024, 256, 4100), (77, 50, 36), (1536, 2304, 300), (1024, 2048, 2000)])
+                                   (1024, 256, 4100), (77, 50, 36), (1536, 2304, 300), (1024, 2048, 2000),
+                                   (256, 2048, 12000), (200, 300, 5000)])
 def test_gemm_tf32x3_against_fp64(torch_cuda, M, N, K):
     import ctypes as C
     from temgymcore_b200 import _lib as L
@@ -523,7 +610,10 @@ def _f16_split(torch, x):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 512), (256, 384, 1536), (200, 136, 1000),
-                                   (1024, 256, 4100), (77, 50, 36), (1536, 2304, 300), (1024, 2048, 2000)])
+                                   (1024, 256, 4100), (77, 50, 36), (1536, 2304, 300), (1024, 2048, 2000),
+                                   # stream-K: every tile split (C2 shape), a rank's row shard (16 tiles x ~9
+                                   # pieces), three data-parallel waves + a split remainder, ragged edges + split
+                                   (1024, 2048, 20000), (128, 2048, 20000), (2048, 4096, 4096), (200, 300, 5000)])
 def test_gemm_f16x3_against_fp64(torch_cuda, M, N, K):
     from temgymcore_b200 import _lib as L
     torch = torch_cuda
@@ -551,6 +641,51 @@ def test_gemm_f16x3_against_fp64(torch_cuda, M, N, K):
                            D.data_ptr(), N + 3, 1, st)
     L.check(rc, "tg_gemm_f16x3 accumulate")
     assert float((D[:, :N] - 2 * ref).norm() / ref.norm()) < 4e-6
+
+
+def test_gemm_streamk_is_deterministic(torch_cuda):
+    """Stream-K pieces of a tile are combined by the last piece to arrive, in slot order -- not in arrival
+    order: repeated runs are bit-identical."""
+    from temgymcore_b200 import _lib as L
+    torch = torch_cuda
+    lib = L.load()
+    M_, N_, K_ = 384, 2048, 16000
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.rand((M_, K_), generator=gen, device="cuda") * 2 - 1
+    B = torch.rand((N_, K_), generator=gen, device="cuda") * 2 - 1
+    Ah, Al = _f16_split(torch, A)
+    Bh, Bl = _f16_split(torch, B)
+    outs = []
+    for _ in range(4):
+        D = torch.empty((M_, N_), dtype=torch.float64, device="cuda")
+        L.check(lib.tg_gemm_f16x3(M_, N_, K_, Ah.data_ptr(), Al.data_ptr(), Bh.data_ptr(), Bl.data_ptr(), K_,
+                                  D.data_ptr(), N_, 0, torch.cuda.current_stream().cuda_stream), "tg_gemm_f16x3")
+        outs.append(D)
+    assert all(bool(torch.equal(outs[0], o)) for o in outs[1:])
+    ref = A.double() @ B.double().T
+    assert float((outs[0] - ref).norm() / ref.norm()) < 3e-6
+
+
+@pytest.mark.parametrize("method", ["auto", "sfu", "tensor"])
+def test_host_pipeline_row_blocks(torch_cuda, method):
+    """The host-buffer call computes the image in row blocks and copies each finished block to the host while
+    the next is computed (tg_make_gaussian_image_host): same image as the device path, for a height that is
+    not a multiple of the block, complex64 output, a row range, and inputs packed into one pinned slab."""
+    from temgymcore_b200.gaussian import (make_gaussian_image_device, make_gaussian_image_host,
+                                          pack_beamlets_pinned)
+    g, model = M.aperture_diffraction_case(700, (640, 384))
+    dev_img = to_np(make_gaussian_image_device(gaussian_to_cuda(torch_cuda, g), model, cull_bits=0, method=method))
+    host_img = to_np(make_gaussian_image_host(g, model, cull_bits=0, method=method))
+    assert host_img.shape == (640, 384) and rel_l2(host_img, dev_img) < 1e-6
+    gp = pack_beamlets_pinned(g)
+    assert gp.y.ctypes.data == gp.x.ctypes.data + 8 * 700          # one slab, upload order
+    packed = to_np(make_gaussian_image_host(gp, model, cull_bits=0, method=method))
+    np.testing.assert_array_equal(packed, host_img)
+    c64 = to_np(make_gaussian_image_host(gp, model, cull_bits=0, method=method, out_dtype=torch_cuda.complex64,
+                                         row0=96, nrows=300))
+    assert c64.dtype == np.complex64 and rel_l2(c64, dev_img[96:396]) < 1e-6
+    ref = O.make_gaussian_image(g, model)
+    assert rel_l2(host_img, ref) < FIELD_TOL
 
 
 @pytest.mark.parametrize("method", ["tensor", "tensor_tf32"])
@@ -648,6 +783,27 @@ def test_run_with_grads(torch_cuda, goldens):
             close(getattr(gall[(rays, fin)], fout), J7[:, i, j])
     with pytest.raises(RuntimeError):
         run_with_grads(rays, model, [M.readme_model()[0].params.focal_length])  # not in this model
+
+
+def test_run_with_grads_container_reference(torch_cuda):
+    """A reference to a whole DescanError node gives one Jacobian per leaf, keyed (descanner, 'descan_error', i)
+    (this used to return a single all-zero Ray)."""
+    from temgymcore_b200.components import DescanError
+    from temgymcore_b200.run import run_with_grads
+    rays = M.random_rays(257)
+    model = M.kitchen_sink_model()
+    desc = model[8]
+    _, gnode = run_with_grads(rays, model, [desc.params.descan_error])
+    assert len(gnode) == 12
+    names = DescanError._fields
+    _, gleaf = run_with_grads(rays, model, [getattr(desc.params.descan_error, n) for n in names])
+    nonzero = 0
+    for i, n in enumerate(names):
+        a, b = gnode[(desc, "descan_error", i)], gleaf[(desc, "descan_error", n)]
+        for f in ("x", "y", "dx", "dy", "z", "pathlength", "_one"):
+            np.testing.assert_array_equal(np.asarray(getattr(a, f)), np.asarray(getattr(b, f)))
+        nonzero += int(np.abs(np.asarray(a.x)).max() > 0 or np.abs(np.asarray(a.dx)).max() > 0)
+    assert nonzero >= 10
 
 
 def test_run_with_grads_krivanek_coefficients(torch_cuda):

@@ -102,6 +102,24 @@ def test_param_refs():
     assert lens.new_with(focal_length=2.0).focal_length == 2.0
 
 
+def test_container_param_refs_expand_into_leaves():
+    """``descanner.params.descan_error`` / ``lens.params.coeffs`` stand for all their leaves, keyed by leaf index
+    (the reference's PathBuilder._find_in, tree_utils.py:100-122)."""
+    from temgymcore_b200.aberrations import KrivanekCoeffs
+    from temgymcore_b200.components import AberratedLensKrivanek, Descanner, DescanError
+    from temgymcore_b200.run import _expand_param_leaves
+    d = Descanner(z=0.0, scan_pos_x=1.5, scan_pos_y=-2.0, descan_error=DescanError(*np.arange(12.0)))
+    leaves = _expand_param_leaves(d, ("descan_error",))
+    assert [s for s, _ in leaves] == [(i,) for i in range(12)]
+    assert leaves[1][1] == ("descan_error", "pxo_pyi")
+    assert all(len(d._tg_param_seeds(leaf)) == 1 for _, leaf in leaves)      # every leaf reaches the kernel
+    assert _expand_param_leaves(d, ("scan_pos_x",)) == [((), ("scan_pos_x",))]
+    lens = AberratedLensKrivanek(z=0.0, focal_length=1e-3, coeffs=KrivanekCoeffs(C30=1.0))
+    cl = _expand_param_leaves(lens, ("coeffs",))
+    assert len(cl) == 25 and cl[0][0] == (0,) and all(lens._tg_param_seeds(leaf) for _, leaf in cl)
+    assert _expand_param_leaves(lens, ("nope",)) == [((), ("nope",))]       # _tg_param_seeds raises for it
+
+
 def test_reference_utils_helpers():
     """Host-side helpers of the reference's utils.py / gaussian.py that sit beside the hot path."""
     from temgymcore_b200 import utils as U
