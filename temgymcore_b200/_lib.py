@@ -87,7 +87,7 @@ SIGNATURES = {
                                           _vp, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "tg_gemm_tf32x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
     "tg_gemm_f16x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
-    "tg_gemm_schedule": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "tg_gemm_schedule": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "tg_peer_alloc": (_i32, [C.c_uint64, C.POINTER(_vp), _vp]),
     "tg_peer_open": (_i32, [_vp, C.POINTER(_vp)]),
     "tg_peer_close": (_i32, [_vp]),

@@ -709,7 +709,16 @@ int make_map(CUtensorMap *m, const void *base, long long rows, long long K, long
 // Host side of the work decomposition (see SkSched).  Stream-K is used when it pays: the tiles do not fill
 // whole waves of the `sms` CTAs and K is deep enough (>= 8 chunks per tile) for the pieces to amortise
 // their partial-tile round trip.  TG_GEMM_STREAMK=0 forces the plain one-tile-at-a-time schedule (A/B runs).
-SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms) {
+int streamk_mode_default() {
+  static const int mode = [] {
+    const char *e = getenv("TG_GEMM_STREAMK");
+    const int v = e ? atoi(e) : 1;
+    return (v >= 0 && v <= 2) ? v : 1;
+  }();
+  return mode;
+}
+SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode = -1) {
+  if (mode < 0 || mode > 2) mode = streamk_mode_default();
   SkSched s;
   const int tiles_m = (M + BM - 1) / BM;
   s.tiles_n = (Np + BN - 1) / BN;
@@ -722,11 +731,15 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms) {
   s.Tl = 0;
   s.qh = 1;
   s.maxparts = 1;
-  static const bool allow = [] {
-    const char *e = getenv("TG_GEMM_STREAMK");
-    return !(e && atoi(e) == 0);
-  }();
-  if (allow && s.nch >= 8 && sms > 1) {
+  // TG_GEMM_STREAMK: 0 = never split, 2 = split whenever the tiles leave a partial wave (experiments); default
+  // 1 = split only when whole tiles would leave more than 30 % of the machine idle.  Measured on B200 (fp16 x 3,
+  // N = 2048, K = 20000): 1024 rows (128 tiles, 86 % of a wave) 0.212 ms whole tiles vs 0.27 ms split -- the
+  // 20 extra SMs do not pay for the partial-tile traffic and the helpers' out-of-step operand reads; 512 rows
+  // 0.197 -> 0.126 ms, 256 rows 0.203 -> 0.085 ms, 128 rows (the row shard of one of 8 ranks) 0.205 -> 0.065 ms.
+  const double waves = (double)s.T / sms;
+  const double dp_eff = waves / ceil(waves);
+  const bool want = mode == 2 || (mode == 1 && dp_eff < 0.7);
+  if (want && s.nch >= 8 && sms > 1) {
     int G = sms, R = s.T % sms;
     if (s.T < sms) {
       const long long cap = (long long)s.T * s.nch / 4;   // at least ~4 chunks per CTA
@@ -751,6 +764,8 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms) {
     } else if (s.T >= sms) {
       s.G = sms;
     }
+  } else if (s.T >= sms) {
+    s.G = sms;
   }
   return s;
 }
@@ -769,6 +784,7 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
   TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
   TG_CUDA(cudaGetDevice(&dev));
+  tg_tune_mempool(dev);
   static int sms_cache[64] = {0};
   if (dev >= 0 && dev < 64 && sms_cache[dev] > 0) {
     sms = sms_cache[dev];
@@ -865,11 +881,11 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
 // The work decomposition of the persistent GEMM for a given shape, as the kernel's three roles enumerate it
 // (host-side mirror, no device needed): units[6 i..] = {cta, tile, chunk_begin, chunk_end, slot, nparts};
 // sched_out[10] = SkSched fields.  Returns the number of units (written up to max_units), < 0 on error.
-extern "C" int tg_gemm_schedule(int M, int N, int K, int f16, int sms, int32_t *units, int max_units,
+extern "C" int tg_gemm_schedule(int M, int N, int K, int f16, int sms, int mode, int32_t *units, int max_units,
                                 int32_t *sched_out) {
   TG_REQUIRE(M > 0 && N > 0 && K > 0 && sms > 0, "bad GEMM shape");
-  const SkSched s = f16 ? make_sched(M, N, K, GemmCfg<true>::BK, GemmCfg<true>::CHUNK_KB, sms)
-                        : make_sched(M, N, K, GemmCfg<false>::BK, GemmCfg<false>::CHUNK_KB, sms);
+  const SkSched s = f16 ? make_sched(M, N, K, GemmCfg<true>::BK, GemmCfg<true>::CHUNK_KB, sms, mode)
+                        : make_sched(M, N, K, GemmCfg<false>::BK, GemmCfg<false>::CHUNK_KB, sms, mode);
   if (sched_out) {
     const int v[10] = {s.tiles_n, s.T, s.nkb, s.nch, s.G, s.R, s.q, s.Tl, s.qh, s.maxparts};
     for (int i = 0; i < 10; ++i) sched_out[i] = v[i];

@@ -24,21 +24,22 @@ SHAPES = [
 ]
 
 
-def schedule(M, N, K, f16, sms=148):
+def schedule(M, N, K, f16, sms=148, mode=2):
     lib = L.load()
     sched = (C.c_int32 * 10)()
-    n = lib.tg_gemm_schedule(M, N, K, f16, sms, None, 0, sched)
+    n = lib.tg_gemm_schedule(M, N, K, f16, sms, mode, None, 0, sched)
     assert n > 0
     units = np.zeros((n, 6), dtype=np.int32)
-    n2 = lib.tg_gemm_schedule(M, N, K, f16, sms, units.ctypes.data, n, sched)
+    n2 = lib.tg_gemm_schedule(M, N, K, f16, sms, mode, units.ctypes.data, n, sched)
     assert n2 == n
     keys = ("tiles_n", "T", "nkb", "nch", "G", "R", "q", "Tl", "qh", "maxparts")
     return units, dict(zip(keys, list(sched)))
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("M,N,K,f16", SHAPES)
-def test_every_chunk_covered_once(M, N, K, f16):
-    units, s = schedule(M, N, K, f16)
+def test_every_chunk_covered_once(M, N, K, f16, mode):
+    units, s = schedule(M, N, K, f16, mode=mode)
     T, nch = s["T"], s["nch"]
     assert T == -(-M // 128) * -(-N // 128)
     cover = np.zeros((T, nch), dtype=np.int32)
@@ -78,6 +79,20 @@ def test_c2_uses_every_sm_and_heads_walk_in_lockstep():
     assert s["G"] == 148 and s["R"] == 128 and s["maxparts"] <= 3
     heads = units[units[:, 4] == 0]
     assert len(heads) == 128 and (heads[:, 2] == 0).all() and (heads[:, 3] == s["q"]).all()
+
+
+def test_default_policy_splits_only_small_shapes():
+    """mode 1 (the library's default): the full C2 / C3 images keep whole tiles (86 % of a wave: measured faster
+    unsplit), row shards and row blocks are split over all SMs."""
+    for M, expect_split in ((1024, False), (512, True), (256, True), (128, True)):
+        _, s = schedule(M, 2048, 20000, 1, mode=1)
+        assert (s["R"] > 0) == expect_split, (M, s)
+        if expect_split:
+            assert s["G"] == 148
+    _, s = schedule(2048, 4096, 32768, 1, mode=1)
+    assert s["R"] == 0 and s["G"] == 148
+    _, s = schedule(1024, 2048, 20000, 1, mode=0)
+    assert s["R"] == 0 and s["G"] == 128
 
 
 def test_streamk_can_be_disabled_by_shape():

@@ -465,7 +465,7 @@ def _oracle_at_pixels(key, g, model, pix):
     return _ORACLE_SAMPLES[key]
 
 
-def _sample_pixels(H, W, n_random=1024, n_border=512, bright_from=None, n_bright=512, seed=7):
+def _sample_pixels(H, W, n_random=1280, n_border=512, bright_from=None, n_bright=512, seed=7):
     """Flat indices: uniform random pixels, pixels on / next to every tile border of the two kernels (SFU tiles
     32 x 128, GEMM tiles 128 rows x 64 complex columns, strips of 16) and -- chosen from ``bright_from``, a
     computed image, only to decide WHERE to look -- pixels among the brightest 2 %."""
@@ -613,7 +613,8 @@ def _f16_split(torch, x):
                                    (1024, 256, 4100), (77, 50, 36), (1536, 2304, 300), (1024, 2048, 2000),
                                    # stream-K: every tile split (C2 shape), a rank's row shard (16 tiles x ~9
                                    # pieces), three data-parallel waves + a split remainder, ragged edges + split
-                                   (1024, 2048, 20000), (128, 2048, 20000), (2048, 4096, 4096), (200, 300, 5000)])
+                                   (1024, 2048, 20000), (128, 2048, 20000), (2048, 4096, 4096), (200, 300, 5000),
+                                   (1280, 1920, 4096)])   # 150 tiles: one whole wave + 2 split tiles
 def test_gemm_f16x3_against_fp64(torch_cuda, M, N, K):
     from temgymcore_b200 import _lib as L
     torch = torch_cuda
