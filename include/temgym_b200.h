@@ -147,6 +147,20 @@ int tg_trace_jets_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in
 int tg_krivanek_f64(int64_t n, const double *alpha_x, const double *alpha_y, const double coeffs[47],
                     double *W, double *dWx, double *dWy, void *stream);
 
+/* concentric_rings(num_points_approx, radius) (utils.py:117-175; the deterministic disc sampler behind
+ * ParallelBeam / PointSource.make_rays, source.py:58-188) generated on the device: (y, x) of every point, ring
+ * by ring, the running angle sums restarted exactly where the reference's multi_cumsum_inplace restarts them
+ * (utils.py:46-80).  tg_concentric_rings_count gives the number of points N (host arithmetic only); y and x must
+ * hold `capacity` >= N doubles. */
+int64_t tg_concentric_rings_count(int64_t num_points_approx, double radius);
+int tg_concentric_rings_f64(int64_t num_points_approx, double radius, int64_t capacity, double *y, double *x,
+                            void *stream);
+/* decompose_Q_inv(Q_inv, wavelength, eps) (gaussian.py:35-89): principal waists (larger first), radii of
+ * curvature and orientation of n complex 2x2 Q_inv (device, (n,2,2) complex128 interleaved); wavelength is n
+ * doubles, or one when wavelength_is_scalar. */
+int tg_decompose_qinv_f64(int64_t n, const double *Q_inv, const double *wavelength, int wavelength_is_scalar,
+                          double eps, double *waist1, double *waist2, double *radius1, double *radius2,
+                          double *theta, void *stream);
 /* fibonacci_spiral(nb_samples, radius, alpha) (utils.py:297-325) written to device arrays x, y: the
  * beamlet-centre sampler of the aperture / biprism examples, generated on the GPU. */
 int tg_fibonacci_spiral_f64(int64_t n, double radius, double alpha, double *x, double *y, void *stream);

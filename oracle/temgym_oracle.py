@@ -1161,3 +1161,80 @@ def stem4d_backproject(data4d, model_fn, scan_grid, detector, source_xy=(0.0, 0.
     out = np.zeros((Oy, Ox))
     np.add.at(out, (py[ok], px[ok]), vals[ok])
     return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# Callers either side of the path: restated for the parity tests of their device versions
+
+
+def multi_cumsum_inplace(values, partitions, start):
+    """utils.py:46-80, statement for statement (plain loop: small inputs only)."""
+    part_idx = 0
+    current_part_len = partitions[part_idx]
+    part_count = 0
+    values[0] = start
+    for v_idx in range(1, values.size):
+        if current_part_len == part_count:
+            part_count = 0
+            part_idx += 1
+            current_part_len = partitions[part_idx]
+            values[v_idx] = start
+        else:
+            values[v_idx] += values[v_idx - 1]
+            part_count += 1
+
+
+def concentric_rings(num_points_approx, radius):
+    """utils.py:117-175 -> (N, 2) array of (y, x)."""
+    num_rings = max(1, int(np.floor((-1 + np.sqrt(1 + 4 * num_points_approx / np.pi)) / 2)))
+    num_points_kth_ring = np.round(2 * np.pi * np.arange(1, num_rings + 1)).astype(int)
+    num_rings = num_points_kth_ring.size
+    points_per_unit = num_points_approx / num_points_kth_ring.sum()
+    points_per_ring = np.round(num_points_kth_ring * points_per_unit).astype(int)
+    radii = np.linspace(0, radius, num_rings + 1, endpoint=True)[1:]
+    with np.errstate(divide="ignore"):
+        div_angle = 2 * np.pi / points_per_ring
+    params = np.stack((radii, div_angle), axis=0)
+    repeats = points_per_ring.tolist()
+    all_params = np.repeat(params, repeats, axis=-1)
+    if all_params.shape[1]:
+        multi_cumsum_inplace(all_params[1, :], points_per_ring, 0.0)
+    all_radii = all_params[0, :]
+    all_angles = all_params[1, :]
+    return np.stack((all_radii * np.sin(all_angles), all_radii * np.cos(all_angles)), axis=-1)
+
+
+def decompose_Q_inv(Q_inv, wavelength, eps=1e-12):
+    """gaussian.py:35-89 -> (waist1, waist2, R1, R2, theta), larger waist first."""
+    Q_inv = np.asarray(Q_inv, dtype=np.complex128)
+    Sm = np.imag(Q_inv)
+    Sm = 0.5 * (Sm + np.swapaxes(Sm, -1, -2))
+    _, evecs = np.linalg.eigh(Sm)
+
+    def _make_right_handed(E):
+        detE = np.linalg.det(E)
+        flip = np.where(detE < 0, -1.0, 1.0)[..., None]
+        E = E.copy()
+        E[..., :, 1] = E[..., :, 1] * flip
+        return E
+
+    evecs = _make_right_handed(evecs)
+    Qd = np.swapaxes(evecs, -1, -2) @ Q_inv @ evecs
+    qd = np.stack([Qd[..., 0, 0], Qd[..., 1, 1]], axis=-1)
+
+    def _waists_from_diag(q):
+        im = np.imag(q)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.sqrt(np.where(np.abs(im) > eps, np.abs(wavelength / (np.pi * im)), np.inf))
+
+    w = _waists_from_diag(qd)
+    swap = w[..., 0] < w[..., 1]
+    qd = np.where(swap[..., None], qd[..., ::-1], qd)
+    evecs = np.where(swap[..., None, None], evecs[..., :, ::-1], evecs)
+    evecs = _make_right_handed(evecs)
+    w = _waists_from_diag(qd)
+    re = np.real(qd)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        R = np.where(np.abs(re) > eps, 1.0 / re, np.inf)
+    theta = np.arctan2(evecs[..., 1, 0], evecs[..., 0, 0])
+    return w[..., 0], w[..., 1], R[..., 0], R[..., 1], theta

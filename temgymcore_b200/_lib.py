@@ -67,6 +67,9 @@ SIGNATURES = {
                                  _vp, _vp]),
     "tg_krivanek_f64": (_i32, [_i64, _vp, _vp, _dp, _vp, _vp, _vp, _vp]),
     "tg_fibonacci_spiral_f64": (_i32, [_i64, C.c_double, C.c_double, _vp, _vp, _vp]),
+    "tg_concentric_rings_count": (C.c_int64, [_i64, C.c_double]),
+    "tg_concentric_rings_f64": (_i32, [_i64, C.c_double, _i64, _vp, _vp, _vp]),
+    "tg_decompose_qinv_f64": (_i32, [_i64, _vp, _vp, _i32, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tg_transfer_rays_f64": (_i32, [_i64, _vp, _i32, _dp, _vp, _vp]),
     "tg_stem4d_backproject": (_i32, [C.POINTER(C.c_int), _dp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "tg_stem4d_indices": (_i32, [C.POINTER(C.c_int), _dp, _i32, _i32, _vp, _vp]),

@@ -20,6 +20,7 @@ $NVCC $COMMON $VERBOSE             -c "$here/field.cu"    -o "$obj/field.o" & pi
 $NVCC $COMMON $VERBOSE             -c "$here/host_api.cu" -o "$obj/host_api.o" & pids+=($!)
 $NVCC $COMMON $VERBOSE             -c "$here/separable.cu" -o "$obj/separable.o" & pids+=($!)
 $NVCC $COMMON $VERBOSE             -c "$here/peer.cu"     -o "$obj/peer.o" & pids+=($!)
+$NVCC $COMMON $VERBOSE -fmad=false -c "$here/sources.cu"  -o "$obj/sources.o" & pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
-$NVCC $ARCH -shared -o "$out" "$obj/trace.o" "$obj/coeffs.o" "$obj/field.o" "$obj/host_api.o" "$obj/separable.o" "$obj/stem4d.o" "$obj/jets.o" "$obj/peer.o" -cudart static
+$NVCC $ARCH -shared -o "$out" "$obj/trace.o" "$obj/coeffs.o" "$obj/field.o" "$obj/host_api.o" "$obj/separable.o" "$obj/stem4d.o" "$obj/jets.o" "$obj/peer.o" "$obj/sources.o" -cudart static
 echo "built $out"

@@ -60,9 +60,27 @@ def gaussian_beam(x, y, q_inv, k, offset_x=0, offset_y=0):
 
 
 def decompose_Q_inv(Q_inv, wavelength, eps=1e-12):
-    """``(waist_x, waist_y, r_x, r_y, theta)`` from 2x2 complex ``Q_inv`` (batched), host numpy
+    """``(waist_x, waist_y, r_x, r_y, theta)`` from 2x2 complex ``Q_inv`` (batched)
     (gaussian.py:35-89): principal axes from the symmetric imaginary part (``eigh``), right-handed
-    eigenvectors, larger waist first, waists from Im, radii from Re of the rotated diagonal."""
+    eigenvectors, larger waist first, waists from Im, radii from Re of the rotated diagonal.
+    A CUDA tensor is decomposed on its device (``tg_decompose_qinv_f64``, closed-form 2x2 eigenvectors) and the
+    results are CUDA tensors; anything else takes the host numpy route of the reference."""
+    if A.kind_of(Q_inv) == A.KIND_CUDA:
+        import torch
+        lib = L.load()
+        dev = Q_inv.device
+        Qc = Q_inv.to(torch.complex128).contiguous()
+        lead = tuple(Qc.shape[:-2])
+        n = int(np.prod(lead)) if lead else 1
+        wl = A.to_device_f64(wavelength, dev)
+        if wl.numel() not in (1, n):
+            raise ValueError("wavelength must be a scalar or match the batch of Q_inv")
+        outs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(5)]
+        with torch.cuda.device(dev):
+            L.check(lib.tg_decompose_qinv_f64(n, torch.view_as_real(Qc).data_ptr(), wl.data_ptr(),
+                                              int(wl.numel() == 1), float(eps), *[o.data_ptr() for o in outs],
+                                              A.current_stream_ptr(dev)), "tg_decompose_qinv_f64")
+        return tuple(o.reshape(lead) for o in outs)
     Q = np.asarray(_to_np(Q_inv), dtype=np.complex128)
     Sm = np.imag(Q)
     Sm = 0.5 * (Sm + np.swapaxes(Sm, -1, -2))

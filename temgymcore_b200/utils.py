@@ -99,11 +99,32 @@ def fibonacci_spiral(nb_samples: int, radius: float, alpha=2, device=None):
     return rr * np.cos(phi), rr * np.sin(phi)
 
 
-def concentric_rings(num_points_approx: int, radius: float):
+def concentric_rings(num_points_approx: int, radius: float, device=None):
     """Approximately uniform ``(y, x)`` samples on concentric rings of a disc
-    (utils.py:117-175; host-side input preparation, numpy as in the reference).  Ring k holds
-    ~2*pi*k points; the angles of a ring start at 0 and advance by running sums of 2*pi/n_k,
-    like the reference's ``multi_cumsum_inplace`` (utils.py:46-80)."""
+    (utils.py:117-175).  Ring k holds ~2*pi*k points; the angles of a ring start at 0 and advance by running
+    sums of 2*pi/n_k, like the reference's ``multi_cumsum_inplace`` (utils.py:46-80).  Host numpy by default
+    like the reference; with ``device="cuda"`` (or a torch device) the points are generated on the GPU
+    (``tg_concentric_rings_f64``: same ring layout, same running sums) and returned as an ``(N, 2)`` CUDA
+    tensor -- no host staging for 1e6-ray runs."""
+    if device is not None:
+        import torch
+        from . import _arrays as A
+        from . import _lib as L
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError("device must be a CUDA device (omit it for the host sampler)")
+        if dev.index is None:
+            dev = torch.device("cuda", A.current_device_index())
+        lib = L.load()
+        n = int(lib.tg_concentric_rings_count(int(num_points_approx), float(radius)))
+        if n < 0:
+            raise ValueError("bad point count")
+        yx = torch.empty((2, max(n, 1)), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.tg_concentric_rings_f64(int(num_points_approx), float(radius), n, yx[0].data_ptr(),
+                                                yx[1].data_ptr(), A.current_stream_ptr(dev)),
+                    "tg_concentric_rings_f64")
+        return yx[:, :n].T
     import numpy as np
     n_rings = max(1, int(np.floor((-1 + np.sqrt(1 + 4 * num_points_approx / np.pi)) / 2)))
     circumference = np.round(2 * np.pi * np.arange(1, n_rings + 1)).astype(int)

@@ -488,10 +488,12 @@ def test_c2_full_size_tensor_path_vs_oracle(torch_cuda):
     from temgymcore_b200.gaussian import make_gaussian_image_device
     g, model = M.aperture_diffraction_case(10_000, (1024, 1024))
     gd = gaussian_to_cuda(torch_cuda, g)
+    pix = None
     for method in ("tensor", "auto", "tensor_tf32"):
         img = to_np(make_gaussian_image_device(gd, model, cull_bits=0, method=method))
-        pix = _sample_pixels(1024, 1024, bright_from=img if method == "tensor" else None)
-        ref = _oracle_at_pixels(("c2", len(pix)), g, model, pix)
+        if pix is None:
+            pix = _sample_pixels(1024, 1024, bright_from=img)
+        ref = _oracle_at_pixels("c2", g, model, pix)
         err = rel_l2(img.reshape(-1)[pix], ref)
         assert len(pix) >= 2048 and err < FIELD_TOL, (method, err)
 
@@ -865,6 +867,73 @@ def test_transfer_rays(torch_cuda):
     tc = transfer_rays_pt_src((0.5, -0.5), (torch_cuda.as_tensor(dxs, device="cuda"),
                                             torch_cuda.as_tensor(dys, device="cuda")), np.eye(5))
     assert tc.is_cuda and tuple(tc.shape) == (4, 4)
+
+
+@pytest.mark.parametrize("n", [1, 7, 100, 5000, 200_000])
+def test_concentric_rings_device(torch_cuda, n):
+    """concentric_rings generated on the device (tg_concentric_rings_f64) against the oracle's restatement of
+    utils.py:117-175 (ring layout, radii and the lagged restarts of the running angle sums are the same fp64
+    operations; sin / cos are CUDA's libm vs numpy's: 1e-14)."""
+    from temgymcore_b200.utils import concentric_rings
+    ref = O.concentric_rings(n, 3.5e-9)
+    got = to_np(concentric_rings(n, 3.5e-9, device="cuda"))
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-14 * 3.5e-9)
+    np.testing.assert_array_equal(concentric_rings(n, 3.5e-9), ref)          # host sampler: bit-exact
+
+
+def test_make_rays_on_device(torch_cuda):
+    """ParallelBeam / PointSource.make_rays(num, device='cuda') (source.py:58-188): the rays are born on the
+    GPU and go through run_to_end without host staging; same rays as the host path."""
+    from temgymcore_b200.components import Detector, Lens
+    from temgymcore_b200.run import run_to_end
+    from temgymcore_b200.source import ParallelBeam, PointSource
+    for src in (ParallelBeam(z=0.0, radius=2e-7, offset_xy=(1e-8, -3e-8)),
+                PointSource(z=-1e-3, semi_conv=5e-3, offset_xy=(2e-9, 0.0))):
+        host = src.make_rays(3000)
+        dev = src.make_rays(3000, device="cuda")
+        assert dev.x.is_cuda and dev.z == host.z and dev.pathlength == 0.0
+        for f in ("x", "y", "dx", "dy"):
+            np.testing.assert_allclose(to_np(getattr(dev, f)), getattr(host, f), rtol=0, atol=1e-20 + 1e-14 * 5e-3)
+        model = [src, Lens(z=0.01, focal_length=0.02), Detector(z=0.05, pixel_size=(1e-6, 1e-6), shape=(64, 64))]
+        out_d, out_h = run_to_end(dev, model), run_to_end(host, model)
+        for f in ("x", "y", "dx", "dy", "pathlength"):
+            close(to_np(getattr(out_d, f)), np.asarray(getattr(out_h, f)), rtol=1e-11)
+    one = ParallelBeam(z=0.0, radius=1.0).make_rays(1, device="cuda")
+    assert one.x.numel() == ParallelBeam(z=0.0, radius=1.0).generate_array(1).shape[0]
+
+
+def test_decompose_q_inv_device(torch_cuda):
+    """decompose_Q_inv on the device (tg_decompose_qinv_f64, closed-form 2x2 eigenvectors) against the oracle's
+    restatement of gaussian.py:35-89 (numpy eigh): waists, radii, and the axis orientation modulo pi (an
+    eigenvector's sign is arbitrary; isotropic beams have no axis)."""
+    from temgymcore_b200.gaussian import decompose_Q_inv
+    torch = torch_cuda
+    rng = np.random.default_rng(5)
+    n = 4000
+    wl = rng.uniform(1e-12, 5e-12, n)
+    w = rng.uniform(0.5e-9, 3e-9, (n, 2))
+    w[:50, 1] = w[:50, 0]                                  # isotropic
+    R = rng.uniform(-1e-3, 1e-3, (n, 2))
+    R[50:120] = np.inf                                      # flat wavefronts
+    th = rng.uniform(-np.pi / 2, np.pi / 2, n)
+    th[120:150] = 0.0                                       # axis-aligned: zero off-diagonal
+    Q = O.gaussian_Q_inv(w, R, wl, th)
+    ref = O.decompose_Q_inv(Q, wl[:, None])
+    got = decompose_Q_inv(torch.as_tensor(Q, device="cuda"), torch.as_tensor(wl, device="cuda"))
+    assert all(g.is_cuda for g in got)
+    got = [to_np(g) for g in got]
+    for k in range(4):
+        fin = np.isfinite(ref[k])
+        np.testing.assert_array_equal(np.isfinite(got[k]), fin)
+        np.testing.assert_allclose(got[k][fin], ref[k][fin], rtol=1e-9)
+    aniso = np.abs(ref[0] - ref[1]) > 1e-6 * ref[0]
+    np.testing.assert_allclose(np.cos(2 * got[4][aniso]), np.cos(2 * ref[4][aniso]), atol=1e-7)
+    np.testing.assert_allclose(np.sin(2 * got[4][aniso]), np.sin(2 * ref[4][aniso]), atol=1e-7)
+    # scalar wavelength, batch shape kept
+    g2 = decompose_Q_inv(torch.as_tensor(Q[:6].reshape(2, 3, 2, 2), device="cuda"), 2e-12)
+    assert tuple(g2[0].shape) == (2, 3)
+    np.testing.assert_allclose(to_np(g2[0]).reshape(-1), O.decompose_Q_inv(Q[:6], 2e-12)[0], rtol=1e-9)
 
 
 def test_decompose_q_inv_round_trip(torch_cuda):

@@ -102,6 +102,28 @@ def test_param_refs():
     assert lens.new_with(focal_length=2.0).focal_length == 2.0
 
 
+def test_oracle_restates_ring_sampler_and_decomposition():
+    """The oracle's concentric_rings / decompose_Q_inv (restatements of utils.py:117-175 and gaussian.py:35-89,
+    used to check the device versions) agree with the package's host versions: the ring sampler bit for bit
+    (including multi_cumsum_inplace's lagged restarts), the decomposition to rounding."""
+    from oracle import temgym_oracle as O
+    from temgymcore_b200 import _lib as L
+    from temgymcore_b200.gaussian import decompose_Q_inv
+    from temgymcore_b200.utils import concentric_rings
+    for n in (1, 2, 7, 50, 1234, 20000):
+        ref = O.concentric_rings(n, 2.5)
+        np.testing.assert_array_equal(concentric_rings(n, 2.5), ref)
+        assert L.load().tg_concentric_rings_count(n, 2.5) == ref.shape[0]
+    rng = np.random.default_rng(3)
+    n = 300
+    wl = rng.uniform(1e-12, 5e-12, n)
+    Q = O.gaussian_Q_inv(rng.uniform(0.5e-9, 3e-9, (n, 2)), rng.uniform(-1e-3, 1e-3, (n, 2)), wl,
+                         rng.uniform(-1.5, 1.5, n))
+    a, b = O.decompose_Q_inv(Q, wl[:, None]), decompose_Q_inv(Q, wl[:, None])   # broadcasts like the reference
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(x, y, rtol=1e-12, atol=1e-15)
+
+
 def test_container_param_refs_expand_into_leaves():
     """``descanner.params.descan_error`` / ``lens.params.coeffs`` stand for all their leaves, keyed by leaf index
     (the reference's PathBuilder._find_in, tree_utils.py:100-122)."""
