@@ -64,7 +64,9 @@ template <bool F16> struct GemmCfg {
   static constexpr int BK = BK_BYTES / ELEM;             // k-elements per k-block (64 fp16 / 32 tf32)
   static constexpr int CHUNK_KB = CHUNK_K / BK;          // k-blocks per accumulation chunk
 };
-constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_THREADS = 384;                // real formulation: 4 service warps + 8 epilogue warps
+constexpr int GEMM_THREADS_GAUSS = 640;          // complex 3-product formulation: 4 + 16 epilogue warps
+constexpr int KCH = 128;                         // beamlets per K'' group of the 3-product layout (= CHUNK_K)
 constexpr int ACC_COLS = 2 * BN;                // one accumulator = [A_hi B_hi | A_hi B_lo + A_lo B_hi], fp32
 constexpr int TMEM_COLS = 2 * ACC_COLS;         // double-buffered: all 512 TMEM columns
 
@@ -245,8 +247,17 @@ struct SkIter {
 // power of two that undoes the pre-scaling of the factors.
 // scratch / counters: stream-K partial tiles (sched.R * sched.maxparts slots of 128 x 128 floats) and one
 // arrival counter per (stream-K tile, epilogue warp), zero on entry and zero again on exit.
-template <bool F16>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+//
+// GAUSS = true: COMPLEX product with three real multiplications per term.  The operands hold, per group of 128
+// beamlets, three blocks of 128 k-elements each (row factors A: Ur + Ui | Ur | Ui, column factors B: Vr | Vi - Vr |
+// Vr + Vi), so accumulation chunk ch of a tile is the real product k_j, j = ch mod 3, of one beamlet group:
+//     k1 = (Ur + Ui) Vr,  k2 = Ur (Vi - Vr),  k3 = Ui (Vr + Vi);   Re(U V) = k1 - k3,  Im(U V) = k1 + k2.
+// The tensor cores run the same real GEMM over K'' = 3 nb (instead of 4 nb real multiply-adds per complex
+// term: 25 % less tensor work, same operand bytes); the epilogue adds each drained chunk into the (re, im)
+// registers with the signs above.  A tile is 128 rows x 128 COMPLEX columns (Np = complex columns, the output row
+// holds 2 Np doubles), 16 epilogue warps of 32 complex columns each.
+template <bool F16, bool GAUSS>
+__global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
     gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    int M, int Np, int K, double *__restrict__ out, long long ldo, int accumulate_out,
@@ -273,7 +284,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       tg_mbar_init(&ctl->tmem_full[a], 1);
-      tg_mbar_init(&ctl->tmem_empty[a], 8);  // one arrive per epilogue warp
+      tg_mbar_init(&ctl->tmem_empty[a], GAUSS ? 16 : 8);  // one arrive per epilogue warp
     }
     tg_fence_mbar_init();
   }
@@ -356,7 +367,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: 8 warps; warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half
+    // ===== epilogue.  REAL: 8 warps; warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half (64 real
+    // columns).  GAUSS: 16 warps; (warp-4)/4 selects 32 of the 128 complex columns; accum = re[32] | im[32].
+    constexpr int NE = GAUSS ? 16 : 8;
+    constexpr int PART_FLOATS = NE * 2048;               // one stream-K partial tile: [warp][64][lane]
     const int q = warp & 3, h = (warp - 4) >> 2, ew = warp - 4;
     const double sc = peak_key ? scalbn(1.0, (int)(tg_prescale_G(*peak_key) - 2.0 * headroom)) : 1.0;
     float accum[64];
@@ -370,20 +384,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const int nchunks = (kb1 - kb0 + CHUNK_KB - 1) / CHUNK_KB;
 #pragma unroll
       for (int i = 0; i < 64; ++i) accum[i] = 0.f;
+      int j3 = u.ch0 % 3;                                 // GAUSS: which of k1, k2, k3 the next chunk is
       for (int ch = 0; ch < nchunks; ++ch, ++chn) {
         const int acc = (int)(chn & 1u);
         tg_mbar_wait(&ctl->tmem_full[acc], (chn >> 1) & 1u);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + h * 64);
-        float v[32];
+        if constexpr (!GAUSS) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + h * 64);
+          float v[32];
 #pragma unroll
-        for (int part = 0; part < 2; ++part) {   // hi*hi columns, then the cross-term columns
-          tc_ld32(taddr + part * BN, v);
+          for (int part = 0; part < 2; ++part) {   // hi*hi columns, then the cross-term columns
+            tc_ld32(taddr + part * BN, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) accum[i] += v[i];
-          tc_ld32(taddr + part * BN + 32, v);
+            for (int i = 0; i < 32; ++i) accum[i] += v[i];
+            tc_ld32(taddr + part * BN + 32, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) accum[32 + i] += v[i];
+            for (int i = 0; i < 32; ++i) accum[32 + i] += v[i];
+          }
+        } else {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + h * 32);
+          float v[32], w[32];
+          tc_ld32(taddr, v);                       // hi*hi
+          tc_ld32(taddr + BN, w);                  // cross terms
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += w[i];
+          if (j3 == 0) {                           // k1: + re, + im
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { accum[i] += v[i]; accum[32 + i] += v[i]; }
+          } else if (j3 == 1) {                    // k2: + im
+#pragma unroll
+            for (int i = 0; i < 32; ++i) accum[32 + i] += v[i];
+          } else {                                 // k3: - re
+#pragma unroll
+            for (int i = 0; i < 32; ++i) accum[i] -= v[i];
+          }
+          j3 = j3 == 2 ? 0 : j3 + 1;
         }
         tc_fence_before();
         __syncwarp();
@@ -392,8 +427,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       if (u.nparts > 1) {
         // stream-K piece: park the fp32 partial ([slot][epilogue warp][column][lane]: coalesced), count the
         // arrival; the last piece of this tile sums the slots in slot order (fp32, like the chunk sums)
-        float *slot0 = scratch + ((size_t)u.tile * sched.maxparts) * (size_t)(BM * BN) + (size_t)ew * 2048 + lane;
-        float *mine = slot0 + (size_t)u.slot * (size_t)(BM * BN);
+        float *slot0 = scratch + ((size_t)u.tile * sched.maxparts) * (size_t)PART_FLOATS + (size_t)ew * 2048 + lane;
+        float *mine = slot0 + (size_t)u.slot * (size_t)PART_FLOATS;
 #pragma unroll
         for (int i = 0; i < 64; ++i) __stcg(mine + i * 32, accum[i]);
         __threadfence();
@@ -401,45 +436,75 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         unsigned int prev = 0;
         if (lane == 0) {
           __threadfence();
-          prev = atomicAdd(counters + u.tile * 8 + ew, 1u);
+          prev = atomicAdd(counters + u.tile * NE + ew, 1u);
         }
         prev = __shfl_sync(0xffffffffu, prev, 0);
         if (prev != (unsigned)(u.nparts - 1)) continue;   // not the last piece
         __threadfence();
-        if (lane == 0) counters[u.tile * 8 + ew] = 0u;    // leave the counters clean for the next launch
+        if (lane == 0) counters[u.tile * NE + ew] = 0u;   // leave the counters clean for the next launch
 #pragma unroll
         for (int i = 0; i < 64; ++i) accum[i] = 0.f;
         for (int s = 0; s < u.nparts; ++s) {
-          const float *src = slot0 + (size_t)s * (size_t)(BM * BN);
+          const float *src = slot0 + (size_t)s * (size_t)PART_FLOATS;
 #pragma unroll
           for (int i = 0; i < 64; ++i) accum[i] += __ldcg(src + i * 32);
         }
       }
       const int row = m0 + q * 32 + lane;
       if (row < M) {
-        double *o = out + (long long)row * ldo + n0 + h * 64;
-        const int ncol = min(64, Np - (n0 + h * 64));
-        if (ncol == 64 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+        if constexpr (!GAUSS) {
+          double *o = out + (long long)row * ldo + n0 + h * 64;
+          const int ncol = min(64, Np - (n0 + h * 64));
+          if (ncol == 64 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-          for (int i = 0; i < 64; i += 2) {
-            double2 w = make_double2((double)accum[i] * sc, (double)accum[i + 1] * sc);
-            if (accumulate_out) {
-              const double2 p = *reinterpret_cast<double2 *>(o + i);
-              w.x += p.x;
-              w.y += p.y;
+            for (int i = 0; i < 64; i += 2) {
+              double2 w = make_double2((double)accum[i] * sc, (double)accum[i + 1] * sc);
+              if (accumulate_out) {
+                const double2 p = *reinterpret_cast<double2 *>(o + i);
+                w.x += p.x;
+                w.y += p.y;
+              }
+              *reinterpret_cast<double2 *>(o + i) = w;
+              // row-sharded multi-GPU sum: the same values go straight into the peers' images (NVLink P2P stores)
+              for (int p = 0; p < peers.n; ++p)
+                *reinterpret_cast<double2 *>(static_cast<double *>(peers.ptr[p]) + (o - out) + i) = w;
             }
-            *reinterpret_cast<double2 *>(o + i) = w;
-            // row-sharded multi-GPU sum: the same values go straight into the peers' images (NVLink P2P stores)
-            for (int p = 0; p < peers.n; ++p)
-              *reinterpret_cast<double2 *>(static_cast<double *>(peers.ptr[p]) + (o - out) + i) = w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i)
+              if (i < ncol) {
+                const double wv = (accumulate_out ? o[i] : 0.0) + (double)accum[i] * sc;
+                o[i] = wv;
+                for (int p = 0; p < peers.n; ++p) (static_cast<double *>(peers.ptr[p]) + (o - out))[i] = wv;
+              }
           }
         } else {
+          // complex columns n0 + 32 h + i: (re, im) pairs, 16-byte aligned when the output base and pitch are
+          const int c0 = n0 + h * 32;
+          double *o = out + (long long)row * ldo + 2 * (long long)c0;
+          const int ncol = min(32, Np - c0);
+          const bool al = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
+          for (int i = 0; i < 32; ++i)
             if (i < ncol) {
-              const double wv = (accumulate_out ? o[i] : 0.0) + (double)accum[i] * sc;
-              o[i] = wv;
-              for (int p = 0; p < peers.n; ++p) (static_cast<double *>(peers.ptr[p]) + (o - out))[i] = wv;
+              double2 w = make_double2((double)accum[i] * sc, (double)accum[32 + i] * sc);
+              if (accumulate_out) {
+                w.x += o[2 * i];
+                w.y += o[2 * i + 1];
+              }
+              if (al) {
+                *reinterpret_cast<double2 *>(o + 2 * i) = w;
+                for (int p = 0; p < peers.n; ++p)
+                  *reinterpret_cast<double2 *>(static_cast<double *>(peers.ptr[p]) + (o - out) + 2 * i) = w;
+              } else {
+                o[2 * i] = w.x;
+                o[2 * i + 1] = w.y;
+                for (int p = 0; p < peers.n; ++p) {
+                  double *po = static_cast<double *>(peers.ptr[p]) + (o - out) + 2 * i;
+                  po[0] = w.x;
+                  po[1] = w.y;
+                }
+              }
             }
         }
       }
