@@ -275,6 +275,8 @@ int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6],
 #define TG_METHOD_SFU 1    /* tg_field_sum_grid */
 #define TG_METHOD_TENSOR 2 /* tg_field_sum_separable (TG_ENOTSEPARABLE if it does not apply): fp16 x 3 */
 #define TG_METHOD_TENSOR_TF32 3 /* the same GEMM with tf32 x 3 operands (fp32 exponent range, half the rate) */
+#define TG_METHOD_TENSOR_4M 4   /* fp16 x 3 with four real multiplications per complex term (the real GEMM on
+                                   interleaved re/im operands); TG_METHOD_TENSOR uses three (Gauss) */
 int tg_field_sum(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                  int nrows, void *out, int out_is_c128, int cull_bits, int method, void *stream);
 
@@ -293,6 +295,15 @@ int tg_gemm_f16x3(int M, int N, int K, const void *A_hi, const void *A_lo, const
                   const void *B_lo, long long ldk, double *D, long long ldd, int accumulate,
                   void *stream);
 
+/* Complex product with THREE real multiplications per term (Gauss): D[m, c] (+)= sum_n U[m, n] V[c, n], D (M, N)
+ * complex128 as interleaved doubles (row pitch ldd doubles).  Operands in the 3-product layout the field sum
+ * builds for its tensor path: per group g of 128 terms, k-elements [384 g, 384 g + 384) of a row hold
+ * Ur + Ui | Ur | Ui (A) resp. Vr | Vi - Vr | Vr + Vi (B), each as fp16 hi and lo parts; K3 = 384 * groups.
+ * Re = k1 - k3, Im = k1 + k2 with k1 = (Ur + Ui) Vr, k2 = Ur (Vi - Vr), k3 = Ui (Vr + Vi): 25 % less tensor work
+ * than the 4-multiplication real GEMM (tg_gemm_f16x3 on the interleaved layout).  Exposed for testing. */
+int tg_gemm_chunk_k(void); /* terms per group of the 3-product layout (= k-elements per TMEM drain): 128 */
+int tg_cgemm3_f16x3(int M, int N, int K3, const void *A_hi, const void *A_lo, const void *B_hi, const void *B_lo,
+                    long long ldk, double *D, long long ldd, int accumulate, void *stream);
 /* The GEMM is one persistent kernel (one CTA per SM): whole 128 x 128 tiles per CTA while they fill waves of
  * `sms` CTAs, and a stream-K split of the remaining tiles (or of ALL tiles when the problem has fewer tiles
  * than SMs, e.g. the row shard of one rank of a multi-GPU field sum) so that every SM gets the same amount of

@@ -10,7 +10,7 @@ import os
 from typing import Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtemgym_b200.so")
+LIB_PATH = os.environ.get("TG_LIB_PATH") or os.path.join(_HERE, "libtemgym_b200.so")   # TG_LIB_PATH: experiment builds
 
 TG_MAX_PEERS = 8
 TG_MAX_COMPS = 24
@@ -21,7 +21,7 @@ TG_OP_KRIVANEK, TG_OP_OFFSET, TG_OP_THICKLENS, TG_OP_ROTATOR = 4, 5, 6, 7
 TG_F_NOPROP = 1
 TG_F_DIST = 2
 TG_JAC_NONE, TG_JAC_ABCD5, TG_JAC_FULL7 = 0, 1, 2
-TG_METHOD = {"auto": 0, "sfu": 1, "tensor": 2, "tensor_tf32": 3}
+TG_METHOD = {"auto": 0, "sfu": 1, "tensor": 2, "tensor_tf32": 3, "tensor_4m": 4}
 TG_OK, TG_EINVAL, TG_ECUDA, TG_ENOTSEPARABLE, TG_EUNSUPPORTED = 0, -1, -2, -3, -4
 
 
@@ -90,6 +90,8 @@ SIGNATURES = {
                                           _vp, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "tg_gemm_tf32x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
     "tg_gemm_f16x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
+    "tg_gemm_chunk_k": (_i32, []),
+    "tg_cgemm3_f16x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
     "tg_gemm_schedule": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "tg_peer_alloc": (_i32, [C.c_uint64, C.POINTER(_vp), _vp]),
     "tg_peer_open": (_i32, [_vp, C.POINTER(_vp)]),

@@ -4,12 +4,12 @@
 set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 root="$(cd "$here/../.." && pwd)"
-out="$here/../libtemgym_b200.so"
-obj="$here/_obj"
+out="${TG_BUILD_OUT:-$here/../libtemgym_b200.so}"   # TG_BUILD_OUT / TG_BUILD_DEFS: experiment builds
+obj="$here/_obj${TG_BUILD_TAG:-}"
 mkdir -p "$obj"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$root/include -I$here $ARCH"
+COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$root/include -I$here $ARCH ${TG_BUILD_DEFS:-}"
 VERBOSE="${TG_PTXAS_V:+-Xptxas -v}"
 pids=()
 $NVCC $COMMON $VERBOSE -fmad=false -c "$here/trace.cu"    -o "$obj/trace.o" & pids+=($!)

@@ -58,7 +58,10 @@ static_assert(BK_BYTES == 128 || BK_BYTES == 64, "k-block = one 128-byte or 64-b
 constexpr int STAGES = 384 / BK_BYTES;          // 3 or 6 stages of 4 tiles: 192 KiB
 constexpr int TILE_BYTES = BM * BK_BYTES;       // 16 or 8 KiB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;     // A_hi, A_lo, B_hi, B_lo
-constexpr int CHUNK_K = 128;                    // k-elements per TMEM accumulation chunk
+#ifndef TG_CHUNK_K
+#define TG_CHUNK_K 128
+#endif
+constexpr int CHUNK_K = TG_CHUNK_K;             // k-elements per TMEM accumulation chunk (multiple of 64)
 template <bool F16> struct GemmCfg {
   static constexpr int ELEM = F16 ? 2 : 4;               // operand bytes
   static constexpr int BK = BK_BYTES / ELEM;             // k-elements per k-block (64 fp16 / 32 tf32)
@@ -66,7 +69,7 @@ template <bool F16> struct GemmCfg {
 };
 constexpr int GEMM_THREADS = 384;                // real formulation: 4 service warps + 8 epilogue warps
 constexpr int GEMM_THREADS_GAUSS = 640;          // complex 3-product formulation: 4 + 16 epilogue warps
-constexpr int KCH = 128;                         // beamlets per K'' group of the 3-product layout (= CHUNK_K)
+constexpr int KCH = CHUNK_K;                     // beamlets per K'' group of the 3-product layout: one chunk per block
 constexpr int ACC_COLS = 2 * BN;                // one accumulator = [A_hi B_hi | A_hi B_lo + A_lo B_hi], fp32
 constexpr int TMEM_COLS = 2 * ACC_COLS;         // double-buffered: all 512 TMEM columns
 
@@ -127,6 +130,20 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float *v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -403,20 +420,23 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
           }
         } else {
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + h * 32);
-          float v[32], w[32];
-          tc_ld32(taddr, v);                       // hi*hi
-          tc_ld32(taddr + BN, w);                  // cross terms
+          // 16 columns at a time, hi*hi then the cross terms: 64 accumulators + 16 loaded values stay inside the
+          // 102-register budget of a 640-thread CTA (32-column loads of both parts spilled 1 KB per thread)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += w[i];
-          if (j3 == 0) {                           // k1: + re, + im
+          for (int pc = 0; pc < 4; ++pc) {
+            float v[16];
+            const int c16 = (pc & 1) * 16;
+            tc_ld16(taddr + (pc >> 1) * BN + c16, v);
+            if (j3 == 0) {                         // k1: + re, + im
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { accum[i] += v[i]; accum[32 + i] += v[i]; }
-          } else if (j3 == 1) {                    // k2: + im
+              for (int i = 0; i < 16; ++i) { accum[c16 + i] += v[i]; accum[32 + c16 + i] += v[i]; }
+            } else if (j3 == 1) {                  // k2: + im
 #pragma unroll
-            for (int i = 0; i < 32; ++i) accum[32 + i] += v[i];
-          } else {                                 // k3: - re
+              for (int i = 0; i < 16; ++i) accum[32 + c16 + i] += v[i];
+            } else {                               // k3: - re
 #pragma unroll
-            for (int i = 0; i < 32; ++i) accum[i] -= v[i];
+              for (int i = 0; i < 16; ++i) accum[c16 + i] -= v[i];
+            }
           }
           j3 = j3 == 2 ? 0 : j3 + 1;
         }
@@ -668,6 +688,68 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ---- 3-product (GAUSS) operand layout: per group of 128 beamlets three blocks of 128 k-elements --------------
+//   rows    A''[r][384 g + 128 j + i]:  j = 0: Ur + Ui,  1: Ur,       2: Ui
+//   columns B''[c][384 g + 128 j + i]:  j = 0: Vr,       1: Vi - Vr,  2: Vr + Vi          (beamlet n = 128 g + i)
+// The sums / differences are formed in fp32 (one rounding, 2^-24) BEFORE the hi / lo split.  One thread owns
+// the beamlet pair (2p, 2p + 1) -> 4-byte stores, consecutive threads consecutive addresses.  Beamlets
+// n >= nbatch of the last group are written as zeros (the tensor map covers whole groups).
+template <bool ROWS>
+__global__ void __launch_bounds__(128)
+    factor_gauss_kernel(const double *__restrict__ table, long long b0, int nbatch, int npad, int s_first, int S,
+                        int W, long long ldk, __half *__restrict__ hi, __half *__restrict__ lo,
+                        const unsigned long long *__restrict__ peak_key,
+                        const unsigned long long *__restrict__ sep_guard) {
+  if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
+  const int n = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int s0 = blockIdx.y * FS;
+  if (n >= npad) return;
+  Strip1D st[2];
+  bool live[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    live[e] = n + e < nbatch;
+    const double *t = table + (b0 + (live[e] ? n + e : 0)) * 12;
+    if (ROWS) {
+      double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
+      mu += Headroom<true>::value - tg_prescale_G(*peak_key);
+      st[e] = strip_setup(t[0], t[2], t[5], t[6 + 0] + mu, t[6 + 2], t[6 + 5], (double)(s_first + s0));
+    } else {
+      const double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1)) - Headroom<true>::value;
+      st[e] = strip_setup(0.0, t[1], t[3], -mu, t[6 + 1], t[6 + 3], (double)s0);
+    }
+  }
+  const long long kk = (long long)(n / KCH) * (3 * KCH) + (n % KCH);
+#pragma unroll 2
+  for (int j = 0; j < FS; ++j) {
+    if (s0 + j >= S) break;
+    float v[3][2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float re = 0.f, im = 0.f;
+      if (live[e]) strip_eval(st[e], j, re, im);
+      if (ROWS) {
+        v[0][e] = re + im;
+        v[1][e] = re;
+        v[2][e] = im;
+      } else {
+        v[0][e] = re;
+        v[1][e] = im - re;
+        v[2][e] = re + im;
+      }
+    }
+    const long long o = (long long)(s0 + j) * ldk + kk;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      float h0, l0, h1, l1;
+      Operand<true>::split(v[b][0], h0, l0);
+      Operand<true>::split(v[b][1], h1, l1);
+      *reinterpret_cast<__half2 *>(hi + o + b * KCH) = __floats2half2_rn(h0, h1);
+      *reinterpret_cast<__half2 *>(lo + o + b * KCH) = __floats2half2_rn(l0, l1);
+    }
+  }
+}
+
 // ---- cost-aware dispatch (AUTO only) -----------------------------------------------------
 // The GEMM is dense: it spends 24 TF32 flops on every beamlet*pixel whether the beamlet reaches the
 // pixel or not, while the SFU kernel skips (tile, beamlet) pairs below the culling threshold.  For
@@ -835,7 +917,7 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode
   return s;
 }
 
-template <bool F16>
+template <bool F16, bool GAUSS = false>
 int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *Blo, int M, int Np, int K,
                 long long ldk, double *out, long long ldo, int accumulate, const unsigned long long *peak_key,
                 const unsigned long long *sep_guard, cudaStream_t st, const TgPeers &peers) {
@@ -846,7 +928,8 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
   if ((rc = make_map<F16>(&tc, Bhi, Np, K, ldk)) != TG_OK) return rc;
   if ((rc = make_map<F16>(&td, Blo, Np, K, ldk)) != TG_OK) return rc;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
-  TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<F16, GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  constexpr int NE = GAUSS ? 16 : 8;
   int dev = 0, sms = 148;
   TG_CUDA(cudaGetDevice(&dev));
   tg_tune_mempool(dev);
@@ -860,8 +943,8 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
   const SkSched sched = make_sched(M, Np, K, GemmCfg<F16>::BK, GemmCfg<F16>::CHUNK_KB, sms);
   // stream-K scratch: arrival counters (zeroed here, left zero by the kernel) | partial tiles
   unsigned char *sk = nullptr;
-  const size_t cnt_bytes = (((size_t)sched.R * 8 * sizeof(unsigned int)) + 255) / 256 * 256;
-  const size_t part_bytes = (size_t)sched.R * sched.maxparts * (size_t)(BM * BN) * sizeof(float);
+  const size_t cnt_bytes = (((size_t)sched.R * NE * sizeof(unsigned int)) + 255) / 256 * 256;
+  const size_t part_bytes = (size_t)sched.R * sched.maxparts * (size_t)(NE * 2048) * sizeof(float);
   if (sched.R > 0 && sched.maxparts > 1) {
     TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&sk), cnt_bytes + part_bytes, st));
     cudaError_t e = cudaMemsetAsync(sk, 0, cnt_bytes, st);
@@ -871,10 +954,10 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
       return TG_ECUDA;
     }
   }
-  gemm_x3_kernel<F16><<<(unsigned)sched.G, GEMM_THREADS, smem, st>>>(
+  gemm_x3_kernel<F16, GAUSS><<<(unsigned)sched.G, GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, smem, st>>>(
       ta, tb, tc, td, M, Np, K, out, ldo, accumulate, peak_key, Headroom<F16>::value, sep_guard, peers, sched,
       sk ? reinterpret_cast<float *>(sk + cnt_bytes) : nullptr, reinterpret_cast<unsigned int *>(sk));
-  rc = tg_launch_check(F16 ? "gemm_x3_kernel<f16>" : "gemm_x3_kernel<tf32>");
+  rc = tg_launch_check(GAUSS ? "gemm_x3_kernel<f16, 3-product>" : F16 ? "gemm_x3_kernel<f16>" : "gemm_x3_kernel<tf32>");
   if (sk) cudaFreeAsync(sk, st);
   return rc;
 }
@@ -892,53 +975,78 @@ __global__ void __launch_bounds__(256)
 // loop: row factors + GEMM of one block; blocks exist for the host-buffer pipeline, whose D2H of a finished
 // block overlaps the GEMMs of the following ones).  acc: fp64 (nrows x 2W) accumulator = the output itself
 // for complex128.  A_hi / A_lo hold one row block.
-template <bool F16>
+template <bool F16, bool GAUSS>
 int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, long long ldk, void *Ahi, void *Alo,
                 void *Bhi, void *Blo, double *acc, const unsigned long long *peak, const unsigned long long *guard,
                 cudaStream_t st, const TgPeers &gemm_peers, int block_rows, const TgEmit *emit, void *out,
                 int out_is_c128) {
-  const int Np = 2 * W;
+  static_assert(!GAUSS || F16, "the 3-product formulation is implemented for fp16 x 3 operands");
+  const int ldo = 2 * W;                     // doubles per output row (re, im interleaved)
+  const int Np = GAUSS ? W : 2 * W;          // B rows: complex columns (3-product) or real columns
   int rc = TG_OK;
   TgPeers none;
   none.n = 0;
   for (long long b0 = 0; b0 < nb && rc == TG_OK; b0 += kBatch) {
     const int nbatch = (int)((nb - b0) < kBatch ? (nb - b0) : kBatch);
-    const int K = 2 * nbatch;
+    const int npad = ((nbatch + KCH - 1) / KCH) * KCH;
+    const int K = GAUSS ? 3 * npad : 2 * nbatch;
     const bool last = b0 + kBatch >= nb;
     // (the tensor maps are encoded with the true K: the TMA unit zero-fills the K padding)
-    dim3 gb((unsigned)((nbatch + 127) / 128), (unsigned)((W + FS - 1) / FS));
-    factor_cols_kernel<F16><<<gb, 128, 0, st>>>(table, b0, nbatch, W, ldk, Bhi, Blo, guard);
+    if constexpr (GAUSS) {
+      dim3 gb((unsigned)((npad / 2 + 127) / 128), (unsigned)((W + FS - 1) / FS));
+      factor_gauss_kernel<false><<<gb, 128, 0, st>>>(table, b0, nbatch, npad, 0, W, W, ldk, static_cast<__half *>(Bhi),
+                                                     static_cast<__half *>(Blo), peak, guard);
+    } else {
+      dim3 gb((unsigned)((nbatch + 127) / 128), (unsigned)((W + FS - 1) / FS));
+      factor_cols_kernel<F16><<<gb, 128, 0, st>>>(table, b0, nbatch, W, ldk, Bhi, Blo, guard);
+    }
     rc = tg_launch_check("factor_cols_kernel");
     int blk = 0;
     for (int r = 0; r < nrows && rc == TG_OK; r += block_rows, ++blk) {
       const int nr = (nrows - r) < block_rows ? (nrows - r) : block_rows;
-      dim3 ga((unsigned)((nbatch + 127) / 128), (unsigned)((nr + FS - 1) / FS));
-      factor_rows_kernel<F16><<<ga, 128, 0, st>>>(table, b0, nbatch, row0 + r, nr, W, ldk, Ahi, Alo, peak, guard);
+      if constexpr (GAUSS) {
+        dim3 ga((unsigned)((npad / 2 + 127) / 128), (unsigned)((nr + FS - 1) / FS));
+        factor_gauss_kernel<true><<<ga, 128, 0, st>>>(table, b0, nbatch, npad, row0 + r, nr, W, ldk,
+                                                      static_cast<__half *>(Ahi), static_cast<__half *>(Alo), peak,
+                                                      guard);
+      } else {
+        dim3 ga((unsigned)((nbatch + 127) / 128), (unsigned)((nr + FS - 1) / FS));
+        factor_rows_kernel<F16><<<ga, 128, 0, st>>>(table, b0, nbatch, row0 + r, nr, W, ldk, Ahi, Alo, peak, guard);
+      }
       rc = tg_launch_check("factor_rows_kernel");
       if (rc != TG_OK) break;
       TgPeers pe = none;
       if (last) {                                         // peers: final batch only
         pe = gemm_peers;
-        for (int p = 0; p < pe.n; ++p) pe.ptr[p] = static_cast<double *>(pe.ptr[p]) + (size_t)r * Np;
+        for (int p = 0; p < pe.n; ++p) pe.ptr[p] = static_cast<double *>(pe.ptr[p]) + (size_t)r * ldo;
       }
-      double *acc_r = acc + (size_t)r * Np;
-      rc = launch_gemm<F16>(Ahi, Alo, Bhi, Blo, nr, Np, K, ldk, acc_r, (long long)Np, b0 > 0 ? 1 : 0, peak, guard,
-                            st, pe);
+      double *acc_r = acc + (size_t)r * ldo;
+      rc = launch_gemm<F16, GAUSS>(Ahi, Alo, Bhi, Blo, nr, Np, K, ldk, acc_r, (long long)ldo, b0 > 0 ? 1 : 0, peak,
+                                   guard, st, pe);
       if (rc == TG_OK && last && !out_is_c128) {
-        const size_t n = (size_t)nr * Np;
+        const size_t n = (size_t)nr * ldo;
         TgPeers pc = none;   // complex64 peers are written by the conversion
-        float *o = static_cast<float *>(out) + (size_t)r * Np;
+        float *o = static_cast<float *>(out) + (size_t)r * ldo;
         f64_to_c64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc_r, o, n, guard, pc);
         rc = tg_launch_check("f64_to_c64_kernel");
       }
       if (rc == TG_OK && last && emit) {
-        const size_t row_bytes = (size_t)Np * (out_is_c128 ? 8 : 4);
+        const size_t row_bytes = (size_t)ldo * (out_is_c128 ? 8 : 4);
         rc = tg_emit_block(emit, blk, st, static_cast<unsigned char *>(out) + (size_t)r * row_bytes,
                            (size_t)r * row_bytes, (size_t)nr * row_bytes);
       }
     }
   }
   return rc;
+}
+
+// TG_TENSOR_GAUSS=0 selects the 4-multiplication real formulation for the fp16 path (A/B runs); default: 3-product
+bool use_gauss() {
+  static const bool g = [] {
+    const char *e = getenv("TG_TENSOR_GAUSS");
+    return !(e && atoi(e) == 0);
+  }();
+  return g;
 }
 
 }  // namespace
@@ -1002,6 +1110,27 @@ extern "C" int tg_gemm_f16x3(int M, int N, int K, const void *A_hi, const void *
                            static_cast<cudaStream_t>(stream), none);
 }
 
+// Complex D[M x N] (+)= sum_n U[m, n] V[c, n] with three real products per term (see gemm_x3_kernel, GAUSS): the
+// operands are in the 3-product layout (A'' / B'' of factor_gauss_kernel: per group of 128 terms the blocks
+// Ur + Ui | Ur | Ui and Vr | Vi - Vr | Vr + Vi, fp16 hi and lo parts), K3 = 3 * 128 * ceil(nterms / 128) <= ldk.
+// D: (M, N) complex128 as interleaved doubles, row pitch ldd doubles.  Exposed for testing.
+extern "C" int tg_gemm_chunk_k(void) { return CHUNK_K; }
+
+extern "C" int tg_cgemm3_f16x3(int M, int N, int K3, const void *A_hi, const void *A_lo, const void *B_hi,
+                               const void *B_lo, long long ldk, double *D, long long ldd, int accumulate,
+                               void *stream) {
+  TG_REQUIRE(M > 0 && N > 0 && K3 > 0 && K3 % (3 * KCH) == 0, "bad shape (K3 must be a multiple of 3 * tg_gemm_chunk_k())");
+  TG_REQUIRE(A_hi && A_lo && B_hi && B_lo && D, "null pointer");
+  TG_REQUIRE(ldk >= K3 && (ldk % 8) == 0 && ldd >= 2LL * N, "bad pitch");
+  TG_REQUIRE(((uintptr_t)A_hi % 16) == 0 && ((uintptr_t)A_lo % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 &&
+                 ((uintptr_t)B_lo % 16) == 0,
+             "operands must be 16-byte aligned");
+  TgPeers none;
+  none.n = 0;
+  return launch_gemm<true, true>(A_hi, A_lo, B_hi, B_lo, M, N, K3, ldk, D, ldd, accumulate, nullptr, nullptr,
+                                 static_cast<cudaStream_t>(stream), none);
+}
+
 extern "C" int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6], int H, int W,
                                       int row0, int nrows, void *out, int out_is_c128, void *stream) {
   return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr,
@@ -1049,9 +1178,11 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
     block_rows = emit->block_rows < nrows ? emit->block_rows : nrows;
   }
   const long long nbatch_max = nb < kBatch ? nb : kBatch;
-  const long long ldk = ((2 * nbatch_max + 63) / 64) * 64;  // whole 128-byte k-blocks in either format
+  const bool gauss = f16 == 1 && use_gauss();   // f16: 0 = tf32 x 3, 1 = fp16 x 3 (3-product unless disabled), 2 = fp16 x 3, 4-multiplication form
+  // operand row pitch: whole 128-byte k-blocks in either format; 3-product layout: 3 x 128 k per 128 beamlets
+  const long long ldk = gauss ? 3 * KCH * ((nbatch_max + KCH - 1) / KCH) : ((2 * nbatch_max + 63) / 64) * 64;
   const size_t elem = f16 ? 2 : 4;
-  const int Np = 2 * W;
+  const int Np = gauss ? W : 2 * W;          // B rows
   const size_t table_bytes = (((size_t)nb * 96 + 255) / 256) * 256;
   const size_t a_bytes = verdict_only ? 0 : (((size_t)block_rows * ldk * elem + 255) / 256) * 256;
   const size_t b_bytes = verdict_only ? 0 : (((size_t)Np * ldk * elem + 255) / 256) * 256;
@@ -1107,10 +1238,12 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
       return TG_ENOTSEPARABLE;
     }
   }
-  rc = f16 ? run_batches<true>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
-                               out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128)
-           : run_batches<false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
-                                out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128);
+  rc = gauss ? run_batches<true, true>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
+                                       out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128)
+       : f16 ? run_batches<true, false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
+                                        out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128)
+             : run_batches<false, false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
+                                         out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128);
   if (rc == TG_OK && !out_is_c128 && pe.n > 0) {
     // complex64 peer images: one more pass over the converted rows (the GEMM's peer stores are fp64-only)
     const size_t n = npix * 2;
@@ -1137,9 +1270,9 @@ int tg_field_sum_impl(int64_t nb, const double *poly, const double px2m[6], int 
   if (method == TG_METHOD_SFU)
     return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st,
                              peers, emit);
-  if (method == TG_METHOD_TENSOR || method == TG_METHOD_TENSOR_TF32)
+  if (method == TG_METHOD_TENSOR || method == TG_METHOD_TENSOR_TF32 || method == TG_METHOD_TENSOR_4M)
     return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr, st, 0,
-                            method == TG_METHOD_TENSOR, peers, emit);
+                            method == TG_METHOD_TENSOR ? 1 : method == TG_METHOD_TENSOR_4M ? 2 : 0, peers, emit);
   TG_REQUIRE(method == TG_METHOD_AUTO, "unknown method");
   if (nb == 0 || nrows == 0)
     return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st,

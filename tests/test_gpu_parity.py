@@ -489,7 +489,7 @@ def test_c2_full_size_tensor_path_vs_oracle(torch_cuda):
     g, model = M.aperture_diffraction_case(10_000, (1024, 1024))
     gd = gaussian_to_cuda(torch_cuda, g)
     pix = None
-    for method in ("tensor", "auto", "tensor_tf32"):
+    for method in ("tensor", "auto", "tensor_4m", "tensor_tf32"):
         img = to_np(make_gaussian_image_device(gd, model, cull_bits=0, method=method))
         if pix is None:
             pix = _sample_pixels(1024, 1024, bright_from=img)
@@ -646,6 +646,50 @@ def test_gemm_f16x3_against_fp64(torch_cuda, M, N, K):
     assert float((D[:, :N] - 2 * ref).norm() / ref.norm()) < 4e-6
 
 
+def _pack3(torch, Xr, Xi, which, kch=128):
+    """(rows, n) real / imaginary parts -> the 3-product operand layout (rows, 3 * kch * ceil(n / kch)) of
+    csrc/separable.cu: per group of kch = tg_gemm_chunk_k() terms  A: Ur + Ui | Ur | Ui,   B: Vr | Vi - Vr | Vr + Vi."""
+    rows, n = Xr.shape
+    g = (n + kch - 1) // kch
+    pad = g * kch - n
+    if pad:
+        z = torch.zeros((rows, pad), dtype=Xr.dtype, device=Xr.device)
+        Xr, Xi = torch.cat([Xr, z], 1), torch.cat([Xi, z], 1)
+    blocks = (Xr + Xi, Xr, Xi) if which == "A" else (Xr, Xi - Xr, Xr + Xi)
+    return torch.stack([b.reshape(rows, g, kch) for b in blocks], dim=2).reshape(rows, g * 3 * kch).contiguous()
+
+
+@pytest.mark.parametrize("M,N,nterms", [(128, 128, 128), (200, 136, 1000), (256, 384, 700), (1024, 1024, 10000),
+                                        (128, 1024, 10000), (77, 50, 36), (1408, 1408, 2048)])
+def test_cgemm3_f16x3_against_fp64(torch_cuda, M, N, nterms):
+    """The complex GEMM with three real products per term (Gauss) on the tensor cores: whole-tile, stream-K
+    (C2 shape: 64 tiles on 148 SMs; a rank's row shard) and mixed schedules, ragged edges, accumulate."""
+    from temgymcore_b200 import _lib as L
+    torch = torch_cuda
+    lib = L.load()
+    gen = torch.Generator(device="cuda").manual_seed(M * 7 + nterms)
+    Ur, Ui = (torch.rand((M, nterms), generator=gen, device="cuda") * 2 - 1 for _ in range(2))
+    Vr, Vi = (torch.rand((N, nterms), generator=gen, device="cuda") * 2 - 1 for _ in range(2))
+    kch = lib.tg_gemm_chunk_k()
+    A, B = _pack3(torch, Ur, Ui, "A", kch), _pack3(torch, Vr, Vi, "B", kch)
+    K3 = A.shape[1]
+    Ah, Al = _f16_split(torch, A)
+    Bh, Bl = _f16_split(torch, B)
+    D = torch.full((M, 2 * N + 2), -1.0, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.tg_cgemm3_f16x3(M, N, K3, Ah.data_ptr(), Al.data_ptr(), Bh.data_ptr(), Bl.data_ptr(), K3,
+                                D.data_ptr(), 2 * N + 2, 0, st), "tg_cgemm3_f16x3")
+    ref = torch.complex(Ur.double(), Ui.double()) @ torch.complex(Vr.double(), Vi.double()).T
+    got = torch.view_as_complex(D[:, :2 * N].reshape(M, N, 2).contiguous())
+    err = float((got - ref).norm() / ref.norm())
+    assert err < 4e-6, err
+    assert bool((D[:, 2 * N:] == -1.0).all())  # columns beyond N untouched
+    L.check(lib.tg_cgemm3_f16x3(M, N, K3, Ah.data_ptr(), Al.data_ptr(), Bh.data_ptr(), Bl.data_ptr(), K3,
+                                D.data_ptr(), 2 * N + 2, 1, st), "tg_cgemm3_f16x3 accumulate")
+    got2 = torch.view_as_complex(D[:, :2 * N].reshape(M, N, 2).contiguous())
+    assert float((got2 - 2 * ref).norm() / ref.norm()) < 6e-6
+
+
 def test_gemm_streamk_is_deterministic(torch_cuda):
     """Stream-K pieces of a tile are combined by the last piece to arrive, in slot order -- not in arrival
     order: repeated runs are bit-identical."""
@@ -691,7 +735,7 @@ def test_host_pipeline_row_blocks(torch_cuda, method):
     assert rel_l2(host_img, ref) < FIELD_TOL
 
 
-@pytest.mark.parametrize("method", ["tensor", "tensor_tf32"])
+@pytest.mark.parametrize("method", ["tensor", "tensor_4m", "tensor_tf32"])
 @pytest.mark.parametrize("name", ["c2_aperture", "c3_biprism_separable"])
 def test_tensor_path_parity(torch_cuda, name, method):
     from temgymcore_b200.gaussian import make_gaussian_image
@@ -718,7 +762,7 @@ def test_tensor_path_fp16_dynamic_range(torch_cuda, scale):
     amp = np.asarray(g.amplitude, dtype=np.float64) * 10.0 ** rng.uniform(-6, 0, np.shape(g.amplitude)) * scale
     g2 = replace(g, amplitude=amp)
     ref = O.make_gaussian_image(g2, model)
-    for method in ("tensor", "tensor_tf32"):
+    for method in ("tensor", "tensor_4m", "tensor_tf32"):
         got = make_gaussian_image(g2, model, method=method)
         assert rel_l2(got, ref) < FIELD_TOL, (method, rel_l2(got, ref))
 
