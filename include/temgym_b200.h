@@ -89,6 +89,17 @@ typedef struct {
   double value[7];
 } tg_ray_in;
 
+/* Per-ray component parameters: Scanner / Descanner (TG_OP_OFFSET) components whose parameters are ARRAYS over
+ * the ray batch -- what the reference gets from jax.vmap over scan positions (components.py:252-372,
+ * run.py:85-116).  ptr[k][j] (device, n doubles; NULL = keep the descriptor's scalar p[j]) replaces offset j
+ * (added to x, y, dx, dy times _one) of model component comp[k]. */
+#define TG_MAX_PERRAY 4
+typedef struct {
+  int32_t n;
+  int32_t comp[TG_MAX_PERRAY];
+  const double *ptr[TG_MAX_PERRAY][4];
+} tg_perray;
+
 /* Jacobian layouts for tg_trace_f64 */
 #define TG_JAC_NONE 0   /* rays only                    == run_to_end (run.py:85-116) */
 #define TG_JAC_ABCD5 1  /* jac = n*25 doubles, (n,5,5) row-major over [x,y,dx,dy,_one]
@@ -109,6 +120,9 @@ int tg_device_count(void);
 int tg_trace_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in,
                  double *const out[7], double *jac, int jac_layout, void *stream);
 
+/* tg_trace_f64 with per-ray Scanner / Descanner offsets (perray may be NULL) */
+int tg_trace_perray_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in, const tg_perray *perray,
+                        double *const out[7], double *jac, int jac_layout, void *stream);
 /* host-buffer variant: pointers in `in`, `out`, `jac` are HOST memory. */
 int tg_trace_f64_host(const tg_model *model_host, int64_t n, const tg_ray_in *in,
                       double *const out[7], double *jac, int jac_layout, int device);

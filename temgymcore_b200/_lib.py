@@ -39,6 +39,13 @@ class tg_ray_in(C.Structure):
     _fields_ = [("ptr", C.c_void_p * 7), ("value", C.c_double * 7)]
 
 
+TG_MAX_PERRAY = 4
+
+
+class tg_perray(C.Structure):
+    _fields_ = [("n", C.c_int32), ("comp", C.c_int32 * TG_MAX_PERRAY), ("ptr", (C.c_void_p * 4) * TG_MAX_PERRAY)]
+
+
 class tg_seed(C.Structure):
     _fields_ = [("comp", C.c_int32), ("slot", C.c_int32), ("lane", C.c_int32), ("reserved", C.c_int32),
                 ("weight", C.c_double)]
@@ -60,6 +67,8 @@ SIGNATURES = {
     "tg_abi_version": (_i32, []),
     "tg_device_count": (_i32, []),
     "tg_trace_f64": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(tg_ray_in), C.POINTER(_vp), _vp, _i32, _vp]),
+    "tg_trace_perray_f64": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(tg_ray_in), C.POINTER(tg_perray), C.POINTER(_vp),
+                                   _vp, _i32, _vp]),
     "tg_trace_f64_host": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(tg_ray_in), C.POINTER(_vp), _vp, _i32, _i32]),
     "tg_trace_grad_f64": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(tg_ray_in), C.POINTER(C.c_int32),
                                  C.POINTER(tg_seed), _i32, C.POINTER(_vp), _vp, _vp]),

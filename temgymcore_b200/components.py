@@ -22,11 +22,29 @@ from .tree_utils import HasParamsMixin
 
 def _f(v) -> float:
     """Component parameters are scalars (the model descriptor lives in kernel-parameter
-    constant memory); arrays of per-ray parameters are not part of this path."""
+    constant memory).  Scanner / Descanner also accept ARRAYS over the ray batch (what ``jax.vmap`` over scan
+    positions gives the reference): see ``_is_array`` / ``_tg_perray``."""
     try:
         return float(v)
     except Exception as exc:  # noqa: BLE001
         raise TypeError(f"component parameter must be a scalar, got {type(v).__name__}") from exc
+
+
+def _is_array(v) -> bool:
+    """True for a numpy array / torch tensor / list with more than one element."""
+    if isinstance(v, (list, tuple)):
+        return len(v) > 1
+    n = getattr(v, "numel", None)
+    if callable(n):
+        return n() > 1
+    return getattr(v, "size", 1) > 1 and getattr(v, "ndim", 0) > 0
+
+
+def _offset_spec(offsets):
+    """(spec params, per-ray arrays) of a TG_OP_OFFSET component from its four offsets, scalars or arrays."""
+    scal = tuple(0.0 if _is_array(o) else _f(o) for o in offsets)
+    arrs = [o if _is_array(o) else None for o in offsets]
+    return scal, (arrs if any(a is not None for a in arrs) else None)
 
 
 class Component(HasParamsMixin):
@@ -146,9 +164,15 @@ class Scanner(Component):  # components.py:252-285
     scan_tilt_y: float = 0.
     _TG_SLOTS = {"scan_pos_x": 1, "scan_pos_y": 2, "scan_tilt_x": 3, "scan_tilt_y": 4}
 
+    def _offsets(self):
+        return (self.scan_pos_x, self.scan_pos_y, self.scan_tilt_x, self.scan_tilt_y)   # components.py:279-285
+
     def _tg_spec(self):
-        return L.TG_OP_OFFSET, _f(self.z), (_f(self.scan_pos_x), _f(self.scan_pos_y),
-                                            _f(self.scan_tilt_x), _f(self.scan_tilt_y))
+        return L.TG_OP_OFFSET, _f(self.z), _offset_spec(self._offsets())[0]
+
+    def _tg_perray(self):
+        """Per-ray offset arrays (or None) when a scan position / tilt is an array over the ray batch."""
+        return _offset_spec(self._offsets())[1]
 
 
 @dataclass(frozen=True)
@@ -160,17 +184,24 @@ class Descanner(Component):  # components.py:288-372
     scan_tilt_y: float = 0.
     descan_error: DescanError = DescanError()
 
-    def _tg_spec(self):
+    def _offsets(self):
         de = self.descan_error
-        sp_x, sp_y = _f(self.scan_pos_x), _f(self.scan_pos_y)
-        st_x, st_y = _f(self.scan_tilt_x), _f(self.scan_tilt_y)
-        # the four 5th-column offsets, same operation order as components.py:343-372
-        return L.TG_OP_OFFSET, _f(self.z), (
-            sp_x * _f(de.pxo_pxi) + sp_y * _f(de.pxo_pyi) + _f(de.offpxi) - sp_x,
-            sp_x * _f(de.pyo_pxi) + sp_y * _f(de.pyo_pyi) + _f(de.offpyi) - sp_y,
-            sp_x * _f(de.sxo_pxi) + sp_y * _f(de.sxo_pyi) + _f(de.offsxi) - st_x,
-            sp_x * _f(de.syo_pxi) + sp_y * _f(de.syo_pyi) + _f(de.offsyi) - st_y,
-        )
+        sp_x, sp_y = self.scan_pos_x, self.scan_pos_y
+        st_x, st_y = self.scan_tilt_x, self.scan_tilt_y
+        if not any(_is_array(v) for v in (sp_x, sp_y, st_x, st_y) + tuple(de)):
+            sp_x, sp_y, st_x, st_y = _f(sp_x), _f(sp_y), _f(st_x), _f(st_y)
+            de = DescanError(*(_f(v) for v in de))
+        # the four 5th-column offsets, same operation order as components.py:343-372 (elementwise on arrays)
+        return (sp_x * de.pxo_pxi + sp_y * de.pxo_pyi + de.offpxi - sp_x,
+                sp_x * de.pyo_pxi + sp_y * de.pyo_pyi + de.offpyi - sp_y,
+                sp_x * de.sxo_pxi + sp_y * de.sxo_pyi + de.offsxi - st_x,
+                sp_x * de.syo_pxi + sp_y * de.syo_pyi + de.offsyi - st_y)
+
+    def _tg_spec(self):
+        return L.TG_OP_OFFSET, _f(self.z), _offset_spec(self._offsets())[0]
+
+    def _tg_perray(self):
+        return _offset_spec(self._offsets())[1]
 
     def _tg_param_seeds(self, path):
         # the kernel sees the four offsets o1..o4 (slots 1..4); chain rule of components.py:343-372

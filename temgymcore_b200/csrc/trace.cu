@@ -20,6 +20,7 @@
 // (cp.async.bulk.global.shared::cta), so HBM sees full lines only.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include "tg_common.cuh"
 
 namespace {
@@ -549,10 +550,14 @@ inline void to_lite(const tg_model &m, ModelLite &l) {
 // In the 5-column mode z and pathlength carry no tangents: d z_out / d {x,y,dx,dy,_one}
 // is identically zero for every component on the path (z only ever receives component
 // constants), and pathlength never feeds back into x,y,dx,dy.
-template <int NC, bool KRIV>
+// PERRAY: Scanner / Descanner components whose parameters are ARRAYS over the ray batch (what the reference gets
+// from jax.vmap over scan positions, components.py:252-372): their four offsets come from per-ray SoA arrays
+// (tg_perray) instead of the constant-bank descriptor.  A separate instantiation, so the common scalar-parameter
+// kernels keep their register count and parameter block.
+template <int NC, bool KRIV, bool PERRAY>
 __global__ void __launch_bounds__(kTraceThreads, KRIV ? (NC == 5 ? 4 : 2) : (NC == 7 ? 3 : 6))
     trace_kernel(const __grid_constant__ typename ModelFor<KRIV>::type model, const tg_ray_in in,
-                 const long long n, const TraceOut out, double *__restrict__ jac) {
+                 const long long n, const TraceOut out, double *__restrict__ jac, const tg_perray pr) {
   constexpr bool FULL = (NC == 7);
   constexpr int NZ = FULL ? 7 : 0;  // tangent width of z and pathlength
   constexpr int ROWS = (NC == 7) ? 7 : 5;
@@ -634,10 +639,20 @@ __global__ void __launch_bounds__(kTraceThreads, KRIV ? (NC == 5 ? 4 : 2) : (NC 
           else dx = dx + cm.p[0] * one * dsign(x);
         } break;
         case TG_OP_OFFSET: {  // Scanner / Descanner, components.py:279-285, 343-372
-          x = x + cm.p[0] * one;
-          y = y + cm.p[1] * one;
-          dx = dx + cm.p[2] * one;
-          dy = dy + cm.p[3] * one;
+          double o0 = cm.p[0], o1 = cm.p[1], o2 = cm.p[2], o3 = cm.p[3];
+          if constexpr (PERRAY) {
+            for (int k = 0; k < pr.n; ++k)
+              if (pr.comp[k] == c) {
+                if (pr.ptr[k][0]) o0 = __ldg(pr.ptr[k][0] + i);
+                if (pr.ptr[k][1]) o1 = __ldg(pr.ptr[k][1] + i);
+                if (pr.ptr[k][2]) o2 = __ldg(pr.ptr[k][2] + i);
+                if (pr.ptr[k][3]) o3 = __ldg(pr.ptr[k][3] + i);
+              }
+          }
+          x = x + o0 * one;
+          y = y + o1 * one;
+          dx = dx + o2 * one;
+          dy = dy + o3 * one;
         } break;
         case TG_OP_ROTATOR: {  // components.py:503-523
           const double cs = cm.p[0], sn = cm.p[1];
@@ -743,36 +758,41 @@ __global__ void __launch_bounds__(kTraceThreads, KRIV ? (NC == 5 ? 4 : 2) : (NC 
   }
 }
 
-template <int NC, bool KRIV>
+template <int NC, bool KRIV, bool PERRAY>
 int launch_trace_k(const tg_model *m, int64_t n, const tg_ray_in *in, double *const out[7],
-                 double *jac, cudaStream_t st) {
+                 double *jac, cudaStream_t st, const tg_perray &pr) {
   TraceOut o;
   for (int f = 0; f < 7; ++f) o.ptr[f] = out ? out[f] : nullptr;
   constexpr int ROWS = (NC == 7) ? 7 : 5;
   const size_t smem = NC > 0 ? (size_t)kTraceThreads * ROWS * NC * sizeof(double) : 0;
   if (smem > 48 * 1024) {
-    TG_CUDA(cudaFuncSetAttribute(trace_kernel<NC, KRIV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TG_CUDA(cudaFuncSetAttribute(trace_kernel<NC, KRIV, PERRAY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
   }
   const long long blocks = (n + kTraceThreads - 1) / kTraceThreads;
   TG_REQUIRE(blocks <= 0x7fffffffLL, "too many rays for one launch");
   if constexpr (KRIV) {
-    trace_kernel<NC, true><<<(unsigned)blocks, kTraceThreads, smem, st>>>(*m, *in, (long long)n, o, jac);
+    trace_kernel<NC, true, PERRAY><<<(unsigned)blocks, kTraceThreads, smem, st>>>(*m, *in, (long long)n, o, jac, pr);
   } else {
     ModelLite lite;
     to_lite(*m, lite);
-    trace_kernel<NC, false><<<(unsigned)blocks, kTraceThreads, smem, st>>>(lite, *in, (long long)n, o, jac);
+    trace_kernel<NC, false, PERRAY><<<(unsigned)blocks, kTraceThreads, smem, st>>>(lite, *in, (long long)n, o, jac, pr);
   }
   return tg_launch_check("trace_kernel");
 }
 
 template <int NC>
 int launch_trace(const tg_model *m, int64_t n, const tg_ray_in *in, double *const out[7],
-                 double *jac, cudaStream_t st) {
+                 double *jac, cudaStream_t st, const tg_perray *perray) {
   bool kriv = false;
   for (int c = 0; c < m->n_comp; ++c) kriv |= (m->comp[c].op == TG_OP_KRIVANEK);
-  return kriv ? launch_trace_k<NC, true>(m, n, in, out, jac, st)
-              : launch_trace_k<NC, false>(m, n, in, out, jac, st);
+  tg_perray none;
+  memset(&none, 0, sizeof(none));
+  if (perray && perray->n > 0)
+    return kriv ? launch_trace_k<NC, true, true>(m, n, in, out, jac, st, *perray)
+                : launch_trace_k<NC, false, true>(m, n, in, out, jac, st, *perray);
+  return kriv ? launch_trace_k<NC, true, false>(m, n, in, out, jac, st, none)
+              : launch_trace_k<NC, false, false>(m, n, in, out, jac, st, none);
 }
 
 // ------------------------------------------------------------------ parameter tangents
@@ -991,7 +1011,21 @@ __global__ void __launch_bounds__(256)
 
 extern "C" int tg_trace_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in,
                             double *const out[7], double *jac, int jac_layout, void *stream) {
+  return tg_trace_perray_f64(model_host, n, in, nullptr, out, jac, jac_layout, stream);
+}
+
+extern "C" int tg_trace_perray_f64(const tg_model *model_host, int64_t n, const tg_ray_in *in,
+                                   const tg_perray *perray, double *const out[7], double *jac, int jac_layout,
+                                   void *stream) {
   TG_REQUIRE(model_host && in, "null model or input");
+  if (perray) {
+    TG_REQUIRE(perray->n >= 0 && perray->n <= TG_MAX_PERRAY, "bad per-ray component count");
+    for (int k = 0; k < perray->n; ++k) {
+      const int c = perray->comp[k];
+      TG_REQUIRE(c >= 0 && c < model_host->n_comp && model_host->comp[c].op == TG_OP_OFFSET,
+                 "per-ray parameters are supported for Scanner / Descanner components (TG_OP_OFFSET)");
+    }
+  }
   TG_REQUIRE(model_host->n_comp >= 0 && model_host->n_comp <= TG_MAX_COMPS, "bad n_comp");
   TG_REQUIRE(n >= 0, "negative n");
   TG_REQUIRE(jac_layout == TG_JAC_NONE || jac != nullptr, "jac requested but pointer is null");
@@ -999,11 +1033,11 @@ extern "C" int tg_trace_f64(const tg_model *model_host, int64_t n, const tg_ray_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (jac_layout) {
     case TG_JAC_NONE:
-      return launch_trace<0>(model_host, n, in, out, nullptr, st);
+      return launch_trace<0>(model_host, n, in, out, nullptr, st, perray);
     case TG_JAC_ABCD5:
-      return launch_trace<5>(model_host, n, in, out, jac, st);
+      return launch_trace<5>(model_host, n, in, out, jac, st, perray);
     case TG_JAC_FULL7:
-      return launch_trace<7>(model_host, n, in, out, jac, st);
+      return launch_trace<7>(model_host, n, in, out, jac, st, perray);
     default:
       tg_set_error("tg_trace_f64: unknown jac_layout %d", jac_layout);
       return TG_EINVAL;

@@ -314,7 +314,7 @@ class PeerImagePlan:
     def __init__(self, gaussian_rays, model, peer_image: "PeerImage", *, cull_bits=None, method="auto"):
         import torch
         from .gaussian import _beamlet_arrays, _device_for
-        from .run import compile_model
+        from .gaussian import compile_model
         self.pimg = peer_image
         grid = model[-1]
         peer_image.check_grid(grid)

@@ -25,7 +25,11 @@ from . import _arrays as A
 from . import _lib as L
 from .grid import Grid
 from .ray import RAY_FIELDS, Ray
-from .run import _check_propagator, compile_model  # noqa: F401
+from .run import _check_propagator, compile_model as _compile_any, require_scalar_params  # noqa: F401
+
+
+def compile_model(model):
+    return require_scalar_params(_compile_any(model), "make_gaussian_image")
 
 DEFAULT_CULL_BITS = 40
 """Beamlets whose envelope over a whole pixel tile is below 2**-40 of the brightest

@@ -32,6 +32,7 @@ def compile_model(components: Sequence[Any], noprop: bool = False) -> L.tg_model
                          f"{L.TG_MAX_COMPS}")
     m = L.tg_model()
     m.n_comp = len(comps)
+    perray = []
     for i, c in enumerate(comps):
         if isinstance(c, Source):
             op, z, params = L.TG_OP_PLANE, float(c.z), ()
@@ -45,7 +46,22 @@ def compile_model(components: Sequence[Any], noprop: bool = False) -> L.tg_model
         m.comp[i].z = z
         for j, v in enumerate(params):
             m.comp[i].p[j] = v
+        arrs = c._tg_perray() if hasattr(c, "_tg_perray") else None
+        if arrs is not None:               # Scanner / Descanner with array-valued parameters (per-ray offsets)
+            perray.append((i, arrs))
+    if len(perray) > L.TG_MAX_PERRAY:
+        raise ValueError(f"at most {L.TG_MAX_PERRAY} components of a model may carry per-ray parameters")
+    m._perray = perray
     return m
+
+
+def require_scalar_params(model: L.tg_model, what: str) -> L.tg_model:
+    """Per-ray component parameters are served by the ray kernel (run_to_end / run_iter / the ABCD calls);
+    everything else takes scalar-parameter models."""
+    if getattr(model, "_perray", None):
+        raise NotImplementedError(f"{what}: array-valued Scanner / Descanner parameters are supported by run_to_end, "
+                                  "run_iter, run_to_end_abcd and ray_jacobian only")
+    return model
 
 
 def _host_z(z, model: L.tg_model) -> float:
@@ -78,6 +94,9 @@ def _trace(ray, model: L.tg_model, jac_layout: int = L.TG_JAC_NONE, want_rays: b
     """Run the ray kernel.  Returns (Ray | None, jac | None)."""
     lib = L.load()
     vals = [getattr(ray, f) for f in RAY_FIELDS]
+    perray = getattr(model, "_perray", None)
+    if perray:
+        return _trace_perray(ray, model, perray, jac_layout, want_rays)
     kinds = [A.kind_of(v) for v in vals]
     kind = max(kinds)
     sizes = [A.numel(v) for v in vals]
@@ -161,6 +180,62 @@ def _trace(ray, model: L.tg_model, jac_layout: int = L.TG_JAC_NONE, want_rays: b
                 res.append(A.to_float(vals[6]) * 1.0)
         out_ray = Ray(*res)
     return out_ray, jac
+
+
+def _trace_perray(ray, model, perray, jac_layout, want_rays):
+    """Ray kernel with per-ray Scanner / Descanner offsets (``tg_trace_perray_f64``): the batch is the common
+    length of the ray arrays and the parameter arrays (scalars broadcast), everything runs on the device and
+    the results come back in the kind of the inputs (CUDA tensors stay, numpy / CPU tensors are copied back)."""
+    import torch
+    lib = L.load()
+    vals = [getattr(ray, f) for f in RAY_FIELDS]
+    arrays = [a for _, arrs in perray for a in arrs if a is not None]
+    kind = max([A.kind_of(v) for v in vals] + [A.kind_of(a) for a in arrays])
+    n = max([A.numel(v) for v in vals] + [A.numel(a) for a in arrays])
+    shape = next((A.shape_of(v) for v in vals + arrays if A.numel(v) == n), (n,))
+    for v in vals + arrays:
+        if A.numel(v) not in (1, n):
+            raise ValueError(f"ray fields and per-ray component parameters must share one batch size ({n})")
+    dev = A.cuda_device_of(vals + arrays) or torch.device("cuda", A.current_device_index())
+    rin = L.tg_ray_in()
+    keep = []
+    for i, v in enumerate(vals):
+        if A.numel(v) == 1:
+            rin.ptr[i] = None
+            rin.value[i] = A.to_float(v)
+        else:
+            t = A.to_device_f64(v, dev)
+            keep.append(t)
+            rin.ptr[i] = t.data_ptr()
+    pr = L.tg_perray()
+    pr.n = len(perray)
+    for k, (ci, arrs) in enumerate(perray):
+        pr.comp[k] = ci
+        for j, a in enumerate(arrs):
+            if a is None:
+                pr.ptr[k][j] = None
+            else:
+                t = A.to_device_f64(a, dev)
+                t = t.expand(n).contiguous() if t.numel() == 1 else t
+                keep.append(t)
+                pr.ptr[k][j] = t.data_ptr()
+    jw = {L.TG_JAC_NONE: 0, L.TG_JAC_ABCD5: 25, L.TG_JAC_FULL7: 49}[jac_layout]
+    jdim = 5 if jw == 25 else 7
+    outs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(7)] if want_rays else None
+    jac = torch.empty((n, jdim, jdim), dtype=torch.float64, device=dev) if jw else None
+    with torch.cuda.device(dev):
+        L.check(lib.tg_trace_perray_f64(C.byref(model), n, C.byref(rin), C.byref(pr),
+                                        L.ptr_array([o.data_ptr() for o in outs] if outs else [None] * 7),
+                                        jac.data_ptr() if jw else None, jac_layout, A.current_stream_ptr(dev)),
+                "tg_trace_perray_f64")
+
+    def back(t, shp):
+        t = t.reshape(shp)
+        if kind == A.KIND_CUDA:
+            return t
+        return t.cpu() if kind == A.KIND_TORCH_CPU else t.cpu().numpy()
+    out_ray = Ray(*(back(o, shape) for o in outs)) if want_rays else None
+    return out_ray, (back(jac, tuple(shape) + (jdim, jdim)) if jw else None)
 
 
 def _check_propagator(propagator):
@@ -273,7 +348,7 @@ class RayTracePlan:
                                                      if device is None else device)
         self.device = dev
         self._layout = L.TG_JAC_ABCD5 if jacobian else L.TG_JAC_NONE
-        self._model = compile_model(components)
+        self._model = require_scalar_params(compile_model(components), "RayTracePlan")
         self._static = Ray(*(v if A.kind_of(v) == A.KIND_SCALAR else A.to_device_f64(v, dev).clone()
                              for v in vals))
         side = torch.cuda.Stream(device=dev)
@@ -329,7 +404,7 @@ def calculate_derivatives(ray, model: Sequence[Any], order: int):
     if order > 3:
         raise NotImplementedError("calculate_derivatives: the CUDA jet kernel implements orders 1..3")
     lib = L.load()
-    cm = compile_model(model)
+    cm = require_scalar_params(compile_model(model), "calculate_derivatives")
     vals = [getattr(ray, f) for f in RAY_FIELDS]
     kinds = [A.kind_of(v) for v in vals]
     kind = max(kinds)
@@ -430,7 +505,7 @@ def run_with_grads(input_ray, model: Sequence[Any], grad_vars: Sequence[Any]):
         raise RuntimeError("Cannot find any variable in parameters")
 
     import torch
-    cm = compile_model(comps)
+    cm = require_scalar_params(compile_model(comps), "run_with_grads")
     vals = [getattr(input_ray, f) for f in RAY_FIELDS]
     kinds = [A.kind_of(v) for v in vals]
     kind = max(kinds)

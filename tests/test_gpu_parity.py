@@ -1304,3 +1304,57 @@ def test_peer_image_world_size_one(torch_cuda, method, dtype_name):
         assert not to_np(pi.image).any()
     finally:
         pi.close()
+
+
+# ------------------------------------------------------------------------------ per-ray component parameters
+def test_scanner_descanner_array_parameters(torch_cuda):
+    """Scanner / Descanner with ARRAY-valued scan positions (one per ray) through run_to_end / run_iter / the ABCD
+    call -- what the reference evaluates under jax.vmap over scan positions (components.py:252-372,
+    run.py:85-116): every ray must equal the single-ray run of a model built with its own scalar parameters."""
+    from temgymcore_b200.components import Descanner, DescanError, Detector, Lens, Scanner
+    from temgymcore_b200.run import run_iter, run_to_end, run_to_end_abcd
+    rng = np.random.default_rng(9)
+    n = 700
+    rays = M.random_rays(n, rng, scale=1e-3, slope=1e-2)
+    spx, spy = rng.uniform(-1e-3, 1e-3, n), rng.uniform(-1e-3, 1e-3, n)
+    err = DescanError(*rng.uniform(-1e-2, 1e-2, 12))
+    det = Detector(z=0.5, pixel_size=(55e-6, 55e-6), shape=(32, 32))
+
+    def model_of(px, py):
+        return [Scanner(z=0.0, scan_pos_x=px, scan_pos_y=py, scan_tilt_x=1e-4), Lens(z=0.05, focal_length=0.2),
+                Descanner(z=0.1, scan_pos_x=px, scan_pos_y=py, scan_tilt_x=1e-4, descan_error=err), det]
+    # oracle: one scalar-parameter model per ray
+    ref_out, ref_abcd = [], []
+    for i in range(0, n, 50):
+        one = type(rays)(*(np.asarray(getattr(rays, f))[i:i + 1] for f in O.RAY_FIELDS))
+        o, a = O.abcd_run_to_end(one, model_of(float(spx[i]), float(spy[i])))
+        ref_out.append([getattr(o, f)[0] for f in O.RAY_FIELDS])
+        ref_abcd.append(a[0])
+    ref_out, ref_abcd = np.array(ref_out), np.array(ref_abcd)
+    # numpy arrays in -> numpy arrays out; CUDA tensors in -> CUDA tensors out
+    model = model_of(spx, spy)
+    out, abcd = run_to_end_abcd(rays, model)
+    for k, f in enumerate(O.RAY_FIELDS):
+        close(np.asarray(getattr(out, f))[::50], ref_out[:, k])
+    close(np.asarray(abcd)[::50], ref_abcd)
+    model_d = model_of(torch_cuda.as_tensor(spx, device="cuda"), torch_cuda.as_tensor(spy, device="cuda"))
+    out_d = run_to_end(ray_to_cuda(torch_cuda, rays), model_d)
+    assert out_d.x.is_cuda
+    for f in O.RAY_FIELDS:
+        np.testing.assert_array_equal(to_np(getattr(out_d, f)), np.asarray(getattr(out, f)))
+    # a single (scalar) ray scanned over all positions: the batch comes from the parameters
+    single = type(rays)(x=1e-4, y=-2e-4, dx=1e-3, dy=0.0, z=0.0, pathlength=0.0, _one=1.0)
+    scan = run_to_end(single, model)
+    assert np.asarray(scan.x).shape == (n,)
+    o0 = O.run_to_end(type(rays)(*(np.array([getattr(single, f)]) for f in O.RAY_FIELDS)),
+                      model_of(float(spx[3]), float(spy[3])))
+    close(np.asarray(scan.x)[3], o0.x[0])
+    close(np.asarray(scan.dy)[3], o0.dy[0])
+    # run_iter: the per-step rays carry the offsets too
+    steps = list(run_iter(rays, model))
+    assert len(steps) == 2 * len(model)
+    close(np.asarray(steps[-1][1].x)[::50], ref_out[:, 0])
+    from temgymcore_b200.gaussian import make_gaussian_image
+    with pytest.raises(NotImplementedError):
+        g, _ = field_cases()["c2_aperture"]
+        make_gaussian_image(g, model)
