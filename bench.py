@@ -338,7 +338,7 @@ def run_ours(args):
     # our kernels per step: trace, coeffs-from-beam + {sfu: prep, field, split-reduce |
     # tensor: prep (+ separability verdict + pre-scaling peak), 2 factor kernels, GEMM | auto: both sets, the
     # unused one exits at once}
-    LAUNCHES = {"sfu": 5, "tensor": 6, "tensor_tf32": 6, "tensor_4m": 6, "auto": 9}
+    LAUNCHES = {"sfu": 5, "tensor": 6, "tensor_tf32": 6, "tensor_4m": 6, "tensor_3m": 6, "auto": 9}
 
     def step_device():
         """inputs resident in HBM: one C-ABI call (tg_make_gaussian_image_f64) captured in a CUDA graph
@@ -800,7 +800,7 @@ def main():
     ap.add_argument("--skip-c3", action="store_true", help="skip the C3 (1e5 beamlets x 2048^2) sections")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch the step's kernels directly instead of replaying a CUDA graph")
-    ap.add_argument("--method", default="auto", choices=["auto", "sfu", "tensor", "tensor_tf32", "tensor_4m"],
+    ap.add_argument("--method", default="auto", choices=["auto", "sfu", "tensor", "tensor_tf32", "tensor_4m", "tensor_3m"],
                     help="field-sum path: auto = tensor cores when separable (C2 is), sfu = general kernel")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -290,7 +290,10 @@ int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6],
 #define TG_METHOD_TENSOR 2 /* tg_field_sum_separable (TG_ENOTSEPARABLE if it does not apply): fp16 x 3 */
 #define TG_METHOD_TENSOR_TF32 3 /* the same GEMM with tf32 x 3 operands (fp32 exponent range, half the rate) */
 #define TG_METHOD_TENSOR_4M 4   /* fp16 x 3 with four real multiplications per complex term (the real GEMM on
-                                   interleaved re/im operands); TG_METHOD_TENSOR uses three (Gauss) */
+                                   interleaved re/im operands) */
+#define TG_METHOD_TENSOR_3M 5   /* fp16 x 3 with three real multiplications per complex term (Gauss: 25 % less tensor
+                                   work, tiles twice as large).  TG_METHOD_TENSOR / AUTO run the 4-multiplication
+                                   form unless the environment sets TG_TENSOR_GAUSS=1 */
 int tg_field_sum(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                  int nrows, void *out, int out_is_c128, int cull_bits, int method, void *stream);
 

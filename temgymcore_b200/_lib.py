@@ -21,7 +21,7 @@ TG_OP_KRIVANEK, TG_OP_OFFSET, TG_OP_THICKLENS, TG_OP_ROTATOR = 4, 5, 6, 7
 TG_F_NOPROP = 1
 TG_F_DIST = 2
 TG_JAC_NONE, TG_JAC_ABCD5, TG_JAC_FULL7 = 0, 1, 2
-TG_METHOD = {"auto": 0, "sfu": 1, "tensor": 2, "tensor_tf32": 3, "tensor_4m": 4}
+TG_METHOD = {"auto": 0, "sfu": 1, "tensor": 2, "tensor_tf32": 3, "tensor_4m": 4, "tensor_3m": 5}
 TG_OK, TG_EINVAL, TG_ECUDA, TG_ENOTSEPARABLE, TG_EUNSUPPORTED = 0, -1, -2, -3, -4
 
 

@@ -541,6 +541,266 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
   }
 }
 
+// ---------------------------------------------------------------- CTA-pair GEMM (tcgen05 cta_group::2)
+// The one-CTA kernel above is bound by what ONE SM can take in: a k-block of four 128-row operand tiles is
+// 64 KB per 768 tensor-pipe cycles (83 B/clk against ~64 B/clk of L2 -> SM bandwidth; ncu: tensor pipe 73 %
+// active, no other unit saturated).  Here two CTAs on the two SMs of a TPC (a cluster of 2) compute a
+// 256 x 128 tile together: each CTA loads its own 128 rows of A_hi / A_lo but only HALF of the B_hi / B_lo tiles
+// (64 rows each), and the leader CTA issues tcgen05.mma.cta_group::2 with M = 256, which reads A from both
+// CTAs' shared memory and the two B halves from both -- 48 KB per k-block and SM instead of 64 KB, so four
+// stages fit where three did.  Each CTA's TMEM receives the accumulators of its own 128 rows.
+//   barriers : full[s]       lives in the LEADER; both CTAs' TMA loads complete_tx on it (peer bit masked off)
+//              empty[s]      one per CTA; the leader's tcgen05.commit multicasts the arrival to both
+//              tmem_full[a]  one per CTA, multicast commit; each CTA's epilogue drains its own TMEM
+//              tmem_empty[a] in the LEADER, 16 arrivals: the 8 epilogue warps of both CTAs (remote arrive)
+// Whole tiles only (persistent over pair tiles); shapes that would leave the machine idle go to the one-CTA
+// stream-K kernel.
+constexpr int P_STAGES = 4;
+constexpr int P_TILE_A = BM * BK_BYTES;                      // 16 KiB: 128 rows
+constexpr int P_TILE_B = (BN / 2) * BK_BYTES;                // 8 KiB: this CTA's 64 rows of the B tile
+constexpr int P_STAGE_BYTES = 2 * P_TILE_A + 2 * P_TILE_B;   // 48 KiB
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;               // shared::cluster address of the even CTA of a pair
+
+struct PairSmemCtl {
+  uint64_t full[P_STAGES];
+  uint64_t empty[P_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (executed by both CTAs)
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(tg_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(tg_smem_u32(bar) & kPeerBitMask),
+      "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the barrier at this offset in both CTAs of the pair once all prior MMAs have completed
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          tg_smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tg_smem_u32(bar) & kPeerBitMask) : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  if constexpr (F16) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// instruction descriptor with M = 256 (pair) and N
+template <bool F16, int N> struct IdescPair {
+  static constexpr uint32_t value = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) |
+                                    ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+};
+
+template <bool F16>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                        const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                        int M, int Np, int K, double *__restrict__ out, long long ldo, int accumulate_out,
+                        const unsigned long long *__restrict__ peak_key, double headroom,
+                        const unsigned long long *__restrict__ sep_guard, const __grid_constant__ TgPeers peers,
+                        int tiles_n, int n_pair_tiles) {
+  // (both CTAs of a cluster read the same key: they leave together)
+  if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
+  constexpr int BK = GemmCfg<F16>::BK, CHUNK_KB = GemmCfg<F16>::CHUNK_KB;
+  constexpr uint32_t kIdesc = IdescPair<F16, BN>::value;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem) + 1023) &
+                                                           ~uintptr_t(1023));
+  PairSmemCtl *ctl = reinterpret_cast<PairSmemCtl *>(tiles + P_STAGES * P_STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int nkb = (K + BK - 1) / BK;
+  const int nchunks_tile = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P_STAGES; ++s) {
+      tg_mbar_init(&ctl->full[s], 1);
+      tg_mbar_init(&ctl->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tg_mbar_init(&ctl->tmem_full[a], 1);
+      tg_mbar_init(&ctl->tmem_empty[a], 16);  // 8 epilogue warps x 2 CTAs (used in the leader only)
+    }
+    tg_fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     tg_smem_u32(&ctl->tmem_base)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // the peer's barriers exist before anything is signalled across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own A rows, own half of the B rows
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int pt = cluster_id; pt < n_pair_tiles; pt += n_clusters) {
+        const int m0 = ((pt / tiles_n) * 2 + (int)rank) * BM;
+        const int n0 = (pt % tiles_n) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = (int)(it % P_STAGES);
+          const uint32_t ph = (it / P_STAGES) & 1u;
+          tg_mbar_wait(&ctl->empty[s], ph ^ 1u);
+          unsigned char *st = tiles + s * P_STAGE_BYTES;
+          if (rank == 0) tg_mbar_expect_tx(&ctl->full[s], 2 * P_STAGE_BYTES);   // both CTAs' bytes land here
+          tma_load_2d_pair(st, &tmA_hi, &ctl->full[s], kb * BK, m0);
+          tma_load_2d_pair(st + P_TILE_A, &tmA_lo, &ctl->full[s], kb * BK, m0);
+          tma_load_2d_pair(st + 2 * P_TILE_A, &tmB_hi, &ctl->full[s], kb * BK, n0);
+          tma_load_2d_pair(st + 2 * P_TILE_A + P_TILE_B, &tmB_lo, &ctl->full[s], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader CTA only
+    if (lane == 0 && rank == 0) {
+      uint32_t it = 0, chn = 0;
+      for (int pt = cluster_id; pt < n_pair_tiles; pt += n_clusters) {
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = (int)(it % P_STAGES);
+          const uint32_t ph = (it / P_STAGES) & 1u;
+          const bool chunk_start = (kb % CHUNK_KB) == 0;
+          const int acc = (int)(chn & 1u);
+          if (chunk_start) {
+            tg_mbar_wait(&ctl->tmem_empty[acc], ((chn >> 1) & 1u) ^ 1u);   // both CTAs have drained this accumulator
+            tc_fence_after();
+          }
+          tg_mbar_wait(&ctl->full[s], ph);
+          tc_fence_after();
+          unsigned char *st = tiles + s * P_STAGE_BYTES;
+          const uint64_t dAh = make_smem_desc(st), dAl = make_smem_desc(st + P_TILE_A);
+          const uint64_t dBh = make_smem_desc(st + 2 * P_TILE_A), dBl = make_smem_desc(st + 2 * P_TILE_A + P_TILE_B);
+          const uint32_t d = tmem_base + (uint32_t)(acc * ACC_COLS);
+#pragma unroll
+          for (int k4 = 0; k4 < BK_BYTES / 32; ++k4) {
+            const uint64_t ko = (uint64_t)(k4 * 32 >> 4);
+            const uint32_t first = (chunk_start && k4 == 0) ? 0u : 1u;
+            tc_mma_pair<F16>(d, dAh + ko, dBh + ko, kIdesc, first);                    // hi * hi
+            tc_mma_pair<F16>(d + (uint32_t)BN, dAh + ko, dBl + ko, kIdesc, first);     // hi * lo
+            tc_mma_pair<F16>(d + (uint32_t)BN, dAl + ko, dBh + ko, kIdesc, 1u);        // lo * hi
+          }
+          tc_commit_pair(&ctl->empty[s]);          // both CTAs' stage s may be refilled once these MMAs have read it
+          if ((kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1) {
+            tc_commit_pair(&ctl->tmem_full[acc]);
+            ++chn;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs): drain the own 128 rows
+    const int q = warp & 3, h = (warp - 4) >> 2;
+    const double sc = peak_key ? scalbn(1.0, (int)(tg_prescale_G(*peak_key) - 2.0 * headroom)) : 1.0;
+    float accum[64];
+    uint32_t chn = 0;
+    for (int pt = cluster_id; pt < n_pair_tiles; pt += n_clusters) {
+      const int m0 = ((pt / tiles_n) * 2 + (int)rank) * BM;
+      const int n0 = (pt % tiles_n) * BN;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) accum[i] = 0.f;
+      for (int ch = 0; ch < nchunks_tile; ++ch, ++chn) {
+        const int acc = (int)(chn & 1u);
+        tg_mbar_wait(&ctl->tmem_full[acc], (chn >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + h * 64);
+        float v[32];
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          tc_ld32(taddr + part * BN, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) accum[i] += v[i];
+          tc_ld32(taddr + part * BN + 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) accum[32 + i] += v[i];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&ctl->tmem_empty[acc]);
+      }
+      const int row = m0 + q * 32 + lane;
+      if (row < M) {
+        double *o = out + (long long)row * ldo + n0 + h * 64;
+        const int ncol = min(64, Np - (n0 + h * 64));
+        if (ncol == 64 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            double2 w = make_double2((double)accum[i] * sc, (double)accum[i + 1] * sc);
+            if (accumulate_out) {
+              const double2 p = *reinterpret_cast<double2 *>(o + i);
+              w.x += p.x;
+              w.y += p.y;
+            }
+            *reinterpret_cast<double2 *>(o + i) = w;
+            for (int p = 0; p < peers.n; ++p)
+              *reinterpret_cast<double2 *>(static_cast<double *>(peers.ptr[p]) + (o - out) + i) = w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i < ncol) {
+              const double wv = (accumulate_out ? o[i] : 0.0) + (double)accum[i] * sc;
+              o[i] = wv;
+              for (int p = 0; p < peers.n; ++p) (static_cast<double *>(peers.ptr[p]) + (o - out))[i] = wv;
+            }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // neither CTA leaves (or frees TMEM) while the pair still reads its shared memory
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- factor builders
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
@@ -832,7 +1092,7 @@ EncodeTiledFn get_encode_fn() {
 // 2-D row-major operand (rows x K elements of 4 (tf32) or 2 (fp16) bytes, pitch ldk elements),
 // box = 128 rows x 128 bytes, 128B swizzle
 template <bool F16>
-int make_map(CUtensorMap *m, const void *base, long long rows, long long K, long long ldk) {
+int make_map(CUtensorMap *m, const void *base, long long rows, long long K, long long ldk, int box_rows = BM) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     tg_set_error("cuTensorMapEncodeTiled entry point not available");
@@ -840,7 +1100,7 @@ int make_map(CUtensorMap *m, const void *base, long long rows, long long K, long
   }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ldk * GemmCfg<F16>::ELEM};
-  cuuint32_t box[2] = {(cuuint32_t)GemmCfg<F16>::BK, (cuuint32_t)BM};
+  cuuint32_t box[2] = {(cuuint32_t)GemmCfg<F16>::BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -856,6 +1116,14 @@ int make_map(CUtensorMap *m, const void *base, long long rows, long long K, long
 // Host side of the work decomposition (see SkSched).  Stream-K is used when it pays: the tiles do not fill
 // whole waves of the `sms` CTAs and K is deep enough (>= 8 chunks per tile) for the pieces to amortise
 // their partial-tile round trip.  TG_GEMM_STREAMK=0 forces the plain one-tile-at-a-time schedule (A/B runs).
+// TG_GEMM_PAIR=1 enables the CTA-pair (cta_group::2) kernel for shapes whose pair tiles fill the machine
+bool pair_mode() {
+  static const bool on = [] {
+    const char *e = getenv("TG_GEMM_PAIR");
+    return e && atoi(e) != 0;
+  }();
+  return on;
+}
 int streamk_mode_default() {
   static const int mode = [] {
     const char *e = getenv("TG_GEMM_STREAMK");
@@ -917,22 +1185,16 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode
   return s;
 }
 
-template <bool F16, bool GAUSS = false>
-int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *Blo, int M, int Np, int K,
-                long long ldk, double *out, long long ldo, int accumulate, const unsigned long long *peak_key,
-                const unsigned long long *sep_guard, cudaStream_t st, const TgPeers &peers) {
-  CUtensorMap ta, tb, tc, td;
-  int rc;
-  if ((rc = make_map<F16>(&ta, Ahi, M, K, ldk)) != TG_OK) return rc;
-  if ((rc = make_map<F16>(&tb, Alo, M, K, ldk)) != TG_OK) return rc;
-  if ((rc = make_map<F16>(&tc, Bhi, Np, K, ldk)) != TG_OK) return rc;
-  if ((rc = make_map<F16>(&td, Blo, Np, K, ldk)) != TG_OK) return rc;
-  const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
-  TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<F16, GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  constexpr int NE = GAUSS ? 16 : 8;
+// Stream-K scratch supplied by the caller (tg_separable_run keeps it in its workspace: a cudaMallocAsync +
+// memset + free per GEMM launch cost 12-15 us, measured): [0, cnt_cap) arrival counters, zero (the kernel
+// leaves them zero), then the partial tiles.
+struct SkWs {
+  unsigned char *p = nullptr;
+  size_t cnt_cap = 0, bytes = 0;
+};
+inline int device_sms(int *sms_out) {
   int dev = 0, sms = 148;
   TG_CUDA(cudaGetDevice(&dev));
-  tg_tune_mempool(dev);
   static int sms_cache[64] = {0};
   if (dev >= 0 && dev < 64 && sms_cache[dev] > 0) {
     sms = sms_cache[dev];
@@ -940,25 +1202,92 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
     TG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (dev >= 0 && dev < 64) sms_cache[dev] = sms;
   }
+  *sms_out = sms;
+  return TG_OK;
+}
+template <bool F16, bool GAUSS>
+void sk_scratch_need(int M, int Np, int K, int sms, size_t *cnt_bytes, size_t *part_bytes) {
+  constexpr int NE = GAUSS ? 16 : 8;
   const SkSched sched = make_sched(M, Np, K, GemmCfg<F16>::BK, GemmCfg<F16>::CHUNK_KB, sms);
-  // stream-K scratch: arrival counters (zeroed here, left zero by the kernel) | partial tiles
-  unsigned char *sk = nullptr;
-  const size_t cnt_bytes = (((size_t)sched.R * NE * sizeof(unsigned int)) + 255) / 256 * 256;
-  const size_t part_bytes = (size_t)sched.R * sched.maxparts * (size_t)(NE * 2048) * sizeof(float);
-  if (sched.R > 0 && sched.maxparts > 1) {
-    TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&sk), cnt_bytes + part_bytes, st));
-    cudaError_t e = cudaMemsetAsync(sk, 0, cnt_bytes, st);
-    if (e != cudaSuccess) {
-      cudaFreeAsync(sk, st);
-      tg_set_error("stream-K counters: %s", cudaGetErrorString(e));
-      return TG_ECUDA;
+  const bool split = sched.R > 0 && sched.maxparts > 1;
+  *cnt_bytes = split ? (((size_t)sched.R * NE * sizeof(unsigned int)) + 255) / 256 * 256 : 0;
+  *part_bytes = split ? (size_t)sched.R * sched.maxparts * (size_t)(NE * 2048) * sizeof(float) : 0;
+}
+
+template <bool F16, bool GAUSS = false>
+int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *Blo, int M, int Np, int K,
+                long long ldk, double *out, long long ldo, int accumulate, const unsigned long long *peak_key,
+                const unsigned long long *sep_guard, cudaStream_t st, const TgPeers &peers,
+                const SkWs *skws = nullptr) {
+  CUtensorMap ta, tb, tc, td;
+  int rc;
+  if ((rc = make_map<F16>(&ta, Ahi, M, K, ldk)) != TG_OK) return rc;
+  if ((rc = make_map<F16>(&tb, Alo, M, K, ldk)) != TG_OK) return rc;
+  if ((rc = make_map<F16>(&tc, Bhi, Np, K, ldk)) != TG_OK) return rc;
+  if ((rc = make_map<F16>(&td, Blo, Np, K, ldk)) != TG_OK) return rc;
+  int sms = 148;
+  if ((rc = device_sms(&sms)) != TG_OK) return rc;
+  if constexpr (!GAUSS) {
+    // CTA-pair kernel (cta_group::2) when whole 256 x 128 pair tiles keep >= 70 % of the SM pairs busy
+    const int tiles_n = (Np + BN - 1) / BN, pair_rows = ((M + BM - 1) / BM + 1) / 2;
+    const int n_pair_tiles = tiles_n * pair_rows, slots = sms / 2;
+    const double waves = (double)n_pair_tiles / slots;
+    if (pair_mode() && M > BM && slots > 0 && waves / ceil(waves) >= 0.7) {
+      CUtensorMap tcp, tdp;
+      if ((rc = make_map<F16>(&tcp, Bhi, Np, K, ldk, BN / 2)) != TG_OK) return rc;
+      if ((rc = make_map<F16>(&tdp, Blo, Np, K, ldk, BN / 2)) != TG_OK) return rc;
+      const size_t psmem = (size_t)P_STAGES * P_STAGE_BYTES + sizeof(PairSmemCtl) + 1024;
+      TG_CUDA(cudaFuncSetAttribute(gemm_x3_pair_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      const int n_clusters = n_pair_tiles < slots ? n_pair_tiles : slots;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(2 * n_clusters));
+      cfg.blockDim = dim3(GEMM_THREADS);
+      cfg.dynamicSmemBytes = psmem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      const double hr = Headroom<F16>::value;
+      TG_CUDA(cudaLaunchKernelEx(&cfg, gemm_x3_pair_kernel<F16>, ta, tb, tcp, tdp, M, Np, K, out, ldo, accumulate,
+                                 peak_key, hr, sep_guard, peers, tiles_n, n_pair_tiles));
+      return tg_launch_check(F16 ? "gemm_x3_pair_kernel<f16>" : "gemm_x3_pair_kernel<tf32>");
+    }
+  }
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
+  TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<F16, GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const SkSched sched = make_sched(M, Np, K, GemmCfg<F16>::BK, GemmCfg<F16>::CHUNK_KB, sms);
+  size_t cnt_bytes = 0, part_bytes = 0;
+  sk_scratch_need<F16, GAUSS>(M, Np, K, sms, &cnt_bytes, &part_bytes);
+  unsigned char *sk = nullptr, *parts = nullptr;
+  bool own = false;
+  if (cnt_bytes) {
+    if (skws && skws->p && cnt_bytes <= skws->cnt_cap && skws->cnt_cap + part_bytes <= skws->bytes) {
+      sk = skws->p;                          // counters are zero on entry by contract
+      parts = skws->p + skws->cnt_cap;
+    } else {
+      int dev = 0;
+      TG_CUDA(cudaGetDevice(&dev));
+      tg_tune_mempool(dev);
+      TG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&sk), cnt_bytes + part_bytes, st));
+      own = true;
+      parts = sk + cnt_bytes;
+      cudaError_t e = cudaMemsetAsync(sk, 0, cnt_bytes, st);
+      if (e != cudaSuccess) {
+        cudaFreeAsync(sk, st);
+        tg_set_error("stream-K counters: %s", cudaGetErrorString(e));
+        return TG_ECUDA;
+      }
     }
   }
   gemm_x3_kernel<F16, GAUSS><<<(unsigned)sched.G, GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, smem, st>>>(
       ta, tb, tc, td, M, Np, K, out, ldo, accumulate, peak_key, Headroom<F16>::value, sep_guard, peers, sched,
-      sk ? reinterpret_cast<float *>(sk + cnt_bytes) : nullptr, reinterpret_cast<unsigned int *>(sk));
+      reinterpret_cast<float *>(parts), reinterpret_cast<unsigned int *>(sk));
   rc = tg_launch_check(GAUSS ? "gemm_x3_kernel<f16, 3-product>" : F16 ? "gemm_x3_kernel<f16>" : "gemm_x3_kernel<tf32>");
-  if (sk) cudaFreeAsync(sk, st);
+  if (own) cudaFreeAsync(sk, st);
   return rc;
 }
 
@@ -979,7 +1308,7 @@ template <bool F16, bool GAUSS>
 int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, long long ldk, void *Ahi, void *Alo,
                 void *Bhi, void *Blo, double *acc, const unsigned long long *peak, const unsigned long long *guard,
                 cudaStream_t st, const TgPeers &gemm_peers, int block_rows, const TgEmit *emit, void *out,
-                int out_is_c128) {
+                int out_is_c128, const SkWs *skws) {
   static_assert(!GAUSS || F16, "the 3-product formulation is implemented for fp16 x 3 operands");
   const int ldo = 2 * W;                     // doubles per output row (re, im interleaved)
   const int Np = GAUSS ? W : 2 * W;          // B rows: complex columns (3-product) or real columns
@@ -1022,7 +1351,7 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
       }
       double *acc_r = acc + (size_t)r * ldo;
       rc = launch_gemm<F16, GAUSS>(Ahi, Alo, Bhi, Blo, nr, Np, K, ldk, acc_r, (long long)ldo, b0 > 0 ? 1 : 0, peak,
-                                   guard, st, pe);
+                                   guard, st, pe, skws);
       if (rc == TG_OK && last && !out_is_c128) {
         const size_t n = (size_t)nr * ldo;
         TgPeers pc = none;   // complex64 peers are written by the conversion
@@ -1040,11 +1369,33 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
   return rc;
 }
 
-// TG_TENSOR_GAUSS=0 selects the 4-multiplication real formulation for the fp16 path (A/B runs); default: 3-product
+// stream-K scratch of a whole call: the largest need over {full, last} row block x {full, last} beamlet batch
+template <bool F16, bool GAUSS>
+void sk_need_for_call(int64_t nb, int nrows, int block_rows, int W, int sms, size_t *cnt_cap, size_t *part_cap) {
+  const int Np = GAUSS ? W : 2 * W;
+  const long long last_b = nb % kBatch ? nb % kBatch : (nb < kBatch ? nb : kBatch);
+  const long long full_b = nb < kBatch ? nb : kBatch;
+  const int last_r = nrows % block_rows ? nrows % block_rows : block_rows;
+  *cnt_cap = *part_cap = 0;
+  for (long long bsz : {full_b, last_b})
+    for (int nr : {block_rows, last_r}) {
+      const int K = GAUSS ? 3 * (int)(((bsz + KCH - 1) / KCH) * KCH) : 2 * (int)bsz;
+      size_t c = 0, p = 0;
+      sk_scratch_need<F16, GAUSS>(nr, Np, K, sms, &c, &p);
+      if (c > *cnt_cap) *cnt_cap = c;
+      if (p > *part_cap) *part_cap = p;
+    }
+}
+
+// Which formulation TG_METHOD_TENSOR / AUTO run.  Measured on B200 (C2 shape, kernel-only): the 3-product GEMM
+// does 25 % less tensor work per image but has half as many (twice as large) tiles, so C2 needs the stream-K
+// split: 0.207 ms against 0.213 ms for the 4-multiplication form on whole tiles; on row shards the
+// 4-multiplication form wins (128 rows: 0.050 vs 0.083 ms).  Default: 4-multiplication; TG_TENSOR_GAUSS=1 flips it,
+// TG_METHOD_TENSOR_3M / _4M select explicitly.
 bool use_gauss() {
   static const bool g = [] {
     const char *e = getenv("TG_TENSOR_GAUSS");
-    return !(e && atoi(e) == 0);
+    return e && atoi(e) != 0;
   }();
   return g;
 }
@@ -1178,7 +1529,8 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
     block_rows = emit->block_rows < nrows ? emit->block_rows : nrows;
   }
   const long long nbatch_max = nb < kBatch ? nb : kBatch;
-  const bool gauss = f16 == 1 && use_gauss();   // f16: 0 = tf32 x 3, 1 = fp16 x 3 (3-product unless disabled), 2 = fp16 x 3, 4-multiplication form
+  // f16: 0 = tf32 x 3, 1 = fp16 x 3 in the default formulation, 2 = fp16 x 3 4-multiplication, 3 = fp16 x 3 3-product
+  const bool gauss = f16 == 3 || (f16 == 1 && use_gauss());
   // operand row pitch: whole 128-byte k-blocks in either format; 3-product layout: 3 x 128 k per 128 beamlets
   const long long ldk = gauss ? 3 * KCH * ((nbatch_max + KCH - 1) / KCH) : ((2 * nbatch_max + 63) / 64) * 64;
   const size_t elem = f16 ? 2 : 4;
@@ -1187,8 +1539,17 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   const size_t a_bytes = verdict_only ? 0 : (((size_t)block_rows * ldk * elem + 255) / 256) * 256;
   const size_t b_bytes = verdict_only ? 0 : (((size_t)Np * ldk * elem + 255) / 256) * 256;
   const size_t acc_bytes = (out_is_c128 || verdict_only) ? 0 : npix * 16;
+  size_t sk_cnt = 0, sk_part = 0;
+  if (!verdict_only) {
+    int sms = 148;
+    int rcs = device_sms(&sms);
+    if (rcs != TG_OK) return rcs;
+    if (gauss) sk_need_for_call<true, true>(nb, nrows, block_rows, W, sms, &sk_cnt, &sk_part);
+    else if (f16) sk_need_for_call<true, false>(nb, nrows, block_rows, W, sms, &sk_cnt, &sk_part);
+    else sk_need_for_call<false, false>(nb, nrows, block_rows, W, sms, &sk_cnt, &sk_part);
+  }
   TgAsyncBuf wsb(st);
-  TG_CUDA(wsb.alloc(table_bytes + 256 + 2 * a_bytes + 2 * b_bytes + acc_bytes));
+  TG_CUDA(wsb.alloc(table_bytes + 256 + 2 * a_bytes + 2 * b_bytes + acc_bytes + sk_cnt + sk_part));
   unsigned char *ws = wsb.as<unsigned char>();
   double *table = reinterpret_cast<double *>(ws);
   // control block after the table: key (8) | peak key (8) || gref (8) at +64 || est (8) at +128
@@ -1197,6 +1558,13 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   const unsigned long long *guard = key_async ? key_async : (capturing ? key : nullptr);  // kernels decide on the device
   unsigned char *Ahi = ws + table_bytes + 256, *Alo = Ahi + a_bytes, *Bhi = Alo + a_bytes, *Blo = Bhi + b_bytes;
   double *acc = out_is_c128 ? static_cast<double *>(out) : reinterpret_cast<double *>(Blo + b_bytes);
+  SkWs skws;
+  if (sk_cnt) {
+    skws.p = Blo + b_bytes + acc_bytes;
+    skws.cnt_cap = sk_cnt;
+    skws.bytes = sk_cnt + sk_part;
+    TG_CUDA(cudaMemsetAsync(skws.p, 0, sk_cnt, st));   // arrival counters: zero once, the kernels leave them zero
+  }
   TG_CUDA(cudaMemsetAsync(ws + table_bytes, 0, 16, st));  // own key slot, peak key
   if (key_async) TG_CUDA(cudaMemsetAsync(key, 0, 8, st));
   // cost model (AUTO with culling enabled): brightest-peak key and tile estimate live after the key slot
@@ -1239,11 +1607,11 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
     }
   }
   rc = gauss ? run_batches<true, true>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
-                                       out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128)
+                                       out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128, &skws)
        : f16 ? run_batches<true, false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
-                                        out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128)
+                                        out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128, &skws)
              : run_batches<false, false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
-                                         out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128);
+                                         out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128, &skws);
   if (rc == TG_OK && !out_is_c128 && pe.n > 0) {
     // complex64 peer images: one more pass over the converted rows (the GEMM's peer stores are fp64-only)
     const size_t n = npix * 2;
@@ -1270,9 +1638,11 @@ int tg_field_sum_impl(int64_t nb, const double *poly, const double px2m[6], int 
   if (method == TG_METHOD_SFU)
     return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st,
                              peers, emit);
-  if (method == TG_METHOD_TENSOR || method == TG_METHOD_TENSOR_TF32 || method == TG_METHOD_TENSOR_4M)
+  if (method == TG_METHOD_TENSOR || method == TG_METHOD_TENSOR_TF32 || method == TG_METHOD_TENSOR_4M ||
+      method == TG_METHOD_TENSOR_3M)
     return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr, st, 0,
-                            method == TG_METHOD_TENSOR ? 1 : method == TG_METHOD_TENSOR_4M ? 2 : 0, peers, emit);
+                            method == TG_METHOD_TENSOR ? 1 : method == TG_METHOD_TENSOR_4M ? 2
+                            : method == TG_METHOD_TENSOR_3M ? 3 : 0, peers, emit);
   TG_REQUIRE(method == TG_METHOD_AUTO, "unknown method");
   if (nb == 0 || nrows == 0)
     return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st,

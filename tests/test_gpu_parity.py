@@ -489,7 +489,7 @@ def test_c2_full_size_tensor_path_vs_oracle(torch_cuda):
     g, model = M.aperture_diffraction_case(10_000, (1024, 1024))
     gd = gaussian_to_cuda(torch_cuda, g)
     pix = None
-    for method in ("tensor", "auto", "tensor_4m", "tensor_tf32"):
+    for method in ("tensor", "auto", "tensor_4m", "tensor_3m", "tensor_tf32"):
         img = to_np(make_gaussian_image_device(gd, model, cull_bits=0, method=method))
         if pix is None:
             pix = _sample_pixels(1024, 1024, bright_from=img)
@@ -516,7 +516,8 @@ def test_c3_full_size_vs_oracle(torch_cuda, variant):
     del first
     runs = [("sfu_culled", dict(method="sfu"))]
     if not general:
-        runs += [("tensor", dict(method="tensor", cull_bits=0)), ("auto_dense", dict(method="auto", cull_bits=0))]
+        runs += [("tensor", dict(method="tensor", cull_bits=0)), ("auto_dense", dict(method="auto", cull_bits=0)),
+                 ("tensor_3m", dict(method="tensor_3m", cull_bits=0))]
     for name, kw in runs:
         img = to_np(make_gaussian_image_device(gd, model, **kw))
         errs[name] = rel_l2(img.reshape(-1)[pix], ref)
@@ -735,7 +736,7 @@ def test_host_pipeline_row_blocks(torch_cuda, method):
     assert rel_l2(host_img, ref) < FIELD_TOL
 
 
-@pytest.mark.parametrize("method", ["tensor", "tensor_4m", "tensor_tf32"])
+@pytest.mark.parametrize("method", ["tensor", "tensor_4m", "tensor_3m", "tensor_tf32"])
 @pytest.mark.parametrize("name", ["c2_aperture", "c3_biprism_separable"])
 def test_tensor_path_parity(torch_cuda, name, method):
     from temgymcore_b200.gaussian import make_gaussian_image
@@ -762,7 +763,7 @@ def test_tensor_path_fp16_dynamic_range(torch_cuda, scale):
     amp = np.asarray(g.amplitude, dtype=np.float64) * 10.0 ** rng.uniform(-6, 0, np.shape(g.amplitude)) * scale
     g2 = replace(g, amplitude=amp)
     ref = O.make_gaussian_image(g2, model)
-    for method in ("tensor", "tensor_4m", "tensor_tf32"):
+    for method in ("tensor", "tensor_4m", "tensor_3m", "tensor_tf32"):
         got = make_gaussian_image(g2, model, method=method)
         assert rel_l2(got, ref) < FIELD_TOL, (method, rel_l2(got, ref))
 
