@@ -32,6 +32,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kChunk = 128;          // beamlets per staged chunk
+constexpr int kScanPer = 8;          // gather mode: bounding boxes tested per thread and scan round
+constexpr int kCandRing = 4096;      // gather mode: capacity of the candidate ring (>= kChunk + kScanPer * kThreads)
 constexpr int kRecDoubles = 18;      // tile-local record: 6 phase + 6 envelope + vertex(2) + {dd,e2} + {cr,ci}
 constexpr double kMagic = 1572864.0; // 1.5 * 2^20: ulp = 2^-32 -> low mantissa word = frac * 2^32
 constexpr double kInv2Pi = 0.15915494309189533577;
@@ -215,8 +217,10 @@ struct FieldSmem {
   alignas(8) uint64_t full[2];
   int warp_cnt[kChunk / 32];
   int n_active;
-  int cand[kChunk + kThreads];   // gather mode: beamlets (relative to the split) whose bounding box meets the tile
-  int gcnt[kThreads / 32];
+  // gather mode: the candidate list (beamlets, relative to the split, whose bounding box meets the tile) is a RING
+  // of kCandRing ints living in `raw` (the TMA staging buffers are not used in gather mode); gcnt holds the
+  // per-(sub-round, warp) hit counts of one scan round
+  int gcnt[kScanPer][kThreads / 32];
 };
 
 // WCULL: culling is enabled -> lane = row / warp = strip mapping with the per-warp column skip; the
@@ -294,8 +298,12 @@ __global__ void __launch_bounds__(kThreads, 2)
   unsigned long long my_active = 0;
   int pending = 0;                   // terms in the fp32 partials since the last flush (<= 1.5 kChunk)
 
-  int ncand = 0;                     // gather mode: candidates waiting in sm.cand
+  int ncand = 0, cand_head = 0;      // gather mode: candidates waiting in the ring / ring position of the first
   long long bpos = b_begin;          // gather mode: next beamlet to scan
+  int *cand = reinterpret_cast<int *>(sm.raw);
+  static_assert(sizeof(sm.raw) >= kCandRing * sizeof(int) && kCandRing >= kChunk + kScanPer * kThreads &&
+                    (kCandRing & (kCandRing - 1)) == 0,
+                "candidate ring");
   for (int c = 0;; ++c) {
     int cnt;
     bool near;
@@ -314,33 +322,53 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
       a = sm.raw[c & 1] + tid * 12;
     } else {
+      // One scan round tests kScanPer * 256 bounding boxes (kScanPer independent 8-byte loads per thread in
+      // flight, two barriers per round): with one box per thread and round the scan was latency-bound -- at the
+      // ~1 % hit rate of BASELINE C3 it took ~58 rounds of an L2 round trip each to collect the 128 candidates
+      // of one evaluation phase, about as long as the phase itself.  Hits are appended in beamlet order:
+      // sub-round j covers boxes bpos + j * 256 + tid.
       while (ncand < kChunk && bpos < b_end) {           // block-uniform conditions
-        const long long i = bpos + tid;
-        bool hit = false;
-        if (i < b_end) {
-          const short4 bb = __ldg(bbox + i);
-          hit = !(bb.y < c0 || bb.x > c0 + TC - 1 || bb.w < r0 || bb.z > r0 + TR - 1);
-        }
-        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
         const int warp = tid >> 5, lane = tid & 31;
-        if (lane == 0) sm.gcnt[warp] = __popc(ballot);
-        __syncthreads();
-        int base = ncand, tot = 0;
+        unsigned ballots[kScanPer];
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) {
-          const int n_w = sm.gcnt[w];
-          base += (w < warp) ? n_w : 0;
-          tot += n_w;
+        for (int j = 0; j < kScanPer; ++j) {
+          const long long i = bpos + (long long)j * kThreads + tid;
+          bool hit = false;
+          if (i < b_end) {
+            const short4 bb = __ldg(bbox + i);
+            hit = !(bb.y < c0 || bb.x > c0 + TC - 1 || bb.w < r0 || bb.z > r0 + TR - 1);
+          }
+          ballots[j] = __ballot_sync(0xffffffffu, hit);
         }
-        if (hit) sm.cand[base + __popc(ballot & ((1u << lane) - 1u))] = (int)(i - b_begin);
+        if (lane < kScanPer) {
+          unsigned b = 0;
+#pragma unroll
+          for (int j = 0; j < kScanPer; ++j) b = (lane == j) ? ballots[j] : b;
+          sm.gcnt[lane][warp] = __popc(b);
+        }
+        __syncthreads();
+        int tot = 0;
+#pragma unroll
+        for (int j = 0; j < kScanPer; ++j) {
+          int base = ncand + tot;
+#pragma unroll
+          for (int w = 0; w < kThreads / 32; ++w) {
+            const int n_w = sm.gcnt[j][w];
+            base += (w < warp) ? n_w : 0;
+            tot += n_w;
+          }
+          if (ballots[j] & (1u << lane))
+            cand[(cand_head + base + __popc(ballots[j] & ((1u << lane) - 1u))) & (kCandRing - 1)] =
+                (int)(bpos + (long long)j * kThreads + tid - b_begin);
+        }
         __syncthreads();                                 // candidates visible, gcnt reusable
         ncand += tot;
-        bpos += kThreads;
+        bpos += (long long)kScanPer * kThreads;
       }
       if (ncand == 0) break;
       cnt = ncand < kChunk ? ncand : kChunk;
       near = tid < cnt;
-      if (near) a = table + (b_begin + (long long)sm.cand[tid]) * 12;
+      if (near) a = table + (b_begin + (long long)cand[(cand_head + tid) & (kCandRing - 1)]) * 12;
     }
 
     // ---- stage: one thread per beamlet re-centres on the tile origin, culls, compacts
@@ -615,13 +643,9 @@ __global__ void __launch_bounds__(kThreads, 2)
       pending = 0;
     }
     __syncthreads();  // records and raw[c&1] are free for the next stage / TMA
-    if (gather) {       // drop the processed candidates: the rest (< kThreads) moves to the front of the list
-      const int rest = ncand - cnt;
-      const int mv = tid < rest ? sm.cand[cnt + tid] : 0;
-      __syncthreads();
-      if (tid < rest) sm.cand[tid] = mv;
-      __syncthreads();
-      ncand = rest;
+    if (gather) {       // drop the processed candidates: the ring's head moves on (no data movement, no barrier)
+      cand_head = (cand_head + cnt) & (kCandRing - 1);
+      ncand -= cnt;
     }
   }
   if (pending) {

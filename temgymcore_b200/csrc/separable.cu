@@ -82,6 +82,12 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
       "r"(c1)
       : "memory");
 }
+// L2 prefetch of a tensor tile (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tg_smem_u32(bar)) : "memory");
 }
@@ -189,6 +195,7 @@ struct GemmSmemCtl {
 // in slot order and writes the output -- deterministic, no atomics on the data path.
 struct SkSched {
   int tiles_n, T, nkb, nch, G, R, q, Tl, qh, maxparts;
+  int prefetch;   // k-blocks the producer prefetches ahead into L2 (0 = none)
 };
 struct SkUnit {
   int tile, ch0, ch1, slot, nparts;
@@ -327,9 +334,26 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
       while (itr.next(sched, cta, u)) {
         const int m0 = (u.tile / sched.tiles_n) * BM, n0 = (u.tile % sched.tiles_n) * BN;
         const int kb0 = u.ch0 * CHUNK_KB, kb1 = min(u.ch1 * CHUNK_KB, nkb);
+        // Experiment knob (TG_GEMM_PREFETCH, default 0): stream-K pieces take ~1.8x longer per k-block than whole
+        // tiles whose CTAs share operand tiles in lockstep; asking the TMA unit to prefetch the tiles `pf` k-blocks
+        // ahead into L2 (cp.async.bulk.prefetch.tensor) was measured and does NOT help (it competes with the loads).
+        const int pf = sched.prefetch;
+        if (pf > 0)
+          for (int kb = kb0; kb < min(kb0 + pf, kb1); ++kb) {
+            tma_prefetch_2d(&tmA_hi, kb * BK, m0);
+            tma_prefetch_2d(&tmA_lo, kb * BK, m0);
+            tma_prefetch_2d(&tmB_hi, kb * BK, n0);
+            tma_prefetch_2d(&tmB_lo, kb * BK, n0);
+          }
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = (int)(it % STAGES);
           const uint32_t ph = (it / STAGES) & 1u;
+          if (pf > 0 && kb + pf < kb1) {
+            tma_prefetch_2d(&tmA_hi, (kb + pf) * BK, m0);
+            tma_prefetch_2d(&tmA_lo, (kb + pf) * BK, m0);
+            tma_prefetch_2d(&tmB_hi, (kb + pf) * BK, n0);
+            tma_prefetch_2d(&tmB_lo, (kb + pf) * BK, n0);
+          }
           tg_mbar_wait(&ctl->empty[s], ph ^ 1u);
           unsigned char *st = tiles + s * STAGE_BYTES;
           tg_mbar_expect_tx(&ctl->full[s], STAGE_BYTES);
@@ -1146,6 +1170,7 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode
   s.Tl = 0;
   s.qh = 1;
   s.maxparts = 1;
+  s.prefetch = 0;
   // TG_GEMM_STREAMK: 0 = never split, 2 = split whenever the tiles leave a partial wave (experiments); default
   // 1 = split only when whole tiles would leave more than 30 % of the machine idle.  Measured on B200 (fp16 x 3,
   // N = 2048, K = 20000): 1024 rows (128 tiles, 86 % of a wave) 0.212 ms whole tiles vs 0.27 ms split -- the
@@ -1162,6 +1187,12 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode
       R = G > s.T ? s.T : 0;
     }
     if (R > 0 && G > R) {
+      static const int pf = [] {            // TG_GEMM_PREFETCH: k-blocks of L2 prefetch distance in stream-K schedules
+        const char *e = getenv("TG_GEMM_PREFETCH");
+        const int v = e ? atoi(e) : 0;      // measured on B200: any distance makes the pieces SLOWER (512 rows:
+        return (v >= 0 && v <= 64) ? v : 0;  // 0.125 ms -> 0.177 ms at 4..12 k-blocks), so the default is off
+      }();
+      s.prefetch = pf;
       s.G = G;
       s.R = R;
       s.q = (int)(((long long)R * s.nch + G - 1) / G);
