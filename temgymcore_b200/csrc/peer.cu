@@ -121,6 +121,13 @@ static int make_peers(void *const images[], int npeers, int self, size_t off, Tg
     if (p != self) pe->ptr[pe->n++] = static_cast<unsigned char *>(images[p]) + off;
   }
   *out = static_cast<unsigned char *>(images[self]) + off;
+  pe->shard_off_bytes = off;
+  static const bool cyclic = [] {          // TG_PEER_CYCLIC_ROWS=0: contiguous row blocks on the SFU path too
+    const char *e = getenv("TG_PEER_CYCLIC_ROWS");
+    return !(e && atoi(e) == 0);
+  }();
+  pe->cyc_world = cyclic ? npeers : 0;
+  pe->cyc_rank = self;
   return TG_OK;
 }
 

@@ -28,6 +28,11 @@ int tg_wave_numbers(int64_t nb, const double *wavelength, const double *pathleng
 struct TgPeers {
   int n;
   void *ptr[TG_MAX_PEERS];
+  // set by tg_field_sum_peers / tg_make_gaussian_image_peers (0 elsewhere): the byte offset of this rank's row block
+  // inside the images (ptr[] and `out` are already advanced by it), and this rank's place among the cyc_world ranks
+  // that share the image -- the SFU path may then take cyclic tile rows of the whole image instead of the block
+  size_t shard_off_bytes = 0;
+  int cyc_world = 0, cyc_rank = 0;
 };
 // Row-block emission of a field sum into HOST memory (the host-buffer entry points): the image is computed in
 // blocks of `block_rows` detector rows on the compute stream, and each finished block is copied to the host on

@@ -1359,3 +1359,39 @@ def test_scanner_descanner_array_parameters(torch_cuda):
     with pytest.raises(NotImplementedError):
         g, _ = field_cases()["c2_aperture"]
         make_gaussian_image(g, model)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case,kw", [("c2_aperture", dict(method="sfu", cull_bits=0)),
+                                     ("c3_biprism_separable", dict(method="sfu", cull_bits=40)),
+                                     ("c3_biprism_separable", dict(method="auto", cull_bits=40)),
+                                     ("c2_aperture", dict(method="tensor", cull_bits=0)),
+                                     ("c3_biprism_general", dict(method="auto", cull_bits=40))])
+def test_peer_stores_emulated_ranks_on_one_gpu(torch_cuda, case, kw, world):
+    """tg_field_sum_peers as `world` ranks would call it, one after the other on ONE GPU with `world` local images
+    standing in for the peers' images: every "rank" stores its rows into all images, so afterwards every image must
+    be the complete single-GPU image.  Exercises the peer stores of the GEMM epilogue / stream-K fix-up and of the
+    split-reduce kernel, and the SFU path's CYCLIC tile-row assignment (each rank takes every world-th 32-row tile
+    row of the whole detector), for heights that do not divide evenly."""
+    from temgymcore_b200 import _lib as L
+    from temgymcore_b200.distributed import row_shards
+    from temgymcore_b200.gaussian import _field_sum_grid, beamlet_polynomials
+    torch = torch_cuda
+    lib = L.load()
+    g, model = field_cases()[case]
+    grid = model[-1]
+    H, W = int(grid.shape[0]), int(grid.shape[1])
+    poly, n, dev = beamlet_polynomials(g, model)
+    ref = _field_sum_grid(poly, n, grid, dev, **kw)
+    images = [torch.full((H, W), float("nan"), dtype=torch.complex128, device=dev) for _ in range(world)]
+    ptrs = L.ptr_array([im.data_ptr() for im in images])
+    for rank, (r0, nr) in enumerate(row_shards(H, world)):
+        L.check(lib.tg_field_sum_peers(n, poly.data_ptr(), L.dbl_array(grid.px2m_affine), H, W, r0, nr, ptrs, world,
+                                       rank, 1, kw["cull_bits"], L.TG_METHOD[kw["method"]],
+                                       torch.cuda.current_stream().cuda_stream), "tg_field_sum_peers")
+    torch.cuda.synchronize()
+    for im in images:
+        assert not bool(torch.isnan(torch.view_as_real(im)).any())
+        assert rel_l2(to_np(im), to_np(ref)) < 1e-6
+    for im in images[1:]:            # every image received exactly the same values
+        np.testing.assert_array_equal(to_np(im), to_np(images[0]))
