@@ -284,7 +284,9 @@ int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6],
 
 /* Method dispatch for the grid field sum.  TG_METHOD_AUTO enqueues both paths with a DEVICE-side
  * separability verdict (no host synchronisation): the kernels of the path that does not apply
- * return immediately. */
+ * return immediately.  Exception: for more than 16 384 beamlets outside a stream capture the verdict
+ * (8 bytes) is read back once and only the path that applies is enqueued -- the dead launches of the
+ * other path cost more than the read-back there; under capture the device-side form is always used. */
 #define TG_METHOD_AUTO 0   /* tensor-core path when the beamlets are separable, else SFU kernel */
 #define TG_METHOD_SFU 1    /* tg_field_sum_grid */
 #define TG_METHOD_TENSOR 2 /* tg_field_sum_separable (TG_ENOTSEPARABLE if it does not apply): fp16 x 3 */

@@ -1681,9 +1681,13 @@ int tg_field_sum_impl(int64_t nb, const double *poly, const double px2m[6], int 
   TgAsyncBuf keyb(st);
   TG_CUDA(keyb.alloc(8));
   unsigned long long *key = keyb.as<unsigned long long>();
-  if (emit) {
-    // host-buffer pipeline: the call is synchronous anyway, so the verdict is read back once (8 bytes) and only
-    // the path that applies is enqueued -- block by block, each block's D2H behind its own event
+  // Large problems outside a graph capture: every kernel of the path that does not apply still has to be launched
+  // and exit (7 batches x {two factor grids of ~10^4 CTAs, GEMM} at C3: ~0.3 ms of dead launches, measured as the
+  // gap between `auto` and the explicit method), which costs far more than reading 8 bytes back once.
+  const bool host_verdict = emit != nullptr || (nb > kBatch && !tg_stream_is_capturing(st));
+  if (host_verdict) {
+    // (host-buffer pipeline: the call is synchronous anyway; only the path that applies is enqueued -- block by
+    // block, each block's D2H behind its own event)
     int rc = tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, key, st, cull_bits, 1, nullptr,
                               nullptr, TG_SEP_VERDICT_ONLY);
     if (rc != TG_OK) return rc;

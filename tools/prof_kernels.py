@@ -70,3 +70,11 @@ if what in ("field_c3",):
     for _ in range(3):
         make_gaussian_image_device(g3d, model3, method="sfu")
     torch.cuda.synchronize()
+if what in ("gemm_shard",):
+    # the stream-K shape of one rank's 128-row shard / a 256-row block of the host pipeline (C2 beamlets)
+    g, model = M.aperture_diffraction_case(10_000, (1024, 1024))
+    poly, n, _ = beamlet_polynomials(g, model)
+    for nrows in (128, 256):
+        for _ in range(3):
+            _field_sum_grid(poly, n, model[-1], dev, row0=256, nrows=nrows, method="tensor")
+    torch.cuda.synchronize()
