@@ -330,8 +330,11 @@ int tg_cgemm3_f16x3(int M, int N, int K3, const void *A_hi, const void *A_lo, co
  * units[6 i ..] = {cta, tile, chunk_begin, chunk_end, slot, nparts} (chunks of 128 k-elements),
  * sched_out[10] = {tiles_n, tiles, k_blocks, chunks, ctas, streamk_tiles, head_chunks, tail_chunks,
  * helper_chunks, max_parts}.  mode: 0 = whole tiles only, 1 = split when whole tiles would leave more than 30 % of
- * the machine idle (what the library does), 2 = split whenever the tiles leave a partial wave, -1 = the library's
- * setting (environment TG_GEMM_STREAMK, default 1).  Returns the number of units (only max_units are written). */
+ * the machine idle (what the library does: plain split-K into floor(sms / tiles) equal k-ranges per tile when
+ * 2 tiles <= sms -- then streamk_tiles == tiles and tail_chunks == 0 -- else the head / tail arrangement),
+ * 2 = split whenever the tiles leave a partial wave, 3 = like 1 with the head / tail arrangement only,
+ * -1 = the library's setting (environment TG_GEMM_STREAMK, default 1).  Returns the number of units (only
+ * max_units are written). */
 int tg_gemm_schedule(int M, int N, int K, int f16, int sms, int mode, int32_t *units, int max_units,
                      int32_t *sched_out);
 

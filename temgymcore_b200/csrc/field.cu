@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(128)
                 unsigned long long *__restrict__ gref_key, const TgPrepExtra ex) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double cross = 0.0, peak = -INFINITY;
+  unsigned long long gmin_key = ~0ULL;          // ordered key of this beamlet's smallest on-detector exponent
   if (i < nb) {
     const double *c = poly + i * 12;
     double a[2][6];
@@ -126,8 +127,8 @@ __global__ void __launch_bounds__(128)
       t[6 + j] = -G[j];
     }
     if (gref_key) {
-      const double gmin = quad_min_rect(G, (double)(H - 1), (double)(W - 1));
-      if (isfinite(gmin)) atomicMin(gref_key, enc_ordered(gmin));
+      const double gm = quad_min_rect(G, (double)(H - 1), (double)(W - 1));
+      if (isfinite(gm)) gmin_key = enc_ordered(gm);
     }
     if (ex.sep_key) {
       // cross-term contribution across the detector, in units of the separability tolerances
@@ -148,14 +149,31 @@ __global__ void __launch_bounds__(128)
       if (!isfinite(peak)) peak = -INFINITY;   // NaN / inf beamlets do not set the scale
     }
   }
-  if (ex.sep_key || ex.peak_key) {             // block-uniform: every lane of every warp gets here
+  // One atomic per warp and key, and only when it can still change the key (a plain read first: the keys move
+  // monotonically, so a stale value only costs a redundant atomic).  The per-THREAD atomicMin this replaces
+  // serialised 1e5 atomics on one address: 70 us of the 1e5-beamlet prep (ncu launch list, round 2).
+  if (gref_key) {                              // block-uniform: every lane of every warp gets here
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, gmin_key, o);
+      gmin_key = other < gmin_key ? other : gmin_key;
+    }
+    if ((threadIdx.x & 31) == 0 && gmin_key != ~0ULL && gmin_key < *reinterpret_cast<volatile unsigned long long *>(gref_key))
+      atomicMin(gref_key, gmin_key);
+  }
+  if (ex.sep_key || ex.peak_key) {
     for (int o = 16; o > 0; o >>= 1) {
       cross = fmax(cross, __shfl_xor_sync(0xffffffffu, cross, o));
       peak = fmax(peak, __shfl_xor_sync(0xffffffffu, peak, o));
     }
     if ((threadIdx.x & 31) == 0) {
-      if (ex.sep_key && cross > 0.0) atomicMax(ex.sep_key, (unsigned long long)__double_as_longlong(cross));
-      if (ex.peak_key && peak > -INFINITY) atomicMax(ex.peak_key, tg_enc_ordered(peak));
+      if (ex.sep_key && cross > 0.0) {
+        const unsigned long long k = (unsigned long long)__double_as_longlong(cross);
+        if (k > *reinterpret_cast<volatile unsigned long long *>(ex.sep_key)) atomicMax(ex.sep_key, k);
+      }
+      if (ex.peak_key && peak > -INFINITY) {
+        const unsigned long long k = tg_enc_ordered(peak);
+        if (k > *reinterpret_cast<volatile unsigned long long *>(ex.peak_key)) atomicMax(ex.peak_key, k);
+      }
     }
   }
 }
@@ -694,27 +712,29 @@ __global__ void __launch_bounds__(256)
                         const unsigned long long *__restrict__ sep_guard, const TgPeers peers, int W, int H,
                         int tile_rows, int ty_stride, int ty_phase) {
   if (sep_guard && tg_key_is_separable(*sep_guard)) return;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npix) return;
-  size_t o = i;                      // position in the output
-  if (ty_stride) {                   // cyclic tile rows: local row -> detector row
-    const size_t lr = i / (size_t)W, col = i - lr * (size_t)W;
-    const size_t grow = ((size_t)ty_phase + (lr / tile_rows) * (size_t)ty_stride) * tile_rows + lr % tile_rows;
-    if (grow >= (size_t)H) return;
-    o = grow * (size_t)W + col;
-  }
-  double re = 0.0, im = 0.0;
-  for (int s = 0; s < nsplit; ++s) {
-    const double2 v = partial[(size_t)s * npix + i];
-    re += v.x;
-    im += v.y;
-  }
-  if (out_is_c128) {
-    static_cast<double2 *>(out)[o] = make_double2(re, im);
-    for (int p = 0; p < peers.n; ++p) static_cast<double2 *>(peers.ptr[p])[o] = make_double2(re, im);  // NVLink P2P
-  } else {
-    static_cast<float2 *>(out)[o] = make_float2((float)re, (float)im);
-    for (int p = 0; p < peers.n; ++p) static_cast<float2 *>(peers.ptr[p])[o] = make_float2((float)re, (float)im);
+  // bounded grid with a stride loop: when the device-side verdict cancels the launch it costs ~2 us, not 3 ns for
+  // each of the thousands of CTAs a pixel-per-thread grid needs (13.7 us per C2 step, measured)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    size_t o = i;                      // position in the output
+    if (ty_stride) {                   // cyclic tile rows: local row -> detector row
+      const size_t lr = i / (size_t)W, col = i - lr * (size_t)W;
+      const size_t grow = ((size_t)ty_phase + (lr / tile_rows) * (size_t)ty_stride) * tile_rows + lr % tile_rows;
+      if (grow >= (size_t)H) continue;
+      o = grow * (size_t)W + col;
+    }
+    double re = 0.0, im = 0.0;
+    for (int s = 0; s < nsplit; ++s) {
+      const double2 v = partial[(size_t)s * npix + i];
+      re += v.x;
+      im += v.y;
+    }
+    if (out_is_c128) {
+      static_cast<double2 *>(out)[o] = make_double2(re, im);
+      for (int p = 0; p < peers.n; ++p) static_cast<double2 *>(peers.ptr[p])[o] = make_double2(re, im);  // NVLink P2P
+    } else {
+      static_cast<float2 *>(out)[o] = make_float2((float)re, (float)im);
+      for (int p = 0; p < peers.n; ++p) static_cast<float2 *>(peers.ptr[p])[o] = make_float2((float)re, (float)im);
+    }
   }
 }
 
@@ -755,6 +775,11 @@ __global__ void __launch_bounds__(128)
     if (out_is_c128) static_cast<double2 *>(out)[i] = make_double2(are, aim);
     else static_cast<float2 *>(out)[i] = make_float2((float)are, (float)aim);
   }
+}
+
+inline unsigned reduce_grid(size_t npix) {
+  const size_t blocks = (npix + 255) / 256, cap = 148 * 16;
+  return (unsigned)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
 }
 
 // choose the beamlet-split count so tiles*S fills whole waves of resident CTAs
@@ -885,7 +910,7 @@ int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int 
     kern<<<grid, kThreads, smem, st>>>(table, g, cull_bits > 0 ? gref : nullptr, bbox, out0, out_is_c128, partial,
                                        nullptr, sep_guard);
     if ((rc = tg_launch_check("field_grid_kernel")) != TG_OK) return rc;
-    split_reduce_kernel<<<(unsigned)((lpix + 255) / 256), 256, 0, st>>>(partial, g.nsplit, lpix, out0, out_is_c128,
+    split_reduce_kernel<<<reduce_grid(lpix), 256, 0, st>>>(partial, g.nsplit, lpix, out0, out_is_c128,
                                                                        sep_guard, base, W, H, S::TR, g.ty_stride,
                                                                        g.ty_phase);
     return tg_launch_check("split_reduce_kernel");
@@ -960,7 +985,7 @@ int tg_field_grid_run(int64_t nb, const double *poly, const double px2m[6], int 
     if (g.via_partial) {
       TgPeers pr = pe;
       for (int p = 0; p < pr.n; ++p) pr.ptr[p] = static_cast<unsigned char *>(pr.ptr[p]) + (size_t)r * W * elt;
-      split_reduce_kernel<<<(unsigned)((bpix + 255) / 256), 256, 0, st>>>(partial, g.nsplit, bpix, out_r,
+      split_reduce_kernel<<<reduce_grid(bpix), 256, 0, st>>>(partial, g.nsplit, bpix, out_r,
                                                                          out_is_c128, sep_guard, pr, W, H, S::TR, 0, 0);
       rc = tg_launch_check("split_reduce_kernel");
       if (rc != TG_OK) return rc;

@@ -923,23 +923,28 @@ __global__ void __launch_bounds__(128)
                        const unsigned long long *__restrict__ peak_key,
                        const unsigned long long *__restrict__ sep_guard) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int m0 = blockIdx.y * FS;
-  if (n >= nbatch) return;
-  const double *t = table + (b0 + n) * 12;
-  double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
-  mu += Headroom<F16>::value - tg_prescale_G(*peak_key);
-  const Strip1D st = strip_setup(t[0], t[2], t[5], t[6 + 0] + mu, t[6 + 2], t[6 + 5], (double)(row0 + m0));
+  // bounded 1-D grid walking the (beamlet block, strip) pairs: a launch that the device-side verdict cancels costs
+  // microseconds instead of ~3 ns for each of ~10^4 CTAs (measured: 245 us of dead launches per C3 image)
+  const int nbx = (nbatch + (int)blockDim.x - 1) / (int)blockDim.x, nby = (M + FS - 1) / FS;
+  for (int vb = blockIdx.x; vb < nbx * nby; vb += gridDim.x) {
+    const int n = (vb % nbx) * blockDim.x + threadIdx.x;
+    const int m0 = (vb / nbx) * FS;
+    if (n >= nbatch) continue;
+    const double *t = table + (b0 + n) * 12;
+    double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
+    mu += Headroom<F16>::value - tg_prescale_G(*peak_key);
+    const Strip1D st = strip_setup(t[0], t[2], t[5], t[6 + 0] + mu, t[6 + 2], t[6 + 5], (double)(row0 + m0));
 #pragma unroll 4
-  for (int j = 0; j < FS; ++j) {
-    if (m0 + j < M) {
-      float re, im, rh, rl, ih, il;
-      strip_eval(st, j, re, im);
-      Operand<F16>::split(re, rh, rl);
-      Operand<F16>::split(im, ih, il);
-      const long long o = (long long)(m0 + j) * ldk + 2 * n;
-      Operand<F16>::store2(Ahi, o, rh, ih);
-      Operand<F16>::store2(Alo, o, rl, il);
+    for (int j = 0; j < FS; ++j) {
+      if (m0 + j < M) {
+        float re, im, rh, rl, ih, il;
+        strip_eval(st, j, re, im);
+        Operand<F16>::split(re, rh, rl);
+        Operand<F16>::split(im, ih, il);
+        const long long o = (long long)(m0 + j) * ldk + 2 * n;
+        Operand<F16>::store2(Ahi, o, rh, ih);
+        Operand<F16>::store2(Alo, o, rl, il);
+      }
     }
   }
 }
@@ -950,24 +955,27 @@ __global__ void __launch_bounds__(128)
                        void *__restrict__ Bhi, void *__restrict__ Blo,
                        const unsigned long long *__restrict__ sep_guard) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int c0 = blockIdx.y * FS;
-  if (n >= nbatch) return;
-  const double *t = table + (b0 + n) * 12;
-  const double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1)) - Headroom<F16>::value;
-  const Strip1D st = strip_setup(0.0, t[1], t[3], -mu, t[6 + 1], t[6 + 3], (double)c0);
+  const int nbx = (nbatch + (int)blockDim.x - 1) / (int)blockDim.x, nby = (W + FS - 1) / FS;
+  for (int vb = blockIdx.x; vb < nbx * nby; vb += gridDim.x) {      // bounded grid, see factor_rows_kernel
+    const int n = (vb % nbx) * blockDim.x + threadIdx.x;
+    const int c0 = (vb / nbx) * FS;
+    if (n >= nbatch) continue;
+    const double *t = table + (b0 + n) * 12;
+    const double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1)) - Headroom<F16>::value;
+    const Strip1D st = strip_setup(0.0, t[1], t[3], -mu, t[6 + 1], t[6 + 3], (double)c0);
 #pragma unroll 4
-  for (int j = 0; j < FS; ++j) {
-    if (c0 + j < W) {
-      float re, im, rh, rl, ih, il;
-      strip_eval(st, j, re, im);
-      Operand<F16>::split(re, rh, rl);
-      Operand<F16>::split(im, ih, il);
-      const long long o0 = (long long)(2 * (c0 + j)) * ldk + 2 * n, o1 = o0 + ldk;
-      Operand<F16>::store2(Bhi, o0, rh, -ih);
-      Operand<F16>::store2(Blo, o0, rl, -il);
-      Operand<F16>::store2(Bhi, o1, ih, rh);
-      Operand<F16>::store2(Blo, o1, il, rl);
+    for (int j = 0; j < FS; ++j) {
+      if (c0 + j < W) {
+        float re, im, rh, rl, ih, il;
+        strip_eval(st, j, re, im);
+        Operand<F16>::split(re, rh, rl);
+        Operand<F16>::split(im, ih, il);
+        const long long o0 = (long long)(2 * (c0 + j)) * ldk + 2 * n, o1 = o0 + ldk;
+        Operand<F16>::store2(Bhi, o0, rh, -ih);
+        Operand<F16>::store2(Blo, o0, rl, -il);
+        Operand<F16>::store2(Bhi, o1, ih, rh);
+        Operand<F16>::store2(Blo, o1, il, rl);
+      }
     }
   }
 }
@@ -985,51 +993,54 @@ __global__ void __launch_bounds__(128)
                         const unsigned long long *__restrict__ peak_key,
                         const unsigned long long *__restrict__ sep_guard) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
-  const int n = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int s0 = blockIdx.y * FS;
-  if (n >= npad) return;
-  Strip1D st[2];
-  bool live[2];
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    live[e] = n + e < nbatch;
-    const double *t = table + (b0 + (live[e] ? n + e : 0)) * 12;
-    if (ROWS) {
-      double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
-      mu += Headroom<true>::value - tg_prescale_G(*peak_key);
-      st[e] = strip_setup(t[0], t[2], t[5], t[6 + 0] + mu, t[6 + 2], t[6 + 5], (double)(s_first + s0));
-    } else {
-      const double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1)) - Headroom<true>::value;
-      st[e] = strip_setup(0.0, t[1], t[3], -mu, t[6 + 1], t[6 + 3], (double)s0);
-    }
-  }
-  const long long kk = (long long)(n / KCH) * (3 * KCH) + (n % KCH);
-#pragma unroll 2
-  for (int j = 0; j < FS; ++j) {
-    if (s0 + j >= S) break;
-    float v[3][2];
+  const int nbx = (npad / 2 + (int)blockDim.x - 1) / (int)blockDim.x, nby = (S + FS - 1) / FS;
+  for (int vb = blockIdx.x; vb < nbx * nby; vb += gridDim.x) {      // bounded grid, see factor_rows_kernel
+    const int n = 2 * ((vb % nbx) * blockDim.x + threadIdx.x);
+    const int s0 = (vb / nbx) * FS;
+    if (n >= npad) continue;
+    Strip1D st[2];
+    bool live[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      float re = 0.f, im = 0.f;
-      if (live[e]) strip_eval(st[e], j, re, im);
+      live[e] = n + e < nbatch;
+      const double *t = table + (b0 + (live[e] ? n + e : 0)) * 12;
       if (ROWS) {
-        v[0][e] = re + im;
-        v[1][e] = re;
-        v[2][e] = im;
+        double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
+        mu += Headroom<true>::value - tg_prescale_G(*peak_key);
+        st[e] = strip_setup(t[0], t[2], t[5], t[6 + 0] + mu, t[6 + 2], t[6 + 5], (double)(s_first + s0));
       } else {
-        v[0][e] = re;
-        v[1][e] = im - re;
-        v[2][e] = re + im;
+        const double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1)) - Headroom<true>::value;
+        st[e] = strip_setup(0.0, t[1], t[3], -mu, t[6 + 1], t[6 + 3], (double)s0);
       }
     }
-    const long long o = (long long)(s0 + j) * ldk + kk;
+    const long long kk = (long long)(n / KCH) * (3 * KCH) + (n % KCH);
+#pragma unroll 2
+    for (int j = 0; j < FS; ++j) {
+      if (s0 + j >= S) break;
+      float v[3][2];
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      float h0, l0, h1, l1;
-      Operand<true>::split(v[b][0], h0, l0);
-      Operand<true>::split(v[b][1], h1, l1);
-      *reinterpret_cast<__half2 *>(hi + o + b * KCH) = __floats2half2_rn(h0, h1);
-      *reinterpret_cast<__half2 *>(lo + o + b * KCH) = __floats2half2_rn(l0, l1);
+      for (int e = 0; e < 2; ++e) {
+        float re = 0.f, im = 0.f;
+        if (live[e]) strip_eval(st[e], j, re, im);
+        if (ROWS) {
+          v[0][e] = re + im;
+          v[1][e] = re;
+          v[2][e] = im;
+        } else {
+          v[0][e] = re;
+          v[1][e] = im - re;
+          v[2][e] = re + im;
+        }
+      }
+      const long long o = (long long)(s0 + j) * ldk + kk;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        float h0, l0, h1, l1;
+        Operand<true>::split(v[b][0], h0, l0);
+        Operand<true>::split(v[b][1], h1, l1);
+        *reinterpret_cast<__half2 *>(hi + o + b * KCH) = __floats2half2_rn(h0, h1);
+        *reinterpret_cast<__half2 *>(lo + o + b * KCH) = __floats2half2_rn(l0, l1);
+      }
     }
   }
 }
@@ -1087,8 +1098,7 @@ __global__ void __launch_bounds__(256)
     f64_to_c64_kernel(const double *__restrict__ in, float *__restrict__ out, size_t n,
                       const unsigned long long *__restrict__ sep_guard, const TgPeers peers) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float v = (float)in[i];
     out[i] = v;
     for (int p = 0; p < peers.n; ++p) static_cast<float *>(peers.ptr[p])[i] = v;
@@ -1322,6 +1332,13 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
   return rc;
 }
 
+// grid of a kernel that walks `blocks` virtual blocks with a stride loop: enough CTAs to fill the machine, few enough
+// that a launch cancelled by the device-side verdict costs microseconds
+inline unsigned bounded_grid(long long blocks) {
+  const long long cap = 148LL * 16;
+  return (unsigned)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
 // explicit tensor method under stream capture: the verdict cannot be read on the host, so a non-separable
 // input poisons the output instead of being silently ignored
 __global__ void __launch_bounds__(256)
@@ -1353,11 +1370,11 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
     const bool last = b0 + kBatch >= nb;
     // (the tensor maps are encoded with the true K: the TMA unit zero-fills the K padding)
     if constexpr (GAUSS) {
-      dim3 gb((unsigned)((npad / 2 + 127) / 128), (unsigned)((W + FS - 1) / FS));
+      const unsigned gb = bounded_grid((long long)((npad / 2 + 127) / 128) * ((W + FS - 1) / FS));
       factor_gauss_kernel<false><<<gb, 128, 0, st>>>(table, b0, nbatch, npad, 0, W, W, ldk, static_cast<__half *>(Bhi),
                                                      static_cast<__half *>(Blo), peak, guard);
     } else {
-      dim3 gb((unsigned)((nbatch + 127) / 128), (unsigned)((W + FS - 1) / FS));
+      const unsigned gb = bounded_grid((long long)((nbatch + 127) / 128) * ((W + FS - 1) / FS));
       factor_cols_kernel<F16><<<gb, 128, 0, st>>>(table, b0, nbatch, W, ldk, Bhi, Blo, guard);
     }
     rc = tg_launch_check("factor_cols_kernel");
@@ -1365,12 +1382,12 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
     for (int r = 0; r < nrows && rc == TG_OK; r += block_rows, ++blk) {
       const int nr = (nrows - r) < block_rows ? (nrows - r) : block_rows;
       if constexpr (GAUSS) {
-        dim3 ga((unsigned)((npad / 2 + 127) / 128), (unsigned)((nr + FS - 1) / FS));
+        const unsigned ga = bounded_grid((long long)((npad / 2 + 127) / 128) * ((nr + FS - 1) / FS));
         factor_gauss_kernel<true><<<ga, 128, 0, st>>>(table, b0, nbatch, npad, row0 + r, nr, W, ldk,
                                                       static_cast<__half *>(Ahi), static_cast<__half *>(Alo), peak,
                                                       guard);
       } else {
-        dim3 ga((unsigned)((nbatch + 127) / 128), (unsigned)((nr + FS - 1) / FS));
+        const unsigned ga = bounded_grid((long long)((nbatch + 127) / 128) * ((nr + FS - 1) / FS));
         factor_rows_kernel<F16><<<ga, 128, 0, st>>>(table, b0, nbatch, row0 + r, nr, W, ldk, Ahi, Alo, peak, guard);
       }
       rc = tg_launch_check("factor_rows_kernel");
@@ -1387,7 +1404,7 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
         const size_t n = (size_t)nr * ldo;
         TgPeers pc = none;   // complex64 peers are written by the conversion
         float *o = static_cast<float *>(out) + (size_t)r * ldo;
-        f64_to_c64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc_r, o, n, guard, pc);
+        f64_to_c64_kernel<<<bounded_grid((long long)((n + 255) / 256)), 256, 0, st>>>(acc_r, o, n, guard, pc);
         rc = tg_launch_check("f64_to_c64_kernel");
       }
       if (rc == TG_OK && last && emit) {
@@ -1646,7 +1663,8 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   if (rc == TG_OK && !out_is_c128 && pe.n > 0) {
     // complex64 peer images: one more pass over the converted rows (the GEMM's peer stores are fp64-only)
     const size_t n = npix * 2;
-    f64_to_c64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, static_cast<float *>(out), n, guard, pe);
+    f64_to_c64_kernel<<<bounded_grid((long long)((n + 255) / 256)), 256, 0, st>>>(acc, static_cast<float *>(out), n, guard,
+                                                                           pe);
     rc = tg_launch_check("f64_to_c64_kernel");
   }
   if (rc == TG_OK && capturing) {
