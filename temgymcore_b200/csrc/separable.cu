@@ -196,11 +196,13 @@ struct GemmSmemCtl {
 struct SkSched {
   int tiles_n, T, nkb, nch, G, R, q, Tl, qh, maxparts;
   int prefetch;   // k-blocks the producer prefetches ahead into L2 (0 = none)
+  int uniform;    // > 0: plain split-K -- CTA c owns chunks [split q, split q + q) of tile c % T, split = c / T
 };
 struct SkUnit {
   int tile, ch0, ch1, slot, nparts;
 };
 __host__ __device__ inline int sk_nparts(const SkSched &s, int tile) {
+  if (s.uniform) return s.maxparts;
   if (s.Tl <= 0) return 1;
   const int first = (int)(((long long)tile * s.Tl) / s.qh);
   const int last = (int)((((long long)tile + 1) * s.Tl - 1) / s.qh);
@@ -213,7 +215,9 @@ struct SkIter {
     phase = 2;
     f0 = f1 = 0;
     t = s.R + cta;
-    if (s.R > 0) {
+    if (s.uniform) {
+      phase = 3;
+    } else if (s.R > 0) {
       if (cta < s.R) {
         phase = 0;
       } else {
@@ -228,6 +232,17 @@ struct SkIter {
     }
   }
   __host__ __device__ __forceinline__ bool next(const SkSched &s, int cta, SkUnit &u) {
+    if (phase == 3) {        // plain split-K: exactly one unit per CTA
+      phase = 4;
+      const int split = cta / s.T;
+      u.tile = cta - split * s.T;
+      u.ch0 = split * s.q;
+      u.ch1 = u.ch0 + s.q < s.nch ? u.ch0 + s.q : s.nch;
+      u.slot = split;
+      u.nparts = s.maxparts;
+      return u.ch0 < u.ch1;
+    }
+    if (phase == 4) return false;
     if (phase == 0) {
       phase = 2;
       u.tile = cta;
@@ -1162,12 +1177,12 @@ int streamk_mode_default() {
   static const int mode = [] {
     const char *e = getenv("TG_GEMM_STREAMK");
     const int v = e ? atoi(e) : 1;
-    return (v >= 0 && v <= 2) ? v : 1;
+    return (v >= 0 && v <= 3) ? v : 1;
   }();
   return mode;
 }
 SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode = -1) {
-  if (mode < 0 || mode > 2) mode = streamk_mode_default();
+  if (mode < 0 || mode > 3) mode = streamk_mode_default();   // 3 = like 1 but head / tail only (no plain split-K)
   SkSched s;
   const int tiles_m = (M + BM - 1) / BM;
   s.tiles_n = (Np + BN - 1) / BN;
@@ -1188,7 +1203,27 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode
   // 0.197 -> 0.126 ms, 256 rows 0.203 -> 0.085 ms, 128 rows (the row shard of one of 8 ranks) 0.205 -> 0.065 ms.
   const double waves = (double)s.T / sms;
   const double dp_eff = waves / ceil(waves);
-  const bool want = mode == 2 || (mode == 1 && dp_eff < 0.7);
+  const bool want = mode == 2 || ((mode == 1 || mode == 3) && dp_eff < 0.7);
+  s.uniform = 0;
+  if (want && s.nch >= 8 && sms > 1 && 2 * s.T <= sms && mode != 3) {
+    // Few tiles (a row shard, a row block of the host pipeline, the 64 complex tiles of C2 in the 3-product form):
+    // PLAIN split-K, every tile cut into S = floor(sms / T) equal k-ranges, CTA c -> (tile c mod T, range c div T).
+    // All tiles' range s is walked at the same time by the T CTAs of group s, so operand tiles are fetched from HBM
+    // once and shared through L2 within a group -- the head / tail arrangement below uses every SM but its helper
+    // CTAs each walk a k-range of their own, and with half the work in helpers (T = 64 on 148 SMs) their unshared
+    // operand reads made the kernel HBM-bound (3-product C2: 0.220 ms head / tail, 0.191 ms plain split-K).
+    int S = sms / s.T;
+    if (S > s.nch / 4) S = s.nch / 4 > 0 ? s.nch / 4 : 1;      // at least ~4 chunks per piece
+    if (S > 1) {
+      s.q = (s.nch + S - 1) / S;
+      s.maxparts = (s.nch + s.q - 1) / s.q;                    // non-empty ranges
+      s.G = s.T * s.maxparts;
+      s.R = s.T;
+      s.uniform = 1;
+      s.Tl = 0;
+      return s;
+    }
+  }
   if (want && s.nch >= 8 && sms > 1) {
     int G = sms, R = s.T % sms;
     if (s.T < sms) {
