@@ -464,25 +464,52 @@ def run_ours(args):
                            Kg, Dg.data_ptr(), Ng, 0, torch.cuda.current_stream().cuda_stream), "tg_gemm_*x3")
             gemm_ms[kind] = float(np.mean(timed(gemm, args.steps, args.warmup)))
             del Ah, Al, Bh, Bl
-        tensor_kind = "tf32" if method == "tensor_tf32" else "f16"
-        g_ms = gemm_ms[tensor_kind]
-        kind_peak = bf16 if tensor_kind == "f16" else bf16 / 2
+        # the 3-product complex GEMM (what TG_METHOD_TENSOR / auto run when the image has >= 64 tiles of 128 rows x
+        # 128 complex columns, i.e. for C2): operands in the 3-product layout, K3 = 3 * 128 * ceil(nb / 128)
+        kch = lib.tg_gemm_chunk_k()
+        groups = (nb + kch - 1) // kch
+        K3 = 3 * kch * groups
+        A3 = torch.rand((Mg, K3), generator=gen, device=dev) * 2 - 1
+        B3 = torch.rand((W, K3), generator=gen, device=dev) * 2 - 1
+        A3h, A3l = split_f16(A3)
+        B3h, B3l = split_f16(B3)
+        del A3, B3
+
+        def gemm3():
+            L.check(lib.tg_cgemm3_f16x3(Mg, W, K3, A3h.data_ptr(), A3l.data_ptr(), B3h.data_ptr(), B3l.data_ptr(), K3,
+                                        Dg.data_ptr(), Ng, 0, torch.cuda.current_stream().cuda_stream), "tg_cgemm3_f16x3")
+        gemm_ms["f16_3product"] = float(np.mean(timed(gemm3, args.steps, args.warmup)))
+        del A3h, A3l, B3h, B3l
+        forced = os.environ.get("TG_TENSOR_GAUSS")
+        three = (forced != "0") and (forced == "1" or ((H + 127) // 128) * ((W + 127) // 128) >= 64)
+        if method == "tensor_tf32":
+            tensor_kind, g_ms, exe_flop = "tf32", gemm_ms["tf32"], 2.0 * Mg * Ng * Kg * 3
+        elif method == "tensor_4m" or (method != "tensor_3m" and not three):
+            tensor_kind, g_ms, exe_flop = "f16", gemm_ms["f16"], 2.0 * Mg * Ng * Kg * 3
+        else:
+            tensor_kind, g_ms, exe_flop = "f16_3product", gemm_ms["f16_3product"], 2.0 * Mg * W * K3 * 3
+        kind_peak = bf16 / 2 if tensor_kind == "tf32" else bf16
         alg_tf = 8.0 * nb * H * W / (g_ms * 1e-3) / 1e12            # one complex MAC per beamlet*pixel
-        exe_tf = 2.0 * Mg * Ng * Kg * 3 / (g_ms * 1e-3) / 1e12      # 3 passes (hi*hi, hi*lo, lo*hi)
+        exe_tf = exe_flop / (g_ms * 1e-3) / 1e12                    # 3 passes (hi*hi, hi*lo, lo*hi)
+        kname = {"f16": "gemm_x3_kernel<f16, 4-multiplication form> (whole tiles)",
+                 "tf32": "gemm_x3_kernel<tf32>",
+                 "f16_3product": "gemm_x3_kernel<f16, 3-product complex form> (64 tiles, plain split-K in 2)"}[tensor_kind]
         roofline_tensor = {"bound": "tensor",
-                           "kernel": f"gemm_x3_kernel<{tensor_kind}> (tcgen05.mma kind::{tensor_kind}, persistent, "
-                                     "stream-K)",
+                           "kernel": kname + " -- tcgen05.mma kind::" + ("tf32" if tensor_kind == "tf32" else "f16")
+                                     + ", persistent",
                            "achieved": alg_tf, "peak": bf16, "unit": "TFLOP/s", "frac": alg_tf / bf16,
-                           "traffic": NCU_TRAFFIC[f"gemm_x3_kernel_{tensor_kind}"][0],
-                           "traffic_source": NCU_TRAFFIC[f"gemm_x3_kernel_{tensor_kind}"][1],
+                           "traffic": NCU_TRAFFIC["gemm_x3_kernel_tf32" if tensor_kind == "tf32" else "gemm_x3_kernel_f16"][0],
+                           "traffic_source": NCU_TRAFFIC["gemm_x3_kernel_tf32" if tensor_kind == "tf32" else "gemm_x3_kernel_f16"][1],
                            "kernel_ms": g_ms, "executed_tflops": exe_tf,
                            "executed_kind_peak": kind_peak, "frac_executed_vs_kind_peak": exe_tf / kind_peak,
                            "kernel_ms_by_operand_format": gemm_ms,
                            "peak_source": pk["source"] + " bf16_tflops (burst: the kernel is timed alone)",
-                           "note": "achieved = algorithmic 8 real flop per beamlet*pixel; the kernel executes 3x "
-                                   "that (hi/lo operand split needed for the 1e-5 parity) in fp16 operands with "
-                                   "fp32 accumulation; peak = measured dense bf16 = the kind::f16 rate; the TF32 "
-                                   "peak is taken as half of it",
+                           "note": "achieved = algorithmic 8 real flop per beamlet*pixel; the kernel executes the hi/lo "
+                                   "operand split needed for the 1e-5 parity (3 fp16 products per real product, fp32 "
+                                   "accumulation) on 4 (4-multiplication form) or 3 (3-product form, Gauss) real products "
+                                   "per complex term; peak = measured dense bf16 = the kind::f16 rate; the TF32 peak is "
+                                   "taken as half of it; the operand tiles here are random numbers in the layout the "
+                                   "factor kernels produce",
                            "evals_per_s": nb * H * W / (g_ms * 1e-3)}
         del A32, B32, Dg
         emit("roofline_tensor_path", roofline_tensor)

@@ -1268,6 +1268,47 @@ struct SkWs {
   unsigned char *p = nullptr;
   size_t cnt_cap = 0, bytes = 0;
 };
+// grow-only scratch of the direct GEMM entry points (see launch_gemm); counters occupy the first cnt_cap bytes
+struct SkCache {
+  unsigned char *p = nullptr;
+  size_t bytes = 0;
+  static constexpr size_t cnt_cap = 16384;      // >= 147 tiles x 16 warps x 4 bytes, rounded up
+  cudaStream_t last = nullptr;
+  cudaEvent_t ev = nullptr;
+  bool used = false;
+};
+inline SkCache *sk_cache_get(size_t part_bytes, cudaStream_t st) {
+  static thread_local SkCache caches[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SkCache &c = caches[dev];
+  const size_t need = SkCache::cnt_cap + part_bytes;
+  if (!c.ev && cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  if (c.bytes < need) {
+    if (c.p) {
+      cudaEventSynchronize(c.ev);
+      cudaFree(c.p);
+      c.p = nullptr;
+      c.bytes = 0;
+    }
+    const size_t want = need + need / 4;
+    if (cudaMalloc(reinterpret_cast<void **>(&c.p), want) != cudaSuccess) {
+      cudaGetLastError();
+      c.p = nullptr;
+      return nullptr;
+    }
+    if (cudaMemset(c.p, 0, SkCache::cnt_cap) != cudaSuccess) return nullptr;
+    c.bytes = want;
+    c.used = false;
+  }
+  if (c.used && c.last != st) cudaStreamWaitEvent(st, c.ev, 0);
+  return &c;
+}
+inline void sk_cache_release(SkCache *c, cudaStream_t st) {
+  cudaEventRecord(c->ev, st);
+  c->last = st;
+  c->used = true;
+}
 inline int device_sms(int *sms_out) {
   int dev = 0, sms = 148;
   TG_CUDA(cudaGetDevice(&dev));
@@ -1340,10 +1381,17 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
   sk_scratch_need<F16, GAUSS>(M, Np, K, sms, &cnt_bytes, &part_bytes);
   unsigned char *sk = nullptr, *parts = nullptr;
   bool own = false;
+  SkCache *cache = nullptr;
   if (cnt_bytes) {
     if (skws && skws->p && cnt_bytes <= skws->cnt_cap && skws->cnt_cap + part_bytes <= skws->bytes) {
       sk = skws->p;                          // counters are zero on entry by contract
       parts = skws->p + skws->cnt_cap;
+    } else if (!tg_stream_is_capturing(st) && cnt_bytes <= SkCache::cnt_cap &&
+               (cache = sk_cache_get(part_bytes, st)) != nullptr) {
+      // direct ABI calls (tg_gemm_*): a per-thread, per-device scratch buffer that only grows; its counters are
+      // zeroed when it is (re)allocated and left zero by every kernel; calls on another stream wait for the last user
+      sk = cache->p;
+      parts = cache->p + SkCache::cnt_cap;
     } else {
       int dev = 0;
       TG_CUDA(cudaGetDevice(&dev));
@@ -1364,6 +1412,7 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
       reinterpret_cast<float *>(parts), reinterpret_cast<unsigned int *>(sk));
   rc = tg_launch_check(GAUSS ? "gemm_x3_kernel<f16, 3-product>" : F16 ? "gemm_x3_kernel<f16>" : "gemm_x3_kernel<tf32>");
   if (own) cudaFreeAsync(sk, st);
+  if (cache) sk_cache_release(cache, st);
   return rc;
 }
 
@@ -1470,17 +1519,20 @@ void sk_need_for_call(int64_t nb, int nrows, int block_rows, int W, int sms, siz
     }
 }
 
-// Which formulation TG_METHOD_TENSOR / AUTO run.  Measured on B200 (C2 shape, kernel-only): the 3-product GEMM
-// does 25 % less tensor work per image but has half as many (twice as large) tiles, so C2 needs the stream-K
-// split: 0.207 ms against 0.213 ms for the 4-multiplication form on whole tiles; on row shards the
-// 4-multiplication form wins (128 rows: 0.050 vs 0.083 ms).  Default: 4-multiplication; TG_TENSOR_GAUSS=1 flips it,
-// TG_METHOD_TENSOR_3M / _4M select explicitly.
-bool use_gauss() {
-  static const bool g = [] {
+// Which formulation TG_METHOD_TENSOR / AUTO run.  The 3-product GEMM does 25 % less tensor work per image on tiles
+// twice as large (128 rows x 128 complex columns), so it needs >= 64 of them to keep the machine busy -- through whole
+// tiles or the plain split-K schedule.  Measured on B200: C2 (64 such tiles, split in 2) 0.191 ms against 0.208 ms
+// for the 4-multiplication form on 128 whole tiles; C3 on the tensor path 7.35 against 8.72 ms; 512 rows a tie
+// (0.120 / 0.123 ms); on smaller row blocks and shards the 4-multiplication form wins (256 rows 0.083 vs 0.091 ms,
+// 128 rows 0.063 vs 0.089 ms).  TG_TENSOR_GAUSS=0 / 1 forces one form for every shape; TG_METHOD_TENSOR_3M / _4M
+// select explicitly.
+bool use_gauss(int rows, int W) {
+  static const int forced = [] {
     const char *e = getenv("TG_TENSOR_GAUSS");
-    return e && atoi(e) != 0;
+    return e ? (atoi(e) != 0 ? 1 : 0) : -1;
   }();
-  return g;
+  if (forced >= 0) return forced == 1;
+  return (long long)((rows + BM - 1) / BM) * ((W + BN - 1) / BN) >= 64;
 }
 
 }  // namespace
@@ -1613,7 +1665,7 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   }
   const long long nbatch_max = nb < kBatch ? nb : kBatch;
   // f16: 0 = tf32 x 3, 1 = fp16 x 3 in the default formulation, 2 = fp16 x 3 4-multiplication, 3 = fp16 x 3 3-product
-  const bool gauss = f16 == 3 || (f16 == 1 && use_gauss());
+  const bool gauss = f16 == 3 || (f16 == 1 && use_gauss(block_rows, W));
   // operand row pitch: whole 128-byte k-blocks in either format; 3-product layout: 3 x 128 k per 128 beamlets
   const long long ldk = gauss ? 3 * KCH * ((nbatch_max + KCH - 1) / KCH) : ((2 * nbatch_max + 63) / 64) * 64;
   const size_t elem = f16 ? 2 : 4;
