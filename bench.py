@@ -464,7 +464,7 @@ def run_ours(args):
                            Kg, Dg.data_ptr(), Ng, 0, torch.cuda.current_stream().cuda_stream), "tg_gemm_*x3")
             gemm_ms[kind] = float(np.mean(timed(gemm, args.steps, args.warmup)))
             del Ah, Al, Bh, Bl
-        # the 3-product complex GEMM (what TG_METHOD_TENSOR / auto run when the image has >= 64 tiles of 128 rows x
+        # the 3-product complex GEMM (what TG_METHOD_TENSOR / auto run when the image has >= 32 tiles of 128 rows x
         # 128 complex columns, i.e. for C2): operands in the 3-product layout, K3 = 3 * 128 * ceil(nb / 128)
         kch = lib.tg_gemm_chunk_k()
         groups = (nb + kch - 1) // kch
@@ -481,7 +481,7 @@ def run_ours(args):
         gemm_ms["f16_3product"] = float(np.mean(timed(gemm3, args.steps, args.warmup)))
         del A3h, A3l, B3h, B3l
         forced = os.environ.get("TG_TENSOR_GAUSS")
-        three = (forced != "0") and (forced == "1" or ((H + 127) // 128) * ((W + 127) // 128) >= 64)
+        three = (forced != "0") and (forced == "1" or ((H + 127) // 128) * ((W + 127) // 128) >= 32)
         if method == "tensor_tf32":
             tensor_kind, g_ms, exe_flop = "tf32", gemm_ms["tf32"], 2.0 * Mg * Ng * Kg * 3
         elif method == "tensor_4m" or (method != "tensor_3m" and not three):

@@ -316,18 +316,18 @@ int tg_gemm_f16x3(int M, int N, int K, const void *A_hi, const void *A_lo, const
 
 /* Complex product with THREE real multiplications per term (Gauss): D[m, c] (+)= sum_n U[m, n] V[c, n], D (M, N)
  * complex128 as interleaved doubles (row pitch ldd doubles).  Operands in the 3-product layout the field sum
- * builds for its tensor path: per group g of 128 terms, k-elements [384 g, 384 g + 384) of a row hold
- * Ur + Ui | Ur | Ui (A) resp. Vr | Vi - Vr | Vr + Vi (B), each as fp16 hi and lo parts; K3 = 384 * groups.
+ * builds for its tensor path: per group g of C = tg_gemm_chunk_k() terms, k-elements [3 C g, 3 C g + 3 C) of a row hold
+ * Ur + Ui | Ur | Ui (A) resp. Vr | Vi - Vr | Vr + Vi (B), each as fp16 hi and lo parts; K3 = 3 C * groups.
  * Re = k1 - k3, Im = k1 + k2 with k1 = (Ur + Ui) Vr, k2 = Ur (Vi - Vr), k3 = Ui (Vr + Vi): 25 % less tensor work
  * than the 4-multiplication real GEMM (tg_gemm_f16x3 on the interleaved layout).  Exposed for testing. */
-int tg_gemm_chunk_k(void); /* terms per group of the 3-product layout (= k-elements per TMEM drain): 128 */
+int tg_gemm_chunk_k(void); /* terms per group of the 3-product layout (= k-elements per TMEM drain): 256 */
 int tg_cgemm3_f16x3(int M, int N, int K3, const void *A_hi, const void *A_lo, const void *B_hi, const void *B_lo,
                     long long ldk, double *D, long long ldd, int accumulate, void *stream);
 /* The GEMM is one persistent kernel (one CTA per SM): whole 128 x 128 tiles per CTA while they fill waves of
  * `sms` CTAs, and a stream-K split of the remaining tiles (or of ALL tiles when the problem has fewer tiles
  * than SMs, e.g. the row shard of one rank of a multi-GPU field sum) so that every SM gets the same amount of
  * K.  This host-only call returns that decomposition for a shape (no device needed; used by the CPU tests):
- * units[6 i ..] = {cta, tile, chunk_begin, chunk_end, slot, nparts} (chunks of 128 k-elements),
+ * units[6 i ..] = {cta, tile, chunk_begin, chunk_end, slot, nparts} (chunks of tg_gemm_chunk_k() k-elements),
  * sched_out[10] = {tiles_n, tiles, k_blocks, chunks, ctas, streamk_tiles, head_chunks, tail_chunks,
  * helper_chunks, max_parts}.  mode: 0 = whole tiles only, 1 = split when whole tiles would leave more than 30 % of
  * the machine idle (what the library does: plain split-K into floor(sms / tiles) equal k-ranges per tile when

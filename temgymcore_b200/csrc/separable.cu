@@ -58,8 +58,12 @@ static_assert(BK_BYTES == 128 || BK_BYTES == 64, "k-block = one 128-byte or 64-b
 constexpr int STAGES = 384 / BK_BYTES;          // 3 or 6 stages of 4 tiles: 192 KiB
 constexpr int TILE_BYTES = BM * BK_BYTES;       // 16 or 8 KiB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;     // A_hi, A_lo, B_hi, B_lo
+// k-elements accumulated in TMEM before the epilogue drains them into registers.  256 (round 2): the epilogue's work per
+// MMA halves -- decisive for the 3-product form, whose 16 epilogue warps pace the kernel at 128 (C2: 0.188 -> 0.178 ms;
+// 4-multiplication form 0.209 -> 0.205 ms; row shards equal or better) -- at a GEMM error of 4.0e-7 instead of 3.2e-7
+// relative to fp64 (the tensor core's accumulator truncates; the field's error stays at the ~1e-6 of its factors).
 #ifndef TG_CHUNK_K
-#define TG_CHUNK_K 128
+#define TG_CHUNK_K 256
 #endif
 constexpr int CHUNK_K = TG_CHUNK_K;             // k-elements per TMEM accumulation chunk (multiple of 64)
 template <bool F16> struct GemmCfg {
@@ -1520,19 +1524,19 @@ void sk_need_for_call(int64_t nb, int nrows, int block_rows, int W, int sms, siz
 }
 
 // Which formulation TG_METHOD_TENSOR / AUTO run.  The 3-product GEMM does 25 % less tensor work per image on tiles
-// twice as large (128 rows x 128 complex columns), so it needs >= 64 of them to keep the machine busy -- through whole
-// tiles or the plain split-K schedule.  Measured on B200: C2 (64 such tiles, split in 2) 0.191 ms against 0.208 ms
-// for the 4-multiplication form on 128 whole tiles; C3 on the tensor path 7.35 against 8.72 ms; 512 rows a tie
-// (0.120 / 0.123 ms); on smaller row blocks and shards the 4-multiplication form wins (256 rows 0.083 vs 0.091 ms,
-// 128 rows 0.063 vs 0.089 ms).  TG_TENSOR_GAUSS=0 / 1 forces one form for every shape; TG_METHOD_TENSOR_3M / _4M
-// select explicitly.
+// twice as large (128 rows x 128 complex columns), so it needs enough of them to keep the machine busy -- through whole
+// tiles or the plain split-K schedule.  Measured on B200 (256-k chunks): C2 (64 such tiles, split in 2) 0.178 ms against
+// 0.205 ms for the 4-multiplication form on 128 whole tiles; C3 on the tensor path 7.4 against 8.7 ms; 512 rows (32
+// tiles, split in 4) 0.111 against 0.119 ms; on smaller row blocks and shards the 4-multiplication form wins (256 rows
+// 0.080 vs 0.088 ms, 128 rows 0.059 vs 0.090 ms).  Hence: 3-product from 32 complex tiles on.  TG_TENSOR_GAUSS=0 / 1
+// forces one form for every shape; TG_METHOD_TENSOR_3M / _4M select explicitly.
 bool use_gauss(int rows, int W) {
   static const int forced = [] {
     const char *e = getenv("TG_TENSOR_GAUSS");
     return e ? (atoi(e) != 0 ? 1 : 0) : -1;
   }();
   if (forced >= 0) return forced == 1;
-  return (long long)((rows + BM - 1) / BM) * ((W + BN - 1) / BN) >= 64;
+  return (long long)((rows + BM - 1) / BM) * ((W + BN - 1) / BN) >= 32;
 }
 
 }  // namespace

@@ -993,7 +993,7 @@ def test_decompose_q_inv_round_trip(torch_cuda):
                         waist_xy=np.array([[w1, w2]]), radii_of_curv=np.array([[R1, R2]]), wavelength=wl,
                         theta=th).to_vector()
         img = evaluate_gaussian_input_image(g, det)
-        ow1, ow2, oR1, oR2, oth = decompose_Q_inv(g.Q_inv, wl)
+        ow1, ow2, oR1, oR2, oth = (to_np(v) for v in decompose_Q_inv(g.Q_inv, wl))   # CUDA Q_inv -> device kernel
         g2 = GaussianRay(x=0.0, y=0.0, dx=0.0, dy=0.0, z=0.0, pathlength=0.0, _one=1.0, amplitude=1.0,
                          waist_xy=np.array([[ow1[0], ow2[0]]]), radii_of_curv=np.array([[oR1[0], oR2[0]]]),
                          wavelength=wl, theta=oth).to_vector()
