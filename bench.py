@@ -348,9 +348,10 @@ def run_ours(args):
                          else False)
         if plan["p"]:
             img = plan["p"].run()
+            launches["n"] += LAUNCHES[plan["p"].method]     # auto is resolved at plan build: one path's launches
         else:
             img = make_gaussian_image_device(g_dev, model, cull_bits=0, method=method)
-        launches["n"] += LAUNCHES[method]
+            launches["n"] += LAUNCHES[method]
         return img
 
     sampler = ClockSampler(local)
@@ -359,7 +360,8 @@ def run_ours(args):
     launches["n"] = 0
     times = timed(step_device, args.steps, args.warmup)
     total_ms = max_over_ranks(float(np.sum(times)))
-    n_launch = launches["n"] - LAUNCHES[method] * args.warmup
+    per_step = LAUNCHES[plan["p"].method] if plan["p"] else LAUNCHES[method]
+    n_launch = launches["n"] - per_step * args.warmup
     evals_per_step = C2_NB * H * W * world          # N images per step at N GPUs
     ms_per_step = total_ms / args.steps
     value = evals_per_step / (ms_per_step * 1e-3)
@@ -797,7 +799,9 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": C2_WORKLOAD,
                        "sum": "dense (cull_bits=0)",
-                       "method": method + (" -> tensor-core path (C2 is separable)" if method == "auto" else ""),
+                       "method": method + ((" -> " + plan["p"].method + " (resolved once at plan build from the device-side "
+                                            "separability / cost verdict; C2 is separable)") if plan["p"] and method == "auto"
+                                           else ""),
                        "launch": "CUDA graph replay of the step (GaussianImagePlan), inputs resident in the "
                                  "plan's HBM buffers" if args.graph else "direct launches",
                        "ms_per_call_direct": direct_ms,

@@ -299,6 +299,13 @@ int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6],
 int tg_field_sum(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                  int nrows, void *out, int out_is_c128, int cull_bits, int method, void *stream);
 
+/* The verdict TG_METHOD_AUTO reaches on the device for these beamlets on this grid, read back to the host
+ * (synchronises `stream`; not inside a stream capture): *use_tensor = 1 -> tensor-core path (separable, and not clearly
+ * more expensive than the culled SFU sum), 0 -> SFU kernel.  Plans (GaussianImagePlan, PeerImagePlan) call it once at
+ * build time and capture the launches of that one path. */
+int tg_field_sum_verdict(int64_t nb, const double *poly, const double px2m[6], int H, int W, int cull_bits,
+                         int *use_tensor, void *stream);
+
 /* D[M x N] = (A_hi + A_lo)[M x K] * (B_hi + B_lo)[N x K]^T, products hi*hi + hi*lo + lo*hi on the
  * tensor cores (kind::tf32, fp32 TMEM accumulation drained every 128 k), fp64 output with row pitch
  * ldd.  Operands: device fp32, row pitch ldk elements (multiple of 4), 16-byte aligned; hi parts

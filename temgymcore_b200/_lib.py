@@ -97,6 +97,7 @@ SIGNATURES = {
     "tg_field_sum": (_i32, [_i64, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "tg_make_gaussian_image_f64": (_i32, [C.POINTER(tg_model), _i64, C.POINTER(_vp), _vp, _vp, _vp,
                                           _vp, _vp, _dp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
+    "tg_field_sum_verdict": (_i32, [_i64, _vp, _dp, _i32, _i32, _i32, C.POINTER(C.c_int), _vp]),
     "tg_gemm_tf32x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
     "tg_gemm_f16x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
     "tg_gemm_chunk_k": (_i32, []),

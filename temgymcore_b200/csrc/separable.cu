@@ -1766,6 +1766,31 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   return rc;
 }
 
+// The verdict TG_METHOD_AUTO reaches on the device, read back to the host (synchronises `stream`): 1 = the tensor-core
+// path applies (separable, and not clearly more expensive than the culled SFU sum), 0 = SFU kernel.  Plans use it to
+// freeze the dispatch at build time, so that the captured graph holds the launches of ONE path only.
+extern "C" int tg_field_sum_verdict(int64_t nb, const double *poly, const double px2m[6], int H, int W, int cull_bits,
+                                    int *use_tensor, void *stream) {
+  TG_REQUIRE(use_tensor && px2m && H > 0 && W > 0 && nb >= 0, "bad arguments");
+  *use_tensor = 0;
+  if (nb == 0) return TG_OK;
+  TG_REQUIRE(poly, "null poly");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TG_REQUIRE(!tg_stream_is_capturing(st), "the verdict is read back on the host: not inside a stream capture");
+  TgAsyncBuf keyb(st);
+  TG_CUDA(keyb.alloc(16));
+  unsigned long long *key = keyb.as<unsigned long long>();
+  // (the output pointer is only range-checked in verdict-only mode)
+  int rc = tg_separable_run(nb, poly, px2m, H, W, 0, H, key + 1, 1, key, st, cull_bits, 1, nullptr, nullptr,
+                            TG_SEP_VERDICT_ONLY);
+  if (rc != TG_OK) return rc;
+  unsigned long long hkey = 0;
+  TG_CUDA(cudaMemcpyAsync(&hkey, key, 8, cudaMemcpyDeviceToHost, st));
+  TG_CUDA(cudaStreamSynchronize(st));
+  *use_tensor = tg_key_is_separable(hkey) ? 1 : 0;
+  return TG_OK;
+}
+
 // method dispatch: AUTO enqueues BOTH paths with a device-side separability verdict (no host sync)
 extern "C" int tg_field_sum(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                             int nrows, void *out, int out_is_c128, int cull_bits, int method, void *stream) {

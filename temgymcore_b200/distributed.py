@@ -311,9 +311,15 @@ class PeerImagePlan:
     device-side barrier, with no host work between the kernels.  All ranks must call ``run()`` the same number
     of times.  ``update(rays)`` copies new beamlet parameters into the static buffers (same on all ranks)."""
 
-    def __init__(self, gaussian_rays, model, peer_image: "PeerImage", *, cull_bits=None, method="auto"):
+    def __init__(self, gaussian_rays, model, peer_image: "PeerImage", *, cull_bits=None, method="auto",
+                 freeze_dispatch: bool = True):
         import torch
-        from .gaussian import _beamlet_arrays, _device_for
+        from .gaussian import _beamlet_arrays, _device_for, auto_dispatch
+        if method == "auto" and freeze_dispatch:
+            # resolved once, from the inputs every rank holds (same verdict on every rank): the graph then holds the
+            # launches of one path only -- see GaussianImagePlan
+            method = auto_dispatch(gaussian_rays, list(model), cull_bits)
+        self.method = method
         from .gaussian import compile_model
         self.pimg = peer_image
         grid = model[-1]

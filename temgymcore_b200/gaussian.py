@@ -475,6 +475,22 @@ def make_gaussian_image_device(gaussian_rays, model, *, cull_bits=None, out_dtyp
     return out
 
 
+def auto_dispatch(gaussian_rays, model, cull_bits=None) -> str:
+    """What ``method="auto"`` decides for these beamlets on ``model[-1]``: ``"tensor"`` or ``"sfu"``
+    (``tg_field_sum_verdict``: the device-side separability + cost verdict, read back once; synchronises)."""
+    lib = L.load()
+    grid = model[-1]
+    poly, nb, dev = beamlet_polynomials(gaussian_rays, model)
+    cull = DEFAULT_CULL_BITS if cull_bits is None else int(cull_bits)
+    use = C.c_int(0)
+    import torch
+    with torch.cuda.device(dev):
+        L.check(lib.tg_field_sum_verdict(nb, poly.data_ptr() if nb else None, L.dbl_array(grid.px2m_affine),
+                                         int(grid.shape[0]), int(grid.shape[1]), cull, C.byref(use),
+                                         A.current_stream_ptr(dev)), "tg_field_sum_verdict")
+    return "tensor" if use.value else "sfu"
+
+
 class GaussianImagePlan:
     """``make_gaussian_image`` captured once into a CUDA graph and replayed.
 
@@ -486,9 +502,18 @@ class GaussianImagePlan:
     tensor.  The model (component parameters) is baked into the graph; build a new plan to change it.
     """
 
-    def __init__(self, gaussian_rays, model, *, cull_bits=None, out_dtype=None, method="auto"):
+    def __init__(self, gaussian_rays, model, *, cull_bits=None, out_dtype=None, method="auto",
+                 freeze_dispatch: bool = True):
+        """``freeze_dispatch`` (default): ``method="auto"`` is resolved ONCE, here, from the plan's first beamlets
+        (``auto_dispatch``) and the graph holds the launches of that path only; ``self.method`` tells which.  The
+        tensor path keeps its device-side separability guard: if ``update()`` later brings beamlets that are not
+        separable on this grid the image is filled with NaN -- build a new plan (or pass ``freeze_dispatch=False``
+        to keep both paths and the device-side verdict in the graph) when the beamlet class can change."""
         import torch
         self._model = list(model)
+        if method == "auto" and freeze_dispatch:
+            method = auto_dispatch(gaussian_rays, self._model, cull_bits)
+        self.method = method
         self._kw = dict(cull_bits=cull_bits, out_dtype=out_dtype, method=method)
         dev = _device_for(gaussian_rays)
         self.device = dev

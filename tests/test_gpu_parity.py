@@ -1123,6 +1123,37 @@ def test_gaussian_image_plan_cuda_graph(torch_cuda):
         np.testing.assert_array_equal(out2, make_gaussian_image(g2, model, cull_bits=0))
 
 
+def test_gaussian_image_plan_explicit_tensor_and_scalar_fields(torch_cuda):
+    """(a) explicit tensor methods are capture-safe (the separability verdict stays on the device
+    under capture; a non-separable input is caught by the plan's eager warm-up), (b) Python-scalar GaussianRay fields
+    are materialised before the capture and honoured by update()."""
+    from dataclasses import fields, replace
+    from temgymcore_b200 import _lib as L
+    from temgymcore_b200.gaussian import GaussianImagePlan, make_gaussian_image_device
+    g, model = field_cases()["c2_aperture"]
+    gd = replace(g, **{f.name: torch_cuda.as_tensor(getattr(g, f.name), device="cuda") for f in fields(g)})
+    for method in ("tensor", "tensor_3m", "tensor_4m", "tensor_tf32"):
+        plan = GaussianImagePlan(gd, model, cull_bits=0, method=method)
+        eager = make_gaussian_image_device(gd, model, cull_bits=0, method=method)
+        for _ in range(2):
+            np.testing.assert_array_equal(to_np(plan.run()), to_np(eager))
+    gg, model_g = field_cases()["c3_biprism_general"]          # not separable
+    ggd = replace(gg, **{f.name: torch_cuda.as_tensor(getattr(gg, f.name), device="cuda") for f in fields(gg)})
+    with pytest.raises(L.TemGymError):
+        GaussianImagePlan(ggd, model_g, method="tensor")
+    # scalar wavelength / amplitude in the plan's inputs: baked as tensors, replaced by update()
+    gs = replace(gd, wavelength=float(np.asarray(g.wavelength).reshape(-1)[0]),
+                 amplitude=float(np.asarray(g.amplitude).reshape(-1)[0]))
+    plan = GaussianImagePlan(gs, model, cull_bits=0)
+    ref = O.make_gaussian_image(g, model)
+    assert rel_l2(to_np(plan.run()), ref) < FIELD_TOL
+    g2 = replace(g, amplitude=np.asarray(g.amplitude) * 3.0)
+    out2 = to_np(plan.update(replace(gs, amplitude=float(np.asarray(g2.amplitude).reshape(-1)[0]))).run())
+    assert rel_l2(out2, 3.0 * ref) < FIELD_TOL
+    with pytest.raises(ValueError):
+        plan.update(replace(gs, x=np.zeros(7)))
+
+
 def test_ray_trace_plan_cuda_graph(torch_cuda):
     from temgymcore_b200.ray import RAY_FIELDS
     from temgymcore_b200.run import RayTracePlan, run_to_end, run_to_end_abcd
