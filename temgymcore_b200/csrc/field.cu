@@ -32,12 +32,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kChunk = 128;          // beamlets per staged chunk
-constexpr int kScanPer = 4;          // gather mode: bounding boxes tested per thread and scan round
-constexpr int kCandRing = 2048;      // gather mode: capacity of the candidate ring (>= kPhaseG + kScanPer * kThreads)
-constexpr int kPhaseG = 240;         // gather mode: records per evaluation phase (128 in sm.rec + 112 in the free part of
-                                     // the TMA staging area): half as many end-of-phase barriers as 128-record phases --
-                                     // ncu put 15 % of all warp samples on that barrier (warps that skipped more records
-                                     // wait for the slowest) -- and 7.5 instead of 4 warps share the fp64 staging work
+constexpr int kScanPer = 8;          // gather mode: bounding boxes tested per thread and scan round
+constexpr int kCandRing = 4096;      // gather mode: capacity of the candidate ring (>= kChunk + kScanPer * kThreads)
 constexpr int kRecDoubles = 18;      // tile-local record: 6 phase + 6 envelope + vertex(2) + {dd,e2} + {cr,ci}
 constexpr double kMagic = 1572864.0; // 1.5 * 2^20: ulp = 2^-32 -> low mantissa word = frac * 2^32
 constexpr double kInv2Pi = 0.15915494309189533577;
@@ -241,7 +237,7 @@ struct FieldSmem {
   alignas(16) Rec rec[kChunk];
   alignas(16) double acc[2 * L * kThreads];  // [component][j][thread]
   alignas(8) uint64_t full[2];
-  int warp_cnt[kThreads / 32];
+  int warp_cnt[kChunk / 32];
   int n_active;
   // gather mode: the candidate list (beamlets, relative to the split, whose bounding box meets the tile) is a RING
   // of kCandRing ints living in `raw` (the TMA staging buffers are not used in gather mode); gcnt holds the
@@ -328,13 +324,9 @@ __global__ void __launch_bounds__(kThreads, 2)
   int ncand = 0, cand_head = 0;      // gather mode: candidates waiting in the ring / ring position of the first
   long long bpos = b_begin;          // gather mode: next beamlet to scan
   int *cand = reinterpret_cast<int *>(sm.raw);
-  Rec *rec2 = reinterpret_cast<Rec *>(reinterpret_cast<unsigned char *>(sm.raw) + kCandRing * sizeof(int));
-  static_assert(sizeof(sm.raw) >= kCandRing * sizeof(int) + (kPhaseG - kChunk) * sizeof(Rec) &&
-                    kCandRing >= kPhaseG + kScanPer * kThreads && (kCandRing & (kCandRing - 1)) == 0 &&
-                    kPhaseG <= kThreads && (kCandRing * sizeof(int)) % 16 == 0,
-                "candidate ring + second record buffer inside the staging area");
-  const int phase_cap = gather ? kPhaseG : kChunk;
-  auto recp = [&](int n) -> Rec * { return n < kChunk ? &sm.rec[n] : &rec2[n - kChunk]; };
+  static_assert(sizeof(sm.raw) >= kCandRing * sizeof(int) && kCandRing >= kChunk + kScanPer * kThreads &&
+                    (kCandRing & (kCandRing - 1)) == 0,
+                "candidate ring");
   for (int c = 0;; ++c) {
     int cnt;
     bool near;
@@ -358,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 2)
       // ~1 % hit rate of BASELINE C3 it took ~58 rounds of an L2 round trip each to collect the 128 candidates
       // of one evaluation phase, about as long as the phase itself.  Hits are appended in beamlet order:
       // sub-round j covers boxes bpos + j * 256 + tid.
-      while (ncand < phase_cap && bpos < b_end) {        // block-uniform conditions
+      while (ncand < kChunk && bpos < b_end) {           // block-uniform conditions
         const int warp = tid >> 5, lane = tid & 31;
         unsigned ballots[kScanPer];
 #pragma unroll
@@ -397,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         bpos += (long long)kScanPer * kThreads;
       }
       if (ncand == 0) break;
-      cnt = ncand < phase_cap ? ncand : phase_cap;
+      cnt = ncand < kChunk ? ncand : kChunk;
       near = tid < cnt;
       if (near) a = table + (b_begin + (long long)cand[(cand_head + tid) & (kCandRing - 1)]) * 12;
     }
@@ -496,18 +488,18 @@ __global__ void __launch_bounds__(kThreads, 2)
       // order-preserving compaction (determinism: beamlets stay in natural order)
       const unsigned ballot = __ballot_sync(0xffffffffu, keep);
       const int warp = tid >> 5, lane = tid & 31;
-      if (lane == 0) sm.warp_cnt[warp] = __popc(ballot);          // (threads beyond cnt have keep == false)
+      if (warp < kChunk / 32 && lane == 0) sm.warp_cnt[warp] = __popc(ballot);
       __syncthreads();
-      {
+      if (warp < kChunk / 32) {
         int base = 0;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) base += (w < warp) ? sm.warp_cnt[w] : 0;
-        if (keep) *recp(base + __popc(ballot & ((1u << lane) - 1u))) = rec;
+        for (int w = 0; w < kChunk / 32; ++w) base += (w < warp) ? sm.warp_cnt[w] : 0;
+        if (keep) sm.rec[base + __popc(ballot & ((1u << lane) - 1u))] = rec;
       }
       if (tid == 0) {
         int tot = 0;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) tot += sm.warp_cnt[w];
+        for (int w = 0; w < kChunk / 32; ++w) tot += sm.warp_cnt[w];
         sm.n_active = tot;
       }
       __syncthreads();
@@ -520,17 +512,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 
     // ---- evaluate: every thread, its strip of L pixels, all active beamlets of the chunk
     for (int n = 0; n < n_active; ++n) {
-      if (pending >= kChunk) {          // long phases: keep the fp32 partial sums at <= 128 terms (own slots: no barrier)
-#pragma unroll
-        for (int j = 0; j < L; ++j) {
-          sm.acc[j * kThreads + tid] += (double)pr[j];
-          sm.acc[(L + j) * kThreads + tid] += (double)pi[j];
-          pr[j] = 0.f;
-          pi[j] = 0.f;
-        }
-        pending = 0;
-      }
-      const Rec &q = *recp(n);
+      const Rec &q = sm.rec[n];
       if constexpr (WCULL) {
         const uint32_t cs = q.cspan;                                  // warp-uniform: same q, same v0
         if (v0 + L - 1 < (int)(cs & 0xffffu) || v0 > (int)(cs >> 16)) continue;
