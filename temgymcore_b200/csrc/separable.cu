@@ -201,16 +201,17 @@ struct SkSched {
   int tiles_n, T, nkb, nch, G, R, q, Tl, qh, maxparts;
   int prefetch;   // k-blocks the producer prefetches ahead into L2 (0 = none)
   int uniform;    // > 0: plain split-K -- CTA c owns chunks [split q, split q + q) of tile c % T, split = c / T
+  int S;          // head / tail arrangement: full pieces of q chunks per stream-K tile (1 = heads only)
 };
 struct SkUnit {
   int tile, ch0, ch1, slot, nparts;
 };
 __host__ __device__ inline int sk_nparts(const SkSched &s, int tile) {
   if (s.uniform) return s.maxparts;
-  if (s.Tl <= 0) return 1;
+  if (s.Tl <= 0) return s.S;
   const int first = (int)(((long long)tile * s.Tl) / s.qh);
   const int last = (int)((((long long)tile + 1) * s.Tl - 1) / s.qh);
-  return 2 + last - first;
+  return s.S + 1 + last - first;
 }
 struct SkIter {
   int phase;  // 0: head of a stream-K tile pending, 1: helper walking its run of tail chunks, 2: data-parallel tiles
@@ -222,12 +223,12 @@ struct SkIter {
     if (s.uniform) {
       phase = 3;
     } else if (s.R > 0) {
-      if (cta < s.R) {
+      if (cta < s.S * s.R) {
         phase = 0;
       } else {
         phase = 1;
         const long long tot = (long long)s.R * s.Tl;
-        long long a = (long long)(cta - s.R) * s.qh, b = a + s.qh;
+        long long a = (long long)(cta - s.S * s.R) * s.qh, b = a + s.qh;
         if (a > tot) a = tot;
         if (b > tot) b = tot;
         f0 = (int)a;
@@ -247,13 +248,14 @@ struct SkIter {
       return u.ch0 < u.ch1;
     }
     if (phase == 4) return false;
-    if (phase == 0) {
+    if (phase == 0) {        // full piece `cta / R` of stream-K tile `cta % R`
       phase = 2;
-      u.tile = cta;
-      u.ch0 = 0;
-      u.ch1 = s.q;
-      u.slot = 0;
-      u.nparts = sk_nparts(s, cta);
+      const int piece = cta / s.R;
+      u.tile = cta - piece * s.R;
+      u.ch0 = piece * s.q;
+      u.ch1 = u.ch0 + s.q;
+      u.slot = piece;
+      u.nparts = sk_nparts(s, u.tile);
       return true;
     }
     if (phase == 1) {
@@ -262,9 +264,9 @@ struct SkIter {
         int c1 = c0 + (f1 - f0);
         if (c1 > s.Tl) c1 = s.Tl;
         u.tile = tile;
-        u.ch0 = s.q + c0;
-        u.ch1 = s.q + c1;
-        u.slot = 1 + (cta - s.R) - (int)(((long long)tile * s.Tl) / s.qh);
+        u.ch0 = s.S * s.q + c0;
+        u.ch1 = s.S * s.q + c1;
+        u.slot = s.S + (cta - s.S * s.R) - (int)(((long long)tile * s.Tl) / s.qh);
         u.nparts = sk_nparts(s, tile);
         f0 += c1 - c0;
         return true;
@@ -1181,12 +1183,12 @@ int streamk_mode_default() {
   static const int mode = [] {
     const char *e = getenv("TG_GEMM_STREAMK");
     const int v = e ? atoi(e) : 1;
-    return (v >= 0 && v <= 3) ? v : 1;
+    return (v >= 0 && v <= 4) ? v : 1;
   }();
   return mode;
 }
 SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode = -1) {
-  if (mode < 0 || mode > 3) mode = streamk_mode_default();   // 3 = like 1 but head / tail only (no plain split-K)
+  if (mode < 0 || mode > 4) mode = streamk_mode_default();   // 3 = like 1 but head / tail only, 4 = like 1 with split-K tails
   SkSched s;
   const int tiles_m = (M + BM - 1) / BM;
   s.tiles_n = (Np + BN - 1) / BN;
@@ -1199,6 +1201,7 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode
   s.Tl = 0;
   s.qh = 1;
   s.maxparts = 1;
+  s.S = 1;
   s.prefetch = 0;
   // TG_GEMM_STREAMK: 0 = never split, 2 = split whenever the tiles leave a partial wave (experiments); default
   // 1 = split only when whole tiles would leave more than 30 % of the machine idle.  Measured on B200 (fp16 x 3,
@@ -1207,9 +1210,9 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode
   // 0.197 -> 0.126 ms, 256 rows 0.203 -> 0.085 ms, 128 rows (the row shard of one of 8 ranks) 0.205 -> 0.065 ms.
   const double waves = (double)s.T / sms;
   const double dp_eff = waves / ceil(waves);
-  const bool want = mode == 2 || ((mode == 1 || mode == 3) && dp_eff < 0.7);
+  const bool want = mode == 2 || ((mode == 1 || mode == 3 || mode == 4) && dp_eff < 0.7);
   s.uniform = 0;
-  if (want && s.nch >= 8 && sms > 1 && 2 * s.T <= sms && mode != 3) {
+  if (want && s.nch >= 8 && sms > 1 && 2 * s.T <= sms && mode != 3) {      // (mode 4: split-K pieces + tails on the SMs left over)
     // Few tiles (a row shard, a row block of the host pipeline, the 64 complex tiles of C2 in the 3-product form):
     // PLAIN split-K, every tile cut into S = floor(sms / T) equal k-ranges, CTA c -> (tile c mod T, range c div T).
     // All tiles' range s is walked at the same time by the T CTAs of group s, so operand tiles are fetched from HBM
@@ -1218,6 +1221,27 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode
     // operand reads made the kernel HBM-bound (3-product C2: 0.220 ms head / tail, 0.191 ms plain split-K).
     int S = sms / s.T;
     if (S > s.nch / 4) S = s.nch / 4 > 0 ? s.nch / 4 : 1;      // at least ~4 chunks per piece
+    // ... and when S pieces per tile leave SMs over (64 tiles x 2 = 128 of 148), the pieces shrink to q = ceil(T nch /
+    // sms) chunks and the remaining nch - S q chunks of every tile -- the SAME k-range for all tiles -- are laid end
+    // to end for the sms - S T helper CTAs: every SM gets the same work, and only a small part of it (13 % for C2)
+    // is done outside the lockstep groups.  MEASURED (B200, C2 3-product GEMM): 0.186 ms against 0.178 ms for the plain
+    // split on 128 SMs -- the GEMM runs at the board's power cap, where 20 more SMs reading k-ranges nobody shares buy
+    // nothing -- so this arrangement is opt-in (mode 4) and the default stays the plain split
+    const int helpers = sms - S * s.T;
+    const int q_all = (int)(((long long)s.T * s.nch + sms - 1) / sms);
+    if (S > 1 && mode == 4 && helpers >= sms / 16 && S * q_all < s.nch && s.nch - S * q_all >= 4) {
+      s.S = S;
+      s.q = q_all;
+      s.Tl = s.nch - S * q_all;
+      s.qh = (int)(((long long)s.T * s.Tl + helpers - 1) / helpers);
+      s.R = s.T;
+      s.G = sms;
+      for (int t = 0; t < s.R; ++t) {
+        const int n = sk_nparts(s, t);
+        if (n > s.maxparts) s.maxparts = n;
+      }
+      return s;
+    }
     if (S > 1) {
       s.q = (s.nch + S - 1) / S;
       s.maxparts = (s.nch + s.q - 1) / s.q;                    // non-empty ranges
@@ -1432,8 +1456,8 @@ inline unsigned bounded_grid(long long blocks) {
 __global__ void __launch_bounds__(256)
     nan_fill_kernel(double *__restrict__ out, size_t n, const unsigned long long *__restrict__ key) {
   if (tg_key_is_separable(*key)) return;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __longlong_as_double(0x7ff8000000000000LL);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
 // Batches of kBatch beamlets (outer loop: the column factors of a batch are built once) x row blocks (inner
@@ -1760,7 +1784,7 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   }
   if (rc == TG_OK && capturing) {
     const size_t n = npix * (out_is_c128 ? 2 : 1);   // complex64: one NaN double covers (re, im)
-    nan_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<double *>(out), n, key);
+    nan_fill_kernel<<<bounded_grid((long long)((n + 255) / 256)), 256, 0, st>>>(static_cast<double *>(out), n, key);
     rc = tg_launch_check("nan_fill_kernel");
   }
   return rc;

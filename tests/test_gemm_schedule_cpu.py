@@ -18,6 +18,7 @@ SHAPES = [
     (2048, 4096, 3392, 1),               # C3 last batch
     (100, 72, 40, 1), (128, 128, 128, 1), (130, 260, 1000, 1), (1, 1, 1, 1), (4096, 128, 64, 1),
     (1024, 2048, 20000, 0), (300, 500, 4000, 0), (128, 2048, 777, 0),
+    (1024, 1024, 30720, 1), (512, 1024, 30720, 1), (512, 2048, 20000, 1),   # 3-product C2 and its row blocks: pieces + tails
     (19 * 128, 128, 5000, 1),            # 19 tiles
     (148 * 128, 128, 4096, 1),           # exactly one wave: no stream-K
     (149 * 128, 128, 4096, 1),           # one wave + 1 tile
@@ -36,7 +37,7 @@ def schedule(M, N, K, f16, sms=148, mode=2):
     return units, dict(zip(keys, list(sched)))
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("M,N,K,f16", SHAPES)
 def test_every_chunk_covered_once(M, N, K, f16, mode):
     units, s = schedule(M, N, K, f16, mode=mode)
@@ -104,6 +105,29 @@ def test_plain_split_k_groups_walk_k_in_lockstep():
         assert c0 == slot * s["q"] and c1 == min(s["nch"], c0 + s["q"])
     _, s3 = schedule(256, 2048, 20000, 1, mode=3)             # mode 3: head / tail instead
     assert s3["G"] == 148 and s3["Tl"] > 0
+
+
+def test_split_k_with_tails_fills_the_idle_sms():
+    """Opt-in mode 4 (measured slower than the plain split at the power cap, kept for other boards).
+    The 3-product C2 GEMM (64 tiles): 2 full pieces per tile on 128 CTAs walking k in lockstep, and the last chunks
+    of every tile -- one common k-range -- laid end to end over the other 20 SMs; every CTA within a chunk of ideal."""
+    kch = L.load().tg_gemm_chunk_k()
+    K3 = 3 * kch * -(-10000 // kch)
+    units, s = schedule(1024, 1024, K3, 1, mode=4)
+    assert s["T"] == 64 and s["G"] == 148 and s["R"] == 64 and s["Tl"] > 0
+    q, nch = s["q"], s["nch"]
+    pieces = units[units[:, 0] < 128]
+    assert len(pieces) == 128
+    for cta, tile, c0, c1, slot, nparts in pieces:
+        assert tile == cta % 64 and slot == cta // 64 and (c0, c1) == (slot * q, slot * q + q)
+    tails = units[units[:, 0] >= 128]
+    assert (tails[:, 2] >= 2 * q).all() and (tails[:, 3] <= nch).all() and (tails[:, 4] >= 2).all()
+    load = np.zeros(148, dtype=np.int64)
+    for cta, tile, c0, c1, slot, nparts in units:
+        load[cta] += c1 - c0
+    assert load.max() <= -(-64 * nch // 148)
+    _, s4 = schedule(1024, 1024, K3, 1, mode=1)
+    assert s4["G"] == 128 and s4["Tl"] == 0 and s4["q"] > q
 
 
 def test_streamk_can_be_disabled_by_shape():
