@@ -15,8 +15,8 @@
 // and every other derivative involving pl_in vanishes (components only ever add to pathlength,
 // components.py:161-559, propagator.py:67-72).
 //
-// Built with -fmad=false like the ray kernel; the Krivanek lens uses the same algebraic harmonic
-// evaluation (powers of the unit phasor) as trace.cu.
+// Built with -fmad=false like the ray kernel; the Krivanek lens enters through a per-ray table of the partial
+// derivatives of its aberration function (same polynomial form as trace.cu), composed per thread.
 #include <math.h>
 #include "tg_common.cuh"
 
@@ -80,17 +80,53 @@ template <int P>
 __device__ __forceinline__ HD<P> operator*(double b, const HD<P> &a) {
   return a * b;
 }
-// product: subset convolution, r[m] = sum_{s subset m} a[s] b[m \ s]   (3^P terms)
+// product: subset convolution, r[m] = sum_{s subset m} a[s] b[m \ s]   (3^P terms).  The value c[0] is one
+// rounded multiplication, like the ray kernel's (bit-faithful fp64 values, this TU is built with -fmad=false);
+// the derivative coefficients are sums of products and use explicit FMAs: 27 fp64 instructions per product at
+// order 3 instead of 46 (the parity tolerance of the derivative tensors is 1e-10, an FMA only rounds less)
+// Written subset-outer so that consecutive FMAs belong to different coefficients: 2^P independent chains in
+// flight instead of one (ncu, order 3 on the C4 column: fixed-latency dependency waits were 36 % of all stalls
+// at 3.5 warps per scheduler).
 template <int P>
 __device__ __forceinline__ HD<P> operator*(const HD<P> &a, const HD<P> &b) {
   HD<P> r;
 #pragma unroll
-  for (int m = 0; m < HD<P>::M; ++m) {
-    double acc = a.c[0] * b.c[m];
+  for (int m = 0; m < HD<P>::M; ++m) r.c[m] = a.c[0] * b.c[m];
+#pragma unroll
+  for (int s = 1; s < HD<P>::M; ++s)
+#pragma unroll
+    for (int m = 1; m < HD<P>::M; ++m)
+      if ((s & m) == s) r.c[m] = fma(a.c[s], b.c[m ^ s], r.c[m]);
+  return r;
+}
+// c + a * b (a propagation step x + dx d): the value is mul-then-add like the ray kernel's, the derivative
+// coefficients start their FMA chains from c
+template <int P>
+__device__ __forceinline__ HD<P> hmuladd(const HD<P> &a, const HD<P> &b, const HD<P> &c) {
+  HD<P> r;
+  r.c[0] = c.c[0] + a.c[0] * b.c[0];
+#pragma unroll
+  for (int m = 1; m < HD<P>::M; ++m) r.c[m] = fma(a.c[0], b.c[m], c.c[m]);
+#pragma unroll
+  for (int s = 1; s < HD<P>::M; ++s)
+#pragma unroll
+    for (int m = 1; m < HD<P>::M; ++m)
+      if ((s & m) == s) r.c[m] = fma(a.c[s], b.c[m ^ s], r.c[m]);
+  return r;
+}
+// a * a: each unordered pair {s, m \ s} once (14 multiplications at order 3 instead of 27); c[0] = a0 a0 and
+// 2 (a0 a_m) are the same doubles the general product gives
+template <int P>
+__device__ __forceinline__ HD<P> hsqr(const HD<P> &a) {
+  HD<P> r;
+  r.c[0] = a.c[0] * a.c[0];
+#pragma unroll
+  for (int m = 1; m < HD<P>::M; ++m) {
+    double acc = a.c[0] * a.c[m];
 #pragma unroll
     for (int s = 1; s < HD<P>::M; ++s)
-      if ((s & m) == s) acc = acc + a.c[s] * b.c[m ^ s];
-    r.c[m] = acc;
+      if ((s & m) == s && s < (m ^ s)) acc = fma(a.c[s], a.c[m ^ s], acc);
+    r.c[m] = 2.0 * acc;
   }
   return r;
 }
@@ -128,200 +164,222 @@ __device__ __forceinline__ HD<P> operator/(const HD<P> &a, double b) {
   return r;
 }
 
-// ---- Krivanek aberration function in hyper-dual arithmetic (aberrations.py:42-108) -----------
+// ---- Krivanek aberration function (aberrations.py:42-108) -----------
 enum {
   K_C10 = 0, K_C12, K_PHI12, K_C21, K_PHI21, K_C23, K_PHI23, K_C30, K_C32, K_PHI32, K_C34,
   K_PHI34, K_C41, K_PHI41, K_C43, K_PHI43, K_C45, K_PHI45, K_C50, K_C52, K_PHI52, K_C54,
   K_PHI54, K_C56, K_PHI56
 };
-// Polynomial form (see trace.cu): with w = ax + i ay, r2 = |w|^2 and z_nm = C_nm / (n + 1) exp(-i m phi_nm)
-//     W = Re[ F0(w) + r2 F1(w) + r2^2 F2(w) + r2^3 F3 ],   F_b = sum of z_nm w^m over the terms with (n + 1 - m) / 2 = b,
-//     dW/dax + i dW/day = sum_b [ r2^b conj(F_b'(w)) + 2 b r2^(b-1) w Re F_b(w) ],
-// evaluated directly in hyper-dual arithmetic: products and sums only (no hypot / arctan2 / reciprocal
-// compositions), 13 hyper-dual products for the BASELINE C4 coefficients instead of ~40 in polar form.
-// The products inside use fused multiply-adds (this TU is built with -fmad=false; fma() is honoured).
-template <int P>
-__device__ __forceinline__ HD<P> hfmul(const HD<P> &a, const HD<P> &b) {
-  HD<P> r;
-#pragma unroll
-  for (int m = 0; m < HD<P>::M; ++m) {
-    double acc = a.c[0] * b.c[m];
-#pragma unroll
-    for (int s = 1; s < HD<P>::M; ++s)
-      if ((s & m) == s) acc = fma(a.c[s], b.c[m ^ s], acc);
-    r.c[m] = acc;
-  }
-  return r;
-}
-template <int P>
-__device__ __forceinline__ void haxpy(HD<P> &acc, double s, const HD<P> &a) {   // acc += s a
-#pragma unroll
-  for (int m = 0; m < HD<P>::M; ++m) acc.c[m] = fma(s, a.c[m], acc.c[m]);
-}
-template <int P>
-struct CH {
-  HD<P> re, im;
+// Polynomial form (see trace.cu): with w = u + i v, r2 = |w|^2 and z_nm = C_nm / (n + 1) exp(-i m phi_nm)
+//     W = Re[ F0(w) + r2 F1(w) + r2^2 F2(w) + r2^3 F3 ],   F_b = sum of z_nm w^m over the terms with (n + 1 - m) / 2 = b
+// (no hypot / arctan2 / reciprocal compositions).  This TU is built with -fmad=false; fma() is honoured.
+
+// ---- the Krivanek lens inside the jet kernel: one table of partials per ray, composed per thread ---------
+// hkrivanek above carries 2^P coefficients of every intermediate through ~13 hyper-dual products in EVERY
+// thread of a ray (56 at order 3): 255 registers, spills, 3.3 ms per 2e5 rays.  But the aberration function
+// depends on two variables only, (u, v) = the ray slope at the lens.  The jet kernel therefore evaluates the
+// partial derivatives W_ij = d^(i+j) W / du^i dv^j, i + j <= P + 1, ONCE per ray (15 numbers at order 3),
+// cooperatively, in scalar complex arithmetic, and every thread composes its hyper-dual slopes with that
+// table: F(u0 + nx, v0 + ny) = sum_ij F_ij nx^i ny^j / (i! j!) for F = W, dW/du, dW/dv, with nx, ny the
+// nilpotent parts -- three sparse products and four cubes instead of the whole polynomial in 8-coefficient
+// arithmetic.
+//
+// The table comes from Wirtinger calculus.  With w = u + i v every term of the polynomial form is
+// z w^a conj(w)^b (a = m + b, b = (n + 1 - m) / 2, z = C_nm / (n + 1) exp(-i m phi_nm)), so
+//     G_pq = d_w^p d_wbar^q G = sum_terms z ff(a, p) ff(b, q) w^(a-p) conj(w)^(b-q),    ff = falling factorial,
+// and, since d/du = d_w + d_wbar and d/dv = i (d_w - d_wbar) are real operators and W = Re G,
+//     W_ij = Re[ i^j sum_{k<=i, l<=j} C(i,k) C(j,l) (-1)^(j-l) G_{k+l, (i-k)+(j-l)} ]
+// (tests/test_krivanek_polynomial_cpu.py checks this restatement against sympy derivatives).
+struct KTerm {
+  int c, g, n, m;      // coefficient index, index of its (cos, sin)(m phi) pair (-1: m = 0), radial / azimuthal order
+};
+__constant__ KTerm kTerms[14] = {
+    {K_C10, -1, 1, 0}, {K_C12, 0, 1, 2},  {K_C21, 2, 2, 1},  {K_C23, 4, 2, 3},  {K_C30, -1, 3, 0},
+    {K_C32, 6, 3, 2},  {K_C34, 8, 3, 4},  {K_C41, 10, 4, 1}, {K_C43, 12, 4, 3}, {K_C45, 14, 4, 5},
+    {K_C50, -1, 5, 0}, {K_C52, 16, 5, 2}, {K_C54, 18, 5, 4}, {K_C56, 20, 5, 6}};
+__constant__ double kKappa[6] = {1.0, 1.0, 0.5, 1.0 / 3.0, 0.25, 0.2};     // 1 / n (index n + 1 is used below)
+__constant__ double kKappa6 = 1.0 / 6.0;
+__constant__ int kBinom[5][5] = {{1, 0, 0, 0, 0}, {1, 1, 0, 0, 0}, {1, 2, 1, 0, 0}, {1, 3, 3, 1, 0}, {1, 4, 6, 4, 1}};
+
+// shared scratch of one ray: powers of w, the Wirtinger derivatives, the table of partials (5 x 5, i + j <= 4 used)
+struct KrivRay {
+  double wr[7], wi[7];
+  double gr[25], gi[25];
+  double t[25];
+};
+// shared by the CTA's rays: z ff(a, p) ff(b, q) per (term, job) -- depends on the lens only
+struct KrivCoef {
+  double cr[14 * 15], ci[14 * 15];
 };
 template <int P>
-__device__ __forceinline__ CH<P> chmul(const CH<P> &a, const CH<P> &b) {
-  CH<P> r;
-  r.re = hfmul(a.re, b.re) - hfmul(a.im, b.im);
-  r.im = hfmul(a.re, b.im) + hfmul(a.im, b.re);
-  return r;
+__host__ __device__ constexpr int kriv_jobs() { return (P + 2) * (P + 3) / 2; }
+__host__ __device__ constexpr int kterm_a(int t) {        // exponents of w and conj(w) of term t (kTerms order)
+  constexpr int n[14] = {1, 1, 2, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 5}, m[14] = {0, 2, 1, 3, 0, 2, 4, 1, 3, 5, 0, 2, 4, 6};
+  return m[t] + (n[t] + 1 - m[t]) / 2;
+}
+__host__ __device__ constexpr int kterm_b(int t) {
+  constexpr int n[14] = {1, 1, 2, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 5}, m[14] = {0, 2, 1, 3, 0, 2, 4, 1, 3, 5, 0, 2, 4, 6};
+  return (n[t] + 1 - m[t]) / 2;
 }
 template <int P>
-__device__ __forceinline__ CH<P> chsqr(const CH<P> &a) {
-  CH<P> r;
-  r.re = hfmul(a.re, a.re) - hfmul(a.im, a.im);
-  r.im = hfmul(a.re, a.im) * 2.0;
-  return r;
-}
-// one group r2^B Re F_B(w) of the polynomial form
-template <int P>
-struct KGroup {
-  double f0;            // the m = 0 term (real constant)
-  double d1r, d1i;      // the m = 1 term's coefficient = constant part of F_B'
-  CH<P> F, D;           // sum_{m >= 1} z w^m,  sum_{m >= 2} m z w^(m-1)
-  bool hasF, hasD;
-};
-template <int P>
-__device__ __forceinline__ void kgroup_init(KGroup<P> &G, double f0) {
-  G.f0 = f0;
-  G.d1r = G.d1i = 0.0;
-  G.F.re = G.F.im = G.D.re = G.D.im = hconst<P>(0.0);
-  G.hasF = G.hasD = false;
-}
-// term z w^K, z = kappa C (c0 - i s0); wk = w^K, wkm1 = w^(K-1)
-template <int K, int P>
-__device__ __forceinline__ void kgroup_term(KGroup<P> &G, double C, double kappa, double c0, double s0,
-                                            const CH<P> &wk, const CH<P> &wkm1) {
-  if (C == 0.0) return;
-  const double s = C * kappa, zr = s * c0, zi = -(s * s0);
-  haxpy(G.F.re, zr, wk.re);
-  haxpy(G.F.re, -zi, wk.im);
-  haxpy(G.F.im, zr, wk.im);
-  haxpy(G.F.im, zi, wk.re);
-  G.hasF = true;
-  if constexpr (K == 1) {
-    G.d1r += zr;
-    G.d1i += zi;
-  } else {
-    const double kr = (double)K * zr, ki = (double)K * zi;
-    haxpy(G.D.re, kr, wkm1.re);
-    haxpy(G.D.re, -ki, wkm1.im);
-    haxpy(G.D.im, kr, wkm1.im);
-    haxpy(G.D.im, ki, wkm1.re);
-    G.hasD = true;
+__device__ __forceinline__ void kriv_job_pq(int job, int &p, int &q) {      // job -> (p, q), p + q <= P + 1
+  p = 0;
+  q = job;
+  while (p <= P + 1 && q > P + 1 - p) {
+    q -= P + 2 - p;
+    ++p;
   }
 }
-// fold a group into W and (Gx, Gy): rho = r2^B, rhom = r2^(B-1) (B >= 2)
-template <int B, int P>
-__device__ __forceinline__ void kgroup_fold(const KGroup<P> &G, const HD<P> &u, const HD<P> &v, const HD<P> &rho,
-                                            const HD<P> &rhom, HD<P> &W, HD<P> &Gx, HD<P> &Gy) {
-  using S = HD<P>;
-  if constexpr (B == 0) {
-    W = W + G.F.re;
-    Gx = Gx + G.D.re;
-    Gy = Gy - G.D.im;
-  } else {
-    // W += rho Re F ; grad += rho conj(F') + 2 B rho^(B-1) w Re F
-    haxpy(W, G.f0, rho);
-    if (G.hasF) W = W + hfmul(rho, G.F.re);
-    haxpy(Gx, G.d1r, rho);
-    haxpy(Gy, -G.d1i, rho);
-    if (G.hasD) {
-      Gx = Gx + hfmul(rho, G.D.re);
-      Gy = Gy - hfmul(rho, G.D.im);
+
+// Called by ALL threads of the CTA (barriers inside); `job` = this thread's index within its ray.
+// Three short stages: (1) all threads fill the lens's coefficient table, one thread per ray the powers of w;
+// (2) job (p, q) sums G_pq over the 14 terms, branch-free (absent terms have zero coefficients);
+// (3) job (i, j) combines the G into W_ij.
+template <int P, int NTHREADS>
+__device__ __forceinline__ void kriv_table(const double *prm, double u0, double v0, int job, KrivRay &K, KrivCoef &C) {
+  constexpr int NJ = kriv_jobs<P>();
+  const double *g = prm + 25;
+  for (int e = threadIdx.x; e < 14 * NJ; e += NTHREADS) {
+    const int t = e / NJ;
+    int p, q;
+    kriv_job_pq<P>(e - t * NJ, p, q);
+    const KTerm T = kTerms[t];
+    const int b = (T.n + 1 - T.m) >> 1, a = T.m + b;
+    double zr = 0.0, zi = 0.0;
+    if (a >= p && b >= q) {
+      int f = 1;
+      for (int k = 0; k < p; ++k) f *= a - k;
+      for (int k = 0; k < q; ++k) f *= b - k;
+      const double s = prm[T.c] * (T.n == 5 ? kKappa6 : kKappa[T.n + 1]) * (double)f;
+      zr = T.g >= 0 ? s * g[T.g] : s;
+      zi = T.g >= 0 ? -(s * g[T.g + 1]) : 0.0;
     }
-    if (B == 1 && !G.hasF) {
-      haxpy(Gx, 2.0 * G.f0, u);
-      haxpy(Gy, 2.0 * G.f0, v);
-    } else {
-      S t;
-      if constexpr (B == 1) {
-        t = G.F.re + G.f0;
-      } else {
-        t = rhom * G.f0;
-        if (G.hasF) t = t + hfmul(rhom, G.F.re);
+    C.cr[e] = zr;
+    C.ci[e] = zi;
+  }
+  if (job == 0) {
+    double r = 1.0, i = 0.0;
+    K.wr[0] = 1.0;
+    K.wi[0] = 0.0;
+#pragma unroll
+    for (int k = 1; k < 7; ++k) {
+      const double nr = fma(r, u0, -(i * v0)), ni = fma(r, v0, i * u0);
+      r = nr;
+      i = ni;
+      K.wr[k] = r;
+      K.wi[k] = i;
+    }
+  }
+  __syncthreads();
+  int pi, qj;
+  kriv_job_pq<P>(job, pi, qj);
+  const bool mine = job < NJ;
+  if (mine) {
+    double ar = 0.0, ai = 0.0;
+#pragma unroll
+    for (int t = 0; t < 14; ++t) {
+      const int ea = kterm_a(t) - pi, eb = kterm_b(t) - qj;          // negative: the coefficient is zero
+      const int ia = ea < 0 ? 0 : ea, ib = eb < 0 ? 0 : eb;
+      const double zr = C.cr[t * NJ + job], zi = C.ci[t * NJ + job];
+      const double xr = K.wr[ia], xi = K.wi[ia], yr = K.wr[ib], yi = -K.wi[ib];
+      const double mr = fma(xr, yr, -(xi * yi)), mi = fma(xr, yi, xi * yr);
+      ar = fma(zr, mr, fma(-zi, mi, ar));
+      ai = fma(zr, mi, fma(zi, mr, ai));
+    }
+    K.gr[pi * 5 + qj] = ar;
+    K.gi[pi * 5 + qj] = ai;
+  }
+  __syncthreads();
+  if (mine) {
+    const int i = pi, j = qj;
+    double ar = 0.0, ai = 0.0;
+    for (int k = 0; k <= i; ++k)
+      for (int l = 0; l <= j; ++l) {
+        const double c = (double)(kBinom[i][k] * kBinom[j][l]) * (((j - l) & 1) ? -1.0 : 1.0);
+        const int e = (k + l) * 5 + (i - k) + (j - l);
+        ar = fma(c, K.gr[e], ar);
+        ai = fma(c, K.gi[e], ai);
       }
-      t = t * (2.0 * (double)B);
-      Gx = Gx + hfmul(u, t);
-      Gy = Gy + hfmul(v, t);
+    const int r = j & 3;                                  // Re[i^j (ar + i ai)]
+    K.t[i * 5 + j] = r == 0 ? ar : (r == 1 ? -ai : (r == 2 ? -ar : ai));
+  }
+  __syncthreads();
+}
+
+__host__ __device__ constexpr int hd_popc(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1); }
+// product of two nilpotent hyper-duals whose coefficients vanish below DA / DB units; only masks with
+// >= DA + DB units are produced (the others are never read)
+template <int P, int DA, int DB>
+__device__ __forceinline__ void nmul(const double (&a)[1 << P], const double (&b)[1 << P], double (&r)[1 << P],
+                                     double scale) {
+#pragma unroll
+  for (int m = 1; m < (1 << P); ++m) {
+    if (hd_popc(m) < DA + DB) continue;
+    double acc = 0.0;
+    bool first = true;
+#pragma unroll
+    for (int s = 1; s < (1 << P); ++s) {
+      if ((s & m) != s || hd_popc(s) < DA || hd_popc(m ^ s) < DB) continue;
+      acc = first ? a[s] * b[m ^ s] : fma(a[s], b[m ^ s], acc);
+      first = false;
     }
+    r[m] = acc * scale;
   }
 }
+// dx, dy hold the hyper-dual slopes (u, v) entering the aberration function; on return
+// dx = u - dW/du / f, dy = v - dW/dv / f, pl += W / f  (components.py:192-215), T = the ray's table W_ij
 template <int P>
-__device__ __forceinline__ void hkrivanek(const double *p, const HD<P> &ax, const HD<P> &ay, HD<P> &dWx,
-                                          HD<P> &dWy, HD<P> &W) {
-  using S = HD<P>;
-  const double *g = p + 25;                           // (cos, sin)(m phi0) pairs
-  // highest power of w in use (uniform branches on kernel-parameter constants)
-  int kmax = 0;
-  if (p[K_C21] != 0.0 || p[K_C41] != 0.0) kmax = 1;
-  if (p[K_C12] != 0.0 || p[K_C32] != 0.0 || p[K_C52] != 0.0) kmax = 2;
-  if (p[K_C23] != 0.0 || p[K_C43] != 0.0) kmax = 3;
-  if (p[K_C34] != 0.0 || p[K_C54] != 0.0) kmax = 4;
-  if (p[K_C45] != 0.0) kmax = 5;
-  if (p[K_C56] != 0.0) kmax = 6;
-  const S uu = hfmul(ax, ax), vv = hfmul(ay, ay);
-  const S r2 = uu + vv;
-  CH<P> w0, w1, w2, w3, w4, w5, w6;
-  w0.re = hconst<P>(1.0);
-  w0.im = hconst<P>(0.0);
-  w1.re = ax;
-  w1.im = ay;
-  w2 = w3 = w4 = w5 = w6 = w0;
-  if (kmax >= 2) {
-    w2.re = uu - vv;
-    w2.im = hfmul(ax, ay) * 2.0;
+__device__ __forceinline__ void kriv_compose(const double *T, double inv_f, HD<P> &dx, HD<P> &dy, HD<P> &pl) {
+  constexpr int M = 1 << P;
+  auto t = [&](int i, int j) -> double { return T[i * 5 + j]; };
+  const bool on_axis = dx.c[0] == 0.0 && dy.c[0] == 0.0;
+  double xx[M] = {0.0}, xy[M] = {0.0}, yy[M] = {0.0};                           // nx^2 / 2, nx ny, ny^2 / 2   (masks with >= 2 units)
+  double x3 = 0.0, x2y = 0.0, xy2 = 0.0, y3 = 0.0;      // nx^3 / 6, nx^2 ny / 2, nx ny^2 / 2, ny^3 / 6   (full mask)
+  if constexpr (P >= 2) {
+    nmul<P, 1, 1>(dx.c, dx.c, xx, 0.5);
+    nmul<P, 1, 1>(dx.c, dy.c, xy, 1.0);
+    nmul<P, 1, 1>(dy.c, dy.c, yy, 0.5);
   }
-  if (kmax >= 3) w3 = chmul(w2, w1);
-  if (kmax >= 4) w4 = chsqr(w2);
-  if (kmax >= 5) w5 = chmul(w4, w1);
-  if (kmax >= 6) w6 = chsqr(w3);
-  W = hconst<P>(0.0);
-  dWx = W;
-  dWy = W;
-  KGroup<P> G;
-  // b = 0: m = n + 1
-  if (p[K_C12] != 0.0 || p[K_C23] != 0.0 || p[K_C34] != 0.0 || p[K_C45] != 0.0 || p[K_C56] != 0.0) {
-    kgroup_init(G, 0.0);
-    kgroup_term<2>(G, p[K_C12], 0.5, g[0], g[1], w2, w1);
-    kgroup_term<3>(G, p[K_C23], 1.0 / 3.0, g[4], g[5], w3, w2);
-    kgroup_term<4>(G, p[K_C34], 0.25, g[8], g[9], w4, w3);
-    kgroup_term<5>(G, p[K_C45], 0.2, g[14], g[15], w5, w4);
-    kgroup_term<6>(G, p[K_C56], 1.0 / 6.0, g[20], g[21], w6, w5);
-    kgroup_fold<0>(G, ax, ay, r2, r2, W, dWx, dWy);
+  if constexpr (P >= 3) {
+    double c[M];
+    nmul<P, 2, 1>(xx, dx.c, c, 1.0 / 3.0);
+    x3 = c[M - 1];
+    nmul<P, 2, 1>(xx, dy.c, c, 1.0);
+    x2y = c[M - 1];
+    nmul<P, 2, 1>(yy, dx.c, c, 1.0);
+    xy2 = c[M - 1];
+    nmul<P, 2, 1>(yy, dy.c, c, 1.0 / 3.0);
+    y3 = c[M - 1];
   }
-  // b = 1: m = n - 1
-  if (p[K_C10] != 0.0 || p[K_C21] != 0.0 || p[K_C32] != 0.0 || p[K_C43] != 0.0 || p[K_C54] != 0.0) {
-    kgroup_init(G, 0.5 * p[K_C10]);
-    kgroup_term<1>(G, p[K_C21], 1.0 / 3.0, g[2], g[3], w1, w0);
-    kgroup_term<2>(G, p[K_C32], 0.25, g[6], g[7], w2, w1);
-    kgroup_term<3>(G, p[K_C43], 0.2, g[12], g[13], w3, w2);
-    kgroup_term<4>(G, p[K_C54], 1.0 / 6.0, g[18], g[19], w4, w3);
-    kgroup_fold<1>(G, ax, ay, r2, r2, W, dWx, dWy);
-  }
-  const bool b2 = p[K_C30] != 0.0 || p[K_C41] != 0.0 || p[K_C52] != 0.0, b3 = p[K_C50] != 0.0;
-  if (b2 || b3) {
-    const S r4 = hfmul(r2, r2);
-    if (b2) {   // b = 2: m = n - 3
-      kgroup_init(G, 0.25 * p[K_C30]);
-      kgroup_term<1>(G, p[K_C41], 0.2, g[10], g[11], w1, w0);
-      kgroup_term<2>(G, p[K_C52], 1.0 / 6.0, g[16], g[17], w2, w1);
-      kgroup_fold<2>(G, ax, ay, r4, r2, W, dWx, dWy);
-    }
-    if (b3) {   // b = 3: C50 alpha^6 / 6
-      kgroup_init(G, p[K_C50] * (1.0 / 6.0));
-      kgroup_fold<3>(G, ax, ay, hfmul(r4, r2), r4, W, dWx, dWy);
-    }
-  }
-  if (ax.c[0] == 0.0 && ay.c[0] == 0.0) {
-    // on-axis ray: jnp.hypot / arctan2 have NaN derivatives at the origin (aberrations.py:66-67), so every
-    // derivative through the lens is NaN in the reference; values stay finite
+  // F = sum F_ij (monomial ij); for W the F_ij are t(i, j), for dW/du t(i + 1, j), for dW/dv t(i, j + 1)
+  auto series = [&](int oi, int oj, int m) -> double {
+    double v = fma(t(1 + oi, oj), dx.c[m], t(oi, 1 + oj) * dy.c[m]);
+    if (P >= 2 && hd_popc(m) >= 2)
+      v = fma(t(2 + oi, oj), xx[m], fma(t(1 + oi, 1 + oj), xy[m], fma(t(oi, 2 + oj), yy[m], v)));
+    if (P >= 3 && hd_popc(m) >= 3)
+      v = fma(t(3 + oi, oj), x3, fma(t(2 + oi, 1 + oj), x2y, fma(t(1 + oi, 2 + oj), xy2, fma(t(oi, 3 + oj), y3, v))));
+    return v;
+  };
+  const double qnan = nan("");
+  pl.c[0] = pl.c[0] + t(0, 0) * inv_f;
+  const double u0 = dx.c[0], v0 = dy.c[0];
+  double ndx[M], ndy[M];
 #pragma unroll
-    for (int m = 1; m < HD<P>::M; ++m) dWx.c[m] = dWy.c[m] = W.c[m] = nan("");
+  for (int m = 1; m < M; ++m) {
+    // the reference's hypot / arctan2 have NaN derivatives at the origin (aberrations.py:66-67): values stay finite
+    const double w = on_axis ? qnan : series(0, 0, m), gx = on_axis ? qnan : series(1, 0, m),
+                 gy = on_axis ? qnan : series(0, 1, m);
+    pl.c[m] = pl.c[m] + w * inv_f;
+    ndx[m] = dx.c[m] - gx * inv_f;
+    ndy[m] = dy.c[m] - gy * inv_f;
   }
+#pragma unroll
+  for (int m = 1; m < M; ++m) {
+    dx.c[m] = ndx[m];
+    dy.c[m] = ndy[m];
+  }
+  dx.c[0] = u0 - t(1, 0) * inv_f;
+  dy.c[0] = v0 - t(0, 1) * inv_f;
 }
 
 // ---- index tuples ------------------------------------------------------------------------
@@ -373,6 +431,9 @@ struct JetOut {
 // (22.3 KB per ray at order 3) are assembled in shared memory -- zero fill, scattered symmetric
 // writes -- and leave as one contiguous, fully coalesced stream per order: the kernel's HBM traffic is
 // its algorithmic output (no memset pass, no 8-byte scatter to global).
+static_assert((49 * 8 * 8) % 16 == 0 && (4 * 49 * 8) % 16 == 0 && (4 * 343 * 8) % 16 == 0 && (2 * 49 * 8) % 16 == 0 &&
+                  (2 * 343 * 8) % 16 == 0 && (2 * 2401 * 8) % 16 == 0,
+              "a full CTA's blocks are whole 16-byte units (bulk copies)");
 template <int P>
 struct JetCfg;
 template <>
@@ -384,10 +445,9 @@ struct JetCfg<3> { static constexpr int kRays = 2; };
 template <int P>
 __host__ __device__ constexpr int jet_doubles_per_ray() { return 49 + (P >= 2 ? 343 : 0) + (P >= 3 ? 2401 : 0); }
 
-// KRIV = the model holds an AberratedLensKrivanek: that instantiation needs ~250 registers (and
-// spills at order 3); every other model runs the lean instantiation at 4+ CTAs per SM.
+// KRIV = the model holds an AberratedLensKrivanek (its table of partials is built in shared memory, see above).
 template <int P, bool KRIV>
-__global__ void __launch_bounds__(Tuples<P>::N * JetCfg<P>::kRays, KRIV ? 2 : (P == 3 ? 4 : 5))
+__global__ void __launch_bounds__(Tuples<P>::N * JetCfg<P>::kRays, P == 3 ? 4 : 5)
     jets_kernel(const __grid_constant__ tg_model model, const tg_ray_in in, const long long n, const JetOut out) {
   using S = HD<P>;
   constexpr int NT = Tuples<P>::N, R = JetCfg<P>::kRays, NTHREADS = NT * R;
@@ -398,12 +458,16 @@ __global__ void __launch_bounds__(Tuples<P>::N * JetCfg<P>::kRays, KRIV ? 2 : (P
   const long long i0 = (long long)blockIdx.x * R;
   const long long i = i0 + rl;
   const bool active = i < n;
+  const long long il = active ? i : n - 1;             // threads past the end shadow the last ray (barriers below)
+  __shared__ KrivRay s_kriv[KRIV ? R : 1];
+  __shared__ KrivCoef s_kcoef;
   int var[P];
   S st[7];
+  for (int k = threadIdx.x; k < R * jet_doubles_per_ray<P>(); k += NTHREADS) s_t[k] = 0.0;   // (barrier below)
 
-  if (active) {
+  {
     Tuples<P>::decode(tup, var);
-    auto ld = [&](int f) -> double { return in.ptr[f] ? __ldg(in.ptr[f] + i) : in.value[f]; };
+    auto ld = [&](int f) -> double { return in.ptr[f] ? __ldg(in.ptr[f] + il) : in.value[f]; };
 #pragma unroll
     for (int f = 0; f < 7; ++f) st[f] = hconst<P>(ld(f));
 #pragma unroll
@@ -420,8 +484,8 @@ __global__ void __launch_bounds__(Tuples<P>::N * JetCfg<P>::kRays, KRIV ? 2 : (P
       const tg_comp &cm = model.comp[c];
       if (!(cm.flags & TG_F_NOPROP)) {   // run.py:77, propagator.py:67-72
         const S d = (cm.flags & TG_F_DIST) ? hconst<P>(cm.z) : cm.z - z;
-        x = x + dx * d;
-        y = y + dy * d;
+        x = hmuladd(dx, d, x);
+        y = hmuladd(dy, d, y);
         z = z + d;
         pl = pl + d;
       }
@@ -431,7 +495,7 @@ __global__ void __launch_bounds__(Tuples<P>::N * JetCfg<P>::kRays, KRIV ? 2 : (P
           // one reciprocal instead of 24 fp64 divisions (<= 1 ulp per coefficient; parity is 1e-10)
           const double inv_f = 1.0 / cm.p[0];
           const S ndx = dx - x * inv_f, ndy = dy - y * inv_f;
-          pl = pl - (x * x + y * y) * (0.5 * inv_f);
+          pl = pl - (hsqr(x) + hsqr(y)) * (0.5 * inv_f);
           dx = ndx;
           dy = ndy;
           one = one * 1.0;
@@ -466,12 +530,11 @@ __global__ void __launch_bounds__(Tuples<P>::N * JetCfg<P>::kRays, KRIV ? 2 : (P
         case TG_OP_KRIVANEK: if constexpr (KRIV) {    // components.py:192-215
           const double inv_f = 1.0 / cm.p[0];
           const S idx = (-x) * inv_f + dx, idy = (-y) * inv_f + dy;
-          pl = pl - (x * x + y * y) * (0.5 * inv_f);
-          S dWx, dWy, W;
-          hkrivanek<P>(cm.p + 1, idx, idy, dWx, dWy, W);
-          dx = idx - dWx * inv_f;
-          dy = idy - dWy * inv_f;
-          pl = pl + W * inv_f;
+          pl = pl - (hsqr(x) + hsqr(y)) * (0.5 * inv_f);
+          dx = idx;
+          dy = idy;
+          kriv_table<P, NTHREADS>(cm.p + 1, dx.c[0], dy.c[0], tup, s_kriv[rl], s_kcoef);      // barriers: every thread gets here
+          kriv_compose<P>(s_kriv[rl].t, inv_f, dx, dy, pl);
           one = one * 1.0;
         } break;
         default:
@@ -480,7 +543,6 @@ __global__ void __launch_bounds__(Tuples<P>::N * JetCfg<P>::kRays, KRIV ? 2 : (P
     }
 
   }
-  for (int k = threadIdx.x; k < R * jet_doubles_per_ray<P>(); k += NTHREADS) s_t[k] = 0.0;
   __syncthreads();
   if (active) {
     // ---- outputs.  Sorted tuple (v0 <= v1 <= v2) in live-variable numbering; w_u = Ray field index.
@@ -539,10 +601,28 @@ __global__ void __launch_bounds__(Tuples<P>::N * JetCfg<P>::kRays, KRIV ? 2 : (P
       }
     }
   }
-  __syncthreads();
-  // contiguous, coalesced emission of this CTA's rays, one stream per order
+  // contiguous emission of this CTA's rays, one stream per order: a full CTA (R rays: every size and offset is a
+  // multiple of 16 bytes) hands the three blocks to the TMA unit as bulk shared -> global copies, so no thread
+  // spends issue slots on the 5600 load / store pairs per CTA of order 3; a ragged last CTA or an output pointer
+  // that is only 8-byte aligned takes the thread loop
   const long long rem = n - i0;
   const int nr = rem >= R ? R : (int)rem;
+  bool bulk_ok = nr == R;
+#pragma unroll
+  for (int k = 0; k < P; ++k) bulk_ok = bulk_ok && ((reinterpret_cast<uintptr_t>(out.d[k]) & 15u) == 0);
+  if (bulk_ok) {
+    tg_fence_proxy_async();            // generic-proxy writes of this thread -> visible to the async proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tg_bulk_s2g(out.d[0] + i0 * 49, s_d1, (uint32_t)(R * 49 * sizeof(double)));
+      if constexpr (P >= 2) tg_bulk_s2g(out.d[1] + i0 * 343, s_d2, (uint32_t)(R * 343 * sizeof(double)));
+      if constexpr (P >= 3) tg_bulk_s2g(out.d[2] + i0 * 2401, s_d3, (uint32_t)(R * 2401 * sizeof(double)));
+      tg_bulk_commit();
+      tg_bulk_wait_read0();            // shared memory must stay valid until the TMA unit has read it
+    }
+    return;
+  }
+  __syncthreads();
   {
     double *g = out.d[0] + i0 * 49;
     for (int k = threadIdx.x; k < nr * 49; k += NTHREADS) g[k] = s_d1[k];

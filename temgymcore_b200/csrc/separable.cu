@@ -34,6 +34,7 @@
 //   warp 2   : TMEM allocator (512 columns)
 //   warps 4-11: epilogue     - tcgen05.ld the finished accumulator (32x32b.x32), add into
 //              registers, release the accumulator; finally write doubles to the output
+#include <atomic>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -202,6 +203,10 @@ struct SkSched {
   int prefetch;   // k-blocks the producer prefetches ahead into L2 (0 = none)
   int uniform;    // > 0: plain split-K -- CTA c owns chunks [split q, split q + q) of tile c % T, split = c / T
   int S;          // head / tail arrangement: full pieces of q chunks per stream-K tile (1 = heads only)
+  // plain split-K in ROUNDS (the host pipeline's row-block streaming): the tiles are walked Tr at a time -- a block
+  // of tile rows -- each round split along K over the whole machine, so that the image is finished block of rows by
+  // block of rows inside ONE launch; rounds = 1, Tr = T is the plain split-K above
+  int rounds, Tr;
 };
 struct SkUnit {
   int tile, ch0, ch1, slot, nparts;
@@ -237,15 +242,21 @@ struct SkIter {
     }
   }
   __host__ __device__ __forceinline__ bool next(const SkSched &s, int cta, SkUnit &u) {
-    if (phase == 3) {        // plain split-K: exactly one unit per CTA
+    if (phase == 3) {        // plain split-K: one unit per CTA and round
+      const int split = cta / s.Tr, col = cta - split * s.Tr;
+      while (f0 < s.rounds) {
+        const int tile = f0 * s.Tr + col;
+        ++f0;
+        if (tile >= s.T) break;
+        u.tile = tile;
+        u.ch0 = split * s.q;
+        u.ch1 = u.ch0 + s.q < s.nch ? u.ch0 + s.q : s.nch;
+        u.slot = split;
+        u.nparts = s.maxparts;
+        if (u.ch0 < u.ch1) return true;
+      }
       phase = 4;
-      const int split = cta / s.T;
-      u.tile = cta - split * s.T;
-      u.ch0 = split * s.q;
-      u.ch1 = u.ch0 + s.q < s.nch ? u.ch0 + s.q : s.nch;
-      u.slot = split;
-      u.nparts = s.maxparts;
-      return u.ch0 < u.ch1;
+      return false;
     }
     if (phase == 4) return false;
     if (phase == 0) {        // full piece `cta / R` of stream-K tile `cta % R`
@@ -309,7 +320,8 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
                    const unsigned long long *__restrict__ peak_key, double headroom,
                    const unsigned long long *__restrict__ sep_guard, const __grid_constant__ TgPeers peers,
                    const __grid_constant__ SkSched sched, float *__restrict__ scratch,
-                   unsigned int *__restrict__ counters) {
+                   unsigned int *__restrict__ counters, unsigned int *__restrict__ round_cnt,
+                   unsigned int *round_flag, unsigned int round_epoch) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;  // the SFU path owns this call
   constexpr int BK = GemmCfg<F16>::BK, CHUNK_KB = GemmCfg<F16>::CHUNK_KB;
   constexpr uint32_t kIdesc = Idesc<F16, BN>::value, kIdesc2 = Idesc<F16, 2 * BN>::value;
@@ -571,6 +583,22 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
                 }
               }
             }
+        }
+      }
+      if (round_flag) {
+        // row-block streaming: this warp's part of the tile is in memory; the last warp of the round's last tile
+        // publishes the round (system scope: a copy-engine read behind cuStreamWaitValue32 follows)
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          const int rnd = u.tile / sched.Tr;
+          const int left = sched.T - rnd * sched.Tr;
+          const unsigned need = (unsigned)((left < sched.Tr ? left : sched.Tr) * NE);
+          if (atomicAdd(round_cnt + rnd, 1u) == need - 1u) {
+            round_cnt[rnd] = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int *>(round_flag + rnd) = round_epoch;
+          }
         }
       }
     }
@@ -868,6 +896,7 @@ __device__ __forceinline__ float tf32_rna(float x) {
 constexpr double kSfuWinsBelow = 0.03;
 constexpr int FS = 32;
 constexpr long long kBatch = 16384;  // beamlets per GEMM pass
+constexpr int kMaxRounds = 64;       // row blocks of one streamed launch (host pipeline)
 constexpr double kMagicF = 1572864.0;  // 1.5 * 2^20
 
 struct Strip1D {
@@ -1144,6 +1173,29 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// cuStreamWaitValue32: lets the copy stream of the host pipeline wait for a flag word that the GEMM kernel sets when
+// a block of rows is complete (row-block streaming inside one launch)
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWaitValue32Fn get_wait_value_fn() {
+  static StreamWaitValue32Fn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<StreamWaitValue32Fn>(p);
+  }();
+  return fn;
+}
+// TG_E2E_STREAM=0 turns the single-launch row-block streaming off (the pipeline then launches one GEMM per block)
+bool stream_rounds_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("TG_E2E_STREAM");
+    return !(e && atoi(e) == 0);
+  }();
+  return on;
+}
+
 // 2-D row-major operand (rows x K elements of 4 (tf32) or 2 (fp16) bytes, pitch ldk elements),
 // box = 128 rows x 128 bytes, 128B swizzle
 template <bool F16>
@@ -1187,7 +1239,7 @@ int streamk_mode_default() {
   }();
   return mode;
 }
-SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode = -1) {
+SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode = -1, int round_tiles_m = 0) {
   if (mode < 0 || mode > 4) mode = streamk_mode_default();   // 3 = like 1 but head / tail only, 4 = like 1 with split-K tails
   SkSched s;
   const int tiles_m = (M + BM - 1) / BM;
@@ -1203,6 +1255,22 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode
   s.maxparts = 1;
   s.S = 1;
   s.prefetch = 0;
+  s.uniform = 0;
+  s.rounds = 1;
+  s.Tr = s.T;
+  if (round_tiles_m > 0 && tiles_m > round_tiles_m && s.tiles_n * round_tiles_m <= sms) {
+    // row-block streaming (host pipeline): rounds of round_tiles_m tile rows, each split over the machine
+    s.Tr = s.tiles_n * round_tiles_m;
+    s.rounds = (tiles_m + round_tiles_m - 1) / round_tiles_m;
+    int S = sms / s.Tr;
+    if (S > s.nch / 4) S = s.nch / 4 > 0 ? s.nch / 4 : 1;
+    s.q = (s.nch + S - 1) / S;
+    s.maxparts = (s.nch + s.q - 1) / s.q;
+    s.G = s.Tr * s.maxparts;
+    s.R = s.T;
+    s.uniform = 1;
+    return s;
+  }
   // TG_GEMM_STREAMK: 0 = never split, 2 = split whenever the tiles leave a partial wave (experiments); default
   // 1 = split only when whole tiles would leave more than 30 % of the machine idle.  Measured on B200 (fp16 x 3,
   // N = 2048, K = 20000): 1024 rows (128 tiles, 86 % of a wave) 0.212 ms whole tiles vs 0.27 ms split -- the
@@ -1211,7 +1279,6 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode
   const double waves = (double)s.T / sms;
   const double dp_eff = waves / ceil(waves);
   const bool want = mode == 2 || ((mode == 1 || mode == 3 || mode == 4) && dp_eff < 0.7);
-  s.uniform = 0;
   if (want && s.nch >= 8 && sms > 1 && 2 * s.T <= sms && mode != 3) {      // (mode 4: split-K pieces + tails on the SMs left over)
     // Few tiles (a row shard, a row block of the host pipeline, the 64 complex tiles of C2 in the 3-product form):
     // PLAIN split-K, every tile cut into S = floor(sms / T) equal k-ranges, CTA c -> (tile c mod T, range c div T).
@@ -1351,19 +1418,27 @@ inline int device_sms(int *sms_out) {
   return TG_OK;
 }
 template <bool F16, bool GAUSS>
-void sk_scratch_need(int M, int Np, int K, int sms, size_t *cnt_bytes, size_t *part_bytes) {
+void sk_scratch_need(int M, int Np, int K, int sms, size_t *cnt_bytes, size_t *part_bytes, int round_tiles_m = 0) {
   constexpr int NE = GAUSS ? 16 : 8;
-  const SkSched sched = make_sched(M, Np, K, GemmCfg<F16>::BK, GemmCfg<F16>::CHUNK_KB, sms);
+  const SkSched sched = make_sched(M, Np, K, GemmCfg<F16>::BK, GemmCfg<F16>::CHUNK_KB, sms, -1, round_tiles_m);
   const bool split = sched.R > 0 && sched.maxparts > 1;
   *cnt_bytes = split ? (((size_t)sched.R * NE * sizeof(unsigned int)) + 255) / 256 * 256 : 0;
   *part_bytes = split ? (size_t)sched.R * sched.maxparts * (size_t)(NE * 2048) * sizeof(float) : 0;
 }
 
+// Row-block streaming of one launch (see SkSched::rounds): cnt[rounds] arrival counters (zero on entry, left zero),
+// flag[round] = epoch when every tile of the round is in memory.
+struct SkStream {
+  int round_tiles_m = 0;
+  unsigned int *cnt = nullptr, *flag = nullptr;
+  unsigned int epoch = 1;
+};
+
 template <bool F16, bool GAUSS = false>
 int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *Blo, int M, int Np, int K,
                 long long ldk, double *out, long long ldo, int accumulate, const unsigned long long *peak_key,
                 const unsigned long long *sep_guard, cudaStream_t st, const TgPeers &peers,
-                const SkWs *skws = nullptr) {
+                const SkWs *skws = nullptr, const SkStream *strm = nullptr) {
   CUtensorMap ta, tb, tc, td;
   int rc;
   if ((rc = make_map<F16>(&ta, Ahi, M, K, ldk)) != TG_OK) return rc;
@@ -1377,7 +1452,7 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
     const int tiles_n = (Np + BN - 1) / BN, pair_rows = ((M + BM - 1) / BM + 1) / 2;
     const int n_pair_tiles = tiles_n * pair_rows, slots = sms / 2;
     const double waves = (double)n_pair_tiles / slots;
-    if (pair_mode() && M > BM && slots > 0 && waves / ceil(waves) >= 0.7) {
+    if (pair_mode() && !strm && M > BM && slots > 0 && waves / ceil(waves) >= 0.7) {
       CUtensorMap tcp, tdp;
       if ((rc = make_map<F16>(&tcp, Bhi, Np, K, ldk, BN / 2)) != TG_OK) return rc;
       if ((rc = make_map<F16>(&tdp, Blo, Np, K, ldk, BN / 2)) != TG_OK) return rc;
@@ -1404,9 +1479,10 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
   }
   const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
   TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<F16, GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const SkSched sched = make_sched(M, Np, K, GemmCfg<F16>::BK, GemmCfg<F16>::CHUNK_KB, sms);
+  const int rtm = strm ? strm->round_tiles_m : 0;
+  const SkSched sched = make_sched(M, Np, K, GemmCfg<F16>::BK, GemmCfg<F16>::CHUNK_KB, sms, -1, rtm);
   size_t cnt_bytes = 0, part_bytes = 0;
-  sk_scratch_need<F16, GAUSS>(M, Np, K, sms, &cnt_bytes, &part_bytes);
+  sk_scratch_need<F16, GAUSS>(M, Np, K, sms, &cnt_bytes, &part_bytes, rtm);
   unsigned char *sk = nullptr, *parts = nullptr;
   bool own = false;
   SkCache *cache = nullptr;
@@ -1437,7 +1513,8 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
   }
   gemm_x3_kernel<F16, GAUSS><<<(unsigned)sched.G, GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, smem, st>>>(
       ta, tb, tc, td, M, Np, K, out, ldo, accumulate, peak_key, Headroom<F16>::value, sep_guard, peers, sched,
-      reinterpret_cast<float *>(parts), reinterpret_cast<unsigned int *>(sk));
+      reinterpret_cast<float *>(parts), reinterpret_cast<unsigned int *>(sk), strm ? strm->cnt : nullptr,
+      strm ? strm->flag : nullptr, strm ? strm->epoch : 0u);
   rc = tg_launch_check(GAUSS ? "gemm_x3_kernel<f16, 3-product>" : F16 ? "gemm_x3_kernel<f16>" : "gemm_x3_kernel<tf32>");
   if (own) cudaFreeAsync(sk, st);
   if (cache) sk_cache_release(cache, st);
@@ -1468,7 +1545,7 @@ template <bool F16, bool GAUSS>
 int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, long long ldk, void *Ahi, void *Alo,
                 void *Bhi, void *Blo, double *acc, const unsigned long long *peak, const unsigned long long *guard,
                 cudaStream_t st, const TgPeers &gemm_peers, int block_rows, const TgEmit *emit, void *out,
-                int out_is_c128, const SkWs *skws) {
+                int out_is_c128, const SkWs *skws, const SkStream *strm = nullptr) {
   static_assert(!GAUSS || F16, "the 3-product formulation is implemented for fp16 x 3 operands");
   const int ldo = 2 * W;                     // doubles per output row (re, im interleaved)
   const int Np = GAUSS ? W : 2 * W;          // B rows: complex columns (3-product) or real columns
@@ -1511,7 +1588,7 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
       }
       double *acc_r = acc + (size_t)r * ldo;
       rc = launch_gemm<F16, GAUSS>(Ahi, Alo, Bhi, Blo, nr, Np, K, ldk, acc_r, (long long)ldo, b0 > 0 ? 1 : 0, peak,
-                                   guard, st, pe, skws);
+                                   guard, st, pe, skws, strm);
       if (rc == TG_OK && last && !out_is_c128) {
         const size_t n = (size_t)nr * ldo;
         TgPeers pc = none;   // complex64 peers are written by the conversion
@@ -1571,8 +1648,10 @@ bool use_gauss(int rows, int W) {
 extern "C" int tg_gemm_schedule(int M, int N, int K, int f16, int sms, int mode, int32_t *units, int max_units,
                                 int32_t *sched_out) {
   TG_REQUIRE(M > 0 && N > 0 && K > 0 && sms > 0, "bad GEMM shape");
-  const SkSched s = f16 ? make_sched(M, N, K, GemmCfg<true>::BK, GemmCfg<true>::CHUNK_KB, sms, mode)
-                        : make_sched(M, N, K, GemmCfg<false>::BK, GemmCfg<false>::CHUNK_KB, sms, mode);
+  const int rtm = mode >= 100 ? mode - 100 : 0;      // mode 100 + r: row-block streaming, rounds of r tile rows
+  if (rtm) mode = -1;
+  const SkSched s = f16 ? make_sched(M, N, K, GemmCfg<true>::BK, GemmCfg<true>::CHUNK_KB, sms, mode, rtm)
+                        : make_sched(M, N, K, GemmCfg<false>::BK, GemmCfg<false>::CHUNK_KB, sms, mode, rtm);
   if (sched_out) {
     const int v[10] = {s.tiles_n, s.T, s.nkb, s.nch, s.G, s.R, s.q, s.Tl, s.qh, s.maxparts};
     for (int i = 0; i < 10; ++i) sched_out[i] = v[i];
@@ -1687,10 +1766,21 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   const bool host_check = !key_async && !(flags & TG_SEP_TRUSTED) && !capturing;
 
   int block_rows = nrows;
+  // Host pipeline, one beamlet batch, complex128: ONE GEMM launch that finishes the image block of rows by block of
+  // rows (rounds of the split-K schedule) and raises a flag per block; the copy stream waits on the flags
+  // (cuStreamWaitValue32) and moves each block to the host while the following rounds run.  A GEMM launch per block
+  // (the fallback below) re-reads all column factors and pays ramp, tail and fix-up per block: 4 x 0.088 ms for the
+  // four 256-row blocks of C2 against 0.18 ms for the whole image.
+  bool streaming = false;
   if (emit) {
     TG_REQUIRE(emit->block_rows > 0 && emit->block_rows % BM == 0 && emit->host_out && emit->ev, "bad emission block");
     block_rows = emit->block_rows < nrows ? emit->block_rows : nrows;
+    streaming = out_is_c128 && nb <= kBatch && block_rows < nrows && !verdict_only && stream_rounds_enabled() &&
+                get_wait_value_fn() != nullptr && (nrows + block_rows - 1) / block_rows <= kMaxRounds &&
+                !tg_stream_is_capturing(st);
   }
+  const int round_rows = block_rows;
+  if (streaming) block_rows = nrows;
   const long long nbatch_max = nb < kBatch ? nb : kBatch;
   // f16: 0 = tf32 x 3, 1 = fp16 x 3 in the default formulation, 2 = fp16 x 3 4-multiplication, 3 = fp16 x 3 3-product
   const bool gauss = f16 == 3 || (f16 == 1 && use_gauss(block_rows, W));
@@ -1707,12 +1797,18 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
     int sms = 148;
     int rcs = device_sms(&sms);
     if (rcs != TG_OK) return rcs;
-    if (gauss) sk_need_for_call<true, true>(nb, nrows, block_rows, W, sms, &sk_cnt, &sk_part);
+    if (streaming) {
+      const int K = gauss ? 3 * (int)(((nb + KCH - 1) / KCH) * KCH) : 2 * (int)nb, rtm = round_rows / BM;
+      if (gauss) sk_scratch_need<true, true>(nrows, Np, K, sms, &sk_cnt, &sk_part, rtm);
+      else if (f16) sk_scratch_need<true, false>(nrows, Np, K, sms, &sk_cnt, &sk_part, rtm);
+      else sk_scratch_need<false, false>(nrows, Np, K, sms, &sk_cnt, &sk_part, rtm);
+    } else if (gauss) sk_need_for_call<true, true>(nb, nrows, block_rows, W, sms, &sk_cnt, &sk_part);
     else if (f16) sk_need_for_call<true, false>(nb, nrows, block_rows, W, sms, &sk_cnt, &sk_part);
     else sk_need_for_call<false, false>(nb, nrows, block_rows, W, sms, &sk_cnt, &sk_part);
   }
+  const size_t sig_bytes = streaming ? 2 * kMaxRounds * sizeof(unsigned int) : 0;     // round counters | round flags
   TgAsyncBuf wsb(st);
-  TG_CUDA(wsb.alloc(table_bytes + 256 + 2 * a_bytes + 2 * b_bytes + acc_bytes + sk_cnt + sk_part));
+  TG_CUDA(wsb.alloc(table_bytes + 256 + 2 * a_bytes + 2 * b_bytes + acc_bytes + sk_cnt + sk_part + sig_bytes));
   unsigned char *ws = wsb.as<unsigned char>();
   double *table = reinterpret_cast<double *>(ws);
   // control block after the table: key (8) | peak key (8) || gref (8) at +64 || est (8) at +128
@@ -1727,6 +1823,17 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
     skws.cnt_cap = sk_cnt;
     skws.bytes = sk_cnt + sk_part;
     TG_CUDA(cudaMemsetAsync(skws.p, 0, sk_cnt, st));   // arrival counters: zero once, the kernels leave them zero
+  }
+  SkStream strm;
+  if (streaming) {
+    strm.round_tiles_m = round_rows / BM;
+    strm.cnt = reinterpret_cast<unsigned int *>(Blo + b_bytes + acc_bytes + sk_cnt + sk_part);
+    strm.flag = strm.cnt + kMaxRounds;
+    static std::atomic<unsigned int> epoch_counter{0};
+    strm.epoch = ++epoch_counter;
+    if (strm.epoch == 0) strm.epoch = ++epoch_counter;
+    TG_CUDA(cudaMemsetAsync(strm.cnt, 0, sig_bytes, st));
+    TG_CUDA(cudaEventRecord(emit->ev[0], st));          // the copy stream's flag waits start behind this memset
   }
   TG_CUDA(cudaMemsetAsync(ws + table_bytes, 0, 16, st));  // own key slot, peak key
   if (key_async) TG_CUDA(cudaMemsetAsync(key, 0, 8, st));
@@ -1769,12 +1876,44 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
       return TG_ENOTSEPARABLE;
     }
   }
+  const TgEmit *emit_b = streaming ? nullptr : emit;          // streaming: the copies are queued below
+  const SkStream *sp = streaming ? &strm : nullptr;
   rc = gauss ? run_batches<true, true>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
-                                       out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128, &skws)
+                                       out_is_c128 ? pe : none, block_rows, emit_b, out, out_is_c128, &skws, sp)
        : f16 ? run_batches<true, false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
-                                        out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128, &skws)
+                                        out_is_c128 ? pe : none, block_rows, emit_b, out, out_is_c128, &skws, sp)
              : run_batches<false, false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
-                                         out_is_c128 ? pe : none, block_rows, emit, out, out_is_c128, &skws);
+                                         out_is_c128 ? pe : none, block_rows, emit_b, out, out_is_c128, &skws, sp);
+  if (rc == TG_OK && streaming) {
+    // The copy stream starts behind this call's memset of the flags (ev[0], recorded ahead of every kernel), then per
+    // block: wait for the flag word to reach this call's epoch, copy the rows.
+    StreamWaitValue32Fn wait_value = get_wait_value_fn();
+    const size_t row_bytes = (size_t)2 * W * sizeof(double);
+    cudaError_t e = cudaStreamWaitEvent(emit->copy, emit->ev[0], 0);
+    int blk = 0;
+    for (int r = 0; r < nrows && e == cudaSuccess; r += round_rows, ++blk) {
+      const int nr = (nrows - r) < round_rows ? (nrows - r) : round_rows;
+      const CUresult cr = wait_value(reinterpret_cast<CUstream>(emit->copy),
+                                     reinterpret_cast<CUdeviceptr>(strm.flag + blk), strm.epoch, CU_STREAM_WAIT_VALUE_GEQ);
+      if (cr != CUDA_SUCCESS) {
+        tg_set_error("cuStreamWaitValue32 failed with CUresult %d", (int)cr);
+        // the flags cannot be waited on: fall back to one copy behind the whole launch
+        cudaStreamSynchronize(st);
+        e = cudaMemcpyAsync(emit->host_out, out, (size_t)nrows * row_bytes, cudaMemcpyDeviceToHost, emit->copy);
+        break;
+      }
+      e = cudaMemcpyAsync(emit->host_out + (size_t)r * row_bytes, static_cast<unsigned char *>(out) + (size_t)r * row_bytes,
+                          (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, emit->copy);
+    }
+    // the workspace (flags included) is released in `st` order when this function returns: keep it alive until the
+    // copy stream is past its last wait
+    if (e == cudaSuccess) e = cudaEventRecord(emit->ev[1], emit->copy);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, emit->ev[1], 0);
+    if (e != cudaSuccess) {
+      tg_set_error("row-block streaming: %s", cudaGetErrorString(e));
+      rc = TG_ECUDA;
+    }
+  }
   if (rc == TG_OK && !out_is_c128 && pe.n > 0) {
     // complex64 peer images: one more pass over the converted rows (the GEMM's peer stores are fp64-only)
     const size_t n = npix * 2;

@@ -74,6 +74,23 @@ def sec_trace():
     np.testing.assert_allclose(abcd.cpu().numpy(), ref, rtol=1e-12, atol=1e-15)
 
 
+def sec_jets():
+    # barriers inside the Krivanek lens (per-ray table of partials in smem), smem tensor assembly, bulk stores;
+    # 203 rays: a ragged last CTA at every order
+    from temgymcore_b200.ray import RAY_FIELDS, Ray
+    from temgymcore_b200.run import calculate_derivatives
+    rays = M.random_rays(203, scale=0.2e-9, slope=1e-6)
+    model = M.six_component_column()
+    dr = Ray(*(torch.as_tensor(getattr(rays, f), device="cuda") for f in RAY_FIELDS))
+    ref = O.calculate_derivatives(rays, model, 3)
+    for order in (1, 2, 3):
+        got = calculate_derivatives(dr, model, order)
+        for k in range(order):
+            g = got[k].tensor.cpu().numpy()
+            for f in range(7):
+                np.testing.assert_allclose(g[:, f], ref[k][:, f], rtol=1e-8, atol=1e-8 * np.abs(ref[k][:, f]).max())
+
+
 def sec_peer():
     from temgymcore_b200.distributed import PeerImage
     from temgymcore_b200.gaussian import beamlet_polynomials
@@ -86,7 +103,8 @@ def sec_peer():
         assert rel_l2(pimg.image.cpu().numpy(), O.make_gaussian_image(g, model)) < 1e-5
 
 
-SECTIONS = {"gemm": sec_gemm, "field": sec_field, "stem4d": sec_stem4d, "trace": sec_trace, "peer": sec_peer}
+SECTIONS = {"gemm": sec_gemm, "field": sec_field, "stem4d": sec_stem4d, "trace": sec_trace, "jets": sec_jets,
+            "peer": sec_peer}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["all"]

@@ -134,3 +134,36 @@ def test_streamk_can_be_disabled_by_shape():
     # shallow K: not worth splitting
     units, s = schedule(128, 2048, 512, 1)
     assert s["R"] == 0 and s["G"] == 16 and len(units) == 16
+
+
+@pytest.mark.parametrize("M,N,K,rtm", [(1024, 1024, 30720, 2), (1024, 1024, 30720, 1), (1024, 2048, 20000, 2),
+                                       (900, 1024, 30720, 2), (1024, 2048, 20000, 1), (640, 1000, 9000, 2),
+                                       (2048, 4096, 32768, 2)])
+def test_row_block_streaming_rounds(M, N, K, rtm):
+    """mode 100 + r (the host pipeline's single-launch streaming): rounds of r tile rows, every round split along K
+    over the machine; every (tile, chunk) once, slots complete, and a CTA meets its tiles in increasing round order
+    with the same k-range in every round (its column-factor slice stays in L2)."""
+    units, s = schedule(M, N, K, 1, mode=100 + rtm)
+    tiles_m, tiles_n = -(-M // 128), s["tiles_n"]
+    T, nch = s["T"], s["nch"]
+    Tr = tiles_n * rtm
+    if tiles_m <= rtm or Tr > 148:
+        pytest.skip("not a streaming shape")
+    assert s["R"] == T and s["G"] == Tr * s["maxparts"] <= 148
+    cover = np.zeros((T, nch), dtype=np.int32)
+    last_round = {}
+    krange = {}
+    slots = {}
+    for cta, tile, c0, c1, slot, nparts in units:
+        cover[tile, c0:c1] += 1
+        rnd = tile // Tr
+        assert tile % Tr == cta % Tr and slot == cta // Tr and nparts == s["maxparts"]
+        assert last_round.get(cta, -1) < rnd
+        last_round[cta] = rnd
+        assert krange.setdefault(cta, (c0, c1)) == (c0, c1)
+        slots.setdefault(tile, []).append(slot)
+    assert (cover == 1).all()
+    for tile, sl in slots.items():
+        assert sorted(sl) == list(range(s["maxparts"]))
+    if M == 1024 and N == 1024 and rtm == 2:
+        assert s["maxparts"] == 9 and s["G"] == 144         # 4 rounds of 16 complex tiles x 9 k-ranges

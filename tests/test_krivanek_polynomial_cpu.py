@@ -8,6 +8,7 @@ formulas, aberrations.py:42-108) -- value, gradient, and the Hessian against cen
 from types import SimpleNamespace
 
 import numpy as np
+import pytest
 
 from oracle import temgym_oracle as O
 
@@ -103,3 +104,60 @@ def test_one_term_derivatives_of_the_polynomial_form():
             setattr(dphi, ph, getattr(p, ph) + np.pi / (2 * m))
             for fp, fm, an, sc in zip(poly_form(qp, u, v)[:3], poly_form(qm, u, v)[:3], poly_form(dphi, u, v)[:3], scale):
                 np.testing.assert_allclose((fp - fm) / (2 * h), an, rtol=0, atol=1e-8 * sc / h * 1e-6 + 1e-7 * np.abs(an).max())
+
+
+def wirtinger_table(p, u0, v0, order=4):
+    """csrc/jets.cu kriv_table restated: W_ij = d^(i+j) W / du^i dv^j for i + j <= order from the Wirtinger
+    derivatives G_pq = sum_terms z ff(a, p) ff(b, q) w^(a-p) conj(w)^(b-q) of G = sum z w^a conj(w)^b, W = Re G."""
+    from math import comb
+
+    def ff(a, k):
+        r = 1
+        for t in range(k):
+            r *= a - t
+        return r
+
+    w = u0 + 1j * v0
+    G = np.zeros((order + 1, order + 1), dtype=complex)
+    for c, ph, n, m in TERMS:
+        z = getattr(p, c) / (n + 1) * np.exp(-1j * m * (getattr(p, ph) if ph else 0.0))
+        b = (n + 1 - m) // 2
+        a = m + b
+        for pp in range(order + 1):
+            for q in range(order + 1 - pp):
+                if a >= pp and b >= q:
+                    G[pp, q] += z * ff(a, pp) * ff(b, q) * w ** (a - pp) * np.conj(w) ** (b - q)
+    T = np.zeros((order + 1, order + 1))
+    for i in range(order + 1):
+        for j in range(order + 1 - i):
+            acc = sum(comb(i, k) * comb(j, l) * (-1) ** (j - l) * G[k + l, (i - k) + (j - l)]
+                      for k in range(i + 1) for l in range(j + 1))
+            T[i, j] = np.real(1j ** j * acc)
+    return T
+
+
+def test_wirtinger_table_of_partials_vs_sympy():
+    """The per-ray table the jet kernel composes with (orders 0..4) against symbolic differentiation of the polar
+    form's polynomial, and its low orders against poly_form (value, gradient, Hessian)."""
+    sp = pytest.importorskip("sympy")
+    rng = np.random.default_rng(5)
+    p = _random_coeffs(rng)
+    u0, v0 = 0.013, -0.007
+    T = wirtinger_table(p, u0, v0)
+    W, Gx, Gy, Hxx, Hxy, Hyy = poly_form(p, np.array([u0]), np.array([v0]))
+    for got, ref in ((T[0, 0], W), (T[1, 0], Gx), (T[0, 1], Gy), (T[2, 0], Hxx), (T[1, 1], Hxy), (T[0, 2], Hyy)):
+        np.testing.assert_allclose(got, ref[0], rtol=1e-12)
+    u, v = sp.symbols("u v", real=True)
+    Ws = 0
+    for c, ph, n, m in TERMS:
+        z = sp.Float(getattr(p, c), 30) / (n + 1) * sp.exp(-sp.I * m * sp.Float(getattr(p, ph) if ph else 0.0, 30))
+        Ws += sp.re(sp.expand(z * (u + sp.I * v) ** m)) * (u * u + v * v) ** ((n + 1 - m) // 2)
+    for i in range(5):
+        for j in range(5 - i):
+            d = Ws
+            if i:
+                d = sp.diff(d, u, i)
+            if j:
+                d = sp.diff(d, v, j)
+            ref = float(d.subs({u: sp.Float(u0, 30), v: sp.Float(v0, 30)}))
+            assert abs(T[i, j] - ref) <= 1e-12 * abs(ref) + 1e-300, (i, j, T[i, j], ref)

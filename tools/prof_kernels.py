@@ -54,6 +54,13 @@ if what in ("jets", "all"):
     for _ in range(3):
         d = calculate_derivatives(rd, M.readme_model(), 3)
     torch.cuda.synchronize()
+if what in ("jets_c4",):
+    from temgymcore_b200.run import calculate_derivatives
+    rr = M.random_rays(200_000, scale=0.2e-9, slope=1e-9)
+    rd = Ray(*(torch.as_tensor(getattr(rr, f), device=dev) for f in RAY_FIELDS))
+    for _ in range(3):
+        d = calculate_derivatives(rd, M.six_component_column(), 3)
+    torch.cuda.synchronize()
 if what in ("c3_tensor",):
     from dataclasses import fields, replace
     from temgymcore_b200.gaussian import make_gaussian_image_device
