@@ -60,6 +60,8 @@ def to_float(v) -> float:
 
 def to_host_f64(v) -> np.ndarray:
     """Flat contiguous float64 numpy array (no copy when already so)."""
+    if type(v) is np.ndarray and v.dtype == np.float64 and v.flags.c_contiguous:
+        return v if v.ndim == 1 else v.reshape(-1)
     if torch is not None and isinstance(v, torch.Tensor):
         v = v.detach().cpu().numpy()
     return np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1))

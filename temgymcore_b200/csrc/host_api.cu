@@ -267,6 +267,7 @@ constexpr int kMaxEmitBlocks = 64;
 struct HostPipe {
   cudaStream_t compute = nullptr, copy = nullptr;
   cudaEvent_t ev[kMaxEmitBlocks] = {};
+  unsigned int *flags_host = nullptr, *flags_dev = nullptr;   // pinned + mapped: block-complete words of a streamed launch
   bool ok = false;
 };
 HostPipe *host_pipe(int dev) {
@@ -278,6 +279,15 @@ HostPipe *host_pipe(int dev) {
     if (cudaStreamCreateWithFlags(&p.copy, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     for (auto &e : p.ev)
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    void *fh = nullptr, *fd = nullptr;
+    if (cudaHostAlloc(&fh, kMaxEmitBlocks * sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess &&
+        cudaHostGetDevicePointer(&fd, fh, 0) == cudaSuccess) {
+      memset(fh, 0, kMaxEmitBlocks * sizeof(unsigned int));
+      p.flags_host = static_cast<unsigned int *>(fh);
+      p.flags_dev = static_cast<unsigned int *>(fd);
+    } else {
+      cudaGetLastError();              // no mapped memory: the pipeline launches one GEMM per block instead
+    }
     p.ok = true;
   }
   return &p;
@@ -363,6 +373,9 @@ extern "C" int tg_make_gaussian_image_host(const tg_model *model_host, int64_t n
     emit.block_rows = block_rows;
     emit.copy = pipe->copy;
     emit.ev = pipe->ev;
+    emit.flags_host = pipe->flags_host;
+    emit.flags_dev = pipe->flags_dev;
+    emit.n_flags = pipe->flags_host ? kMaxEmitBlocks : 0;
     const double *dr[7] = {dst[0], dst[1], dst[2], dst[3], dst[4], dst[5], dst[6]};
     rc = tg_make_gaussian_image_impl(model_host, nb, dr, dst[7], dst[8], dst[9], dst[10], dst[11], px2m, H, W, row0,
                                      nrows, dout, out_is_c128, cull_bits, method, s, &emit, nullptr);

@@ -644,7 +644,7 @@ int launch_jets_k(const tg_model *m, int64_t n, const tg_ray_in *in, const JetOu
   TG_REQUIRE(blocks <= 0x7fffffffLL, "too many rays for one launch");
   const size_t smem = (size_t)R * jet_doubles_per_ray<P>() * sizeof(double);
   static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
+  if ((KRIV || smem > 40 * 1024) && !attr_set) {      // dynamic + static (Krivanek tables) can pass 48 KB
     TG_CUDA(cudaFuncSetAttribute(jets_kernel<P, KRIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }

@@ -323,6 +323,11 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
                    unsigned int *__restrict__ counters, unsigned int *__restrict__ round_cnt,
                    unsigned int *round_flag, unsigned int round_epoch) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;  // the SFU path owns this call
+  // Programmatic dependent launch: a following GEMM of the host pipeline (the next block of rows, launched with
+  // programmatic stream serialisation) may start on SMs this grid leaves idle or frees -- the launches share
+  // operands that were complete before the first of them started, and write disjoint rows, scratch and counters.
+  // Without such a dependent the instruction does nothing.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   constexpr int BK = GemmCfg<F16>::BK, CHUNK_KB = GemmCfg<F16>::CHUNK_KB;
   constexpr uint32_t kIdesc = Idesc<F16, BN>::value, kIdesc2 = Idesc<F16, 2 * BN>::value;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -1173,27 +1178,21 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// cuStreamWaitValue32: lets the copy stream of the host pipeline wait for a flag word that the GEMM kernel sets when
-// a block of rows is complete (row-block streaming inside one launch)
-typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-StreamWaitValue32Fn get_wait_value_fn() {
-  static StreamWaitValue32Fn fn = [] {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<StreamWaitValue32Fn>(p);
-  }();
-  return fn;
-}
-// TG_E2E_STREAM=0 turns the single-launch row-block streaming off (the pipeline then launches one GEMM per block)
+// TG_E2E_STREAM=1: ONE GEMM launch for the whole image, walked in rounds of row blocks (SkSched::rounds).  Measured
+// slower than a launch per block -- a round of 256 rows is split 9 ways along K and the last piece of every tile
+// sums nine partial tiles (C2: 0.51 ms of kernels against 0.41 ms) -- so it is opt-in.  Read on every call.
 bool stream_rounds_enabled() {
-  static const bool on = [] {
-    const char *e = getenv("TG_E2E_STREAM");
-    return !(e && atoi(e) == 0);
-  }();
-  return on;
+  const char *e = getenv("TG_E2E_STREAM");
+  return e && atoi(e) != 0;
+}
+// TG_E2E_FLAGGED=1: the per-block launches are chained with programmatic dependent launch and raise flag words that
+// the call polls, instead of being separated by events.  Measured on C2 (4 blocks of 256 rows): the kernels take the
+// same 0.42 ms (a block's launch costs ~20 us beyond its tensor work whether or not its ramp overlaps the previous
+// tail -- tools/exp_gemm3.py), and the host-polled copies start a little later than event-driven ones (0.585 vs
+// 0.568 ms per image), so this too is opt-in.
+bool flagged_blocks_enabled() {
+  const char *e = getenv("TG_E2E_FLAGGED");
+  return e && atoi(e) != 0;
 }
 
 // 2-D row-major operand (rows x K elements of 4 (tf32) or 2 (fp16) bytes, pitch ldk elements),
@@ -1362,6 +1361,7 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode
 struct SkWs {
   unsigned char *p = nullptr;
   size_t cnt_cap = 0, bytes = 0;
+  unsigned char *parts = nullptr;     // partial tiles when they do not follow the counters directly
 };
 // grow-only scratch of the direct GEMM entry points (see launch_gemm); counters occupy the first cnt_cap bytes
 struct SkCache {
@@ -1432,6 +1432,7 @@ struct SkStream {
   int round_tiles_m = 0;
   unsigned int *cnt = nullptr, *flag = nullptr;
   unsigned int epoch = 1;
+  bool pdl = false;       // launch with programmatic stream serialisation (may overlap the GEMM launched before it)
 };
 
 template <bool F16, bool GAUSS = false>
@@ -1489,7 +1490,7 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
   if (cnt_bytes) {
     if (skws && skws->p && cnt_bytes <= skws->cnt_cap && skws->cnt_cap + part_bytes <= skws->bytes) {
       sk = skws->p;                          // counters are zero on entry by contract
-      parts = skws->p + skws->cnt_cap;
+      parts = skws->parts ? skws->parts : skws->p + skws->cnt_cap;
     } else if (!tg_stream_is_capturing(st) && cnt_bytes <= SkCache::cnt_cap &&
                (cache = sk_cache_get(part_bytes, st)) != nullptr) {
       // direct ABI calls (tg_gemm_*): a per-thread, per-device scratch buffer that only grows; its counters are
@@ -1511,10 +1512,34 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
       }
     }
   }
-  gemm_x3_kernel<F16, GAUSS><<<(unsigned)sched.G, GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, smem, st>>>(
-      ta, tb, tc, td, M, Np, K, out, ldo, accumulate, peak_key, Headroom<F16>::value, sep_guard, peers, sched,
-      reinterpret_cast<float *>(parts), reinterpret_cast<unsigned int *>(sk), strm ? strm->cnt : nullptr,
-      strm ? strm->flag : nullptr, strm ? strm->epoch : 0u);
+  if (strm && strm->pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)sched.G);
+    cfg.blockDim = dim3(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const double hr = Headroom<F16>::value;
+    float *pf = reinterpret_cast<float *>(parts);
+    unsigned int *pc = reinterpret_cast<unsigned int *>(sk);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_x3_kernel<F16, GAUSS>, ta, tb, tc, td, M, Np, K, out, ldo, accumulate,
+                                        peak_key, hr, sep_guard, peers, sched, pf, pc, strm->cnt, strm->flag, strm->epoch);
+    if (le != cudaSuccess) {
+      tg_set_error("gemm_x3_kernel (dependent launch): %s", cudaGetErrorString(le));
+      if (own) cudaFreeAsync(sk, st);
+      if (cache) sk_cache_release(cache, st);
+      return TG_ECUDA;
+    }
+  } else {
+    gemm_x3_kernel<F16, GAUSS><<<(unsigned)sched.G, GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, smem, st>>>(
+        ta, tb, tc, td, M, Np, K, out, ldo, accumulate, peak_key, Headroom<F16>::value, sep_guard, peers, sched,
+        reinterpret_cast<float *>(parts), reinterpret_cast<unsigned int *>(sk), strm ? strm->cnt : nullptr,
+        strm ? strm->flag : nullptr, strm ? strm->epoch : 0u);
+  }
   rc = tg_launch_check(GAUSS ? "gemm_x3_kernel<f16, 3-product>" : F16 ? "gemm_x3_kernel<f16>" : "gemm_x3_kernel<tf32>");
   if (own) cudaFreeAsync(sk, st);
   if (cache) sk_cache_release(cache, st);
@@ -1545,8 +1570,12 @@ template <bool F16, bool GAUSS>
 int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, long long ldk, void *Ahi, void *Alo,
                 void *Bhi, void *Blo, double *acc, const unsigned long long *peak, const unsigned long long *guard,
                 cudaStream_t st, const TgPeers &gemm_peers, int block_rows, const TgEmit *emit, void *out,
-                int out_is_c128, const SkWs *skws, const SkStream *strm = nullptr) {
+                int out_is_c128, const SkWs *skws, const SkStream *strm = nullptr, const SkStream *blk_sig = nullptr,
+                size_t blk_cnt_stride = 0, size_t blk_part_stride = 0) {
   static_assert(!GAUSS || F16, "the 3-product formulation is implemented for fp16 x 3 operands");
+  // blk_sig: one beamlet batch, the row factors of ALL rows built at once (A_hi / A_lo hold nrows rows), then one
+  // GEMM launch per row block, back to back with programmatic dependent launch, each raising flag[block] when its
+  // rows are in memory (the caller polls the flags and queues the D2H copies; no events between the launches)
   const int ldo = 2 * W;                     // doubles per output row (re, im interleaved)
   const int Np = GAUSS ? W : 2 * W;          // B rows: complex columns (3-product) or real columns
   int rc = TG_OK;
@@ -1568,6 +1597,36 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
     }
     rc = tg_launch_check("factor_cols_kernel");
     int blk = 0;
+    if (blk_sig) {
+      if constexpr (GAUSS) {
+        const unsigned ga = bounded_grid((long long)((npad / 2 + 127) / 128) * ((nrows + FS - 1) / FS));
+        factor_gauss_kernel<true><<<ga, 128, 0, st>>>(table, b0, nbatch, npad, row0, nrows, W, ldk,
+                                                      static_cast<__half *>(Ahi), static_cast<__half *>(Alo), peak,
+                                                      guard);
+      } else {
+        const unsigned ga = bounded_grid((long long)((nbatch + 127) / 128) * ((nrows + FS - 1) / FS));
+        factor_rows_kernel<F16><<<ga, 128, 0, st>>>(table, b0, nbatch, row0, nrows, W, ldk, Ahi, Alo, peak, guard);
+      }
+      rc = tg_launch_check("factor_rows_kernel");
+      const size_t elem = GemmCfg<F16>::ELEM;
+      for (int r = 0; r < nrows && rc == TG_OK; r += block_rows, ++blk) {
+        const int nr = (nrows - r) < block_rows ? (nrows - r) : block_rows;
+        SkStream sg = *blk_sig;
+        sg.cnt += blk;
+        sg.flag += blk;
+        sg.pdl = blk > 0;
+        SkWs w = *skws;
+        if (w.p) {                         // per-block counters and partial tiles (the launches overlap)
+          w.p += (size_t)blk * blk_cnt_stride;
+          w.parts += (size_t)blk * blk_part_stride;
+        }
+        const unsigned char *a_hi = static_cast<const unsigned char *>(Ahi) + (size_t)r * ldk * elem;
+        const unsigned char *a_lo = static_cast<const unsigned char *>(Alo) + (size_t)r * ldk * elem;
+        rc = launch_gemm<F16, GAUSS>(a_hi, a_lo, Bhi, Blo, nr, Np, K, ldk, acc + (size_t)r * ldo, (long long)ldo, 0, peak,
+                                     guard, st, none, &w, &sg);
+      }
+      return rc;
+    }
     for (int r = 0; r < nrows && rc == TG_OK; r += block_rows, ++blk) {
       const int nr = (nrows - r) < block_rows ? (nrows - r) : block_rows;
       if constexpr (GAUSS) {
@@ -1766,21 +1825,31 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   const bool host_check = !key_async && !(flags & TG_SEP_TRUSTED) && !capturing;
 
   int block_rows = nrows;
-  // Host pipeline, one beamlet batch, complex128: ONE GEMM launch that finishes the image block of rows by block of
-  // rows (rounds of the split-K schedule) and raises a flag per block; the copy stream waits on the flags
-  // (cuStreamWaitValue32) and moves each block to the host while the following rounds run.  A GEMM launch per block
-  // (the fallback below) re-reads all column factors and pays ramp, tail and fix-up per block: 4 x 0.088 ms for the
-  // four 256-row blocks of C2 against 0.18 ms for the whole image.
+  // Variant (TG_E2E_STREAM=1; one beamlet batch, complex128): ONE GEMM launch that finishes the image block of rows by block of
+  // rows (rounds of the split-K schedule) and raises a flag word in pinned host memory per block; this (synchronous)
+  // call polls the flags and queues the D2H copy of each block as soon as it is complete, while the following rounds
+  // run.  A GEMM launch per block (the fallback below) re-reads all column factors and pays ramp, tail and fix-up per
+  // block: 4 x 0.088 ms for the four 256-row blocks of C2 against 0.18 ms for the whole image.  (cuStreamWaitValue32
+  // on the copy stream instead of host polling was measured first: ~0.15 ms of latency per wait on this driver.)
   bool streaming = false;
   if (emit) {
     TG_REQUIRE(emit->block_rows > 0 && emit->block_rows % BM == 0 && emit->host_out && emit->ev, "bad emission block");
     block_rows = emit->block_rows < nrows ? emit->block_rows : nrows;
-    streaming = out_is_c128 && nb <= kBatch && block_rows < nrows && !verdict_only && stream_rounds_enabled() &&
-                get_wait_value_fn() != nullptr && (nrows + block_rows - 1) / block_rows <= kMaxRounds &&
-                !tg_stream_is_capturing(st);
+    streaming = out_is_c128 && nb <= kBatch && block_rows < nrows && !verdict_only && !key_async && stream_rounds_enabled() &&
+                emit->flags_host && emit->flags_dev && (nrows + block_rows - 1) / block_rows <= emit->n_flags &&
+                (nrows + block_rows - 1) / block_rows <= kMaxRounds && !tg_stream_is_capturing(st);
   }
   const int round_rows = block_rows;
   if (streaming) block_rows = nrows;
+  // Variant (TG_E2E_FLAGGED=1; one beamlet batch, complex128): row factors of all rows at once, then one GEMM launch
+  // per block of rows, chained with programmatic dependent launch so that a block's ramp (and its first CTAs, on the
+  // SMs the previous block's split-K grid leaves idle) overlap the previous block's tail; each launch raises a flag
+  // word in pinned host memory when its rows are in memory, this call polls the words and queues the D2H copies.
+  // No event sits between the launches (an event record would serialise them).
+  const int nblocks = (nrows + block_rows - 1) / block_rows;
+  const bool flagged = emit && !streaming && out_is_c128 && nb <= kBatch && nblocks >= 2 && !verdict_only &&
+                       !key_async && flagged_blocks_enabled() && emit->flags_host && emit->flags_dev &&
+                       nblocks <= emit->n_flags && nblocks <= kMaxRounds && !tg_stream_is_capturing(st);
   const long long nbatch_max = nb < kBatch ? nb : kBatch;
   // f16: 0 = tf32 x 3, 1 = fp16 x 3 in the default formulation, 2 = fp16 x 3 4-multiplication, 3 = fp16 x 3 3-product
   const bool gauss = f16 == 3 || (f16 == 1 && use_gauss(block_rows, W));
@@ -1789,7 +1858,7 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   const size_t elem = f16 ? 2 : 4;
   const int Np = gauss ? W : 2 * W;          // B rows
   const size_t table_bytes = (((size_t)nb * 96 + 255) / 256) * 256;
-  const size_t a_bytes = verdict_only ? 0 : (((size_t)block_rows * ldk * elem + 255) / 256) * 256;
+  const size_t a_bytes = verdict_only ? 0 : (((size_t)(flagged ? nrows : block_rows) * ldk * elem + 255) / 256) * 256;
   const size_t b_bytes = verdict_only ? 0 : (((size_t)Np * ldk * elem + 255) / 256) * 256;
   const size_t acc_bytes = (out_is_c128 || verdict_only) ? 0 : npix * 16;
   size_t sk_cnt = 0, sk_part = 0;
@@ -1806,7 +1875,12 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
     else if (f16) sk_need_for_call<true, false>(nb, nrows, block_rows, W, sms, &sk_cnt, &sk_part);
     else sk_need_for_call<false, false>(nb, nrows, block_rows, W, sms, &sk_cnt, &sk_part);
   }
-  const size_t sig_bytes = streaming ? 2 * kMaxRounds * sizeof(unsigned int) : 0;     // round counters | round flags
+  const size_t sig_bytes = (streaming || flagged) ? kMaxRounds * sizeof(unsigned int) : 0;     // arrival counters
+  const size_t sk_cnt1 = sk_cnt, sk_part1 = sk_part;       // per launch
+  if (flagged) {                                           // overlapping launches: scratch per block
+    sk_cnt *= (size_t)nblocks;
+    sk_part *= (size_t)nblocks;
+  }
   TgAsyncBuf wsb(st);
   TG_CUDA(wsb.alloc(table_bytes + 256 + 2 * a_bytes + 2 * b_bytes + acc_bytes + sk_cnt + sk_part + sig_bytes));
   unsigned char *ws = wsb.as<unsigned char>();
@@ -1820,20 +1894,20 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   SkWs skws;
   if (sk_cnt) {
     skws.p = Blo + b_bytes + acc_bytes;
-    skws.cnt_cap = sk_cnt;
-    skws.bytes = sk_cnt + sk_part;
+    skws.cnt_cap = sk_cnt1;
+    skws.bytes = sk_cnt1 + sk_part1;
+    skws.parts = skws.p + sk_cnt;
     TG_CUDA(cudaMemsetAsync(skws.p, 0, sk_cnt, st));   // arrival counters: zero once, the kernels leave them zero
   }
   SkStream strm;
-  if (streaming) {
-    strm.round_tiles_m = round_rows / BM;
+  if (streaming || flagged) {
+    strm.round_tiles_m = streaming ? round_rows / BM : 0;
     strm.cnt = reinterpret_cast<unsigned int *>(Blo + b_bytes + acc_bytes + sk_cnt + sk_part);
-    strm.flag = strm.cnt + kMaxRounds;
-    static std::atomic<unsigned int> epoch_counter{0};
+    strm.flag = emit->flags_dev;
+    static std::atomic<unsigned int> epoch_counter{0};   // a value no earlier call has written into the flag words
     strm.epoch = ++epoch_counter;
     if (strm.epoch == 0) strm.epoch = ++epoch_counter;
     TG_CUDA(cudaMemsetAsync(strm.cnt, 0, sig_bytes, st));
-    TG_CUDA(cudaEventRecord(emit->ev[0], st));          // the copy stream's flag waits start behind this memset
   }
   TG_CUDA(cudaMemsetAsync(ws + table_bytes, 0, 16, st));  // own key slot, peak key
   if (key_async) TG_CUDA(cudaMemsetAsync(key, 0, 8, st));
@@ -1876,42 +1950,44 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
       return TG_ENOTSEPARABLE;
     }
   }
-  const TgEmit *emit_b = streaming ? nullptr : emit;          // streaming: the copies are queued below
-  const SkStream *sp = streaming ? &strm : nullptr;
+  const TgEmit *emit_b = (streaming || flagged) ? nullptr : emit;          // the copies are queued below
+  const SkStream *sp = streaming ? &strm : nullptr, *bs = flagged ? &strm : nullptr;
   rc = gauss ? run_batches<true, true>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
-                                       out_is_c128 ? pe : none, block_rows, emit_b, out, out_is_c128, &skws, sp)
+                                       out_is_c128 ? pe : none, block_rows, emit_b, out, out_is_c128, &skws, sp, bs, sk_cnt1, sk_part1)
        : f16 ? run_batches<true, false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
-                                        out_is_c128 ? pe : none, block_rows, emit_b, out, out_is_c128, &skws, sp)
+                                        out_is_c128 ? pe : none, block_rows, emit_b, out, out_is_c128, &skws, sp, bs, sk_cnt1, sk_part1)
              : run_batches<false, false>(nb, table, row0, nrows, W, ldk, Ahi, Alo, Bhi, Blo, acc, peak, guard, st,
-                                         out_is_c128 ? pe : none, block_rows, emit_b, out, out_is_c128, &skws, sp);
-  if (rc == TG_OK && streaming) {
-    // The copy stream starts behind this call's memset of the flags (ev[0], recorded ahead of every kernel), then per
-    // block: wait for the flag word to reach this call's epoch, copy the rows.
-    StreamWaitValue32Fn wait_value = get_wait_value_fn();
+                                         out_is_c128 ? pe : none, block_rows, emit_b, out, out_is_c128, &skws, sp, bs, sk_cnt1, sk_part1);
+  if (rc == TG_OK && (streaming || flagged)) {
+    // per block: spin on the flag word (the kernel writes it after a system-scope fence), then queue the copy
     const size_t row_bytes = (size_t)2 * W * sizeof(double);
-    cudaError_t e = cudaStreamWaitEvent(emit->copy, emit->ev[0], 0);
+    volatile unsigned int *flags = emit->flags_host;
     int blk = 0;
-    for (int r = 0; r < nrows && e == cudaSuccess; r += round_rows, ++blk) {
+    for (int r = 0; r < nrows && rc == TG_OK; r += round_rows, ++blk) {
       const int nr = (nrows - r) < round_rows ? (nrows - r) : round_rows;
-      const CUresult cr = wait_value(reinterpret_cast<CUstream>(emit->copy),
-                                     reinterpret_cast<CUdeviceptr>(strm.flag + blk), strm.epoch, CU_STREAM_WAIT_VALUE_GEQ);
-      if (cr != CUDA_SUCCESS) {
-        tg_set_error("cuStreamWaitValue32 failed with CUresult %d", (int)cr);
-        // the flags cannot be waited on: fall back to one copy behind the whole launch
-        cudaStreamSynchronize(st);
-        e = cudaMemcpyAsync(emit->host_out, out, (size_t)nrows * row_bytes, cudaMemcpyDeviceToHost, emit->copy);
-        break;
+      unsigned spins = 0;
+      while (flags[blk] != strm.epoch) {
+        if ((++spins & 0x3ffu) == 0) {                 // every 1024 polls: did the stream stop without the flag?
+          const cudaError_t q = cudaStreamQuery(st);
+          if (q == cudaErrorNotReady) continue;
+          if (q != cudaSuccess) {
+            tg_set_error("row-block streaming: %s", cudaGetErrorString(q));
+            rc = TG_ECUDA;
+          } else if (flags[blk] != strm.epoch) {
+            tg_set_error("row-block streaming: the launch finished without completing block %d", blk);
+            rc = TG_ECUDA;
+          }
+          break;
+        }
       }
-      e = cudaMemcpyAsync(emit->host_out + (size_t)r * row_bytes, static_cast<unsigned char *>(out) + (size_t)r * row_bytes,
-                          (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, emit->copy);
-    }
-    // the workspace (flags included) is released in `st` order when this function returns: keep it alive until the
-    // copy stream is past its last wait
-    if (e == cudaSuccess) e = cudaEventRecord(emit->ev[1], emit->copy);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, emit->ev[1], 0);
-    if (e != cudaSuccess) {
-      tg_set_error("row-block streaming: %s", cudaGetErrorString(e));
-      rc = TG_ECUDA;
+      if (rc != TG_OK) break;
+      const cudaError_t e = cudaMemcpyAsync(emit->host_out + (size_t)r * row_bytes,
+                                            static_cast<unsigned char *>(out) + (size_t)r * row_bytes,
+                                            (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, emit->copy);
+      if (e != cudaSuccess) {
+        tg_set_error("row-block D2H: %s", cudaGetErrorString(e));
+        rc = TG_ECUDA;
+      }
     }
   }
   if (rc == TG_OK && !out_is_c128 && pe.n > 0) {

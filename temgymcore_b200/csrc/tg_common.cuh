@@ -42,6 +42,11 @@ struct TgEmit {
   int block_rows;           // multiple of 128 (GEMM tile) -- hence of 32 (SFU tile)
   cudaStream_t copy;
   cudaEvent_t *ev;          // >= ceil(nrows / block_rows) events (cudaEventDisableTiming)
+  // optional: n_flags words of pinned, device-mapped host memory (and their device address).  With them a one-batch
+  // tensor-path call runs ONE GEMM launch that raises flag i when block i is complete, and the (synchronous)
+  // caller polls the words instead of waiting on events of per-block launches
+  unsigned int *flags_host = nullptr, *flags_dev = nullptr;
+  int n_flags = 0;
 };
 #define TG_SEP_VERDICT_ONLY 1 /* tg_separable_run: table + separability / cost verdict into *key_async, nothing else */
 #define TG_SEP_TRUSTED 2      /* tg_separable_run: the caller has read the verdict; skip the host-side check */

@@ -316,7 +316,18 @@ def pack_beamlets_pinned(gaussian_rays):
         v[:] = h
         views[f] = v.reshape(n, 2) if width == 2 else v
         off += n * width
-    return type(g)(**views)
+    packed = type(g)(**views)
+    # the host-buffer call's pointer arguments, resolved once (twelve array-interface lookups are ~25 us of
+    # Python per call otherwise); `dataclasses.replace` / `derive` make a new object without this memo
+    hp = _host_ptr
+    object.__setattr__(packed, "_tg_host_args", (
+        n, tuple(hp(views[f]) for f in RAY_FIELDS),
+        tuple(hp(views[f]) for f in ("amplitude", "waist_xy", "radii_of_curv", "wavelength", "theta")), slab))
+    return packed
+
+
+def _host_ptr(a: np.ndarray) -> int:
+    return a.__array_interface__["data"][0]
 
 
 def make_gaussian_image_host(gaussian_rays, model, *, cull_bits=None, out_dtype=None, row0=0,
@@ -329,30 +340,35 @@ def make_gaussian_image_host(gaussian_rays, model, *, cull_bits=None, out_dtype=
     grid = model[-1]
     H, W = int(grid.shape[0]), int(grid.shape[1])
     nrows = H - row0 if nrows is None else nrows
-    n = 1
-    for f in RAY_FIELDS + ("amplitude", "wavelength", "theta"):
-        n = max(n, A.numel(getattr(g, f)))
-    n = max(n, A.numel(g.waist_xy) // 2, A.numel(g.radii_of_curv) // 2)
+    memo = getattr(g, "_tg_host_args", None)       # pack_beamlets_pinned resolved the pointers already
+    if memo is not None:
+        n, ray_ptrs, (p_amp, p_waist, p_radii, p_wl, p_th), _slab = memo
+    else:
+        n = 1
+        for f in RAY_FIELDS + ("amplitude", "wavelength", "theta"):
+            n = max(n, A.numel(getattr(g, f)))
+        n = max(n, A.numel(g.waist_xy) // 2, A.numel(g.radii_of_curv) // 2)
 
-    def vec(v, width=1):
-        h = A.to_host_f64(v)
-        if h.size == width and n > 1:
-            h = np.ascontiguousarray(np.broadcast_to(h.reshape(1, width), (n, width)).reshape(-1))
-        if h.size != n * width:
-            raise ValueError("GaussianRay fields have mismatched sizes")
-        return h
+        def vec(v, width=1):
+            h = A.to_host_f64(v)
+            if h.size == width and n > 1:
+                h = np.ascontiguousarray(np.broadcast_to(h.reshape(1, width), (n, width)).reshape(-1))
+            if h.size != n * width:
+                raise ValueError("GaussianRay fields have mismatched sizes")
+            return h
 
-    rays = [vec(getattr(g, f)) for f in RAY_FIELDS]
-    amp, wl, th = vec(g.amplitude), vec(g.wavelength), vec(g.theta)
-    waist, radii = vec(g.waist_xy, 2), vec(g.radii_of_curv, 2)
+        keep = [vec(getattr(g, f)) for f in RAY_FIELDS]
+        keep += [vec(g.amplitude), vec(g.waist_xy, 2), vec(g.radii_of_curv, 2), vec(g.wavelength), vec(g.theta)]
+        hp = _host_ptr
+        ray_ptrs = tuple(hp(r) for r in keep[:7])
+        p_amp, p_waist, p_radii, p_wl, p_th = (hp(r) for r in keep[7:])
     out_dtype = torch.complex128 if out_dtype is None else out_dtype
     out = _pinned_empty((nrows, W), out_dtype)
     cull = DEFAULT_CULL_BITS if cull_bits is None else int(cull_bits)
     cm = compile_model(model)
     dev = A.current_device_index() if device is None else int(device)
     L.check(lib.tg_make_gaussian_image_host(
-        C.byref(cm), n, L.ptr_array([r.ctypes.data for r in rays]), amp.ctypes.data,
-        waist.ctypes.data, radii.ctypes.data, wl.ctypes.data, th.ctypes.data,
+        C.byref(cm), n, L.ptr_array(ray_ptrs), p_amp, p_waist, p_radii, p_wl, p_th,
         L.dbl_array(grid.px2m_affine), H, W, row0, nrows, out.data_ptr(),
         int(out_dtype == torch.complex128), cull, L.TG_METHOD[method], dev),
         "tg_make_gaussian_image_host")

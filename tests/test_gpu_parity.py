@@ -736,13 +736,15 @@ def test_host_pipeline_row_blocks(torch_cuda, method):
     assert rel_l2(host_img, ref) < FIELD_TOL
 
 
+@pytest.mark.parametrize("variant", ["TG_E2E_STREAM", "TG_E2E_FLAGGED"])
 @pytest.mark.parametrize("method", ["tensor_4m", "tensor_3m", "tensor_tf32"])
-def test_host_pipeline_streamed_rounds(torch_cuda, method):
-    """One beamlet batch through the host-buffer call: ONE GEMM launch walks the image in rounds of 256 rows, each
-    split along K over the machine (deep K: several partial tiles per output tile), raises a flag per finished
-    block, and the copy stream moves the block behind cuStreamWaitValue32.  Same image as the device path; repeated
-    calls (the flag words live in a recycled workspace) stay identical."""
+def test_host_pipeline_flag_variants(torch_cuda, method, variant, monkeypatch):
+    """The two opt-in variants of the host pipeline that signal finished row blocks through flag words in pinned host
+    memory, polled by the call: TG_E2E_STREAM=1 -- ONE GEMM launch walks the image in rounds of 256 rows, each split
+    along K over the machine (deep K: several partial tiles per output tile); TG_E2E_FLAGGED=1 -- one launch per
+    block, chained with programmatic dependent launch.  Same image as the device path; repeated calls stay identical."""
     from temgymcore_b200.gaussian import make_gaussian_image_device, make_gaussian_image_host, pack_beamlets_pinned
+    monkeypatch.setenv(variant, "1")
     g, model = M.aperture_diffraction_case(6000, (768, 256))
     dev_img = to_np(make_gaussian_image_device(gaussian_to_cuda(torch_cuda, g), model, cull_bits=0, method=method))
     gp = pack_beamlets_pinned(g)
