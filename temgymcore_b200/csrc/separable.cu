@@ -312,6 +312,20 @@ struct SkIter {
 // term: 25 % less tensor work, same operand bytes); the epilogue adds each drained chunk into the (re, im)
 // registers with the signs above.  A tile is 128 rows x 128 COMPLEX columns (Np = complex columns, the output row
 // holds 2 Np doubles), 16 epilogue warps of 32 complex columns each.
+// Experiment builds (TG_BUILD_DEFS=-DTG_GEMM_TRACE): %globaltimer stamps of every CTA's milestones, read back with
+// tg_debug_gemm_trace -- where a launch spends the ~20 us it costs beyond its tensor work (tools/exp_gemm_trace.py)
+#ifdef TG_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[148 * 8];
+__device__ __forceinline__ void gemm_trace(int cta, int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  if (cta < 148) g_gemm_trace[cta * 8 + slot] = t;
+}
+#define GEMM_TRACE(cta, slot) gemm_trace(cta, slot)
+#else
+#define GEMM_TRACE(cta, slot) ((void)0)
+#endif
+
 template <bool F16, bool GAUSS>
 __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
     gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -338,6 +352,7 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x;
   const int nkb = sched.nkb;
+  if (threadIdx.x == 0) GEMM_TRACE(cta, 0);           // kernel entry
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -361,6 +376,7 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  if (threadIdx.x == 0) GEMM_TRACE(cta, 1);           // prologue done (barriers, TMEM)
 
   if (warp == 0) {
     // ===== TMA producer: the shared-memory ring runs on across unit boundaries =====
@@ -422,6 +438,7 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
           }
           tg_mbar_wait(&ctl->full[s], ph);
           tc_fence_after();
+          if (it == 0) GEMM_TRACE(cta, 2);             // first operand stage has landed
           unsigned char *st = tiles + s * STAGE_BYTES;
           const uint64_t dAh = make_smem_desc(st + 0 * TILE_BYTES), dAl = make_smem_desc(st + 1 * TILE_BYTES);
           const uint64_t dBh = make_smem_desc(st + 2 * TILE_BYTES);
@@ -443,6 +460,7 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
             ++chn;
           }
         }
+        GEMM_TRACE(cta, 3);                            // all MMAs of the (last) unit issued
       }
     }
   } else if (warp >= 4) {
@@ -506,6 +524,7 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
       }
+      if (ew == 0 && lane == 0) GEMM_TRACE(cta, 4);     // last chunk drained from TMEM
       if (u.nparts > 1) {
         // stream-K piece: park the fp32 partial ([slot][epilogue warp][column][lane]: coalesced), count the
         // arrival; the last piece of this tile sums the slots in slot order (fp32, like the chunk sums)
@@ -521,6 +540,7 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
           prev = atomicAdd(counters + u.tile * NE + ew, 1u);
         }
         prev = __shfl_sync(0xffffffffu, prev, 0);
+        if (ew == 0 && lane == 0) GEMM_TRACE(cta, 5);   // partial parked, arrival counted
         if (prev != (unsigned)(u.nparts - 1)) continue;   // not the last piece
         __threadfence();
         if (lane == 0) counters[u.tile * NE + ew] = 0u;   // leave the counters clean for the next launch
@@ -590,6 +610,7 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
             }
         }
       }
+      if (ew == 0 && lane == 0) GEMM_TRACE(cta, 6);     // output rows stored (final writer)
       if (round_flag) {
         // row-block streaming: this warp's part of the tile is in memory; the last warp of the round's last tile
         // publishes the round (system scope: a copy-engine read behind cuStreamWaitValue32 follows)
@@ -617,6 +638,7 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
                  "r"((uint32_t)TMEM_COLS)
                  : "memory");
   }
+  if (threadIdx.x == 0) GEMM_TRACE(cta, 7);           // CTA done
 }
 
 // ---------------------------------------------------------------- CTA-pair GEMM (tcgen05 cta_group::2)
@@ -1730,6 +1752,19 @@ extern "C" int tg_gemm_schedule(int M, int N, int K, int f16, int sms, int mode,
   }
   return n;
 }
+
+#ifdef TG_GEMM_TRACE
+extern "C" int tg_debug_gemm_trace(unsigned long long *out, int clear) {
+  TG_REQUIRE(out, "null pointer");
+  TG_CUDA(cudaDeviceSynchronize());
+  TG_CUDA(cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(unsigned long long) * 148 * 8));
+  if (clear) {
+    static unsigned long long zero[148 * 8] = {};
+    TG_CUDA(cudaMemcpyToSymbol(g_gemm_trace, zero, sizeof(zero)));
+  }
+  return TG_OK;
+}
+#endif
 
 // D[M x N] = (A_hi + A_lo)[M x K] * (B_hi + B_lo)[N x K]^T on the tensor cores (3 x TF32), fp64 out.
 extern "C" int tg_gemm_tf32x3(int M, int N, int K, const float *A_hi, const float *A_lo, const float *B_hi,
