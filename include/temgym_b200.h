@@ -296,12 +296,20 @@ int tg_field_sum_separable(int64_t nb, const double *poly, const double px2m[6],
 #define TG_METHOD_TENSOR_3M 5   /* fp16 x 3 with three real multiplications per complex term (Gauss: 25 % less tensor
                                    work, tiles twice as large).  TG_METHOD_TENSOR / AUTO run the 4-multiplication
                                    form unless the environment sets TG_TENSOR_GAUSS=1 */
+#define TG_METHOD_TENSOR_BINNED 6 /* tile-binned (block-sparse K) tensor-core sum for separable beamlets that each reach a
+                                   small part of the detector (BASELINE C3): every 128-row x 64-column output tile only
+                                   multiplies the beamlets whose bounding box {envelope >= brightest peak - cull_bits}
+                                   meets it.  Needs cull_bits > 0.  TG_METHOD_AUTO picks it (outside stream capture, for
+                                   more than 16384 beamlets or host-buffer calls) when the beamlets are separable and
+                                   sparse; TG_EUNSUPPORTED when the operands would exceed the capacity limit, and under
+                                   stream capture unless the same call ran once eagerly on this host thread before */
 int tg_field_sum(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0,
                  int nrows, void *out, int out_is_c128, int cull_bits, int method, void *stream);
 
 /* The verdict TG_METHOD_AUTO reaches on the device for these beamlets on this grid, read back to the host
- * (synchronises `stream`; not inside a stream capture): *use_tensor = 1 -> tensor-core path (separable, and not clearly
- * more expensive than the culled SFU sum), 0 -> SFU kernel.  Plans (GaussianImagePlan, PeerImagePlan) call it once at
+ * (synchronises `stream`; not inside a stream capture): *use_tensor = 1 -> dense tensor-core path (separable, and not
+ * clearly more expensive than the culled SFU sum), 2 -> tile-binned tensor-core path (separable and sparse,
+ * TG_METHOD_TENSOR_BINNED), 0 -> SFU kernel.  Plans (GaussianImagePlan, PeerImagePlan) call it once at
  * build time and capture the launches of that one path. */
 int tg_field_sum_verdict(int64_t nb, const double *poly, const double px2m[6], int H, int W, int cull_bits,
                          int *use_tensor, void *stream);
@@ -344,6 +352,13 @@ int tg_cgemm3_f16x3(int M, int N, int K3, const void *A_hi, const void *A_lo, co
  * max_units are written). */
 int tg_gemm_schedule(int M, int N, int K, int f16, int sms, int mode, int32_t *units, int max_units,
                      int32_t *sched_out);
+/* The RAGGED decomposition the tile-binned sum (TG_METHOD_TENSOR_BINNED) builds on the device, mirrored on the host (no
+ * device needed): tile t owns chunks_per_tile[t] accumulation chunks of one concatenated k axis, `sms` CTAs split that
+ * axis evenly.  units[8 i..] = {cta, tile, chunk_begin, chunk_end, slot, nparts, scratch slot written, first CTA of the
+ * tile}; readers[] = for every unit in turn the nparts scratch slots the tile's last arriver sums.  Returns the number
+ * of units. */
+int tg_gemm_schedule_ragged(int T, const int32_t *chunks_per_tile, int sms, int32_t *units, int max_units,
+                            int32_t *readers, int max_readers);
 
 /* ---- host-buffer field sum (make_gaussian_image end to end, gaussian.py:225-273) -- */
 /* All pointers HOST.  rays[7] are the central rays (length nb each), waist_xy /

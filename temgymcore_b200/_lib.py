@@ -21,7 +21,8 @@ TG_OP_KRIVANEK, TG_OP_OFFSET, TG_OP_THICKLENS, TG_OP_ROTATOR = 4, 5, 6, 7
 TG_F_NOPROP = 1
 TG_F_DIST = 2
 TG_JAC_NONE, TG_JAC_ABCD5, TG_JAC_FULL7 = 0, 1, 2
-TG_METHOD = {"auto": 0, "sfu": 1, "tensor": 2, "tensor_tf32": 3, "tensor_4m": 4, "tensor_3m": 5}
+TG_METHOD = {"auto": 0, "sfu": 1, "tensor": 2, "tensor_tf32": 3, "tensor_4m": 4, "tensor_3m": 5,
+             "tensor_binned": 6}
 TG_OK, TG_EINVAL, TG_ECUDA, TG_ENOTSEPARABLE, TG_EUNSUPPORTED = 0, -1, -2, -3, -4
 
 
@@ -103,6 +104,7 @@ SIGNATURES = {
     "tg_gemm_chunk_k": (_i32, []),
     "tg_cgemm3_f16x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
     "tg_gemm_schedule": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "tg_gemm_schedule_ragged": (_i32, [_i32, _vp, _i32, _vp, _i32, _vp, _i32]),
     "tg_peer_alloc": (_i32, [C.c_uint64, C.POINTER(_vp), _vp]),
     "tg_peer_open": (_i32, [_vp, C.POINTER(_vp)]),
     "tg_peer_close": (_i32, [_vp]),

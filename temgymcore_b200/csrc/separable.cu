@@ -207,9 +207,15 @@ struct SkSched {
   // of tile rows -- each round split along K over the whole machine, so that the image is finished block of rows by
   // block of rows inside ONE launch; rounds = 1, Tr = T is the plain split-K above
   int rounds, Tr;
+  // RAGGED schedule of the tile-binned (block-sparse K) sum: tile t owns the GLOBAL accumulation chunks [P[t], P[t+1])
+  // of one concatenated k axis, P and the chunks per CTA live in device memory (bins[]: built on the device from the
+  // beamlets' bounding boxes, never read by the host); CTA c takes chunks [c q, (c + 1) q)
+  const int *bins;
 };
+enum { BIN_CTOT = 0, BIN_Q = 1, BIN_OVERFLOW = 2, BIN_NEED = 3, BIN_HDR = 4 };   // bins[]: header, then P[0..T]
 struct SkUnit {
   int tile, ch0, ch1, slot, nparts;
+  int first, p0, rq;   // ragged: first CTA of the tile, P[tile], chunks per CTA
 };
 __host__ __device__ inline int sk_nparts(const SkSched &s, int tile) {
   if (s.uniform) return s.maxparts;
@@ -221,10 +227,27 @@ __host__ __device__ inline int sk_nparts(const SkSched &s, int tile) {
 struct SkIter {
   int phase;  // 0: head of a stream-K tile pending, 1: helper walking its run of tail chunks, 2: data-parallel tiles
   int f0, f1, t;
+  template <bool RG = false>
   __host__ __device__ __forceinline__ void init(const SkSched &s, int cta) {
     phase = 2;
     f0 = f1 = 0;
     t = s.R + cta;
+    if (RG) {                // ragged: f0 = position, f1 = end (global chunks), t = tile holding f0
+      phase = 5;
+      const int ctot = s.bins[BIN_CTOT], q = s.bins[BIN_Q];
+      const long long a = (long long)cta * q;
+      f0 = (int)(a < ctot ? a : ctot);
+      f1 = (int)(a + q < ctot ? a + q : ctot);
+      const int *P = s.bins + BIN_HDR;
+      int lo = 0, hi = s.T;                       // P[0] = 0 <= f0 < P[T] = ctot (when the CTA has work)
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (P[mid] <= f0) lo = mid;
+        else hi = mid;
+      }
+      t = lo;
+      return;
+    }
     if (s.uniform) {
       phase = 3;
     } else if (s.R > 0) {
@@ -241,7 +264,24 @@ struct SkIter {
       }
     }
   }
+  template <bool RG = false>
   __host__ __device__ __forceinline__ bool next(const SkSched &s, int cta, SkUnit &u) {
+    if (RG) {                // ragged: the rest of this CTA's chunk range that lies inside the next non-empty tile
+      if (f0 >= f1) return false;
+      const int *P = s.bins + BIN_HDR;
+      while (P[t + 1] <= f0) ++t;
+      const int p0 = P[t], p1 = P[t + 1], q = s.bins[BIN_Q];
+      u.tile = t;
+      u.ch0 = f0;                                  // GLOBAL chunk indices: the k coordinate of the operands
+      u.ch1 = f1 < p1 ? f1 : p1;
+      u.first = p0 / q;
+      u.nparts = (p1 - 1) / q - u.first + 1;
+      u.slot = cta - u.first;
+      u.p0 = p0;
+      u.rq = q;
+      f0 = u.ch1;
+      return true;
+    }
     if (phase == 3) {        // plain split-K: one unit per CTA and round
       const int split = cta / s.Tr, col = cta - split * s.Tr;
       while (f0 < s.rounds) {
@@ -326,7 +366,7 @@ __device__ __forceinline__ void gemm_trace(int cta, int slot) {
 #define GEMM_TRACE(cta, slot) ((void)0)
 #endif
 
-template <bool F16, bool GAUSS>
+template <bool F16, bool GAUSS, bool RAGGED = false>
 __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
     gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -382,11 +422,12 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
     // ===== TMA producer: the shared-memory ring runs on across unit boundaries =====
     if (lane == 0) {
       SkIter itr;
-      itr.init(sched, cta);
+      itr.template init<RAGGED>(sched, cta);
       SkUnit u;
       uint32_t it = 0;
-      while (itr.next(sched, cta, u)) {
-        const int m0 = (u.tile / sched.tiles_n) * BM, n0 = (u.tile % sched.tiles_n) * BN;
+      while (itr.template next<RAGGED>(sched, cta, u)) {
+        // (ragged schedule: every tile's operands are 128-row blocks of their own at the tile's global chunks)
+        const int m0 = RAGGED ? 0 : (u.tile / sched.tiles_n) * BM, n0 = RAGGED ? 0 : (u.tile % sched.tiles_n) * BN;
         const int kb0 = u.ch0 * CHUNK_KB, kb1 = min(u.ch1 * CHUNK_KB, nkb);
         // Experiment knob (TG_GEMM_PREFETCH, default 0): stream-K pieces take ~1.8x longer per k-block than whole
         // tiles whose CTAs share operand tiles in lockstep; asking the TMA unit to prefetch the tiles `pf` k-blocks
@@ -422,10 +463,10 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
     // ===== MMA issuer =====
     if (lane == 0) {
       SkIter itr;
-      itr.init(sched, cta);
+      itr.template init<RAGGED>(sched, cta);
       SkUnit u;
       uint32_t it = 0, chn = 0;
-      while (itr.next(sched, cta, u)) {
+      while (itr.template next<RAGGED>(sched, cta, u)) {
         const int kb0 = u.ch0 * CHUNK_KB, kb1 = min(u.ch1 * CHUNK_KB, nkb);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = (int)(it % STAGES);
@@ -472,10 +513,10 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
     const double sc = peak_key ? scalbn(1.0, (int)(tg_prescale_G(*peak_key) - 2.0 * headroom)) : 1.0;
     float accum[64];
     SkIter itr;
-    itr.init(sched, cta);
+    itr.template init<RAGGED>(sched, cta);
     SkUnit u;
     uint32_t chn = 0;
-    while (itr.next(sched, cta, u)) {
+    while (itr.template next<RAGGED>(sched, cta, u)) {
       const int m0 = (u.tile / sched.tiles_n) * BM, n0 = (u.tile % sched.tiles_n) * BN;
       const int kb0 = u.ch0 * CHUNK_KB, kb1 = min(u.ch1 * CHUNK_KB, nkb);
       const int nchunks = (kb1 - kb0 + CHUNK_KB - 1) / CHUNK_KB;
@@ -528,8 +569,12 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
       if (u.nparts > 1) {
         // stream-K piece: park the fp32 partial ([slot][epilogue warp][column][lane]: coalesced), count the
         // arrival; the last piece of this tile sums the slots in slot order (fp32, like the chunk sums)
-        float *slot0 = scratch + ((size_t)u.tile * sched.maxparts) * (size_t)PART_FLOATS + (size_t)ew * 2048 + lane;
-        float *mine = slot0 + (size_t)u.slot * (size_t)PART_FLOATS;
+        // static schedules: slot s of tile t at [t maxparts + s]; ragged: two slots per CTA -- a CTA's first unit
+        // (which may start inside a tile) parks in slot 2c, a later partial unit (it starts at its tile's first chunk
+        // and is the CTA's last) in slot 2c + 1
+        constexpr bool rg = RAGGED;
+        float *slot0 = scratch + (rg ? (size_t)0 : (size_t)u.tile * sched.maxparts) * (size_t)PART_FLOATS + (size_t)ew * 2048 + lane;
+        float *mine = slot0 + (rg ? (size_t)(2 * cta + (u.ch0 == cta * u.rq ? 0 : 1)) : (size_t)u.slot) * (size_t)PART_FLOATS;
 #pragma unroll
         for (int i = 0; i < 64; ++i) __stcg(mine + i * 32, accum[i]);
         __threadfence();
@@ -547,7 +592,12 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
 #pragma unroll
         for (int i = 0; i < 64; ++i) accum[i] = 0.f;
         for (int s = 0; s < u.nparts; ++s) {
-          const float *src = slot0 + (size_t)s * (size_t)PART_FLOATS;
+          size_t si = (size_t)s;
+          if (rg) {
+            const int c = u.first + s;
+            si = (size_t)(2 * c + ((long long)c * u.rq >= (long long)u.p0 ? 0 : 1));
+          }
+          const float *src = slot0 + si * (size_t)PART_FLOATS;
 #pragma unroll
           for (int i = 0; i < 64; ++i) accum[i] += __ldcg(src + i * 32);
         }
@@ -1166,9 +1216,14 @@ __global__ void __launch_bounds__(256)
   for (int o = 16; o > 0; o >>= 1) tiles += __shfl_xor_sync(0xffffffffu, tiles, o);
   if ((threadIdx.x & 31) == 0 && tiles > 0.0) atomicAdd(est_tiles, tiles);
 }
-__global__ void verdict_kernel(unsigned long long *key, const double *est_tiles, double nominal_evals, double ratio) {
-  if (*est_tiles * 4096.0 < ratio * nominal_evals)
-    atomicMax(key, (unsigned long long)__double_as_longlong(2.0));   // > 1: "not for the tensor path"
+// split != NULL: the cost verdict goes to *split (1 = the beamlets are sparse on this grid) and the key keeps the pure
+// separability verdict -- the host then picks the tile-binned tensor sum for "separable and sparse"
+__global__ void verdict_kernel(unsigned long long *key, const double *est_tiles, double nominal_evals, double ratio,
+                               unsigned long long *split) {
+  if (*est_tiles * 4096.0 < ratio * nominal_evals) {
+    if (split) *split = 1ULL;
+    else atomicMax(key, (unsigned long long)__double_as_longlong(2.0));   // > 1: "not for the tensor path"
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1180,6 +1235,242 @@ __global__ void __launch_bounds__(256)
     out[i] = v;
     for (int p = 0; p < peers.n; ++p) static_cast<float *>(peers.ptr[p])[i] = v;
   }
+}
+
+// ---------------------------------------------------------------- tile-binned (block-sparse K) separable sum
+// BASELINE C3 is separable but SPARSE: 1e5 beamlets of ~100 px reach on a 2048^2 detector, so the dense GEMM spends 98 %
+// of its tensor work on (beamlet, pixel) pairs below the culling threshold, and the culled SFU kernel evaluates the
+// remaining 1-3 % pixel by pixel.  Here the sum stays on the tensor cores but every output tile only multiplies the
+// beamlets whose bounding box {envelope >= brightest on-detector peak - cull_bits} meets it:
+//   * bin_ranges_kernel: per beamlet, the range of 128-row x 64-complex-column tiles its box touches;
+//   * bin_tiles_kernel<false>: per tile (one CTA; each of its 8 warps scans a contiguous eighth of the beamlets) the
+//     number of beamlets that reach it; bin_prefix_kernel: chunks of 128 beamlets per tile -> P[0..T] (exclusive scan),
+//     the chunks per CTA of the ragged GEMM schedule, the overflow verdict against the operand capacity;
+//   * bin_tiles_kernel<true>: the same scan again, appending the beamlet indices IN BEAMLET ORDER (deterministic sums)
+//     to the tile's slots sel[P[t] * 128 ...], padded with -1 to whole chunks; chunk -> tile map c2t;
+//   * factor_*_binned_kernel: row / column factors of slot s for the 128 rows / 64 columns of ITS tile into operands of
+//     128 rows x (capacity * 256) k-elements -- one concatenated k axis, chunk g at k = 256 g;
+//   * gemm_x3_kernel with the ragged schedule (SkSched::bins): 148 CTAs split the chunk axis evenly, tiles cut by a CTA
+//     boundary are fixed up by the last arriver like every stream-K piece.
+// Per (beamlet, tile) pair: 192 factor evaluations and 2 KB of operands instead of up to 8192 SFU pixel evaluations;
+// the operands are read once each (no reuse across tiles), so the kernel streams them at the HBM rate.
+constexpr int BIN_SLOTS = CHUNK_K / 2;   // beamlets per accumulation chunk (4-multiplication real form: 2 k per beamlet)
+constexpr int BIN_TN = BN / 2;           // complex columns per tile
+constexpr int BIN_WARPS = 8;
+
+// tr[i] = (first tile column, last tile column, first tile row, last tile row) of beamlet i inside rows
+// [row0, row0 + nrows); (1, 0, 1, 0) when it reaches nothing.  Same box as field.cu's bbox_kernel (+-1 px slack;
+// non-concave or non-finite envelopes get everything, so NaN beamlets poison the image as in the dense sum).
+__global__ void __launch_bounds__(256)
+    bin_ranges_kernel(long long nb, const double *__restrict__ table, int H, int W, int row0, int nrows,
+                      const unsigned long long *__restrict__ gref_key, int cull_bits, short4 *__restrict__ tr) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  double c_lo = 0.0, c_hi = (double)(W - 1), r_lo = (double)row0, r_hi = (double)(row0 + nrows - 1);
+  bool empty = false;
+  const unsigned long long k = *gref_key;
+  const double *e = table + i * 12 + 6;   // E(c, r) = e0 + e1 c + e2 r + e3 c^2 + e4 c r + e5 r^2 [bits]
+  const double det = e[3] * e[5] - 0.25 * e[4] * e[4];
+  if (k != ~0ULL && e[3] < 0.0 && e[5] < 0.0 && det > 0.0) {
+    const double e_thr = -(tg_dec_ordered(k) + (double)cull_bits);
+    const double cs = (0.5 * e[4] * e[2] - e[5] * e[1]) / (2.0 * det);
+    const double rs = (0.5 * e[4] * e[1] - e[3] * e[2]) / (2.0 * det);
+    const double d = (e[0] + 0.5 * (e[1] * cs + e[2] * rs)) - e_thr;
+    if (d < 0.0) {
+      empty = true;
+    } else if (isfinite(d) && isfinite(cs) && isfinite(rs)) {
+      const double hc = sqrt(d * (-e[5]) / det) + 1.0, hr = sqrt(d * (-e[3]) / det) + 1.0;
+      c_lo = fmax(c_lo, floor(cs - hc));
+      c_hi = fmin(c_hi, ceil(cs + hc));
+      r_lo = fmax(r_lo, floor(rs - hr));
+      r_hi = fmin(r_hi, ceil(rs + hr));
+      empty = c_hi < c_lo || r_hi < r_lo;
+    }
+  }
+  short4 o = make_short4(1, 0, 1, 0);
+  if (!empty)
+    o = make_short4((short)((int)c_lo / BIN_TN), (short)((int)c_hi / BIN_TN), (short)(((int)r_lo - row0) / BM),
+                    (short)(((int)r_hi - row0) / BM));
+  tr[i] = o;
+}
+
+// One CTA per tile, warp w scans beamlets [w seg, (w + 1) seg).  FILL = false: wc[t][w] = hits of warp w.
+// FILL = true: append the hits in order behind the hits of the warps before, pad the tile's last chunk, fill c2t.
+template <bool FILL>
+__global__ void __launch_bounds__(32 * BIN_WARPS)
+    bin_tiles_kernel(long long nb, const short4 *__restrict__ tr, int tiles_n, int T, int *__restrict__ wc,
+                     const int *__restrict__ bins, int *__restrict__ sel, int *__restrict__ c2t) {
+  if (FILL && bins[BIN_OVERFLOW]) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long seg = (((nb + BIN_WARPS - 1) / BIN_WARPS + 31) / 32) * 32;
+  const long long b0 = (long long)warp * seg, b1 = (b0 + seg < nb) ? b0 + seg : nb;
+  for (int t = blockIdx.x; t < T; t += gridDim.x) {
+    const short tm = (short)(t / tiles_n), tn = (short)(t % tiles_n);
+    long long base = 0;
+    int total = 0;
+    if (FILL) {
+      const int *P = bins + BIN_HDR;
+      base = (long long)P[t] * BIN_SLOTS;
+      for (int w = 0; w < BIN_WARPS; ++w) {
+        const int c = wc[t * BIN_WARPS + w];
+        base += (w < warp) ? c : 0;
+        total += c;
+      }
+    }
+    int pos = 0;
+#pragma unroll 4
+    for (long long i0 = b0; i0 < b1; i0 += 32) {
+      const long long i = i0 + lane;
+      bool hit = false;
+      if (i < b1) {
+        const short4 r = __ldg(tr + i);
+        hit = r.x <= tn && tn <= r.y && r.z <= tm && tm <= r.w;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (FILL && hit) sel[base + pos + __popc(bal & ((1u << lane) - 1u))] = (int)i;
+      pos += __popc(bal);
+    }
+    if (!FILL) {
+      if (lane == 0) wc[t * BIN_WARPS + warp] = pos;
+    } else {
+      const int *P = bins + BIN_HDR;
+      const int p0 = P[t], p1 = P[t + 1];
+      if (warp == 0)
+        for (long long s = (long long)p0 * BIN_SLOTS + total + lane; s < (long long)p1 * BIN_SLOTS; s += 32) sel[s] = -1;
+      if (warp == 1)
+        for (int g = p0 + lane; g < p1; g += 32) c2t[g] = t;
+    }
+  }
+}
+
+// P[t] = chunks before tile t; bins header: total chunks (0 on overflow), chunks per GEMM CTA, overflow flag, chunks needed
+__global__ void __launch_bounds__(1024)
+    bin_prefix_kernel(int T, const int *__restrict__ wc, int *__restrict__ bins, int G, int cap_chunks) {
+  __shared__ long long wsum[32];
+  __shared__ long long carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  int *P = bins + BIN_HDR;
+  for (int base = 0; base < T; base += 1024) {
+    const int t = base + threadIdx.x;
+    long long cnt = 0;
+    if (t < T)
+      for (int w = 0; w < BIN_WARPS; ++w) cnt += wc[t * BIN_WARPS + w];
+    const long long ch = (cnt + BIN_SLOTS - 1) / BIN_SLOTS;
+    long long inc = ch;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    long long before = carry_s;
+    for (int w = 0; w < warp; ++w) before += wsum[w];
+    const long long excl = before + inc - ch;
+    if (t < T) P[t] = (int)(excl < 0x7fffffffLL ? excl : 0x7fffffffLL);
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = before + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const long long tot = carry_s;
+    const bool over = tot > (long long)cap_chunks;
+    bins[BIN_OVERFLOW] = over ? 1 : 0;
+    bins[BIN_NEED] = (int)(tot < 0x7fffffffLL ? tot : 0x7fffffffLL);   // chunks the beamlets need (also when over capacity)
+    bins[BIN_CTOT] = over ? 0 : (int)tot;
+    const long long q = (tot + G - 1) / G;
+    bins[BIN_Q] = (int)(q > 0 ? q : 1);
+    P[T] = over ? 0 : (int)tot;
+  }
+  __syncthreads();
+  if (bins[BIN_OVERFLOW])
+    for (int t = threadIdx.x; t < T; t += 1024) P[t] = 0;
+}
+
+// A[(row in tile)][2 s, 2 s + 1] = U_n(row), n = sel[s], for the 128 rows of the tile that owns slot s
+template <bool F16>
+__global__ void __launch_bounds__(BIN_SLOTS)
+    factor_rows_binned_kernel(const double *__restrict__ table, const int *__restrict__ bins, const int *__restrict__ sel,
+                              const int *__restrict__ c2t, int tiles_n, int row0, int M, int W, long long ldk,
+                              void *__restrict__ Ahi, void *__restrict__ Alo,
+                              const unsigned long long *__restrict__ peak_key,
+                              const unsigned long long *__restrict__ sep_guard) {
+  if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
+  constexpr int NS = BM / FS;
+  const long long items = (long long)bins[BIN_CTOT] * NS;
+  for (long long vb = blockIdx.x; vb < items; vb += gridDim.x) {
+    const int g = (int)(vb / NS), sidx = (int)(vb % NS);
+    const long long s = (long long)g * BIN_SLOTS + threadIdx.x;
+    const int n = sel[s];
+    const int m0 = (c2t[g] / tiles_n) * BM + sidx * FS;      // first row of the strip, relative to row0
+    Strip1D st = {};
+    if (n >= 0) {
+      const double *t = table + (long long)n * 12;
+      double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
+      mu += Headroom<F16>::value - tg_prescale_G(*peak_key);
+      st = strip_setup(t[0], t[2], t[5], t[6 + 0] + mu, t[6 + 2], t[6 + 5], (double)(row0 + m0));
+    }
+#pragma unroll 4
+    for (int j = 0; j < FS; ++j) {
+      float rh = 0.f, rl = 0.f, ih = 0.f, il = 0.f;
+      if (n >= 0 && m0 + j < M) {
+        float re, im;
+        strip_eval(st, j, re, im);
+        Operand<F16>::split(re, rh, rl);
+        Operand<F16>::split(im, ih, il);
+      }
+      const long long o = (long long)(sidx * FS + j) * ldk + 2 * s;
+      Operand<F16>::store2(Ahi, o, rh, ih);
+      Operand<F16>::store2(Alo, o, rl, il);
+    }
+  }
+}
+// B[2 c][2 s..] = (Re V, -Im V), B[2 c + 1][2 s..] = (Im V, Re V) for the 64 columns c of the tile that owns slot s
+template <bool F16>
+__global__ void __launch_bounds__(BIN_SLOTS)
+    factor_cols_binned_kernel(const double *__restrict__ table, const int *__restrict__ bins, const int *__restrict__ sel,
+                              const int *__restrict__ c2t, int tiles_n, int W, long long ldk, void *__restrict__ Bhi,
+                              void *__restrict__ Blo, const unsigned long long *__restrict__ sep_guard) {
+  if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
+  constexpr int NS = BIN_TN / FS;
+  const long long items = (long long)bins[BIN_CTOT] * NS;
+  for (long long vb = blockIdx.x; vb < items; vb += gridDim.x) {
+    const int g = (int)(vb / NS), sidx = (int)(vb % NS);
+    const long long s = (long long)g * BIN_SLOTS + threadIdx.x;
+    const int n = sel[s];
+    const int c0 = (c2t[g] % tiles_n) * BIN_TN + sidx * FS;
+    Strip1D st = {};
+    if (n >= 0) {
+      const double *t = table + (long long)n * 12;
+      const double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1)) - Headroom<F16>::value;
+      st = strip_setup(0.0, t[1], t[3], -mu, t[6 + 1], t[6 + 3], (double)c0);
+    }
+#pragma unroll 4
+    for (int j = 0; j < FS; ++j) {
+      float rh = 0.f, rl = 0.f, ih = 0.f, il = 0.f;
+      if (n >= 0 && c0 + j < W) {
+        float re, im;
+        strip_eval(st, j, re, im);
+        Operand<F16>::split(re, rh, rl);
+        Operand<F16>::split(im, ih, il);
+      }
+      const long long o0 = (long long)(2 * (sidx * FS + j)) * ldk + 2 * s, o1 = o0 + ldk;
+      Operand<F16>::store2(Bhi, o0, rh, -ih);
+      Operand<F16>::store2(Blo, o0, rl, -il);
+      Operand<F16>::store2(Bhi, o1, ih, rh);
+      Operand<F16>::store2(Blo, o1, il, rl);
+    }
+  }
+}
+// capacity overflow (a captured graph replayed on beamlets that need more operand chunks than it was built for) or a
+// non-separable input under capture: poison the output instead of returning a partial sum
+__global__ void __launch_bounds__(256)
+    nan_fill_binned_kernel(double *__restrict__ out, size_t n, const int *__restrict__ bins,
+                           const unsigned long long *__restrict__ key) {
+  if (!bins[BIN_OVERFLOW] && (!key || tg_key_is_separable(*key))) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
 // ---------------------------------------------------------------- host side
@@ -1276,6 +1567,7 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode
   s.maxparts = 1;
   s.S = 1;
   s.prefetch = 0;
+  s.bins = nullptr;
   s.uniform = 0;
   s.rounds = 1;
   s.Tr = s.T;
@@ -1712,6 +2004,12 @@ void sk_need_for_call(int64_t nb, int nrows, int block_rows, int W, int sms, siz
 // tiles, split in 4) 0.111 against 0.119 ms; on smaller row blocks and shards the 4-multiplication form wins (256 rows
 // 0.080 vs 0.088 ms, 128 rows 0.059 vs 0.090 ms).  Hence: 3-product from 32 complex tiles on.  TG_TENSOR_GAUSS=0 / 1
 // forces one form for every shape; TG_METHOD_TENSOR_3M / _4M select explicitly.
+// TG_TENSOR_BINNED=0: AUTO never takes the tile-binned sum (sparse separable beamlets go to the culled SFU kernel as
+// before) -- for A/B measurements.  Read on every call.
+bool binned_enabled() {
+  const char *e = getenv("TG_TENSOR_BINNED");
+  return !(e && atoi(e) == 0);
+}
 bool use_gauss(int rows, int W) {
   static const int forced = [] {
     const char *e = getenv("TG_TENSOR_GAUSS");
@@ -1750,6 +2048,54 @@ extern "C" int tg_gemm_schedule(int M, int N, int K, int f16, int sms, int mode,
       ++n;
     }
   }
+  return n;
+}
+
+// The RAGGED decomposition of the tile-binned sum (SkSched::bins), host-side mirror: chunks_per_tile[T] -> every unit
+// as the kernel's roles enumerate it, units[8 i..] = {cta, tile, chunk_begin, chunk_end (global chunk indices), slot,
+// nparts, scratch slot the unit parks its partial tile in, first CTA of the tile}; readers[] (may be NULL, sized by the
+// caller as sum of nparts over the returned units) lists for every unit the scratch slots a last arriver would sum,
+// part by part.  Returns the number of units, < 0 on error.
+extern "C" int tg_gemm_schedule_ragged(int T, const int32_t *chunks_per_tile, int sms, int32_t *units, int max_units,
+                                       int32_t *readers, int max_readers) {
+  TG_REQUIRE(T > 0 && chunks_per_tile && sms > 0, "bad arguments");
+  int *bins = static_cast<int *>(malloc(sizeof(int) * (size_t)(BIN_HDR + T + 1)));
+  TG_REQUIRE(bins, "out of memory");
+  long long tot = 0;
+  for (int t = 0; t < T; ++t) {
+    bins[BIN_HDR + t] = (int)tot;
+    tot += chunks_per_tile[t] > 0 ? chunks_per_tile[t] : 0;
+  }
+  bins[BIN_HDR + T] = (int)tot;
+  bins[BIN_CTOT] = (int)tot;
+  const long long q = (tot + sms - 1) / sms;
+  bins[BIN_Q] = (int)(q > 0 ? q : 1);
+  bins[BIN_OVERFLOW] = 0;
+  bins[BIN_NEED] = (int)tot;
+  SkSched s = make_sched(BM, BN, CHUNK_K, GemmCfg<true>::BK, GemmCfg<true>::CHUNK_KB, sms, 0);
+  s.T = T;
+  s.G = sms;
+  s.bins = bins;
+  int n = 0, nr = 0;
+  for (int cta = 0; cta < sms; ++cta) {
+    SkIter it;
+    it.init<true>(s, cta);
+    SkUnit u;
+    while (it.next<true>(s, cta, u)) {
+      if (units && n < max_units) {
+        int32_t *o = units + 8 * (size_t)n;
+        o[0] = cta; o[1] = u.tile; o[2] = u.ch0; o[3] = u.ch1; o[4] = u.slot; o[5] = u.nparts;
+        o[6] = 2 * cta + (u.ch0 == cta * u.rq ? 0 : 1);
+        o[7] = u.first;
+      }
+      for (int part = 0; part < u.nparts; ++part, ++nr) {
+        const int c = u.first + part;
+        if (readers && nr < max_readers) readers[nr] = 2 * c + ((long long)c * u.rq >= (long long)u.p0 ? 0 : 1);
+      }
+      ++n;
+    }
+  }
+  free(bins);
   return n;
 }
 
@@ -1945,7 +2291,7 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
     TG_CUDA(cudaMemsetAsync(strm.cnt, 0, sig_bytes, st));
   }
   TG_CUDA(cudaMemsetAsync(ws + table_bytes, 0, 16, st));  // own key slot, peak key
-  if (key_async) TG_CUDA(cudaMemsetAsync(key, 0, 8, st));
+  if (key_async) TG_CUDA(cudaMemsetAsync(key, 0, (flags & TG_SEP_VERDICT_SPLIT) ? 16 : 8, st));
   // cost model (AUTO with culling enabled): brightest-peak key and tile estimate live after the key slot
   const bool cost = key_async != nullptr && cost_cull_bits > 0;
   unsigned long long *gref = reinterpret_cast<unsigned long long *>(ws + table_bytes + 64);
@@ -1969,7 +2315,8 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
       const double v = e ? atof(e) : kSfuWinsBelow;
       return (v >= 0.0 && v <= 1.0) ? v : kSfuWinsBelow;
     }();
-    verdict_kernel<<<1, 1, 0, st>>>(key, est, (double)nb * (double)H * (double)W, sfu_wins_below);
+    verdict_kernel<<<1, 1, 0, st>>>(key, est, (double)nb * (double)H * (double)W, sfu_wins_below,
+                                    (flags & TG_SEP_VERDICT_SPLIT) ? key + 1 : nullptr);
     rc = tg_launch_check("cost kernels");
     if (rc != TG_OK) return rc;
   }
@@ -2040,6 +2387,192 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   return rc;
 }
 
+// ---- tile-binned tensor-core sum (see the kernels above) --------------------------------------------------------
+namespace {
+constexpr int kBinMaxChunks = 24576;        // operand capacity limit: 256 KiB per chunk -> 6 GiB
+struct BinCapKey {
+  long long nb;
+  int H, W, row0, nrows, cull, dev, need;
+};
+// chunks the last eager call of this thread needed, per shape: the capacity of a captured call
+BinCapKey *bin_cap_slot(long long nb, int H, int W, int row0, int nrows, int cull, int dev, bool create) {
+  static thread_local BinCapKey tab[16];
+  static thread_local int used = 0, next = 0;
+  for (int i = 0; i < used; ++i) {
+    BinCapKey &k = tab[i];
+    if (k.nb == nb && k.H == H && k.W == W && k.row0 == row0 && k.nrows == nrows && k.cull == cull && k.dev == dev) return &k;
+  }
+  if (!create) return nullptr;
+  BinCapKey &k = tab[next];
+  next = (next + 1) % 16;
+  if (used < 16) ++used;
+  k = BinCapKey{nb, H, W, row0, nrows, cull, dev, 0};
+  return &k;
+}
+}  // namespace
+
+int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0, int nrows,
+                            void *out, int out_is_c128, int cull_bits, cudaStream_t st, const TgPeers *peers,
+                            const TgEmit *emit, int flags) {
+  TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad shape");
+  TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
+  TG_REQUIRE(px2m && out, "null pointer");
+  TG_REQUIRE(cull_bits > 0, "the tile-binned sum needs a culling threshold (cull_bits > 0)");
+  if (nrows == 0) return TG_OK;
+  const size_t npix = (size_t)nrows * W;
+  const size_t out_bytes = npix * (out_is_c128 ? 16 : 8);
+  TgPeers none;
+  none.n = 0;
+  const TgPeers &pe = peers ? *peers : none;
+  if (nb == 0) {
+    TG_CUDA(cudaMemsetAsync(out, 0, out_bytes, st));
+    for (int p = 0; p < pe.n; ++p) TG_CUDA(cudaMemsetAsync(pe.ptr[p], 0, out_bytes, st));
+    if (emit) return tg_emit_block(emit, 0, st, out, 0, out_bytes);
+    return TG_OK;
+  }
+  TG_REQUIRE(poly, "null poly");
+  const int tiles_m = (nrows + BM - 1) / BM, tiles_n = (W + BIN_TN - 1) / BIN_TN;
+  const long long Tl = (long long)tiles_m * tiles_n;
+  if (tiles_m > 32767 || tiles_n > 32767 || Tl > (1 << 20)) {
+    tg_set_error("tile-binned sum: %lld tiles are more than this path handles", Tl);
+    return TG_EUNSUPPORTED;
+  }
+  const int T = (int)Tl;
+  int dev = 0, sms = 148;
+  TG_CUDA(cudaGetDevice(&dev));
+  tg_tune_mempool(dev);
+  int rc = device_sms(&sms);
+  if (rc != TG_OK) return rc;
+  const bool capturing = tg_stream_is_capturing(st);
+
+  // ---- phase 1: table, verdicts, tile ranges, per-tile counts, prefix
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t table_bytes = al((size_t)nb * 96), tr_bytes = al((size_t)nb * sizeof(short4)),
+               wc_bytes = al((size_t)T * BIN_WARPS * sizeof(int)), bins_bytes = al((size_t)(BIN_HDR + T + 1) * sizeof(int));
+  TgAsyncBuf ws1(st);
+  TG_CUDA(ws1.alloc(table_bytes + 256 + tr_bytes + wc_bytes + bins_bytes));
+  unsigned char *w1 = ws1.as<unsigned char>();
+  double *table = reinterpret_cast<double *>(w1);
+  unsigned long long *key = reinterpret_cast<unsigned long long *>(w1 + table_bytes);
+  unsigned long long *peak = key + 1, *gref = reinterpret_cast<unsigned long long *>(w1 + table_bytes + 64);
+  short4 *tr = reinterpret_cast<short4 *>(w1 + table_bytes + 256);
+  int *wc = reinterpret_cast<int *>(w1 + table_bytes + 256 + tr_bytes);
+  int *bins = reinterpret_cast<int *>(w1 + table_bytes + 256 + tr_bytes + wc_bytes);
+  TG_CUDA(cudaMemsetAsync(key, 0, 16, st));
+  TG_CUDA(cudaMemsetAsync(gref, 0xFF, 8, st));
+  TgPrepExtra ex;
+  ex.sep_key = key;
+  ex.peak_key = peak;
+  ex.row0 = row0;
+  ex.nrows = nrows;
+  rc = tg_launch_prep(nb, poly, px2m, H, W, table, gref, st, &ex);
+  if (rc != TG_OK) return rc;
+  bin_ranges_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, table, H, W, row0, nrows, gref, cull_bits, tr);
+  bin_tiles_kernel<false><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, tr, tiles_n, T, wc, nullptr, nullptr, nullptr);
+  rc = tg_launch_check("bin_tiles_kernel");
+  if (rc != TG_OK) return rc;
+  int cap = 0;
+  if (!capturing) {
+    bin_prefix_kernel<<<1, 1024, 0, st>>>(T, wc, bins, sms, 0x7fffffff);
+    rc = tg_launch_check("bin_prefix_kernel");
+    if (rc != TG_OK) return rc;
+    int hdr[BIN_HDR];
+    unsigned long long hkey = 0;
+    TG_CUDA(cudaMemcpyAsync(hdr, bins, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaMemcpyAsync(&hkey, key, 8, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaStreamSynchronize(st));
+    if (!(flags & TG_SEP_TRUSTED) && !tg_key_is_separable(hkey)) {
+      double worst;
+      memcpy(&worst, &hkey, 8);
+      tg_set_error("beamlets are not separable on this grid (cross term %.3g x tolerance)", worst);
+      return TG_ENOTSEPARABLE;
+    }
+    cap = hdr[BIN_NEED];
+    if (BinCapKey *k = bin_cap_slot(nb, H, W, row0, nrows, cull_bits, dev, true)) k->need = cap;
+  } else {
+    const BinCapKey *k = bin_cap_slot(nb, H, W, row0, nrows, cull_bits, dev, false);
+    if (!k) {
+      tg_set_error("tile-binned sum under stream capture: run the same call once outside the capture first (the operand "
+                   "capacity of the graph is taken from it)");
+      return TG_EUNSUPPORTED;
+    }
+    const long long c = (long long)k->need + k->need / 4 + 64;
+    cap = (int)(c < kBinMaxChunks ? c : kBinMaxChunks);
+    bin_prefix_kernel<<<1, 1024, 0, st>>>(T, wc, bins, sms, cap);
+    rc = tg_launch_check("bin_prefix_kernel");
+    if (rc != TG_OK) return rc;
+  }
+  if (cap > kBinMaxChunks) {
+    tg_set_error("tile-binned sum: %d operand chunks exceed the capacity limit of %d (use the SFU kernel)", cap, kBinMaxChunks);
+    return TG_EUNSUPPORTED;
+  }
+  TG_CUDA(cudaMemsetAsync(out, 0, out_bytes, st));
+  for (int p = 0; p < pe.n; ++p) TG_CUDA(cudaMemsetAsync(pe.ptr[p], 0, out_bytes, st));
+  if (cap == 0) {      // no beamlet reaches these rows
+    if (emit) return tg_emit_block(emit, 0, st, out, 0, out_bytes);
+    return TG_OK;
+  }
+
+  // ---- phase 2: slots, operands, ragged GEMM
+  constexpr int NE = 8;
+  const long long capK = (long long)cap * CHUNK_K;                       // k-elements of the concatenated axis
+  const size_t c2t_bytes = al((size_t)cap * sizeof(int)), sel_bytes = al((size_t)cap * BIN_SLOTS * sizeof(int)),
+               op_bytes = al((size_t)BM * capK * 2), cnt_bytes = al((size_t)T * NE * sizeof(unsigned int)),
+               part_bytes = (size_t)2 * sms * (NE * 2048) * sizeof(float), acc_bytes = out_is_c128 ? 0 : npix * 16;
+  TgAsyncBuf ws2(st);
+  TG_CUDA(ws2.alloc(c2t_bytes + sel_bytes + 4 * op_bytes + cnt_bytes + part_bytes + acc_bytes));
+  unsigned char *w2 = ws2.as<unsigned char>();
+  int *c2t = reinterpret_cast<int *>(w2);
+  int *sel = reinterpret_cast<int *>(w2 + c2t_bytes);
+  unsigned char *Ahi = w2 + c2t_bytes + sel_bytes, *Alo = Ahi + op_bytes, *Bhi = Alo + op_bytes, *Blo = Bhi + op_bytes;
+  unsigned int *counters = reinterpret_cast<unsigned int *>(Blo + op_bytes);
+  float *parts = reinterpret_cast<float *>(Blo + op_bytes + cnt_bytes);
+  double *acc = out_is_c128 ? static_cast<double *>(out) : reinterpret_cast<double *>(Blo + op_bytes + cnt_bytes + part_bytes);
+  TG_CUDA(cudaMemsetAsync(counters, 0, cnt_bytes, st));
+  if (!out_is_c128) TG_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
+  const unsigned long long *guard = capturing ? key : nullptr;          // under capture the verdict stays on the device
+  bin_tiles_kernel<true><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, tr, tiles_n, T, wc, bins, sel, c2t);
+  const unsigned gf = bounded_grid((long long)cap * (BM / FS));
+  factor_rows_binned_kernel<true><<<gf, BIN_SLOTS, 0, st>>>(table, bins, sel, c2t, tiles_n, row0, nrows, W, capK, Ahi, Alo,
+                                                            peak, guard);
+  factor_cols_binned_kernel<true><<<gf, BIN_SLOTS, 0, st>>>(table, bins, sel, c2t, tiles_n, W, capK, Bhi, Blo, guard);
+  rc = tg_launch_check("binned factor kernels");
+  if (rc != TG_OK) return rc;
+  CUtensorMap ta, tb, tc, td;
+  if ((rc = make_map<true>(&ta, Ahi, BM, capK, capK)) != TG_OK) return rc;
+  if ((rc = make_map<true>(&tb, Alo, BM, capK, capK)) != TG_OK) return rc;
+  if ((rc = make_map<true>(&tc, Bhi, BN, capK, capK)) != TG_OK) return rc;
+  if ((rc = make_map<true>(&td, Blo, BN, capK, capK)) != TG_OK) return rc;
+  SkSched sc = make_sched(nrows, 2 * W, CHUNK_K, GemmCfg<true>::BK, GemmCfg<true>::CHUNK_KB, sms, 0);
+  sc.T = T;
+  sc.tiles_n = tiles_n;
+  sc.nkb = (int)((long long)cap * GemmCfg<true>::CHUNK_KB);
+  sc.G = sms;
+  sc.bins = bins;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
+  TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TgPeers gp = out_is_c128 ? pe : none;                                 // complex64 peers are written by the conversion
+  gemm_x3_kernel<true, false, true><<<(unsigned)sms, GEMM_THREADS, smem, st>>>(
+      ta, tb, tc, td, nrows, 2 * W, (int)(capK < 0x7fffffffLL ? capK : 0x7fffffffLL), acc, (long long)(2 * W), 1, peak,
+      Headroom<true>::value, guard, gp, sc, parts, counters, nullptr, nullptr, 0u);
+  rc = tg_launch_check("gemm_x3_kernel<f16> (tile-binned)");
+  if (rc != TG_OK) return rc;
+  if (!out_is_c128) {
+    const size_t n = npix * 2;
+    f64_to_c64_kernel<<<bounded_grid((long long)((n + 255) / 256)), 256, 0, st>>>(acc, static_cast<float *>(out), n, guard, pe);
+    rc = tg_launch_check("f64_to_c64_kernel");
+    if (rc != TG_OK) return rc;
+  }
+  if (capturing) {
+    const size_t n = npix * (out_is_c128 ? 2 : 1);
+    nan_fill_binned_kernel<<<bounded_grid((long long)((n + 255) / 256)), 256, 0, st>>>(static_cast<double *>(out), n, bins, key);
+    rc = tg_launch_check("nan_fill_binned_kernel");
+    if (rc != TG_OK) return rc;
+  }
+  if (emit) return tg_emit_block(emit, 0, st, out, 0, out_bytes);
+  return TG_OK;
+}
+
 // The verdict TG_METHOD_AUTO reaches on the device, read back to the host (synchronises `stream`): 1 = the tensor-core
 // path applies (separable, and not clearly more expensive than the culled SFU sum), 0 = SFU kernel.  Plans use it to
 // freeze the dispatch at build time, so that the captured graph holds the launches of ONE path only.
@@ -2052,16 +2585,17 @@ extern "C" int tg_field_sum_verdict(int64_t nb, const double *poly, const double
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TG_REQUIRE(!tg_stream_is_capturing(st), "the verdict is read back on the host: not inside a stream capture");
   TgAsyncBuf keyb(st);
-  TG_CUDA(keyb.alloc(16));
+  TG_CUDA(keyb.alloc(24));
   unsigned long long *key = keyb.as<unsigned long long>();
   // (the output pointer is only range-checked in verdict-only mode)
-  int rc = tg_separable_run(nb, poly, px2m, H, W, 0, H, key + 1, 1, key, st, cull_bits, 1, nullptr, nullptr,
-                            TG_SEP_VERDICT_ONLY);
+  int rc = tg_separable_run(nb, poly, px2m, H, W, 0, H, key + 2, 1, key, st, cull_bits, 1, nullptr, nullptr,
+                            TG_SEP_VERDICT_ONLY | TG_SEP_VERDICT_SPLIT);
   if (rc != TG_OK) return rc;
-  unsigned long long hkey = 0;
-  TG_CUDA(cudaMemcpyAsync(&hkey, key, 8, cudaMemcpyDeviceToHost, st));
+  unsigned long long hkey[2] = {0, 0};
+  TG_CUDA(cudaMemcpyAsync(hkey, key, 16, cudaMemcpyDeviceToHost, st));
   TG_CUDA(cudaStreamSynchronize(st));
-  *use_tensor = tg_key_is_separable(hkey) ? 1 : 0;
+  // 1 = dense GEMM, 2 = separable and sparse: tile-binned GEMM, 0 = SFU kernel
+  *use_tensor = !tg_key_is_separable(hkey[0]) ? 0 : hkey[1] == 0 ? 1 : (cull_bits > 0 && binned_enabled()) ? 2 : 0;
   return TG_OK;
 }
 
@@ -2082,12 +2616,14 @@ int tg_field_sum_impl(int64_t nb, const double *poly, const double px2m[6], int 
     return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr, st, 0,
                             method == TG_METHOD_TENSOR ? 1 : method == TG_METHOD_TENSOR_4M ? 2
                             : method == TG_METHOD_TENSOR_3M ? 3 : 0, peers, emit);
+  if (method == TG_METHOD_TENSOR_BINNED)
+    return tg_separable_binned_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, st, peers, emit);
   TG_REQUIRE(method == TG_METHOD_AUTO, "unknown method");
   if (nb == 0 || nrows == 0)
     return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st,
                              peers, emit);
   TgAsyncBuf keyb(st);
-  TG_CUDA(keyb.alloc(8));
+  TG_CUDA(keyb.alloc(16));
   unsigned long long *key = keyb.as<unsigned long long>();
   // Large problems outside a graph capture: every kernel of the path that does not apply still has to be launched
   // and exit (7 batches x {two factor grids of ~10^4 CTAs, GEMM} at C3: ~0.3 ms of dead launches, measured as the
@@ -2097,14 +2633,21 @@ int tg_field_sum_impl(int64_t nb, const double *poly, const double px2m[6], int 
     // (host-buffer pipeline: the call is synchronous anyway; only the path that applies is enqueued -- block by
     // block, each block's D2H behind its own event)
     int rc = tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, key, st, cull_bits, 1, nullptr,
-                              nullptr, TG_SEP_VERDICT_ONLY);
+                              nullptr, TG_SEP_VERDICT_ONLY | TG_SEP_VERDICT_SPLIT);
     if (rc != TG_OK) return rc;
-    unsigned long long hkey = 0;
-    TG_CUDA(cudaMemcpyAsync(&hkey, key, 8, cudaMemcpyDeviceToHost, st));
+    unsigned long long hkey[2] = {0, 0};
+    TG_CUDA(cudaMemcpyAsync(hkey, key, 16, cudaMemcpyDeviceToHost, st));
     TG_CUDA(cudaStreamSynchronize(st));
-    if (tg_key_is_separable(hkey))
+    if (tg_key_is_separable(hkey[0]) && hkey[1] == 0)
       return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr, st, 0, 1, peers, emit,
                               TG_SEP_TRUSTED);
+    if (tg_key_is_separable(hkey[0]) && cull_bits > 0 && binned_enabled()) {
+      // separable AND sparse (every beamlet reaches a small part of the detector): the tile-binned tensor-core sum;
+      // the SFU kernel remains the fallback when the operands of the (beamlet, tile) pairs would not fit
+      rc = tg_separable_binned_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, st, peers, emit,
+                                   TG_SEP_TRUSTED);
+      if (rc != TG_EUNSUPPORTED) return rc;
+    }
     return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st,
                              peers, emit);
   }

@@ -50,6 +50,7 @@ struct TgEmit {
 };
 #define TG_SEP_VERDICT_ONLY 1 /* tg_separable_run: table + separability / cost verdict into *key_async, nothing else */
 #define TG_SEP_TRUSTED 2      /* tg_separable_run: the caller has read the verdict; skip the host-side check */
+#define TG_SEP_VERDICT_SPLIT 4 /* verdict-only: key_async[0] = separability, key_async[1] = 1 when the beamlets are sparse */
 
 // stream-ordered scratch allocation, released (stream-ordered) when the scope ends -- also on error returns
 struct TgAsyncBuf {
@@ -100,6 +101,13 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
                      int nrows, void *out, int out_is_c128, unsigned long long *key_async,
                      cudaStream_t stream, int cost_cull_bits, int f16, const TgPeers *peers = nullptr,
                      const TgEmit *emit = nullptr, int flags = 0);
+// Tile-binned (block-sparse K) tensor-core sum for separable beamlets that each reach a small part of the detector
+// (cull_bits > 0).  TG_EUNSUPPORTED when the operands would not fit (use the SFU kernel), TG_ENOTSEPARABLE like
+// tg_separable_run.  Under stream capture the operand capacity comes from the last eager call of this host thread with
+// the same shape (plans warm up eagerly), and beamlets that need more poison the output with NaN.
+int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0, int nrows,
+                            void *out, int out_is_c128, int cull_bits, cudaStream_t stream,
+                            const TgPeers *peers = nullptr, const TgEmit *emit = nullptr, int flags = 0);
 int tg_field_sum_impl(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0, int nrows,
                       void *out, int out_is_c128, int cull_bits, int method, cudaStream_t st, const TgPeers *peers,
                       const TgEmit *emit = nullptr);

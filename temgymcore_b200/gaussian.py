@@ -492,7 +492,8 @@ def make_gaussian_image_device(gaussian_rays, model, *, cull_bits=None, out_dtyp
 
 
 def auto_dispatch(gaussian_rays, model, cull_bits=None) -> str:
-    """What ``method="auto"`` decides for these beamlets on ``model[-1]``: ``"tensor"`` or ``"sfu"``
+    """What ``method="auto"`` decides for these beamlets on ``model[-1]``: ``"tensor"`` (dense GEMM), ``"tensor_binned"``
+    (separable and sparse: tile-binned GEMM) or ``"sfu"``
     (``tg_field_sum_verdict``: the device-side separability + cost verdict, read back once; synchronises)."""
     lib = L.load()
     grid = model[-1]
@@ -504,7 +505,7 @@ def auto_dispatch(gaussian_rays, model, cull_bits=None) -> str:
         L.check(lib.tg_field_sum_verdict(nb, poly.data_ptr() if nb else None, L.dbl_array(grid.px2m_affine),
                                          int(grid.shape[0]), int(grid.shape[1]), cull, C.byref(use),
                                          A.current_stream_ptr(dev)), "tg_field_sum_verdict")
-    return "tensor" if use.value else "sfu"
+    return {0: "sfu", 1: "tensor", 2: "tensor_binned"}[use.value]
 
 
 class GaussianImagePlan:

@@ -167,3 +167,65 @@ def test_row_block_streaming_rounds(M, N, K, rtm):
         assert sorted(sl) == list(range(s["maxparts"]))
     if M == 1024 and N == 1024 and rtm == 2:
         assert s["maxparts"] == 9 and s["G"] == 144         # 4 rounds of 16 complex tiles x 9 k-ranges
+
+
+# ---- ragged schedule of the tile-binned sum (TG_METHOD_TENSOR_BINNED): tiles own different numbers of chunks --------
+def ragged(chunks, sms=148):
+    lib = L.load()
+    ch = np.ascontiguousarray(chunks, dtype=np.int32)
+    n = lib.tg_gemm_schedule_ragged(len(ch), ch.ctypes.data, sms, None, 0, None, 0)
+    assert n >= 0
+    units = np.zeros((max(n, 1), 8), dtype=np.int32)
+    readers = np.full(max(n, 1) * (sms + 1), -1, dtype=np.int32)
+    n2 = lib.tg_gemm_schedule_ragged(len(ch), ch.ctypes.data, sms, units.ctypes.data, n, readers.ctypes.data,
+                                     len(readers))
+    assert n2 == n
+    return units[:n], readers
+
+
+RAGGED_CASES = [
+    ("c3_like", lambda r: r.integers(8, 20, size=512)),
+    ("mostly_empty", lambda r: np.where(r.random(512) < 0.9, 0, r.integers(1, 40, size=512))),
+    ("one_huge_tile", lambda r: np.array([0, 0, 5000, 0, 3, 0])),
+    ("fewer_chunks_than_ctas", lambda r: np.array([1, 0, 2, 0, 0, 1, 3])),
+    ("single_chunk", lambda r: np.array([0, 1, 0])),
+    ("uniform", lambda r: np.full(148, 7)),
+    ("ramp", lambda r: np.arange(300) % 17),
+]
+
+
+@pytest.mark.parametrize("sms", [148, 132, 7])
+@pytest.mark.parametrize("name,gen", RAGGED_CASES)
+def test_ragged_schedule_covers_every_chunk_once(name, gen, sms):
+    chunks = np.asarray(gen(np.random.default_rng(7)), dtype=np.int64)
+    P = np.concatenate([[0], np.cumsum(chunks)])
+    tot = int(P[-1])
+    units, readers = ragged(chunks, sms)
+    cover = np.zeros(tot, dtype=np.int32)
+    load = np.zeros(sms, dtype=np.int64)
+    by_tile, written = {}, {}
+    ri = 0
+    for cta, tile, c0, c1, slot, nparts, wslot, first in units:
+        assert 0 <= cta < sms and P[tile] <= c0 < c1 <= P[tile + 1], (cta, tile, c0, c1)
+        cover[c0:c1] += 1
+        load[cta] += c1 - c0
+        assert 0 <= slot < nparts and cta == first + slot
+        by_tile.setdefault(tile, []).append((slot, nparts))
+        if nparts > 1:
+            assert wslot in (2 * cta, 2 * cta + 1)
+            assert wslot not in written, "two partial units of one launch share a scratch slot"
+            written[wslot] = (tile, slot)
+        rd = readers[ri:ri + nparts]
+        ri += nparts
+        by_tile[tile][-1] += (tuple(rd),)
+    assert (cover == 1).all()
+    q = max(1, -(-tot // sms))
+    assert load.max() <= q                                   # even split of the chunk axis
+    for tile, parts in by_tile.items():
+        nparts = parts[0][1]
+        assert sorted(p[0] for p in parts) == list(range(nparts))          # the arrival counter reaches nparts
+        if nparts > 1:
+            for slot, _, rd in parts:
+                # whoever arrives last reads, part by part, exactly the slots the parts were parked in
+                assert [written[r] for r in rd] == [(tile, s) for s in range(nparts)]
+    assert set(np.nonzero(chunks)[0]) == set(by_tile)        # empty tiles get no unit

@@ -517,7 +517,7 @@ def test_c3_full_size_vs_oracle(torch_cuda, variant):
     runs = [("sfu_culled", dict(method="sfu"))]
     if not general:
         runs += [("tensor", dict(method="tensor", cull_bits=0)), ("auto_dense", dict(method="auto", cull_bits=0)),
-                 ("tensor_3m", dict(method="tensor_3m", cull_bits=0))]
+                 ("tensor_3m", dict(method="tensor_3m", cull_bits=0)), ("tensor_binned", dict(method="tensor_binned"))]
     for name, kw in runs:
         img = to_np(make_gaussian_image_device(gd, model, **kw))
         errs[name] = rel_l2(img.reshape(-1)[pix], ref)
@@ -1324,6 +1324,114 @@ def test_auto_dispatch_is_cost_aware(torch_cuda):
     auto = _field_sum_grid(poly, n, model[-1], dev, method="auto")
     tens = _field_sum_grid(poly, n, model[-1], dev, method="tensor")
     assert torch_cuda.equal(auto, tens)
+
+
+# ------------------------------------------------------------------------------ tile-binned tensor-core sum
+@pytest.mark.parametrize("nb,shape,fov", [(600, (256, 256), None), (1, (320, 416), 3 * 1024 * 55e-6 / 2),
+                                          (127, (320, 416), 3 * 1024 * 55e-6 / 2),
+                                          (129, (320, 416), 3 * 1024 * 55e-6 / 2),
+                                          (1000, (320, 416), 3 * 1024 * 55e-6 / 2),
+                                          (3000, (200, 136), None), (4000, (1024, 1024), None)])
+def test_tensor_binned_parity(torch_cuda, nb, shape, fov):
+    """TG_METHOD_TENSOR_BINNED (separable beamlets, each tile multiplies only the beamlets whose bounding box meets
+    it): against the oracle where it finishes in seconds, against the dense sums of both kernels everywhere, on ragged
+    shapes, beamlet counts around the chunk size (128), a row shard that is not tile-aligned, complex64, and
+    bit-identical from run to run (slots are filled in beamlet order)."""
+    from temgymcore_b200.gaussian import _field_sum_grid, beamlet_polynomials
+    kw = {} if fov is None else dict(fov=fov)
+    g, model = M.biprism_case(nb, shape, **kw)
+    grid = model[-1]
+    poly, n, dev = beamlet_polynomials(g, model)
+    dense = to_np(_field_sum_grid(poly, n, grid, dev, cull_bits=0, method="sfu"))
+    binned_t = _field_sum_grid(poly, n, grid, dev, cull_bits=40, method="tensor_binned")
+    binned = to_np(binned_t)
+    assert binned.shape == tuple(shape) and binned.dtype == np.complex128
+    assert rel_l2(binned, dense) < 3e-6, rel_l2(binned, dense)
+    if nb * shape[0] * shape[1] <= 600 * 256 * 256:
+        assert rel_l2(binned, O.make_gaussian_image(g, model)) < FIELD_TOL
+    again = _field_sum_grid(poly, n, grid, dev, cull_bits=40, method="tensor_binned")
+    assert torch_cuda.equal(again, binned_t)
+    H = shape[0]
+    r0, nr = (96, 130) if H >= 226 else (40, 100)
+    rows = to_np(_field_sum_grid(poly, n, grid, dev, cull_bits=40, method="tensor_binned", row0=r0, nrows=nr))
+    assert rel_l2(rows, dense[r0:r0 + nr]) < 3e-6
+    c64 = to_np(_field_sum_grid(poly, n, grid, dev, cull_bits=40, method="tensor_binned",
+                                out_dtype=torch_cuda.complex64))
+    assert c64.dtype == np.complex64 and rel_l2(c64, dense) < 1e-6 + 3e-6
+    # a narrower threshold drops more of every beamlet's tail but stays within the culling error
+    b20 = to_np(_field_sum_grid(poly, n, grid, dev, cull_bits=24, method="tensor_binned"))
+    assert rel_l2(b20, dense) < 1e-5
+
+
+def test_tensor_binned_edge_cases(torch_cuda):
+    from temgymcore_b200 import _lib as L
+    from temgymcore_b200.components import Detector
+    from temgymcore_b200.gaussian import _field_sum_grid, beamlet_polynomials, make_gaussian_image
+    g, model = M.biprism_case(500, (320, 416), fov=3 * 1024 * 55e-6 / 2)
+    det = model[-1]
+    poly, n, dev = beamlet_polynomials(g, model)
+    # a detector far off to the side: no bounding box meets any tile -> zeros (to the culling error)
+    far = Detector(z=det.z, pixel_size=det.pixel_size, shape=det.shape, centre=(10 * 320 * det.pixel_size[0], 0.0))
+    model_far = list(model[:-1]) + [far]
+    poly_f, n_f, _ = beamlet_polynomials(g, model_far)
+    dense = _field_sum_grid(poly, n, det, dev, cull_bits=0, method="sfu")
+    out_f = _field_sum_grid(poly_f, n_f, far, dev, cull_bits=40, method="tensor_binned")
+    assert float(out_f.abs().max()) <= 1e-9 * float(dense.abs().max())
+    # no beamlets at all
+    empty = _field_sum_grid(poly[:0], 0, det, dev, cull_bits=40, method="tensor_binned")
+    assert float(empty.abs().max()) == 0.0
+    # needs a threshold; rejects beamlets with a cross term
+    with pytest.raises(L.TemGymError):
+        _field_sum_grid(poly, n, det, dev, cull_bits=0, method="tensor_binned")
+    gg, model_g = field_cases()["c3_biprism_general"]
+    with pytest.raises(L.TemGymError):
+        make_gaussian_image(gg, model_g, method="tensor_binned")
+    # beamlets that cover the whole detector (C2 geometry): every tile lists every beamlet -- still the same sum
+    g2, model2 = M.aperture_diffraction_case(300, (256, 192))
+    poly2, n2, _ = beamlet_polynomials(g2, model2)
+    d2 = to_np(_field_sum_grid(poly2, n2, model2[-1], dev, cull_bits=0, method="sfu"))
+    b2 = to_np(_field_sum_grid(poly2, n2, model2[-1], dev, cull_bits=40, method="tensor_binned"))
+    assert rel_l2(b2, d2) < 3e-6
+    # a NaN beamlet poisons the image as in the dense sums
+    gn, model_n = M.biprism_case(200, (256, 256))
+    xn = np.array(gn.x, dtype=np.float64)
+    xn[7] = np.nan
+    from dataclasses import replace
+    bad = to_np(make_gaussian_image(replace(gn, x=xn), model_n, method="tensor_binned"))
+    assert np.isnan(bad).any()
+
+
+def test_tensor_binned_auto_and_plan(torch_cuda, monkeypatch):
+    """`auto` hands separable AND sparse beamlets (more than one GEMM batch of them) to the tile-binned sum; plans
+    resolve that at build time and capture it with the operand capacity of their eager warm-up; beamlets that need
+    more than the captured capacity poison the image instead of returning a partial sum."""
+    from dataclasses import replace
+    from temgymcore_b200.gaussian import (GaussianImagePlan, auto_dispatch, make_gaussian_image_device)
+    g, model = M.biprism_case(20_000, (1024, 1024), fov=2 * 1024 * 55e-6 / 2)
+    gd = gaussian_to_cuda(torch_cuda, g)
+    assert auto_dispatch(gd, model) == "tensor_binned"
+    auto = make_gaussian_image_device(gd, model)
+    binned = make_gaussian_image_device(gd, model, method="tensor_binned")
+    sfu = make_gaussian_image_device(gd, model, method="sfu")
+    assert torch_cuda.equal(auto, binned)
+    assert rel_l2(to_np(binned), to_np(sfu)) < 3e-6
+    monkeypatch.setenv("TG_TENSOR_BINNED", "0")
+    assert auto_dispatch(gd, model) == "sfu"
+    assert torch_cuda.equal(make_gaussian_image_device(gd, model), sfu)
+    monkeypatch.delenv("TG_TENSOR_BINNED")
+    plan = GaussianImagePlan(gd, model)
+    assert plan.method == "tensor_binned"
+    for _ in range(2):
+        assert torch_cuda.equal(plan.run(), binned)
+    g2 = replace(g, x=np.asarray(g.x) * 0.9, amplitude=np.asarray(g.amplitude) * 2.0)
+    out2 = to_np(plan.update(g2).run()).copy()
+    ref2 = to_np(make_gaussian_image_device(gaussian_to_cuda(torch_cuda, g2), model, method="sfu"))
+    assert rel_l2(out2, ref2) < 3e-6
+    # ten times wider beamlets: far more (beamlet, tile) pairs than the graph has operand room for
+    wide = replace(g, waist_xy=np.asarray(g.waist_xy) * 0.1)
+    out3 = to_np(plan.update(wide).run())
+    ok = to_np(make_gaussian_image_device(gaussian_to_cuda(torch_cuda, wide), model, method="sfu"))
+    assert np.isnan(out3).all() or rel_l2(out3, ok) < 3e-6
 
 
 # ------------------------------------------------------------------------------ peer-memory field sum
