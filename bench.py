@@ -383,7 +383,9 @@ def run_ours(args):
                  ("c2_sfu_general_kernel", g_sh, model, dict(cull_bits=0, method="sfu"), C2_NB * H * W)]
         if not args.skip_c3:
             g3s, m3s = M.biprism_case(100_000, (2048, 2048))
-            cases.append(("c3_auto", to_dev(g3s), m3s, dict(method="auto"), 100_000 * 2048 * 2048))
+            g3sd = to_dev(g3s)
+            cases.append(("c3_auto", g3sd, m3s, dict(method="auto"), 100_000 * 2048 * 2048))
+            cases.append(("c3_sfu_culled", g3sd, m3s, dict(method="sfu"), 100_000 * 2048 * 2048))
             g3g, m3g = M.biprism_case(100_000, (2048, 2048), general=True, rng=np.random.default_rng(M.SEED))
             cases.append(("c3_general_variant", to_dev(g3g), m3g, dict(method="auto"), 100_000 * 2048 * 2048))
         for label, gg, mm, kw, nominal in cases:
@@ -400,9 +402,10 @@ def run_ours(args):
                     ms = max_over_ranks(float(np.median(tt)))
                     err = max_over_ranks(max(err, rel_l2(pplan.run(), single)))
                     st = pimg.status()
+                    plan_method = pplan.method
                     del pplan
                 entry = {"ms_per_image": ms, "nominal_evals_per_s": nominal / (ms * 1e-3),
-                         "rel_l2_vs_single_gpu": err, "barrier_timeouts": st[1],
+                         "rel_l2_vs_single_gpu": err, "barrier_timeouts": st[1], "method": plan_method,
                          "ms_single_gpu_direct_call_same_rank": t1, "scaling": "strong"}
                 del single
             except Exception as exc:   # e.g. CUDA IPC not permitted in this container
@@ -676,11 +679,23 @@ def run_ours(args):
 
         def c3_auto():
             keep3["a"] = make_gaussian_image_device(g3d, model3)                   # the API's defaults
+
+        def c3_binned():
+            keep3["b"] = make_gaussian_image_device(g3d, model3, method="tensor_binned")   # default culling (40 bits)
         # median of 5 after 2 warm-ups: the first calls grow the stream-ordered pool by the operand workspace
         t3 = max_over_ranks(float(np.median(timed(c3_tensor, 5, 2, flush=False))))
         s3 = max_over_ranks(float(np.median(timed(c3_sfu, 5, 2, flush=False))))
+        b3 = max_over_ranks(float(np.median(timed(c3_binned, 5, 2, flush=False))))
+        chunks3 = int(L.load().tg_binned_last_chunks())
         a3 = max_over_ranks(float(np.median(timed(c3_auto, 5, 2, flush=False))))
         diff = rel_l2(keep3["s"], keep3["t"])
+        diff_b = rel_l2(keep3["b"], keep3["t"])
+        # the same image as a graph plan (auto resolved at build time; no host read-back of the operand count)
+        plan3 = GaussianImagePlan(g3d, model3)
+        p3 = max_over_ranks(float(np.median(timed(plan3.run, 10, 3, flush=False))))
+        plan3_method = plan3.method
+        diff_p = rel_l2(plan3.run(), keep3["t"])
+        del plan3
         ev3 = 100_000 * 2048 * 2048
         # executed evaluations of the culled kernel (roofline on EXECUTED evaluations, both
         # executed and nominal throughput reported) and a dense timing on a row subset for comparison
@@ -705,11 +720,28 @@ def run_ours(args):
                                                                  "split reduce)"}},
               "sfu_path_dense_row_subset": {"rows": dense_rows, "ms": d3,
                                             "evals_per_s": nb3 * dense_rows * 2048 / (d3 * 1e-3)},
+              # tile-binned tensor-core sum: every 128 x 64 tile multiplies only the beamlets whose footprint meets it.
+              # Its kernels stream operands that are used once: HBM-bound, bytes = chunks x 256 KiB written by the
+              # factor kernels and read back by the GEMM
+              "tensor_binned_path": {"ms_per_image": b3, "nominal_evals_per_s": ev3 * world / (b3 * 1e-3),
+                                     "cull_bits": 40, "operand_chunks": chunks3,
+                                     "beamlet_tile_pairs_padded": chunks3 * 128,
+                                     "operand_bytes": chunks3 * 262144,
+                                     "plan_ms_per_image": p3, "plan_method": plan3_method,
+                                     "roofline_hbm": {"bound": "hbm", "achieved": 2 * chunks3 * 262144 / (p3 * 1e-3) / 1e9,
+                                                      "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                                      "frac": 2 * chunks3 * 262144 / (p3 * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                                      "basis": "operand bytes written once and read once / the whole "
+                                                               "graph-replayed image (ray kernel, coefficients, binning, "
+                                                               "factor kernels, GEMM)"},
+                                     "rel_l2_vs_dense_tensor": diff_b, "plan_rel_l2_vs_dense_tensor": diff_p},
               "auto_default": {"ms_per_image": a3, "nominal_evals_per_s": ev3 * world / (a3 * 1e-3),
-                               "note": "method=auto, cull_bits=40: the device-side cost model compares the dense fp16 "
-                                       "GEMM with the culled SFU sum and runs the cheaper one ("
-                                       + ("culled SFU kernel" if abs(a3 - s3) <= abs(a3 - t3) else "tensor cores")
-                                       + " here, judged by which timing it matches)"},
+                               "note": "method=auto, cull_bits=40: separable AND sparse beamlets (device-side verdicts, "
+                                       "read back once for calls of more than 16384 beamlets) go to the tile-binned "
+                                       "tensor-core sum; runs the "
+                                       + min((("culled SFU kernel", s3), ("dense GEMM", t3), ("tile-binned GEMM", b3)),
+                                             key=lambda kv: abs(a3 - kv[1]))[0]
+                                       + " here, judged by which timing it matches"},
               "rel_l2_tensor_vs_culled_sfu": diff, "scaling": "weak"}
         del keep3, g3d, poly3
         torch.cuda.empty_cache()
@@ -779,6 +811,10 @@ def run_ours(args):
         }
         if c3:
             also["c3"] = {"tensor_ms": c3["tensor_path"]["ms_per_image"], "sfu_culled_ms": c3["sfu_path_culled"]["ms_per_image"],
+                          "tensor_binned_ms": c3["tensor_binned_path"]["ms_per_image"],
+                          "tensor_binned_plan_ms": c3["tensor_binned_path"]["plan_ms_per_image"],
+                          "tensor_binned_hbm_frac": c3["tensor_binned_path"]["roofline_hbm"]["frac"],
+                          "rel_l2_binned_vs_dense_tensor": c3["tensor_binned_path"]["rel_l2_vs_dense_tensor"],
                           "auto_ms": c3["auto_default"]["ms_per_image"], "general_variant_ms": c3["general_variant"]["ms_per_image"],
                           "executed_fraction": c3["sfu_path_culled"]["executed_fraction"],
                           "executed_evals_per_s": c3["sfu_path_culled"]["executed_evals_per_s"],

@@ -359,6 +359,9 @@ int tg_gemm_schedule(int M, int N, int K, int f16, int sms, int mode, int32_t *u
  * of units. */
 int tg_gemm_schedule_ragged(int T, const int32_t *chunks_per_tile, int sms, int32_t *units, int max_units,
                             int32_t *readers, int max_readers);
+/* Operand chunks (128 beamlet slots, 256 KiB of fp16 hi / lo row and column factors each) that the calling thread's
+ * last eager TG_METHOD_TENSOR_BINNED sum built; -1 if there was none.  (Measurement aid: bench.py's HBM roofline.) */
+int tg_binned_last_chunks(void);
 
 /* ---- host-buffer field sum (make_gaussian_image end to end, gaussian.py:225-273) -- */
 /* All pointers HOST.  rays[7] are the central rays (length nb each), waist_xy /

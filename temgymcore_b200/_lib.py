@@ -105,6 +105,7 @@ SIGNATURES = {
     "tg_cgemm3_f16x3": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong, _i32, _vp]),
     "tg_gemm_schedule": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "tg_gemm_schedule_ragged": (_i32, [_i32, _vp, _i32, _vp, _i32, _vp, _i32]),
+    "tg_binned_last_chunks": (_i32, []),
     "tg_peer_alloc": (_i32, [C.c_uint64, C.POINTER(_vp), _vp]),
     "tg_peer_open": (_i32, [_vp, C.POINTER(_vp)]),
     "tg_peer_close": (_i32, [_vp]),

@@ -1242,7 +1242,7 @@ __global__ void __launch_bounds__(256)
 // of its tensor work on (beamlet, pixel) pairs below the culling threshold, and the culled SFU kernel evaluates the
 // remaining 1-3 % pixel by pixel.  Here the sum stays on the tensor cores but every output tile only multiplies the
 // beamlets whose bounding box {envelope >= brightest on-detector peak - cull_bits} meets it:
-//   * bin_ranges_kernel: per beamlet, the range of 128-row x 64-complex-column tiles its box touches;
+//   * bin_ranges_kernel: per beamlet, the elliptical footprint {envelope >= threshold} in detector pixels;
 //   * bin_tiles_kernel<false>: per tile (one CTA; each of its 8 warps scans a contiguous eighth of the beamlets) the
 //     number of beamlets that reach it; bin_prefix_kernel: chunks of 128 beamlets per tile -> P[0..T] (exclusive scan),
 //     the chunks per CTA of the ragged GEMM schedule, the overflow verdict against the operand capacity;
@@ -1258,16 +1258,16 @@ constexpr int BIN_SLOTS = CHUNK_K / 2;   // beamlets per accumulation chunk (4-m
 constexpr int BIN_TN = BN / 2;           // complex columns per tile
 constexpr int BIN_WARPS = 8;
 
-// tr[i] = (first tile column, last tile column, first tile row, last tile row) of beamlet i inside rows
-// [row0, row0 + nrows); (1, 0, 1, 0) when it reaches nothing.  Same box as field.cu's bbox_kernel (+-1 px slack;
-// non-concave or non-finite envelopes get everything, so NaN beamlets poison the image as in the dense sum).
+// fp[i] = (centre column, centre row, half-width, half-height) in detector pixels of the axis-aligned ellipse
+// {envelope of beamlet i >= threshold} (+1 px slack on both half-axes; separable beamlets have no cross term to speak
+// of); half-width < 0: the beamlet reaches nothing; non-concave or non-finite envelopes get a footprint that covers
+// everything, so NaN beamlets poison the image as in the dense sum.  Same threshold as field.cu's bbox_kernel.
 __global__ void __launch_bounds__(256)
-    bin_ranges_kernel(long long nb, const double *__restrict__ table, int H, int W, int row0, int nrows,
-                      const unsigned long long *__restrict__ gref_key, int cull_bits, short4 *__restrict__ tr) {
+    bin_ranges_kernel(long long nb, const double *__restrict__ table, int H, int W,
+                      const unsigned long long *__restrict__ gref_key, int cull_bits, float4 *__restrict__ fp) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nb) return;
-  double c_lo = 0.0, c_hi = (double)(W - 1), r_lo = (double)row0, r_hi = (double)(row0 + nrows - 1);
-  bool empty = false;
+  float4 o = make_float4(0.f, 0.f, 1e30f, 1e30f);
   const unsigned long long k = *gref_key;
   const double *e = table + i * 12 + 6;   // E(c, r) = e0 + e1 c + e2 r + e3 c^2 + e4 c r + e5 r^2 [bits]
   const double det = e[3] * e[5] - 0.25 * e[4] * e[4];
@@ -1277,35 +1277,40 @@ __global__ void __launch_bounds__(256)
     const double rs = (0.5 * e[4] * e[1] - e[3] * e[2]) / (2.0 * det);
     const double d = (e[0] + 0.5 * (e[1] * cs + e[2] * rs)) - e_thr;
     if (d < 0.0) {
-      empty = true;
+      o.z = o.w = -1.f;
     } else if (isfinite(d) && isfinite(cs) && isfinite(rs)) {
       const double hc = sqrt(d * (-e[5]) / det) + 1.0, hr = sqrt(d * (-e[3]) / det) + 1.0;
-      c_lo = fmax(c_lo, floor(cs - hc));
-      c_hi = fmin(c_hi, ceil(cs + hc));
-      r_lo = fmax(r_lo, floor(rs - hr));
-      r_hi = fmin(r_hi, ceil(rs + hr));
-      empty = c_hi < c_lo || r_hi < r_lo;
+      // (fp32 footprints: the centre rounds by < 2^-24 of its magnitude -- widen the half-axes by that much)
+      const double slack = (fabs(cs) + fabs(rs)) * 1.2e-7;
+      o = make_float4((float)cs, (float)rs, (float)fmin(hc + slack, 1e30), (float)fmin(hr + slack, 1e30));
     }
   }
-  short4 o = make_short4(1, 0, 1, 0);
-  if (!empty)
-    o = make_short4((short)((int)c_lo / BIN_TN), (short)((int)c_hi / BIN_TN), (short)(((int)r_lo - row0) / BM),
-                    (short)(((int)r_hi - row0) / BM));
-  tr[i] = o;
+  fp[i] = o;
 }
 
-// One CTA per tile, warp w scans beamlets [w seg, (w + 1) seg).  FILL = false: wc[t][w] = hits of warp w.
-// FILL = true: append the hits in order behind the hits of the warps before, pad the tile's last chunk, fill c2t.
+// does the footprint meet the pixel rectangle [c0, c1] x [r0, r1]?  (closest point of the rectangle to the centre)
+__device__ __forceinline__ bool bin_hit(const float4 f, float c0, float c1, float r0, float r1) {
+  const float dx = fmaxf(fmaxf(c0 - f.x, f.x - c1), 0.f), dy = fmaxf(fmaxf(r0 - f.y, f.y - r1), 0.f);
+  const float a = dx * f.w, b = dy * f.z, c = f.z * f.w;
+  return f.z >= 0.f && a * a + b * b <= c * c * 1.000001f;
+}
+
+// One CTA per tile, warp w scans beamlets [w seg, (w + 1) seg), 8 footprints per lane in flight.  FILL = false:
+// wc[t][w] = hits of warp w.  FILL = true: append the hits in beamlet order behind the hits of the warps before, pad
+// the tile's last chunk, fill c2t.
+constexpr int BIN_ILP = 8;
 template <bool FILL>
 __global__ void __launch_bounds__(32 * BIN_WARPS)
-    bin_tiles_kernel(long long nb, const short4 *__restrict__ tr, int tiles_n, int T, int *__restrict__ wc,
-                     const int *__restrict__ bins, int *__restrict__ sel, int *__restrict__ c2t) {
+    bin_tiles_kernel(long long nb, const float4 *__restrict__ fp, int tiles_n, int T, int row0, int nrows, int W,
+                     int *__restrict__ wc, const int *__restrict__ bins, int *__restrict__ sel, int *__restrict__ c2t) {
   if (FILL && bins[BIN_OVERFLOW]) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long seg = (((nb + BIN_WARPS - 1) / BIN_WARPS + 31) / 32) * 32;
   const long long b0 = (long long)warp * seg, b1 = (b0 + seg < nb) ? b0 + seg : nb;
   for (int t = blockIdx.x; t < T; t += gridDim.x) {
-    const short tm = (short)(t / tiles_n), tn = (short)(t % tiles_n);
+    const int tm = t / tiles_n, tn = t % tiles_n;
+    const float c0 = (float)(tn * BIN_TN), c1 = (float)min(tn * BIN_TN + BIN_TN - 1, W - 1);
+    const float r0 = (float)(row0 + tm * BM), r1 = (float)(row0 + min(tm * BM + BM - 1, nrows - 1));
     long long base = 0;
     int total = 0;
     if (FILL) {
@@ -1318,17 +1323,20 @@ __global__ void __launch_bounds__(32 * BIN_WARPS)
       }
     }
     int pos = 0;
-#pragma unroll 4
-    for (long long i0 = b0; i0 < b1; i0 += 32) {
-      const long long i = i0 + lane;
-      bool hit = false;
-      if (i < b1) {
-        const short4 r = __ldg(tr + i);
-        hit = r.x <= tn && tn <= r.y && r.z <= tm && tm <= r.w;
+    for (long long i0 = b0; i0 < b1; i0 += 32 * BIN_ILP) {
+      float4 f[BIN_ILP];
+#pragma unroll
+      for (int j = 0; j < BIN_ILP; ++j) {
+        const long long i = i0 + j * 32 + lane;
+        f[j] = i < b1 ? __ldg(fp + i) : make_float4(0.f, 0.f, -1.f, -1.f);
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      if (FILL && hit) sel[base + pos + __popc(bal & ((1u << lane) - 1u))] = (int)i;
-      pos += __popc(bal);
+#pragma unroll
+      for (int j = 0; j < BIN_ILP; ++j) {
+        const bool hit = bin_hit(f[j], c0, c1, r0, r1);
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (FILL && hit) sel[base + pos + __popc(bal & ((1u << lane) - 1u))] = (int)(i0 + j * 32 + lane);
+        pos += __popc(bal);
+      }
     }
     if (!FILL) {
       if (lane == 0) wc[t * BIN_WARPS + warp] = pos;
@@ -1460,6 +1468,27 @@ __global__ void __launch_bounds__(BIN_SLOTS)
       Operand<F16>::store2(Blo, o0, rl, -il);
       Operand<F16>::store2(Bhi, o1, ih, rh);
       Operand<F16>::store2(Blo, o1, il, rl);
+    }
+  }
+}
+// tiles no beamlet reaches get no GEMM unit: their pixels are zeroed here (in `out` and in every peer image), every
+// other tile is written whole by its final GEMM unit
+__global__ void __launch_bounds__(256)
+    bin_zero_empty_kernel(const int *__restrict__ bins, int T, int tiles_n, int M, int Np, double *__restrict__ out,
+                          long long ldo, const TgPeers peers, const unsigned long long *__restrict__ sep_guard) {
+  if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
+  const int *P = bins + BIN_HDR;
+  for (int t = blockIdx.x; t < T; t += gridDim.x) {
+    if (P[t + 1] != P[t]) continue;
+    const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+    for (int idx = threadIdx.x; idx < BM * (BN / 2); idx += blockDim.x) {
+      const int row = m0 + idx / (BN / 2), col = n0 + 2 * (idx % (BN / 2));
+      if (row < M && col < Np) {                   // Np = 2 W is even: (col, col + 1) is one complex pixel
+        const long long o = (long long)row * ldo + col;
+        *reinterpret_cast<double2 *>(out + o) = make_double2(0.0, 0.0);
+        for (int p = 0; p < peers.n; ++p)
+          *reinterpret_cast<double2 *>(static_cast<double *>(peers.ptr[p]) + o) = make_double2(0.0, 0.0);
+      }
     }
   }
 }
@@ -2390,6 +2419,7 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
 // ---- tile-binned tensor-core sum (see the kernels above) --------------------------------------------------------
 namespace {
 constexpr int kBinMaxChunks = 24576;        // operand capacity limit: 256 KiB per chunk -> 6 GiB
+thread_local int g_bin_last_chunks = -1;    // operand chunks of this thread's last eager tile-binned call
 struct BinCapKey {
   long long nb;
   int H, W, row0, nrows, cull, dev, need;
@@ -2447,7 +2477,7 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
 
   // ---- phase 1: table, verdicts, tile ranges, per-tile counts, prefix
   auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-  const size_t table_bytes = al((size_t)nb * 96), tr_bytes = al((size_t)nb * sizeof(short4)),
+  const size_t table_bytes = al((size_t)nb * 96), tr_bytes = al((size_t)nb * sizeof(float4)),
                wc_bytes = al((size_t)T * BIN_WARPS * sizeof(int)), bins_bytes = al((size_t)(BIN_HDR + T + 1) * sizeof(int));
   TgAsyncBuf ws1(st);
   TG_CUDA(ws1.alloc(table_bytes + 256 + tr_bytes + wc_bytes + bins_bytes));
@@ -2455,7 +2485,7 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   double *table = reinterpret_cast<double *>(w1);
   unsigned long long *key = reinterpret_cast<unsigned long long *>(w1 + table_bytes);
   unsigned long long *peak = key + 1, *gref = reinterpret_cast<unsigned long long *>(w1 + table_bytes + 64);
-  short4 *tr = reinterpret_cast<short4 *>(w1 + table_bytes + 256);
+  float4 *tr = reinterpret_cast<float4 *>(w1 + table_bytes + 256);
   int *wc = reinterpret_cast<int *>(w1 + table_bytes + 256 + tr_bytes);
   int *bins = reinterpret_cast<int *>(w1 + table_bytes + 256 + tr_bytes + wc_bytes);
   TG_CUDA(cudaMemsetAsync(key, 0, 16, st));
@@ -2467,8 +2497,9 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   ex.nrows = nrows;
   rc = tg_launch_prep(nb, poly, px2m, H, W, table, gref, st, &ex);
   if (rc != TG_OK) return rc;
-  bin_ranges_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, table, H, W, row0, nrows, gref, cull_bits, tr);
-  bin_tiles_kernel<false><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, tr, tiles_n, T, wc, nullptr, nullptr, nullptr);
+  bin_ranges_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, table, H, W, gref, cull_bits, tr);
+  bin_tiles_kernel<false><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, tr, tiles_n, T, row0, nrows, W, wc, nullptr, nullptr,
+                                                                      nullptr);
   rc = tg_launch_check("bin_tiles_kernel");
   if (rc != TG_OK) return rc;
   int cap = 0;
@@ -2488,6 +2519,7 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
       return TG_ENOTSEPARABLE;
     }
     cap = hdr[BIN_NEED];
+    g_bin_last_chunks = cap;
     if (BinCapKey *k = bin_cap_slot(nb, H, W, row0, nrows, cull_bits, dev, true)) k->need = cap;
   } else {
     const BinCapKey *k = bin_cap_slot(nb, H, W, row0, nrows, cull_bits, dev, false);
@@ -2506,9 +2538,9 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
     tg_set_error("tile-binned sum: %d operand chunks exceed the capacity limit of %d (use the SFU kernel)", cap, kBinMaxChunks);
     return TG_EUNSUPPORTED;
   }
-  TG_CUDA(cudaMemsetAsync(out, 0, out_bytes, st));
-  for (int p = 0; p < pe.n; ++p) TG_CUDA(cudaMemsetAsync(pe.ptr[p], 0, out_bytes, st));
-  if (cap == 0) {      // no beamlet reaches these rows
+  if (cap == 0) {      // no beamlet reaches these rows (eager calls only: a captured call always has room for 64 chunks)
+    TG_CUDA(cudaMemsetAsync(out, 0, out_bytes, st));
+    for (int p = 0; p < pe.n; ++p) TG_CUDA(cudaMemsetAsync(pe.ptr[p], 0, out_bytes, st));
     if (emit) return tg_emit_block(emit, 0, st, out, 0, out_bytes);
     return TG_OK;
   }
@@ -2529,9 +2561,8 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   float *parts = reinterpret_cast<float *>(Blo + op_bytes + cnt_bytes);
   double *acc = out_is_c128 ? static_cast<double *>(out) : reinterpret_cast<double *>(Blo + op_bytes + cnt_bytes + part_bytes);
   TG_CUDA(cudaMemsetAsync(counters, 0, cnt_bytes, st));
-  if (!out_is_c128) TG_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
   const unsigned long long *guard = capturing ? key : nullptr;          // under capture the verdict stays on the device
-  bin_tiles_kernel<true><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, tr, tiles_n, T, wc, bins, sel, c2t);
+  bin_tiles_kernel<true><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, tr, tiles_n, T, row0, nrows, W, wc, bins, sel, c2t);
   const unsigned gf = bounded_grid((long long)cap * (BM / FS));
   factor_rows_binned_kernel<true><<<gf, BIN_SLOTS, 0, st>>>(table, bins, sel, c2t, tiles_n, row0, nrows, W, capK, Ahi, Alo,
                                                             peak, guard);
@@ -2552,8 +2583,9 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
   TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TgPeers gp = out_is_c128 ? pe : none;                                 // complex64 peers are written by the conversion
+  bin_zero_empty_kernel<<<bounded_grid(T), 256, 0, st>>>(bins, T, tiles_n, nrows, 2 * W, acc, (long long)(2 * W), gp, guard);
   gemm_x3_kernel<true, false, true><<<(unsigned)sms, GEMM_THREADS, smem, st>>>(
-      ta, tb, tc, td, nrows, 2 * W, (int)(capK < 0x7fffffffLL ? capK : 0x7fffffffLL), acc, (long long)(2 * W), 1, peak,
+      ta, tb, tc, td, nrows, 2 * W, (int)(capK < 0x7fffffffLL ? capK : 0x7fffffffLL), acc, (long long)(2 * W), 0, peak,
       Headroom<true>::value, guard, gp, sc, parts, counters, nullptr, nullptr, 0u);
   rc = tg_launch_check("gemm_x3_kernel<f16> (tile-binned)");
   if (rc != TG_OK) return rc;
@@ -2572,6 +2604,10 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   if (emit) return tg_emit_block(emit, 0, st, out, 0, out_bytes);
   return TG_OK;
 }
+
+// Operand chunks (128 beamlet slots = 256 KiB of fp16 hi / lo row and column factors each) of the calling thread's last
+// eager tile-binned sum, -1 if there was none: what bench.py turns into the path's HBM traffic.
+extern "C" int tg_binned_last_chunks(void) { return g_bin_last_chunks; }
 
 // The verdict TG_METHOD_AUTO reaches on the device, read back to the host (synchronises `stream`): 1 = the tensor-core
 // path applies (separable, and not clearly more expensive than the culled SFU sum), 0 = SFU kernel.  Plans use it to

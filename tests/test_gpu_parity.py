@@ -1525,6 +1525,7 @@ def test_scanner_descanner_array_parameters(torch_cuda):
                                      ("c3_biprism_separable", dict(method="sfu", cull_bits=40)),
                                      ("c3_biprism_separable", dict(method="auto", cull_bits=40)),
                                      ("c2_aperture", dict(method="tensor", cull_bits=0)),
+                                     ("c3_biprism_separable", dict(method="tensor_binned", cull_bits=40)),
                                      ("c3_biprism_general", dict(method="auto", cull_bits=40))])
 def test_peer_stores_emulated_ranks_on_one_gpu(torch_cuda, case, kw, world):
     """tg_field_sum_peers as `world` ranks would call it, one after the other on ONE GPU with `world` local images
