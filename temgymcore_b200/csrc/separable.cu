@@ -433,8 +433,11 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
         // tiles whose CTAs share operand tiles in lockstep; asking the TMA unit to prefetch the tiles `pf` k-blocks
         // ahead into L2 (cp.async.bulk.prefetch.tensor) was measured and does NOT help (it competes with the loads).
         const int pf = sched.prefetch;
-        if (pf > 0)
-          for (int kb = kb0; kb < min(kb0 + pf, kb1); ++kb) {
+        // (ragged schedule: a CTA walks ONE contiguous k-range through all its tiles and every operand byte comes from
+        // HBM exactly once -- there the prefetch runs ahead across unit boundaries, up to the end of the CTA's range)
+        const int pf_end = RAGGED ? itr.f1 * CHUNK_KB : kb1;
+        if (pf > 0 && (!RAGGED || it == 0))
+          for (int kb = kb0; kb < min(kb0 + pf, pf_end); ++kb) {
             tma_prefetch_2d(&tmA_hi, kb * BK, m0);
             tma_prefetch_2d(&tmA_lo, kb * BK, m0);
             tma_prefetch_2d(&tmB_hi, kb * BK, n0);
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = (int)(it % STAGES);
           const uint32_t ph = (it / STAGES) & 1u;
-          if (pf > 0 && kb + pf < kb1) {
+          if (pf > 0 && kb + pf < pf_end) {
             tma_prefetch_2d(&tmA_hi, (kb + pf) * BK, m0);
             tma_prefetch_2d(&tmA_lo, (kb + pf) * BK, m0);
             tma_prefetch_2d(&tmB_hi, (kb + pf) * BK, n0);
@@ -1262,12 +1265,17 @@ constexpr int BIN_WARPS = 8;
 // {envelope of beamlet i >= threshold} (+1 px slack on both half-axes; separable beamlets have no cross term to speak
 // of); half-width < 0: the beamlet reaches nothing; non-concave or non-finite envelopes get a footprint that covers
 // everything, so NaN beamlets poison the image as in the dense sum.  Same threshold as field.cu's bbox_kernel.
+// tr[i] = the tiles its bounding box touches inside rows [row0, row0 + nrows): (first, last tile column, first, last
+// tile row), (1, 0, 1, 0) if none -- the cheap first test of the per-tile scans.
 __global__ void __launch_bounds__(256)
-    bin_ranges_kernel(long long nb, const double *__restrict__ table, int H, int W,
-                      const unsigned long long *__restrict__ gref_key, int cull_bits, float4 *__restrict__ fp) {
+    bin_ranges_kernel(long long nb, const double *__restrict__ table, int H, int W, int row0, int nrows,
+                      const unsigned long long *__restrict__ gref_key, int cull_bits, float4 *__restrict__ fp,
+                      short4 *__restrict__ tr) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nb) return;
   float4 o = make_float4(0.f, 0.f, 1e30f, 1e30f);
+  const int tm_last = (nrows - 1) / BM, tn_last = (W - 1) / BIN_TN;
+  short4 r = make_short4(0, (short)tn_last, 0, (short)tm_last);
   const unsigned long long k = *gref_key;
   const double *e = table + i * 12 + 6;   // E(c, r) = e0 + e1 c + e2 r + e3 c^2 + e4 c r + e5 r^2 [bits]
   const double det = e[3] * e[5] - 0.25 * e[4] * e[4];
@@ -1278,14 +1286,22 @@ __global__ void __launch_bounds__(256)
     const double d = (e[0] + 0.5 * (e[1] * cs + e[2] * rs)) - e_thr;
     if (d < 0.0) {
       o.z = o.w = -1.f;
+      r = make_short4(1, 0, 1, 0);
     } else if (isfinite(d) && isfinite(cs) && isfinite(rs)) {
-      const double hc = sqrt(d * (-e[5]) / det) + 1.0, hr = sqrt(d * (-e[3]) / det) + 1.0;
       // (fp32 footprints: the centre rounds by < 2^-24 of its magnitude -- widen the half-axes by that much)
       const double slack = (fabs(cs) + fabs(rs)) * 1.2e-7;
-      o = make_float4((float)cs, (float)rs, (float)fmin(hc + slack, 1e30), (float)fmin(hr + slack, 1e30));
+      const double hc = sqrt(d * (-e[5]) / det) + 1.0 + slack, hr = sqrt(d * (-e[3]) / det) + 1.0 + slack;
+      o = make_float4((float)cs, (float)rs, (float)fmin(hc, 1e30), (float)fmin(hr, 1e30));
+      const double c_lo = fmax(floor(cs - hc), 0.0), c_hi = fmin(ceil(cs + hc), (double)(W - 1));
+      const double r_lo = fmax(floor(rs - hr), (double)row0), r_hi = fmin(ceil(rs + hr), (double)(row0 + nrows - 1));
+      if (c_hi < c_lo || r_hi < r_lo) r = make_short4(1, 0, 1, 0);
+      else
+        r = make_short4((short)((int)c_lo / BIN_TN), (short)((int)c_hi / BIN_TN), (short)(((int)r_lo - row0) / BM),
+                        (short)(((int)r_hi - row0) / BM));
     }
   }
   fp[i] = o;
+  tr[i] = r;
 }
 
 // does the footprint meet the pixel rectangle [c0, c1] x [r0, r1]?  (closest point of the rectangle to the centre)
@@ -1295,20 +1311,23 @@ __device__ __forceinline__ bool bin_hit(const float4 f, float c0, float c1, floa
   return f.z >= 0.f && a * a + b * b <= c * c * 1.000001f;
 }
 
-// One CTA per tile, warp w scans beamlets [w seg, (w + 1) seg), 8 footprints per lane in flight.  FILL = false:
-// wc[t][w] = hits of warp w.  FILL = true: append the hits in beamlet order behind the hits of the warps before, pad
-// the tile's last chunk, fill c2t.
+// One CTA per tile, warp w scans beamlets [w seg, (w + 1) seg), 8 tile ranges per lane in flight; a lane whose range
+// holds the tile tests the elliptical footprint.  FILL = false: wc[t][w] = hits of warp w, and (hits != NULL) the
+// ballot word of every group of 32 beamlets.  FILL = true: append the hits in beamlet order behind the hits of the
+// warps before -- from the ballot words, or by scanning again without them -- pad the tile's last chunk, fill c2t.
 constexpr int BIN_ILP = 8;
 template <bool FILL>
 __global__ void __launch_bounds__(32 * BIN_WARPS)
-    bin_tiles_kernel(long long nb, const float4 *__restrict__ fp, int tiles_n, int T, int row0, int nrows, int W,
-                     int *__restrict__ wc, const int *__restrict__ bins, int *__restrict__ sel, int *__restrict__ c2t) {
+    bin_tiles_kernel(long long nb, const float4 *__restrict__ fp, const short4 *__restrict__ tr, int tiles_n, int T,
+                     int row0, int nrows, int W, int *__restrict__ wc, unsigned *__restrict__ hits,
+                     const int *__restrict__ bins, int *__restrict__ sel, int *__restrict__ c2t) {
   if (FILL && bins[BIN_OVERFLOW]) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long seg = (((nb + BIN_WARPS - 1) / BIN_WARPS + 31) / 32) * 32;
   const long long b0 = (long long)warp * seg, b1 = (b0 + seg < nb) ? b0 + seg : nb;
+  const long long wpt = (nb + 31) / 32;                      // ballot words per tile
   for (int t = blockIdx.x; t < T; t += gridDim.x) {
-    const int tm = t / tiles_n, tn = t % tiles_n;
+    const short tm = (short)(t / tiles_n), tn = (short)(t % tiles_n);
     const float c0 = (float)(tn * BIN_TN), c1 = (float)min(tn * BIN_TN + BIN_TN - 1, W - 1);
     const float r0 = (float)(row0 + tm * BM), r1 = (float)(row0 + min(tm * BM + BM - 1, nrows - 1));
     long long base = 0;
@@ -1323,19 +1342,38 @@ __global__ void __launch_bounds__(32 * BIN_WARPS)
       }
     }
     int pos = 0;
-    for (long long i0 = b0; i0 < b1; i0 += 32 * BIN_ILP) {
-      float4 f[BIN_ILP];
-#pragma unroll
-      for (int j = 0; j < BIN_ILP; ++j) {
-        const long long i = i0 + j * 32 + lane;
-        f[j] = i < b1 ? __ldg(fp + i) : make_float4(0.f, 0.f, -1.f, -1.f);
+    if (FILL && hits) {
+      // 32 ballot words per round, one per lane; the set bits are the beamlets of this tile, in order
+      const unsigned *hw = hits + (long long)t * wpt;
+      for (long long g0 = b0 / 32; g0 < (b1 + 31) / 32; g0 += 32) {
+        const long long g = g0 + lane;
+        const unsigned mine = g < (b1 + 31) / 32 ? hw[g] : 0u;
+        unsigned any = __ballot_sync(0xffffffffu, mine != 0u);
+        while (any) {
+          const int k = __ffs(any) - 1;
+          any &= any - 1;
+          const unsigned bal = __shfl_sync(0xffffffffu, mine, k);
+          if (bal & (1u << lane)) sel[base + pos + __popc(bal & ((1u << lane) - 1u))] = (int)((g0 + k) * 32 + lane);
+          pos += __popc(bal);
+        }
       }
+    } else {
+      for (long long i0 = b0; i0 < b1; i0 += 32 * BIN_ILP) {
+        short4 r[BIN_ILP];
 #pragma unroll
-      for (int j = 0; j < BIN_ILP; ++j) {
-        const bool hit = bin_hit(f[j], c0, c1, r0, r1);
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (FILL && hit) sel[base + pos + __popc(bal & ((1u << lane) - 1u))] = (int)(i0 + j * 32 + lane);
-        pos += __popc(bal);
+        for (int j = 0; j < BIN_ILP; ++j) {
+          const long long i = i0 + j * 32 + lane;
+          r[j] = i < b1 ? __ldg(tr + i) : make_short4(1, 0, 1, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < BIN_ILP; ++j) {
+          bool hit = r[j].x <= tn && tn <= r[j].y && r[j].z <= tm && tm <= r[j].w;
+          if (hit) hit = bin_hit(__ldg(fp + i0 + j * 32 + lane), c0, c1, r0, r1);
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          if (FILL && hit) sel[base + pos + __popc(bal & ((1u << lane) - 1u))] = (int)(i0 + j * 32 + lane);
+          if (!FILL && hits && lane == 0 && i0 + j * 32 < b1) hits[(long long)t * wpt + (i0 + j * 32) / 32] = bal;
+          pos += __popc(bal);
+        }
       }
     }
     if (!FILL) {
@@ -1421,16 +1459,15 @@ __global__ void __launch_bounds__(BIN_SLOTS)
     }
 #pragma unroll 4
     for (int j = 0; j < FS; ++j) {
-      float rh = 0.f, rl = 0.f, ih = 0.f, il = 0.f;
-      if (n >= 0 && m0 + j < M) {
-        float re, im;
-        strip_eval(st, j, re, im);
-        Operand<F16>::split(re, rh, rl);
-        Operand<F16>::split(im, ih, il);
-      }
+      float re = 0.f, im = 0.f;
+      if (n >= 0 && m0 + j < M) strip_eval(st, j, re, im);
+      // (re, im) split as one packed pair: hi = fp16(x), lo = fp16(x - hi) -- the values Operand<true>::split gives
+      const __half2 hi = __floats2half2_rn(re, im);
+      const float2 hf = __half22float2(hi);
+      const __half2 lo = __floats2half2_rn(re - hf.x, im - hf.y);
       const long long o = (long long)(sidx * FS + j) * ldk + 2 * s;
-      Operand<F16>::store2(Ahi, o, rh, ih);
-      Operand<F16>::store2(Alo, o, rl, il);
+      *reinterpret_cast<__half2 *>(static_cast<__half *>(Ahi) + o) = hi;
+      *reinterpret_cast<__half2 *>(static_cast<__half *>(Alo) + o) = lo;
     }
   }
 }
@@ -1456,18 +1493,18 @@ __global__ void __launch_bounds__(BIN_SLOTS)
     }
 #pragma unroll 4
     for (int j = 0; j < FS; ++j) {
-      float rh = 0.f, rl = 0.f, ih = 0.f, il = 0.f;
-      if (n >= 0 && c0 + j < W) {
-        float re, im;
-        strip_eval(st, j, re, im);
-        Operand<F16>::split(re, rh, rl);
-        Operand<F16>::split(im, ih, il);
-      }
+      float re = 0.f, im = 0.f;
+      if (n >= 0 && c0 + j < W) strip_eval(st, j, re, im);
+      const __half2 hi = __floats2half2_rn(re, im);
+      const float2 hf = __half22float2(hi);
+      const __half2 lo = __floats2half2_rn(re - hf.x, im - hf.y);
+      // row 2 c: (Re, -Im) = the pair with the sign bit of its upper half flipped; row 2 c + 1: (Im, Re) = the halves swapped
+      const unsigned hb = *reinterpret_cast<const unsigned *>(&hi), lb = *reinterpret_cast<const unsigned *>(&lo);
       const long long o0 = (long long)(2 * (sidx * FS + j)) * ldk + 2 * s, o1 = o0 + ldk;
-      Operand<F16>::store2(Bhi, o0, rh, -ih);
-      Operand<F16>::store2(Blo, o0, rl, -il);
-      Operand<F16>::store2(Bhi, o1, ih, rh);
-      Operand<F16>::store2(Blo, o1, il, rl);
+      *reinterpret_cast<unsigned *>(static_cast<__half *>(Bhi) + o0) = hb ^ 0x80000000u;
+      *reinterpret_cast<unsigned *>(static_cast<__half *>(Blo) + o0) = lb ^ 0x80000000u;
+      *reinterpret_cast<unsigned *>(static_cast<__half *>(Bhi) + o1) = __byte_perm(hb, 0, 0x1032);
+      *reinterpret_cast<unsigned *>(static_cast<__half *>(Blo) + o1) = __byte_perm(lb, 0, 0x1032);
     }
   }
 }
@@ -2478,16 +2515,23 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   // ---- phase 1: table, verdicts, tile ranges, per-tile counts, prefix
   auto al = [](size_t b) { return (b + 255) / 256 * 256; };
   const size_t table_bytes = al((size_t)nb * 96), tr_bytes = al((size_t)nb * sizeof(float4)),
-               wc_bytes = al((size_t)T * BIN_WARPS * sizeof(int)), bins_bytes = al((size_t)(BIN_HDR + T + 1) * sizeof(int));
+               tr2_bytes = al((size_t)nb * sizeof(short4)), wc_bytes = al((size_t)T * BIN_WARPS * sizeof(int)),
+               bins_bytes = al((size_t)(BIN_HDR + T + 1) * sizeof(int));
+  // ballot words of the counting scan (one bit per (tile, beamlet)), reused by the fill scan when they fit 256 MiB
+  const size_t hits_need = (size_t)T * (size_t)((nb + 31) / 32) * sizeof(unsigned);
+  const size_t hits_bytes = hits_need <= ((size_t)256 << 20) ? al(hits_need) : 0;
   TgAsyncBuf ws1(st);
-  TG_CUDA(ws1.alloc(table_bytes + 256 + tr_bytes + wc_bytes + bins_bytes));
+  TG_CUDA(ws1.alloc(table_bytes + 256 + tr_bytes + tr2_bytes + wc_bytes + bins_bytes + hits_bytes));
   unsigned char *w1 = ws1.as<unsigned char>();
   double *table = reinterpret_cast<double *>(w1);
   unsigned long long *key = reinterpret_cast<unsigned long long *>(w1 + table_bytes);
   unsigned long long *peak = key + 1, *gref = reinterpret_cast<unsigned long long *>(w1 + table_bytes + 64);
   float4 *tr = reinterpret_cast<float4 *>(w1 + table_bytes + 256);
-  int *wc = reinterpret_cast<int *>(w1 + table_bytes + 256 + tr_bytes);
-  int *bins = reinterpret_cast<int *>(w1 + table_bytes + 256 + tr_bytes + wc_bytes);
+  short4 *tr2 = reinterpret_cast<short4 *>(w1 + table_bytes + 256 + tr_bytes);
+  int *wc = reinterpret_cast<int *>(w1 + table_bytes + 256 + tr_bytes + tr2_bytes);
+  int *bins = reinterpret_cast<int *>(w1 + table_bytes + 256 + tr_bytes + tr2_bytes + wc_bytes);
+  unsigned *hits = hits_bytes ? reinterpret_cast<unsigned *>(w1 + table_bytes + 256 + tr_bytes + tr2_bytes + wc_bytes + bins_bytes)
+                              : nullptr;
   TG_CUDA(cudaMemsetAsync(key, 0, 16, st));
   TG_CUDA(cudaMemsetAsync(gref, 0xFF, 8, st));
   TgPrepExtra ex;
@@ -2497,9 +2541,9 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   ex.nrows = nrows;
   rc = tg_launch_prep(nb, poly, px2m, H, W, table, gref, st, &ex);
   if (rc != TG_OK) return rc;
-  bin_ranges_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, table, H, W, gref, cull_bits, tr);
-  bin_tiles_kernel<false><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, tr, tiles_n, T, row0, nrows, W, wc, nullptr, nullptr,
-                                                                      nullptr);
+  bin_ranges_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, table, H, W, row0, nrows, gref, cull_bits, tr, tr2);
+  bin_tiles_kernel<false><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, tr, tr2, tiles_n, T, row0, nrows, W, wc, hits,
+                                                                      nullptr, nullptr, nullptr);
   rc = tg_launch_check("bin_tiles_kernel");
   if (rc != TG_OK) return rc;
   int cap = 0;
@@ -2562,7 +2606,8 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   double *acc = out_is_c128 ? static_cast<double *>(out) : reinterpret_cast<double *>(Blo + op_bytes + cnt_bytes + part_bytes);
   TG_CUDA(cudaMemsetAsync(counters, 0, cnt_bytes, st));
   const unsigned long long *guard = capturing ? key : nullptr;          // under capture the verdict stays on the device
-  bin_tiles_kernel<true><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, tr, tiles_n, T, row0, nrows, W, wc, bins, sel, c2t);
+  bin_tiles_kernel<true><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, tr, tr2, tiles_n, T, row0, nrows, W, wc, hits, bins,
+                                                                     sel, c2t);
   const unsigned gf = bounded_grid((long long)cap * (BM / FS));
   factor_rows_binned_kernel<true><<<gf, BIN_SLOTS, 0, st>>>(table, bins, sel, c2t, tiles_n, row0, nrows, W, capK, Ahi, Alo,
                                                             peak, guard);
@@ -2580,6 +2625,14 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   sc.nkb = (int)((long long)cap * GemmCfg<true>::CHUNK_KB);
   sc.G = sms;
   sc.bins = bins;
+  // L2 prefetch distance of the operand stream in k-blocks of 64 KiB per CTA (TG_BIN_PREFETCH; 0 = off): the three-stage
+  // shared-memory ring alone covers an L2 hit, not an HBM access, and this GEMM has no operand reuse to find in L2
+  static const int bin_pf = [] {
+    const char *e = getenv("TG_BIN_PREFETCH");
+    const int v = e ? atoi(e) : 6;
+    return (v >= 0 && v <= 64) ? v : 6;
+  }();
+  sc.prefetch = bin_pf;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
   TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TgPeers gp = out_is_c128 ? pe : none;                                 // complex64 peers are written by the conversion
