@@ -438,27 +438,31 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
         const int pf_end = RAGGED ? itr.f1 * CHUNK_KB : kb1;
         if (pf > 0 && (!RAGGED || it == 0))
           for (int kb = kb0; kb < min(kb0 + pf, pf_end); ++kb) {
-            tma_prefetch_2d(&tmA_hi, kb * BK, m0);
-            tma_prefetch_2d(&tmA_lo, kb * BK, m0);
-            tma_prefetch_2d(&tmB_hi, kb * BK, n0);
-            tma_prefetch_2d(&tmB_lo, kb * BK, n0);
+            tma_prefetch_2d(&tmA_hi, RAGGED ? 0 : kb * BK, RAGGED ? kb * BM : m0);
+            tma_prefetch_2d(&tmA_lo, RAGGED ? 0 : kb * BK, RAGGED ? kb * BM : m0);
+            tma_prefetch_2d(&tmB_hi, RAGGED ? 0 : kb * BK, RAGGED ? kb * BN : n0);
+            tma_prefetch_2d(&tmB_lo, RAGGED ? 0 : kb * BK, RAGGED ? kb * BN : n0);
           }
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = (int)(it % STAGES);
           const uint32_t ph = (it / STAGES) & 1u;
           if (pf > 0 && kb + pf < pf_end) {
-            tma_prefetch_2d(&tmA_hi, (kb + pf) * BK, m0);
-            tma_prefetch_2d(&tmA_lo, (kb + pf) * BK, m0);
-            tma_prefetch_2d(&tmB_hi, (kb + pf) * BK, n0);
-            tma_prefetch_2d(&tmB_lo, (kb + pf) * BK, n0);
+            tma_prefetch_2d(&tmA_hi, RAGGED ? 0 : (kb + pf) * BK, RAGGED ? (kb + pf) * BM : m0);
+            tma_prefetch_2d(&tmA_lo, RAGGED ? 0 : (kb + pf) * BK, RAGGED ? (kb + pf) * BM : m0);
+            tma_prefetch_2d(&tmB_hi, RAGGED ? 0 : (kb + pf) * BK, RAGGED ? (kb + pf) * BN : n0);
+            tma_prefetch_2d(&tmB_lo, RAGGED ? 0 : (kb + pf) * BK, RAGGED ? (kb + pf) * BN : n0);
           }
           tg_mbar_wait(&ctl->empty[s], ph ^ 1u);
           unsigned char *st = tiles + s * STAGE_BYTES;
           tg_mbar_expect_tx(&ctl->full[s], STAGE_BYTES);
-          tma_load_2d(st + 0 * TILE_BYTES, &tmA_hi, &ctl->full[s], kb * BK, m0);
-          tma_load_2d(st + 1 * TILE_BYTES, &tmA_lo, &ctl->full[s], kb * BK, m0);
-          tma_load_2d(st + 2 * TILE_BYTES, &tmB_hi, &ctl->full[s], kb * BK, n0);
-          tma_load_2d(st + 3 * TILE_BYTES, &tmB_lo, &ctl->full[s], kb * BK, n0);
+          // (ragged schedule: operands are stored k-block by k-block, each 128-row x 128-byte tile contiguous -- a
+          // tensor of 128-byte rows, tile kb at rows [128 kb, 128 kb + 128) -- so a load is ONE 16 KiB run of DRAM
+          // instead of 128 lines a whole operand row apart)
+          const int ck = RAGGED ? 0 : kb * BK, cra = RAGGED ? kb * BM : m0, crb = RAGGED ? kb * BN : n0;
+          tma_load_2d(st + 0 * TILE_BYTES, &tmA_hi, &ctl->full[s], ck, cra);
+          tma_load_2d(st + 1 * TILE_BYTES, &tmA_lo, &ctl->full[s], ck, cra);
+          tma_load_2d(st + 2 * TILE_BYTES, &tmB_hi, &ctl->full[s], ck, crb);
+          tma_load_2d(st + 3 * TILE_BYTES, &tmB_lo, &ctl->full[s], ck, crb);
         }
       }
     }
@@ -1365,10 +1369,15 @@ __global__ void __launch_bounds__(32 * BIN_WARPS)
           const long long i = i0 + j * 32 + lane;
           r[j] = i < b1 ? __ldg(tr + i) : make_short4(1, 0, 1, 0);
         }
+        float4 f[BIN_ILP];                       // (all refinement loads are issued before the first ballot needs one)
 #pragma unroll
         for (int j = 0; j < BIN_ILP; ++j) {
-          bool hit = r[j].x <= tn && tn <= r[j].y && r[j].z <= tm && tm <= r[j].w;
-          if (hit) hit = bin_hit(__ldg(fp + i0 + j * 32 + lane), c0, c1, r0, r1);
+          const bool coarse = r[j].x <= tn && tn <= r[j].y && r[j].z <= tm && tm <= r[j].w;
+          f[j] = coarse ? __ldg(fp + i0 + j * 32 + lane) : make_float4(0.f, 0.f, -1.f, -1.f);
+        }
+#pragma unroll
+        for (int j = 0; j < BIN_ILP; ++j) {
+          const bool hit = bin_hit(f[j], c0, c1, r0, r1);
           const unsigned bal = __ballot_sync(0xffffffffu, hit);
           if (FILL && hit) sel[base + pos + __popc(bal & ((1u << lane) - 1u))] = (int)(i0 + j * 32 + lane);
           if (!FILL && hits && lane == 0 && i0 + j * 32 < b1) hits[(long long)t * wpt + (i0 + j * 32) / 32] = bal;
@@ -1465,7 +1474,8 @@ __global__ void __launch_bounds__(BIN_SLOTS)
       const __half2 hi = __floats2half2_rn(re, im);
       const float2 hf = __half22float2(hi);
       const __half2 lo = __floats2half2_rn(re - hf.x, im - hf.y);
-      const long long o = (long long)(sidx * FS + j) * ldk + 2 * s;
+      // tiled layout: k-block s / 32 holds rows [0, 128) x 64 k-elements contiguously
+      const long long o = ((s >> 5) * BM + (sidx * FS + j)) * 64 + 2 * (s & 31);
       *reinterpret_cast<__half2 *>(static_cast<__half *>(Ahi) + o) = hi;
       *reinterpret_cast<__half2 *>(static_cast<__half *>(Alo) + o) = lo;
     }
@@ -1500,7 +1510,7 @@ __global__ void __launch_bounds__(BIN_SLOTS)
       const __half2 lo = __floats2half2_rn(re - hf.x, im - hf.y);
       // row 2 c: (Re, -Im) = the pair with the sign bit of its upper half flipped; row 2 c + 1: (Im, Re) = the halves swapped
       const unsigned hb = *reinterpret_cast<const unsigned *>(&hi), lb = *reinterpret_cast<const unsigned *>(&lo);
-      const long long o0 = (long long)(2 * (sidx * FS + j)) * ldk + 2 * s, o1 = o0 + ldk;
+      const long long o0 = ((s >> 5) * BN + 2 * (sidx * FS + j)) * 64 + 2 * (s & 31), o1 = o0 + 64;
       *reinterpret_cast<unsigned *>(static_cast<__half *>(Bhi) + o0) = hb ^ 0x80000000u;
       *reinterpret_cast<unsigned *>(static_cast<__half *>(Blo) + o0) = lb ^ 0x80000000u;
       *reinterpret_cast<unsigned *>(static_cast<__half *>(Bhi) + o1) = __byte_perm(hb, 0, 0x1032);
@@ -2615,22 +2625,25 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   rc = tg_launch_check("binned factor kernels");
   if (rc != TG_OK) return rc;
   CUtensorMap ta, tb, tc, td;
-  if ((rc = make_map<true>(&ta, Ahi, BM, capK, capK)) != TG_OK) return rc;
-  if ((rc = make_map<true>(&tb, Alo, BM, capK, capK)) != TG_OK) return rc;
-  if ((rc = make_map<true>(&tc, Bhi, BN, capK, capK)) != TG_OK) return rc;
-  if ((rc = make_map<true>(&td, Blo, BN, capK, capK)) != TG_OK) return rc;
+  // tiled operands: tensors of 128-byte rows (64 fp16), k-block kb at rows [128 kb, 128 kb + 128)
+  const long long op_rows = capK / GemmCfg<true>::BK * BM;
+  if ((rc = make_map<true>(&ta, Ahi, op_rows, GemmCfg<true>::BK, GemmCfg<true>::BK)) != TG_OK) return rc;
+  if ((rc = make_map<true>(&tb, Alo, op_rows, GemmCfg<true>::BK, GemmCfg<true>::BK)) != TG_OK) return rc;
+  if ((rc = make_map<true>(&tc, Bhi, op_rows, GemmCfg<true>::BK, GemmCfg<true>::BK)) != TG_OK) return rc;
+  if ((rc = make_map<true>(&td, Blo, op_rows, GemmCfg<true>::BK, GemmCfg<true>::BK)) != TG_OK) return rc;
   SkSched sc = make_sched(nrows, 2 * W, CHUNK_K, GemmCfg<true>::BK, GemmCfg<true>::CHUNK_KB, sms, 0);
   sc.T = T;
   sc.tiles_n = tiles_n;
   sc.nkb = (int)((long long)cap * GemmCfg<true>::CHUNK_KB);
   sc.G = sms;
   sc.bins = bins;
-  // L2 prefetch distance of the operand stream in k-blocks of 64 KiB per CTA (TG_BIN_PREFETCH; 0 = off): the three-stage
-  // shared-memory ring alone covers an L2 hit, not an HBM access, and this GEMM has no operand reuse to find in L2
+  // L2 prefetch distance of the operand stream in k-blocks of 64 KiB per CTA (TG_BIN_PREFETCH, experiment knob, default
+  // off).  MEASURED on B200 (C3): cp.async.bulk.prefetch.tensor at distances 3 / 6 / 10 / 16 takes the GEMM from 0.58 to
+  // 1.11 ms whatever the distance -- the prefetches queue in the same TMA unit as the loads they are meant to help
   static const int bin_pf = [] {
     const char *e = getenv("TG_BIN_PREFETCH");
-    const int v = e ? atoi(e) : 6;
-    return (v >= 0 && v <= 64) ? v : 6;
+    const int v = e ? atoi(e) : 0;
+    return (v >= 0 && v <= 64) ? v : 0;
   }();
   sc.prefetch = bin_pf;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
