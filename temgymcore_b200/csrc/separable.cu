@@ -1249,14 +1249,16 @@ __global__ void __launch_bounds__(256)
 // of its tensor work on (beamlet, pixel) pairs below the culling threshold, and the culled SFU kernel evaluates the
 // remaining 1-3 % pixel by pixel.  Here the sum stays on the tensor cores but every output tile only multiplies the
 // beamlets whose bounding box {envelope >= brightest on-detector peak - cull_bits} meets it:
-//   * bin_ranges_kernel: per beamlet, the elliptical footprint {envelope >= threshold} in detector pixels;
-//   * bin_tiles_kernel<false>: per tile (one CTA; each of its 8 warps scans a contiguous eighth of the beamlets) the
-//     number of beamlets that reach it; bin_prefix_kernel: chunks of 128 beamlets per tile -> P[0..T] (exclusive scan),
-//     the chunks per CTA of the ragged GEMM schedule, the overflow verdict against the operand capacity;
-//   * bin_tiles_kernel<true>: the same scan again, appending the beamlet indices IN BEAMLET ORDER (deterministic sums)
-//     to the tile's slots sel[P[t] * 128 ...], padded with -1 to whole chunks; chunk -> tile map c2t;
-//   * factor_*_binned_kernel: row / column factors of slot s for the 128 rows / 64 columns of ITS tile into operands of
-//     128 rows x (capacity * 256) k-elements -- one concatenated k axis, chunk g at k = 256 g;
+//   * bin_mark_kernel: one thread per beamlet sets its bit in the word of every tile its elliptical footprint
+//     {envelope >= threshold} meets (hits[tile][beamlet / 32], atomicOr: ~1e6 of them at C3);
+//   * bin_tiles_kernel<false>: per tile (one CTA, each of its 8 warps owns a contiguous eighth of the tile's words) the
+//     number of set bits; bin_prefix_kernel: chunks of 128 beamlets per tile -> P[0..T] (exclusive scan), the chunks per
+//     CTA of the ragged GEMM schedule, the overflow verdict against the operand capacity;
+//   * bin_tiles_kernel<true>: the set bits expanded IN BEAMLET ORDER (deterministic sums) into the tile's slots
+//     sel[P[t] * 128 ...], padded with -1 to whole chunks; chunk -> tile map c2t;
+//   * factor_*_binned_kernel: row / column factors of slot s for the 128 rows / 64 columns of ITS tile, on one
+//     concatenated k axis (chunk g at k = 256 g), stored k-block by k-block: each 128-row x 64-k tile of an operand is
+//     16 KiB of contiguous memory, so the factor kernels write and the GEMM's TMA loads read whole DRAM pages;
 //   * gemm_x3_kernel with the ragged schedule (SkSched::bins): 148 CTAs split the chunk axis evenly, tiles cut by a CTA
 //     boundary are fixed up by the last arriver like every stream-K piece.
 // Per (beamlet, tile) pair: 192 factor evaluations and 2 KB of operands instead of up to 8192 SFU pixel evaluations;
@@ -1265,21 +1267,18 @@ constexpr int BIN_SLOTS = CHUNK_K / 2;   // beamlets per accumulation chunk (4-m
 constexpr int BIN_TN = BN / 2;           // complex columns per tile
 constexpr int BIN_WARPS = 8;
 
-// fp[i] = (centre column, centre row, half-width, half-height) in detector pixels of the axis-aligned ellipse
-// {envelope of beamlet i >= threshold} (+1 px slack on both half-axes; separable beamlets have no cross term to speak
-// of); half-width < 0: the beamlet reaches nothing; non-concave or non-finite envelopes get a footprint that covers
-// everything, so NaN beamlets poison the image as in the dense sum.  Same threshold as field.cu's bbox_kernel.
-// tr[i] = the tiles its bounding box touches inside rows [row0, row0 + nrows): (first, last tile column, first, last
-// tile row), (1, 0, 1, 0) if none -- the cheap first test of the per-tile scans.
+// One thread per beamlet: the axis-aligned ellipse {envelope >= threshold} in detector pixels (+1 px slack on both
+// half-axes; separable beamlets have no cross term to speak of; same threshold as field.cu's bbox_kernel), then every
+// tile of its bounding box whose pixel rectangle the ellipse meets gets bit (i mod 32) of word hits[t][i / 32] set.
+// Non-concave or non-finite envelopes mark every tile, so NaN beamlets poison the image as in the dense sum.
 __global__ void __launch_bounds__(256)
-    bin_ranges_kernel(long long nb, const double *__restrict__ table, int H, int W, int row0, int nrows,
-                      const unsigned long long *__restrict__ gref_key, int cull_bits, float4 *__restrict__ fp,
-                      short4 *__restrict__ tr) {
+    bin_mark_kernel(long long nb, const double *__restrict__ table, int H, int W, int row0, int nrows, int tiles_n,
+                    const unsigned long long *__restrict__ gref_key, int cull_bits, unsigned *__restrict__ hits) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nb) return;
-  float4 o = make_float4(0.f, 0.f, 1e30f, 1e30f);
-  const int tm_last = (nrows - 1) / BM, tn_last = (W - 1) / BIN_TN;
-  short4 r = make_short4(0, (short)tn_last, 0, (short)tm_last);
+  const long long wpt = (nb + 31) / 32;
+  int tn_lo = 0, tn_hi = (W - 1) / BIN_TN, tm_lo = 0, tm_hi = (nrows - 1) / BM;
+  float cx = 0.f, cy = 0.f, hx = 1e30f, hy = 1e30f;
   const unsigned long long k = *gref_key;
   const double *e = table + i * 12 + 6;   // E(c, r) = e0 + e1 c + e2 r + e3 c^2 + e4 c r + e5 r^2 [bits]
   const double det = e[3] * e[5] - 0.25 * e[4] * e[4];
@@ -1288,52 +1287,52 @@ __global__ void __launch_bounds__(256)
     const double cs = (0.5 * e[4] * e[2] - e[5] * e[1]) / (2.0 * det);
     const double rs = (0.5 * e[4] * e[1] - e[3] * e[2]) / (2.0 * det);
     const double d = (e[0] + 0.5 * (e[1] * cs + e[2] * rs)) - e_thr;
-    if (d < 0.0) {
-      o.z = o.w = -1.f;
-      r = make_short4(1, 0, 1, 0);
-    } else if (isfinite(d) && isfinite(cs) && isfinite(rs)) {
-      // (fp32 footprints: the centre rounds by < 2^-24 of its magnitude -- widen the half-axes by that much)
+    if (d < 0.0) return;                                      // below the threshold everywhere
+    if (isfinite(d) && isfinite(cs) && isfinite(rs)) {
+      // (fp32 tests: the centre rounds by < 2^-24 of its magnitude -- widen the half-axes by that much)
       const double slack = (fabs(cs) + fabs(rs)) * 1.2e-7;
       const double hc = sqrt(d * (-e[5]) / det) + 1.0 + slack, hr = sqrt(d * (-e[3]) / det) + 1.0 + slack;
-      o = make_float4((float)cs, (float)rs, (float)fmin(hc, 1e30), (float)fmin(hr, 1e30));
       const double c_lo = fmax(floor(cs - hc), 0.0), c_hi = fmin(ceil(cs + hc), (double)(W - 1));
       const double r_lo = fmax(floor(rs - hr), (double)row0), r_hi = fmin(ceil(rs + hr), (double)(row0 + nrows - 1));
-      if (c_hi < c_lo || r_hi < r_lo) r = make_short4(1, 0, 1, 0);
-      else
-        r = make_short4((short)((int)c_lo / BIN_TN), (short)((int)c_hi / BIN_TN), (short)(((int)r_lo - row0) / BM),
-                        (short)(((int)r_hi - row0) / BM));
+      if (c_hi < c_lo || r_hi < r_lo) return;                 // off the detector / outside these rows
+      tn_lo = (int)c_lo / BIN_TN;
+      tn_hi = (int)c_hi / BIN_TN;
+      tm_lo = ((int)r_lo - row0) / BM;
+      tm_hi = ((int)r_hi - row0) / BM;
+      cx = (float)cs;
+      cy = (float)rs;
+      hx = (float)fmin(hc, 1e30);
+      hy = (float)fmin(hr, 1e30);
     }
   }
-  fp[i] = o;
-  tr[i] = r;
+  const unsigned bit = 1u << (unsigned)(i & 31);
+  const float hh = hx * hy;
+  for (int tm = tm_lo; tm <= tm_hi; ++tm) {
+    const float r0 = (float)(row0 + tm * BM), r1 = (float)(row0 + min(tm * BM + BM - 1, nrows - 1));
+    const float dy = fmaxf(fmaxf(r0 - cy, cy - r1), 0.f) * hx;
+    for (int tn = tn_lo; tn <= tn_hi; ++tn) {
+      // closest point of the tile's pixel rectangle to the centre, inside the ellipse?
+      const float c0 = (float)(tn * BIN_TN), c1 = (float)min(tn * BIN_TN + BIN_TN - 1, W - 1);
+      const float dx = fmaxf(fmaxf(c0 - cx, cx - c1), 0.f) * hy;
+      if (dx * dx + dy * dy <= hh * hh * 1.000001f) atomicOr(hits + (long long)(tm * tiles_n + tn) * wpt + (i >> 5), bit);
+    }
+  }
 }
 
-// does the footprint meet the pixel rectangle [c0, c1] x [r0, r1]?  (closest point of the rectangle to the centre)
-__device__ __forceinline__ bool bin_hit(const float4 f, float c0, float c1, float r0, float r1) {
-  const float dx = fmaxf(fmaxf(c0 - f.x, f.x - c1), 0.f), dy = fmaxf(fmaxf(r0 - f.y, f.y - r1), 0.f);
-  const float a = dx * f.w, b = dy * f.z, c = f.z * f.w;
-  return f.z >= 0.f && a * a + b * b <= c * c * 1.000001f;
-}
-
-// One CTA per tile, warp w scans beamlets [w seg, (w + 1) seg), 8 tile ranges per lane in flight; a lane whose range
-// holds the tile tests the elliptical footprint.  FILL = false: wc[t][w] = hits of warp w, and (hits != NULL) the
-// ballot word of every group of 32 beamlets.  FILL = true: append the hits in beamlet order behind the hits of the
-// warps before -- from the ballot words, or by scanning again without them -- pad the tile's last chunk, fill c2t.
-constexpr int BIN_ILP = 8;
+// One CTA per tile; warp w owns the beamlets [w seg, (w + 1) seg) (seg a multiple of 32) = a run of the tile's words.
+// FILL = false: wc[t][w] = set bits of warp w's words.  FILL = true: the set bits ARE the tile's beamlets in order --
+// append them behind the beamlets of the warps before, pad the tile's last chunk with -1, fill c2t.
 template <bool FILL>
 __global__ void __launch_bounds__(32 * BIN_WARPS)
-    bin_tiles_kernel(long long nb, const float4 *__restrict__ fp, const short4 *__restrict__ tr, int tiles_n, int T,
-                     int row0, int nrows, int W, int *__restrict__ wc, unsigned *__restrict__ hits,
+    bin_tiles_kernel(long long nb, int T, int *__restrict__ wc, const unsigned *__restrict__ hits,
                      const int *__restrict__ bins, int *__restrict__ sel, int *__restrict__ c2t) {
   if (FILL && bins[BIN_OVERFLOW]) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long seg = (((nb + BIN_WARPS - 1) / BIN_WARPS + 31) / 32) * 32;
-  const long long b0 = (long long)warp * seg, b1 = (b0 + seg < nb) ? b0 + seg : nb;
-  const long long wpt = (nb + 31) / 32;                      // ballot words per tile
+  const long long wpt = (nb + 31) / 32;                      // words per tile
+  const long long g_lo = (long long)warp * (seg / 32), g_hi = (g_lo + seg / 32 < wpt) ? g_lo + seg / 32 : wpt;
   for (int t = blockIdx.x; t < T; t += gridDim.x) {
-    const short tm = (short)(t / tiles_n), tn = (short)(t % tiles_n);
-    const float c0 = (float)(tn * BIN_TN), c1 = (float)min(tn * BIN_TN + BIN_TN - 1, W - 1);
-    const float r0 = (float)(row0 + tm * BM), r1 = (float)(row0 + min(tm * BM + BM - 1, nrows - 1));
+    const unsigned *hw = hits + (long long)t * wpt;
     long long base = 0;
     int total = 0;
     if (FILL) {
@@ -1346,46 +1345,31 @@ __global__ void __launch_bounds__(32 * BIN_WARPS)
       }
     }
     int pos = 0;
-    if (FILL && hits) {
-      // 32 ballot words per round, one per lane; the set bits are the beamlets of this tile, in order
-      const unsigned *hw = hits + (long long)t * wpt;
-      for (long long g0 = b0 / 32; g0 < (b1 + 31) / 32; g0 += 32) {
-        const long long g = g0 + lane;
-        const unsigned mine = g < (b1 + 31) / 32 ? hw[g] : 0u;
-        unsigned any = __ballot_sync(0xffffffffu, mine != 0u);
-        while (any) {
-          const int k = __ffs(any) - 1;
-          any &= any - 1;
-          const unsigned bal = __shfl_sync(0xffffffffu, mine, k);
-          if (bal & (1u << lane)) sel[base + pos + __popc(bal & ((1u << lane) - 1u))] = (int)((g0 + k) * 32 + lane);
-          pos += __popc(bal);
-        }
-      }
-    } else {
-      for (long long i0 = b0; i0 < b1; i0 += 32 * BIN_ILP) {
-        short4 r[BIN_ILP];
+    for (long long g0 = g_lo; g0 < g_hi; g0 += 32) {
+      const long long g = g0 + lane;
+      unsigned m = g < g_hi ? hw[g] : 0u;
+      const int p = __popc(m);
+      if (!FILL) {
+        pos += p;
+      } else {
+        int incl = p;                                        // the lanes' words in order: exclusive scan of the bit counts
 #pragma unroll
-        for (int j = 0; j < BIN_ILP; ++j) {
-          const long long i = i0 + j * 32 + lane;
-          r[j] = i < b1 ? __ldg(tr + i) : make_short4(1, 0, 1, 0);
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
         }
-        float4 f[BIN_ILP];                       // (all refinement loads are issued before the first ballot needs one)
-#pragma unroll
-        for (int j = 0; j < BIN_ILP; ++j) {
-          const bool coarse = r[j].x <= tn && tn <= r[j].y && r[j].z <= tm && tm <= r[j].w;
-          f[j] = coarse ? __ldg(fp + i0 + j * 32 + lane) : make_float4(0.f, 0.f, -1.f, -1.f);
+        long long dst = base + pos + incl - p;
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          sel[dst++] = (int)(g * 32 + b);
         }
-#pragma unroll
-        for (int j = 0; j < BIN_ILP; ++j) {
-          const bool hit = bin_hit(f[j], c0, c1, r0, r1);
-          const unsigned bal = __ballot_sync(0xffffffffu, hit);
-          if (FILL && hit) sel[base + pos + __popc(bal & ((1u << lane) - 1u))] = (int)(i0 + j * 32 + lane);
-          if (!FILL && hits && lane == 0 && i0 + j * 32 < b1) hits[(long long)t * wpt + (i0 + j * 32) / 32] = bal;
-          pos += __popc(bal);
-        }
+        pos += __shfl_sync(0xffffffffu, incl, 31);
       }
     }
     if (!FILL) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) pos += __shfl_xor_sync(0xffffffffu, pos, o);
       if (lane == 0) wc[t * BIN_WARPS + warp] = pos;
     } else {
       const int *P = bins + BIN_HDR;
@@ -2524,24 +2508,25 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
 
   // ---- phase 1: table, verdicts, tile ranges, per-tile counts, prefix
   auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-  const size_t table_bytes = al((size_t)nb * 96), tr_bytes = al((size_t)nb * sizeof(float4)),
-               tr2_bytes = al((size_t)nb * sizeof(short4)), wc_bytes = al((size_t)T * BIN_WARPS * sizeof(int)),
+  const size_t table_bytes = al((size_t)nb * 96), wc_bytes = al((size_t)T * BIN_WARPS * sizeof(int)),
                bins_bytes = al((size_t)(BIN_HDR + T + 1) * sizeof(int));
-  // ballot words of the counting scan (one bit per (tile, beamlet)), reused by the fill scan when they fit 256 MiB
+  // one bit per (tile, beamlet): set by the beamlets (bin_mark_kernel), counted and expanded per tile
   const size_t hits_need = (size_t)T * (size_t)((nb + 31) / 32) * sizeof(unsigned);
-  const size_t hits_bytes = hits_need <= ((size_t)256 << 20) ? al(hits_need) : 0;
+  if (hits_need > ((size_t)1 << 30)) {
+    tg_set_error("tile-binned sum: %d tiles x %lld beamlets are more than this path handles", T, (long long)nb);
+    return TG_EUNSUPPORTED;
+  }
+  const size_t hits_bytes = al(hits_need);
   TgAsyncBuf ws1(st);
-  TG_CUDA(ws1.alloc(table_bytes + 256 + tr_bytes + tr2_bytes + wc_bytes + bins_bytes + hits_bytes));
+  TG_CUDA(ws1.alloc(table_bytes + 256 + wc_bytes + bins_bytes + hits_bytes));
   unsigned char *w1 = ws1.as<unsigned char>();
   double *table = reinterpret_cast<double *>(w1);
   unsigned long long *key = reinterpret_cast<unsigned long long *>(w1 + table_bytes);
   unsigned long long *peak = key + 1, *gref = reinterpret_cast<unsigned long long *>(w1 + table_bytes + 64);
-  float4 *tr = reinterpret_cast<float4 *>(w1 + table_bytes + 256);
-  short4 *tr2 = reinterpret_cast<short4 *>(w1 + table_bytes + 256 + tr_bytes);
-  int *wc = reinterpret_cast<int *>(w1 + table_bytes + 256 + tr_bytes + tr2_bytes);
-  int *bins = reinterpret_cast<int *>(w1 + table_bytes + 256 + tr_bytes + tr2_bytes + wc_bytes);
-  unsigned *hits = hits_bytes ? reinterpret_cast<unsigned *>(w1 + table_bytes + 256 + tr_bytes + tr2_bytes + wc_bytes + bins_bytes)
-                              : nullptr;
+  int *wc = reinterpret_cast<int *>(w1 + table_bytes + 256);
+  int *bins = reinterpret_cast<int *>(w1 + table_bytes + 256 + wc_bytes);
+  unsigned *hits = reinterpret_cast<unsigned *>(w1 + table_bytes + 256 + wc_bytes + bins_bytes);
+  TG_CUDA(cudaMemsetAsync(hits, 0, hits_bytes, st));
   TG_CUDA(cudaMemsetAsync(key, 0, 16, st));
   TG_CUDA(cudaMemsetAsync(gref, 0xFF, 8, st));
   TgPrepExtra ex;
@@ -2551,9 +2536,8 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   ex.nrows = nrows;
   rc = tg_launch_prep(nb, poly, px2m, H, W, table, gref, st, &ex);
   if (rc != TG_OK) return rc;
-  bin_ranges_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, table, H, W, row0, nrows, gref, cull_bits, tr, tr2);
-  bin_tiles_kernel<false><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, tr, tr2, tiles_n, T, row0, nrows, W, wc, hits,
-                                                                      nullptr, nullptr, nullptr);
+  bin_mark_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, table, H, W, row0, nrows, tiles_n, gref, cull_bits, hits);
+  bin_tiles_kernel<false><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, T, wc, hits, nullptr, nullptr, nullptr);
   rc = tg_launch_check("bin_tiles_kernel");
   if (rc != TG_OK) return rc;
   int cap = 0;
@@ -2616,8 +2600,7 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   double *acc = out_is_c128 ? static_cast<double *>(out) : reinterpret_cast<double *>(Blo + op_bytes + cnt_bytes + part_bytes);
   TG_CUDA(cudaMemsetAsync(counters, 0, cnt_bytes, st));
   const unsigned long long *guard = capturing ? key : nullptr;          // under capture the verdict stays on the device
-  bin_tiles_kernel<true><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, tr, tr2, tiles_n, T, row0, nrows, W, wc, hits, bins,
-                                                                     sel, c2t);
+  bin_tiles_kernel<true><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, T, wc, hits, bins, sel, c2t);
   const unsigned gf = bounded_grid((long long)cap * (BM / FS));
   factor_rows_binned_kernel<true><<<gf, BIN_SLOTS, 0, st>>>(table, bins, sel, c2t, tiles_n, row0, nrows, W, capK, Ahi, Alo,
                                                             peak, guard);
