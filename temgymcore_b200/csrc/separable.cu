@@ -1256,7 +1256,7 @@ __global__ void __launch_bounds__(256)
 //     CTA of the ragged GEMM schedule, the overflow verdict against the operand capacity;
 //   * bin_tiles_kernel<true>: the set bits expanded IN BEAMLET ORDER (deterministic sums) into the tile's slots
 //     sel[P[t] * 128 ...], padded with -1 to whole chunks; chunk -> tile map c2t;
-//   * factor_*_binned_kernel: row / column factors of slot s for the 128 rows / 64 columns of ITS tile, on one
+//   * factor_binned_kernel: row / column factors of slot s for the 128 rows / 64 columns of ITS tile, on one
 //     concatenated k axis (chunk g at k = 256 g), stored k-block by k-block: each 128-row x 64-k tile of an operand is
 //     16 KiB of contiguous memory, so the factor kernels write and the GEMM's TMA loads read whole DRAM pages;
 //   * gemm_x3_kernel with the ragged schedule (SkSched::bins): 148 CTAs split the chunk axis evenly, tiles cut by a CTA
@@ -1427,78 +1427,71 @@ __global__ void __launch_bounds__(1024)
     for (int t = threadIdx.x; t < T; t += 1024) P[t] = 0;
 }
 
-// A[(row in tile)][2 s, 2 s + 1] = U_n(row), n = sel[s], for the 128 rows of the tile that owns slot s
+// One CTA per operand chunk (128 slots), one thread per slot s, n = sel[s]: the beamlet's table entry is read once, then
+//   A[k-block s / 32][row][2 (s % 32) ..]       = U_n(row)                for the 128 rows of the chunk's tile,
+//   B[k-block s / 32][2 c][..] = (Re V, -Im V),  B[..][2 c + 1][..] = (Im V, Re V)   for its 64 columns c
+// in strips of 32 (fp64 strip setup, fp32 recurrences: the dense factor kernels' arithmetic), each value split into
+// fp16 hi + lo as one packed pair.  Rows and columns in ONE kernel: the row strips are issue-bound, the column strips
+// (four stores per value) write-bound, and CTAs in different phases overlap the two (separate kernels: 257 + 218 us).
+// Tiled layout: k-block kb of an operand holds rows [0, 128) x 64 k-elements contiguously (16 KiB).
 template <bool F16>
 __global__ void __launch_bounds__(BIN_SLOTS)
-    factor_rows_binned_kernel(const double *__restrict__ table, const int *__restrict__ bins, const int *__restrict__ sel,
-                              const int *__restrict__ c2t, int tiles_n, int row0, int M, int W, long long ldk,
-                              void *__restrict__ Ahi, void *__restrict__ Alo,
-                              const unsigned long long *__restrict__ peak_key,
-                              const unsigned long long *__restrict__ sep_guard) {
+    factor_binned_kernel(const double *__restrict__ table, const int *__restrict__ bins, const int *__restrict__ sel,
+                         const int *__restrict__ c2t, int tiles_n, int row0, int M, int W, void *__restrict__ Ahi,
+                         void *__restrict__ Alo, void *__restrict__ Bhi, void *__restrict__ Blo,
+                         const unsigned long long *__restrict__ peak_key,
+                         const unsigned long long *__restrict__ sep_guard) {
+  static_assert(F16, "the tile-binned sum uses fp16 x 3 operands");
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
-  constexpr int NS = BM / FS;
-  const long long items = (long long)bins[BIN_CTOT] * NS;
-  for (long long vb = blockIdx.x; vb < items; vb += gridDim.x) {
-    const int g = (int)(vb / NS), sidx = (int)(vb % NS);
+  const int ctot = bins[BIN_CTOT];
+  const double G = tg_prescale_G(*peak_key);
+  for (int g = blockIdx.x; g < ctot; g += gridDim.x) {
     const long long s = (long long)g * BIN_SLOTS + threadIdx.x;
     const int n = sel[s];
-    const int m0 = (c2t[g] / tiles_n) * BM + sidx * FS;      // first row of the strip, relative to row0
-    Strip1D st = {};
-    if (n >= 0) {
-      const double *t = table + (long long)n * 12;
-      double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
-      mu += Headroom<F16>::value - tg_prescale_G(*peak_key);
-      st = strip_setup(t[0], t[2], t[5], t[6 + 0] + mu, t[6 + 2], t[6 + 5], (double)(row0 + m0));
-    }
+    const int tile = c2t[g], tm = tile / tiles_n, tn = tile - tm * tiles_n;
+    double t[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) t[i] = n >= 0 ? __ldg(table + (long long)n * 12 + i) : 0.0;
+    const double cm = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1));
+    const long long kb_rows = (s >> 5) * BM;              // first row of the slot's k-block in the tiled operands
+    const int kk = 2 * (int)(s & 31);
+#pragma unroll 1
+    for (int sidx = 0; sidx < BM / FS; ++sidx) {
+      const int m0 = tm * BM + sidx * FS;                 // first row of the strip, relative to row0
+      const Strip1D st = strip_setup(t[0], t[2], t[5], t[6 + 0] + cm + Headroom<F16>::value - G, t[6 + 2], t[6 + 5],
+                                     (double)(row0 + m0));
 #pragma unroll 4
-    for (int j = 0; j < FS; ++j) {
-      float re = 0.f, im = 0.f;
-      if (n >= 0 && m0 + j < M) strip_eval(st, j, re, im);
-      // (re, im) split as one packed pair: hi = fp16(x), lo = fp16(x - hi) -- the values Operand<true>::split gives
-      const __half2 hi = __floats2half2_rn(re, im);
-      const float2 hf = __half22float2(hi);
-      const __half2 lo = __floats2half2_rn(re - hf.x, im - hf.y);
-      // tiled layout: k-block s / 32 holds rows [0, 128) x 64 k-elements contiguously
-      const long long o = ((s >> 5) * BM + (sidx * FS + j)) * 64 + 2 * (s & 31);
-      *reinterpret_cast<__half2 *>(static_cast<__half *>(Ahi) + o) = hi;
-      *reinterpret_cast<__half2 *>(static_cast<__half *>(Alo) + o) = lo;
+      for (int j = 0; j < FS; ++j) {
+        float re = 0.f, im = 0.f;
+        if (n >= 0 && m0 + j < M) strip_eval(st, j, re, im);
+        // (re, im) split as one packed pair: hi = fp16(x), lo = fp16(x - hi) -- the values Operand<true>::split gives
+        const __half2 hi = __floats2half2_rn(re, im);
+        const float2 hf = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(re - hf.x, im - hf.y);
+        const long long o = (kb_rows + (sidx * FS + j)) * 64 + kk;
+        *reinterpret_cast<__half2 *>(static_cast<__half *>(Ahi) + o) = hi;
+        *reinterpret_cast<__half2 *>(static_cast<__half *>(Alo) + o) = lo;
+      }
     }
-  }
-}
-// B[2 c][2 s..] = (Re V, -Im V), B[2 c + 1][2 s..] = (Im V, Re V) for the 64 columns c of the tile that owns slot s
-template <bool F16>
-__global__ void __launch_bounds__(BIN_SLOTS)
-    factor_cols_binned_kernel(const double *__restrict__ table, const int *__restrict__ bins, const int *__restrict__ sel,
-                              const int *__restrict__ c2t, int tiles_n, int W, long long ldk, void *__restrict__ Bhi,
-                              void *__restrict__ Blo, const unsigned long long *__restrict__ sep_guard) {
-  if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
-  constexpr int NS = BIN_TN / FS;
-  const long long items = (long long)bins[BIN_CTOT] * NS;
-  for (long long vb = blockIdx.x; vb < items; vb += gridDim.x) {
-    const int g = (int)(vb / NS), sidx = (int)(vb % NS);
-    const long long s = (long long)g * BIN_SLOTS + threadIdx.x;
-    const int n = sel[s];
-    const int c0 = (c2t[g] % tiles_n) * BIN_TN + sidx * FS;
-    Strip1D st = {};
-    if (n >= 0) {
-      const double *t = table + (long long)n * 12;
-      const double mu = tg_col_env_max(t[6 + 1], t[6 + 3], (double)(W - 1)) - Headroom<F16>::value;
-      st = strip_setup(0.0, t[1], t[3], -mu, t[6 + 1], t[6 + 3], (double)c0);
-    }
+#pragma unroll 1
+    for (int sidx = 0; sidx < BIN_TN / FS; ++sidx) {
+      const int c0 = tn * BIN_TN + sidx * FS;
+      const Strip1D st = strip_setup(0.0, t[1], t[3], Headroom<F16>::value - cm, t[6 + 1], t[6 + 3], (double)c0);
 #pragma unroll 4
-    for (int j = 0; j < FS; ++j) {
-      float re = 0.f, im = 0.f;
-      if (n >= 0 && c0 + j < W) strip_eval(st, j, re, im);
-      const __half2 hi = __floats2half2_rn(re, im);
-      const float2 hf = __half22float2(hi);
-      const __half2 lo = __floats2half2_rn(re - hf.x, im - hf.y);
-      // row 2 c: (Re, -Im) = the pair with the sign bit of its upper half flipped; row 2 c + 1: (Im, Re) = the halves swapped
-      const unsigned hb = *reinterpret_cast<const unsigned *>(&hi), lb = *reinterpret_cast<const unsigned *>(&lo);
-      const long long o0 = ((s >> 5) * BN + 2 * (sidx * FS + j)) * 64 + 2 * (s & 31), o1 = o0 + 64;
-      *reinterpret_cast<unsigned *>(static_cast<__half *>(Bhi) + o0) = hb ^ 0x80000000u;
-      *reinterpret_cast<unsigned *>(static_cast<__half *>(Blo) + o0) = lb ^ 0x80000000u;
-      *reinterpret_cast<unsigned *>(static_cast<__half *>(Bhi) + o1) = __byte_perm(hb, 0, 0x1032);
-      *reinterpret_cast<unsigned *>(static_cast<__half *>(Blo) + o1) = __byte_perm(lb, 0, 0x1032);
+      for (int j = 0; j < FS; ++j) {
+        float re = 0.f, im = 0.f;
+        if (n >= 0 && c0 + j < W) strip_eval(st, j, re, im);
+        const __half2 hi = __floats2half2_rn(re, im);
+        const float2 hf = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(re - hf.x, im - hf.y);
+        // row 2 c: (Re, -Im) = the pair with the sign bit of its upper half flipped; row 2 c + 1: (Im, Re) = halves swapped
+        const unsigned hb = *reinterpret_cast<const unsigned *>(&hi), lb = *reinterpret_cast<const unsigned *>(&lo);
+        const long long o0 = (kb_rows + 2 * (sidx * FS + j)) * 64 + kk, o1 = o0 + 64;
+        *reinterpret_cast<unsigned *>(static_cast<__half *>(Bhi) + o0) = hb ^ 0x80000000u;
+        *reinterpret_cast<unsigned *>(static_cast<__half *>(Blo) + o0) = lb ^ 0x80000000u;
+        *reinterpret_cast<unsigned *>(static_cast<__half *>(Bhi) + o1) = __byte_perm(hb, 0, 0x1032);
+        *reinterpret_cast<unsigned *>(static_cast<__half *>(Blo) + o1) = __byte_perm(lb, 0, 0x1032);
+      }
     }
   }
 }
@@ -2601,10 +2594,8 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   TG_CUDA(cudaMemsetAsync(counters, 0, cnt_bytes, st));
   const unsigned long long *guard = capturing ? key : nullptr;          // under capture the verdict stays on the device
   bin_tiles_kernel<true><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, T, wc, hits, bins, sel, c2t);
-  const unsigned gf = bounded_grid((long long)cap * (BM / FS));
-  factor_rows_binned_kernel<true><<<gf, BIN_SLOTS, 0, st>>>(table, bins, sel, c2t, tiles_n, row0, nrows, W, capK, Ahi, Alo,
-                                                            peak, guard);
-  factor_cols_binned_kernel<true><<<gf, BIN_SLOTS, 0, st>>>(table, bins, sel, c2t, tiles_n, W, capK, Bhi, Blo, guard);
+  factor_binned_kernel<true><<<bounded_grid(cap), BIN_SLOTS, 0, st>>>(table, bins, sel, c2t, tiles_n, row0, nrows, W, Ahi, Alo,
+                                                                      Bhi, Blo, peak, guard);
   rc = tg_launch_check("binned factor kernels");
   if (rc != TG_OK) return rc;
   CUtensorMap ta, tb, tc, td;
