@@ -1516,6 +1516,19 @@ __global__ void __launch_bounds__(256)
     }
   }
 }
+// Row-sharded multi-GPU sum: this rank's finished rows go into every peer's image as whole 512-byte warp stores over
+// NVLink.  (The dense GEMM's epilogue stores its tiles to the peers itself, 16 bytes per lane a detector row apart: fine
+// for the 2 MB of a C2 shard, but the 59 MB a C3 shard sends to seven peers took longer than the sum -- measured 0.64 ms
+// per image at N = 8 against 0.67 ms at N = 2.)
+__global__ void __launch_bounds__(256)
+    peer_push_kernel(const double2 *__restrict__ src, size_t n, const TgPeers peers,
+                     const unsigned long long *__restrict__ sep_guard) {
+  if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double2 v = src[i];
+    for (int p = 0; p < peers.n; ++p) static_cast<double2 *>(peers.ptr[p])[i] = v;
+  }
+}
 // capacity overflow (a captured graph replayed on beamlets that need more operand chunks than it was built for) or a
 // non-separable input under capture: poison the output instead of returning a partial sum
 __global__ void __launch_bounds__(256)
@@ -2622,13 +2635,20 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   sc.prefetch = bin_pf;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
   TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TgPeers gp = out_is_c128 ? pe : none;                                 // complex64 peers are written by the conversion
+  // peers: complex64 images are written by the conversion kernel, complex128 ones by peer_push_kernel below
+  const TgPeers &gp = none;
   bin_zero_empty_kernel<<<bounded_grid(T), 256, 0, st>>>(bins, T, tiles_n, nrows, 2 * W, acc, (long long)(2 * W), gp, guard);
   gemm_x3_kernel<true, false, true><<<(unsigned)sms, GEMM_THREADS, smem, st>>>(
       ta, tb, tc, td, nrows, 2 * W, (int)(capK < 0x7fffffffLL ? capK : 0x7fffffffLL), acc, (long long)(2 * W), 0, peak,
       Headroom<true>::value, guard, gp, sc, parts, counters, nullptr, nullptr, 0u);
   rc = tg_launch_check("gemm_x3_kernel<f16> (tile-binned)");
   if (rc != TG_OK) return rc;
+  if (out_is_c128 && pe.n > 0) {
+    peer_push_kernel<<<bounded_grid((long long)((npix + 255) / 256)), 256, 0, st>>>(reinterpret_cast<const double2 *>(acc), npix,
+                                                                                 pe, guard);
+    rc = tg_launch_check("peer_push_kernel");
+    if (rc != TG_OK) return rc;
+  }
   if (!out_is_c128) {
     const size_t n = npix * 2;
     f64_to_c64_kernel<<<bounded_grid((long long)((n + 255) / 256)), 256, 0, st>>>(acc, static_cast<float *>(out), n, guard, pe);
