@@ -540,8 +540,32 @@ def run_ours(args):
     e2e_ms = max_over_ranks(float(np.sum(et))) / args.steps
     h2d = C2_NB * 8 * (7 + 1 + 2 + 2 + 1 + 1)
     d2h = H * W * 16
+    # the PCIe floor of that step on this box: a plain pinned D2H of the image bytes (and H2D of the input bytes), nothing
+    # else, on every rank at the same time -- what the host's PCIe / memory system gives N concurrent streams
+    hraw = torch.empty(d2h, dtype=torch.uint8, pin_memory=True)
+    draw = torch.empty(d2h, dtype=torch.uint8, device=dev)
+
+    def raw_copy(nbytes_h2d):
+        if nbytes_h2d:
+            draw[:nbytes_h2d].copy_(hraw[:nbytes_h2d], non_blocking=True)
+        hraw.copy_(draw, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    for _ in range(3):
+        raw_copy(h2d)
+    rt = []
+    for _ in range(max(5, args.steps)):
+        barrier()
+        t0 = time.perf_counter()
+        raw_copy(h2d)
+        rt.append((time.perf_counter() - t0) * 1e3)
+    raw_ms = max_over_ranks(float(np.median(rt)))
+    del hraw, draw
     e2e = {"value": evals_per_step / (e2e_ms * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+           "pcie_floor": {"ms": raw_ms, "GBps_per_rank": (h2d + d2h) / (raw_ms * 1e-3) / 1e9,
+                          "what": "cudaMemcpyAsync of the step's input bytes (H2D) and image bytes (D2H) from / to pinned "
+                                  "memory and one stream synchronise, on all ranks at once, max over ranks: the part of "
+                                  "ms_per_step that no kernel can shorten"},
            "api": "make_gaussian_image(host GaussianRay) -> tg_make_gaussian_image_host: one packed H2D, kernels, "
                   "row-block D2H overlapped with the following blocks; timed with the host wall clock around the "
                   "synchronous call (Python + ctypes included)"}

@@ -51,6 +51,19 @@ def sec_field():
     assert rel_l2(make_gaussian_image_device(to_cuda(g), model, method="sfu").cpu().numpy(), ref) < 1e-5
 
 
+def sec_binned():
+    # tile-binned sum: atomicOr bitmaps, ordered expansion, ragged stream-K schedule (partial tiles through scratch slots
+    # + arrival counters), tiled operands; 900 narrow beamlets on 3 x 7 tiles, and a row block
+    from temgymcore_b200.gaussian import _field_sum_grid, beamlet_polynomials
+    g, model = M.biprism_case(900, (300, 416), fov=3 * 1024 * 55e-6 / 2)
+    poly, n, dev = beamlet_polynomials(to_cuda(g), model)
+    dense = _field_sum_grid(poly, n, model[-1], dev, cull_bits=0, method="sfu").cpu().numpy()
+    got = _field_sum_grid(poly, n, model[-1], dev, cull_bits=40, method="tensor_binned").cpu().numpy()
+    assert rel_l2(got, dense) < 3e-6
+    rows = _field_sum_grid(poly, n, model[-1], dev, cull_bits=40, method="tensor_binned", row0=70, nrows=200).cpu().numpy()
+    assert rel_l2(rows, dense[70:270]) < 3e-6
+
+
 def sec_stem4d():
     from temgymcore_b200.stem4d import backproject_4dstem, system_geometry
     fn, sg, det = M.stem4d_case((8, 6), (64, 48))
@@ -103,7 +116,7 @@ def sec_peer():
         assert rel_l2(pimg.image.cpu().numpy(), O.make_gaussian_image(g, model)) < 1e-5
 
 
-SECTIONS = {"gemm": sec_gemm, "field": sec_field, "stem4d": sec_stem4d, "trace": sec_trace, "jets": sec_jets,
+SECTIONS = {"gemm": sec_gemm, "field": sec_field, "binned": sec_binned, "stem4d": sec_stem4d, "trace": sec_trace, "jets": sec_jets,
             "peer": sec_peer}
 
 if __name__ == "__main__":

@@ -1434,6 +1434,22 @@ def test_tensor_binned_auto_and_plan(torch_cuda, monkeypatch):
     assert np.isnan(out3).all() or rel_l2(out3, ok) < 3e-6
 
 
+def test_tensor_binned_host_pipeline(torch_cuda):
+    """Host-buffer call (tg_make_gaussian_image_host): `auto` reads the verdicts on the host there whatever the beamlet
+    count, so sparse separable beamlets take the tile-binned sum and the image comes back as one emitted block."""
+    from temgymcore_b200.gaussian import make_gaussian_image_device, make_gaussian_image_host, pack_beamlets_pinned
+    g, model = M.biprism_case(6000, (1024, 1024), fov=2 * 1024 * 55e-6 / 2)
+    ref = to_np(make_gaussian_image_device(gaussian_to_cuda(torch_cuda, g), model, method="sfu"))
+    gp = pack_beamlets_pinned(g)
+    for method in ("tensor_binned", "auto"):
+        host = to_np(make_gaussian_image_host(gp, model, method=method))
+        assert host.shape == (1024, 1024) and rel_l2(host, ref) < 3e-6, (method, rel_l2(host, ref))
+    part = to_np(make_gaussian_image_host(gp, model, method="tensor_binned", row0=200, nrows=300))
+    assert rel_l2(part, ref[200:500]) < 3e-6
+    c64 = to_np(make_gaussian_image_host(gp, model, method="tensor_binned", out_dtype=torch_cuda.complex64))
+    assert c64.dtype == np.complex64 and rel_l2(c64, ref) < 4e-6
+
+
 # ------------------------------------------------------------------------------ peer-memory field sum
 @pytest.mark.parametrize("method,dtype_name", [("sfu", "complex128"), ("tensor", "complex128"), ("auto", "complex128"),
                                                ("tensor", "complex64"), ("sfu", "complex64")])
