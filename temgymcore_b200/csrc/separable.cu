@@ -1271,11 +1271,18 @@ constexpr int BIN_WARPS = 8;
 // half-axes; separable beamlets have no cross term to speak of; same threshold as field.cu's bbox_kernel), then every
 // tile of its bounding box whose pixel rectangle the ellipse meets gets bit (i mod 32) of word hits[t][i / 32] set.
 // Non-concave or non-finite envelopes mark every tile, so NaN beamlets poison the image as in the dense sum.
+// probe mode (TG_BIN_PROBE): ctl[0] = separability key, ctl[BIN_CTL_SPLIT] = 1 when the cost model found the beamlets
+// sparse; the binning kernels of a call that AUTO will hand to another path return at once
+constexpr int BIN_CTL_SPLIT = 9;
+__device__ __forceinline__ bool bin_probe_skip(const unsigned long long *ctl) {
+  return ctl && (!tg_key_is_separable(ctl[0]) || ctl[BIN_CTL_SPLIT] == 0ULL);
+}
 __global__ void __launch_bounds__(256)
     bin_mark_kernel(long long nb, const double *__restrict__ table, int H, int W, int row0, int nrows, int tiles_n,
-                    const unsigned long long *__restrict__ gref_key, int cull_bits, unsigned *__restrict__ hits) {
+                    const unsigned long long *__restrict__ gref_key, int cull_bits, unsigned *__restrict__ hits,
+                    const unsigned long long *__restrict__ probe) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nb) return;
+  if (i >= nb || bin_probe_skip(probe)) return;
   const long long wpt = (nb + 31) / 32;
   int tn_lo = 0, tn_hi = (W - 1) / BIN_TN, tm_lo = 0, tm_hi = (nrows - 1) / BM;
   float cx = 0.f, cy = 0.f, hx = 1e30f, hy = 1e30f;
@@ -1325,8 +1332,10 @@ __global__ void __launch_bounds__(256)
 template <bool FILL>
 __global__ void __launch_bounds__(32 * BIN_WARPS)
     bin_tiles_kernel(long long nb, int T, int *__restrict__ wc, const unsigned *__restrict__ hits,
-                     const int *__restrict__ bins, int *__restrict__ sel, int *__restrict__ c2t) {
+                     const int *__restrict__ bins, int *__restrict__ sel, int *__restrict__ c2t,
+                     const unsigned long long *__restrict__ probe) {
   if (FILL && bins[BIN_OVERFLOW]) return;
+  if (bin_probe_skip(probe)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long seg = (((nb + BIN_WARPS - 1) / BIN_WARPS + 31) / 32) * 32;
   const long long wpt = (nb + 31) / 32;                      // words per tile
@@ -1384,7 +1393,9 @@ __global__ void __launch_bounds__(32 * BIN_WARPS)
 
 // P[t] = chunks before tile t; bins header: total chunks (0 on overflow), chunks per GEMM CTA, overflow flag, chunks needed
 __global__ void __launch_bounds__(1024)
-    bin_prefix_kernel(int T, const int *__restrict__ wc, int *__restrict__ bins, int G, int cap_chunks) {
+    bin_prefix_kernel(int T, const int *__restrict__ wc, int *__restrict__ bins, int G, int cap_chunks,
+                      const unsigned long long *__restrict__ probe) {
+  if (bin_probe_skip(probe)) return;
   __shared__ long long wsum[32];
   __shared__ long long carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -2072,6 +2083,14 @@ void sk_need_for_call(int64_t nb, int nrows, int block_rows, int W, int sms, siz
 // tiles, split in 4) 0.111 against 0.119 ms; on smaller row blocks and shards the 4-multiplication form wins (256 rows
 // 0.080 vs 0.088 ms, 128 rows 0.059 vs 0.090 ms).  Hence: 3-product from 32 complex tiles on.  TG_TENSOR_GAUSS=0 / 1
 // forces one form for every shape; TG_METHOD_TENSOR_3M / _4M select explicitly.
+double sfu_wins_ratio() {                        // tuning knob: TG_SFU_WINS_BELOW overrides the constant
+  static const double v = [] {
+    const char *e = getenv("TG_SFU_WINS_BELOW");
+    const double x = e ? atof(e) : kSfuWinsBelow;
+    return (x >= 0.0 && x <= 1.0) ? x : kSfuWinsBelow;
+  }();
+  return v;
+}
 // TG_TENSOR_BINNED=0: AUTO never takes the tile-binned sum (sparse separable beamlets go to the culled SFU kernel as
 // before) -- for A/B measurements.  Read on every call.
 bool binned_enabled() {
@@ -2378,11 +2397,7 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   if (rc != TG_OK) return rc;
   if (cost) {
     sfu_cost_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(table, nb, H, W, gref, cost_cull_bits, est);
-    static const double sfu_wins_below = [] {       // tuning knob: TG_SFU_WINS_BELOW overrides the constant
-      const char *e = getenv("TG_SFU_WINS_BELOW");
-      const double v = e ? atof(e) : kSfuWinsBelow;
-      return (v >= 0.0 && v <= 1.0) ? v : kSfuWinsBelow;
-    }();
+    const double sfu_wins_below = sfu_wins_ratio();
     verdict_kernel<<<1, 1, 0, st>>>(key, est, (double)nb * (double)H * (double)W, sfu_wins_below,
                                     (flags & TG_SEP_VERDICT_SPLIT) ? key + 1 : nullptr);
     rc = tg_launch_check("cost kernels");
@@ -2482,7 +2497,8 @@ BinCapKey *bin_cap_slot(long long nb, int H, int W, int row0, int nrows, int cul
 
 int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0, int nrows,
                             void *out, int out_is_c128, int cull_bits, cudaStream_t st, const TgPeers *peers,
-                            const TgEmit *emit, int flags) {
+                            const TgEmit *emit, int flags, int *probe_verdict) {
+  if (probe_verdict) *probe_verdict = -1;
   TG_REQUIRE(nb >= 0 && H > 0 && W > 0, "bad shape");
   TG_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "bad row range");
   TG_REQUIRE(px2m && out, "null pointer");
@@ -2513,6 +2529,8 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   int rc = device_sms(&sms);
   if (rc != TG_OK) return rc;
   const bool capturing = tg_stream_is_capturing(st);
+  const bool probing = (flags & TG_BIN_PROBE) != 0;
+  TG_REQUIRE(!probing || (!capturing && probe_verdict), "the probe reads its verdicts on the host: eager calls only");
 
   // ---- phase 1: table, verdicts, tile ranges, per-tile counts, prefix
   auto al = [](size_t b) { return (b + 255) / 256 * 256; };
@@ -2544,20 +2562,44 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   ex.nrows = nrows;
   rc = tg_launch_prep(nb, poly, px2m, H, W, table, gref, st, &ex);
   if (rc != TG_OK) return rc;
-  bin_mark_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, table, H, W, row0, nrows, tiles_n, gref, cull_bits, hits);
-  bin_tiles_kernel<false><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, T, wc, hits, nullptr, nullptr, nullptr);
+  const unsigned long long *probe = nullptr;
+  if (probing) {
+    // AUTO's cost verdict (see sfu_cost_kernel), kept apart from the separability key: ctl[BIN_CTL_SPLIT] = 1 if sparse
+    double *est = reinterpret_cast<double *>(w1 + table_bytes + 128);
+    TG_CUDA(cudaMemsetAsync(w1 + table_bytes + 8 * BIN_CTL_SPLIT, 0, 8, st));
+    TG_CUDA(cudaMemsetAsync(est, 0, 8, st));
+    TG_CUDA(cudaMemsetAsync(bins, 0, BIN_HDR * sizeof(int), st));
+    sfu_cost_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(table, nb, H, W, gref, cull_bits, est);
+    verdict_kernel<<<1, 1, 0, st>>>(key, est, (double)nb * (double)H * (double)W, sfu_wins_ratio(), key + BIN_CTL_SPLIT);
+    probe = key;
+  }
+  bin_mark_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(nb, table, H, W, row0, nrows, tiles_n, gref, cull_bits, hits,
+                                                                probe);
+  bin_tiles_kernel<false><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, T, wc, hits, nullptr, nullptr, nullptr, probe);
   rc = tg_launch_check("bin_tiles_kernel");
   if (rc != TG_OK) return rc;
   int cap = 0;
   if (!capturing) {
-    bin_prefix_kernel<<<1, 1024, 0, st>>>(T, wc, bins, sms, 0x7fffffff);
+    bin_prefix_kernel<<<1, 1024, 0, st>>>(T, wc, bins, sms, 0x7fffffff, probe);
     rc = tg_launch_check("bin_prefix_kernel");
     if (rc != TG_OK) return rc;
     int hdr[BIN_HDR];
-    unsigned long long hkey = 0;
+    unsigned long long hctl[BIN_CTL_SPLIT + 1];
     TG_CUDA(cudaMemcpyAsync(hdr, bins, sizeof(hdr), cudaMemcpyDeviceToHost, st));
-    TG_CUDA(cudaMemcpyAsync(&hkey, key, 8, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaMemcpyAsync(hctl, key, sizeof(hctl), cudaMemcpyDeviceToHost, st));
     TG_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long hkey = hctl[0];
+    if (probing) {
+      if (!tg_key_is_separable(hkey)) {
+        *probe_verdict = 0;
+        return TG_NOT_BINNED;
+      }
+      if (hctl[BIN_CTL_SPLIT] == 0ULL) {
+        *probe_verdict = 1;
+        return TG_NOT_BINNED;
+      }
+      *probe_verdict = 2;
+    }
     if (!(flags & TG_SEP_TRUSTED) && !tg_key_is_separable(hkey)) {
       double worst;
       memcpy(&worst, &hkey, 8);
@@ -2576,7 +2618,7 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
     }
     const long long c = (long long)k->need + k->need / 4 + 64;
     cap = (int)(c < kBinMaxChunks ? c : kBinMaxChunks);
-    bin_prefix_kernel<<<1, 1024, 0, st>>>(T, wc, bins, sms, cap);
+    bin_prefix_kernel<<<1, 1024, 0, st>>>(T, wc, bins, sms, cap, nullptr);
     rc = tg_launch_check("bin_prefix_kernel");
     if (rc != TG_OK) return rc;
   }
@@ -2608,7 +2650,7 @@ int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6]
   double *acc = out_is_c128 ? static_cast<double *>(out) : reinterpret_cast<double *>(Blo + op_bytes + cnt_bytes + part_bytes);
   TG_CUDA(cudaMemsetAsync(counters, 0, cnt_bytes, st));
   const unsigned long long *guard = capturing ? key : nullptr;          // under capture the verdict stays on the device
-  bin_tiles_kernel<true><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, T, wc, hits, bins, sel, c2t);
+  bin_tiles_kernel<true><<<bounded_grid(T), 32 * BIN_WARPS, 0, st>>>(nb, T, wc, hits, bins, sel, c2t, nullptr);
   factor_binned_kernel<true><<<bounded_grid(cap), BIN_SLOTS, 0, st>>>(table, bins, sel, c2t, tiles_n, row0, nrows, W, Ahi, Alo,
                                                                       Bhi, Blo, peak, guard);
   rc = tg_launch_check("binned factor kernels");
@@ -2727,6 +2769,21 @@ int tg_field_sum_impl(int64_t nb, const double *poly, const double px2m[6], int 
   // and exit (7 batches x {two factor grids of ~10^4 CTAs, GEMM} at C3: ~0.3 ms of dead launches, measured as the
   // gap between `auto` and the explicit method), which costs far more than reading 8 bytes back once.
   const bool host_verdict = emit != nullptr || (nb > kBatch && !tg_stream_is_capturing(st));
+  if (host_verdict && cull_bits > 0 && binned_enabled()) {
+    // one read-back for both verdicts and, when they say "separable and sparse", the operand count of the tile-binned
+    // sum, which then simply goes on (TG_BIN_PROBE); the SFU kernel remains the fallback when its operands would not fit
+    int verdict = -1;
+    int rc = tg_separable_binned_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, st, peers, emit,
+                                     TG_BIN_PROBE, &verdict);
+    if (rc != TG_NOT_BINNED && !(rc == TG_EUNSUPPORTED && verdict != 1)) return rc;     // done, or a real error
+    if (rc == TG_NOT_BINNED && verdict == 1)
+      return tg_separable_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, nullptr, st, 0, 1, peers, emit,
+                              TG_SEP_TRUSTED);
+    if (rc == TG_NOT_BINNED || verdict == 2)             // not separable, or sparse but over the capacity limit
+      return tg_field_grid_run(nb, poly, px2m, H, W, row0, nrows, out, out_is_c128, cull_bits, nullptr, nullptr, st,
+                               peers, emit);
+    // (TG_EUNSUPPORTED before any verdict: a shape the binned path does not take -- the two-step flow below decides)
+  }
   if (host_verdict) {
     // (host-buffer pipeline: the call is synchronous anyway; only the path that applies is enqueued -- block by
     // block, each block's D2H behind its own event)

@@ -51,6 +51,10 @@ struct TgEmit {
 #define TG_SEP_VERDICT_ONLY 1 /* tg_separable_run: table + separability / cost verdict into *key_async, nothing else */
 #define TG_SEP_TRUSTED 2      /* tg_separable_run: the caller has read the verdict; skip the host-side check */
 #define TG_SEP_VERDICT_SPLIT 4 /* verdict-only: key_async[0] = separability, key_async[1] = 1 when the beamlets are sparse */
+#define TG_BIN_PROBE 8         /* tg_separable_binned_run (eager calls): also form AUTO's verdicts (separable? sparse?)
+                                 and go on only when both hold -- one host read-back for the verdicts AND the operand
+                                 count.  Otherwise returns TG_NOT_BINNED with *probe_verdict = 1 (dense GEMM) or 0 (SFU) */
+#define TG_NOT_BINNED 1       /* internal return code of the probe, not an error */
 
 // stream-ordered scratch allocation, released (stream-ordered) when the scope ends -- also on error returns
 struct TgAsyncBuf {
@@ -107,7 +111,8 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
 // the same shape (plans warm up eagerly), and beamlets that need more poison the output with NaN.
 int tg_separable_binned_run(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0, int nrows,
                             void *out, int out_is_c128, int cull_bits, cudaStream_t stream,
-                            const TgPeers *peers = nullptr, const TgEmit *emit = nullptr, int flags = 0);
+                            const TgPeers *peers = nullptr, const TgEmit *emit = nullptr, int flags = 0,
+                            int *probe_verdict = nullptr);
 int tg_field_sum_impl(int64_t nb, const double *poly, const double px2m[6], int H, int W, int row0, int nrows,
                       void *out, int out_is_c128, int cull_bits, int method, cudaStream_t st, const TgPeers *peers,
                       const TgEmit *emit = nullptr);

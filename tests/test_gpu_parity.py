@@ -1415,6 +1415,16 @@ def test_tensor_binned_auto_and_plan(torch_cuda, monkeypatch):
     sfu = make_gaussian_image_device(gd, model, method="sfu")
     assert torch_cuda.equal(auto, binned)
     assert rel_l2(to_np(binned), to_np(sfu)) < 3e-6
+    # the same probe when its verdicts send the call elsewhere: beamlets that cover the detector -> dense GEMM,
+    # beamlets with a cross term -> SFU kernel (more than one GEMM batch of them, so that the host reads the verdicts)
+    gw, model_w = M.aperture_diffraction_case(17_000, (256, 192))
+    gwd = gaussian_to_cuda(torch_cuda, gw)
+    assert auto_dispatch(gwd, model_w) == "tensor"
+    assert torch_cuda.equal(make_gaussian_image_device(gwd, model_w), make_gaussian_image_device(gwd, model_w, method="tensor"))
+    gg, model_g = M.biprism_case(17_000, (160, 200), general=True)
+    ggd = gaussian_to_cuda(torch_cuda, gg)
+    assert auto_dispatch(ggd, model_g) == "sfu"
+    assert torch_cuda.equal(make_gaussian_image_device(ggd, model_g), make_gaussian_image_device(ggd, model_g, method="sfu"))
     monkeypatch.setenv("TG_TENSOR_BINNED", "0")
     assert auto_dispatch(gd, model) == "sfu"
     assert torch_cuda.equal(make_gaussian_image_device(gd, model), sfu)
