@@ -564,7 +564,12 @@ __global__ void __launch_bounds__(kTraceThreads, KRIV ? (NC == 5 ? 4 : 2) : (NC 
   constexpr int JW = ROWS * (NC > 0 ? NC : 1);  // doubles per ray in the Jacobian
   extern __shared__ __align__(16) double s_jac[];
 
-  const long long block_first = (long long)blockIdx.x * kTraceThreads;
+  // The launcher may bound the grid (TG_TRACE_PERSIST): a CTA then walks several blocks of 128 rays; its staging
+  // buffer is free again once thread 0 has seen the bulk store read it (wait below) and the CTA has met at the barrier.
+  const long long nblk = (n + kTraceThreads - 1) / kTraceThreads;
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+  if (NC > 0 && blk != (long long)blockIdx.x) __syncthreads();
+  const long long block_first = blk * kTraceThreads;
   const long long i = block_first + threadIdx.x;
   const bool active = i < n;
 
@@ -756,6 +761,21 @@ __global__ void __launch_bounds__(kTraceThreads, KRIV ? (NC == 5 ? 4 : 2) : (NC 
       for (int k = threadIdx.x; k < total; k += kTraceThreads) gdst[k] = s_jac[k];
     }
   }
+  }   // blocks of this CTA
+}
+
+// TG_TRACE_PERSIST=<CTAs per SM> (experiment knob, default 0 = one CTA per block of 128 rays): bounded grid whose CTAs
+// walk the blocks with a stride.  MEASURED on B200 (RayTracePlan replays, L2 flushed): slower at every setting -- C1 at
+// 1e6 rays 0.0594 ms with one CTA per block against 0.0614-0.080 ms with 4 / 6 / 8 / 12 CTAs per SM, 1e7 rays 0.494
+// against 0.508-0.684 ms, C4 0.602 against 0.61-0.72 ms: the hardware's block scheduler refills an SM the moment a
+// CTA's bulk store has been read, a persistent CTA serialises its own load -> compute -> store chain.
+inline int trace_persist() {
+  static const int v = [] {
+    const char *e = getenv("TG_TRACE_PERSIST");
+    const int x = e ? atoi(e) : 0;
+    return (x >= 0 && x <= 32) ? x : 0;
+  }();
+  return v;
 }
 
 template <int NC, bool KRIV, bool PERRAY>
@@ -769,8 +789,15 @@ int launch_trace_k(const tg_model *m, int64_t n, const tg_ray_in *in, double *co
     TG_CUDA(cudaFuncSetAttribute(trace_kernel<NC, KRIV, PERRAY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
   }
-  const long long blocks = (n + kTraceThreads - 1) / kTraceThreads;
+  long long blocks = (n + kTraceThreads - 1) / kTraceThreads;
   TG_REQUIRE(blocks <= 0x7fffffffLL, "too many rays for one launch");
+  if (trace_persist() > 0) {
+    int dev = 0, sms = 148;
+    TG_CUDA(cudaGetDevice(&dev));
+    TG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long cap = (long long)sms * trace_persist();
+    if (blocks > cap) blocks = cap;
+  }
   if constexpr (KRIV) {
     trace_kernel<NC, true, PERRAY><<<(unsigned)blocks, kTraceThreads, smem, st>>>(*m, *in, (long long)n, o, jac, pr);
   } else {
