@@ -32,6 +32,6 @@ def test_sanitizer_subset(tool, clean):
                        cwd=ROOT, capture_output=True, text=True, timeout=1200)
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-4000:]
-    for sec in ("gemm", "field", "stem4d", "trace", "peer"):
+    for sec in ("gemm", "field", "binned", "stem4d", "trace", "jets", "peer"):
         assert f"section {sec}: ok" in out, out[-4000:]
     assert clean in out, out[-4000:]
