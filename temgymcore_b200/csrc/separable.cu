@@ -211,6 +211,9 @@ struct SkSched {
   // of one concatenated k axis, P and the chunks per CTA live in device memory (bins[]: built on the device from the
   // beamlets' bounding boxes, never read by the host); CTA c takes chunks [c q, (c + 1) q)
   const int *bins;
+  // TILED operands of a static schedule (the 3-product path of tg_separable_run): k-block kb of A / B is stored as
+  // tiled_a / tiled_b rows x 64 k-elements of contiguous memory (0 = row-major operands, rows a pitch apart)
+  int tiled_a, tiled_b;
 };
 enum { BIN_CTOT = 0, BIN_Q = 1, BIN_OVERFLOW = 2, BIN_NEED = 3, BIN_HDR = 4 };   // bins[]: header, then P[0..T]
 struct SkUnit {
@@ -458,7 +461,10 @@ __global__ void __launch_bounds__(GAUSS ? GEMM_THREADS_GAUSS : GEMM_THREADS, 1)
           // (ragged schedule: operands are stored k-block by k-block, each 128-row x 128-byte tile contiguous -- a
           // tensor of 128-byte rows, tile kb at rows [128 kb, 128 kb + 128) -- so a load is ONE 16 KiB run of DRAM
           // instead of 128 lines a whole operand row apart)
-          const int ck = RAGGED ? 0 : kb * BK, cra = RAGGED ? kb * BM : m0, crb = RAGGED ? kb * BN : n0;
+          const bool tl = !RAGGED && sched.tiled_a > 0;          // tiled operands of a static schedule, same idea
+          const int ck = (RAGGED || tl) ? 0 : kb * BK;
+          const int cra = RAGGED ? kb * BM : tl ? kb * sched.tiled_a + m0 : m0;
+          const int crb = RAGGED ? kb * BN : tl ? kb * sched.tiled_b + n0 : n0;
           tma_load_2d(st + 0 * TILE_BYTES, &tmA_hi, &ctl->full[s], ck, cra);
           tma_load_2d(st + 1 * TILE_BYTES, &tmA_lo, &ctl->full[s], ck, cra);
           tma_load_2d(st + 2 * TILE_BYTES, &tmB_hi, &ctl->full[s], ck, crb);
@@ -1125,7 +1131,7 @@ __global__ void __launch_bounds__(128)
     factor_gauss_kernel(const double *__restrict__ table, long long b0, int nbatch, int npad, int s_first, int S,
                         int W, long long ldk, __half *__restrict__ hi, __half *__restrict__ lo,
                         const unsigned long long *__restrict__ peak_key,
-                        const unsigned long long *__restrict__ sep_guard) {
+                        const unsigned long long *__restrict__ sep_guard, int rows_pad) {
   if (sep_guard && !tg_key_is_separable(*sep_guard)) return;
   const int nbx = (npad / 2 + (int)blockDim.x - 1) / (int)blockDim.x, nby = (S + FS - 1) / FS;
   for (int vb = blockIdx.x; vb < nbx * nby; vb += gridDim.x) {      // bounded grid, see factor_rows_kernel
@@ -1166,14 +1172,17 @@ __global__ void __launch_bounds__(128)
           v[2][e] = re + im;
         }
       }
-      const long long o = (long long)(s0 + j) * ldk + kk;
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
         float h0, l0, h1, l1;
         Operand<true>::split(v[b][0], h0, l0);
         Operand<true>::split(v[b][1], h1, l1);
-        *reinterpret_cast<__half2 *>(hi + o + b * KCH) = __floats2half2_rn(h0, h1);
-        *reinterpret_cast<__half2 *>(lo + o + b * KCH) = __floats2half2_rn(l0, l1);
+        // rows_pad > 0: tiled operands -- k-block k / 64 holds rows_pad rows x 64 k-elements contiguously, so that the
+        // rows of a strip are 128 bytes apart instead of a whole operand row (DRAM pages, see factor_binned_kernel)
+        const long long k = kk + b * KCH;
+        const long long o = rows_pad > 0 ? ((k >> 6) * rows_pad + (s0 + j)) * 64 + (k & 63) : (long long)(s0 + j) * ldk + k;
+        *reinterpret_cast<__half2 *>(hi + o) = __floats2half2_rn(h0, h1);
+        *reinterpret_cast<__half2 *>(lo + o) = __floats2half2_rn(l0, l1);
       }
     }
   }
@@ -1648,6 +1657,7 @@ SkSched make_sched(int M, int Np, int K, int BK, int chunk_kb, int sms, int mode
   s.S = 1;
   s.prefetch = 0;
   s.bins = nullptr;
+  s.tiled_a = s.tiled_b = 0;
   s.uniform = 0;
   s.rounds = 1;
   s.Tr = s.T;
@@ -1833,13 +1843,23 @@ template <bool F16, bool GAUSS = false>
 int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *Blo, int M, int Np, int K,
                 long long ldk, double *out, long long ldo, int accumulate, const unsigned long long *peak_key,
                 const unsigned long long *sep_guard, cudaStream_t st, const TgPeers &peers,
-                const SkWs *skws = nullptr, const SkStream *strm = nullptr) {
+                const SkWs *skws = nullptr, const SkStream *strm = nullptr, int tiled_a = 0, int tiled_b = 0) {
   CUtensorMap ta, tb, tc, td;
   int rc;
-  if ((rc = make_map<F16>(&ta, Ahi, M, K, ldk)) != TG_OK) return rc;
-  if ((rc = make_map<F16>(&tb, Alo, M, K, ldk)) != TG_OK) return rc;
-  if ((rc = make_map<F16>(&tc, Bhi, Np, K, ldk)) != TG_OK) return rc;
-  if ((rc = make_map<F16>(&td, Blo, Np, K, ldk)) != TG_OK) return rc;
+  if (tiled_a > 0) {
+    // tiled operands (K a whole number of k-blocks): tensors of 128-byte rows, k-block kb at rows [kb rows_pad, ...)
+    constexpr int BKe = GemmCfg<F16>::BK;
+    const long long nkb = (K + BKe - 1) / BKe;
+    if ((rc = make_map<F16>(&ta, Ahi, nkb * tiled_a, BKe, BKe)) != TG_OK) return rc;
+    if ((rc = make_map<F16>(&tb, Alo, nkb * tiled_a, BKe, BKe)) != TG_OK) return rc;
+    if ((rc = make_map<F16>(&tc, Bhi, nkb * tiled_b, BKe, BKe)) != TG_OK) return rc;
+    if ((rc = make_map<F16>(&td, Blo, nkb * tiled_b, BKe, BKe)) != TG_OK) return rc;
+  } else {
+    if ((rc = make_map<F16>(&ta, Ahi, M, K, ldk)) != TG_OK) return rc;
+    if ((rc = make_map<F16>(&tb, Alo, M, K, ldk)) != TG_OK) return rc;
+    if ((rc = make_map<F16>(&tc, Bhi, Np, K, ldk)) != TG_OK) return rc;
+    if ((rc = make_map<F16>(&td, Blo, Np, K, ldk)) != TG_OK) return rc;
+  }
   int sms = 148;
   if ((rc = device_sms(&sms)) != TG_OK) return rc;
   if constexpr (!GAUSS) {
@@ -1875,7 +1895,9 @@ int launch_gemm(const void *Ahi, const void *Alo, const void *Bhi, const void *B
   const size_t smem = (size_t)STAGES * STAGE_BYTES + sizeof(GemmSmemCtl) + 1024;
   TG_CUDA(cudaFuncSetAttribute(gemm_x3_kernel<F16, GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int rtm = strm ? strm->round_tiles_m : 0;
-  const SkSched sched = make_sched(M, Np, K, GemmCfg<F16>::BK, GemmCfg<F16>::CHUNK_KB, sms, -1, rtm);
+  SkSched sched = make_sched(M, Np, K, GemmCfg<F16>::BK, GemmCfg<F16>::CHUNK_KB, sms, -1, rtm);
+  sched.tiled_a = tiled_a;
+  sched.tiled_b = tiled_b;
   size_t cnt_bytes = 0, part_bytes = 0;
   sk_scratch_need<F16, GAUSS>(M, Np, K, sms, &cnt_bytes, &part_bytes, rtm);
   unsigned char *sk = nullptr, *parts = nullptr;
@@ -1956,6 +1978,17 @@ __global__ void __launch_bounds__(256)
     out[i] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
+// TG_GEMM_TILED=1 (experiment knob, default off): tiled operands on the dense 3-product path as well.  MEASURED on
+// B200 (C2 graph replay, L2 flushed, two A/B pairs): 0.2717 ms tiled against 0.2696 ms row-major, same image -- unlike
+// the tile-binned sum, whose operands are streamed once from HBM, the dense GEMM finds its operand tiles in L2 and the
+// dense factor kernels were not limited by DRAM pages.  Validated (43 tensor-path tests) and left off.  Read once.
+bool tiled_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("TG_GEMM_TILED");
+    return e && atoi(e) != 0;
+  }();
+  return on;
+}
 // Batches of kBatch beamlets (outer loop: the column factors of a batch are built once) x row blocks (inner
 // loop: row factors + GEMM of one block; blocks exist for the host-buffer pipeline, whose D2H of a finished
 // block overlaps the GEMMs of the following ones).  acc: fp64 (nrows x 2W) accumulator = the output itself
@@ -1972,6 +2005,10 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
   // rows are in memory (the caller polls the flags and queues the D2H copies; no events between the launches)
   const int ldo = 2 * W;                     // doubles per output row (re, im interleaved)
   const int Np = GAUSS ? W : 2 * W;          // B rows: complex columns (3-product) or real columns
+  // 3-product path, one launch per row block: optionally TILED operands (k-block by k-block, see SkSched::tiled_a and
+  // tiled_enabled: measured without gain here)
+  const bool tiled = GAUSS && !blk_sig && !strm && tiled_enabled();
+  const int b_pad = tiled ? ((Np + BN - 1) / BN) * BN : 0;
   int rc = TG_OK;
   TgPeers none;
   none.n = 0;
@@ -1984,7 +2021,7 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
     if constexpr (GAUSS) {
       const unsigned gb = bounded_grid((long long)((npad / 2 + 127) / 128) * ((W + FS - 1) / FS));
       factor_gauss_kernel<false><<<gb, 128, 0, st>>>(table, b0, nbatch, npad, 0, W, W, ldk, static_cast<__half *>(Bhi),
-                                                     static_cast<__half *>(Blo), peak, guard);
+                                                     static_cast<__half *>(Blo), peak, guard, b_pad);
     } else {
       const unsigned gb = bounded_grid((long long)((nbatch + 127) / 128) * ((W + FS - 1) / FS));
       factor_cols_kernel<F16><<<gb, 128, 0, st>>>(table, b0, nbatch, W, ldk, Bhi, Blo, guard);
@@ -1996,7 +2033,7 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
         const unsigned ga = bounded_grid((long long)((npad / 2 + 127) / 128) * ((nrows + FS - 1) / FS));
         factor_gauss_kernel<true><<<ga, 128, 0, st>>>(table, b0, nbatch, npad, row0, nrows, W, ldk,
                                                       static_cast<__half *>(Ahi), static_cast<__half *>(Alo), peak,
-                                                      guard);
+                                                      guard, 0);
       } else {
         const unsigned ga = bounded_grid((long long)((nbatch + 127) / 128) * ((nrows + FS - 1) / FS));
         factor_rows_kernel<F16><<<ga, 128, 0, st>>>(table, b0, nbatch, row0, nrows, W, ldk, Ahi, Alo, peak, guard);
@@ -2027,7 +2064,7 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
         const unsigned ga = bounded_grid((long long)((npad / 2 + 127) / 128) * ((nr + FS - 1) / FS));
         factor_gauss_kernel<true><<<ga, 128, 0, st>>>(table, b0, nbatch, npad, row0 + r, nr, W, ldk,
                                                       static_cast<__half *>(Ahi), static_cast<__half *>(Alo), peak,
-                                                      guard);
+                                                      guard, tiled ? ((nr + BM - 1) / BM) * BM : 0);
       } else {
         const unsigned ga = bounded_grid((long long)((nbatch + 127) / 128) * ((nr + FS - 1) / FS));
         factor_rows_kernel<F16><<<ga, 128, 0, st>>>(table, b0, nbatch, row0 + r, nr, W, ldk, Ahi, Alo, peak, guard);
@@ -2041,7 +2078,7 @@ int run_batches(int64_t nb, const double *table, int row0, int nrows, int W, lon
       }
       double *acc_r = acc + (size_t)r * ldo;
       rc = launch_gemm<F16, GAUSS>(Ahi, Alo, Bhi, Blo, nr, Np, K, ldk, acc_r, (long long)ldo, b0 > 0 ? 1 : 0, peak,
-                                   guard, st, pe, skws, strm);
+                                   guard, st, pe, skws, strm, tiled ? ((nr + BM - 1) / BM) * BM : 0, b_pad);
       if (rc == TG_OK && last && !out_is_c128) {
         const size_t n = (size_t)nr * ldo;
         TgPeers pc = none;   // complex64 peers are written by the conversion
@@ -2327,8 +2364,10 @@ int tg_separable_run(int64_t nb, const double *poly, const double px2m[6], int H
   const size_t elem = f16 ? 2 : 4;
   const int Np = gauss ? W : 2 * W;          // B rows
   const size_t table_bytes = (((size_t)nb * 96 + 255) / 256) * 256;
-  const size_t a_bytes = verdict_only ? 0 : (((size_t)(flagged ? nrows : block_rows) * ldk * elem + 255) / 256) * 256;
-  const size_t b_bytes = verdict_only ? 0 : (((size_t)Np * ldk * elem + 255) / 256) * 256;
+  // (rows padded to whole 128-row tiles: the tiled layout of the 3-product path addresses k-blocks of whole tiles)
+  auto pad128 = [](size_t r) { return (r + 127) / 128 * 128; };
+  const size_t a_bytes = verdict_only ? 0 : ((pad128((size_t)(flagged ? nrows : block_rows)) * ldk * elem + 255) / 256) * 256;
+  const size_t b_bytes = verdict_only ? 0 : ((pad128((size_t)Np) * ldk * elem + 255) / 256) * 256;
   const size_t acc_bytes = (out_is_c128 || verdict_only) ? 0 : npix * 16;
   size_t sk_cnt = 0, sk_part = 0;
   if (!verdict_only) {
